@@ -1,0 +1,125 @@
+/*
+ * myyuvb200.h -- C ABI of the B200-native (sm_100a) implementation of myyuv_lib's hot path:
+ * BMP XRGB8888 -> IYUV conversion, DCT-q compression, decompression, compressed-payload layout.
+ *
+ * This is the drop-in boundary.  The reference (mahbhlddnhakkh/yuv-manipulations-2) has no FFI of its
+ * own: its plugin boundary is three public static registries of std::function in class myyuv::YUV
+ * (myyuv_lib/myyuv_yuv.hpp:106,111,116; entries defined at myyuv_lib/myyuv_yuv.cpp:88,130,146).  Each
+ * entry point below is what one of those registry entries binds to; INTEGRATION.md shows the binding.
+ * Plain pointers and sizes only; every function returns MYYUVB_OK (0) or an error code, and
+ * myyuvb_last_error() returns the message the reference would have thrown for that condition.
+ *
+ * Payload layout (identical to the reference, DCT.cpp:16-73,112-173), little-endian, packed:
+ *   payload := u32 planes_sizes[3]  plane[Y] plane[U] plane[V]
+ *   plane   := u32 n_chunks  u32 content_size  u8 chunk_size[n_chunks]  u8 content[content_size]
+ *   chunk   := u16 code_bits  u8 table_bytes  group*  code_stream[(code_bits+7)/8]      (Huffman.cpp:279-326)
+ * It is what YUV::data holds when header.compression == DCT (header.data_size bytes).
+ */
+#ifndef MYYUVB200_H
+#define MYYUVB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define MYYUVB_API
+#else
+#define MYYUVB_API __attribute__((visibility("default")))
+#endif
+
+enum {
+  MYYUVB_OK = 0,
+  MYYUVB_ERR_CUDA = 1,          /* a CUDA runtime call failed (message carries cudaGetErrorString)          */
+  MYYUVB_ERR_ARG = 2,           /* null pointer / zero size                                                 */
+  MYYUVB_ERR_QUALITY = 3,       /* "Level of quality must be between 1 and 100"       DCT.cpp:378-382,438-442 */
+  MYYUVB_ERR_WIDTH = 4,         /* "Error. width % 8 must be 0"                       DCT.cpp:280-282,338-340 */
+  MYYUVB_ERR_HEIGHT = 5,        /* "Error. height % 8 must be 0"                      DCT.cpp:283-285,341-343 */
+  MYYUVB_ERR_CAPACITY = 6,      /* output buffer smaller than the produced payload                          */
+  MYYUVB_ERR_DCTYUV_SIZE = 7,   /* "DCTYUV load bad size"                             DCT.cpp:132-134,143-145 */
+  MYYUVB_ERR_PLANE_SIZE = 8,    /* "DCTYUVPlane load bad size" (+ chunks_sizes_size / content_size variants) DCT.cpp:41-55 */
+  MYYUVB_ERR_HUFFMAN = 9,       /* "Huffman bad code"                                 Huffman.cpp:121,130,139 */
+  MYYUVB_ERR_EVEN = 10,         /* colour conversion needs even width and height      myyuv_yuv.cpp:98       */
+  MYYUVB_ERR_TOO_LARGE = 11     /* sizes do not fit the format's uint32 fields        myyuv_yuv.hpp:20-26    */
+};
+
+typedef struct myyuvb_ctx myyuvb_ctx; /* one device, one stream, reusable device/pinned scratch; not thread-safe
+                                         per context (use one context per thread), contexts are independent. */
+
+/* device: CUDA ordinal.  stream: a cudaStream_t to run on (e.g. the caller's torch stream), or NULL to
+ * let the context create its own non-blocking stream. */
+MYYUVB_API int myyuvb_ctx_create(int device, void* stream, myyuvb_ctx** out);
+MYYUVB_API void myyuvb_ctx_destroy(myyuvb_ctx* ctx);
+MYYUVB_API const char* myyuvb_last_error(void); /* thread-local, valid until the next call on this thread */
+MYYUVB_API int myyuvb_sync(myyuvb_ctx* ctx);    /* wait for the context's stream */
+MYYUVB_API void* myyuvb_stream(myyuvb_ctx* ctx);
+
+/* Upper bound of a compressed payload for one w x h IYUV frame (a chunk is at most 255 bytes because
+ * its size is stored in a uint8, DCT.cpp:19,310). */
+MYYUVB_API uint64_t myyuvb_compress_bound(uint32_t width, uint32_t height);
+
+/* ---- host-pointer entry points: what the class API / registries bind (H2D + kernels + D2H inside) ---- */
+
+/* replaces bmp_to_yuv_map[IYUV] (myyuv_yuv.cpp:88-128) with BMP::colorData()'s row flip
+ * (myyuv_bmp.cpp:80-103) folded in.  bgrx: width*height*4 bytes, rows as stored in the BMP file;
+ * bottom_up != 0 when BMP height > 0.  iyuv_out: width*height*3/2 bytes. */
+MYYUVB_API int myyuvb_xrgb_to_iyuv(myyuvb_ctx* ctx, const uint8_t* bgrx, uint32_t width, uint32_t height,
+                                   int bottom_up, uint8_t* iyuv_out);
+
+/* replaces compress_map[DCT][IYUV] -> myyuvDCT::compress_DCT_planar (myyuv_yuv.cpp:130-143, DCT.cpp:371-430).
+ * quality[3]: Y,U,V quality 1..100.  out receives the payload (YUV::data of the compressed image). */
+MYYUVB_API int myyuvb_dct_compress(myyuvb_ctx* ctx, const uint8_t* iyuv, uint32_t width, uint32_t height,
+                                   const uint8_t quality[3], uint8_t* out, uint64_t out_capacity,
+                                   uint32_t* out_size);
+
+/* replaces decompress_map[DCT][IYUV] -> myyuvDCT::decompress_DCT_planar (myyuv_yuv.cpp:146-159, DCT.cpp:432-488). */
+MYYUVB_API int myyuvb_dct_decompress(myyuvb_ctx* ctx, const uint8_t* payload, uint32_t payload_size, uint32_t width,
+                                     uint32_t height, const uint8_t quality[3], uint8_t* iyuv_out);
+
+/* ---- device-pointer batch entry points (asynchronous on the context stream) ----
+ * All frames of a batch share width/height/quality.  Frames are independent units. */
+
+/* d_bgrx: n_frames * w*h*4, d_iyuv: n_frames * w*h*3/2. */
+MYYUVB_API int myyuvb_xrgb_to_iyuv_batch_dev(myyuvb_ctx* ctx, const uint8_t* d_bgrx, uint32_t width, uint32_t height,
+                                             int bottom_up, uint32_t n_frames, uint8_t* d_iyuv);
+
+/* Payloads are written back to back into d_out; d_offsets[f] .. d_offsets[f+1] (n_frames+1 entries,
+ * device memory) delimit frame f.  Nothing is written past out_capacity: an overflow is reported by
+ * myyuvb_batch_status as MYYUVB_ERR_CAPACITY.  n_frames * myyuvb_compress_bound() always suffices. */
+MYYUVB_API int myyuvb_dct_compress_batch_dev(myyuvb_ctx* ctx, const uint8_t* d_iyuv, uint32_t width, uint32_t height,
+                                             const uint8_t quality[3], uint32_t n_frames, uint8_t* d_out,
+                                             uint64_t out_capacity, uint64_t* d_offsets);
+
+/* d_payloads + d_offsets as produced above (any packing is fine as long as frame f occupies
+ * [d_offsets[f], d_offsets[f+1])).  d_iyuv: n_frames * w*h*3/2. */
+MYYUVB_API int myyuvb_dct_decompress_batch_dev(myyuvb_ctx* ctx, const uint8_t* d_payloads, const uint64_t* d_offsets,
+                                               uint32_t width, uint32_t height, const uint8_t quality[3],
+                                               uint32_t n_frames, uint8_t* d_iyuv);
+
+/* Synchronises the stream and returns the first data-dependent error raised by the batch calls issued
+ * since the previous status call (capacity overflow, malformed payload), MYYUVB_OK otherwise. */
+MYYUVB_API int myyuvb_batch_status(myyuvb_ctx* ctx);
+
+/* ---- host-pointer batch entry points: pinned staging, H2D / kernels / D2H pipelined over chunks of
+ * frames on two streams.  This is the end-to-end path bench.py times ("e2e"). ---- */
+MYYUVB_API int myyuvb_dct_compress_batch_host(myyuvb_ctx* ctx, const uint8_t* iyuv, uint32_t width, uint32_t height,
+                                              const uint8_t quality[3], uint32_t n_frames, uint8_t* out,
+                                              uint64_t out_capacity, uint64_t* offsets /* n_frames+1 */);
+MYYUVB_API int myyuvb_dct_decompress_batch_host(myyuvb_ctx* ctx, const uint8_t* payloads, const uint64_t* offsets,
+                                                uint32_t width, uint32_t height, const uint8_t quality[3],
+                                                uint32_t n_frames, uint8_t* iyuv_out);
+
+/* pinned host memory helpers (so callers in any language can hand the batch_host calls DMA-able buffers) */
+MYYUVB_API int myyuvb_host_alloc(size_t bytes, void** out);
+MYYUVB_API void myyuvb_host_free(void* p);
+
+/* number of kernels this library has launched on this thread's contexts since process start (bench.py's gpu_launches) */
+MYYUVB_API uint64_t myyuvb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MYYUVB200_H */

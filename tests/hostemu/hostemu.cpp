@@ -1,0 +1,146 @@
+// tests/hostemu/hostemu.cpp -- TEST INFRASTRUCTURE ONLY.
+// Compiles the product's per-block entropy coder (yuv-manipulations-2_b200/csrc/block_codec.cuh, the exact
+// source the CUDA kernels inline) for the host with g++, so its logic -- libstdc++ tie-break emulation,
+// canonical codes, serialisation, decoder -- can be checked against the oracle without a GPU.
+// It also checks the two arithmetic identities the kernels rely on (exact division by one Newton step,
+// round-half-away via a round-toward-zero add).  Nothing in the product links this file.
+#include <cfenv>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <random>
+
+#include "../../yuv-manipulations-2_b200/csrc/block_codec.cuh"
+
+using namespace myyuvb;
+
+namespace {
+const uint8_t kZigzag[64] = {MYB_ZIGZAG_LIST};
+
+struct ZArray {
+  int16_t* z;
+  int get(int i) const { return z[i]; }
+  void set(int i, int v) { z[i] = (int16_t)v; }
+};
+}  // namespace
+
+extern "C" {
+
+// coef: n x 64 row-major.  stride: element stride of the scratch arrays (1, or e.g. 128 to mimic the
+// shared-memory interleave).  fast_cap16 != 0: try the 16-symbol scratch first like the kernel does.
+int hostemu_encode_blocks(const int16_t* coef, uint32_t n, int stride, int fast_cap16, uint8_t* out, uint8_t* sizes) {
+  using Fast = HuffScratch<16>;
+  using Big = HuffScratch<64>;
+  uint8_t* fb = new uint8_t[(size_t)Fast::kBytes * stride]();
+  int16_t* fh = new int16_t[(size_t)Fast::kSyms * stride]();
+  uint8_t* bb = new uint8_t[(size_t)Big::kBytes * stride]();
+  int16_t* bh = new int16_t[(size_t)Big::kSyms * stride]();
+  int big_used = 0;
+  for (uint32_t b = 0; b < n; b++) {
+    int16_t z[64];
+    for (int i = 0; i < 64; i++) z[i] = coef[64 * (size_t)b + kZigzag[i]];
+    int L = 64;
+    while (L > 0 && z[L - 1] == 0) L--;
+    ZArray za{z};
+    Fast fs{fb, fh, stride};
+    Big bs{bb, bh, stride};
+    HuffPlan pl;
+    pl.n = -1;
+    if (fast_cap16) pl = huff_plan<16>(za, L, fs);
+    bool big = false;
+    if (pl.n < 0) {
+      big = true;
+      big_used++;
+      pl = huff_plan<64>(za, L, bs);
+    }
+    uint8_t tmp[256];
+    if (big) huff_emit<64>(za, pl, bs, tmp);
+    else huff_emit<16>(za, pl, fs, tmp);
+    const int sz = pl.size();
+    memcpy(out, tmp, (size_t)sz);
+    out += sz;
+    sizes[b] = (uint8_t)sz;
+  }
+  delete[] fb; delete[] fh; delete[] bb; delete[] bh;
+  return big_used;
+}
+
+int hostemu_decode_blocks(const uint8_t* chunks, const uint8_t* sizes, uint32_t n, int16_t* coef) {
+  for (uint32_t b = 0; b < n; b++) {
+    int16_t* c = coef + 64 * (size_t)b;
+    memset(c, 0, 128);
+    const int err = huff_decode_block(chunks, sizes[b], [&](int j, int v) { c[kZigzag[j]] = (int16_t)v; });
+    if (err) return (int)b + 1;
+    chunks += sizes[b];
+  }
+  return 0;
+}
+
+// kernels.cu fdct_quant_pair: q1 = fma(fma(-q, y*r, y), r, y*r) with r = RN(1/q) must equal RN(y/q)
+// for every integer divisor 1..255.  Returns the number of mismatches over `samples` random y per divisor
+// plus structured y around rounding ties (k + 0.5) * q.
+uint64_t hostemu_division_check(uint32_t samples, uint32_t seed) {
+  std::mt19937 rng(seed);
+  uint64_t bad = 0;
+  for (int q = 1; q <= 255; q++) {
+    const float d = (float)q, r = 1.0f / d;
+    auto test = [&](float y) {
+      const volatile float q0 = y * r;
+      const float rem = fmaf(-d, q0, y);
+      const float q1 = fmaf(rem, r, q0);
+      const volatile float ref = y / d;
+      if (!(q1 == ref)) bad++;
+    };
+    for (uint32_t s = 0; s < samples; s++) {
+      uint32_t bits = rng();
+      // |y| < 8192 covers every DCT output (|Y| <= 1024 * 8); random mantissa/exponent/sign
+      const int e = 87 + (int)((bits >> 23) % 53);  // 2^-40 .. 2^12
+      bits = (bits & 0x807fffffu) | ((uint32_t)e << 23);
+      float y;
+      memcpy(&y, &bits, 4);
+      test(y);
+    }
+    for (int k = -1100; k <= 1100; k++) {
+      const float t = ((float)k + 0.5f) * d;
+      test(t);
+      test(nextafterf(t, 1e9f));
+      test(nextafterf(t, -1e9f));
+    }
+  }
+  return bad;
+}
+
+// round half away from zero == trunc(RZ(v + copysign(0.5, v)))
+uint64_t hostemu_round_check(uint32_t samples, uint32_t seed) {
+  std::mt19937 rng(seed);
+  uint64_t bad = 0;
+  auto test = [&](float v) {
+    const float ref = roundf(v);
+    fesetround(FE_TOWARDZERO);
+    const volatile float t = v + copysignf(0.5f, v);
+    fesetround(FE_TONEAREST);
+    if ((int)truncf(t) != (int)ref) bad++;
+  };
+  for (uint32_t s = 0; s < samples; s++) {
+    uint32_t bits = rng();
+    const int e = 100 + (int)((bits >> 23) % 40);
+    bits = (bits & 0x807fffffu) | ((uint32_t)e << 23);
+    float v;
+    memcpy(&v, &bits, 4);
+    test(v);
+  }
+  for (int k = -2000; k <= 2000; k++) {
+    const float t = (float)k + 0.5f;
+    test(t);
+    test(nextafterf(t, 1e9f));
+    test(nextafterf(t, -1e9f));
+    test((float)k);
+  }
+  test(0.49999997f);
+  test(-0.49999997f);
+  test(0.0f);
+  test(-0.0f);
+  return bad;
+}
+
+}  // extern "C"

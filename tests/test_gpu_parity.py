@@ -1,0 +1,269 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle, the reference's golden files and the
+reference itself.  Integer/byte work: bit-exact everywhere (no tolerance)."""
+import hashlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+SMALL = [(16, 16), (32, 16), (16, 32), (48, 80), (256, 128), (992, 736), (1296, 720)]
+QS = [(50, 50, 50), (90, 90, 90), (10, 10, 10), (1, 1, 1), (100, 100, 100), (50, 51, 75), (97, 3, 64)]
+
+
+def frames(synth, w, h, n=1, first=0):
+    return synth.iyuv_frames_numpy(w, h, n, first)
+
+
+@pytest.mark.parametrize("w,h", SMALL)
+def test_colour_conversion_matches_oracle(ctx, ora, synth, w, h):
+    bgrx = synth.bgrx_frames_numpy(w, h, 1, first=3)[0]
+    for bottom_up in (True, False):
+        got = ctx.xrgb_to_iyuv(bgrx, w, h, bottom_up)
+        assert np.array_equal(got, ora.bgrx_to_iyuv(bgrx, w, h, bottom_up))
+
+
+def test_colour_conversion_extremes(ctx, ora):
+    # every (B,G,R) on a coarse lattice plus the pure-blue quad whose Cb sum wraps to 0
+    vals = np.array([0, 1, 2, 15, 16, 17, 63, 64, 127, 128, 129, 191, 200, 253, 254, 255], np.uint8)
+    b, g, r = np.meshgrid(vals, vals, vals, indexing="ij")
+    px = np.stack([b.ravel(), g.ravel(), r.ravel(), np.zeros(b.size, np.uint8)], 1)  # 4096 pixels
+    w, h = 64, 64
+    img = px.reshape(h, w, 4)
+    img = np.repeat(np.repeat(img, 2, 0), 2, 1)  # uniform 2x2 quads, 128 x 128
+    got = ctx.xrgb_to_iyuv(img, 128, 128, True)
+    assert np.array_equal(got, ora.bgrx_to_iyuv(img, 128, 128, True))
+    blue = np.zeros((16, 16, 4), np.uint8)
+    blue[..., 0] = 255
+    out = ctx.xrgb_to_iyuv(blue, 16, 16, True)
+    assert out[0] == 29 and out[256] == 0 and out[256 + 64] == 108
+
+
+@pytest.mark.parametrize("w,h", SMALL)
+@pytest.mark.parametrize("q", QS[:4])
+def test_compress_matches_oracle(ctx, ora, synth, w, h, q):
+    f = frames(synth, w, h)[0]
+    got = ctx.compress(f, w, h, q)
+    want = ora.compress(f, w, h, q)
+    assert got.size == want.size
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("q", QS)
+def test_compress_decompress_edge_cases(ctx, ora, synth, q):
+    w, h = 128, 128
+    f = synth.edge_case_iyuv(w, h)
+    got = ctx.compress(f, w, h, q)
+    want = ora.compress(f, w, h, q)
+    assert np.array_equal(got, want)
+    assert np.array_equal(ctx.decompress(want, w, h, q), ora.decompress(want, w, h, q))
+
+
+def test_random_noise_many_symbols(ctx, ora):
+    # uniform noise at q=100: ~60 distinct symbols per block -> local-memory scratch path, all rehash steps
+    rng = np.random.default_rng(5)
+    w, h = 256, 256
+    f = rng.integers(0, 256, w * h * 3 // 2, dtype=np.uint8)
+    for q in ((100, 100, 100), (95, 90, 85)):
+        got = ctx.compress(f, w, h, q)
+        want = ora.compress(f, w, h, q)
+        assert np.array_equal(got, want)
+        assert np.array_equal(ctx.decompress(got, w, h, q), ora.decompress(want, w, h, q))
+
+
+def test_flat_frames_all_zero_blocks(ctx, ora):
+    w, h = 64, 48 * 2  # 6144 px
+    for level in (0, 128, 255):
+        f = np.full(w * h * 3 // 2, level, np.uint8)
+        got = ctx.compress(f, w, h, (50, 50, 50))
+        assert np.array_equal(got, ora.compress(f, w, h, (50, 50, 50)))
+        assert np.array_equal(ctx.decompress(got, w, h, (50, 50, 50)), ora.decompress(got, w, h, (50, 50, 50)))
+
+
+@pytest.mark.parametrize("w,h", SMALL)
+@pytest.mark.parametrize("q", QS[:3])
+def test_decompress_matches_oracle(ctx, ora, synth, w, h, q):
+    f = frames(synth, w, h, first=7)[0]
+    payload = ora.compress(f, w, h, q)
+    got = ctx.decompress(payload, w, h, q)
+    assert np.array_equal(got, ora.decompress(payload, w, h, q))
+
+
+def test_golden_files(ctx, golden_dir):
+    """The reference's own golden vectors: bmp -> myyuv -> DCT-50 / DCT-90, decodes."""
+    import oracle as O
+
+    bmp = O.read_bmp32(golden_dir / "chef-with-trumpet.bmp")
+    raw = O.read_myyuv(golden_dir / "chef-with-trumpet.myyuv")
+    assert np.array_equal(ctx.xrgb_to_iyuv(bmp["data"], bmp["w"], bmp["h"], bmp["bottom_up"]), raw["data"])
+    for q, dec_sha in ((50, "a95127da47152"), (90, "749ef0edb7ddd")):
+        g = O.read_myyuv(golden_dir / f"chef-with-trumpet-DCT-{q}.myyuv")
+        assert np.array_equal(ctx.compress(raw["data"], raw["w"], raw["h"], [q] * 3), g["data"])
+        dec = ctx.decompress(g["data"], g["w"], g["h"], g["params"])
+        hdr = O.YUV_HDR.pack(b"YU", 0x56555949, dec.size, 0, 0, 0, g["w"], g["h"], 64, bytes(32))
+        assert hashlib.sha256(hdr + dec.tobytes()).hexdigest().startswith(dec_sha)
+
+
+def test_golden_big_decode_and_recompress(ctx, ora, golden_dir):
+    import oracle as O
+
+    big = O.read_myyuv(golden_dir / "chef-with-trumpet-big-DCT-50.myyuv")
+    dec = ctx.decompress(big["data"], big["w"], big["h"], big["params"])
+    hdr = O.YUV_HDR.pack(b"YU", 0x56555949, dec.size, 0, 0, 0, big["w"], big["h"], 64, bytes(32))
+    assert hashlib.sha256(hdr + dec.tobytes()).hexdigest().startswith("5e77691911882")
+    # BASELINE config 2: 4032x3008 at q=90, and re-encoding at q=50 reproduces an oracle stream
+    for q in (90, 50):
+        got = ctx.compress(dec, big["w"], big["h"], [q] * 3)
+        assert np.array_equal(got, ora.compress(dec, big["w"], big["h"], [q] * 3))
+
+
+def test_cross_decode_with_reference(ctx, ref, synth):
+    w, h, q = 320, 240 - 240 % 16, (60, 40, 80)
+    f = frames(synth, w, h, first=11)[0]
+    ours = ctx.compress(f, w, h, q)
+    theirs = ref.compress(f, w, h, q)
+    assert np.array_equal(ours, theirs)
+    assert np.array_equal(ref.decompress(ours, w, h, q), ctx.decompress(theirs, w, h, q))
+
+
+def test_batch_device_api(ctx, ora, synth, pkg):
+    torch = pytest.importorskip("torch")
+    w, h, n, q = 256, 144 - 144 % 16, 5, (50, 50, 50)
+    host = frames(synth, w, h, n)
+    d_in = torch.from_numpy(host).cuda()
+    cap = pkg.capi.compress_bound(w, h) * n
+    d_out = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    d_off = torch.empty(n + 1, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    ctx.compress_batch_dev(d_in, w, h, q, n, d_out, cap, d_off)
+    ctx.batch_status()
+    off = d_off.cpu().numpy()
+    out = d_out.cpu().numpy()
+    assert off[0] == 0
+    for i in range(n):
+        want = ora.compress(host[i], w, h, q)
+        assert np.array_equal(out[off[i]: off[i + 1]], want), f"frame {i}"
+    d_back = torch.zeros_like(d_in)
+    ctx.decompress_batch_dev(d_out, d_off, w, h, q, n, d_back)
+    ctx.batch_status()
+    back = d_back.cpu().numpy()
+    for i in range(n):
+        assert np.array_equal(back[i], ora.decompress(out[off[i]: off[i + 1]], w, h, q))
+    # colour conversion batch
+    bg = synth.bgrx_frames_numpy(w, h, 3)
+    d_bg = torch.from_numpy(bg).cuda()
+    d_yuv = torch.empty((3, w * h * 3 // 2), dtype=torch.uint8, device="cuda")
+    ctx.xrgb_to_iyuv_batch_dev(d_bg, w, h, True, 3, d_yuv)
+    ctx.batch_status()
+    got = d_yuv.cpu().numpy()
+    for i in range(3):
+        assert np.array_equal(got[i], ora.bgrx_to_iyuv(bg[i], w, h, True))
+
+
+def test_batch_host_api_multi_chunk(ctx, ora, synth, pkg):
+    # 1920x1088 frames are 3.1 MB: 30 frames span two 64 MB pipeline chunks
+    w, h, n, q = 1920, 1088, 30, (50, 50, 50)
+    host = frames(synth, w, h, n)
+    cap = 40 << 20
+    out = np.empty(cap, np.uint8)
+    off = np.zeros(n + 1, np.uint64)
+    ctx.compress_batch_host(host, w, h, q, n, out, off)
+    for i in (0, 1, 20, 21, 29):
+        assert np.array_equal(out[int(off[i]): int(off[i + 1])], ora.compress(host[i], w, h, q)), f"frame {i}"
+    back = np.empty_like(host)
+    ctx.decompress_batch_host(out, off, w, h, q, n, back)
+    for i in (0, 19, 20, 21, 29):
+        assert np.array_equal(back[i], ora.decompress(out[int(off[i]): int(off[i + 1])], w, h, q))
+
+
+def test_round_trip_properties_4k(ctx, synth):
+    """Size-independent properties at the benchmark's frame size: decode(encode(x)) is idempotent under a
+    second encode/decode cycle's stream sizes, planes stay within the quantisation error, chunk sizes sum up."""
+    w, h, q = 3840, 2160, (50, 50, 50)
+    f = frames(synth, w, h)[0]
+    p1 = ctx.compress(f, w, h, q)
+    d1 = ctx.decompress(p1, w, h, q)
+    psz = p1[:12].view(np.uint32)
+    assert 12 + int(psz.sum()) == p1.size
+    pos = 12
+    for p, n in enumerate((w * h // 64, w * h // 256, w * h // 256)):
+        nchunks, content = p1[pos: pos + 8].view(np.uint32)
+        assert nchunks == n and psz[p] == 8 + n + content
+        assert int(p1[pos + 8: pos + 8 + n].sum(dtype=np.int64)) == content
+        pos += int(psz[p])
+    err = np.abs(d1.astype(np.int16) - f.astype(np.int16))
+    assert err.max() < 64 and err.mean() < 6
+    p2 = ctx.compress(d1, w, h, q)
+    d2 = ctx.decompress(p2, w, h, q)
+    assert np.abs(d2.astype(np.int16) - d1.astype(np.int16)).mean() < 1.0
+
+
+def test_error_behaviour(ctx, pkg, ora, synth):
+    M = pkg.MyyuvError
+    f = frames(synth, 32, 32)[0]
+    with pytest.raises(M, match="Level of quality must be between 1 and 100"):
+        ctx.compress(f, 32, 32, (0, 50, 50))
+    with pytest.raises(M, match="Level of quality must be between 1 and 100"):
+        ctx.compress(f, 32, 32, (50, 101, 50))
+    with pytest.raises(M, match="width % 8 must be 0"):
+        ctx.compress(np.zeros(24 * 32 * 3 // 2, np.uint8), 24, 32, (50, 50, 50))  # chroma width 12
+    with pytest.raises(M, match="height % 8 must be 0"):
+        ctx.compress(np.zeros(32 * 24 * 3 // 2, np.uint8), 32, 24, (50, 50, 50))
+    good = ora.compress(f, 32, 32, (50, 50, 50))
+    with pytest.raises(M, match="DCTYUV load bad size"):
+        ctx.decompress(good[:12], 32, 32, (50, 50, 50))
+    with pytest.raises(M, match="DCTYUV load bad size"):
+        ctx.decompress(good[:-1], 32, 32, (50, 50, 50))
+    bad = good.copy()
+    bad[12:16] = 0  # n_chunks = 0
+    with pytest.raises(M, match="DCTYUVPlane load"):
+        ctx.decompress(bad, 32, 32, (50, 50, 50))
+    with pytest.raises(M, match="too small"):
+        ctx.compress(f, 32, 32, (50, 50, 50), capacity=good.size - 1)
+    # context still usable afterwards
+    assert np.array_equal(ctx.compress(f, 32, 32, (50, 50, 50)), good)
+
+
+def test_corrupt_code_stream_is_reported(ctx, ora, synth):
+    w, h, q = 64, 64, (90, 90, 90)
+    f = frames(synth, w, h)[0]
+    good = ora.compress(f, w, h, q)
+    n = w * h // 64
+    first_chunk = 12 + 8 + n
+    bad = good.copy()
+    bad[first_chunk] = 0xFF  # code_bits low byte: far more bits than the chunk holds
+    bad[first_chunk + 1] = 0x01
+    with pytest.raises(Exception, match="Huffman bad code"):
+        ctx.decompress(bad, w, h, q)
+    with pytest.raises(Exception):
+        ora.decompress(bad, w, h, q)
+
+
+def test_class_api_round_trip(pkg, ora, synth, tmp_path):
+    """The reference-style class API (YUV(bmp, IYUV) -> compress -> dump -> load -> decompress)."""
+    YUV, BMP = pkg.YUV, pkg.BMP
+    w, h = 64, 48 - 48 % 16
+    bgrx = synth.bgrx_frames_numpy(w, h, 1)[0]
+    bmp = BMP()
+    bmp.header.width, bmp.header.height, bmp.header.bit_count = w, h, 32
+    bmp.header.header_size, bmp.header.compression, bmp.header.planes = 124, 3, 1
+    bmp.header.data_pos = 138
+    bmp.header.file_size = 138 + bgrx.size
+    bmp.data = bgrx.reshape(-1).copy()
+    bmp.dump(str(tmp_path / "a.bmp"))
+    bmp2 = BMP(str(tmp_path / "a.bmp"))
+    yuv = YUV(bmp2, YUV.FourccFormats.IYUV)
+    assert yuv.isValid() and not yuv.isCompressed()
+    assert np.array_equal(yuv.data, ora.bgrx_to_iyuv(bgrx, w, h, True))
+    c = yuv.compress(YUV.Compressions.DCT, [50, 60, 70])
+    assert c.isValid() and c.isCompressed() and c.header.data_pos == 67 and c.header.compression_params_size == 3
+    assert np.array_equal(c.data, ora.compress(yuv.data, w, h, (50, 60, 70)))
+    c.dump(str(tmp_path / "c.myyuv"))
+    c2 = YUV(str(tmp_path / "c.myyuv"))
+    d = c2.decompress()
+    assert d.isValid() and d.header.data_size == w * h * 3 // 2 and d.header.data_pos == 64
+    assert np.array_equal(d.data, ora.decompress(c.data, w, h, (50, 60, 70)))
+    with pytest.raises(RuntimeError, match="Error already compressed"):
+        c.compress(YUV.Compressions.DCT, [50, 50, 50])
+    with pytest.raises(RuntimeError, match="3 parameters required"):
+        yuv.compress(YUV.Compressions.DCT, [50])

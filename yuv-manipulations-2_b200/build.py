@@ -1,0 +1,76 @@
+"""Build the native parts of the package in-tree (so the .so files travel with the repo snapshot).
+
+  lib/libmyyuvb200.so   CUDA kernels + C ABI (include/myyuvb200.h), sm_100a only
+  lib/libmyyuv_lib.so   drop-in C++ class library (myyuv::BMP / myyuv::YUV, include/myyuv*.hpp) on top of the C ABI
+  lib/myyuv_cli         the reference's UNMODIFIED CLI object (oracle/_ref/myyuv_cli_main.o) linked against it, when present
+
+Flags that matter for bit-exactness: -fmad=false for device code (no FMUL+FADD -> FFMA contraction) and
+-ffp-contract=off for host code (quantisation tables use the reference's float expression).
+"""
+from __future__ import annotations
+
+import os
+import pathlib
+import shutil
+import subprocess
+import sys
+
+PKG = pathlib.Path(__file__).resolve().parent
+ROOT = PKG.parent
+CSRC = PKG / "csrc"
+LIB = PKG / "lib"
+
+NVCC = os.environ.get("NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+CXX = os.environ.get("MYYUVB_CXX", "/usr/bin/g++")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+
+
+def _newer(target: pathlib.Path, sources) -> bool:
+    if not target.exists():
+        return True
+    t = target.stat().st_mtime
+    return any(pathlib.Path(s).stat().st_mtime > t for s in sources)
+
+
+def _run(cmd, verbose):
+    if verbose:
+        print(" ".join(str(c) for c in cmd), flush=True)
+    subprocess.run([str(c) for c in cmd], check=True)
+
+
+def build_cuda(force: bool = False, verbose: bool = False) -> pathlib.Path:
+    LIB.mkdir(exist_ok=True)
+    out = LIB / "libmyyuvb200.so"
+    srcs = [CSRC / "kernels.cu", CSRC / "capi.cu"]
+    deps = srcs + [CSRC / "kernels.h", CSRC / "block_codec.cuh", CSRC / "dct_matrix.inc", ROOT / "include/myyuvb200.h"]
+    if force or _newer(out, deps):
+        _run([NVCC, *ARCH, "-O3", "-lineinfo", "-std=c++17", "-fmad=false", "-ccbin", CXX,
+              "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden", "--shared", "-o", out, *srcs], verbose)
+    return out
+
+
+def build_cxx(force: bool = False, verbose: bool = False):
+    """The drop-in class library and (if the reference CLI object is available) the unmodified CLI on top of it."""
+    LIB.mkdir(exist_ok=True)
+    out = LIB / "libmyyuv_lib.so"
+    srcs = [CSRC / "myyuv_bmp.cpp", CSRC / "myyuv_yuv.cpp"]
+    if not all(s.exists() for s in srcs):
+        return None
+    deps = srcs + list((ROOT / "include").glob("*.h*"))
+    if force or _newer(out, deps):
+        _run([CXX, "-std=gnu++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", f"-I{ROOT / 'include'}", *srcs,
+              f"-L{LIB}", "-lmyyuvb200", "-Wl,-rpath,$ORIGIN", "-o", out], verbose)
+    cli_obj = ROOT / "oracle/_ref/myyuv_cli_main.o"
+    cli = LIB / "myyuv_cli"
+    if cli_obj.exists() and (force or _newer(cli, [cli_obj, out])):
+        _run([CXX, cli_obj, f"-L{LIB}", "-lmyyuv_lib", "-lmyyuvb200", "-Wl,-rpath,$ORIGIN", "-o", cli], verbose)
+    return out
+
+
+def build(force: bool = False, verbose: bool = False):
+    build_cuda(force, verbose)
+    build_cxx(force, verbose)
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose=True)

@@ -1,0 +1,243 @@
+"""ctypes binding of the C ABI in include/myyuvb200.h (lib/libmyyuvb200.so).
+
+Everything here calls into the CUDA library; nothing is computed in Python.  Loading fails loudly when
+the library has not been built (``python -m yuv-manipulations-2_b200.build`` / ``__graft_entry__.build()``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import pathlib
+
+import numpy as np
+
+_PKG = pathlib.Path(__file__).resolve().parent
+_u8p = C.POINTER(C.c_uint8)
+_u64p = C.POINTER(C.c_uint64)
+
+# error codes of include/myyuvb200.h
+OK, ERR_CUDA, ERR_ARG, ERR_QUALITY, ERR_WIDTH, ERR_HEIGHT, ERR_CAPACITY, ERR_DCTYUV_SIZE, ERR_PLANE_SIZE, ERR_HUFFMAN, \
+    ERR_EVEN, ERR_TOO_LARGE = range(12)
+
+EXPORTS = [
+    "myyuvb_ctx_create", "myyuvb_ctx_destroy", "myyuvb_last_error", "myyuvb_sync", "myyuvb_stream",
+    "myyuvb_compress_bound", "myyuvb_xrgb_to_iyuv", "myyuvb_dct_compress", "myyuvb_dct_decompress",
+    "myyuvb_xrgb_to_iyuv_batch_dev", "myyuvb_dct_compress_batch_dev", "myyuvb_dct_decompress_batch_dev",
+    "myyuvb_batch_status", "myyuvb_dct_compress_batch_host", "myyuvb_dct_decompress_batch_host",
+    "myyuvb_host_alloc", "myyuvb_host_free", "myyuvb_launch_count",
+]
+
+
+class MyyuvError(RuntimeError):
+    """Raised with the message the reference would have thrown (std::runtime_error) and the C-ABI code."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(message)
+        self.code = code
+
+
+def library_path() -> pathlib.Path:
+    return _PKG / "lib" / "libmyyuvb200.so"
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not path.exists():
+        raise ImportError(f"{path} is missing: build the CUDA library first (python __graft_entry__.py build). "
+                          "There is no CPU fallback.")
+    L = C.CDLL(str(path))
+    L.myyuvb_last_error.restype = C.c_char_p
+    L.myyuvb_ctx_create.argtypes = [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
+    L.myyuvb_ctx_destroy.argtypes = [C.c_void_p]
+    L.myyuvb_ctx_destroy.restype = None
+    L.myyuvb_sync.argtypes = [C.c_void_p]
+    L.myyuvb_stream.argtypes = [C.c_void_p]
+    L.myyuvb_stream.restype = C.c_void_p
+    L.myyuvb_compress_bound.argtypes = [C.c_uint32, C.c_uint32]
+    L.myyuvb_compress_bound.restype = C.c_uint64
+    L.myyuvb_xrgb_to_iyuv.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p]
+    L.myyuvb_dct_compress.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, _u8p, C.c_void_p, C.c_uint64,
+                                      C.POINTER(C.c_uint32)]
+    L.myyuvb_dct_decompress.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, _u8p, C.c_void_p]
+    L.myyuvb_xrgb_to_iyuv_batch_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_void_p]
+    L.myyuvb_dct_compress_batch_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, _u8p, C.c_uint32, C.c_void_p,
+                                                C.c_uint64, C.c_void_p]
+    L.myyuvb_dct_decompress_batch_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, _u8p, C.c_uint32,
+                                                  C.c_void_p]
+    L.myyuvb_batch_status.argtypes = [C.c_void_p]
+    L.myyuvb_dct_compress_batch_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, _u8p, C.c_uint32, C.c_void_p,
+                                                 C.c_uint64, C.c_void_p]
+    L.myyuvb_dct_decompress_batch_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, _u8p, C.c_uint32,
+                                                   C.c_void_p]
+    L.myyuvb_host_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
+    L.myyuvb_host_free.argtypes = [C.c_void_p]
+    L.myyuvb_host_free.restype = None
+    L.myyuvb_launch_count.restype = C.c_uint64
+    _lib = L
+    return L
+
+
+def _check(rc: int):
+    if rc:
+        raise MyyuvError(rc, lib().myyuvb_last_error().decode())
+
+
+def _q(q) -> np.ndarray:
+    qa = np.ascontiguousarray(np.asarray(q).astype(np.uint8))
+    if qa.size != 3:
+        # compress_map lambda, myyuv_yuv.cpp:134-136
+        raise MyyuvError(ERR_ARG, "Error compression: incorrect parameters count. 3 parameters required")
+    return qa
+
+
+def compress_bound(w: int, h: int) -> int:
+    return int(lib().myyuvb_compress_bound(w, h))
+
+
+def launch_count() -> int:
+    return int(lib().myyuvb_launch_count())
+
+
+class PinnedBuffer:
+    """Page-locked host memory from the library (cudaHostAlloc), viewed as a numpy uint8 array."""
+
+    def __init__(self, nbytes: int):
+        p = C.c_void_p()
+        _check(lib().myyuvb_host_alloc(nbytes, C.byref(p)))
+        self.ptr = p.value
+        self.nbytes = nbytes
+        self.array = np.ctypeslib.as_array(C.cast(p, _u8p), shape=(max(nbytes, 1),))[:nbytes]
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            lib().myyuvb_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def _ptr(x) -> int:
+    """Address of a numpy array (host) or a torch tensor (host or device)."""
+    if isinstance(x, np.ndarray):
+        assert x.flags.c_contiguous
+        return x.ctypes.data
+    if hasattr(x, "data_ptr"):
+        assert x.is_contiguous()
+        return x.data_ptr()
+    if isinstance(x, int):
+        return x
+    raise TypeError(type(x))
+
+
+class Context:
+    """One CUDA device + stream + reusable scratch (myyuvb_ctx).  Not thread-safe; use one per thread."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self._h = C.c_void_p()
+        _check(lib().myyuvb_ctx_create(device, C.c_void_p(stream) if stream else None, C.byref(self._h)))
+        self.device = device
+
+    def close(self):
+        if self._h:
+            lib().myyuvb_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def sync(self):
+        _check(lib().myyuvb_sync(self._h))
+
+    @property
+    def stream(self) -> int:
+        return int(lib().myyuvb_stream(self._h) or 0)
+
+    # ---- host-pointer single image calls (numpy in, numpy out) ----
+    def xrgb_to_iyuv(self, bgrx: np.ndarray, w: int, h: int, bottom_up: bool = True) -> np.ndarray:
+        bgrx = np.ascontiguousarray(bgrx, dtype=np.uint8).reshape(-1)
+        if bgrx.size != w * h * 4:
+            raise ValueError("bgrx must hold width*height*4 bytes")
+        out = np.empty(w * h * 3 // 2, np.uint8)
+        _check(lib().myyuvb_xrgb_to_iyuv(self._h, bgrx.ctypes.data, w, h, int(bottom_up), out.ctypes.data))
+        return out
+
+    def compress(self, iyuv: np.ndarray, w: int, h: int, q, capacity: int | None = None) -> np.ndarray:
+        iyuv = np.ascontiguousarray(iyuv, dtype=np.uint8).reshape(-1)
+        if iyuv.size != w * h * 3 // 2:
+            raise ValueError("iyuv must hold width*height*3/2 bytes")
+        qa = _q(q)
+        cap = compress_bound(w, h) if capacity is None else capacity
+        out = np.empty(max(cap, 1), np.uint8)
+        n = C.c_uint32(0)
+        _check(lib().myyuvb_dct_compress(self._h, iyuv.ctypes.data, w, h, qa.ctypes.data_as(_u8p), out.ctypes.data, cap, C.byref(n)))
+        return out[: n.value].copy()
+
+    def decompress(self, payload: np.ndarray, w: int, h: int, q) -> np.ndarray:
+        payload = np.ascontiguousarray(payload, dtype=np.uint8).reshape(-1)
+        qa = _q(q)
+        out = np.empty(w * h * 3 // 2, np.uint8)
+        _check(lib().myyuvb_dct_decompress(self._h, payload.ctypes.data if payload.size else None, payload.size, w, h,
+                                           qa.ctypes.data_as(_u8p), out.ctypes.data))
+        return out
+
+    # ---- host-pointer batch calls (pipelined H2D / kernels / D2H) ----
+    def compress_batch_host(self, iyuv, w: int, h: int, q, n_frames: int, out, offsets: np.ndarray) -> None:
+        qa = _q(q)
+        assert offsets.dtype == np.uint64 and offsets.size >= n_frames + 1
+        nbytes = out.nbytes if isinstance(out, np.ndarray) else out.numel()
+        _check(lib().myyuvb_dct_compress_batch_host(self._h, _ptr(iyuv), w, h, qa.ctypes.data_as(_u8p), n_frames, _ptr(out), nbytes,
+                                                    offsets.ctypes.data))
+
+    def decompress_batch_host(self, payloads, offsets: np.ndarray, w: int, h: int, q, n_frames: int, out) -> None:
+        qa = _q(q)
+        assert offsets.dtype == np.uint64 and offsets.size >= n_frames + 1
+        _check(lib().myyuvb_dct_decompress_batch_host(self._h, _ptr(payloads), offsets.ctypes.data, w, h, qa.ctypes.data_as(_u8p),
+                                                      n_frames, _ptr(out)))
+
+    # ---- device-pointer batch calls (torch CUDA tensors or raw device addresses; asynchronous) ----
+    def xrgb_to_iyuv_batch_dev(self, d_bgrx, w: int, h: int, bottom_up: bool, n_frames: int, d_iyuv) -> None:
+        _check(lib().myyuvb_xrgb_to_iyuv_batch_dev(self._h, _ptr(d_bgrx), w, h, int(bottom_up), n_frames, _ptr(d_iyuv)))
+
+    def compress_batch_dev(self, d_iyuv, w: int, h: int, q, n_frames: int, d_out, out_capacity: int, d_offsets) -> None:
+        qa = _q(q)
+        _check(lib().myyuvb_dct_compress_batch_dev(self._h, _ptr(d_iyuv), w, h, qa.ctypes.data_as(_u8p), n_frames, _ptr(d_out),
+                                                   out_capacity, _ptr(d_offsets)))
+
+    def decompress_batch_dev(self, d_payloads, d_offsets, w: int, h: int, q, n_frames: int, d_iyuv) -> None:
+        qa = _q(q)
+        _check(lib().myyuvb_dct_decompress_batch_dev(self._h, _ptr(d_payloads), _ptr(d_offsets), w, h, qa.ctypes.data_as(_u8p),
+                                                     n_frames, _ptr(d_iyuv)))
+
+    def batch_status(self) -> None:
+        """Synchronise and raise the first data-dependent error of the batch calls issued so far."""
+        _check(lib().myyuvb_batch_status(self._h))
+
+
+_default_ctx: Context | None = None
+
+
+def default_context() -> Context:
+    """Lazily created context on device 0 (what the class API uses, like the reference's free functions)."""
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(0)
+    return _default_ctx

@@ -1,0 +1,458 @@
+// block_codec.cuh -- per-8x8-block entropy coding of the reference's DCT payload, written for one GPU
+// thread per block.  Everything here is integer/byte work with data-dependent control flow, so it is
+// plain __host__ __device__ code: the kernels in kernels.cu call it on the device, and
+// tests/hostemu/hostemu.cpp compiles the same header with g++ so the logic can be checked against the
+// oracle on a machine without a GPU (test infrastructure only -- the product never runs it on the CPU).
+//
+// Format and semantics follow the reference (paths relative to /root/reference):
+//   Huffman.cpp:172-241  fromData   zigzag, trailing-zero trim, histogram, tree, canonical codes, code stream
+//   Huffman.cpp:279-326  dump       u16 bits | u8 table_bytes | groups {(len-1)<<5|(cnt-1), 11-bit symbols} | stream
+//   Huffman.cpp:243-277  fromDump,  :106-154 decodeSymbol / decodeFromTreeData
+// Byte-exactness with the reference needs its tie-breaking, which comes from libstdc++ (GCC 13):
+// std::unordered_map<int16_t,uint8_t> iteration order and std::priority_queue's heap algorithms
+// (Huffman.cpp:173,204-217).  list_place()/heap_*() below re-implement those published semantics with
+// fixed-size arrays; see SURVEY.md App. A.5 and DESIGN.md "Tie-breaking".
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define MYB_HD __host__ __device__ __forceinline__
+#else
+#define MYB_HD inline
+#endif
+
+namespace myyuvb {
+
+// zigzag scan position -> row-major coefficient index (JPEG zigzag; Huffman.cpp:32-34)
+#define MYB_ZIGZAG_LIST                                                                                       \
+  0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7,   \
+      14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, \
+      46, 53, 60, 61, 54, 47, 55, 62, 63
+
+MYB_HD uint32_t bit_reverse32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+  return __brev(v);
+#else
+  v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1);
+  v = ((v >> 2) & 0x33333333u) | ((v & 0x33333333u) << 2);
+  v = ((v >> 4) & 0x0f0f0f0fu) | ((v & 0x0f0f0f0fu) << 4);
+  v = ((v >> 8) & 0x00ff00ffu) | ((v & 0x00ff00ffu) << 8);
+  return (v >> 16) | (v << 16);
+#endif
+}
+
+MYB_HD int ctz64(uint64_t v) {
+#if defined(__CUDA_ARCH__)
+  return __ffsll((long long)v) - 1;
+#else
+  return __builtin_ctzll(v);
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Scratch memory of one block's Huffman build.  All arrays are bytes addressed as b[(off + i) * stride]
+// (symbols: 16-bit, h[i * stride]).  On the GPU the fast instance lives in shared memory with
+// stride = threads per CTA, so the lanes of a warp hit consecutive bytes; the fallback instance for
+// blocks with many distinct symbols lives in per-thread local memory with stride 1.
+// CAP = max distinct symbols (+1 slot for the key 0 that freq[0] may insert, Huffman.cpp:195).
+// ---------------------------------------------------------------------------------------------------
+template <int CAP>
+struct HuffScratch {
+  uint8_t* b;
+  int16_t* h;
+  int stride;
+  static constexpr int kCnt = 0;                 // [CAP+1] occurrences of slot s in the message
+  static constexpr int kOrd = kCnt + CAP + 1;    // [CAP+1] hash-list order: slot at list position p
+  static constexpr int kBkt = kOrd + CAP + 1;    // [CAP+1] bucket of list position p; later: heap
+  static constexpr int kFreq = kBkt + CAP + 1;   // [2*CAP] node weight
+  static constexpr int kPar = kFreq + 2 * CAP;   // [2*CAP] parent node, then depth
+  static constexpr int kLen = kPar + 2 * CAP;    // [CAP]   code length of slot s
+  static constexpr int kCode = kLen + CAP;       // [CAP]   bit-reversed canonical code of slot s
+  static constexpr int kSorted = kCode + CAP;    // [CAP]   slots ordered by (length, symbol value)
+  static constexpr int kBytes = kSorted + CAP;   // bytes per block
+  static constexpr int kSyms = CAP + 1;          // int16 per block
+  MYB_HD uint8_t& at(int off, int i) const { return b[(off + i) * stride]; }
+  MYB_HD int16_t& sym(int i) const { return h[i * stride]; }
+};
+
+struct HuffPlan {
+  int n;           // distinct symbols (leaves); < 0: scratch capacity exceeded, retry with the large instance
+  int msg_len;     // coded symbols (1..64)
+  int bits;        // code stream bits
+  int table_bytes; // bytes of the serialised code table
+  MYB_HD int size() const { return 3 + table_bytes + ((bits + 7) >> 3); }
+};
+
+// std::hash<short>(v) % nb with v sign-extended to 64 bits (libstdc++ functional_hash.h); nb in {13,29,59,127}.
+// 2^64 mod nb = 3, 24, 5, 2 respectively.
+MYB_HD int hash_bucket(int v, int nb) {
+  int m, two64;
+  switch (nb) {
+    case 13: two64 = 3; m = (v < 0 ? -v : v) % 13; break;
+    case 29: two64 = 24; m = (v < 0 ? -v : v) % 29; break;
+    case 59: two64 = 5; m = (v < 0 ? -v : v) % 59; break;
+    default: two64 = 2; m = (v < 0 ? -v : v) % 127; break;
+  }
+  if (v >= 0) return m;
+  int r = two64 - m;
+  return r < 0 ? r + nb : r;
+}
+
+// libstdc++ _M_insert_bucket_begin / _M_rehash_aux: a key whose bucket already holds nodes goes right
+// before the first node of that bucket's run, otherwise to the front of the whole list.
+template <int CAP>
+MYB_HD void list_place(const HuffScratch<CAP>& S, int& ln, int slot, int bucket) {
+  int p = 0;
+  for (int i = 0; i < ln; i++)
+    if (S.at(S.kBkt, i) == bucket) { p = i; break; }
+  for (int i = ln; i > p; i--) {
+    S.at(S.kOrd, i) = S.at(S.kOrd, i - 1);
+    S.at(S.kBkt, i) = S.at(S.kBkt, i - 1);
+  }
+  S.at(S.kOrd, p) = (uint8_t)slot;
+  S.at(S.kBkt, p) = (uint8_t)bucket;
+  ln++;
+}
+
+// Iteration order of the reference's freq map after inserting keys slot 0..m-1 (first-occurrence order)
+// and erasing `erase_slot` (>= 0) at the end.  Result: S.kOrd[0..n).  Returns n.
+template <int CAP>
+MYB_HD int hash_list_order(const HuffScratch<CAP>& S, int m, int erase_slot) {
+  int ln = 0;
+  if (m <= 13) {
+    // one table size (13 buckets): keep list + buckets as 4-bit fields of two 64-bit registers
+    uint64_t ord = 0, bkt = ~0ull;  // empty fields hold 0xF, which is no bucket
+    for (int s = 0; s < m; s++) {
+      const uint64_t b = (uint64_t)hash_bucket(S.sym(s), 13);
+      const uint64_t x = bkt ^ (b * 0x1111111111111111ull);
+      const uint64_t zero_nib = (x - 0x1111111111111111ull) & ~x & 0x8888888888888888ull;  // lowest hit is exact
+      const int p4 = zero_nib ? (ctz64(zero_nib) & ~3) : 0;
+      const uint64_t low = (1ull << p4) - 1ull;
+      ord = (ord & low) | ((ord & ~low) << 4) | ((uint64_t)s << p4);
+      bkt = (bkt & low) | ((bkt & ~low) << 4) | (b << p4);
+    }
+    for (int i = 0; i < m; i++) {
+      const int s = (int)((ord >> (4 * i)) & 15u);
+      if (s != erase_slot) S.at(S.kOrd, ln++) = (uint8_t)s;
+    }
+    return ln;
+  }
+  // general case: 13 -> 29 -> 59 -> 127 buckets, rehash before inserting key number 14, 30, 60
+  // (_Prime_rehash_policy::_M_need_rehash with max_load_factor 1, growth factor 2)
+  int nb = 13;
+  for (int s = 0; s < m; s++) {
+    if (s == 13 || s == 29 || s == 59) {
+      nb = (s == 13) ? 29 : (s == 29) ? 59 : 127;
+      // walk the old list front to back and re-place every node (old order parked in kFreq, unused so far)
+      for (int i = 0; i < ln; i++) S.at(S.kFreq, i) = S.at(S.kOrd, i);
+      const int old = ln;
+      ln = 0;
+      for (int i = 0; i < old; i++) {
+        const int t = S.at(S.kFreq, i);
+        list_place(S, ln, t, hash_bucket(S.sym(t), nb));
+      }
+    }
+    list_place(S, ln, s, hash_bucket(S.sym(s), nb));
+  }
+  if (erase_slot >= 0) {
+    int w = 0;
+    for (int i = 0; i < ln; i++) {
+      const uint8_t t = S.at(S.kOrd, i);
+      if (t != erase_slot) S.at(S.kOrd, w++) = t;
+    }
+    ln = w;
+  }
+  return ln;
+}
+
+// std::push_heap with Compare(a,b) = a.freq > b.freq (Huffman.hpp:41-45; stl_heap.h __push_heap).
+// heap lives in kBkt (free after hash_list_order).
+template <int CAP>
+MYB_HD void heap_sift_up(const HuffScratch<CAP>& S, int hole, int node, int wnode) {
+  while (hole > 0) {
+    const int parent = (hole - 1) >> 1;
+    const int pn = S.at(S.kBkt, parent);
+    if (!(S.at(S.kFreq, pn) > wnode)) break;
+    S.at(S.kBkt, hole) = (uint8_t)pn;
+    hole = parent;
+  }
+  S.at(S.kBkt, hole) = (uint8_t)node;
+}
+
+// std::pop_heap + pop_back (stl_heap.h __pop_heap / __adjust_heap); returns the removed top node.
+template <int CAP>
+MYB_HD int heap_pop(const HuffScratch<CAP>& S, int& hsize) {
+  const int top = S.at(S.kBkt, 0);
+  const int len = hsize - 1;
+  hsize = len;
+  if (len == 0) return top;
+  const int value = S.at(S.kBkt, len);
+  int hole = 0, child = 0;
+  while (child < ((len - 1) >> 1)) {
+    child = 2 * (child + 1);
+    if (S.at(S.kFreq, S.at(S.kBkt, child)) > S.at(S.kFreq, S.at(S.kBkt, child - 1))) child--;
+    S.at(S.kBkt, hole) = S.at(S.kBkt, child);
+    hole = child;
+  }
+  if ((len & 1) == 0 && child == ((len - 2) >> 1)) {
+    child = 2 * (child + 1);
+    S.at(S.kBkt, hole) = S.at(S.kBkt, child - 1);
+    hole = child - 1;
+  }
+  heap_sift_up(S, hole, value, S.at(S.kFreq, value));
+  return top;
+}
+
+MYB_HD int group_table_bytes(int cnt) {  // one code length with cnt symbols, split in groups of <= 32 (Huffman.cpp:284-293)
+  int bytes = 0;
+  while (cnt > 0) {
+    const int c = cnt > 32 ? 32 : cnt;
+    bytes += 1 + ((c * 11 + 7) >> 3);
+    cnt -= c;
+  }
+  return bytes;
+}
+
+// Build the code of one block.  Z: accessor with  int get(int i)  (zigzag coefficient i) and
+// void set(int i, int v); on success the first msg_len entries are overwritten with slot numbers
+// (the coefficient of slot s is S.sym(s)).  L = index of the last non-zero zigzag coefficient + 1 (0: all zero).
+template <int CAP, class Z>
+MYB_HD HuffPlan huff_plan(Z& z, int L, const HuffScratch<CAP>& S) {
+  HuffPlan pl;
+  if (L == 0) {  // all-zero block: the single symbol 0, one bit (Huffman.cpp:195-199)
+    S.sym(0) = 0;
+    S.at(S.kCnt, 0) = 1;
+    S.at(S.kLen, 0) = 1;
+    S.at(S.kCode, 0) = 0;
+    S.at(S.kSorted, 0) = 0;
+    z.set(0, 0);
+    pl.n = 1; pl.msg_len = 1; pl.bits = 1; pl.table_bytes = 3;
+    return pl;
+  }
+  // histogram in first-occurrence order (Huffman.cpp:176-189, message part only; the trailing zeros
+  // only matter through the key 0 they may add to the map, handled below)
+  int n = 0, zero_slot = -1;
+  for (int i = 0; i < L; i++) {
+    const int v = z.get(i);
+    int s = 0;
+    while (s < n && S.sym(s) != v) s++;
+    if (s == n) {
+      if (n == CAP) {  // does not fit this scratch instance: undo and let the caller retry with the big one
+        for (int j = 0; j < i; j++) z.set(j, S.sym(z.get(j)));
+        pl.n = -1; pl.msg_len = 0; pl.bits = 0; pl.table_bytes = 0;
+        return pl;
+      }
+      S.sym(n) = (int16_t)v;
+      S.at(S.kCnt, n) = 0;
+      if (v == 0) zero_slot = n;
+      n++;
+    }
+    S.at(S.kCnt, s)++;
+    z.set(i, s);
+  }
+  pl.n = n;
+  pl.msg_len = L;
+  if (n <= 2) {  // one or two symbols: every code has length 1 (Huffman.cpp:76, :218-221)
+    int lo = 0;
+    if (n == 2 && S.sym(1) < S.sym(0)) lo = 1;
+    S.at(S.kSorted, 0) = (uint8_t)lo;
+    S.at(S.kLen, lo) = 1;
+    S.at(S.kCode, lo) = 0;
+    if (n == 2) {
+      S.at(S.kSorted, 1) = (uint8_t)(1 - lo);
+      S.at(S.kLen, 1 - lo) = 1;
+      S.at(S.kCode, 1 - lo) = 1;
+    }
+    pl.bits = L;
+    pl.table_bytes = group_table_bytes(n);
+    return pl;
+  }
+  // map iteration order.  Key 0 is always in the reference's map while it is filled (trailing zeros or
+  // freq[0], Huffman.cpp:192-195); when the message itself has no zero it is erased again (:201) and can
+  // only have mattered by triggering a rehash as key number 14, 30 or 60.
+  int m = n, erase_slot = -1;
+  if (zero_slot < 0 && (n == 13 || n == 29 || n == 59)) {
+    S.sym(n) = 0;
+    erase_slot = n;
+    m = n + 1;
+  }
+  hash_list_order(S, m, erase_slot);
+  // leaves pushed in list order (Huffman.cpp:207-209); node id = list position, weights in kFreq
+  int hsize = 0;
+  for (int j = 0; j < n; j++) {
+    const int w = S.at(S.kCnt, S.at(S.kOrd, j));
+    S.at(S.kFreq, j) = (uint8_t)w;
+    hsize++;
+    heap_sift_up(S, hsize - 1, j, w);
+  }
+  int nnode = n;
+  while (hsize > 1) {  // Huffman.cpp:210-217
+    const int l = heap_pop(S, hsize);
+    const int r = heap_pop(S, hsize);
+    const int w = S.at(S.kFreq, l) + S.at(S.kFreq, r);
+    S.at(S.kFreq, nnode) = (uint8_t)w;
+    S.at(S.kPar, l) = (uint8_t)nnode;
+    S.at(S.kPar, r) = (uint8_t)nnode;
+    hsize++;
+    heap_sift_up(S, hsize - 1, nnode, w);
+    nnode++;
+  }
+  // code length = leaf depth (Huffman.cpp:71-83); parents always have larger ids than children
+  S.at(S.kPar, nnode - 1) = 0;
+  for (int i = nnode - 2; i >= 0; i--) S.at(S.kPar, i) = (uint8_t)(S.at(S.kPar, S.at(S.kPar, i)) + 1);
+  for (int j = 0; j < n; j++) S.at(S.kLen, S.at(S.kOrd, j)) = S.at(S.kPar, j);
+  // tree_data: lengths ascending, symbols ascending inside a length (Huffman.cpp:76-78): insertion sort
+  for (int i = 0; i < n; i++) {
+    const int key = ((int)S.at(S.kLen, i) << 12) + (S.sym(i) + 2048);
+    int j = i - 1;
+    while (j >= 0) {
+      const int t = S.at(S.kSorted, j);
+      if ((((int)S.at(S.kLen, t) << 12) + (S.sym(t) + 2048)) <= key) break;
+      S.at(S.kSorted, j + 1) = (uint8_t)t;
+      j--;
+    }
+    S.at(S.kSorted, j + 1) = (uint8_t)i;
+  }
+  // canonical codes (Huffman.cpp:86-103) stored bit-reversed, sizes
+  int code = 0, prev = 0, bits = 0, table = 0, run = 0;
+  for (int i = 0; i < n; i++) {
+    const int s = S.at(S.kSorted, i);
+    const int len = S.at(S.kLen, s);
+    if (len != prev) {
+      table += group_table_bytes(run);
+      run = 0;
+    }
+    code = (code << (len - prev)) & 0xff;
+    S.at(S.kCode, s) = (uint8_t)(bit_reverse32((uint32_t)code) >> (32 - len));
+    code = (code + 1) & 0xff;
+    prev = len;
+    run++;
+    bits += len * (int)S.at(S.kCnt, s);
+  }
+  table += group_table_bytes(run);
+  pl.bits = bits;
+  pl.table_bytes = table;
+  return pl;
+}
+
+// little-endian bit writer into bytes
+struct BitSink {
+  uint8_t* p;
+  uint64_t acc;
+  int nb;
+  MYB_HD void put(uint32_t v, int len) {
+    acc |= (uint64_t)v << nb;
+    nb += len;
+    while (nb >= 8) {
+      *p++ = (uint8_t)acc;
+      acc >>= 8;
+      nb -= 8;
+    }
+  }
+  MYB_HD void flush() {
+    if (nb > 0) *p++ = (uint8_t)acc;
+    acc = 0;
+    nb = 0;
+  }
+};
+
+// Serialise the chunk planned by huff_plan into dst[0 .. pl.size()).
+template <int CAP, class Z>
+MYB_HD void huff_emit(Z& z, const HuffPlan& pl, const HuffScratch<CAP>& S, uint8_t* dst) {
+  dst[0] = (uint8_t)(pl.bits & 0xff);
+  dst[1] = (uint8_t)(pl.bits >> 8);
+  dst[2] = (uint8_t)pl.table_bytes;
+  BitSink w{dst + 3, 0, 0};
+  int i = 0;
+  while (i < pl.n) {  // code table, Huffman.cpp:300-316
+    const int len = S.at(S.kLen, S.at(S.kSorted, i));
+    int j = i;
+    while (j < pl.n && S.at(S.kLen, S.at(S.kSorted, j)) == len) j++;
+    while (i < j) {
+      const int c = (j - i) > 32 ? 32 : (j - i);
+      w.put((uint32_t)(((len - 1) << 5) | (c - 1)), 8);
+      for (int k = 0; k < c; k++) w.put((uint32_t)S.sym(S.at(S.kSorted, i + k)) & 0x7ffu, 11);  // pack11bit :36-52
+      w.flush();
+      i += c;
+    }
+  }
+  for (int k = 0; k < pl.msg_len; k++) {  // code stream, Huffman.cpp:227-236, :319-325
+    const int s = z.get(k);
+    w.put(S.at(S.kCode, s), S.at(S.kLen, s));
+  }
+  w.flush();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Decoder (Huffman.cpp:243-277, :54-69, :106-154).  chunk/size: one block's bytes.  emit(j, v) receives
+// the value v of zigzag position j for every decoded symbol (positions never emitted are 0).
+// Returns 0, or non-zero for the conditions on which the reference throws "Huffman bad code" /
+// "Huffman unknown symbol" and for reads the reference would do outside the chunk.
+// ---------------------------------------------------------------------------------------------------
+MYB_HD int table_symbol(const uint8_t* groups, int table_bytes, int len, int idx, int* out) {
+  int i = 0;
+  while (i < table_bytes) {  // groups of the same length are concatenated in file order (Huffman.cpp:258-266)
+    const int info = groups[i];
+    const int glen = (info >> 5) + 1, c = (info & 31) + 1;
+    if (glen == len) {
+      if (idx < c) {
+        const int bit = idx * 11, byte = i + 1 + (bit >> 3);
+        uint32_t v = groups[byte] | ((uint32_t)groups[byte + 1] << 8);
+        if ((bit & 7) > 5) v |= (uint32_t)groups[byte + 2] << 16;
+        v = (v >> (bit & 7)) & 0x7ffu;
+        *out = (v >= 1024u) ? (int)v - 2048 : (int)v;
+        return 0;
+      }
+      idx -= c;
+    }
+    i += 1 + ((c * 11 + 7) >> 3);
+  }
+  return 1;
+}
+
+template <class Emit>
+MYB_HD int huff_decode_block(const uint8_t* chunk, int size, Emit&& emit) {
+  if (size < 3) return 1;
+  const int bits = chunk[0] | (chunk[1] << 8);
+  const int table_bytes = chunk[2];
+  if (bits > 512 || 3 + table_bytes + ((bits + 7) >> 3) > size) return 1;
+  const uint8_t* groups = chunk + 3;
+  uint64_t counts = 0;  // symbols per code length 1..8, one byte each
+  {
+    int i = 0;
+    while (i < table_bytes) {
+      const int info = groups[i];
+      const int len = (info >> 5) + 1, c = (info & 31) + 1;
+      i += 1 + ((c * 11 + 7) >> 3);
+      if (i > table_bytes) return 1;
+      const int sh = 8 * (len - 1);
+      if (((counts >> sh) & 0xff) + (uint64_t)c > 64) return 1;  // more symbols than a block can hold
+      counts += (uint64_t)c << sh;
+    }
+  }
+  const uint8_t* data = groups + table_bytes;
+  int p = 0, j = 0;
+  while (p < bits && j < 64) {
+    uint32_t code = 0, first = 0;  // uint8_t in the reference (Huffman.cpp:107-108): keep the 8-bit wrap
+    int len = 1;
+    for (; len <= 8; len++) {
+      const uint32_t c = (uint32_t)(counts >> (8 * (len - 1))) & 0xff;
+      if (p >= bits) return 1;  // "Huffman bad code" :120-122
+      code |= (uint32_t)(data[p >> 3] >> (p & 7)) & 1u;
+      p++;
+      if (code < c + first) {
+        int v;
+        if (table_symbol(groups, table_bytes, len, (int)(code - first), &v)) return 1;
+        emit(j, v);
+        j++;
+        break;
+      }
+      first = ((first + c) << 1) & 0xff;
+      code = (code << 1) & 0xff;
+    }
+    if (len > 8) return 1;  // "Huffman unknown symbol" :139
+  }
+  return 0;
+}
+
+}  // namespace myyuvb

@@ -1,0 +1,473 @@
+// capi.cu -- the C ABI declared in include/myyuvb200.h: contexts, argument checks that mirror the
+// reference's exceptions, quantisation tables, device/pinned buffer management, H2D/D2H, kernel launches.
+// There is NO CPU implementation of the codec in this library: every entry point either runs the CUDA
+// kernels of kernels.cu or fails.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+
+#include "../../include/myyuvb200.h"
+#include "kernels.h"
+
+using namespace myyuvb;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CU(call)                                                                                              \
+  do {                                                                                                        \
+    cudaError_t e_ = (call);                                                                                  \
+    if (e_ != cudaSuccess)                                                                                    \
+      return fail(MYYUVB_ERR_CUDA, std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #call);      \
+  } while (0)
+
+// JPEG Annex K quantisation tables at quality 50 (the reference's lum_q_table / chroma_q_table, DCT.cpp:199-219)
+const uint8_t kLumaQ50[64] = {16, 11, 10, 16, 24,  40,  51,  61,  12, 12, 14, 19, 26,  58,  60,  55,
+                              14, 13, 16, 24, 40,  57,  69,  56,  14, 17, 22, 29, 51,  87,  80,  62,
+                              18, 22, 37, 56, 68,  109, 103, 77,  24, 35, 55, 64, 81,  104, 113, 92,
+                              49, 64, 78, 87, 103, 121, 120, 101, 72, 92, 95, 98, 112, 100, 103, 99};
+const uint8_t kChromaQ50[64] = {17, 18, 24, 47, 99, 99, 99, 99, 18, 21, 26, 66, 99, 99, 99, 99,
+                                24, 26, 56, 99, 99, 99, 99, 99, 47, 66, 99, 99, 99, 99, 99, 99,
+                                99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99,
+                                99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99};
+
+// DCT.cpp:286-290: mul = q >= 50.5 ? (100-q)/50 : 50/q ; table = clamp(round(q50 * mul), 1, 255), all in float.
+// Host code is compiled without FMA contraction (build.py: -ffp-contract=off), each step is one float op.
+void make_qtables(const uint8_t quality[3], QTables* qt) {
+  for (int p = 0; p < 3; p++) {
+    const volatile float qf = (float)quality[p];
+    const volatile float mul = (qf >= 50.5f) ? (100.0f - qf) / 50.0f : 50.0f / qf;
+    const uint8_t* base = p == 0 ? kLumaQ50 : kChromaQ50;
+    for (int i = 0; i < 64; i++) {
+      const volatile float prod = (float)base[i] * mul;
+      float v = roundf(prod);
+      v = v < 1.0f ? 1.0f : (v > 255.0f ? 255.0f : v);
+      qt->q[p][i] = v;
+      qt->rq[p][i] = 1.0f / v;  // correctly rounded reciprocal, used by the exact-division step in the kernel
+    }
+  }
+}
+
+struct Buffer {
+  void* p = nullptr;
+  size_t cap = 0;
+  bool pinned = false;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return MYYUVB_OK;
+    release();
+    const size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = pinned ? cudaHostAlloc(&p, want, cudaHostAllocDefault) : cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      p = nullptr;
+      return fail(MYYUVB_ERR_CUDA, std::string("CUDA error: ") + cudaGetErrorString(e) + " allocating " + std::to_string(want) + " bytes");
+    }
+    cap = want;
+    return MYYUVB_OK;
+  }
+  void release() {
+    if (p) { if (pinned) cudaFreeHost(p); else cudaFree(p); }
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+int check_quality(const uint8_t q[3]) {
+  for (int i = 0; i < 3; i++)
+    if (q[i] < 1 || q[i] > 100) return fail(MYYUVB_ERR_QUALITY, "Level of quality must be between 1 and 100");
+  return MYYUVB_OK;
+}
+
+// applyDCTPlane / restoreDCTPlane throw on the first plane whose width or height is not a multiple of 8
+// (DCT.cpp:280-285, :338-343); planes are Y (w x h) then U, V (w/2 x h/2).
+int check_dims(uint32_t w, uint32_t h) {
+  if (w == 0 || h == 0) return fail(MYYUVB_ERR_ARG, "Error. empty image");
+  if (w % 8 != 0) return fail(MYYUVB_ERR_WIDTH, "Error. width % 8 must be 0");
+  if (h % 8 != 0) return fail(MYYUVB_ERR_HEIGHT, "Error. height % 8 must be 0");
+  if ((w / 2) % 8 != 0) return fail(MYYUVB_ERR_WIDTH, "Error. width % 8 must be 0");
+  if ((h / 2) % 8 != 0) return fail(MYYUVB_ERR_HEIGHT, "Error. height % 8 must be 0");
+  if ((uint64_t)w * h * 3 / 2 > 0xffffffffull) return fail(MYYUVB_ERR_TOO_LARGE, "Error. image does not fit the format's uint32 sizes");
+  return MYYUVB_OK;
+}
+
+}  // namespace
+
+struct myyuvb_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  bool own_stream = false;
+  int grid = 0;
+  Buffer d_in, d_out, d_status, d_tiles, d_plane_start, d_counters, d_sizes, d_overflow, d_desc, d_offsets;
+  Buffer h_small, h_stage_in, h_stage_out;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  myyuvb_ctx() { h_small.pinned = h_stage_in.pinned = h_stage_out.pinned = true; }
+};
+
+namespace {
+
+int ensure_workspace(myyuvb_ctx* c, const FrameGeom& g, bool encoder, Workspace* ws) {
+  const uint64_t tiles = (uint64_t)g.tiles_per_frame * g.n_frames;
+  int rc;
+  if ((rc = c->d_tiles.reserve(tiles * 8))) return rc;
+  if ((rc = c->d_plane_start.reserve(((uint64_t)g.n_frames * 3 + 1) * 8))) return rc;
+  if (!c->d_counters.p) {
+    if ((rc = c->d_counters.reserve(64))) return rc;
+    CU(cudaMemsetAsync(c->d_counters.p, 0, 64, c->stream));
+  }
+  if (encoder) {
+    if ((rc = c->d_sizes.reserve((uint64_t)g.nblk_frame * g.n_frames))) return rc;
+    if ((rc = c->d_overflow.reserve((uint64_t)c->grid * 65536))) return rc;
+  } else {
+    if ((rc = c->d_desc.reserve((uint64_t)g.n_frames * 3 * sizeof(PlaneDesc)))) return rc;
+  }
+  ws->tile_status = c->d_tiles.as<uint64_t>();
+  ws->plane_start = c->d_plane_start.as<uint64_t>();
+  ws->counters = c->d_counters.as<uint32_t>();
+  ws->chunk_sizes = c->d_sizes.as<uint8_t>();
+  ws->overflow = c->d_overflow.as<uint8_t>();
+  ws->plane_desc = c->d_desc.p;
+  ws->grid = c->grid;
+  return MYYUVB_OK;
+}
+
+int flags_to_error(uint32_t flags) {
+  if (flags & kFlagDctYuvSize) return fail(MYYUVB_ERR_DCTYUV_SIZE, "DCTYUV load bad size");
+  if (flags & kFlagPlaneSize) return fail(MYYUVB_ERR_PLANE_SIZE, "DCTYUVPlane load bad size");
+  if (flags & kFlagHuffman) return fail(MYYUVB_ERR_HUFFMAN, "Huffman bad code");
+  if (flags & kFlagCapacity) return fail(MYYUVB_ERR_CAPACITY, "Error. output buffer is too small for the compressed data");
+  return MYYUVB_OK;
+}
+
+// reads and clears the device error flags (synchronises the stream)
+int read_flags(myyuvb_ctx* c) {
+  int rc;
+  if ((rc = c->h_small.reserve(256))) return rc;
+  uint32_t* h = c->h_small.as<uint32_t>();
+  CU(cudaMemcpyAsync(h, c->d_counters.as<uint32_t>() + 1, 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemsetAsync(c->d_counters.as<uint32_t>() + 1, 0, 4, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return flags_to_error(*h);
+}
+
+bool is_pinned_or_device(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* myyuvb_last_error(void) { return g_err.c_str(); }
+
+uint64_t myyuvb_launch_count(void) { return g_launches; }
+
+uint64_t myyuvb_compress_bound(uint32_t width, uint32_t height) {
+  const uint64_t nblk = (uint64_t)(width / 8) * (height / 8) + 2ull * (width / 16) * (height / 16);
+  return 12 + 24 + nblk + nblk * 255;
+}
+
+int myyuvb_ctx_create(int device, void* stream, myyuvb_ctx** out) {
+  if (!out) return fail(MYYUVB_ERR_ARG, "myyuvb_ctx_create: null output pointer");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(MYYUVB_ERR_CUDA, std::string("CUDA error: no usable CUDA device (") + cudaGetErrorString(e) + "); this library has no CPU path");
+  if (device < 0 || device >= count) return fail(MYYUVB_ERR_ARG, "myyuvb_ctx_create: bad device ordinal");
+  CU(cudaSetDevice(device));
+  myyuvb_ctx* c = new myyuvb_ctx();
+  c->device = device;
+  if (stream) {
+    c->stream = reinterpret_cast<cudaStream_t>(stream);
+  } else {
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->own_stream = true;
+  }
+  CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  for (auto& ev : c->ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  c->grid = codec_grid_size(device, true);
+  *out = c;
+  return MYYUVB_OK;
+}
+
+void myyuvb_ctx_destroy(myyuvb_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  cudaStreamSynchronize(c->copy_stream);
+  for (Buffer* b : {&c->d_in, &c->d_out, &c->d_status, &c->d_tiles, &c->d_plane_start, &c->d_counters, &c->d_sizes,
+                    &c->d_overflow, &c->d_desc, &c->d_offsets, &c->h_small, &c->h_stage_in, &c->h_stage_out})
+    b->release();
+  for (auto& ev : c->ev)
+    if (ev) cudaEventDestroy(ev);
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  cudaStreamDestroy(c->copy_stream);
+  delete c;
+}
+
+int myyuvb_sync(myyuvb_ctx* c) {
+  if (!c) return fail(MYYUVB_ERR_ARG, "null context");
+  CU(cudaStreamSynchronize(c->stream));
+  return MYYUVB_OK;
+}
+
+void* myyuvb_stream(myyuvb_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+int myyuvb_host_alloc(size_t bytes, void** out) {
+  if (!out) return fail(MYYUVB_ERR_ARG, "null output pointer");
+  CU(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+  return MYYUVB_OK;
+}
+
+void myyuvb_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+// ------------------------------------------------------------------------------------------------
+// device-pointer batch entry points
+// ------------------------------------------------------------------------------------------------
+int myyuvb_xrgb_to_iyuv_batch_dev(myyuvb_ctx* c, const uint8_t* d_bgrx, uint32_t w, uint32_t h, int bottom_up,
+                                  uint32_t n_frames, uint8_t* d_iyuv) {
+  if (!c || !d_bgrx || !d_iyuv) return fail(MYYUVB_ERR_ARG, "null argument");
+  if (w == 0 || h == 0 || (w % 2) || (h % 2)) return fail(MYYUVB_ERR_EVEN, "Error. width and height must be even");
+  if (w % 4) return fail(MYYUVB_ERR_EVEN, "Error. width must be a multiple of 4 (BMP rows are not padded, myyuv_bmp.cpp:130)");
+  if ((uint64_t)w * h * 4 > 0xffffffffull) return fail(MYYUVB_ERR_TOO_LARGE, "Error. image does not fit the format's uint32 sizes");
+  if (((uintptr_t)d_bgrx & 15) || ((uintptr_t)d_iyuv & 3)) return fail(MYYUVB_ERR_ARG, "device buffers must be 16-byte aligned");
+  CU(cudaSetDevice(c->device));
+  launch_xrgb_to_iyuv(d_bgrx, d_iyuv, w, h, bottom_up, n_frames, c->stream);
+  CU(cudaGetLastError());
+  return MYYUVB_OK;
+}
+
+int myyuvb_dct_compress_batch_dev(myyuvb_ctx* c, const uint8_t* d_iyuv, uint32_t w, uint32_t h, const uint8_t quality[3],
+                                  uint32_t n_frames, uint8_t* d_out, uint64_t out_capacity, uint64_t* d_offsets) {
+  if (!c || !d_iyuv || !quality || !d_out || !d_offsets || n_frames == 0) return fail(MYYUVB_ERR_ARG, "null argument");
+  int rc;
+  if ((rc = check_quality(quality))) return rc;
+  if ((rc = check_dims(w, h))) return rc;
+  if ((uintptr_t)d_iyuv & 7) return fail(MYYUVB_ERR_ARG, "device input must be 8-byte aligned");
+  CU(cudaSetDevice(c->device));
+  const FrameGeom g = make_geom(w, h, n_frames);
+  if ((uint64_t)g.tiles_per_frame * n_frames > 0x7fffffffull) return fail(MYYUVB_ERR_TOO_LARGE, "batch too large");
+  Workspace ws;
+  if ((rc = ensure_workspace(c, g, true, &ws))) return rc;
+  QTables qt;
+  make_qtables(quality, &qt);
+  launch_compress(d_iyuv, g, qt, d_out, out_capacity, d_offsets, ws, c->stream);
+  CU(cudaGetLastError());
+  return MYYUVB_OK;
+}
+
+int myyuvb_dct_decompress_batch_dev(myyuvb_ctx* c, const uint8_t* d_payloads, const uint64_t* d_offsets, uint32_t w,
+                                    uint32_t h, const uint8_t quality[3], uint32_t n_frames, uint8_t* d_iyuv) {
+  if (!c || !d_payloads || !d_offsets || !quality || !d_iyuv || n_frames == 0) return fail(MYYUVB_ERR_ARG, "null argument");
+  int rc;
+  if ((rc = check_quality(quality))) return rc;
+  if ((rc = check_dims(w, h))) return rc;
+  if ((uintptr_t)d_iyuv & 7) return fail(MYYUVB_ERR_ARG, "device output must be 8-byte aligned");
+  CU(cudaSetDevice(c->device));
+  const FrameGeom g = make_geom(w, h, n_frames);
+  if ((uint64_t)g.tiles_per_frame * n_frames > 0x7fffffffull) return fail(MYYUVB_ERR_TOO_LARGE, "batch too large");
+  Workspace ws;
+  if ((rc = ensure_workspace(c, g, false, &ws))) return rc;
+  QTables qt;
+  make_qtables(quality, &qt);
+  launch_decompress(d_payloads, d_offsets, g, qt, d_iyuv, ws, c->stream);
+  CU(cudaGetLastError());
+  return MYYUVB_OK;
+}
+
+int myyuvb_batch_status(myyuvb_ctx* c) {
+  if (!c) return fail(MYYUVB_ERR_ARG, "null context");
+  CU(cudaSetDevice(c->device));
+  if (!c->d_counters.p) {
+    CU(cudaStreamSynchronize(c->stream));
+    return MYYUVB_OK;
+  }
+  return read_flags(c);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-pointer single image entry points
+// ------------------------------------------------------------------------------------------------
+int myyuvb_xrgb_to_iyuv(myyuvb_ctx* c, const uint8_t* bgrx, uint32_t w, uint32_t h, int bottom_up, uint8_t* iyuv_out) {
+  if (!c || !bgrx || !iyuv_out) return fail(MYYUVB_ERR_ARG, "null argument");
+  if (w == 0 || h == 0 || (w % 2) || (h % 2)) return fail(MYYUVB_ERR_EVEN, "Error. width and height must be even");
+  CU(cudaSetDevice(c->device));
+  const size_t in_bytes = (size_t)w * h * 4, out_bytes = (size_t)w * h * 3 / 2;
+  int rc;
+  if ((rc = c->d_in.reserve(in_bytes))) return rc;
+  if ((rc = c->d_out.reserve(out_bytes))) return rc;
+  CU(cudaMemcpyAsync(c->d_in.p, bgrx, in_bytes, cudaMemcpyHostToDevice, c->stream));
+  if ((rc = myyuvb_xrgb_to_iyuv_batch_dev(c, c->d_in.as<uint8_t>(), w, h, bottom_up, 1, c->d_out.as<uint8_t>()))) return rc;
+  CU(cudaMemcpyAsync(iyuv_out, c->d_out.p, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return MYYUVB_OK;
+}
+
+int myyuvb_dct_compress(myyuvb_ctx* c, const uint8_t* iyuv, uint32_t w, uint32_t h, const uint8_t quality[3], uint8_t* out,
+                        uint64_t out_capacity, uint32_t* out_size) {
+  if (!c || !iyuv || !quality || !out || !out_size) return fail(MYYUVB_ERR_ARG, "null argument");
+  uint64_t offsets[2];
+  const int rc = myyuvb_dct_compress_batch_host(c, iyuv, w, h, quality, 1, out, out_capacity, offsets);
+  if (rc) return rc;
+  *out_size = (uint32_t)(offsets[1] - offsets[0]);
+  return MYYUVB_OK;
+}
+
+int myyuvb_dct_decompress(myyuvb_ctx* c, const uint8_t* payload, uint32_t payload_size, uint32_t w, uint32_t h,
+                          const uint8_t quality[3], uint8_t* iyuv_out) {
+  if (!c || !payload || !quality || !iyuv_out) return fail(MYYUVB_ERR_ARG, "null argument");
+  // DCTYUV::load's first check (DCT.cpp:132-134) needs no device work
+  if (payload_size <= 12) {
+    int rc;
+    if ((rc = check_quality(quality))) return rc;
+    return fail(MYYUVB_ERR_DCTYUV_SIZE, "DCTYUV load bad size");
+  }
+  const uint64_t offsets[2] = {0, payload_size};
+  return myyuvb_dct_decompress_batch_host(c, payload, offsets, w, h, quality, 1, iyuv_out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-pointer batch entry points: frames are processed in chunks; the H2D copy of chunk i+1 and the D2H
+// copy of chunk i-1 run on the copy stream while chunk i is coded on the compute stream.
+// ------------------------------------------------------------------------------------------------
+int myyuvb_dct_compress_batch_host(myyuvb_ctx* c, const uint8_t* iyuv, uint32_t w, uint32_t h, const uint8_t quality[3],
+                                   uint32_t n_frames, uint8_t* out, uint64_t out_capacity, uint64_t* offsets) {
+  if (!c || !iyuv || !quality || !out || !offsets || n_frames == 0) return fail(MYYUVB_ERR_ARG, "null argument");
+  int rc;
+  if ((rc = check_quality(quality))) return rc;
+  if ((rc = check_dims(w, h))) return rc;
+  CU(cudaSetDevice(c->device));
+  const uint64_t frame_bytes = (uint64_t)w * h * 3 / 2;
+  const uint64_t bound = myyuvb_compress_bound(w, h);
+  // chunk size: ~64 MB of input per chunk, at least one frame
+  const uint32_t per = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(n_frames, (64ull << 20) / frame_bytes));
+  if ((rc = c->d_in.reserve(2 * per * frame_bytes))) return rc;
+  if ((rc = c->d_out.reserve(2 * per * bound))) return rc;
+  if ((rc = c->d_offsets.reserve(2 * (per + 1) * 8))) return rc;
+  if ((rc = c->h_small.reserve(256 + 2 * (per + 1) * 8))) return rc;
+  const bool in_dma = is_pinned_or_device(iyuv), out_dma = is_pinned_or_device(out);
+  if (!in_dma && (rc = c->h_stage_in.reserve(2 * per * frame_bytes))) return rc;
+  uint64_t* h_off = reinterpret_cast<uint64_t*>(c->h_small.as<uint8_t>() + 256);
+  uint64_t written = 0;
+  offsets[0] = 0;
+  const uint32_t n_chunks = (n_frames + per - 1) / per;
+  // software pipeline over chunks: upload(k+1) overlaps code(k); download(k) is issued once sizes are known
+  auto upload = [&](uint32_t k) -> int {
+    const uint32_t f0 = k * per, nf = std::min(per, n_frames - f0), slot = k & 1;
+    const uint8_t* src = iyuv + (uint64_t)f0 * frame_bytes;
+    uint8_t* dst = c->d_in.as<uint8_t>() + (uint64_t)slot * per * frame_bytes;
+    if (!in_dma) {
+      uint8_t* st = c->h_stage_in.as<uint8_t>() + (uint64_t)slot * per * frame_bytes;
+      memcpy(st, src, (size_t)nf * frame_bytes);
+      src = st;
+    }
+    CU(cudaMemcpyAsync(dst, src, (size_t)nf * frame_bytes, cudaMemcpyHostToDevice, c->copy_stream));
+    CU(cudaEventRecord(c->ev[slot], c->copy_stream));
+    return MYYUVB_OK;
+  };
+  if ((rc = upload(0))) return rc;
+  for (uint32_t k = 0; k < n_chunks; k++) {
+    const uint32_t f0 = k * per, nf = std::min(per, n_frames - f0), slot = k & 1;
+    uint8_t* d_src = c->d_in.as<uint8_t>() + (uint64_t)slot * per * frame_bytes;
+    uint8_t* d_dst = c->d_out.as<uint8_t>() + (uint64_t)slot * per * bound;
+    uint64_t* d_off = c->d_offsets.as<uint64_t>() + (uint64_t)slot * (per + 1);
+    CU(cudaStreamWaitEvent(c->stream, c->ev[slot], 0));
+    if ((rc = myyuvb_dct_compress_batch_dev(c, d_src, w, h, quality, nf, d_dst, (uint64_t)per * bound, d_off))) return rc;
+    CU(cudaMemcpyAsync(h_off + (uint64_t)slot * (per + 1), d_off, (size_t)(nf + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaEventRecord(c->ev[2 + slot], c->stream));
+    if (k + 1 < n_chunks) {
+      // the other input slot was last read by chunk k-1, which has been synchronised below
+      if ((rc = upload(k + 1))) return rc;
+    }
+    CU(cudaEventSynchronize(c->ev[2 + slot]));
+    const uint64_t* ho = h_off + (uint64_t)slot * (per + 1);
+    const uint64_t bytes = ho[nf] - ho[0];
+    if (written + bytes > out_capacity) return fail(MYYUVB_ERR_CAPACITY, "Error. output buffer is too small for the compressed data");
+    for (uint32_t i = 0; i <= nf; i++) offsets[f0 + i] = written + (ho[i] - ho[0]);
+    // download on the compute stream: the next chunk's kernels use the other output slot
+    CU(cudaMemcpyAsync(out + written, d_dst + ho[0], (size_t)bytes, cudaMemcpyDeviceToHost, c->stream));
+    (void)out_dma;
+    written += bytes;
+  }
+  return read_flags(c);
+}
+
+int myyuvb_dct_decompress_batch_host(myyuvb_ctx* c, const uint8_t* payloads, const uint64_t* offsets, uint32_t w, uint32_t h,
+                                     const uint8_t quality[3], uint32_t n_frames, uint8_t* iyuv_out) {
+  if (!c || !payloads || !offsets || !quality || !iyuv_out || n_frames == 0) return fail(MYYUVB_ERR_ARG, "null argument");
+  int rc;
+  if ((rc = check_quality(quality))) return rc;
+  if ((rc = check_dims(w, h))) return rc;
+  for (uint32_t f = 0; f < n_frames; f++)
+    if (offsets[f + 1] < offsets[f]) return fail(MYYUVB_ERR_ARG, "frame offsets must be non-decreasing");
+  CU(cudaSetDevice(c->device));
+  const uint64_t frame_bytes = (uint64_t)w * h * 3 / 2;
+  const uint32_t per = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(n_frames, (64ull << 20) / frame_bytes));
+  const uint32_t n_chunks = (n_frames + per - 1) / per;
+  uint64_t max_in = 0;
+  for (uint32_t k = 0; k < n_chunks; k++) {
+    const uint32_t f0 = k * per, nf = std::min(per, n_frames - f0);
+    max_in = std::max(max_in, offsets[f0 + nf] - offsets[f0]);
+  }
+  if ((rc = c->d_in.reserve(2 * (max_in + 16)))) return rc;
+  if ((rc = c->d_out.reserve(2 * per * frame_bytes))) return rc;
+  if ((rc = c->d_offsets.reserve(2 * (per + 1) * 8))) return rc;
+  if ((rc = c->h_small.reserve(256 + 2 * (per + 1) * 8))) return rc;
+  const bool in_dma = is_pinned_or_device(payloads);
+  if (!in_dma && (rc = c->h_stage_in.reserve(2 * (max_in + 16)))) return rc;
+  uint64_t* h_off = reinterpret_cast<uint64_t*>(c->h_small.as<uint8_t>() + 256);
+  const uint64_t in_slot = (max_in + 16) & ~15ull;
+  auto upload = [&](uint32_t k) -> int {
+    const uint32_t f0 = k * per, nf = std::min(per, n_frames - f0), slot = k & 1;
+    const uint64_t beg = offsets[f0], bytes = offsets[f0 + nf] - beg;
+    const uint8_t* src = payloads + beg;
+    if (!in_dma) {
+      uint8_t* st = c->h_stage_in.as<uint8_t>() + (uint64_t)slot * in_slot;
+      memcpy(st, src, (size_t)bytes);
+      src = st;
+    }
+    uint64_t* ho = h_off + (uint64_t)slot * (per + 1);
+    for (uint32_t i = 0; i <= nf; i++) ho[i] = offsets[f0 + i] - beg;
+    CU(cudaMemcpyAsync(c->d_in.as<uint8_t>() + (uint64_t)slot * in_slot, src, (size_t)bytes, cudaMemcpyHostToDevice, c->copy_stream));
+    CU(cudaMemcpyAsync(c->d_offsets.as<uint64_t>() + (uint64_t)slot * (per + 1), ho, (size_t)(nf + 1) * 8, cudaMemcpyHostToDevice,
+                       c->copy_stream));
+    CU(cudaEventRecord(c->ev[slot], c->copy_stream));
+    return MYYUVB_OK;
+  };
+  if ((rc = upload(0))) return rc;
+  for (uint32_t k = 0; k < n_chunks; k++) {
+    const uint32_t f0 = k * per, nf = std::min(per, n_frames - f0), slot = k & 1;
+    uint8_t* d_dst = c->d_out.as<uint8_t>() + (uint64_t)slot * per * frame_bytes;
+    CU(cudaStreamWaitEvent(c->stream, c->ev[slot], 0));
+    if ((rc = myyuvb_dct_decompress_batch_dev(c, c->d_in.as<uint8_t>() + (uint64_t)slot * in_slot,
+                                              c->d_offsets.as<uint64_t>() + (uint64_t)slot * (per + 1), w, h, quality, nf, d_dst)))
+      return rc;
+    CU(cudaMemcpyAsync(iyuv_out + (uint64_t)f0 * frame_bytes, d_dst, (size_t)nf * frame_bytes, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaEventRecord(c->ev[2 + slot], c->stream));
+    if (k + 1 < n_chunks) {
+      // slot (k+1)&1 was used by chunk k-1: wait until its kernels and download are done before overwriting
+      if (k >= 1) CU(cudaEventSynchronize(c->ev[2 + ((k + 1) & 1)]));
+      if ((rc = upload(k + 1))) return rc;
+    }
+  }
+  return read_flags(c);
+}
+
+}  // extern "C"

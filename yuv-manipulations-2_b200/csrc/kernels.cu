@@ -1,0 +1,794 @@
+// kernels.cu -- hand-written sm_100a kernels for myyuv's hot path (XRGB->IYUV, DCT-q compress, decompress).
+//
+// Design (see DESIGN.md for the full rationale):
+//  * The reference's DCT is a plain float C.X.C^T with sequential, UNFUSED multiply/add in a fixed order
+//    (DCT.cpp:232-277) and its results are pinned by golden files, so every product and every sum below
+//    is an individually rounded IEEE binary32 operation: no FMA contraction of mul+add, no tensor cores,
+//    no fast factorisation.  The issue-slot cost is halved with Blackwell's packed FP32x2 instructions:
+//    one thread transforms TWO 8x8 blocks at once, lane .x = block A, lane .y = block B
+//    (mul.rn.f32x2 / fma.rn.f32x2 -> SASS FMUL2 / FFMA2), the 64 DCT constants are immediates.
+//  * ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under -fmad=false (checked with cuobjdump),
+//    which would change results.  The accumulation  acc + p  is therefore issued as fma(p, ONE, acc) with
+//    ONE = 1.0f passed at run time: bit-identical to an add, and not contractible with the producing mul.
+//  * Entropy coding is one thread per block (block_codec.cuh) on coefficients staged in shared memory;
+//    chunk bytes are laid out per tile in shared memory, the tile's global byte offset comes from a
+//    single-pass decoupled look-back over tiles in file order, and the tile is written out coalesced.
+//  * Persistent CTAs take tiles from an atomic ticket, so look-back predecessors are always resident.
+#include "kernels.h"
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "block_codec.cuh"
+
+namespace myyuvb {
+
+thread_local uint64_t g_launches = 0;
+
+// ---------------------------------------------------------------------------------------------------
+// packed FP32x2 helpers
+// ---------------------------------------------------------------------------------------------------
+struct __align__(8) f2 {
+  float x, y;
+};
+typedef unsigned long long u64;
+#define MYB_D __device__ __forceinline__
+#define F2R(v) reinterpret_cast<u64&>(v)
+
+MYB_D f2 dup(float c) { f2 r; r.x = c; r.y = c; return r; }
+MYB_D f2 mul2(f2 a, f2 b) {  // RN(a*b) per lane
+  f2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(F2R(d)) : "l"(F2R(a)), "l"(F2R(b)));
+  return d;
+}
+MYB_D f2 fma2(f2 a, f2 b, f2 c) {  // RN(a*b+c) per lane (only where a true FMA is wanted)
+  f2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(F2R(d)) : "l"(F2R(a)), "l"(F2R(b)), "l"(F2R(c)));
+  return d;
+}
+MYB_D f2 sum2(f2 acc, f2 p, f2 one) { return fma2(p, one, acc); }  // RN(acc+p); see header note on ONE
+MYB_D f2 add2(f2 a, f2 b) {  // plain packed add; only used where neither input is a product
+  f2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(F2R(d)) : "l"(F2R(a)), "l"(F2R(b)));
+  return d;
+}
+MYB_D f2 add2_rz(f2 a, f2 b) {
+  f2 d;
+  asm("add.rz.f32x2 %0, %1, %2;" : "=l"(F2R(d)) : "l"(F2R(a)), "l"(F2R(b)));
+  return d;
+}
+// round half away from zero to int32 (std::round, DCT.cpp:274,360): trunc(RZ(v + copysign(0.5, v))).
+// RZ(|v|+0.5) lies in [floor(|v|+0.5), |v|+0.5], so its truncation is floor(|v|+0.5) exactly.
+MYB_D f2 half_like(f2 v) {
+  f2 h;
+  h.x = __int_as_float((__float_as_int(v.x) & 0x80000000) | 0x3f000000);
+  h.y = __int_as_float((__float_as_int(v.y) & 0x80000000) | 0x3f000000);
+  return h;
+}
+
+// the reference's 8x8 DCT matrix, [frequency][sample] (DCT.cpp:221-230) -- immediates after unrolling
+MYB_D constexpr float dct_c(int i) {
+  constexpr float t[64] = {
+#include "dct_matrix.inc"
+  };
+  return t[i];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// geometry
+// ---------------------------------------------------------------------------------------------------
+FrameGeom make_geom(uint32_t width, uint32_t height, uint32_t n_frames) {
+  FrameGeom g{};
+  g.width = width; g.height = height; g.n_frames = n_frames;
+  g.pw[0] = width; g.ph[0] = height;
+  g.pw[1] = g.pw[2] = width / 2; g.ph[1] = g.ph[2] = height / 2;
+  g.plane_off[0] = 0;
+  g.plane_off[1] = (uint64_t)width * height;
+  g.plane_off[2] = (uint64_t)width * height * 5 / 4;
+  g.frame_bytes = (uint64_t)width * height * 3 / 2;
+  g.tiles_per_frame = 0; g.nblk_frame = 0;
+  for (int p = 0; p < 3; p++) {
+    g.bw[p] = g.pw[p] / 8;
+    g.nblk[p] = g.bw[p] * (g.ph[p] / 8);
+    g.tiles[p] = (g.nblk[p] + kTileBlocks - 1) / kTileBlocks;
+    g.tiles_per_frame += g.tiles[p];
+    g.nblk_frame += g.nblk[p];
+  }
+  return g;
+}
+
+struct TileCoord {
+  uint32_t frame, plane, k0, nblk;   // first block of the tile inside its plane, blocks in the tile
+  uint32_t first_tile_of_plane;      // global tile index of the plane's first tile
+};
+
+MYB_D TileCoord tile_coord(const FrameGeom& g, uint32_t tile) {
+  TileCoord t;
+  t.frame = tile / g.tiles_per_frame;
+  uint32_t r = tile - t.frame * g.tiles_per_frame;
+  uint32_t base = t.frame * g.tiles_per_frame;
+  t.plane = 0;
+  if (r >= g.tiles[0]) { r -= g.tiles[0]; base += g.tiles[0]; t.plane = 1; }
+  if (t.plane == 1 && r >= g.tiles[1]) { r -= g.tiles[1]; base += g.tiles[1]; t.plane = 2; }
+  t.k0 = r * kTileBlocks;
+  const uint32_t left = g.nblk[t.plane] - t.k0;
+  t.nblk = left < (uint32_t)kTileBlocks ? left : (uint32_t)kTileBlocks;
+  t.first_tile_of_plane = base;
+  return t;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// decoupled look-back over tile_status words: [63:62] 0 = empty, 1 = tile aggregate, 2 = inclusive prefix;
+// [61:0] value.  Called by warp 0 only.  `first` = first tile of the scan domain (its exclusive prefix is 0).
+// Returns the tile's exclusive prefix.
+// ---------------------------------------------------------------------------------------------------
+constexpr u64 kAgg = 1ull << 62, kPre = 2ull << 62, kValMask = (1ull << 62) - 1;
+
+MYB_D u64 ld_status(const uint64_t* p) { return *reinterpret_cast<const volatile u64*>(p); }
+MYB_D void st_status(uint64_t* p, u64 v) { *reinterpret_cast<volatile u64*>(p) = v; }
+
+MYB_D u64 lookback(uint64_t* status, uint32_t tile, uint32_t first, u64 aggregate, int lane) {
+  if (tile == first) {
+    if (lane == 0) st_status(status + tile, kPre | aggregate);
+    return 0;
+  }
+  if (lane == 0) st_status(status + tile, kAgg | aggregate);
+  u64 excl = 0;
+  int64_t idx = (int64_t)tile - 1;
+  while (true) {
+    const int64_t j = idx - lane;
+    u64 v = kPre;  // tiles before the domain act as a zero prefix
+    if (j >= (int64_t)first) v = ld_status(status + j);
+    const unsigned fl = (unsigned)(v >> 62);
+    const unsigned pre = __ballot_sync(0xffffffffu, fl == 2);
+    const unsigned empty = __ballot_sync(0xffffffffu, fl == 0);
+    unsigned upto = 0xffffffffu;
+    if (pre) upto = (2u << (__ffs(pre) - 1)) - 1u;  // lanes up to and including the first prefix holder
+    if (empty & upto) continue;                     // a needed predecessor has not published yet
+    u64 part = (upto >> lane) & 1u ? (v & kValMask) : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    excl += part;
+    if (pre) break;
+    idx -= 32;
+  }
+  if (lane == 0) st_status(status + tile, kPre | ((excl + aggregate) & kValMask));
+  return excl;
+}
+
+// CTA-wide exclusive scan of one value per thread (kCtaThreads = 128 -> 4 warps); returns exclusive
+// prefix, *total gets the CTA sum.  Contains two __syncthreads.
+MYB_D uint32_t cta_exclusive_scan(uint32_t v, uint32_t* warp_sums /* [4] shared */, uint32_t* total) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += n;
+  }
+  if (lane == 31) warp_sums[wid] = inc;
+  __syncthreads();
+  uint32_t base = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < kCtaThreads / 32; w++) {
+    const uint32_t s = warp_sums[w];
+    if (w < wid) base += s;
+    tot += s;
+  }
+  __syncthreads();
+  *total = tot;
+  return base + inc - v;
+}
+
+// Copy n bytes from shared memory (4-byte aligned base) to global memory at arbitrary alignment with
+// coalesced 32-bit stores.
+MYB_D void copy_smem_to_global(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint32_t n) {
+  const uint32_t head = min((uint32_t)((4 - ((uintptr_t)dst & 3)) & 3), n);
+  if (threadIdx.x < head) dst[threadIdx.x] = src[threadIdx.x];
+  const uint32_t words = (n - head) >> 2;
+  uint32_t* dw = reinterpret_cast<uint32_t*>(dst + head);
+  const uint32_t* sw = reinterpret_cast<const uint32_t*>(src);
+  const uint32_t sh = head * 8;  // source is `head` bytes off word alignment
+  for (uint32_t w = threadIdx.x; w < words; w += kCtaThreads) {
+    const uint32_t lo = sw[w], hi = sw[w + 1];  // sw[w+1] is inside the padded staging buffer
+    dw[w] = sh ? __funnelshift_r(lo, hi, sh) : lo;
+  }
+  const uint32_t done = head + (words << 2);
+  if (threadIdx.x < n - done) dst[done + threadIdx.x] = src[done + threadIdx.x];
+}
+
+// ===================================================================================================
+// Colour conversion  (myyuv_yuv.cpp:34-52, :88-128; row flip of myyuv_bmp.cpp:95-98 folded into addressing)
+// One thread = 4 pixels x 2 rows: two 128-bit loads, two 32-bit Y stores, one 16-bit U and V store.
+// ===================================================================================================
+MYB_D void pixel_yuv(uint32_t px, uint32_t& y, uint32_t& cb, uint32_t& cr) {
+  const float B = (float)(px & 0xff), G = (float)((px >> 8) & 0xff), R = (float)((px >> 16) & 0xff);
+  const float Y = __fadd_rn(__fadd_rn(__fmul_rn(0.299f, R), __fmul_rn(0.587f, G)), __fmul_rn(0.114f, B));
+  y = (uint32_t)__float2int_rz(Y) & 0xff;
+  // (uint8_t)(float) of a possibly negative value is cvttss2si + low byte on the reference's x86-64 build,
+  // then "+ 128" and the store to uint8_t wrap again (myyuv_yuv.cpp:48-49)
+  cb = (uint32_t)(__float2int_rz(__fmul_rn(__fsub_rn(B, Y), 0.564f)) + 128) & 0xff;
+  cr = (uint32_t)(__float2int_rz(__fmul_rn(__fsub_rn(R, Y), 0.713f)) + 128) & 0xff;
+}
+
+__global__ void __launch_bounds__(256) xrgb_to_iyuv_kernel(const uint8_t* __restrict__ bgrx, uint8_t* __restrict__ iyuv,
+                                                            uint32_t w, uint32_t h, int bottom_up, uint32_t n_frames) {
+  const uint32_t qw = w >> 2;                       // 4-pixel groups per row
+  const uint64_t per_frame = (uint64_t)qw * (h >> 1);
+  const uint64_t total = per_frame * n_frames;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t f = (uint32_t)(i / per_frame);
+    const uint32_t r = (uint32_t)(i - (uint64_t)f * per_frame);
+    const uint32_t row = (r / qw) * 2, col = (r % qw) * 4;
+    const uint8_t* src = bgrx + (uint64_t)f * w * h * 4;
+    uint8_t* dst = iyuv + (uint64_t)f * w * h * 3 / 2;
+    const uint32_t fr0 = bottom_up ? (h - 1 - row) : row, fr1 = bottom_up ? (h - 2 - row) : row + 1;
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(src + ((uint64_t)fr0 * w + col) * 4));
+    const uint4 b = __ldg(reinterpret_cast<const uint4*>(src + ((uint64_t)fr1 * w + col) * 4));
+    uint32_t y0[4], y1[4], cb0[4], cb1[4], cr0[4], cr1[4];
+    pixel_yuv(a.x, y0[0], cb0[0], cr0[0]); pixel_yuv(a.y, y0[1], cb0[1], cr0[1]);
+    pixel_yuv(a.z, y0[2], cb0[2], cr0[2]); pixel_yuv(a.w, y0[3], cb0[3], cr0[3]);
+    pixel_yuv(b.x, y1[0], cb1[0], cr1[0]); pixel_yuv(b.y, y1[1], cb1[1], cr1[1]);
+    pixel_yuv(b.z, y1[2], cb1[2], cr1[2]); pixel_yuv(b.w, y1[3], cb1[3], cr1[3]);
+    // divide_roundnearest(v, 4) on each sample, sum of four stored to uint8_t (wraps) -- myyuv_yuv.cpp:114-115
+    const uint32_t u0 = (((cb0[0] + 2) >> 2) + ((cb0[1] + 2) >> 2) + ((cb1[0] + 2) >> 2) + ((cb1[1] + 2) >> 2)) & 0xff;
+    const uint32_t u1 = (((cb0[2] + 2) >> 2) + ((cb0[3] + 2) >> 2) + ((cb1[2] + 2) >> 2) + ((cb1[3] + 2) >> 2)) & 0xff;
+    const uint32_t v0 = (((cr0[0] + 2) >> 2) + ((cr0[1] + 2) >> 2) + ((cr1[0] + 2) >> 2) + ((cr1[1] + 2) >> 2)) & 0xff;
+    const uint32_t v1 = (((cr0[2] + 2) >> 2) + ((cr0[3] + 2) >> 2) + ((cr1[2] + 2) >> 2) + ((cr1[3] + 2) >> 2)) & 0xff;
+    *reinterpret_cast<uint32_t*>(dst + (uint64_t)row * w + col) = y0[0] | (y0[1] << 8) | (y0[2] << 16) | (y0[3] << 24);
+    *reinterpret_cast<uint32_t*>(dst + (uint64_t)(row + 1) * w + col) = y1[0] | (y1[1] << 8) | (y1[2] << 16) | (y1[3] << 24);
+    const uint64_t k = ((uint64_t)col + (uint64_t)row * w / 2) / 2;  // myyuv_yuv.cpp:120
+    *reinterpret_cast<uint16_t*>(dst + (uint64_t)w * h + k) = (uint16_t)(u0 | (u1 << 8));
+    *reinterpret_cast<uint16_t*>(dst + (uint64_t)w * h * 5 / 4 + k) = (uint16_t)(v0 | (v1 << 8));
+  }
+}
+
+void launch_xrgb_to_iyuv(const uint8_t* d_bgrx, uint8_t* d_iyuv, uint32_t w, uint32_t h, int bottom_up, uint32_t n_frames,
+                         cudaStream_t s) {
+  const uint64_t total = (uint64_t)(w / 4) * (h / 2) * n_frames;
+  if (total == 0) return;
+  const uint64_t want = (total + 255) / 256;
+  const int grid = (int)(want < 148ull * 32 ? want : 148ull * 32);
+  xrgb_to_iyuv_kernel<<<grid, 256, 0, s>>>(d_bgrx, d_iyuv, w, h, bottom_up, n_frames);
+  g_launches++;
+}
+
+// ===================================================================================================
+// Compression
+// ===================================================================================================
+constexpr int kStageBytes = 12 * 1024;                 // shared-memory staging of one tile's chunk bytes
+constexpr int kFastSyms = 16;                          // distinct symbols handled with shared-memory scratch
+using FastScratch = HuffScratch<kFastSyms>;
+using BigScratch = HuffScratch<64>;
+
+struct EncSmem {
+  uint16_t zz[64][kTileBlocks];                        // quantised coefficients, zigzag order; later slot ids
+  uint8_t hs_bytes[FastScratch::kBytes][kCtaThreads];
+  int16_t hs_syms[FastScratch::kSyms][kCtaThreads];
+  alignas(16) uint8_t stage[kStageBytes + 8];
+  alignas(4) uint8_t lbound[kTileBlocks];              // upper bound (multiple of 8) of the message length
+  alignas(4) uint8_t csize[kTileBlocks];
+  uint32_t warp_sums[4];
+  uint32_t tile;
+  u64 base;
+};
+
+struct ZShared {  // accessor of one block's column in EncSmem::zz
+  uint16_t* col;
+  MYB_D int get(int i) const { return (int)(int16_t)col[i * kTileBlocks]; }
+  MYB_D void set(int i, int v) { col[i * kTileBlocks] = (uint16_t)v; }
+};
+
+struct EncParams {
+  const uint8_t* src;
+  uint8_t* out;
+  uint64_t out_cap;
+  FrameGeom g;
+  Workspace ws;
+  uint32_t total_tiles;
+  float one;
+};
+
+// forward DCT + quantisation of two blocks held as f2 x[64] (row-major), results to zz[*][b0], zz[*][b0+1]
+MYB_D void fdct_quant_pair(f2 (&x)[64], const QTables& qt, int plane, float onef, uint16_t (*zz)[kTileBlocks], int b0,
+                           uint32_t (&gor)[8]) {
+  const f2 ONE = dup(onef);
+  // T = C . X  (DCT.cpp:232-242): per column c, T[a][c] = sum_k C[a][k] * X[k][c], k ascending
+#pragma unroll
+  for (int c = 0; c < 8; c++) {
+    f2 t[8];
+#pragma unroll
+    for (int a = 0; a < 8; a++) {
+      f2 acc = mul2(x[c], dup(dct_c(a * 8)));
+#pragma unroll
+      for (int k = 1; k < 8; k++) acc = sum2(acc, mul2(x[k * 8 + c], dup(dct_c(a * 8 + k))), ONE);
+      t[a] = acc;
+    }
+#pragma unroll
+    for (int a = 0; a < 8; a++) x[a * 8 + c] = t[a];
+  }
+  // Y = T . C^T (DCT.cpp:244-254): Y[a][b] = sum_k T[a][k] * C[b][k]
+#pragma unroll
+  for (int a = 0; a < 8; a++) {
+    f2 t[8];
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+      f2 acc = mul2(x[a * 8], dup(dct_c(b * 8)));
+#pragma unroll
+      for (int k = 1; k < 8; k++) acc = sum2(acc, mul2(x[a * 8 + k], dup(dct_c(b * 8 + k))), ONE);
+      t[b] = acc;
+    }
+#pragma unroll
+    for (int b = 0; b < 8; b++) x[a * 8 + b] = t[b];
+  }
+  // coef = (int16) round(Y / q) (DCT.cpp:274).  The divisor is an integer 1..255, so one Newton step on
+  // q0 = Y * RN(1/q) is the correctly rounded quotient: rem = Y - q*q0 is exact, and Y/q is never closer
+  // than ulp/510 to a rounding boundary while the step's error is < 2^-23 ulp (DESIGN.md "Exact division").
+  constexpr int zz_of[64] = {0,  1,  5,  6,  14, 15, 27, 28, 2,  4,  7,  13, 16, 26, 29, 42, 3,  8,  12, 17, 25, 30,
+                             41, 43, 9,  11, 18, 24, 31, 40, 44, 53, 10, 19, 23, 32, 39, 45, 52, 54, 20, 22, 33, 38,
+                             46, 51, 55, 60, 21, 34, 37, 47, 50, 56, 59, 61, 35, 36, 48, 49, 57, 58, 62, 63};
+#pragma unroll
+  for (int g8 = 0; g8 < 8; g8++) gor[g8] = 0;
+#pragma unroll
+  for (int i = 0; i < 64; i++) {
+    const f2 r = dup(qt.rq[plane][i]);
+    const f2 nq = dup(-qt.q[plane][i]);
+    const f2 q0 = mul2(x[i], r);
+    const f2 rem = fma2(nq, q0, x[i]);
+    const f2 q1 = fma2(rem, r, q0);
+    const f2 t = add2_rz(q1, half_like(q1));
+    const uint32_t na = (uint32_t)__float2int_rz(t.x), nb = (uint32_t)__float2int_rz(t.y);
+    const uint32_t packed = __byte_perm(na, nb, 0x5410);  // low halves: A | B << 16
+    const int zi = zz_of[i];
+    *reinterpret_cast<uint32_t*>(&zz[zi][b0]) = packed;
+    gor[zi >> 3] |= packed;
+  }
+}
+
+// blocks with more than kFastSyms distinct symbols: same code on per-thread local-memory scratch, kept out of line
+__device__ __noinline__ HuffPlan plan_big(ZShared z, int L, BigScratch bs) { return huff_plan<64>(z, L, bs); }
+__device__ __noinline__ void emit_big(ZShared z, HuffPlan pl, BigScratch bs, uint8_t* dst) { huff_emit<64>(z, pl, bs, dst); }
+
+__global__ void __launch_bounds__(kCtaThreads, 3)
+    dct_compress_kernel(const __grid_constant__ EncParams P, const __grid_constant__ QTables qt) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  EncSmem& sm = *reinterpret_cast<EncSmem*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const FrameGeom& g = P.g;
+
+  while (true) {
+    if (tid == 0) sm.tile = atomicAdd(&P.ws.counters[0], 1u);
+    __syncthreads();
+    const uint32_t tile = sm.tile;
+    if (tile >= P.total_tiles) break;
+    const TileCoord tc = tile_coord(g, tile);
+    const int plane = (int)tc.plane;
+    const uint32_t pw = g.pw[plane], bw = g.bw[plane];
+    const uint8_t* plane_src = P.src + (uint64_t)tc.frame * g.frame_bytes + g.plane_off[plane];
+
+    // ---- phase A: load two blocks per thread, forward DCT, quantise, coefficients to shared memory ----
+    {
+      const int b0 = 2 * tid;
+      f2 x[64];
+      uint32_t raw[2][16];
+#pragma unroll
+      for (int s = 0; s < 2; s++) {
+        const uint32_t b = (uint32_t)b0 + s;
+        if (b < tc.nblk) {
+          const uint32_t k = tc.k0 + b;
+          const uint32_t by = k / bw, bx = k - by * bw;
+          const uint8_t* p = plane_src + (uint64_t)by * 8 * pw + (uint64_t)bx * 8;
+#pragma unroll
+          for (int r = 0; r < 8; r++) {
+            const uint2 v = __ldg(reinterpret_cast<const uint2*>(p + (uint64_t)r * pw));
+            raw[s][2 * r] = v.x;
+            raw[s][2 * r + 1] = v.y;
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < 16; r++) raw[s][r] = 0x80808080u;
+        }
+      }
+      // (float)px - 128 (DCT.cpp:303): 0x4B000000 | px is the float 2^23 + px; subtracting 2^23 + 128 is exact
+      const f2 bias = dup(-8388736.0f);
+#pragma unroll
+      for (int wd = 0; wd < 16; wd++) {
+#pragma unroll
+        for (int bt = 0; bt < 4; bt++) {
+          f2 v;
+          v.x = __uint_as_float(__byte_perm(raw[0][wd], 0x4B000000u, 0x7440 + bt));
+          v.y = __uint_as_float(__byte_perm(raw[1][wd], 0x4B000000u, 0x7440 + bt));
+          x[wd * 4 + bt] = add2(v, bias);
+        }
+      }
+      uint32_t gor[8];
+      fdct_quant_pair(x, qt, plane, P.one, sm.zz, b0, gor);
+      // upper bound of the message length per block: highest group of 8 zigzag positions with a non-zero
+      int la = 0, lb = 0;
+#pragma unroll
+      for (int g8 = 0; g8 < 8; g8++) {
+        if (gor[g8] & 0xffffu) la = 8 * (g8 + 1);
+        if (gor[g8] >> 16) lb = 8 * (g8 + 1);
+      }
+      *reinterpret_cast<uint16_t*>(&sm.lbound[b0]) = (uint16_t)(la | (lb << 8));
+    }
+    __syncthreads();
+
+    // ---- phase B: one block per thread, two passes in raster order; chunk bytes staged in tile order ----
+    FastScratch fs{&sm.hs_bytes[0][tid], &sm.hs_syms[0][tid], kCtaThreads};
+    uint8_t* const overflow = P.ws.overflow + (uint64_t)blockIdx.x * 65536u;
+    uint32_t carried = 0;  // bytes staged by earlier passes
+#pragma unroll 1
+    for (int pass = 0; pass < kTileBlocks / kCtaThreads; pass++) {
+      const int blk = pass * kCtaThreads + tid;
+      const bool live = (uint32_t)blk < tc.nblk;
+      ZShared z{&sm.zz[0][blk]};
+      HuffPlan pl;
+      pl.n = 0;
+      bool big = false;
+      uint8_t lbytes[BigScratch::kBytes];
+      int16_t lsyms[BigScratch::kSyms];
+      BigScratch bs{lbytes, lsyms, 1};
+      uint32_t size = 0;
+      if (live) {
+        int L = sm.lbound[blk];
+        while (L > 0 && z.get(L - 1) == 0) L--;  // exact message length (Huffman.cpp:184-190)
+        pl = huff_plan<kFastSyms>(z, L, fs);
+        if (pl.n < 0) {
+          big = true;
+          pl = plan_big(z, L, bs);
+        }
+        size = (uint32_t)pl.size();
+        sm.csize[blk] = (uint8_t)size;
+      }
+      uint32_t pass_total;
+      const uint32_t off = carried + cta_exclusive_scan(size, sm.warp_sums, &pass_total);
+      if (live) {
+        uint8_t* dst = (off + size <= (uint32_t)kStageBytes) ? &sm.stage[off] : overflow + off;
+        if (big) emit_big(z, pl, bs, dst);
+        else huff_emit<kFastSyms>(z, pl, fs, dst);
+      }
+      carried += pass_total;
+    }
+    __syncthreads();
+
+    // ---- tile offset: decoupled look-back over all tiles of the batch in file order ----
+    if (wid == 0) {
+      const u64 excl = lookback(P.ws.tile_status, tile, 0, carried, lane);
+      if (lane == 0) {
+        sm.base = excl;
+        if (tc.k0 == 0) P.ws.plane_start[tc.frame * 3 + plane] = excl;               // code bytes before this plane
+        if (tile == P.total_tiles - 1) P.ws.plane_start[g.n_frames * 3] = excl + carried;
+      }
+    }
+    __syncthreads();
+    // chunk sizes go to a linear side array; finalize_frames_kernel moves them behind the plane headers,
+    // whose position depends on the (data dependent) size of the previous planes
+    {
+      const uint64_t gblk = (uint64_t)tc.frame * g.nblk_frame + (plane > 0 ? g.nblk[0] : 0) + (plane > 1 ? g.nblk[1] : 0) + tc.k0;
+      for (uint32_t b = tid; b < tc.nblk; b += kCtaThreads) P.ws.chunk_sizes[gblk + b] = sm.csize[b];
+    }
+    // content bytes: absolute position = fixed part (headers + size arrays up to this plane) + code bytes before
+    {
+      uint32_t fixed = 12 + 8 * (plane + 1) + g.nblk[0] + (plane > 0 ? g.nblk[1] : 0) + (plane > 1 ? g.nblk[2] : 0);
+      const u64 pos = (u64)tc.frame * (36 + g.nblk_frame) + fixed + sm.base;
+      if (pos + carried > P.out_cap) {
+        if (tid == 0) atomicOr(&P.ws.counters[1], kFlagCapacity);
+      } else {
+        const uint32_t in_smem = carried < (uint32_t)kStageBytes ? carried : (uint32_t)kStageBytes;
+        // staged bytes beyond the last whole chunk that fits in shared memory live in the overflow area;
+        // chunks never straddle, so copy [0, split) from shared memory and [split, carried) from global
+        uint32_t split = in_smem;
+        if (carried > (uint32_t)kStageBytes) {
+          // recompute the split point: first chunk whose end exceeds kStageBytes starts the overflow part
+          // (tile order = raster order, offsets are the running sum of csize)
+          if (tid == 0) {
+            uint32_t run = 0, b = 0;
+            while (b < tc.nblk && run + sm.csize[b] <= (uint32_t)kStageBytes) run += sm.csize[b++];
+            sm.warp_sums[0] = run;
+          }
+          __syncthreads();
+          split = sm.warp_sums[0];
+        }
+        copy_smem_to_global(P.out + pos, sm.stage, split);
+        for (uint32_t i = split + tid; i < carried; i += kCtaThreads) P.out[pos + i] = overflow[i];
+      }
+    }
+    __syncthreads();  // shared memory is reused by the next tile
+  }
+}
+
+// After the main kernel: one CTA per frame writes the frame's headers and moves the chunk sizes into place.
+__global__ void __launch_bounds__(256) finalize_frames_kernel(const __grid_constant__ EncParams P, uint64_t* __restrict__ offsets) {
+  const FrameGeom& g = P.g;
+  const uint32_t f = blockIdx.x;
+  const uint64_t* ps = P.ws.plane_start + (uint64_t)f * 3;
+  const u64 frame_pos = (u64)f * (36 + g.nblk_frame) + ps[0];
+  const u64 next_pos = (u64)(f + 1) * (36 + g.nblk_frame) + ps[3];
+  if (threadIdx.x == 0) {
+    offsets[f] = frame_pos;
+    if (f == g.n_frames - 1) offsets[f + 1] = next_pos;
+  }
+  if (next_pos > P.out_cap) {
+    if (threadIdx.x == 0) atomicOr(&P.ws.counters[1], kFlagCapacity);
+    return;
+  }
+  uint8_t* out = P.out + frame_pos;
+  u64 ppos = 12, sidx = (u64)f * g.nblk_frame;
+  for (int p = 0; p < 3; p++) {
+    const uint32_t content = (uint32_t)(ps[p + 1] - ps[p]);
+    const uint32_t n = g.nblk[p];
+    if (threadIdx.x < 12) {  // planes_sizes[p], n_chunks, content_size -- byte stores, frames are not aligned
+      const uint32_t field = threadIdx.x >> 2, byte = threadIdx.x & 3;
+      const uint32_t val = field == 0 ? 8 + n + content : field == 1 ? n : content;
+      uint8_t* dst = field == 0 ? out + 4 * p : out + ppos + 4 * (field - 1);
+      dst[byte] = (uint8_t)(val >> (8 * byte));
+    }
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) out[ppos + 8 + i] = P.ws.chunk_sizes[sidx + i];
+    ppos += 8 + (u64)n + content;
+    sidx += n;
+  }
+}
+
+int codec_grid_size(int device, bool encoder) {
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  (void)encoder;
+  return sms * 3;
+}
+
+// ===================================================================================================
+// Decompression
+// ===================================================================================================
+constexpr int kDecStageBytes = 8 * 1024;
+struct DecSmem {
+  float coef[64][kTileBlocks];        // dequantised coefficients B[k][c] (row-major index), per block column
+  uint8_t stage[kDecStageBytes];      // the tile's chunk bytes
+  uint32_t boff[kTileBlocks];         // chunk offset of each block inside the tile
+  alignas(4) uint8_t csize[kTileBlocks];
+  uint8_t zigzag[64];
+  float q[64];
+  uint32_t warp_sums[4];
+  uint32_t tile;
+  u64 base;
+};
+
+struct DecParams {
+  const uint8_t* payloads;
+  const uint64_t* offsets;
+  uint8_t* dst;
+  FrameGeom g;
+  Workspace ws;
+  uint32_t total_tiles;
+  float one;
+};
+
+// Reads and checks the payload headers of every frame (DCTYUV::load, DCT.cpp:130-159; DCTYUVPlane::load :39-62)
+__global__ void parse_payload_kernel(const __grid_constant__ DecParams P) {
+  const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= P.g.n_frames) return;
+  PlaneDesc* desc = reinterpret_cast<PlaneDesc*>(P.ws.plane_desc) + (uint64_t)f * 3;
+  const u64 beg = P.offsets[f], size = P.offsets[f + 1] - beg;
+  const uint8_t* pl = P.payloads + beg;
+  auto rd32 = [&](u64 o) { return (uint32_t)pl[o] | ((uint32_t)pl[o + 1] << 8) | ((uint32_t)pl[o + 2] << 16) | ((uint32_t)pl[o + 3] << 24); };
+  for (int p = 0; p < 3; p++) desc[p].ok = 0;
+  if (size <= 12) { atomicOr(&P.ws.counters[1], kFlagDctYuvSize); return; }
+  u64 psz[3], tot = 12;
+  for (int p = 0; p < 3; p++) { psz[p] = rd32(4 * p); tot += psz[p]; }
+  if (size < tot) { atomicOr(&P.ws.counters[1], kFlagDctYuvSize); return; }
+  u64 ppos = 12;
+  for (int p = 0; p < 3; p++) {
+    if (psz[p] <= 8) { atomicOr(&P.ws.counters[1], kFlagPlaneSize); return; }
+    const uint32_t n = rd32(ppos), content = rd32(ppos + 4);
+    if (n == 0 || content == 0 || psz[p] < 8ull + n + content || n < P.g.nblk[p]) {
+      atomicOr(&P.ws.counters[1], kFlagPlaneSize);
+      return;
+    }
+    desc[p].sizes_off = beg + ppos + 8;
+    desc[p].content_off = beg + ppos + 8 + n;
+    desc[p].content_size = content;
+    desc[p].ok = 1;
+    ppos += psz[p];
+  }
+}
+
+// inverse DCT of two blocks: x = B (dequantised), D = C^T . B, P = D . C (DCT.cpp:333-334, :256-266, :232-242)
+MYB_D void idct_pair(f2 (&x)[64], float onef) {
+  const f2 ONE = dup(onef);
+#pragma unroll
+  for (int c = 0; c < 8; c++) {  // D[a][c] = sum_k C[k][a] * B[k][c]
+    f2 t[8];
+#pragma unroll
+    for (int a = 0; a < 8; a++) {
+      f2 acc = mul2(x[c], dup(dct_c(a)));
+#pragma unroll
+      for (int k = 1; k < 8; k++) acc = sum2(acc, mul2(x[k * 8 + c], dup(dct_c(k * 8 + a))), ONE);
+      t[a] = acc;
+    }
+#pragma unroll
+    for (int a = 0; a < 8; a++) x[a * 8 + c] = t[a];
+  }
+#pragma unroll
+  for (int a = 0; a < 8; a++) {  // P[a][b] = sum_k D[a][k] * C[k][b]
+    f2 t[8];
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+      f2 acc = mul2(x[a * 8], dup(dct_c(b)));
+#pragma unroll
+      for (int k = 1; k < 8; k++) acc = sum2(acc, mul2(x[a * 8 + k], dup(dct_c(k * 8 + b))), ONE);
+      t[b] = acc;
+    }
+#pragma unroll
+    for (int b = 0; b < 8; b++) x[a * 8 + b] = t[b];
+  }
+}
+
+__global__ void __launch_bounds__(kCtaThreads, 3)
+    dct_decompress_kernel(const __grid_constant__ DecParams P, const __grid_constant__ QTables qt) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  DecSmem& sm = *reinterpret_cast<DecSmem*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const FrameGeom& g = P.g;
+  if (tid < 64) {
+    constexpr uint8_t zz[64] = {MYB_ZIGZAG_LIST};
+    sm.zigzag[tid] = zz[tid];
+  }
+  int q_plane = -1;
+
+  while (true) {
+    __syncthreads();  // previous tile done with shared memory (and zigzag table visible)
+    if (tid == 0) sm.tile = atomicAdd(&P.ws.counters[0], 1u);
+    __syncthreads();
+    const uint32_t tile = sm.tile;
+    if (tile >= P.total_tiles) break;
+    const TileCoord tc = tile_coord(g, tile);
+    const int plane = (int)tc.plane;
+    const PlaneDesc d = reinterpret_cast<const PlaneDesc*>(P.ws.plane_desc)[(uint64_t)tc.frame * 3 + plane];
+    if (!d.ok) continue;  // header error already flagged by parse_payload_kernel (uniform per CTA)
+    if (q_plane != plane) {
+      if (tid < 64) sm.q[tid] = qt.q[plane][tid];
+      q_plane = plane;
+    }
+    // chunk sizes of the tile, CTA scan, plane-local look-back -> byte offset of the tile inside content[]
+    const uint8_t* sizes = P.payloads + d.sizes_off + tc.k0;
+    uint32_t my = 0;
+    {
+      const uint32_t b = 2 * tid;
+      uint32_t s0 = 0, s1 = 0;
+      if (b < tc.nblk) s0 = sizes[b];
+      if (b + 1 < tc.nblk) s1 = sizes[b + 1];
+      sm.csize[b] = (uint8_t)s0;
+      sm.csize[b + 1] = (uint8_t)s1;
+      my = s0 + s1;
+    }
+    uint32_t total;
+    const uint32_t pair_off = cta_exclusive_scan(my, sm.warp_sums, &total);
+    if (wid == 0) {
+      const u64 excl = lookback(P.ws.tile_status, tile, tc.first_tile_of_plane, total, lane);
+      if (lane == 0) sm.base = excl;
+    }
+    // zero the coefficient tile while warp 0 looks back
+    {
+      float4* c4 = reinterpret_cast<float4*>(&sm.coef[0][0]);
+      for (int i = tid; i < 64 * kTileBlocks / 4; i += kCtaThreads) c4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+    const u64 base = sm.base;
+    const bool tile_ok = base + total <= d.content_size;  // chunks must lie inside content[] (UB in the reference)
+    if (!tile_ok) {
+      if (tid == 0) atomicOr(&P.ws.counters[1], kFlagHuffman);
+      continue;
+    }
+    // stage the tile's chunk bytes in shared memory (coalesced byte loads; the global offset is arbitrary)
+    const uint8_t* content = P.payloads + d.content_off + base;
+    {
+      const uint32_t n = total < (uint32_t)kDecStageBytes ? total : (uint32_t)kDecStageBytes;
+      for (uint32_t i = tid; i < n; i += kCtaThreads) sm.stage[i] = __ldg(content + i);
+    }
+    sm.boff[2 * tid] = pair_off;
+    sm.boff[2 * tid + 1] = pair_off + sm.csize[2 * tid];
+    __syncthreads();
+
+    // ---- phase 1: one block per thread: canonical Huffman decode + dequantise into shared memory ----
+#pragma unroll 1
+    for (int pass = 0; pass < kTileBlocks / kCtaThreads; pass++) {
+      const int blk = pass * kCtaThreads + tid;
+      if ((uint32_t)blk < tc.nblk) {
+        const uint32_t off = sm.boff[blk], size = sm.csize[blk];
+        const uint8_t* chunk = (off + size <= (uint32_t)kDecStageBytes) ? &sm.stage[off] : content + off;
+        float* col = &sm.coef[0][blk];
+        const int err = huff_decode_block(chunk, (int)size, [&](int j, int v) {
+          const int pos = sm.zigzag[j];
+          col[pos * kTileBlocks] = __fmul_rn((float)v, sm.q[pos]);  // DCT.cpp:330-332
+        });
+        if (err) atomicOr(&P.ws.counters[1], kFlagHuffman);
+      }
+    }
+    __syncthreads();
+
+    // ---- phase 2: two blocks per thread: inverse DCT, round, clamp, store ----
+    {
+      const int b0 = 2 * tid;
+      if ((uint32_t)b0 < tc.nblk) {
+        f2 x[64];
+#pragma unroll
+        for (int i = 0; i < 64; i++) x[i] = *reinterpret_cast<const f2*>(&sm.coef[i][b0]);
+        idct_pair(x, P.one);
+        const uint32_t pw = g.pw[plane], bw = g.bw[plane];
+        uint8_t* plane_dst = P.dst + (uint64_t)tc.frame * g.frame_bytes + g.plane_off[plane];
+        uint32_t outw[2][16];
+#pragma unroll
+        for (int wd = 0; wd < 16; wd++) {
+          uint32_t pa = 0, pb = 0;
+#pragma unroll
+          for (int bt = 0; bt < 4; bt++) {
+            const f2 v = x[wd * 4 + bt];
+            const f2 t = add2_rz(v, half_like(v));
+            // clamp((int)round(v) + 128, 0, 255)  (DCT.cpp:360)
+            const int ia = __viaddmin_s32_relu(__float2int_rz(t.x), 128, 255);
+            const int ib = __viaddmin_s32_relu(__float2int_rz(t.y), 128, 255);
+            pa |= (uint32_t)ia << (8 * bt);
+            pb |= (uint32_t)ib << (8 * bt);
+          }
+          outw[0][wd] = pa;
+          outw[1][wd] = pb;
+        }
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+          const uint32_t b = (uint32_t)b0 + s;
+          if (b < tc.nblk) {
+            const uint32_t k = tc.k0 + b;
+            const uint32_t by = k / bw, bx = k - by * bw;
+            uint8_t* p = plane_dst + (uint64_t)by * 8 * pw + (uint64_t)bx * 8;
+#pragma unroll
+            for (int r = 0; r < 8; r++)
+              *reinterpret_cast<uint2*>(p + (uint64_t)r * pw) = make_uint2(outw[s][2 * r], outw[s][2 * r + 1]);
+          }
+        }
+      }
+    }
+  }
+}
+
+// ===================================================================================================
+// launchers
+// ===================================================================================================
+void launch_compress(const uint8_t* d_iyuv, const FrameGeom& g, const QTables& qt, uint8_t* d_out, uint64_t out_cap,
+                     uint64_t* d_offsets, const Workspace& ws, cudaStream_t s) {
+  EncParams P;
+  P.src = d_iyuv; P.out = d_out; P.out_cap = out_cap; P.g = g; P.ws = ws;
+  P.total_tiles = g.tiles_per_frame * g.n_frames;
+  P.one = 1.0f;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(dct_compress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncSmem));
+    attr_set = true;
+  }
+  cudaMemsetAsync(ws.tile_status, 0, (size_t)P.total_tiles * 8, s);
+  cudaMemsetAsync(ws.counters, 0, 4, s);  // ticket only; error flags accumulate until read
+  const int grid = (int)(P.total_tiles < (uint32_t)ws.grid ? P.total_tiles : (uint32_t)ws.grid);
+  dct_compress_kernel<<<grid, kCtaThreads, sizeof(EncSmem), s>>>(P, qt);
+  finalize_frames_kernel<<<g.n_frames, 256, 0, s>>>(P, d_offsets);
+  g_launches += 2;
+}
+
+void launch_decompress(const uint8_t* d_payloads, const uint64_t* d_offsets, const FrameGeom& g, const QTables& qt,
+                       uint8_t* d_iyuv, const Workspace& ws, cudaStream_t s) {
+  DecParams P;
+  P.payloads = d_payloads; P.offsets = d_offsets; P.dst = d_iyuv; P.g = g; P.ws = ws;
+  P.total_tiles = g.tiles_per_frame * g.n_frames;
+  P.one = 1.0f;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(dct_decompress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecSmem));
+    attr_set = true;
+  }
+  cudaMemsetAsync(ws.tile_status, 0, (size_t)P.total_tiles * 8, s);
+  cudaMemsetAsync(ws.counters, 0, 4, s);
+  parse_payload_kernel<<<(g.n_frames + 127) / 128, 128, 0, s>>>(P);
+  const int grid = (int)(P.total_tiles < (uint32_t)ws.grid ? P.total_tiles : (uint32_t)ws.grid);
+  dct_decompress_kernel<<<grid, kCtaThreads, sizeof(DecSmem), s>>>(P, qt);
+  g_launches += 2;
+}
+
+}  // namespace myyuvb

@@ -1,0 +1,70 @@
+// kernels.h -- internal launch interface between capi.cu (host logic) and kernels.cu (sm_100a kernels).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace myyuvb {
+
+constexpr int kTileBlocks = 256;   // 8x8 blocks per tile (one CTA pass)
+constexpr int kCtaThreads = 128;   // threads per CTA of the codec kernels
+
+// error bits raised by kernels (OR-ed into Workspace::flags)
+enum : uint32_t {
+  kFlagCapacity = 1u << 0,
+  kFlagDctYuvSize = 1u << 1,
+  kFlagPlaneSize = 1u << 2,
+  kFlagHuffman = 1u << 3,
+};
+
+// Quantisation tables of the three planes, computed on the host with the reference's float expression
+// (DCT.cpp:286-290).  q = divisor / dequantisation factor, rq = correctly rounded 1/q.
+struct QTables {
+  float q[3][64];
+  float rq[3][64];
+};
+
+// Geometry shared by all frames of a batch.
+struct FrameGeom {
+  uint32_t width, height, n_frames;
+  uint32_t pw[3], ph[3];          // plane width / height in pixels
+  uint32_t bw[3];                 // plane width in 8x8 blocks
+  uint32_t nblk[3];               // blocks per plane
+  uint32_t tiles[3];              // tiles per plane
+  uint32_t tiles_per_frame;
+  uint32_t nblk_frame;            // blocks per frame
+  uint64_t plane_off[3];          // byte offset of each plane inside one IYUV frame
+  uint64_t frame_bytes;           // w*h*3/2
+};
+
+FrameGeom make_geom(uint32_t width, uint32_t height, uint32_t n_frames);
+
+// Device scratch owned by a context (sized for the current batch by capi.cu).
+struct Workspace {
+  uint64_t* tile_status;   // [total tiles] decoupled look-back words
+  uint64_t* plane_start;   // [n_frames*3 + 1] code bytes before each plane (compress)
+  uint32_t* counters;      // [0] tile ticket, [1] error flags
+  uint8_t* chunk_sizes;    // [n_frames * nblk_frame] per-block chunk size, linear block order (compress)
+  uint8_t* overflow;       // [grid * 65536] staging overflow area (compress)
+  void* plane_desc;        // [n_frames*3] PlaneDesc (decompress)
+  int grid;                // persistent grid size of the codec kernels
+};
+
+struct PlaneDesc {
+  uint64_t sizes_off;     // offset of chunk_size[] in the payload buffer
+  uint64_t content_off;   // offset of content[]
+  uint32_t content_size;
+  uint32_t ok;
+};
+
+int codec_grid_size(int device, bool encoder);
+
+void launch_xrgb_to_iyuv(const uint8_t* d_bgrx, uint8_t* d_iyuv, uint32_t w, uint32_t h, int bottom_up, uint32_t n_frames,
+                         cudaStream_t s);
+void launch_compress(const uint8_t* d_iyuv, const FrameGeom& g, const QTables& qt, uint8_t* d_out, uint64_t out_cap,
+                     uint64_t* d_offsets, const Workspace& ws, cudaStream_t s);
+void launch_decompress(const uint8_t* d_payloads, const uint64_t* d_offsets, const FrameGeom& g, const QTables& qt,
+                       uint8_t* d_iyuv, const Workspace& ws, cudaStream_t s);
+
+extern thread_local uint64_t g_launches;
+
+}  // namespace myyuvb
