@@ -1,0 +1,348 @@
+#!/usr/bin/env python3
+"""bench.py -- BASELINE.json metric: 4K IYUV DCT-50 compress+decompress, Mpixel/s (and GB/s vs HBM).
+
+  python bench.py --gpus N --steps K --warmup W            our arm (one process per GPU; torchrun for N > 1)
+  python bench.py --impl reference --gpus N --steps K ...   the reference's own OpenMP CPU path (oracle/_ref)
+
+A step = one pass of the hot path over one batch of synthetic frames per GPU:
+  compress (IYUV -> payload, device resident) followed by decompress (payload -> IYUV, device resident)
+of `--frames` 3840x2160 IYUV frames at quality 50/50/50.  Mpixel/s counts every frame's luma pixels once per
+round trip.  Frames are independent units: ranks get their own frames, no data-path collective ("weak").
+One JSON line on stdout (rank 0); everything else goes to stderr.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import pathlib
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = pathlib.Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+W, H = 3840, 2160
+METRIC = "4K IYUV DCT-50 compress+decompress throughput"
+UNIT = "Mpixel/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=64, help="4K frames per GPU per step")
+    ap.add_argument("--quality", type=int, default=50)
+    ap.add_argument("--cpu-frames", type=int, default=4, help="frames per step of the CPU reference arm / baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(args, n_gpus):
+    return {
+        "workload": f"{W}x{H} IYUV (4:2:0) frames, DCT quality {args.quality}/{args.quality}/{args.quality}, "
+                    f"compress then decompress, {args.frames} frames per GPU per step (BASELINE configs[2]/[4] frame shape; "
+                    "the metric's 4K DCT-50 round trip)",
+        "frames_per_gpu": args.frames, "width": W, "height": H, "quality": args.quality,
+        "frame_content": "synthetic noise-grad (SURVEY 8(d)(ii)), seed 20261018",
+        "parallelism": f"frames sharded over {n_gpus} GPU(s), no collective",
+        "l2_policy": "inputs larger than L2 (796 MB IYUV + ~180 MB payload per step vs 126 MB L2), no flush needed",
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            if ts < t0 or ts > t1 + 0.15:
+                continue
+            p = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(p[0]))
+                mx = float(p[1])
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, p[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference arm: the UNMODIFIED reference library (OpenMP build) through oracle/ref_shim.cpp
+# ------------------------------------------------------------------------------------------------
+def run_reference_sample(frames_np, quality, repeats):
+    """compress + decompress each frame with the reference; returns best seconds per pass over the sample."""
+    import oracle
+
+    try:
+        ref = oracle.Reference("omp")
+        kind = "reference"
+        threads = ref.threads
+        comp = lambda f: ref.compress(f, W, H, quality)
+        dec = lambda p: ref.decompress(p, W, H, quality)
+    except oracle.ReferenceUnavailable:
+        ora = oracle.Oracle()
+        kind, threads = "port", int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
+        comp = lambda f: ora.compress(f, W, H, quality)
+        dec = lambda p: ora.decompress(p, W, H, quality)
+    times = []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        for f in frames_np:
+            dec(comp(f))
+        times.append(time.perf_counter() - t0)
+    return times, kind, threads
+
+
+def reference_main(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    os.environ.setdefault("OMP_NUM_THREADS", str(os.cpu_count() or 1))
+    synth = importlib.import_module("yuv-manipulations-2_b200.synth")
+    q = (args.quality,) * 3
+    frames = synth.iyuv_frames_numpy(W, H, args.cpu_frames)
+    times, kind, threads = run_reference_sample(list(frames), q, args.warmup + args.steps)
+    timed = times[args.warmup:]
+    total = sum(timed)
+    value = args.cpu_frames * W * H * len(timed) / total / 1e6
+    cfg = workload_config(args, 1)
+    sample = f"{args.cpu_frames} frames of the same synthetic 4K workload per step, YUV::compress + YUV::decompress each"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus, "steps": len(timed),
+        "warmup": args.warmup, "ms_per_step": round(1e3 * total / len(timed), 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 DCT + u8/int16 entropy coding", "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": threads, "kind": kind, "sample": sample,
+                         "omp_num_threads": os.environ.get("OMP_NUM_THREADS")},
+        "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def cpu_baseline_leg(args):
+    """Times the reference arm in fresh processes (OpenMP settings are fixed at library load) and keeps the best."""
+    best = None
+    ncpu = os.cpu_count() or 1
+    for omp in (str(ncpu), f"1,{ncpu}"):
+        env = dict(os.environ, OMP_NUM_THREADS=omp)
+        for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+            env.pop(k, None)
+        try:
+            out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "3", "--warmup", "1",
+                                  "--cpu-frames", str(args.cpu_frames), "--quality", str(args.quality)],
+                                 env=env, capture_output=True, text=True, timeout=600)
+            line = json.loads(out.stdout.strip().splitlines()[-1])
+            cb = line["cpu_baseline"]
+            log(f"[cpu_baseline] OMP_NUM_THREADS={omp}: {cb['value']} {cb['unit']} ({cb['kind']}, {cb['cores']} threads)")
+            if best is None or cb["value"] > best["value"]:
+                best = cb
+        except Exception as e:  # noqa: BLE001
+            log(f"[cpu_baseline] OMP_NUM_THREADS={omp} failed: {e}")
+    return best
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def b200_main(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the b200 arm has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    pkg = importlib.import_module("yuv-manipulations-2_b200")
+    synth = importlib.import_module("yuv-manipulations-2_b200.synth")
+    capi = pkg.capi
+
+    F, q = args.frames, (args.quality,) * 3
+    frame_bytes = W * H * 3 // 2
+    dev = torch.device("cuda", local)
+    stream = torch.cuda.current_stream()
+    ctx = pkg.Context(local, stream.cuda_stream)
+
+    # inputs resident in HBM before the timed region; every rank codes its own frames
+    d_in = synth.iyuv_frames_torch(W, H, F, dev, first=rank * F)
+    cap = F * 6 * 1024 * 1024  # 6 MB per frame: > 2x what this content needs; overflow would be reported
+    d_out = torch.empty(cap, dtype=torch.uint8, device=dev)
+    d_off = torch.zeros(F + 1, dtype=torch.int64, device=dev)
+    d_back = torch.empty_like(d_in)
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        ctx.compress_batch_dev(d_in, W, H, q, F, d_out, cap, d_off)
+        ctx.decompress_batch_dev(d_out, d_off, W, H, q, F, d_back)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    ctx.batch_status()
+    payload_bytes = int(d_off[F].item())
+
+    # per-kernel device time of the two codec kernels (events recorded inside the library around each kernel)
+    comp_ms, dec_ms = [], []
+    for _ in range(3):
+        ctx.compress_batch_dev(d_in, W, H, q, F, d_out, cap, d_off)
+        comp_ms.append(ctx.last_kernel_ms())
+        ctx.decompress_batch_dev(d_out, d_off, W, H, q, F, d_back)
+        dec_ms.append(ctx.last_kernel_ms())
+
+    launches0 = capi.launch_count()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    kc, kd = [], []
+    barrier()
+    t0 = time.perf_counter()
+    ev[0].record(stream)
+    for _ in range(args.steps):
+        step()
+    ev[1].record(stream)
+    barrier()
+    t1 = time.perf_counter()
+    dev_ms = ev[0].elapsed_time(ev[1])
+    ctx.batch_status()
+    launches = capi.launch_count() - launches0
+    clocks = sampler.stop(t0, t1) if sampler else None
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = world * F * W * H * args.steps / (total_ms / 1e3) / 1e6
+
+    # correctness gate inside the bench: the round trip must reproduce what a second decode gives, and sizes are sane
+    assert payload_bytes > 0 and int(d_off[0].item()) == 0
+
+    # ---- end to end through the C ABI with host buffers (pinned), H2D/D2H inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        Fe = min(F, 32)
+        h_in = capi.PinnedBuffer(Fe * frame_bytes)
+        h_in.array[:] = d_in[:Fe].reshape(-1).cpu().numpy()
+        h_pay = capi.PinnedBuffer(Fe * 6 * 1024 * 1024)
+        h_back = capi.PinnedBuffer(Fe * frame_bytes)
+        offs = np.zeros(Fe + 1, np.uint64)
+        ectx = pkg.Context(local)
+
+        def e2e_step():
+            ectx.compress_batch_host(h_in.array, W, H, q, Fe, h_pay.array, offs)
+            ectx.decompress_batch_host(h_pay.array, offs, W, H, q, Fe, h_back.array)
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        n_e2e = max(3, min(args.steps, 5))
+        te0 = time.perf_counter()
+        for _ in range(n_e2e):
+            e2e_step()
+        barrier()
+        te = torch.tensor([time.perf_counter() - te0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        pay = int(offs[Fe])
+        e2e = {"value": round(world * Fe * W * H * n_e2e / float(te.item()) / 1e6, 1), "unit": UNIT,
+               "h2d_bytes_per_step": Fe * frame_bytes + pay, "d2h_bytes_per_step": pay + Fe * frame_bytes,
+               "frames_per_step": Fe, "steps": n_e2e, "api": "myyuvb_dct_compress_batch_host + myyuvb_dct_decompress_batch_host, pinned host buffers"}
+        same = bool((torch.from_numpy(h_back.array.copy()).to(dev) == d_back[:Fe].reshape(-1)).all().item())
+        e2e["matches_device_path"] = same
+        ectx.close()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:  # noqa: BLE001
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    alg_bytes = F * frame_bytes + payload_bytes  # compress: read IYUV + write payload; decompress: the mirror image
+    c_ms, d_ms = statistics.median(comp_ms), statistics.median(dec_ms)
+    dom = "dct_compress_kernel" if c_ms >= d_ms else "dct_decompress_kernel"
+    dom_ms = max(c_ms, d_ms)
+    achieved = alg_bytes / (dom_ms / 1e3) / 1e9
+    roofline = {
+        "bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
+        "frac": round(achieved / hbm_peak, 4), "traffic": None, "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": round(dom_ms, 4),
+        "compress_kernel_ms": round(c_ms, 4), "decompress_kernel_ms": round(d_ms, 4),
+        "compress_GBps": round(alg_bytes / (c_ms / 1e3) / 1e9, 1), "decompress_GBps": round(alg_bytes / (d_ms / 1e3) / 1e9, 1),
+        "compress_Mpixel_s": round(F * W * H / (c_ms / 1e3) / 1e6, 1), "decompress_Mpixel_s": round(F * W * H / (d_ms / 1e3) / 1e6, 1),
+        # the bit-exact unfused 8x8 float DCT: 1920 FP32 mul/add per block; issue-rate view of the same kernel
+        "fp32_ops_per_launch": F * (W * H // 64 * 3 // 2) * 1920,
+        "fp32_issue_frac_of_148x128_lanes_at_max_clock": round(
+            F * (W * H // 64 * 3 // 2) * 1920 / (dom_ms / 1e3) / (148 * 128 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6), 4),
+    }
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline_leg(args)
+    line = {
+        "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": round(total_ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 DCT (unfused, packed f32x2) + u8/int16 entropy coding", "data": "synthetic",
+        "config": workload_config(args, world), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": roofline, "cpu_baseline": cpu,
+        "payload_bytes_per_step_per_gpu": payload_bytes, "bytes_per_pixel": round(payload_bytes / (F * W * H), 4),
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    sys.exit(reference_main(a) if a.impl == "reference" else b200_main(a))

@@ -23,7 +23,7 @@ EXPORTS = [
     "myyuvb_compress_bound", "myyuvb_xrgb_to_iyuv", "myyuvb_dct_compress", "myyuvb_dct_decompress",
     "myyuvb_xrgb_to_iyuv_batch_dev", "myyuvb_dct_compress_batch_dev", "myyuvb_dct_decompress_batch_dev",
     "myyuvb_batch_status", "myyuvb_dct_compress_batch_host", "myyuvb_dct_decompress_batch_host",
-    "myyuvb_host_alloc", "myyuvb_host_free", "myyuvb_launch_count",
+    "myyuvb_host_alloc", "myyuvb_host_free", "myyuvb_launch_count", "myyuvb_last_kernel_ms",
 ]
 
 
@@ -78,6 +78,7 @@ def lib() -> C.CDLL:
     L.myyuvb_host_free.argtypes = [C.c_void_p]
     L.myyuvb_host_free.restype = None
     L.myyuvb_launch_count.restype = C.c_uint64
+    L.myyuvb_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     _lib = L
     return L
 
@@ -226,6 +227,11 @@ class Context:
         qa = _q(q)
         _check(lib().myyuvb_dct_decompress_batch_dev(self._h, _ptr(d_payloads), _ptr(d_offsets), w, h, qa.ctypes.data_as(_u8p),
                                                      n_frames, _ptr(d_iyuv)))
+
+    def last_kernel_ms(self) -> float:
+        ms = C.c_float(0)
+        _check(lib().myyuvb_last_kernel_ms(self._h, C.byref(ms)))
+        return float(ms.value)
 
     def batch_status(self) -> None:
         """Synchronise and raise the first data-dependent error of the batch calls issued so far."""

@@ -111,6 +111,7 @@ struct myyuvb_ctx {
   Buffer d_in, d_out, d_status, d_tiles, d_plane_start, d_counters, d_sizes, d_overflow, d_desc, d_offsets;
   Buffer h_small, h_stage_in, h_stage_out;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t kev[2] = {nullptr, nullptr};  // timing events around the last main codec kernel
   myyuvb_ctx() { h_small.pinned = h_stage_in.pinned = h_stage_out.pinned = true; }
 };
 
@@ -138,6 +139,8 @@ int ensure_workspace(myyuvb_ctx* c, const FrameGeom& g, bool encoder, Workspace*
   ws->overflow = c->d_overflow.as<uint8_t>();
   ws->plane_desc = c->d_desc.p;
   ws->grid = c->grid;
+  ws->k_begin = c->kev[0];
+  ws->k_end = c->kev[1];
   return MYYUVB_OK;
 }
 
@@ -200,6 +203,7 @@ int myyuvb_ctx_create(int device, void* stream, myyuvb_ctx** out) {
   }
   CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   for (auto& ev : c->ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  for (auto& ev : c->kev) CU(cudaEventCreate(&ev));
   c->grid = codec_grid_size(device, true);
   *out = c;
   return MYYUVB_OK;
@@ -215,6 +219,8 @@ void myyuvb_ctx_destroy(myyuvb_ctx* c) {
     b->release();
   for (auto& ev : c->ev)
     if (ev) cudaEventDestroy(ev);
+  for (auto& ev : c->kev)
+    if (ev) cudaEventDestroy(ev);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   cudaStreamDestroy(c->copy_stream);
   delete c;
@@ -227,6 +233,13 @@ int myyuvb_sync(myyuvb_ctx* c) {
 }
 
 void* myyuvb_stream(myyuvb_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+int myyuvb_last_kernel_ms(myyuvb_ctx* c, float* ms) {
+  if (!c || !ms) return fail(MYYUVB_ERR_ARG, "null argument");
+  CU(cudaEventSynchronize(c->kev[1]));
+  CU(cudaEventElapsedTime(ms, c->kev[0], c->kev[1]));
+  return MYYUVB_OK;
+}
 
 int myyuvb_host_alloc(size_t bytes, void** out) {
   if (!out) return fail(MYYUVB_ERR_ARG, "null output pointer");

@@ -767,7 +767,9 @@ void launch_compress(const uint8_t* d_iyuv, const FrameGeom& g, const QTables& q
   cudaMemsetAsync(ws.tile_status, 0, (size_t)P.total_tiles * 8, s);
   cudaMemsetAsync(ws.counters, 0, 4, s);  // ticket only; error flags accumulate until read
   const int grid = (int)(P.total_tiles < (uint32_t)ws.grid ? P.total_tiles : (uint32_t)ws.grid);
+  if (ws.k_begin) cudaEventRecord(ws.k_begin, s);
   dct_compress_kernel<<<grid, kCtaThreads, sizeof(EncSmem), s>>>(P, qt);
+  if (ws.k_end) cudaEventRecord(ws.k_end, s);
   finalize_frames_kernel<<<g.n_frames, 256, 0, s>>>(P, d_offsets);
   g_launches += 2;
 }
@@ -787,7 +789,9 @@ void launch_decompress(const uint8_t* d_payloads, const uint64_t* d_offsets, con
   cudaMemsetAsync(ws.counters, 0, 4, s);
   parse_payload_kernel<<<(g.n_frames + 127) / 128, 128, 0, s>>>(P);
   const int grid = (int)(P.total_tiles < (uint32_t)ws.grid ? P.total_tiles : (uint32_t)ws.grid);
+  if (ws.k_begin) cudaEventRecord(ws.k_begin, s);
   dct_decompress_kernel<<<grid, kCtaThreads, sizeof(DecSmem), s>>>(P, qt);
+  if (ws.k_end) cudaEventRecord(ws.k_end, s);
   g_launches += 2;
 }
 

@@ -47,6 +47,7 @@ struct Workspace {
   uint8_t* overflow;       // [grid * 65536] staging overflow area (compress)
   void* plane_desc;        // [n_frames*3] PlaneDesc (decompress)
   int grid;                // persistent grid size of the codec kernels
+  cudaEvent_t k_begin, k_end;  // recorded around the main codec kernel of each launch (myyuvb_last_kernel_ms)
 };
 
 struct PlaneDesc {
