@@ -149,7 +149,9 @@ def reference_main(args):
         "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus, "steps": len(timed),
         "warmup": args.warmup, "ms_per_step": round(1e3 * total / len(timed), 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32 DCT + u8/int16 entropy coding", "data": "synthetic", "config": cfg,
-        "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": threads, "kind": kind, "sample": sample,
+        "cpu_baseline": {"value": round(value, 3), "unit": UNIT,
+                         "cores": max([threads] + [int(x) for x in os.environ.get("OMP_NUM_THREADS", "1").split(",") if x.strip().isdigit()]),
+                         "kind": kind, "sample": sample,
                          "omp_num_threads": os.environ.get("OMP_NUM_THREADS")},
         "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -204,7 +206,10 @@ def b200_main(args):
     F, q = args.frames, (args.quality,) * 3
     frame_bytes = W * H * 3 // 2
     dev = torch.device("cuda", local)
-    stream = torch.cuda.current_stream()
+    # a real (non-default) torch stream, shared with the library: torch.cuda.Event only sees the stream it is recorded on
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx = pkg.Context(local, stream.cuda_stream)
 
     # inputs resident in HBM before the timed region; every rank codes its own frames

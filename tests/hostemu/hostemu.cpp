@@ -27,9 +27,9 @@ struct ZArray {
 extern "C" {
 
 // coef: n x 64 row-major.  stride: element stride of the scratch arrays (1, or e.g. 128 to mimic the
-// shared-memory interleave).  fast_cap16 != 0: try the 16-symbol scratch first like the kernel does.
+// shared-memory interleave).  fast_cap16 != 0: try the 15-symbol scratch first like the kernel does.
 int hostemu_encode_blocks(const int16_t* coef, uint32_t n, int stride, int fast_cap16, uint8_t* out, uint8_t* sizes) {
-  using Fast = HuffScratch<16>;
+  using Fast = HuffScratch<15>;
   using Big = HuffScratch<64>;
   uint8_t* fb = new uint8_t[(size_t)Fast::kBytes * stride]();
   int16_t* fh = new int16_t[(size_t)Fast::kSyms * stride]();
@@ -46,16 +46,16 @@ int hostemu_encode_blocks(const int16_t* coef, uint32_t n, int stride, int fast_
     Big bs{bb, bh, stride};
     HuffPlan pl;
     pl.n = -1;
-    if (fast_cap16) pl = huff_plan<16>(za, L, fs);
+    if (fast_cap16) pl = huff_plan<15>(za, L, fs, NoWarp{});
     bool big = false;
     if (pl.n < 0) {
       big = true;
       big_used++;
-      pl = huff_plan<64>(za, L, bs);
+      pl = huff_plan<64>(za, L, bs, NoWarp{});
     }
     uint8_t tmp[256];
-    if (big) huff_emit<64>(za, pl, bs, tmp);
-    else huff_emit<16>(za, pl, fs, tmp);
+    if (big) huff_emit<64>(za, pl, bs, tmp, NoWarp{});
+    else huff_emit<15>(za, pl, fs, tmp, NoWarp{});
     const int sz = pl.size();
     memcpy(out, tmp, (size_t)sz);
     out += sz;
@@ -69,7 +69,7 @@ int hostemu_decode_blocks(const uint8_t* chunks, const uint8_t* sizes, uint32_t 
   for (uint32_t b = 0; b < n; b++) {
     int16_t* c = coef + 64 * (size_t)b;
     memset(c, 0, 128);
-    const int err = huff_decode_block(chunks, sizes[b], [&](int j, int v) { c[kZigzag[j]] = (int16_t)v; });
+    const int err = huff_decode_block(chunks, sizes[b], [&](int j, int v) { c[kZigzag[j]] = (int16_t)v; }, NoWarp{});
     if (err) return (int)b + 1;
     chunks += sizes[b];
   }

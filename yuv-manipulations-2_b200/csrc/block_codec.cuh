@@ -1,8 +1,11 @@
 // block_codec.cuh -- per-8x8-block entropy coding of the reference's DCT payload, written for one GPU
-// thread per block.  Everything here is integer/byte work with data-dependent control flow, so it is
-// plain __host__ __device__ code: the kernels in kernels.cu call it on the device, and
-// tests/hostemu/hostemu.cpp compiles the same header with g++ so the logic can be checked against the
-// oracle on a machine without a GPU (test infrastructure only -- the product never runs it on the CPU).
+// thread per block with the 32 lanes of a warp running in LOCKSTEP: every loop has a warp-uniform trip
+// count (the warp maximum) and a predicated body, so lanes with short messages idle in step instead of
+// drifting apart (the first, free-running version averaged 2.6 active lanes per instruction, see
+// profiles/r01_notes.md).  Everything here is integer/byte work, so it is plain __host__ __device__ code:
+// the kernels in kernels.cu call it with the WarpLockstep policy, and tests/hostemu/hostemu.cpp compiles
+// the same header with g++ (policy NoWarp) so the logic can be checked against the oracle without a GPU
+// (test infrastructure only -- the product never runs it on the CPU).
 //
 // Format and semantics follow the reference (paths relative to /root/reference):
 //   Huffman.cpp:172-241  fromData   zigzag, trailing-zero trim, histogram, tree, canonical codes, code stream
@@ -28,6 +31,20 @@ namespace myyuvb {
   0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7,   \
       14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, \
       46, 53, 60, 61, 54, 47, 55, 62, 63
+
+// ---- warp cooperation policies -------------------------------------------------------------------
+struct NoWarp {  // host emulation and the out-of-line fallback path: every "lane" runs alone
+  MYB_HD int max(int v) const { return v; }
+  MYB_HD bool any(bool p) const { return p; }
+  MYB_HD void sync() const {}
+};
+#if defined(__CUDACC__)
+struct WarpLockstep {  // all 32 lanes of the warp call the codec functions together
+  __device__ __forceinline__ int max(int v) const { return __reduce_max_sync(0xffffffffu, v); }
+  __device__ __forceinline__ bool any(bool p) const { return __any_sync(0xffffffffu, p) != 0; }
+  __device__ __forceinline__ void sync() const { __syncwarp(); }
+};
+#endif
 
 MYB_HD uint32_t bit_reverse32(uint32_t v) {
 #if defined(__CUDA_ARCH__)
@@ -61,6 +78,7 @@ struct HuffScratch {
   uint8_t* b;
   int16_t* h;
   int stride;
+  static constexpr int kCap = CAP;
   static constexpr int kCnt = 0;                 // [CAP+1] occurrences of slot s in the message
   static constexpr int kOrd = kCnt + CAP + 1;    // [CAP+1] hash-list order: slot at list position p
   static constexpr int kBkt = kOrd + CAP + 1;    // [CAP+1] bucket of list position p; later: heap
@@ -76,25 +94,32 @@ struct HuffScratch {
 };
 
 struct HuffPlan {
-  int n;           // distinct symbols (leaves); < 0: scratch capacity exceeded, retry with the large instance
-  int msg_len;     // coded symbols (1..64)
-  int bits;        // code stream bits
-  int table_bytes; // bytes of the serialised code table
+  int n;            // distinct symbols (leaves); < 0: scratch capacity exceeded, retry with the large instance
+  int msg_len;      // coded symbols (1..64)
+  int bits;         // code stream bits
+  int table_bytes;  // bytes of the serialised code table
+  uint64_t per_len; // symbols per code length 1..8, one byte each
   MYB_HD int size() const { return 3 + table_bytes + ((bits + 7) >> 3); }
 };
 
 // std::hash<short>(v) % nb with v sign-extended to 64 bits (libstdc++ functional_hash.h); nb in {13,29,59,127}.
 // 2^64 mod nb = 3, 24, 5, 2 respectively.
+MYB_HD int hash_bucket13(int v) {
+  const int m = (v < 0 ? -v : v) % 13;
+  if (v >= 0) return m;
+  const int r = 3 - m;
+  return r < 0 ? r + 13 : r;
+}
 MYB_HD int hash_bucket(int v, int nb) {
   int m, two64;
   switch (nb) {
-    case 13: two64 = 3; m = (v < 0 ? -v : v) % 13; break;
+    case 13: return hash_bucket13(v);
     case 29: two64 = 24; m = (v < 0 ? -v : v) % 29; break;
     case 59: two64 = 5; m = (v < 0 ? -v : v) % 59; break;
     default: two64 = 2; m = (v < 0 ? -v : v) % 127; break;
   }
   if (v >= 0) return m;
-  int r = two64 - m;
+  const int r = two64 - m;
   return r < 0 ? r + nb : r;
 }
 
@@ -114,32 +139,12 @@ MYB_HD void list_place(const HuffScratch<CAP>& S, int& ln, int slot, int bucket)
   ln++;
 }
 
-// Iteration order of the reference's freq map after inserting keys slot 0..m-1 (first-occurrence order)
-// and erasing `erase_slot` (>= 0) at the end.  Result: S.kOrd[0..n).  Returns n.
+// General case of the map's iteration order (more than 13 keys): 13 -> 29 -> 59 -> 127 buckets, rehash before
+// inserting key number 14, 30, 60 (_Prime_rehash_policy::_M_need_rehash, max_load_factor 1, growth 2).
+// Keys are slots 0..m-1 in first-occurrence order; erase_slot (>= 0) is removed at the end.  Result in kOrd.
 template <int CAP>
-MYB_HD int hash_list_order(const HuffScratch<CAP>& S, int m, int erase_slot) {
-  int ln = 0;
-  if (m <= 13) {
-    // one table size (13 buckets): keep list + buckets as 4-bit fields of two 64-bit registers
-    uint64_t ord = 0, bkt = ~0ull;  // empty fields hold 0xF, which is no bucket
-    for (int s = 0; s < m; s++) {
-      const uint64_t b = (uint64_t)hash_bucket(S.sym(s), 13);
-      const uint64_t x = bkt ^ (b * 0x1111111111111111ull);
-      const uint64_t zero_nib = (x - 0x1111111111111111ull) & ~x & 0x8888888888888888ull;  // lowest hit is exact
-      const int p4 = zero_nib ? (ctz64(zero_nib) & ~3) : 0;
-      const uint64_t low = (1ull << p4) - 1ull;
-      ord = (ord & low) | ((ord & ~low) << 4) | ((uint64_t)s << p4);
-      bkt = (bkt & low) | ((bkt & ~low) << 4) | (b << p4);
-    }
-    for (int i = 0; i < m; i++) {
-      const int s = (int)((ord >> (4 * i)) & 15u);
-      if (s != erase_slot) S.at(S.kOrd, ln++) = (uint8_t)s;
-    }
-    return ln;
-  }
-  // general case: 13 -> 29 -> 59 -> 127 buckets, rehash before inserting key number 14, 30, 60
-  // (_Prime_rehash_policy::_M_need_rehash with max_load_factor 1, growth factor 2)
-  int nb = 13;
+MYB_HD void hash_list_order_general(const HuffScratch<CAP>& S, int m, int erase_slot) {
+  int ln = 0, nb = 13;
   for (int s = 0; s < m; s++) {
     if (s == 13 || s == 29 || s == 59) {
       nb = (s == 13) ? 29 : (s == 29) ? 59 : 127;
@@ -160,13 +165,11 @@ MYB_HD int hash_list_order(const HuffScratch<CAP>& S, int m, int erase_slot) {
       const uint8_t t = S.at(S.kOrd, i);
       if (t != erase_slot) S.at(S.kOrd, w++) = t;
     }
-    ln = w;
   }
-  return ln;
 }
 
 // std::push_heap with Compare(a,b) = a.freq > b.freq (Huffman.hpp:41-45; stl_heap.h __push_heap).
-// heap lives in kBkt (free after hash_list_order).
+// heap lives in kBkt (free after the list order is final).
 template <int CAP>
 MYB_HD void heap_sift_up(const HuffScratch<CAP>& S, int hole, int node, int wnode) {
   while (hole > 0) {
@@ -205,54 +208,71 @@ MYB_HD int heap_pop(const HuffScratch<CAP>& S, int& hsize) {
 
 MYB_HD int group_table_bytes(int cnt) {  // one code length with cnt symbols, split in groups of <= 32 (Huffman.cpp:284-293)
   int bytes = 0;
-  while (cnt > 0) {
-    const int c = cnt > 32 ? 32 : cnt;
-    bytes += 1 + ((c * 11 + 7) >> 3);
-    cnt -= c;
+  if (cnt > 32) {
+    bytes = 45;
+    cnt -= 32;
   }
+  if (cnt > 0) bytes += 1 + ((cnt * 11 + 7) >> 3);
   return bytes;
 }
 
 // Build the code of one block.  Z: accessor with  int get(int i)  (zigzag coefficient i) and
 // void set(int i, int v); on success the first msg_len entries are overwritten with slot numbers
 // (the coefficient of slot s is S.sym(s)).  L = index of the last non-zero zigzag coefficient + 1 (0: all zero).
-template <int CAP, class Z>
-MYB_HD HuffPlan huff_plan(Z& z, int L, const HuffScratch<CAP>& S) {
+// `warp`: cooperation policy; with WarpLockstep all 32 lanes must call this together (idle lanes pass L = 0).
+template <int CAP, class Z, class W>
+MYB_HD HuffPlan huff_plan(Z& z, int L, const HuffScratch<CAP>& S, const W& warp) {
   HuffPlan pl;
+  // ---- histogram in first-occurrence order (Huffman.cpp:176-189, message part only; the trailing zeros
+  // only matter through the key 0 they may add to the map, handled below).  Coefficients in [-8, 7] find
+  // their slot through a 16 x 4-bit table held in a register pair; the rest by a short linear search.
+  int n = 0, zero_slot = -1;
+  bool bail = false;
+  uint64_t small = ~0ull;  // nibble v+8: slot of value v, 0xF = not seen (or slot >= 15)
+  const int Lw = warp.max(L);
+  for (int i = 0; i < Lw; i++) {
+    if (i < L && !bail) {
+      const int v = z.get(i);
+      const unsigned vi = (unsigned)(v + 8);
+      int s = -1;
+      if (vi < 16u) {
+        const int t = (int)((small >> (4 * vi)) & 15u);
+        if (t != 15) s = t;
+      }
+      if (s < 0 && (vi >= 16u || n > 15)) {  // not answered by the table: short linear search
+        int k = 0;
+        while (k < n && S.sym(k) != v) k++;
+        if (k < n) s = k;
+      }
+      if (s < 0) {
+        if (n == CAP) {
+          bail = true;  // does not fit this scratch instance: undo and let the caller retry with the big one
+          for (int j = 0; j < i; j++) z.set(j, S.sym(z.get(j)));
+        } else {
+          s = n++;
+          S.sym(s) = (int16_t)v;
+          S.at(S.kCnt, s) = 0;
+          if (v == 0) zero_slot = s;
+          if (vi < 16u && s < 15) small = (small & ~(15ull << (4 * vi))) | ((uint64_t)s << (4 * vi));
+        }
+      }
+      if (!bail) {
+        S.at(S.kCnt, s)++;
+        z.set(i, s);
+      }
+    }
+    warp.sync();
+  }
   if (L == 0) {  // all-zero block: the single symbol 0, one bit (Huffman.cpp:195-199)
     S.sym(0) = 0;
     S.at(S.kCnt, 0) = 1;
-    S.at(S.kLen, 0) = 1;
-    S.at(S.kCode, 0) = 0;
-    S.at(S.kSorted, 0) = 0;
     z.set(0, 0);
-    pl.n = 1; pl.msg_len = 1; pl.bits = 1; pl.table_bytes = 3;
-    return pl;
+    n = 1;
   }
-  // histogram in first-occurrence order (Huffman.cpp:176-189, message part only; the trailing zeros
-  // only matter through the key 0 they may add to the map, handled below)
-  int n = 0, zero_slot = -1;
-  for (int i = 0; i < L; i++) {
-    const int v = z.get(i);
-    int s = 0;
-    while (s < n && S.sym(s) != v) s++;
-    if (s == n) {
-      if (n == CAP) {  // does not fit this scratch instance: undo and let the caller retry with the big one
-        for (int j = 0; j < i; j++) z.set(j, S.sym(z.get(j)));
-        pl.n = -1; pl.msg_len = 0; pl.bits = 0; pl.table_bytes = 0;
-        return pl;
-      }
-      S.sym(n) = (int16_t)v;
-      S.at(S.kCnt, n) = 0;
-      if (v == 0) zero_slot = n;
-      n++;
-    }
-    S.at(S.kCnt, s)++;
-    z.set(i, s);
-  }
-  pl.n = n;
-  pl.msg_len = L;
-  if (n <= 2) {  // one or two symbols: every code has length 1 (Huffman.cpp:76, :218-221)
+  pl.n = bail ? -1 : n;
+  pl.msg_len = L == 0 ? 1 : L;
+  const bool tree = !bail && n > 2;  // one or two symbols: every code has length 1 (Huffman.cpp:76, :218-221)
+  if (!bail && n <= 2) {
     int lo = 0;
     if (n == 2 && S.sym(1) < S.sym(0)) lo = 1;
     S.at(S.kSorted, 0) = (uint8_t)lo;
@@ -263,91 +283,126 @@ MYB_HD HuffPlan huff_plan(Z& z, int L, const HuffScratch<CAP>& S) {
       S.at(S.kLen, 1 - lo) = 1;
       S.at(S.kCode, 1 - lo) = 1;
     }
-    pl.bits = L;
-    pl.table_bytes = group_table_bytes(n);
-    return pl;
   }
-  // map iteration order.  Key 0 is always in the reference's map while it is filled (trailing zeros or
+  // ---- map iteration order.  Key 0 is always in the reference's map while it is filled (trailing zeros or
   // freq[0], Huffman.cpp:192-195); when the message itself has no zero it is erased again (:201) and can
   // only have mattered by triggering a rehash as key number 14, 30 or 60.
-  int m = n, erase_slot = -1;
-  if (zero_slot < 0 && (n == 13 || n == 29 || n == 59)) {
+  int m = tree ? n : 0, erase_slot = -1;
+  if (tree && zero_slot < 0 && (n == 13 || n == 29 || n == 59)) {
     S.sym(n) = 0;
     erase_slot = n;
     m = n + 1;
   }
-  hash_list_order(S, m, erase_slot);
-  // leaves pushed in list order (Huffman.cpp:207-209); node id = list position, weights in kFreq
+  {
+    // up to 13 keys: one table size (13 buckets); list and buckets are 4-bit fields of two 64-bit registers
+    const bool fast = m <= 13;
+    const int mw = warp.max(fast ? m : 0);
+    uint64_t ord = 0, bkt = ~0ull;  // empty fields hold 0xF, which is no bucket
+    for (int s = 0; s < mw; s++) {
+      if (s < m && fast) {
+        const uint64_t b = (uint64_t)hash_bucket13(S.sym(s));
+        const uint64_t x = bkt ^ (b * 0x1111111111111111ull);
+        const uint64_t zero_nib = (x - 0x1111111111111111ull) & ~x & 0x8888888888888888ull;  // lowest hit is exact
+        const int p4 = zero_nib ? (ctz64(zero_nib) & ~3) : 0;
+        const uint64_t low = (1ull << p4) - 1ull;
+        ord = (ord & low) | ((ord & ~low) << 4) | ((uint64_t)s << p4);
+        bkt = (bkt & low) | ((bkt & ~low) << 4) | (b << p4);
+      }
+    }
+    if (fast) {
+      for (int i = 0; i < mw; i++)
+        if (i < m) S.at(S.kOrd, i) = (uint8_t)((ord >> (4 * i)) & 15u);
+    } else {
+      hash_list_order_general(S, m, erase_slot);
+    }
+    warp.sync();
+  }
+  // ---- leaves pushed in list order (Huffman.cpp:207-209); node id = list position, weights in kFreq
+  const int nt = tree ? n : 0;
+  const int nw = warp.max(nt);
   int hsize = 0;
-  for (int j = 0; j < n; j++) {
-    const int w = S.at(S.kCnt, S.at(S.kOrd, j));
-    S.at(S.kFreq, j) = (uint8_t)w;
-    hsize++;
-    heap_sift_up(S, hsize - 1, j, w);
-  }
-  int nnode = n;
-  while (hsize > 1) {  // Huffman.cpp:210-217
-    const int l = heap_pop(S, hsize);
-    const int r = heap_pop(S, hsize);
-    const int w = S.at(S.kFreq, l) + S.at(S.kFreq, r);
-    S.at(S.kFreq, nnode) = (uint8_t)w;
-    S.at(S.kPar, l) = (uint8_t)nnode;
-    S.at(S.kPar, r) = (uint8_t)nnode;
-    hsize++;
-    heap_sift_up(S, hsize - 1, nnode, w);
-    nnode++;
-  }
-  // code length = leaf depth (Huffman.cpp:71-83); parents always have larger ids than children
-  S.at(S.kPar, nnode - 1) = 0;
-  for (int i = nnode - 2; i >= 0; i--) S.at(S.kPar, i) = (uint8_t)(S.at(S.kPar, S.at(S.kPar, i)) + 1);
-  for (int j = 0; j < n; j++) S.at(S.kLen, S.at(S.kOrd, j)) = S.at(S.kPar, j);
-  // tree_data: lengths ascending, symbols ascending inside a length (Huffman.cpp:76-78): insertion sort
-  for (int i = 0; i < n; i++) {
-    const int key = ((int)S.at(S.kLen, i) << 12) + (S.sym(i) + 2048);
-    int j = i - 1;
-    while (j >= 0) {
-      const int t = S.at(S.kSorted, j);
-      if ((((int)S.at(S.kLen, t) << 12) + (S.sym(t) + 2048)) <= key) break;
-      S.at(S.kSorted, j + 1) = (uint8_t)t;
-      j--;
+  for (int j = 0; j < nw; j++) {
+    if (j < nt) {
+      const int w = S.at(S.kCnt, S.at(S.kOrd, j));
+      S.at(S.kFreq, j) = (uint8_t)w;
+      hsize++;
+      heap_sift_up(S, hsize - 1, j, w);
     }
-    S.at(S.kSorted, j + 1) = (uint8_t)i;
+    warp.sync();
   }
-  // canonical codes (Huffman.cpp:86-103) stored bit-reversed, sizes
-  int code = 0, prev = 0, bits = 0, table = 0, run = 0;
-  for (int i = 0; i < n; i++) {
-    const int s = S.at(S.kSorted, i);
-    const int len = S.at(S.kLen, s);
-    if (len != prev) {
-      table += group_table_bytes(run);
-      run = 0;
+  int nnode = nt;
+  for (int t = 0; t + 1 < nw; t++) {  // Huffman.cpp:210-217: n - 1 merges
+    if (t + 1 < nt) {
+      const int l = heap_pop(S, hsize);
+      const int r = heap_pop(S, hsize);
+      const int w = S.at(S.kFreq, l) + S.at(S.kFreq, r);
+      S.at(S.kFreq, nnode) = (uint8_t)w;
+      S.at(S.kPar, l) = (uint8_t)nnode;
+      S.at(S.kPar, r) = (uint8_t)nnode;
+      hsize++;
+      heap_sift_up(S, hsize - 1, nnode, w);
+      nnode++;
     }
-    code = (code << (len - prev)) & 0xff;
-    S.at(S.kCode, s) = (uint8_t)(bit_reverse32((uint32_t)code) >> (32 - len));
-    code = (code + 1) & 0xff;
-    prev = len;
-    run++;
-    bits += len * (int)S.at(S.kCnt, s);
+    warp.sync();
   }
-  table += group_table_bytes(run);
+  // ---- code length = leaf depth (Huffman.cpp:71-83); parents always have larger ids than children
+  if (tree) S.at(S.kPar, nnode - 1) = 0;
+  for (int k = 2; k <= 2 * nw - 1; k++) {
+    const int i = nnode - k;
+    if (tree && i >= 0) S.at(S.kPar, i) = (uint8_t)(S.at(S.kPar, S.at(S.kPar, i)) + 1);
+  }
+  for (int j = 0; j < nw; j++)
+    if (j < nt) S.at(S.kLen, S.at(S.kOrd, j)) = S.at(S.kPar, j);
+  // ---- tree_data: lengths ascending, symbols ascending inside a length (Huffman.cpp:76-78): insertion sort
+  for (int i = 0; i < nw; i++) {
+    if (i < nt) {
+      const int key = ((int)S.at(S.kLen, i) << 12) + (S.sym(i) + 2048);
+      int j = i - 1;
+      while (j >= 0) {
+        const int t = S.at(S.kSorted, j);
+        if ((((int)S.at(S.kLen, t) << 12) + (S.sym(t) + 2048)) <= key) break;
+        S.at(S.kSorted, j + 1) = (uint8_t)t;
+        j--;
+      }
+      S.at(S.kSorted, j + 1) = (uint8_t)i;
+    }
+    warp.sync();
+  }
+  // ---- canonical codes (Huffman.cpp:86-103) stored bit-reversed; sizes.  Runs for every block (n <= 2 too).
+  const int nc = bail ? 0 : n;
+  const int ncw = warp.max(nc);
+  int code = 0, prev = 0, bits = 0;
+  uint64_t per_len = 0;
+  for (int i = 0; i < ncw; i++) {
+    if (i < nc) {
+      const int s = S.at(S.kSorted, i);
+      const int len = S.at(S.kLen, s);
+      code = (code << (len - prev)) & 0xff;
+      S.at(S.kCode, s) = (uint8_t)(bit_reverse32((uint32_t)code) >> (32 - len));
+      code = (code + 1) & 0xff;
+      prev = len;
+      per_len += 1ull << (8 * (len - 1));
+      bits += len * (int)S.at(S.kCnt, s);
+    }
+  }
+  int table = 0;
+  for (int len = 0; len < 8; len++) table += group_table_bytes((int)((per_len >> (8 * len)) & 0xff));
   pl.bits = bits;
   pl.table_bytes = table;
+  pl.per_len = per_len;
   return pl;
 }
 
-// little-endian bit writer into bytes
+// little-endian bit writer into bytes; put() takes at most 16 bits while fewer than 8 are pending
 struct BitSink {
   uint8_t* p;
-  uint64_t acc;
+  uint32_t acc;
   int nb;
   MYB_HD void put(uint32_t v, int len) {
-    acc |= (uint64_t)v << nb;
+    acc |= v << nb;
     nb += len;
-    while (nb >= 8) {
-      *p++ = (uint8_t)acc;
-      acc >>= 8;
-      nb -= 8;
-    }
+    if (nb >= 8) { *p++ = (uint8_t)acc; acc >>= 8; nb -= 8; }
+    if (nb >= 8) { *p++ = (uint8_t)acc; acc >>= 8; nb -= 8; }
   }
   MYB_HD void flush() {
     if (nb > 0) *p++ = (uint8_t)acc;
@@ -356,29 +411,42 @@ struct BitSink {
   }
 };
 
-// Serialise the chunk planned by huff_plan into dst[0 .. pl.size()).
-template <int CAP, class Z>
-MYB_HD void huff_emit(Z& z, const HuffPlan& pl, const HuffScratch<CAP>& S, uint8_t* dst) {
-  dst[0] = (uint8_t)(pl.bits & 0xff);
-  dst[1] = (uint8_t)(pl.bits >> 8);
-  dst[2] = (uint8_t)pl.table_bytes;
+// Serialise the chunk planned by huff_plan into dst[0 .. pl.size()).  Lanes without a chunk pass pl.n = 0.
+template <int CAP, class Z, class W>
+MYB_HD void huff_emit(Z& z, const HuffPlan& pl, const HuffScratch<CAP>& S, uint8_t* dst, const W& warp) {
+  const int n = pl.n > 0 ? pl.n : 0;
+  if (n > 0) {
+    dst[0] = (uint8_t)(pl.bits & 0xff);
+    dst[1] = (uint8_t)(pl.bits >> 8);
+    dst[2] = (uint8_t)pl.table_bytes;
+  }
   BitSink w{dst + 3, 0, 0};
-  int i = 0;
-  while (i < pl.n) {  // code table, Huffman.cpp:300-316
-    const int len = S.at(S.kLen, S.at(S.kSorted, i));
-    int j = i;
-    while (j < pl.n && S.at(S.kLen, S.at(S.kSorted, j)) == len) j++;
-    while (i < j) {
-      const int c = (j - i) > 32 ? 32 : (j - i);
-      w.put((uint32_t)(((len - 1) << 5) | (c - 1)), 8);
-      for (int k = 0; k < c; k++) w.put((uint32_t)S.sym(S.at(S.kSorted, i + k)) & 0x7ffu, 11);  // pack11bit :36-52
-      w.flush();
-      i += c;
+  // code table, Huffman.cpp:300-316: symbols in (length, value) order; a group header before the first symbol of
+  // a length and after every 32 symbols of the same length; every group is padded to whole bytes
+  const int nw = warp.max(n);
+  int run_len = 0, in_run = 0;
+  for (int i = 0; i < nw; i++) {
+    if (i < n) {
+      const int s = S.at(S.kSorted, i);
+      const int len = S.at(S.kLen, s);
+      if (len != run_len) { run_len = len; in_run = 0; }
+      if ((in_run & 31) == 0) {
+        w.flush();
+        const int left = (int)((pl.per_len >> (8 * (len - 1))) & 0xff) - in_run;
+        w.put((uint32_t)(((len - 1) << 5) | ((left > 32 ? 32 : left) - 1)), 8);
+      }
+      w.put((uint32_t)S.sym(s) & 0x7ffu, 11);  // pack11bit :36-52
+      in_run++;
     }
   }
-  for (int k = 0; k < pl.msg_len; k++) {  // code stream, Huffman.cpp:227-236, :319-325
-    const int s = z.get(k);
-    w.put(S.at(S.kCode, s), S.at(S.kLen, s));
+  w.flush();
+  const int L = n > 0 ? pl.msg_len : 0;
+  const int Lw = warp.max(L);
+  for (int k = 0; k < Lw; k++) {  // code stream, Huffman.cpp:227-236, :319-325
+    if (k < L) {
+      const int s = z.get(k);
+      w.put(S.at(S.kCode, s), S.at(S.kLen, s));
+    }
   }
   w.flush();
 }
@@ -388,6 +456,7 @@ MYB_HD void huff_emit(Z& z, const HuffPlan& pl, const HuffScratch<CAP>& S, uint8
 // the value v of zigzag position j for every decoded symbol (positions never emitted are 0).
 // Returns 0, or non-zero for the conditions on which the reference throws "Huffman bad code" /
 // "Huffman unknown symbol" and for reads the reference would do outside the chunk.
+// With WarpLockstep all 32 lanes call it together (idle lanes pass size = 0 and ignore the result).
 // ---------------------------------------------------------------------------------------------------
 MYB_HD int table_symbol(const uint8_t* groups, int table_bytes, int len, int idx, int* out) {
   int i = 0;
@@ -410,49 +479,90 @@ MYB_HD int table_symbol(const uint8_t* groups, int table_bytes, int len, int idx
   return 1;
 }
 
-template <class Emit>
-MYB_HD int huff_decode_block(const uint8_t* chunk, int size, Emit&& emit) {
-  if (size < 3) return 1;
-  const int bits = chunk[0] | (chunk[1] << 8);
-  const int table_bytes = chunk[2];
-  if (bits > 512 || 3 + table_bytes + ((bits + 7) >> 3) > size) return 1;
+template <class Emit, class W>
+MYB_HD int huff_decode_block(const uint8_t* chunk, int size, Emit&& emit, const W& warp) {
+  int err = 0;
+  int bits = 0, table_bytes = 0;
+  if (size >= 3) {
+    bits = chunk[0] | (chunk[1] << 8);
+    table_bytes = chunk[2];
+    if (bits > 512 || 3 + table_bytes + ((bits + 7) >> 3) > size) err = 1;
+  } else if (size > 0) {
+    err = 1;
+  }
+  if (err || size == 0) { bits = 0; table_bytes = 0; }
   const uint8_t* groups = chunk + 3;
-  uint64_t counts = 0;  // symbols per code length 1..8, one byte each
+  // code table: symbols per length (one byte each) and, when the groups come in non-decreasing length order
+  // with at most 32 symbols per length (every stream the reference writes for <= 32 symbols of a length),
+  // the byte offset of each length's single group, so a symbol is one 11-bit extract away.
+  uint64_t counts = 0, goff = 0;
+  bool direct = true;
   {
-    int i = 0;
-    while (i < table_bytes) {
-      const int info = groups[i];
-      const int len = (info >> 5) + 1, c = (info & 31) + 1;
-      i += 1 + ((c * 11 + 7) >> 3);
-      if (i > table_bytes) return 1;
-      const int sh = 8 * (len - 1);
-      if (((counts >> sh) & 0xff) + (uint64_t)c > 64) return 1;  // more symbols than a block can hold
-      counts += (uint64_t)c << sh;
-    }
-  }
-  const uint8_t* data = groups + table_bytes;
-  int p = 0, j = 0;
-  while (p < bits && j < 64) {
-    uint32_t code = 0, first = 0;  // uint8_t in the reference (Huffman.cpp:107-108): keep the 8-bit wrap
-    int len = 1;
-    for (; len <= 8; len++) {
-      const uint32_t c = (uint32_t)(counts >> (8 * (len - 1))) & 0xff;
-      if (p >= bits) return 1;  // "Huffman bad code" :120-122
-      code |= (uint32_t)(data[p >> 3] >> (p & 7)) & 1u;
-      p++;
-      if (code < c + first) {
-        int v;
-        if (table_symbol(groups, table_bytes, len, (int)(code - first), &v)) return 1;
-        emit(j, v);
-        j++;
-        break;
+    int i = 0, last_len = 0;
+    const int tw = warp.max(table_bytes);
+    for (int guard = 0; guard < tw; guard++) {  // at most one group per iteration, each group is >= 3 bytes
+      if (i < table_bytes && !err) {
+        const int info = groups[i];
+        const int len = (info >> 5) + 1, c = (info & 31) + 1;
+        const int sh = 8 * (len - 1);
+        if (len <= last_len) direct = false;
+        last_len = len;
+        goff |= (uint64_t)(i + 1) << sh;
+        i += 1 + ((c * 11 + 7) >> 3);
+        if (i > table_bytes || ((counts >> sh) & 0xff) + (uint64_t)c > 64) err = 1;  // more symbols than a block holds
+        counts += (uint64_t)c << sh;
       }
-      first = ((first + c) << 1) & 0xff;
-      code = (code << 1) & 0xff;
+      if (!warp.any(i < table_bytes && !err)) break;
     }
-    if (len > 8) return 1;  // "Huffman unknown symbol" :139
   }
-  return 0;
+  if (err) bits = 0;
+  const uint8_t* data = groups + table_bytes;
+  // bit reader: `acc` holds `have` not yet consumed bits of the stream, LSB first
+  uint32_t acc = 0;
+  int have = 0, nbyte = 0, p = 0, j = 0;
+  const int data_bytes = (bits + 7) >> 3;
+  while (warp.any(p < bits && j < 64)) {
+    if (p < bits && j < 64) {
+      if (have <= 8 && nbyte < data_bytes) { acc |= (uint32_t)data[nbyte++] << have; have += 8; }
+      if (have <= 8 && nbyte < data_bytes) { acc |= (uint32_t)data[nbyte++] << have; have += 8; }
+      uint32_t code = 0, first = 0;  // uint8_t in the reference (Huffman.cpp:107-108): keep the 8-bit wrap
+      int len = 1, found = 0;
+      for (; len <= 8; len++) {
+        const uint32_t c = (uint32_t)(counts >> (8 * (len - 1))) & 0xff;
+        if (p + len - 1 >= bits) break;  // "Huffman bad code" :120-122
+        code |= (acc >> (len - 1)) & 1u;
+        if (code < c + first) { found = 1; break; }
+        first = ((first + c) << 1) & 0xff;
+        code = (code << 1) & 0xff;
+      }
+      if (!found) {
+        err = 1;  // ran out of bits, or "Huffman unknown symbol" :139
+        bits = 0;
+      } else {
+        int v = 0;
+        const int idx = (int)(code - first);
+        if (direct) {
+          const int bit = idx * 11, byte = (int)((goff >> (8 * (len - 1))) & 0xff) + (bit >> 3);
+          uint32_t t = groups[byte] | ((uint32_t)groups[byte + 1] << 8);
+          if ((bit & 7) > 5) t |= (uint32_t)groups[byte + 2] << 16;
+          t = (t >> (bit & 7)) & 0x7ffu;
+          v = (t >= 1024u) ? (int)t - 2048 : (int)t;
+        } else if (table_symbol(groups, table_bytes, len, idx, &v)) {
+          err = 1;
+          bits = 0;
+        }
+        if (!err) {
+          emit(j, v);
+          j++;
+          p += len;
+          acc >>= len;
+          have -= len;
+        }
+      }
+    }
+    warp.sync();
+  }
+  return err;
 }
 
 }  // namespace myyuvb

@@ -144,7 +144,10 @@ MYB_D u64 lookback(uint64_t* status, uint32_t tile, uint32_t first, u64 aggregat
     const unsigned empty = __ballot_sync(0xffffffffu, fl == 0);
     unsigned upto = 0xffffffffu;
     if (pre) upto = (2u << (__ffs(pre) - 1)) - 1u;  // lanes up to and including the first prefix holder
-    if (empty & upto) continue;                     // a needed predecessor has not published yet
+    if (empty & upto) {                             // a needed predecessor has not published yet
+      __nanosleep(200);
+      continue;
+    }
     u64 part = (upto >> lane) & 1u ? (v & kValMask) : 0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
@@ -257,7 +260,7 @@ void launch_xrgb_to_iyuv(const uint8_t* d_bgrx, uint8_t* d_iyuv, uint32_t w, uin
 // Compression
 // ===================================================================================================
 constexpr int kStageBytes = 12 * 1024;                 // shared-memory staging of one tile's chunk bytes
-constexpr int kFastSyms = 16;                          // distinct symbols handled with shared-memory scratch
+constexpr int kFastSyms = 15;                          // distinct symbols handled with shared-memory scratch
 using FastScratch = HuffScratch<kFastSyms>;
 using BigScratch = HuffScratch<64>;
 
@@ -346,8 +349,8 @@ MYB_D void fdct_quant_pair(f2 (&x)[64], const QTables& qt, int plane, float onef
 }
 
 // blocks with more than kFastSyms distinct symbols: same code on per-thread local-memory scratch, kept out of line
-__device__ __noinline__ HuffPlan plan_big(ZShared z, int L, BigScratch bs) { return huff_plan<64>(z, L, bs); }
-__device__ __noinline__ void emit_big(ZShared z, HuffPlan pl, BigScratch bs, uint8_t* dst) { huff_emit<64>(z, pl, bs, dst); }
+__device__ __noinline__ HuffPlan plan_big(ZShared z, int L, BigScratch bs) { return huff_plan<64>(z, L, bs, NoWarp{}); }
+__device__ __noinline__ void emit_big(ZShared z, HuffPlan pl, BigScratch bs, uint8_t* dst) { huff_emit<64>(z, pl, bs, dst, NoWarp{}); }
 
 __global__ void __launch_bounds__(kCtaThreads, 3)
     dct_compress_kernel(const __grid_constant__ EncParams P, const __grid_constant__ QTables qt) {
@@ -430,24 +433,28 @@ __global__ void __launch_bounds__(kCtaThreads, 3)
       int16_t lsyms[BigScratch::kSyms];
       BigScratch bs{lbytes, lsyms, 1};
       uint32_t size = 0;
+      // all 32 lanes run the coder in lockstep; lanes without a block pose as an all-zero block and are ignored
+      int L = live ? (int)sm.lbound[blk] : 0;
+      while (L > 0 && z.get(L - 1) == 0) L--;  // exact message length (Huffman.cpp:184-190); at most 8 steps
+      __syncwarp();
+      pl = huff_plan<kFastSyms>(z, L, fs, WarpLockstep{});
+      if (live && pl.n < 0) {  // more distinct symbols than the shared-memory scratch holds
+        big = true;
+        pl = plan_big(z, L, bs);
+      }
+      __syncwarp();
       if (live) {
-        int L = sm.lbound[blk];
-        while (L > 0 && z.get(L - 1) == 0) L--;  // exact message length (Huffman.cpp:184-190)
-        pl = huff_plan<kFastSyms>(z, L, fs);
-        if (pl.n < 0) {
-          big = true;
-          pl = plan_big(z, L, bs);
-        }
         size = (uint32_t)pl.size();
         sm.csize[blk] = (uint8_t)size;
       }
       uint32_t pass_total;
       const uint32_t off = carried + cta_exclusive_scan(size, sm.warp_sums, &pass_total);
-      if (live) {
-        uint8_t* dst = (off + size <= (uint32_t)kStageBytes) ? &sm.stage[off] : overflow + off;
-        if (big) emit_big(z, pl, bs, dst);
-        else huff_emit<kFastSyms>(z, pl, fs, dst);
-      }
+      uint8_t* dst = (off + size <= (uint32_t)kStageBytes) ? &sm.stage[off] : overflow + off;
+      HuffPlan plf = pl;
+      if (!live || big) plf.n = 0;
+      huff_emit<kFastSyms>(z, plf, fs, dst, WarpLockstep{});
+      if (live && big) emit_big(z, pl, bs, dst);
+      __syncwarp();
       carried += pass_total;
     }
     __syncthreads();
@@ -693,16 +700,16 @@ __global__ void __launch_bounds__(kCtaThreads, 3)
 #pragma unroll 1
     for (int pass = 0; pass < kTileBlocks / kCtaThreads; pass++) {
       const int blk = pass * kCtaThreads + tid;
-      if ((uint32_t)blk < tc.nblk) {
-        const uint32_t off = sm.boff[blk], size = sm.csize[blk];
-        const uint8_t* chunk = (off + size <= (uint32_t)kDecStageBytes) ? &sm.stage[off] : content + off;
-        float* col = &sm.coef[0][blk];
-        const int err = huff_decode_block(chunk, (int)size, [&](int j, int v) {
-          const int pos = sm.zigzag[j];
-          col[pos * kTileBlocks] = __fmul_rn((float)v, sm.q[pos]);  // DCT.cpp:330-332
-        });
-        if (err) atomicOr(&P.ws.counters[1], kFlagHuffman);
-      }
+      const bool live = (uint32_t)blk < tc.nblk;
+      const uint32_t off = live ? sm.boff[blk] : 0u, size = live ? (uint32_t)sm.csize[blk] : 0u;
+      const uint8_t* chunk = (off + size <= (uint32_t)kDecStageBytes) ? &sm.stage[off] : content + off;
+      float* col = &sm.coef[0][live ? blk : 0];
+      // all 32 lanes decode in lockstep (idle lanes pass size 0); a zero-size chunk of a live block is malformed
+      const int err = huff_decode_block(chunk, (int)size, [&](int j, int v) {
+        const int pos = sm.zigzag[j];
+        col[pos * kTileBlocks] = __fmul_rn((float)v, sm.q[pos]);  // DCT.cpp:330-332
+      }, WarpLockstep{});
+      if (live && (err || size == 0)) atomicOr(&P.ws.counters[1], kFlagHuffman);
     }
     __syncthreads();
 
