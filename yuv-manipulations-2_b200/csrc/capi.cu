@@ -54,8 +54,14 @@ void make_qtables(const uint8_t quality[3], QTables* qt) {
       float v = roundf(prod);
       v = v < 1.0f ? 1.0f : (v > 255.0f ? 255.0f : v);
       qt->q[p][i] = v;
-      qt->rq[p][i] = 1.0f / v;  // correctly rounded reciprocal, used by the exact-division step in the kernel
     }
+    for (int a2 = 0; a2 < 4; a2++)
+      for (int b = 0; b < 8; b++) {
+        const float q0 = qt->q[p][(2 * a2) * 8 + b], q1 = qt->q[p][(2 * a2 + 1) * 8 + b];
+        // correctly rounded reciprocals, used by the exact-division step in the kernel
+        qt->rqp[p][a2 * 8 + b] = {1.0f / q0, 1.0f / q1};
+        qt->nqp[p][a2 * 8 + b] = {-q0, -q1};
+      }
   }
 }
 
@@ -128,7 +134,7 @@ int ensure_workspace(myyuvb_ctx* c, const FrameGeom& g, bool encoder, Workspace*
   }
   if (encoder) {
     if ((rc = c->d_sizes.reserve((uint64_t)g.nblk_frame * g.n_frames))) return rc;
-    if ((rc = c->d_overflow.reserve((uint64_t)c->grid * 65536))) return rc;
+    if ((rc = c->d_overflow.reserve((uint64_t)c->grid * 32768))) return rc;
   } else {
     if ((rc = c->d_desc.reserve((uint64_t)g.n_frames * 3 * sizeof(PlaneDesc)))) return rc;
   }

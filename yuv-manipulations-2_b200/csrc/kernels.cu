@@ -258,8 +258,14 @@ void launch_xrgb_to_iyuv(const uint8_t* d_bgrx, uint8_t* d_iyuv, uint32_t w, uin
 
 // ===================================================================================================
 // Compression
+// One thread = one 8x8 block for both phases (tile = 128 blocks = 128 threads), sized so that five CTAs
+// (20 warps) fit an SM: <= 102 registers, <= 44 KB shared memory.
+// The DCT is packed along the ROW-PAIR axis: lane .x = row a, lane .y = row a+1 of the same block.
+//   stage 1:  (T[a][c], T[a+1][c]) = sum_k (C[a][k], C[a+1][k]) * X[k][c]      scalar register broadcast x constant pair
+//   stage 2:  (Y[a][b], Y[a+1][b]) = sum_k (T[a][k], T[a+1][k]) * C[b][k]      data pair x broadcast immediate
+// so no transposition or register shuffling is needed between the stages (cuobjdump: 960 FMUL2/FFMA2, 0 MOV).
 // ===================================================================================================
-constexpr int kStageBytes = 12 * 1024;                 // shared-memory staging of one tile's chunk bytes
+constexpr int kStageBytes = 4 * 1024;                  // shared-memory staging of one tile's chunk bytes
 constexpr int kFastSyms = 15;                          // distinct symbols handled with shared-memory scratch
 using FastScratch = HuffScratch<kFastSyms>;
 using BigScratch = HuffScratch<64>;
@@ -269,12 +275,13 @@ struct EncSmem {
   uint8_t hs_bytes[FastScratch::kBytes][kCtaThreads];
   int16_t hs_syms[FastScratch::kSyms][kCtaThreads];
   alignas(16) uint8_t stage[kStageBytes + 8];
-  alignas(4) uint8_t lbound[kTileBlocks];              // upper bound (multiple of 8) of the message length
   alignas(4) uint8_t csize[kTileBlocks];
   uint32_t warp_sums[4];
   uint32_t tile;
+  uint32_t split;
   u64 base;
 };
+static_assert(sizeof(EncSmem) <= 44 * 1024 + 256, "EncSmem must allow 5 CTAs per SM");
 
 struct ZShared {  // accessor of one block's column in EncSmem::zz
   uint16_t* col;
@@ -292,72 +299,98 @@ struct EncParams {
   float one;
 };
 
-// forward DCT + quantisation of two blocks held as f2 x[64] (row-major), results to zz[*][b0], zz[*][b0+1]
-MYB_D void fdct_quant_pair(f2 (&x)[64], const QTables& qt, int plane, float onef, uint16_t (*zz)[kTileBlocks], int b0,
-                           uint32_t (&gor)[8]) {
+// row-major coefficient index -> zigzag scan position
+MYB_D constexpr int zigzag_of(int i) {
+  constexpr int t[64] = {0,  1,  5,  6,  14, 15, 27, 28, 2,  4,  7,  13, 16, 26, 29, 42, 3,  8,  12, 17, 25, 30,
+                         41, 43, 9,  11, 18, 24, 31, 40, 44, 53, 10, 19, 23, 32, 39, 45, 52, 54, 20, 22, 33, 38,
+                         46, 51, 55, 60, 21, 34, 37, 47, 50, 56, 59, 61, 35, 36, 48, 49, 57, 58, 62, 63};
+  return t[i];
+}
+
+MYB_D f2 mkp(float a, float b) { f2 r; r.x = a; r.y = b; return r; }
+
+// Forward DCT + quantisation of one block.  raw: 8 rows x 2 words of pixels.  Writes the 64 coefficients in
+// zigzag order to zcol[i * kTileBlocks]; returns an upper bound (multiple of 8) of the message length.
+MYB_D int fdct_quant_block(const uint32_t (&raw)[16], const QTables& qt, int plane, float onef, uint16_t* zcol) {
   const f2 ONE = dup(onef);
-  // T = C . X  (DCT.cpp:232-242): per column c, T[a][c] = sum_k C[a][k] * X[k][c], k ascending
+  // (float)px - 128 (DCT.cpp:303): 0x4B000000 | px is the float 2^23 + px; subtracting 2^23 + 128 is exact
+  float x[64];
+  {
+    const f2 bias = dup(-8388736.0f);
+#pragma unroll
+    for (int wd = 0; wd < 16; wd++) {
+#pragma unroll
+      for (int bt = 0; bt < 4; bt += 2) {
+        f2 v;
+        v.x = __uint_as_float(__byte_perm(raw[wd], 0x4B000000u, 0x7440 + bt));
+        v.y = __uint_as_float(__byte_perm(raw[wd], 0x4B000000u, 0x7441 + bt));
+        v = add2(v, bias);
+        x[wd * 4 + bt] = v.x;
+        x[wd * 4 + bt + 1] = v.y;
+      }
+    }
+  }
+  // T = C . X  (DCT.cpp:232-242), k ascending, every product and sum rounded separately
+  f2 t[32];  // t[a2 * 8 + c] = (T[2 a2][c], T[2 a2 + 1][c])
 #pragma unroll
   for (int c = 0; c < 8; c++) {
-    f2 t[8];
 #pragma unroll
-    for (int a = 0; a < 8; a++) {
-      f2 acc = mul2(x[c], dup(dct_c(a * 8)));
+    for (int a2 = 0; a2 < 4; a2++) {
+      f2 acc = mul2(dup(x[c]), mkp(dct_c(a2 * 16), dct_c(a2 * 16 + 8)));
 #pragma unroll
-      for (int k = 1; k < 8; k++) acc = sum2(acc, mul2(x[k * 8 + c], dup(dct_c(a * 8 + k))), ONE);
-      t[a] = acc;
+      for (int k = 1; k < 8; k++)
+        acc = sum2(acc, mul2(dup(x[k * 8 + c]), mkp(dct_c(a2 * 16 + k), dct_c(a2 * 16 + 8 + k))), ONE);
+      t[a2 * 8 + c] = acc;
     }
-#pragma unroll
-    for (int a = 0; a < 8; a++) x[a * 8 + c] = t[a];
   }
-  // Y = T . C^T (DCT.cpp:244-254): Y[a][b] = sum_k T[a][k] * C[b][k]
-#pragma unroll
-  for (int a = 0; a < 8; a++) {
-    f2 t[8];
-#pragma unroll
-    for (int b = 0; b < 8; b++) {
-      f2 acc = mul2(x[a * 8], dup(dct_c(b * 8)));
-#pragma unroll
-      for (int k = 1; k < 8; k++) acc = sum2(acc, mul2(x[a * 8 + k], dup(dct_c(b * 8 + k))), ONE);
-      t[b] = acc;
-    }
-#pragma unroll
-    for (int b = 0; b < 8; b++) x[a * 8 + b] = t[b];
-  }
-  // coef = (int16) round(Y / q) (DCT.cpp:274).  The divisor is an integer 1..255, so one Newton step on
-  // q0 = Y * RN(1/q) is the correctly rounded quotient: rem = Y - q*q0 is exact, and Y/q is never closer
-  // than ulp/510 to a rounding boundary while the step's error is < 2^-23 ulp (DESIGN.md "Exact division").
-  constexpr int zz_of[64] = {0,  1,  5,  6,  14, 15, 27, 28, 2,  4,  7,  13, 16, 26, 29, 42, 3,  8,  12, 17, 25, 30,
-                             41, 43, 9,  11, 18, 24, 31, 40, 44, 53, 10, 19, 23, 32, 39, 45, 52, 54, 20, 22, 33, 38,
-                             46, 51, 55, 60, 21, 34, 37, 47, 50, 56, 59, 61, 35, 36, 48, 49, 57, 58, 62, 63};
+  // Y = T . C^T (DCT.cpp:244-254): Y[a][b] = sum_k T[a][k] * C[b][k]; then coef = (int16) round(Y / q) (DCT.cpp:274).
+  // The divisor is an integer 1..255, so one Newton step on q0 = Y * RN(1/q) is the correctly rounded quotient:
+  // rem = Y - q*q0 is exact, and Y/q is never closer than ulp/510 to a rounding boundary while the step's error is
+  // < 2^-23 ulp (DESIGN.md "Exact division"; checked exhaustively around ties by tests/hostemu).
+  int gor[8];
 #pragma unroll
   for (int g8 = 0; g8 < 8; g8++) gor[g8] = 0;
 #pragma unroll
-  for (int i = 0; i < 64; i++) {
-    const f2 r = dup(qt.rq[plane][i]);
-    const f2 nq = dup(-qt.q[plane][i]);
-    const f2 q0 = mul2(x[i], r);
-    const f2 rem = fma2(nq, q0, x[i]);
-    const f2 q1 = fma2(rem, r, q0);
-    const f2 t = add2_rz(q1, half_like(q1));
-    const uint32_t na = (uint32_t)__float2int_rz(t.x), nb = (uint32_t)__float2int_rz(t.y);
-    const uint32_t packed = __byte_perm(na, nb, 0x5410);  // low halves: A | B << 16
-    const int zi = zz_of[i];
-    *reinterpret_cast<uint32_t*>(&zz[zi][b0]) = packed;
-    gor[zi >> 3] |= packed;
+  for (int a2 = 0; a2 < 4; a2++) {
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+      f2 acc = mul2(t[a2 * 8], dup(dct_c(b * 8)));
+#pragma unroll
+      for (int k = 1; k < 8; k++) acc = sum2(acc, mul2(t[a2 * 8 + k], dup(dct_c(b * 8 + k))), ONE);
+      const f2 r = mkp(qt.rqp[plane][a2 * 8 + b].x, qt.rqp[plane][a2 * 8 + b].y);
+      const f2 nq = mkp(qt.nqp[plane][a2 * 8 + b].x, qt.nqp[plane][a2 * 8 + b].y);
+      const f2 q0 = mul2(acc, r);
+      const f2 rem = fma2(nq, q0, acc);
+      const f2 q1 = fma2(rem, r, q0);
+      const f2 rr = add2_rz(q1, half_like(q1));
+      const int na = __float2int_rz(rr.x), nb = __float2int_rz(rr.y);
+      const int za = zigzag_of((2 * a2) * 8 + b), zb = zigzag_of((2 * a2 + 1) * 8 + b);
+      zcol[za * kTileBlocks] = (uint16_t)na;
+      zcol[zb * kTileBlocks] = (uint16_t)nb;
+      gor[za >> 3] |= na;
+      gor[zb >> 3] |= nb;
+    }
   }
+  int lb = 0;
+#pragma unroll
+  for (int g8 = 0; g8 < 8; g8++)
+    if (gor[g8]) lb = 8 * (g8 + 1);
+  return lb;
 }
 
 // blocks with more than kFastSyms distinct symbols: same code on per-thread local-memory scratch, kept out of line
 __device__ __noinline__ HuffPlan plan_big(ZShared z, int L, BigScratch bs) { return huff_plan<64>(z, L, bs, NoWarp{}); }
 __device__ __noinline__ void emit_big(ZShared z, HuffPlan pl, BigScratch bs, uint8_t* dst) { huff_emit<64>(z, pl, bs, dst, NoWarp{}); }
 
-__global__ void __launch_bounds__(kCtaThreads, 3)
+__global__ void __launch_bounds__(kCtaThreads, 5)
     dct_compress_kernel(const __grid_constant__ EncParams P, const __grid_constant__ QTables qt) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   EncSmem& sm = *reinterpret_cast<EncSmem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const FrameGeom& g = P.g;
+  FastScratch fs{&sm.hs_bytes[0][tid], &sm.hs_syms[0][tid], kCtaThreads};
+  ZShared z{&sm.zz[0][tid]};
+  uint8_t* const overflow = P.ws.overflow + (uint64_t)blockIdx.x * 32768u;
 
   while (true) {
     if (tid == 0) sm.tile = atomicAdd(&P.ws.counters[0], 1u);
@@ -366,139 +399,85 @@ __global__ void __launch_bounds__(kCtaThreads, 3)
     if (tile >= P.total_tiles) break;
     const TileCoord tc = tile_coord(g, tile);
     const int plane = (int)tc.plane;
-    const uint32_t pw = g.pw[plane], bw = g.bw[plane];
-    const uint8_t* plane_src = P.src + (uint64_t)tc.frame * g.frame_bytes + g.plane_off[plane];
+    const bool live = (uint32_t)tid < tc.nblk;
 
-    // ---- phase A: load two blocks per thread, forward DCT, quantise, coefficients to shared memory ----
+    // ---- phase A: load the block, forward DCT, quantise, coefficients (zigzag order) to shared memory ----
+    int L;
     {
-      const int b0 = 2 * tid;
-      f2 x[64];
-      uint32_t raw[2][16];
-#pragma unroll
-      for (int s = 0; s < 2; s++) {
-        const uint32_t b = (uint32_t)b0 + s;
-        if (b < tc.nblk) {
-          const uint32_t k = tc.k0 + b;
-          const uint32_t by = k / bw, bx = k - by * bw;
-          const uint8_t* p = plane_src + (uint64_t)by * 8 * pw + (uint64_t)bx * 8;
-#pragma unroll
-          for (int r = 0; r < 8; r++) {
-            const uint2 v = __ldg(reinterpret_cast<const uint2*>(p + (uint64_t)r * pw));
-            raw[s][2 * r] = v.x;
-            raw[s][2 * r + 1] = v.y;
-          }
-        } else {
-#pragma unroll
-          for (int r = 0; r < 16; r++) raw[s][r] = 0x80808080u;
-        }
-      }
-      // (float)px - 128 (DCT.cpp:303): 0x4B000000 | px is the float 2^23 + px; subtracting 2^23 + 128 is exact
-      const f2 bias = dup(-8388736.0f);
-#pragma unroll
-      for (int wd = 0; wd < 16; wd++) {
-#pragma unroll
-        for (int bt = 0; bt < 4; bt++) {
-          f2 v;
-          v.x = __uint_as_float(__byte_perm(raw[0][wd], 0x4B000000u, 0x7440 + bt));
-          v.y = __uint_as_float(__byte_perm(raw[1][wd], 0x4B000000u, 0x7440 + bt));
-          x[wd * 4 + bt] = add2(v, bias);
-        }
-      }
-      uint32_t gor[8];
-      fdct_quant_pair(x, qt, plane, P.one, sm.zz, b0, gor);
-      // upper bound of the message length per block: highest group of 8 zigzag positions with a non-zero
-      int la = 0, lb = 0;
-#pragma unroll
-      for (int g8 = 0; g8 < 8; g8++) {
-        if (gor[g8] & 0xffffu) la = 8 * (g8 + 1);
-        if (gor[g8] >> 16) lb = 8 * (g8 + 1);
-      }
-      *reinterpret_cast<uint16_t*>(&sm.lbound[b0]) = (uint16_t)(la | (lb << 8));
-    }
-    __syncthreads();
-
-    // ---- phase B: one block per thread, two passes in raster order; chunk bytes staged in tile order ----
-    FastScratch fs{&sm.hs_bytes[0][tid], &sm.hs_syms[0][tid], kCtaThreads};
-    uint8_t* const overflow = P.ws.overflow + (uint64_t)blockIdx.x * 65536u;
-    uint32_t carried = 0;  // bytes staged by earlier passes
-#pragma unroll 1
-    for (int pass = 0; pass < kTileBlocks / kCtaThreads; pass++) {
-      const int blk = pass * kCtaThreads + tid;
-      const bool live = (uint32_t)blk < tc.nblk;
-      ZShared z{&sm.zz[0][blk]};
-      HuffPlan pl;
-      pl.n = 0;
-      bool big = false;
-      uint8_t lbytes[BigScratch::kBytes];
-      int16_t lsyms[BigScratch::kSyms];
-      BigScratch bs{lbytes, lsyms, 1};
-      uint32_t size = 0;
-      // all 32 lanes run the coder in lockstep; lanes without a block pose as an all-zero block and are ignored
-      int L = live ? (int)sm.lbound[blk] : 0;
-      while (L > 0 && z.get(L - 1) == 0) L--;  // exact message length (Huffman.cpp:184-190); at most 8 steps
-      __syncwarp();
-      pl = huff_plan<kFastSyms>(z, L, fs, WarpLockstep{});
-      if (live && pl.n < 0) {  // more distinct symbols than the shared-memory scratch holds
-        big = true;
-        pl = plan_big(z, L, bs);
-      }
-      __syncwarp();
+      uint32_t raw[16];
       if (live) {
-        size = (uint32_t)pl.size();
-        sm.csize[blk] = (uint8_t)size;
+        const uint32_t pw = g.pw[plane], bw = g.bw[plane];
+        const uint32_t k = tc.k0 + tid;
+        const uint32_t by = k / bw, bx = k - by * bw;
+        const uint8_t* p = P.src + (uint64_t)tc.frame * g.frame_bytes + g.plane_off[plane] + (uint64_t)by * 8 * pw + (uint64_t)bx * 8;
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+          const uint2 v = __ldg(reinterpret_cast<const uint2*>(p + (uint64_t)r * pw));
+          raw[2 * r] = v.x;
+          raw[2 * r + 1] = v.y;
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < 16; r++) raw[r] = 0x80808080u;
       }
-      uint32_t pass_total;
-      const uint32_t off = carried + cta_exclusive_scan(size, sm.warp_sums, &pass_total);
+      L = fdct_quant_block(raw, qt, plane, P.one, z.col);
+    }
+    // ---- phase B: entropy-code the block (same thread, so no CTA barrier in between); warp lockstep ----
+    if (!live) L = 0;
+    while (L > 0 && z.get(L - 1) == 0) L--;  // exact message length (Huffman.cpp:184-190); at most 8 steps
+    __syncwarp();
+    HuffPlan pl = huff_plan<kFastSyms>(z, L, fs, WarpLockstep{});
+    bool big = false;
+    uint8_t lbytes[BigScratch::kBytes];
+    int16_t lsyms[BigScratch::kSyms];
+    BigScratch bs{lbytes, lsyms, 1};
+    if (live && pl.n < 0) {  // more distinct symbols than the shared-memory scratch holds
+      big = true;
+      pl = plan_big(z, L, bs);
+    }
+    __syncwarp();
+    const uint32_t size = live ? (uint32_t)pl.size() : 0u;
+    sm.csize[tid] = (uint8_t)size;
+    uint32_t total;
+    const uint32_t off = cta_exclusive_scan(size, sm.warp_sums, &total);
+    {
       uint8_t* dst = (off + size <= (uint32_t)kStageBytes) ? &sm.stage[off] : overflow + off;
       HuffPlan plf = pl;
       if (!live || big) plf.n = 0;
       huff_emit<kFastSyms>(z, plf, fs, dst, WarpLockstep{});
       if (live && big) emit_big(z, pl, bs, dst);
-      __syncwarp();
-      carried += pass_total;
     }
+    // first chunk that did not fit the shared staging buffer (chunks never straddle; offsets are increasing)
+    if (tid == 0) sm.split = total;
     __syncthreads();
+    if (live && off + size > (uint32_t)kStageBytes && off <= (uint32_t)kStageBytes) atomicMin(&sm.split, off);
 
     // ---- tile offset: decoupled look-back over all tiles of the batch in file order ----
     if (wid == 0) {
-      const u64 excl = lookback(P.ws.tile_status, tile, 0, carried, lane);
+      const u64 excl = lookback(P.ws.tile_status, tile, 0, total, lane);
       if (lane == 0) {
         sm.base = excl;
         if (tc.k0 == 0) P.ws.plane_start[tc.frame * 3 + plane] = excl;               // code bytes before this plane
-        if (tile == P.total_tiles - 1) P.ws.plane_start[g.n_frames * 3] = excl + carried;
+        if (tile == P.total_tiles - 1) P.ws.plane_start[g.n_frames * 3] = excl + total;
       }
     }
     __syncthreads();
     // chunk sizes go to a linear side array; finalize_frames_kernel moves them behind the plane headers,
     // whose position depends on the (data dependent) size of the previous planes
-    {
+    if (live) {
       const uint64_t gblk = (uint64_t)tc.frame * g.nblk_frame + (plane > 0 ? g.nblk[0] : 0) + (plane > 1 ? g.nblk[1] : 0) + tc.k0;
-      for (uint32_t b = tid; b < tc.nblk; b += kCtaThreads) P.ws.chunk_sizes[gblk + b] = sm.csize[b];
+      P.ws.chunk_sizes[gblk + tid] = (uint8_t)size;
     }
     // content bytes: absolute position = fixed part (headers + size arrays up to this plane) + code bytes before
     {
-      uint32_t fixed = 12 + 8 * (plane + 1) + g.nblk[0] + (plane > 0 ? g.nblk[1] : 0) + (plane > 1 ? g.nblk[2] : 0);
+      const uint32_t fixed = 12 + 8 * (plane + 1) + g.nblk[0] + (plane > 0 ? g.nblk[1] : 0) + (plane > 1 ? g.nblk[2] : 0);
       const u64 pos = (u64)tc.frame * (36 + g.nblk_frame) + fixed + sm.base;
-      if (pos + carried > P.out_cap) {
+      if (pos + total > P.out_cap) {
         if (tid == 0) atomicOr(&P.ws.counters[1], kFlagCapacity);
       } else {
-        const uint32_t in_smem = carried < (uint32_t)kStageBytes ? carried : (uint32_t)kStageBytes;
-        // staged bytes beyond the last whole chunk that fits in shared memory live in the overflow area;
-        // chunks never straddle, so copy [0, split) from shared memory and [split, carried) from global
-        uint32_t split = in_smem;
-        if (carried > (uint32_t)kStageBytes) {
-          // recompute the split point: first chunk whose end exceeds kStageBytes starts the overflow part
-          // (tile order = raster order, offsets are the running sum of csize)
-          if (tid == 0) {
-            uint32_t run = 0, b = 0;
-            while (b < tc.nblk && run + sm.csize[b] <= (uint32_t)kStageBytes) run += sm.csize[b++];
-            sm.warp_sums[0] = run;
-          }
-          __syncthreads();
-          split = sm.warp_sums[0];
-        }
+        const uint32_t split = sm.split;
         copy_smem_to_global(P.out + pos, sm.stage, split);
-        for (uint32_t i = split + tid; i < carried; i += kCtaThreads) P.out[pos + i] = overflow[i];
+        for (uint32_t i = split + tid; i < total; i += kCtaThreads) P.out[pos + i] = overflow[i];
       }
     }
     __syncthreads();  // shared memory is reused by the next tile
@@ -541,24 +520,23 @@ int codec_grid_size(int device, bool encoder) {
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
   (void)encoder;
-  return sms * 3;
+  return sms * 5;
 }
 
 // ===================================================================================================
-// Decompression
+// Decompression (one thread = one block; tile = 128 blocks; five CTAs per SM)
 // ===================================================================================================
-constexpr int kDecStageBytes = 8 * 1024;
+constexpr int kDecStageBytes = 4 * 1024;
 struct DecSmem {
   float coef[64][kTileBlocks];        // dequantised coefficients B[k][c] (row-major index), per block column
-  uint8_t stage[kDecStageBytes];      // the tile's chunk bytes
-  uint32_t boff[kTileBlocks];         // chunk offset of each block inside the tile
-  alignas(4) uint8_t csize[kTileBlocks];
+  alignas(16) uint8_t stage[kDecStageBytes];  // the tile's chunk bytes
   uint8_t zigzag[64];
   float q[64];
   uint32_t warp_sums[4];
   uint32_t tile;
   u64 base;
 };
+static_assert(sizeof(DecSmem) <= 44 * 1024 + 256, "DecSmem must allow 5 CTAs per SM");
 
 struct DecParams {
   const uint8_t* payloads;
@@ -599,38 +577,46 @@ __global__ void parse_payload_kernel(const __grid_constant__ DecParams P) {
   }
 }
 
-// inverse DCT of two blocks: x = B (dequantised), D = C^T . B, P = D . C (DCT.cpp:333-334, :256-266, :232-242)
-MYB_D void idct_pair(f2 (&x)[64], float onef) {
+// Inverse DCT of one block, packed along the row-pair axis like the forward transform:
+//   D = C^T . B :  (D[a][c], D[a+1][c]) = sum_k (C[k][a], C[k][a+1]) * B[k][c]       (DCT.cpp:256-266)
+//   P = D . C   :  (P[a][b], P[a+1][b]) = sum_k (D[a][k], D[a+1][k]) * C[k][b]       (DCT.cpp:232-242)
+// followed by round, +128, clamp (DCT.cpp:360).  out[r] = 8 pixels of row r as two words.
+MYB_D void idct_block(const float* col, float onef, uint32_t (&out)[16]) {
   const f2 ONE = dup(onef);
+  f2 d[32];  // d[a2 * 8 + c] = (D[2 a2][c], D[2 a2 + 1][c])
 #pragma unroll
-  for (int c = 0; c < 8; c++) {  // D[a][c] = sum_k C[k][a] * B[k][c]
-    f2 t[8];
+  for (int c = 0; c < 8; c++) {
+    float bk[8];
 #pragma unroll
-    for (int a = 0; a < 8; a++) {
-      f2 acc = mul2(x[c], dup(dct_c(a)));
+    for (int k = 0; k < 8; k++) bk[k] = col[(k * 8 + c) * kTileBlocks];
 #pragma unroll
-      for (int k = 1; k < 8; k++) acc = sum2(acc, mul2(x[k * 8 + c], dup(dct_c(k * 8 + a))), ONE);
-      t[a] = acc;
+    for (int a2 = 0; a2 < 4; a2++) {
+      f2 acc = mul2(dup(bk[0]), mkp(dct_c(2 * a2), dct_c(2 * a2 + 1)));
+#pragma unroll
+      for (int k = 1; k < 8; k++) acc = sum2(acc, mul2(dup(bk[k]), mkp(dct_c(k * 8 + 2 * a2), dct_c(k * 8 + 2 * a2 + 1))), ONE);
+      d[a2 * 8 + c] = acc;
     }
-#pragma unroll
-    for (int a = 0; a < 8; a++) x[a * 8 + c] = t[a];
   }
 #pragma unroll
-  for (int a = 0; a < 8; a++) {  // P[a][b] = sum_k D[a][k] * C[k][b]
-    f2 t[8];
+  for (int r = 0; r < 16; r++) out[r] = 0;
+#pragma unroll
+  for (int a2 = 0; a2 < 4; a2++) {
 #pragma unroll
     for (int b = 0; b < 8; b++) {
-      f2 acc = mul2(x[a * 8], dup(dct_c(b)));
+      f2 acc = mul2(d[a2 * 8], dup(dct_c(b)));
 #pragma unroll
-      for (int k = 1; k < 8; k++) acc = sum2(acc, mul2(x[a * 8 + k], dup(dct_c(k * 8 + b))), ONE);
-      t[b] = acc;
+      for (int k = 1; k < 8; k++) acc = sum2(acc, mul2(d[a2 * 8 + k], dup(dct_c(k * 8 + b))), ONE);
+      const f2 t = add2_rz(acc, half_like(acc));
+      // clamp((int)round(v) + 128, 0, 255)  (DCT.cpp:360)
+      const uint32_t ia = (uint32_t)__viaddmin_s32_relu(__float2int_rz(t.x), 128, 255);
+      const uint32_t ib = (uint32_t)__viaddmin_s32_relu(__float2int_rz(t.y), 128, 255);
+      out[(2 * a2) * 2 + (b >> 2)] |= ia << (8 * (b & 3));
+      out[(2 * a2 + 1) * 2 + (b >> 2)] |= ib << (8 * (b & 3));
     }
-#pragma unroll
-    for (int b = 0; b < 8; b++) x[a * 8 + b] = t[b];
   }
 }
 
-__global__ void __launch_bounds__(kCtaThreads, 3)
+__global__ void __launch_bounds__(kCtaThreads, 5)
     dct_decompress_kernel(const __grid_constant__ DecParams P, const __grid_constant__ QTables qt) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   DecSmem& sm = *reinterpret_cast<DecSmem*>(smem_raw);
@@ -641,6 +627,7 @@ __global__ void __launch_bounds__(kCtaThreads, 3)
     sm.zigzag[tid] = zz[tid];
   }
   int q_plane = -1;
+  float* const col = &sm.coef[0][tid];
 
   while (true) {
     __syncthreads();  // previous tile done with shared memory (and zigzag table visible)
@@ -656,33 +643,21 @@ __global__ void __launch_bounds__(kCtaThreads, 3)
       if (tid < 64) sm.q[tid] = qt.q[plane][tid];
       q_plane = plane;
     }
+    const bool live = (uint32_t)tid < tc.nblk;
     // chunk sizes of the tile, CTA scan, plane-local look-back -> byte offset of the tile inside content[]
-    const uint8_t* sizes = P.payloads + d.sizes_off + tc.k0;
-    uint32_t my = 0;
-    {
-      const uint32_t b = 2 * tid;
-      uint32_t s0 = 0, s1 = 0;
-      if (b < tc.nblk) s0 = sizes[b];
-      if (b + 1 < tc.nblk) s1 = sizes[b + 1];
-      sm.csize[b] = (uint8_t)s0;
-      sm.csize[b + 1] = (uint8_t)s1;
-      my = s0 + s1;
-    }
+    const uint32_t size = live ? (uint32_t)P.payloads[d.sizes_off + tc.k0 + tid] : 0u;
     uint32_t total;
-    const uint32_t pair_off = cta_exclusive_scan(my, sm.warp_sums, &total);
+    const uint32_t off = cta_exclusive_scan(size, sm.warp_sums, &total);
     if (wid == 0) {
       const u64 excl = lookback(P.ws.tile_status, tile, tc.first_tile_of_plane, total, lane);
       if (lane == 0) sm.base = excl;
     }
-    // zero the coefficient tile while warp 0 looks back
-    {
-      float4* c4 = reinterpret_cast<float4*>(&sm.coef[0][0]);
-      for (int i = tid; i < 64 * kTileBlocks / 4; i += kCtaThreads) c4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+    // zero this thread's coefficient column while warp 0 looks back
+#pragma unroll
+    for (int i = 0; i < 64; i++) col[i * kTileBlocks] = 0.0f;
     __syncthreads();
     const u64 base = sm.base;
-    const bool tile_ok = base + total <= d.content_size;  // chunks must lie inside content[] (UB in the reference)
-    if (!tile_ok) {
+    if (base + total > d.content_size) {  // chunks must lie inside content[] (undefined behaviour in the reference)
       if (tid == 0) atomicOr(&P.ws.counters[1], kFlagHuffman);
       continue;
     }
@@ -692,66 +667,29 @@ __global__ void __launch_bounds__(kCtaThreads, 3)
       const uint32_t n = total < (uint32_t)kDecStageBytes ? total : (uint32_t)kDecStageBytes;
       for (uint32_t i = tid; i < n; i += kCtaThreads) sm.stage[i] = __ldg(content + i);
     }
-    sm.boff[2 * tid] = pair_off;
-    sm.boff[2 * tid + 1] = pair_off + sm.csize[2 * tid];
     __syncthreads();
 
-    // ---- phase 1: one block per thread: canonical Huffman decode + dequantise into shared memory ----
-#pragma unroll 1
-    for (int pass = 0; pass < kTileBlocks / kCtaThreads; pass++) {
-      const int blk = pass * kCtaThreads + tid;
-      const bool live = (uint32_t)blk < tc.nblk;
-      const uint32_t off = live ? sm.boff[blk] : 0u, size = live ? (uint32_t)sm.csize[blk] : 0u;
+    // ---- phase 1: canonical Huffman decode + dequantise into the thread's shared-memory column (warp lockstep) ----
+    {
       const uint8_t* chunk = (off + size <= (uint32_t)kDecStageBytes) ? &sm.stage[off] : content + off;
-      float* col = &sm.coef[0][live ? blk : 0];
-      // all 32 lanes decode in lockstep (idle lanes pass size 0); a zero-size chunk of a live block is malformed
       const int err = huff_decode_block(chunk, (int)size, [&](int j, int v) {
         const int pos = sm.zigzag[j];
         col[pos * kTileBlocks] = __fmul_rn((float)v, sm.q[pos]);  // DCT.cpp:330-332
       }, WarpLockstep{});
-      if (live && (err || size == 0)) atomicOr(&P.ws.counters[1], kFlagHuffman);
+      if (live && (err || size == 0)) atomicOr(&P.ws.counters[1], kFlagHuffman);  // a chunk is at least 7 bytes
     }
-    __syncthreads();
-
-    // ---- phase 2: two blocks per thread: inverse DCT, round, clamp, store ----
+    __syncwarp();
+    // ---- phase 2: inverse DCT, round, clamp, store ----
     {
-      const int b0 = 2 * tid;
-      if ((uint32_t)b0 < tc.nblk) {
-        f2 x[64];
-#pragma unroll
-        for (int i = 0; i < 64; i++) x[i] = *reinterpret_cast<const f2*>(&sm.coef[i][b0]);
-        idct_pair(x, P.one);
+      uint32_t outw[16];
+      idct_block(col, P.one, outw);
+      if (live) {
         const uint32_t pw = g.pw[plane], bw = g.bw[plane];
-        uint8_t* plane_dst = P.dst + (uint64_t)tc.frame * g.frame_bytes + g.plane_off[plane];
-        uint32_t outw[2][16];
+        const uint32_t k = tc.k0 + tid;
+        const uint32_t by = k / bw, bx = k - by * bw;
+        uint8_t* p = P.dst + (uint64_t)tc.frame * g.frame_bytes + g.plane_off[plane] + (uint64_t)by * 8 * pw + (uint64_t)bx * 8;
 #pragma unroll
-        for (int wd = 0; wd < 16; wd++) {
-          uint32_t pa = 0, pb = 0;
-#pragma unroll
-          for (int bt = 0; bt < 4; bt++) {
-            const f2 v = x[wd * 4 + bt];
-            const f2 t = add2_rz(v, half_like(v));
-            // clamp((int)round(v) + 128, 0, 255)  (DCT.cpp:360)
-            const int ia = __viaddmin_s32_relu(__float2int_rz(t.x), 128, 255);
-            const int ib = __viaddmin_s32_relu(__float2int_rz(t.y), 128, 255);
-            pa |= (uint32_t)ia << (8 * bt);
-            pb |= (uint32_t)ib << (8 * bt);
-          }
-          outw[0][wd] = pa;
-          outw[1][wd] = pb;
-        }
-#pragma unroll
-        for (int s = 0; s < 2; s++) {
-          const uint32_t b = (uint32_t)b0 + s;
-          if (b < tc.nblk) {
-            const uint32_t k = tc.k0 + b;
-            const uint32_t by = k / bw, bx = k - by * bw;
-            uint8_t* p = plane_dst + (uint64_t)by * 8 * pw + (uint64_t)bx * 8;
-#pragma unroll
-            for (int r = 0; r < 8; r++)
-              *reinterpret_cast<uint2*>(p + (uint64_t)r * pw) = make_uint2(outw[s][2 * r], outw[s][2 * r + 1]);
-          }
-        }
+        for (int r = 0; r < 8; r++) *reinterpret_cast<uint2*>(p + (uint64_t)r * pw) = make_uint2(outw[2 * r], outw[2 * r + 1]);
       }
     }
   }

@@ -5,7 +5,7 @@
 
 namespace myyuvb {
 
-constexpr int kTileBlocks = 256;   // 8x8 blocks per tile (one CTA pass)
+constexpr int kTileBlocks = 128;   // 8x8 blocks per tile (one per thread)
 constexpr int kCtaThreads = 128;   // threads per CTA of the codec kernels
 
 // error bits raised by kernels (OR-ed into Workspace::flags)
@@ -18,9 +18,13 @@ enum : uint32_t {
 
 // Quantisation tables of the three planes, computed on the host with the reference's float expression
 // (DCT.cpp:286-290).  q = divisor / dequantisation factor, rq = correctly rounded 1/q.
+struct QPair {
+  float x, y;
+};
 struct QTables {
-  float q[3][64];
-  float rq[3][64];
+  float q[3][64];        // row-major, decoder side (coef * q)
+  QPair rqp[3][32];      // [a/2 * 8 + b] = (1/q[a][b], 1/q[a+1][b]) for even a: the encoder's row-pair lanes
+  QPair nqp[3][32];      // [a/2 * 8 + b] = (-q[a][b], -q[a+1][b])
 };
 
 // Geometry shared by all frames of a batch.
@@ -44,7 +48,7 @@ struct Workspace {
   uint64_t* plane_start;   // [n_frames*3 + 1] code bytes before each plane (compress)
   uint32_t* counters;      // [0] tile ticket, [1] error flags
   uint8_t* chunk_sizes;    // [n_frames * nblk_frame] per-block chunk size, linear block order (compress)
-  uint8_t* overflow;       // [grid * 65536] staging overflow area (compress)
+  uint8_t* overflow;       // [grid * 32768] staging overflow area (compress; a tile is at most 128 * 255 bytes)
   void* plane_desc;        // [n_frames*3] PlaneDesc (decompress)
   int grid;                // persistent grid size of the codec kernels
   cudaEvent_t k_begin, k_end;  // recorded around the main codec kernel of each launch (myyuvb_last_kernel_ms)
