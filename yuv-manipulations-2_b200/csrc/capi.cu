@@ -113,7 +113,7 @@ struct myyuvb_ctx {
   int device = 0;
   cudaStream_t stream = nullptr, copy_stream = nullptr;
   bool own_stream = false;
-  int grid = 0;
+  int grid = 0, grid_dec = 0;
   Buffer d_in, d_out, d_status, d_tiles, d_plane_start, d_counters, d_sizes, d_overflow, d_desc, d_offsets;
   Buffer h_small, h_stage_in, h_stage_out;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -134,7 +134,7 @@ int ensure_workspace(myyuvb_ctx* c, const FrameGeom& g, bool encoder, Workspace*
   }
   if (encoder) {
     if ((rc = c->d_sizes.reserve((uint64_t)g.nblk_frame * g.n_frames))) return rc;
-    if ((rc = c->d_overflow.reserve((uint64_t)c->grid * 32768))) return rc;
+    if ((rc = c->d_overflow.reserve((uint64_t)c->grid * kEncTile * 256))) return rc;
   } else {
     if ((rc = c->d_desc.reserve((uint64_t)g.n_frames * 3 * sizeof(PlaneDesc)))) return rc;
   }
@@ -144,7 +144,7 @@ int ensure_workspace(myyuvb_ctx* c, const FrameGeom& g, bool encoder, Workspace*
   ws->chunk_sizes = c->d_sizes.as<uint8_t>();
   ws->overflow = c->d_overflow.as<uint8_t>();
   ws->plane_desc = c->d_desc.p;
-  ws->grid = c->grid;
+  ws->grid = encoder ? c->grid : c->grid_dec;
   ws->k_begin = c->kev[0];
   ws->k_end = c->kev[1];
   return MYYUVB_OK;
@@ -211,6 +211,7 @@ int myyuvb_ctx_create(int device, void* stream, myyuvb_ctx** out) {
   for (auto& ev : c->ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   for (auto& ev : c->kev) CU(cudaEventCreate(&ev));
   c->grid = codec_grid_size(device, true);
+  c->grid_dec = codec_grid_size(device, false);
   *out = c;
   return MYYUVB_OK;
 }
@@ -281,7 +282,7 @@ int myyuvb_dct_compress_batch_dev(myyuvb_ctx* c, const uint8_t* d_iyuv, uint32_t
   if ((rc = check_dims(w, h))) return rc;
   if ((uintptr_t)d_iyuv & 7) return fail(MYYUVB_ERR_ARG, "device input must be 8-byte aligned");
   CU(cudaSetDevice(c->device));
-  const FrameGeom g = make_geom(w, h, n_frames);
+  const FrameGeom g = make_geom(w, h, n_frames, kEncTile);
   if ((uint64_t)g.tiles_per_frame * n_frames > 0x7fffffffull) return fail(MYYUVB_ERR_TOO_LARGE, "batch too large");
   Workspace ws;
   if ((rc = ensure_workspace(c, g, true, &ws))) return rc;
@@ -300,7 +301,7 @@ int myyuvb_dct_decompress_batch_dev(myyuvb_ctx* c, const uint8_t* d_payloads, co
   if ((rc = check_dims(w, h))) return rc;
   if ((uintptr_t)d_iyuv & 7) return fail(MYYUVB_ERR_ARG, "device output must be 8-byte aligned");
   CU(cudaSetDevice(c->device));
-  const FrameGeom g = make_geom(w, h, n_frames);
+  const FrameGeom g = make_geom(w, h, n_frames, kDecTile);
   if ((uint64_t)g.tiles_per_frame * n_frames > 0x7fffffffull) return fail(MYYUVB_ERR_TOO_LARGE, "batch too large");
   Workspace ws;
   if ((rc = ensure_workspace(c, g, false, &ws))) return rc;

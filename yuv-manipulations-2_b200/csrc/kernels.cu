@@ -77,8 +77,9 @@ MYB_D constexpr float dct_c(int i) {
 // ---------------------------------------------------------------------------------------------------
 // geometry
 // ---------------------------------------------------------------------------------------------------
-FrameGeom make_geom(uint32_t width, uint32_t height, uint32_t n_frames) {
+FrameGeom make_geom(uint32_t width, uint32_t height, uint32_t n_frames, uint32_t tile_blocks) {
   FrameGeom g{};
+  g.tile_blocks = tile_blocks;
   g.width = width; g.height = height; g.n_frames = n_frames;
   g.pw[0] = width; g.ph[0] = height;
   g.pw[1] = g.pw[2] = width / 2; g.ph[1] = g.ph[2] = height / 2;
@@ -90,7 +91,7 @@ FrameGeom make_geom(uint32_t width, uint32_t height, uint32_t n_frames) {
   for (int p = 0; p < 3; p++) {
     g.bw[p] = g.pw[p] / 8;
     g.nblk[p] = g.bw[p] * (g.ph[p] / 8);
-    g.tiles[p] = (g.nblk[p] + kTileBlocks - 1) / kTileBlocks;
+    g.tiles[p] = (g.nblk[p] + tile_blocks - 1) / tile_blocks;
     g.tiles_per_frame += g.tiles[p];
     g.nblk_frame += g.nblk[p];
   }
@@ -110,9 +111,9 @@ MYB_D TileCoord tile_coord(const FrameGeom& g, uint32_t tile) {
   t.plane = 0;
   if (r >= g.tiles[0]) { r -= g.tiles[0]; base += g.tiles[0]; t.plane = 1; }
   if (t.plane == 1 && r >= g.tiles[1]) { r -= g.tiles[1]; base += g.tiles[1]; t.plane = 2; }
-  t.k0 = r * kTileBlocks;
+  t.k0 = r * g.tile_blocks;
   const uint32_t left = g.nblk[t.plane] - t.k0;
-  t.nblk = left < (uint32_t)kTileBlocks ? left : (uint32_t)kTileBlocks;
+  t.nblk = left < g.tile_blocks ? left : g.tile_blocks;
   t.first_tile_of_plane = base;
   return t;
 }
@@ -265,7 +266,7 @@ void launch_xrgb_to_iyuv(const uint8_t* d_bgrx, uint8_t* d_iyuv, uint32_t w, uin
 //   stage 2:  (Y[a][b], Y[a+1][b]) = sum_k (T[a][k], T[a+1][k]) * C[b][k]      data pair x broadcast immediate
 // so no transposition or register shuffling is needed between the stages (cuobjdump: 960 FMUL2/FFMA2, 0 MOV).
 // ===================================================================================================
-constexpr int kStageBytes = 4 * 1024;                  // shared-memory staging of one tile's chunk bytes
+constexpr int kStageBytes = 12 * 1024;                 // shared-memory staging of one tile's chunk bytes
 constexpr int kFastSyms = 15;                          // distinct symbols handled with shared-memory scratch
 using FastScratch = HuffScratch<kFastSyms>;
 using BigScratch = HuffScratch<64>;
@@ -275,13 +276,12 @@ struct EncSmem {
   uint8_t hs_bytes[FastScratch::kBytes][kCtaThreads];
   int16_t hs_syms[FastScratch::kSyms][kCtaThreads];
   alignas(16) uint8_t stage[kStageBytes + 8];
-  alignas(4) uint8_t csize[kTileBlocks];
   uint32_t warp_sums[4];
   uint32_t tile;
   uint32_t split;
   u64 base;
 };
-static_assert(sizeof(EncSmem) <= 44 * 1024 + 256, "EncSmem must allow 5 CTAs per SM");
+static_assert(sizeof(EncSmem) <= 55 * 1024, "EncSmem must allow 4 CTAs per SM");
 
 struct ZShared {  // accessor of one block's column in EncSmem::zz
   uint16_t* col;
@@ -382,7 +382,7 @@ MYB_D int fdct_quant_block(const uint32_t (&raw)[16], const QTables& qt, int pla
 __device__ __noinline__ HuffPlan plan_big(ZShared z, int L, BigScratch bs) { return huff_plan<64>(z, L, bs, NoWarp{}); }
 __device__ __noinline__ void emit_big(ZShared z, HuffPlan pl, BigScratch bs, uint8_t* dst) { huff_emit<64>(z, pl, bs, dst, NoWarp{}); }
 
-__global__ void __launch_bounds__(kCtaThreads, 5)
+__global__ void __launch_bounds__(kCtaThreads, 4)
     dct_compress_kernel(const __grid_constant__ EncParams P, const __grid_constant__ QTables qt) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   EncSmem& sm = *reinterpret_cast<EncSmem*>(smem_raw);
@@ -390,94 +390,103 @@ __global__ void __launch_bounds__(kCtaThreads, 5)
   const FrameGeom& g = P.g;
   FastScratch fs{&sm.hs_bytes[0][tid], &sm.hs_syms[0][tid], kCtaThreads};
   ZShared z{&sm.zz[0][tid]};
-  uint8_t* const overflow = P.ws.overflow + (uint64_t)blockIdx.x * 32768u;
+  uint8_t* const overflow = P.ws.overflow + (uint64_t)blockIdx.x * (kEncTile * 256u);
 
   while (true) {
-    if (tid == 0) sm.tile = atomicAdd(&P.ws.counters[0], 1u);
+    if (tid == 0) {
+      sm.tile = atomicAdd(&P.ws.counters[0], 1u);
+      sm.split = 0xffffffffu;
+    }
     __syncthreads();
     const uint32_t tile = sm.tile;
     if (tile >= P.total_tiles) break;
     const TileCoord tc = tile_coord(g, tile);
     const int plane = (int)tc.plane;
-    const bool live = (uint32_t)tid < tc.nblk;
+    const uint32_t pw = g.pw[plane], bw = g.bw[plane];
+    const uint8_t* plane_src = P.src + (uint64_t)tc.frame * g.frame_bytes + g.plane_off[plane];
+    const uint64_t gblk0 = (uint64_t)tc.frame * g.nblk_frame + (plane > 0 ? g.nblk[0] : 0) + (plane > 1 ? g.nblk[1] : 0) + tc.k0;
+    uint32_t carried = 0;  // chunk bytes staged by the earlier passes of this tile
 
-    // ---- phase A: load the block, forward DCT, quantise, coefficients (zigzag order) to shared memory ----
-    int L;
-    {
-      uint32_t raw[16];
-      if (live) {
-        const uint32_t pw = g.pw[plane], bw = g.bw[plane];
-        const uint32_t k = tc.k0 + tid;
-        const uint32_t by = k / bw, bx = k - by * bw;
-        const uint8_t* p = P.src + (uint64_t)tc.frame * g.frame_bytes + g.plane_off[plane] + (uint64_t)by * 8 * pw + (uint64_t)bx * 8;
+    // A tile is kEncPasses passes of 128 blocks (one per thread) so that the serial look-back chain advances
+    // 512 blocks per hop; each pass runs phase A (DCT) and phase B (entropy coding) and appends to the staging area.
+#pragma unroll 1
+    for (uint32_t pass = 0; pass * kTileBlocks < tc.nblk; pass++) {
+      const uint32_t blk = pass * kTileBlocks + tid;
+      const bool live = blk < tc.nblk;
+      // ---- phase A: load the block, forward DCT, quantise, coefficients (zigzag order) to shared memory ----
+      int L;
+      {
+        uint32_t raw[16];
+        if (live) {
+          const uint32_t k = tc.k0 + blk;
+          const uint32_t by = k / bw, bx = k - by * bw;
+          const uint8_t* p = plane_src + (uint64_t)by * 8 * pw + (uint64_t)bx * 8;
 #pragma unroll
-        for (int r = 0; r < 8; r++) {
-          const uint2 v = __ldg(reinterpret_cast<const uint2*>(p + (uint64_t)r * pw));
-          raw[2 * r] = v.x;
-          raw[2 * r + 1] = v.y;
+          for (int r = 0; r < 8; r++) {
+            const uint2 v = __ldg(reinterpret_cast<const uint2*>(p + (uint64_t)r * pw));
+            raw[2 * r] = v.x;
+            raw[2 * r + 1] = v.y;
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < 16; r++) raw[r] = 0x80808080u;
         }
-      } else {
-#pragma unroll
-        for (int r = 0; r < 16; r++) raw[r] = 0x80808080u;
+        L = fdct_quant_block(raw, qt, plane, P.one, z.col);
       }
-      L = fdct_quant_block(raw, qt, plane, P.one, z.col);
+      // ---- phase B: entropy-code the block (same thread, so no CTA barrier in between); warp lockstep ----
+      if (!live) L = 0;
+      while (L > 0 && z.get(L - 1) == 0) L--;  // exact message length (Huffman.cpp:184-190); at most 8 steps
+      __syncwarp();
+      HuffPlan pl = huff_plan<kFastSyms>(z, L, fs, WarpLockstep{});
+      bool big = false;
+      uint8_t lbytes[BigScratch::kBytes];
+      int16_t lsyms[BigScratch::kSyms];
+      BigScratch bs{lbytes, lsyms, 1};
+      if (live && pl.n < 0) {  // more distinct symbols than the shared-memory scratch holds
+        big = true;
+        pl = plan_big(z, L, bs);
+      }
+      __syncwarp();
+      const uint32_t size = live ? (uint32_t)pl.size() : 0u;
+      // chunk sizes go to a linear side array; finalize_frames_kernel moves them behind the plane headers,
+      // whose position depends on the (data dependent) size of the previous planes
+      if (live) P.ws.chunk_sizes[gblk0 + blk] = (uint8_t)size;
+      uint32_t pass_total;
+      const uint32_t off = carried + cta_exclusive_scan(size, sm.warp_sums, &pass_total);
+      {
+        const bool fits = off + size <= (uint32_t)kStageBytes;
+        uint8_t* dst = fits ? &sm.stage[off] : overflow + off;
+        // first chunk that does not fit the shared staging buffer (chunks never straddle; offsets only grow)
+        if (live && !fits && off <= (uint32_t)kStageBytes) atomicMin(&sm.split, off);
+        HuffPlan plf = pl;
+        if (!live || big) plf.n = 0;
+        huff_emit<kFastSyms>(z, plf, fs, dst, WarpLockstep{});
+        if (live && big) emit_big(z, pl, bs, dst);
+      }
+      carried += pass_total;
     }
-    // ---- phase B: entropy-code the block (same thread, so no CTA barrier in between); warp lockstep ----
-    if (!live) L = 0;
-    while (L > 0 && z.get(L - 1) == 0) L--;  // exact message length (Huffman.cpp:184-190); at most 8 steps
-    __syncwarp();
-    HuffPlan pl = huff_plan<kFastSyms>(z, L, fs, WarpLockstep{});
-    bool big = false;
-    uint8_t lbytes[BigScratch::kBytes];
-    int16_t lsyms[BigScratch::kSyms];
-    BigScratch bs{lbytes, lsyms, 1};
-    if (live && pl.n < 0) {  // more distinct symbols than the shared-memory scratch holds
-      big = true;
-      pl = plan_big(z, L, bs);
-    }
-    __syncwarp();
-    const uint32_t size = live ? (uint32_t)pl.size() : 0u;
-    sm.csize[tid] = (uint8_t)size;
-    uint32_t total;
-    const uint32_t off = cta_exclusive_scan(size, sm.warp_sums, &total);
-    {
-      uint8_t* dst = (off + size <= (uint32_t)kStageBytes) ? &sm.stage[off] : overflow + off;
-      HuffPlan plf = pl;
-      if (!live || big) plf.n = 0;
-      huff_emit<kFastSyms>(z, plf, fs, dst, WarpLockstep{});
-      if (live && big) emit_big(z, pl, bs, dst);
-    }
-    // first chunk that did not fit the shared staging buffer (chunks never straddle; offsets are increasing)
-    if (tid == 0) sm.split = total;
     __syncthreads();
-    if (live && off + size > (uint32_t)kStageBytes && off <= (uint32_t)kStageBytes) atomicMin(&sm.split, off);
 
     // ---- tile offset: decoupled look-back over all tiles of the batch in file order ----
     if (wid == 0) {
-      const u64 excl = lookback(P.ws.tile_status, tile, 0, total, lane);
+      const u64 excl = lookback(P.ws.tile_status, tile, 0, carried, lane);
       if (lane == 0) {
         sm.base = excl;
         if (tc.k0 == 0) P.ws.plane_start[tc.frame * 3 + plane] = excl;               // code bytes before this plane
-        if (tile == P.total_tiles - 1) P.ws.plane_start[g.n_frames * 3] = excl + total;
+        if (tile == P.total_tiles - 1) P.ws.plane_start[g.n_frames * 3] = excl + carried;
       }
     }
     __syncthreads();
-    // chunk sizes go to a linear side array; finalize_frames_kernel moves them behind the plane headers,
-    // whose position depends on the (data dependent) size of the previous planes
-    if (live) {
-      const uint64_t gblk = (uint64_t)tc.frame * g.nblk_frame + (plane > 0 ? g.nblk[0] : 0) + (plane > 1 ? g.nblk[1] : 0) + tc.k0;
-      P.ws.chunk_sizes[gblk + tid] = (uint8_t)size;
-    }
     // content bytes: absolute position = fixed part (headers + size arrays up to this plane) + code bytes before
     {
       const uint32_t fixed = 12 + 8 * (plane + 1) + g.nblk[0] + (plane > 0 ? g.nblk[1] : 0) + (plane > 1 ? g.nblk[2] : 0);
       const u64 pos = (u64)tc.frame * (36 + g.nblk_frame) + fixed + sm.base;
-      if (pos + total > P.out_cap) {
+      if (pos + carried > P.out_cap) {
         if (tid == 0) atomicOr(&P.ws.counters[1], kFlagCapacity);
       } else {
-        const uint32_t split = sm.split;
+        const uint32_t split = sm.split < carried ? sm.split : carried;
         copy_smem_to_global(P.out + pos, sm.stage, split);
-        for (uint32_t i = split + tid; i < total; i += kCtaThreads) P.out[pos + i] = overflow[i];
+        for (uint32_t i = split + tid; i < carried; i += kCtaThreads) P.out[pos + i] = overflow[i];
       }
     }
     __syncthreads();  // shared memory is reused by the next tile
@@ -519,8 +528,7 @@ __global__ void __launch_bounds__(256) finalize_frames_kernel(const __grid_const
 int codec_grid_size(int device, bool encoder) {
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-  (void)encoder;
-  return sms * 5;
+  return sms * (encoder ? 4 : 5);
 }
 
 // ===================================================================================================
@@ -532,6 +540,10 @@ struct DecSmem {
   alignas(16) uint8_t stage[kDecStageBytes];  // the tile's chunk bytes
   uint8_t zigzag[64];
   float q[64];
+  uint32_t hist[64];                  // counting sort of the tile's blocks by chunk size
+  uint32_t boff[kTileBlocks];         // chunk offset of block b inside the tile
+  uint8_t bsize[kTileBlocks];
+  uint8_t perm[kTileBlocks];          // perm[t] = block decoded by thread t
   uint32_t warp_sums[4];
   uint32_t tile;
   u64 base;
@@ -645,9 +657,32 @@ __global__ void __launch_bounds__(kCtaThreads, 5)
     }
     const bool live = (uint32_t)tid < tc.nblk;
     // chunk sizes of the tile, CTA scan, plane-local look-back -> byte offset of the tile inside content[]
-    const uint32_t size = live ? (uint32_t)P.payloads[d.sizes_off + tc.k0 + tid] : 0u;
+    const uint32_t bsz = live ? (uint32_t)P.payloads[d.sizes_off + tc.k0 + tid] : 0u;
     uint32_t total;
-    const uint32_t off = cta_exclusive_scan(size, sm.warp_sums, &total);
+    const uint32_t boff = cta_exclusive_scan(bsz, sm.warp_sums, &total);
+    // Counting sort of the blocks by chunk size: thread t decodes the block of rank t, so the lanes of a warp
+    // get messages of similar length and the lockstep decode loop wastes few lanes.
+    sm.boff[tid] = boff;
+    sm.bsize[tid] = (uint8_t)bsz;
+    if (tid < 64) sm.hist[tid] = 0;
+    __syncthreads();
+    const uint32_t key = (bsz >> 2) < 63u ? (bsz >> 2) : 63u;
+    const uint32_t within = atomicAdd(&sm.hist[key], 1u);
+    __syncthreads();
+    if (wid == 0) {  // exclusive prefix of the 64 bins, two per lane
+      const uint32_t h0 = sm.hist[2 * lane], h1 = sm.hist[2 * lane + 1];
+      uint32_t inc = h0 + h1;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += n;
+      }
+      __syncwarp();
+      sm.hist[2 * lane] = inc - h0 - h1;
+      sm.hist[2 * lane + 1] = inc - h1;
+    }
+    __syncthreads();
+    sm.perm[sm.hist[key] + within] = (uint8_t)tid;
     if (wid == 0) {
       const u64 excl = lookback(P.ws.tile_status, tile, tc.first_tile_of_plane, total, lane);
       if (lane == 0) sm.base = excl;
@@ -670,22 +705,25 @@ __global__ void __launch_bounds__(kCtaThreads, 5)
     __syncthreads();
 
     // ---- phase 1: canonical Huffman decode + dequantise into the thread's shared-memory column (warp lockstep) ----
+    const uint32_t blk = sm.perm[tid];  // written before the __syncthreads above
+    const bool mine = blk < tc.nblk;
     {
+      const uint32_t off = sm.boff[blk], size = sm.bsize[blk];
       const uint8_t* chunk = (off + size <= (uint32_t)kDecStageBytes) ? &sm.stage[off] : content + off;
       const int err = huff_decode_block(chunk, (int)size, [&](int j, int v) {
         const int pos = sm.zigzag[j];
         col[pos * kTileBlocks] = __fmul_rn((float)v, sm.q[pos]);  // DCT.cpp:330-332
       }, WarpLockstep{});
-      if (live && (err || size == 0)) atomicOr(&P.ws.counters[1], kFlagHuffman);  // a chunk is at least 7 bytes
+      if (mine && (err || size == 0)) atomicOr(&P.ws.counters[1], kFlagHuffman);  // a chunk is at least 7 bytes
     }
     __syncwarp();
     // ---- phase 2: inverse DCT, round, clamp, store ----
     {
       uint32_t outw[16];
       idct_block(col, P.one, outw);
-      if (live) {
+      if (mine) {
         const uint32_t pw = g.pw[plane], bw = g.bw[plane];
-        const uint32_t k = tc.k0 + tid;
+        const uint32_t k = tc.k0 + blk;
         const uint32_t by = k / bw, bx = k - by * bw;
         uint8_t* p = P.dst + (uint64_t)tc.frame * g.frame_bytes + g.plane_off[plane] + (uint64_t)by * 8 * pw + (uint64_t)bx * 8;
 #pragma unroll

@@ -5,7 +5,10 @@
 
 namespace myyuvb {
 
-constexpr int kTileBlocks = 128;   // 8x8 blocks per tile (one per thread)
+constexpr int kTileBlocks = 128;   // 8x8 blocks per pass of a CTA (one per thread)
+constexpr int kEncPasses = 4;      // compress: passes per tile -> one look-back per 512 blocks
+constexpr int kEncTile = kTileBlocks * kEncPasses;
+constexpr int kDecTile = kTileBlocks;
 constexpr int kCtaThreads = 128;   // threads per CTA of the codec kernels
 
 // error bits raised by kernels (OR-ed into Workspace::flags)
@@ -33,6 +36,7 @@ struct FrameGeom {
   uint32_t pw[3], ph[3];          // plane width / height in pixels
   uint32_t bw[3];                 // plane width in 8x8 blocks
   uint32_t nblk[3];               // blocks per plane
+  uint32_t tile_blocks;           // blocks per tile (kEncTile or kDecTile)
   uint32_t tiles[3];              // tiles per plane
   uint32_t tiles_per_frame;
   uint32_t nblk_frame;            // blocks per frame
@@ -40,7 +44,7 @@ struct FrameGeom {
   uint64_t frame_bytes;           // w*h*3/2
 };
 
-FrameGeom make_geom(uint32_t width, uint32_t height, uint32_t n_frames);
+FrameGeom make_geom(uint32_t width, uint32_t height, uint32_t n_frames, uint32_t tile_blocks);
 
 // Device scratch owned by a context (sized for the current batch by capi.cu).
 struct Workspace {
@@ -48,7 +52,7 @@ struct Workspace {
   uint64_t* plane_start;   // [n_frames*3 + 1] code bytes before each plane (compress)
   uint32_t* counters;      // [0] tile ticket, [1] error flags
   uint8_t* chunk_sizes;    // [n_frames * nblk_frame] per-block chunk size, linear block order (compress)
-  uint8_t* overflow;       // [grid * 32768] staging overflow area (compress; a tile is at most 128 * 255 bytes)
+  uint8_t* overflow;       // [grid * kEncTile * 256] staging overflow area (compress; a chunk is at most 255 bytes)
   void* plane_desc;        // [n_frames*3] PlaneDesc (decompress)
   int grid;                // persistent grid size of the codec kernels
   cudaEvent_t k_begin, k_end;  // recorded around the main codec kernel of each launch (myyuvb_last_kernel_ms)
