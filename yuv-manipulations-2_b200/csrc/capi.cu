@@ -115,6 +115,7 @@ struct myyuvb_ctx {
   bool own_stream = false;
   int grid = 0, grid_dec = 0;
   Buffer d_in, d_out, d_status, d_tiles, d_plane_start, d_counters, d_sizes, d_overflow, d_desc, d_offsets;
+  Buffer d_scratch, d_tile_pos, d_tile_total, d_tile_prefix;
   Buffer h_small, h_stage_in, h_stage_out;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t kev[2] = {nullptr, nullptr};  // timing events around the last main codec kernel
@@ -123,7 +124,7 @@ struct myyuvb_ctx {
 
 namespace {
 
-int ensure_workspace(myyuvb_ctx* c, const FrameGeom& g, bool encoder, Workspace* ws) {
+int ensure_workspace(myyuvb_ctx* c, const FrameGeom& g, bool encoder, Workspace* ws, uint64_t out_capacity = 0) {
   const uint64_t tiles = (uint64_t)g.tiles_per_frame * g.n_frames;
   int rc;
   if ((rc = c->d_tiles.reserve(tiles * 8))) return rc;
@@ -135,6 +136,13 @@ int ensure_workspace(myyuvb_ctx* c, const FrameGeom& g, bool encoder, Workspace*
   if (encoder) {
     if ((rc = c->d_sizes.reserve((uint64_t)g.nblk_frame * g.n_frames))) return rc;
     if ((rc = c->d_overflow.reserve((uint64_t)c->grid * kEncTile * 256))) return rc;
+    // pass-1 parking area: never more than the payload itself, i.e. never more than the caller's capacity
+    const uint64_t worst = (uint64_t)g.nblk_frame * g.n_frames * 255;
+    ws->scratch_cap = std::min<uint64_t>(out_capacity, worst);
+    if ((rc = c->d_scratch.reserve(ws->scratch_cap + 16))) return rc;
+    if ((rc = c->d_tile_pos.reserve(tiles * 8))) return rc;
+    if ((rc = c->d_tile_total.reserve(tiles * 4))) return rc;
+    if ((rc = c->d_tile_prefix.reserve(tiles * 8))) return rc;
   } else {
     if ((rc = c->d_desc.reserve((uint64_t)g.n_frames * 3 * sizeof(PlaneDesc)))) return rc;
   }
@@ -143,6 +151,10 @@ int ensure_workspace(myyuvb_ctx* c, const FrameGeom& g, bool encoder, Workspace*
   ws->counters = c->d_counters.as<uint32_t>();
   ws->chunk_sizes = c->d_sizes.as<uint8_t>();
   ws->overflow = c->d_overflow.as<uint8_t>();
+  ws->scratch = c->d_scratch.as<uint8_t>();
+  ws->tile_pos = c->d_tile_pos.as<uint64_t>();
+  ws->tile_total = c->d_tile_total.as<uint32_t>();
+  ws->tile_prefix = c->d_tile_prefix.as<uint64_t>();
   ws->plane_desc = c->d_desc.p;
   ws->grid = encoder ? c->grid : c->grid_dec;
   ws->k_begin = c->kev[0];
@@ -222,7 +234,7 @@ void myyuvb_ctx_destroy(myyuvb_ctx* c) {
   cudaStreamSynchronize(c->stream);
   cudaStreamSynchronize(c->copy_stream);
   for (Buffer* b : {&c->d_in, &c->d_out, &c->d_status, &c->d_tiles, &c->d_plane_start, &c->d_counters, &c->d_sizes,
-                    &c->d_overflow, &c->d_desc, &c->d_offsets, &c->h_small, &c->h_stage_in, &c->h_stage_out})
+                    &c->d_overflow, &c->d_desc, &c->d_offsets, &c->d_scratch, &c->d_tile_pos, &c->d_tile_total, &c->d_tile_prefix, &c->h_small, &c->h_stage_in, &c->h_stage_out})
     b->release();
   for (auto& ev : c->ev)
     if (ev) cudaEventDestroy(ev);
@@ -285,7 +297,7 @@ int myyuvb_dct_compress_batch_dev(myyuvb_ctx* c, const uint8_t* d_iyuv, uint32_t
   const FrameGeom g = make_geom(w, h, n_frames, kEncTile);
   if ((uint64_t)g.tiles_per_frame * n_frames > 0x7fffffffull) return fail(MYYUVB_ERR_TOO_LARGE, "batch too large");
   Workspace ws;
-  if ((rc = ensure_workspace(c, g, true, &ws))) return rc;
+  if ((rc = ensure_workspace(c, g, true, &ws, out_capacity))) return rc;
   QTables qt;
   make_qtables(quality, &qt);
   launch_compress(d_iyuv, g, qt, d_out, out_capacity, d_offsets, ws, c->stream);

@@ -10,10 +10,15 @@
 //  * ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under -fmad=false (checked with cuobjdump),
 //    which would change results.  The accumulation  acc + p  is therefore issued as fma(p, ONE, acc) with
 //    ONE = 1.0f passed at run time: bit-identical to an add, and not contractible with the producing mul.
-//  * Entropy coding is one thread per block (block_codec.cuh) on coefficients staged in shared memory;
-//    chunk bytes are laid out per tile in shared memory, the tile's global byte offset comes from a
-//    single-pass decoupled look-back over tiles in file order, and the tile is written out coalesced.
-//  * Persistent CTAs take tiles from an atomic ticket, so look-back predecessors are always resident.
+//  * Entropy coding is one thread per block (block_codec.cuh) on coefficients staged in shared memory, the
+//    lanes of a warp in lockstep.  Chunk bytes are laid out per tile in shared memory.
+//  * Compress needs the byte offset of every chunk in file order.  A single-pass decoupled look-back made
+//    every tile wait for all earlier tiles still being coded (17% of issued instructions were the spin,
+//    18% of stalls the barrier behind it: profiles/r01_notes.md), so compress is three launches with no
+//    inter-CTA waiting: (1) code tiles, park each tile's bytes in a bump-allocated scratch area;
+//    (2) scan the tile totals; (3) move every tile to its final place and write headers and size arrays.
+//    Decompress knows all sizes up front and keeps the look-back (per plane, aggregates published at tile start).
+//  * Persistent CTAs take tiles from an atomic ticket (load balance; look-back predecessors always resident).
 #include "kernels.h"
 
 #include <cuda_runtime.h>
@@ -201,6 +206,28 @@ MYB_D void copy_smem_to_global(uint8_t* __restrict__ dst, const uint8_t* __restr
   if (threadIdx.x < n - done) dst[done + threadIdx.x] = src[done + threadIdx.x];
 }
 
+
+// Copy n bytes global -> global, both at arbitrary alignment, by the whole CTA: destination-aligned 32-bit
+// stores, source words funnel-shifted.  Reads stay inside [src, src + n) rounded out to aligned words that
+// overlap it (never touches a word that holds no source byte).
+MYB_D void copy_global_to_global(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint32_t n, int nthreads) {
+  const uint32_t head = min((uint32_t)((4 - ((uintptr_t)dst & 3)) & 3), n);
+  if (threadIdx.x < head) dst[threadIdx.x] = src[threadIdx.x];
+  const uint32_t words = (n - head) >> 2;
+  uint32_t* dw = reinterpret_cast<uint32_t*>(dst + head);
+  const uint8_t* s0 = src + head;
+  const uint32_t mis = (uint32_t)((uintptr_t)s0 & 3);
+  const uint32_t* sw = reinterpret_cast<const uint32_t*>(s0 - mis);
+  for (uint32_t w = threadIdx.x; w < words; w += nthreads) {
+    const uint32_t lo = sw[w];
+    uint32_t v = lo;
+    if (mis) v = __funnelshift_r(lo, sw[w + 1], mis * 8);  // sw[w+1] holds source bytes 4w+4-mis.. < n
+    dw[w] = v;
+  }
+  const uint32_t done = head + (words << 2);
+  if (threadIdx.x < n - done) dst[done + threadIdx.x] = src[done + threadIdx.x];
+}
+
 // ===================================================================================================
 // Colour conversion  (myyuv_yuv.cpp:34-52, :88-128; row flip of myyuv_bmp.cpp:95-98 folded into addressing)
 // One thread = 4 pixels x 2 rows: two 128-bit loads, two 32-bit Y stores, one 16-bit U and V store.
@@ -266,7 +293,7 @@ void launch_xrgb_to_iyuv(const uint8_t* d_bgrx, uint8_t* d_iyuv, uint32_t w, uin
 //   stage 2:  (Y[a][b], Y[a+1][b]) = sum_k (T[a][k], T[a+1][k]) * C[b][k]      data pair x broadcast immediate
 // so no transposition or register shuffling is needed between the stages (cuobjdump: 960 FMUL2/FFMA2, 0 MOV).
 // ===================================================================================================
-constexpr int kStageBytes = 12 * 1024;                 // shared-memory staging of one tile's chunk bytes
+constexpr int kStageBytes = 4 * 1024;                  // shared-memory staging of one tile's chunk bytes
 constexpr int kFastSyms = 15;                          // distinct symbols handled with shared-memory scratch
 using FastScratch = HuffScratch<kFastSyms>;
 using BigScratch = HuffScratch<64>;
@@ -281,7 +308,7 @@ struct EncSmem {
   uint32_t split;
   u64 base;
 };
-static_assert(sizeof(EncSmem) <= 55 * 1024, "EncSmem must allow 4 CTAs per SM");
+static_assert(sizeof(EncSmem) <= 44 * 1024 + 256, "EncSmem must allow 5 CTAs per SM");
 
 struct ZShared {  // accessor of one block's column in EncSmem::zz
   uint16_t* col;
@@ -382,7 +409,7 @@ MYB_D int fdct_quant_block(const uint32_t (&raw)[16], const QTables& qt, int pla
 __device__ __noinline__ HuffPlan plan_big(ZShared z, int L, BigScratch bs) { return huff_plan<64>(z, L, bs, NoWarp{}); }
 __device__ __noinline__ void emit_big(ZShared z, HuffPlan pl, BigScratch bs, uint8_t* dst) { huff_emit<64>(z, pl, bs, dst, NoWarp{}); }
 
-__global__ void __launch_bounds__(kCtaThreads, 4)
+__global__ void __launch_bounds__(kCtaThreads, 5)
     dct_compress_kernel(const __grid_constant__ EncParams P, const __grid_constant__ QTables qt) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   EncSmem& sm = *reinterpret_cast<EncSmem*>(smem_raw);
@@ -467,29 +494,92 @@ __global__ void __launch_bounds__(kCtaThreads, 4)
     }
     __syncthreads();
 
-    // ---- tile offset: decoupled look-back over all tiles of the batch in file order ----
-    if (wid == 0) {
-      const u64 excl = lookback(P.ws.tile_status, tile, 0, carried, lane);
-      if (lane == 0) {
-        sm.base = excl;
-        if (tc.k0 == 0) P.ws.plane_start[tc.frame * 3 + plane] = excl;               // code bytes before this plane
-        if (tile == P.total_tiles - 1) P.ws.plane_start[g.n_frames * 3] = excl + carried;
-      }
+    // ---- park the tile's bytes in the scratch area (bump allocation, completion order); file-order offsets
+    //      are computed afterwards by scan_tiles_kernel, so no CTA ever waits for another one ----
+    if (tid == 0) {
+      const u64 pos = atomicAdd(reinterpret_cast<u64*>(P.ws.counters + 2), (u64)carried);
+      P.ws.tile_pos[tile] = pos;
+      P.ws.tile_total[tile] = carried;
+      sm.base = pos;
     }
     __syncthreads();
-    // content bytes: absolute position = fixed part (headers + size arrays up to this plane) + code bytes before
     {
-      const uint32_t fixed = 12 + 8 * (plane + 1) + g.nblk[0] + (plane > 0 ? g.nblk[1] : 0) + (plane > 1 ? g.nblk[2] : 0);
-      const u64 pos = (u64)tc.frame * (36 + g.nblk_frame) + fixed + sm.base;
-      if (pos + carried > P.out_cap) {
+      const u64 pos = sm.base;
+      if (pos + carried > P.ws.scratch_cap) {
         if (tid == 0) atomicOr(&P.ws.counters[1], kFlagCapacity);
       } else {
         const uint32_t split = sm.split < carried ? sm.split : carried;
-        copy_smem_to_global(P.out + pos, sm.stage, split);
-        for (uint32_t i = split + tid; i < carried; i += kCtaThreads) P.out[pos + i] = overflow[i];
+        copy_smem_to_global(P.ws.scratch + pos, sm.stage, split);
+        for (uint32_t i = split + tid; i < carried; i += kCtaThreads) P.ws.scratch[pos + i] = overflow[i];
       }
     }
     __syncthreads();  // shared memory is reused by the next tile
+  }
+}
+
+// Pass 2: exclusive scan of the tile totals in file order (one CTA; a 4K batch of 64 frames has ~10^5 tiles),
+// plus the number of code bytes before every plane.
+__global__ void __launch_bounds__(1024) scan_tiles_kernel(const __grid_constant__ EncParams P) {
+  __shared__ u64 warp_sums[32];
+  __shared__ u64 carry_s;
+  const FrameGeom& g = P.g;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < P.total_tiles; base += 1024) {
+    const uint32_t t = base + threadIdx.x;
+    const u64 v = t < P.total_tiles ? (u64)P.ws.tile_total[t] : 0;
+    u64 inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const u64 n = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += n;
+    }
+    if (lane == 31) warp_sums[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+      u64 w = warp_sums[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const u64 n = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += n;
+      }
+      warp_sums[lane] = w;  // inclusive over warps
+    }
+    __syncthreads();
+    const u64 carry = carry_s;
+    const u64 excl = carry + (wid ? warp_sums[wid - 1] : 0) + inc - v;
+    if (t < P.total_tiles) {
+      P.ws.tile_prefix[t] = excl;
+      // first tile of a plane: code bytes before this plane
+      const uint32_t f = t / g.tiles_per_frame, r = t - f * g.tiles_per_frame;
+      if (r == 0) P.ws.plane_start[f * 3] = excl;
+      else if (r == g.tiles[0]) P.ws.plane_start[f * 3 + 1] = excl;
+      else if (r == g.tiles[0] + g.tiles[1]) P.ws.plane_start[f * 3 + 2] = excl;
+      if (t == P.total_tiles - 1) P.ws.plane_start[g.n_frames * 3] = excl + v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = carry + warp_sums[31];
+    __syncthreads();
+  }
+}
+
+// Pass 3: move every tile's chunk bytes from the scratch area to their place in the payload.
+// Absolute position = fixed part (headers + size arrays up to this plane) + code bytes before the tile.
+__global__ void __launch_bounds__(256) place_tiles_kernel(const __grid_constant__ EncParams P) {
+  const FrameGeom& g = P.g;
+  for (uint32_t tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+    const TileCoord tc = tile_coord(g, tile);
+    const int plane = (int)tc.plane;
+    const uint32_t total = P.ws.tile_total[tile];
+    const u64 src = P.ws.tile_pos[tile];
+    const uint32_t fixed = 12 + 8 * (plane + 1) + g.nblk[0] + (plane > 0 ? g.nblk[1] : 0) + (plane > 1 ? g.nblk[2] : 0);
+    const u64 pos = (u64)tc.frame * (36 + g.nblk_frame) + fixed + P.ws.tile_prefix[tile];
+    if (pos + total > P.out_cap || src + total > P.ws.scratch_cap) {
+      if (threadIdx.x == 0) atomicOr(&P.ws.counters[1], kFlagCapacity);
+      continue;
+    }
+    copy_global_to_global(P.out + pos, P.ws.scratch + src, total, 256);
   }
 }
 
@@ -528,7 +618,8 @@ __global__ void __launch_bounds__(256) finalize_frames_kernel(const __grid_const
 int codec_grid_size(int device, bool encoder) {
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-  return sms * (encoder ? 4 : 5);
+  (void)encoder;
+  return sms * 5;
 }
 
 // ===================================================================================================
@@ -747,14 +838,17 @@ void launch_compress(const uint8_t* d_iyuv, const FrameGeom& g, const QTables& q
     cudaFuncSetAttribute(dct_compress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncSmem));
     attr_set = true;
   }
-  cudaMemsetAsync(ws.tile_status, 0, (size_t)P.total_tiles * 8, s);
-  cudaMemsetAsync(ws.counters, 0, 4, s);  // ticket only; error flags accumulate until read
+  cudaMemsetAsync(ws.counters, 0, 4, s);      // ticket only; error flags accumulate until read
+  cudaMemsetAsync(ws.counters + 2, 0, 8, s);  // scratch bump allocator
   const int grid = (int)(P.total_tiles < (uint32_t)ws.grid ? P.total_tiles : (uint32_t)ws.grid);
   if (ws.k_begin) cudaEventRecord(ws.k_begin, s);
   dct_compress_kernel<<<grid, kCtaThreads, sizeof(EncSmem), s>>>(P, qt);
   if (ws.k_end) cudaEventRecord(ws.k_end, s);
+  scan_tiles_kernel<<<1, 1024, 0, s>>>(P);
+  const int pgrid = (int)(P.total_tiles < 148u * 16 ? P.total_tiles : 148u * 16);
+  place_tiles_kernel<<<pgrid, 256, 0, s>>>(P);
   finalize_frames_kernel<<<g.n_frames, 256, 0, s>>>(P, d_offsets);
-  g_launches += 2;
+  g_launches += 4;
 }
 
 void launch_decompress(const uint8_t* d_payloads, const uint64_t* d_offsets, const FrameGeom& g, const QTables& qt,

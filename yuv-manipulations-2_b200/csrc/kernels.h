@@ -6,7 +6,7 @@
 namespace myyuvb {
 
 constexpr int kTileBlocks = 128;   // 8x8 blocks per pass of a CTA (one per thread)
-constexpr int kEncPasses = 4;      // compress: passes per tile -> one look-back per 512 blocks
+constexpr int kEncPasses = 1;      // compress: passes of 128 blocks per tile
 constexpr int kEncTile = kTileBlocks * kEncPasses;
 constexpr int kDecTile = kTileBlocks;
 constexpr int kCtaThreads = 128;   // threads per CTA of the codec kernels
@@ -50,9 +50,14 @@ FrameGeom make_geom(uint32_t width, uint32_t height, uint32_t n_frames, uint32_t
 struct Workspace {
   uint64_t* tile_status;   // [total tiles] decoupled look-back words
   uint64_t* plane_start;   // [n_frames*3 + 1] code bytes before each plane (compress)
-  uint32_t* counters;      // [0] tile ticket, [1] error flags
+  uint32_t* counters;      // [0] tile ticket, [1] error flags, [2..3] u64 scratch bump allocator
   uint8_t* chunk_sizes;    // [n_frames * nblk_frame] per-block chunk size, linear block order (compress)
   uint8_t* overflow;       // [grid * kEncTile * 256] staging overflow area (compress; a chunk is at most 255 bytes)
+  uint8_t* scratch;        // [scratch_cap] chunk bytes of all tiles in completion order (compress, pass 1)
+  uint64_t scratch_cap;
+  uint64_t* tile_pos;      // [total tiles] position of each tile's bytes in scratch
+  uint32_t* tile_total;    // [total tiles] chunk bytes of each tile
+  uint64_t* tile_prefix;   // [total tiles] chunk bytes before each tile in file order (scan_tiles_kernel)
   void* plane_desc;        // [n_frames*3] PlaneDesc (decompress)
   int grid;                // persistent grid size of the codec kernels
   cudaEvent_t k_begin, k_end;  // recorded around the main codec kernel of each launch (myyuvb_last_kernel_ms)
