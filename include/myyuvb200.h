@@ -56,8 +56,9 @@ MYYUVB_API void myyuvb_ctx_destroy(myyuvb_ctx* ctx);
 MYYUVB_API const char* myyuvb_last_error(void); /* thread-local, valid until the next call on this thread */
 MYYUVB_API int myyuvb_sync(myyuvb_ctx* ctx);    /* wait for the context's stream */
 MYYUVB_API void* myyuvb_stream(myyuvb_ctx* ctx);
-/* Device time (CUDA events on the context stream) of the main codec kernel of the most recent
- * compress/decompress launch on this context -- the figure bench.py's roofline uses.  Synchronises. */
+/* Device time (CUDA events on the context stream) of the most recent compress launch sequence (code tiles,
+ * scan, place, headers: 4 kernels) or decompress kernel on this context -- the figure bench.py's roofline uses.
+ * Synchronises. */
 MYYUVB_API int myyuvb_last_kernel_ms(myyuvb_ctx* ctx, float* ms);
 
 /* Upper bound of a compressed payload for one w x h IYUV frame (a chunk is at most 255 bytes because

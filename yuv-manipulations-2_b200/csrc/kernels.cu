@@ -413,7 +413,7 @@ __global__ void __launch_bounds__(kCtaThreads, 5)
     dct_compress_kernel(const __grid_constant__ EncParams P, const __grid_constant__ QTables qt) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   EncSmem& sm = *reinterpret_cast<EncSmem*>(smem_raw);
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int tid = threadIdx.x;
   const FrameGeom& g = P.g;
   FastScratch fs{&sm.hs_bytes[0][tid], &sm.hs_syms[0][tid], kCtaThreads};
   ZShared z{&sm.zz[0][tid]};
@@ -843,11 +843,11 @@ void launch_compress(const uint8_t* d_iyuv, const FrameGeom& g, const QTables& q
   const int grid = (int)(P.total_tiles < (uint32_t)ws.grid ? P.total_tiles : (uint32_t)ws.grid);
   if (ws.k_begin) cudaEventRecord(ws.k_begin, s);
   dct_compress_kernel<<<grid, kCtaThreads, sizeof(EncSmem), s>>>(P, qt);
-  if (ws.k_end) cudaEventRecord(ws.k_end, s);
   scan_tiles_kernel<<<1, 1024, 0, s>>>(P);
   const int pgrid = (int)(P.total_tiles < 148u * 16 ? P.total_tiles : 148u * 16);
   place_tiles_kernel<<<pgrid, 256, 0, s>>>(P);
   finalize_frames_kernel<<<g.n_frames, 256, 0, s>>>(P, d_offsets);
+  if (ws.k_end) cudaEventRecord(ws.k_end, s);  // the whole compress sequence (4 kernels) is what gets timed
   g_launches += 4;
 }
 
