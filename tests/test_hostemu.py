@@ -1,0 +1,92 @@
+"""The product's per-block entropy coder (csrc/block_codec.cuh, the source the CUDA kernels inline) compiled for
+the host and compared with the oracle -- runs without a GPU.  Also checks the two arithmetic identities the
+kernels rely on for bit-exactness: exact division by a single Newton step, rounding via a round-toward-zero add."""
+import ctypes as C
+import pathlib
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = pathlib.Path(__file__).parent / "hostemu"
+u8p, i16p = C.POINTER(C.c_uint8), C.POINTER(C.c_int16)
+
+
+@pytest.fixture(scope="module")
+def emu():
+    subprocess.run(["make", "-s", "-C", str(HERE)], check=True)
+    L = C.CDLL(str(HERE / "libhostemu.so"))
+    L.hostemu_encode_blocks.argtypes = [i16p, C.c_uint32, C.c_int, C.c_int, u8p, u8p]
+    L.hostemu_decode_blocks.argtypes = [u8p, u8p, C.c_uint32, i16p]
+    L.hostemu_division_check.argtypes = [C.c_uint32, C.c_uint32]
+    L.hostemu_division_check.restype = C.c_uint64
+    L.hostemu_round_check.argtypes = [C.c_uint32, C.c_uint32]
+    L.hostemu_round_check.restype = C.c_uint64
+    return L
+
+
+def make_blocks(kind, n, rng):
+    b = np.zeros((n, 64), np.int16)
+    if kind == "sparse":
+        for i in range(n):
+            k = rng.integers(0, 20)
+            b[i, rng.integers(0, 64, k)] = rng.integers(-6, 7, k)
+    elif kind == "mid":
+        for i in range(n):
+            k = rng.integers(0, 40)
+            b[i, rng.integers(0, 64, k)] = rng.integers(-40, 41, k)
+    elif kind == "distinct":
+        for i in range(n):
+            m = rng.integers(1, 65)
+            vals = rng.choice(np.arange(-1024, 1024), m, replace=False)
+            b[i] = vals[rng.integers(0, m, 64)]
+    elif kind == "full":
+        b = rng.integers(-1024, 1024, (n, 64)).astype(np.int16)
+    elif kind == "small":
+        b = rng.integers(-3, 4, (n, 64)).astype(np.int16)
+    elif kind == "nozero":  # no zero in the message and exactly 13/29/59 distinct symbols: the appended-key-0 rehash
+        nz = np.concatenate([np.arange(-1024, 0), np.arange(1, 1024)])
+        for i in range(n):
+            m = [13, 29, 59, 12, 14, 28, 30, 58, 60][i % 9]
+            vals = rng.choice(nz, m, replace=False)
+            seq = np.concatenate([vals, vals[rng.integers(0, m, 64 - m)]])
+            rng.shuffle(seq)
+            b[i] = seq
+    elif kind == "zeros":
+        pass
+    return b
+
+
+@pytest.mark.parametrize("kind,n", [("sparse", 6000), ("mid", 6000), ("distinct", 6000), ("full", 1500), ("small", 6000),
+                                    ("nozero", 1800), ("zeros", 64)])
+@pytest.mark.parametrize("stride,fast", [(1, 1), (128, 1), (1, 0)])
+def test_block_coder_matches_oracle(emu, ora, kind, n, stride, fast):
+    rng = np.random.default_rng(hash(kind) % 1000)
+    b = make_blocks(kind, n, rng)
+    want_c, want_s = ora.huff_encode_blocks(b)
+    out = np.empty(n * 256, np.uint8)
+    sizes = np.empty(n, np.uint8)
+    emu.hostemu_encode_blocks(b.ctypes.data_as(i16p), n, stride, fast, out.ctypes.data_as(u8p), sizes.ctypes.data_as(u8p))
+    assert np.array_equal(sizes, want_s)
+    assert np.array_equal(out[: int(sizes.sum(dtype=np.int64))], want_c)
+    dec = np.empty((n, 64), np.int16)
+    rc = emu.hostemu_decode_blocks(want_c.ctypes.data_as(u8p), want_s.ctypes.data_as(u8p), n, dec.ctypes.data_as(i16p))
+    assert rc == 0 and np.array_equal(dec, b)
+
+
+def test_decoder_rejects_truncated_stream(emu, ora):
+    b = make_blocks("mid", 4, np.random.default_rng(1))
+    c, s = ora.huff_encode_blocks(b)
+    bad = c.copy()
+    bad[0] = 0xFF
+    bad[1] = 0x01  # 511 code bits in a chunk that holds far fewer
+    dec = np.empty((4, 64), np.int16)
+    assert emu.hostemu_decode_blocks(bad.ctypes.data_as(u8p), s.ctypes.data_as(u8p), 4, dec.ctypes.data_as(i16p)) == 1
+
+
+def test_exact_division_identity(emu):
+    assert emu.hostemu_division_check(40000, 1) == 0
+
+
+def test_round_half_away_identity(emu):
+    assert emu.hostemu_round_check(400000, 2) == 0
