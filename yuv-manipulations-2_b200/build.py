@@ -53,7 +53,7 @@ def build_cxx(force: bool = False, verbose: bool = False):
     """The drop-in class library and (if the reference CLI object is available) the unmodified CLI on top of it."""
     LIB.mkdir(exist_ok=True)
     out = LIB / "libmyyuv_lib.so"
-    srcs = [CSRC / "myyuv_bmp.cpp", CSRC / "myyuv_yuv.cpp"]
+    srcs = [CSRC / "bmp_host.cpp", CSRC / "yuv_host.cpp"]
     if not all(s.exists() for s in srcs):
         return None
     deps = srcs + list((ROOT / "include").glob("*.h*"))
