@@ -35,6 +35,16 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# The contract is ONE JSON line on stdout.  Libraries (NCCL's version banner, for one) also write to fd 1, so fd 1
+# is pointed at stderr for the whole run and the JSON line is written to the saved descriptor at the end.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -156,7 +166,7 @@ def reference_main(args):
         "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -324,6 +334,8 @@ def b200_main(args):
         "frac": round(achieved / hbm_peak, 4), "traffic": None, "peak_source": peak_src,
         "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": round(dom_ms, 4),
         "compress_kernel_ms": round(c_ms, 4), "decompress_kernel_ms": round(d_ms, 4),
+        "timed": "CUDA events recorded inside the library on its stream: compress = the 4-kernel sequence code/scan/place/headers "
+                 "(dct_compress_kernel is >85% of it, profiles/), decompress = dct_decompress_kernel",
         "compress_GBps": round(alg_bytes / (c_ms / 1e3) / 1e9, 1), "decompress_GBps": round(alg_bytes / (d_ms / 1e3) / 1e9, 1),
         "compress_Mpixel_s": round(F * W * H / (c_ms / 1e3) / 1e6, 1), "decompress_Mpixel_s": round(F * W * H / (d_ms / 1e3) / 1e6, 1),
         # the bit-exact unfused 8x8 float DCT: 1920 FP32 mul/add per block; issue-rate view of the same kernel
@@ -342,7 +354,7 @@ def b200_main(args):
         "roofline": roofline, "cpu_baseline": cpu,
         "payload_bytes_per_step_per_gpu": payload_bytes, "bytes_per_pixel": round(payload_bytes / (F * W * H), 4),
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
