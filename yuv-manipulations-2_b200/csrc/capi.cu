@@ -114,7 +114,7 @@ struct myyuvb_ctx {
   cudaStream_t stream = nullptr, copy_stream = nullptr;
   bool own_stream = false;
   int grid = 0, grid_dec = 0;
-  Buffer d_in, d_out, d_status, d_tiles, d_plane_start, d_counters, d_sizes, d_overflow, d_desc, d_offsets;
+  Buffer d_in, d_out, d_plane_start, d_counters, d_sizes, d_overflow, d_desc, d_offsets;
   Buffer d_scratch, d_tile_pos, d_tile_total, d_tile_prefix;
   Buffer h_small, h_stage_in, h_stage_out;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -127,14 +127,13 @@ namespace {
 int ensure_workspace(myyuvb_ctx* c, const FrameGeom& g, bool encoder, Workspace* ws, uint64_t out_capacity = 0) {
   const uint64_t tiles = (uint64_t)g.tiles_per_frame * g.n_frames;
   int rc;
-  if ((rc = c->d_tiles.reserve(tiles * 8))) return rc;
   if ((rc = c->d_plane_start.reserve(((uint64_t)g.n_frames * 3 + 1) * 8))) return rc;
   if (!c->d_counters.p) {
     if ((rc = c->d_counters.reserve(64))) return rc;
     CU(cudaMemsetAsync(c->d_counters.p, 0, 64, c->stream));
   }
   if (encoder) {
-    if ((rc = c->d_sizes.reserve((uint64_t)g.nblk_frame * g.n_frames))) return rc;
+    if ((rc = c->d_sizes.reserve((uint64_t)g.nblk_frame * g.n_frames + 16))) return rc;
     if ((rc = c->d_overflow.reserve((uint64_t)c->grid * kEncTile * 256))) return rc;
     // pass-1 parking area: never more than the payload itself, i.e. never more than the caller's capacity
     const uint64_t worst = (uint64_t)g.nblk_frame * g.n_frames * 255;
@@ -145,8 +144,9 @@ int ensure_workspace(myyuvb_ctx* c, const FrameGeom& g, bool encoder, Workspace*
     if ((rc = c->d_tile_prefix.reserve(tiles * 8))) return rc;
   } else {
     if ((rc = c->d_desc.reserve((uint64_t)g.n_frames * 3 * sizeof(PlaneDesc)))) return rc;
+    if ((rc = c->d_tile_total.reserve(tiles * 4))) return rc;
+    if ((rc = c->d_tile_prefix.reserve(tiles * 8))) return rc;
   }
-  ws->tile_status = c->d_tiles.as<uint64_t>();
   ws->plane_start = c->d_plane_start.as<uint64_t>();
   ws->counters = c->d_counters.as<uint32_t>();
   ws->chunk_sizes = c->d_sizes.as<uint8_t>();
@@ -233,7 +233,7 @@ void myyuvb_ctx_destroy(myyuvb_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   cudaStreamSynchronize(c->copy_stream);
-  for (Buffer* b : {&c->d_in, &c->d_out, &c->d_status, &c->d_tiles, &c->d_plane_start, &c->d_counters, &c->d_sizes,
+  for (Buffer* b : {&c->d_in, &c->d_out, &c->d_plane_start, &c->d_counters, &c->d_sizes,
                     &c->d_overflow, &c->d_desc, &c->d_offsets, &c->d_scratch, &c->d_tile_pos, &c->d_tile_total, &c->d_tile_prefix, &c->h_small, &c->h_stage_in, &c->h_stage_out})
     b->release();
   for (auto& ev : c->ev)

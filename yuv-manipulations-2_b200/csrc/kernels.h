@@ -48,7 +48,6 @@ FrameGeom make_geom(uint32_t width, uint32_t height, uint32_t n_frames, uint32_t
 
 // Device scratch owned by a context (sized for the current batch by capi.cu).
 struct Workspace {
-  uint64_t* tile_status;   // [total tiles] decoupled look-back words
   uint64_t* plane_start;   // [n_frames*3 + 1] code bytes before each plane (compress)
   uint32_t* counters;      // [0] tile ticket, [1] error flags, [2..3] u64 scratch bump allocator
   uint8_t* chunk_sizes;    // [n_frames * nblk_frame] per-block chunk size, linear block order (compress)
@@ -57,7 +56,8 @@ struct Workspace {
   uint64_t scratch_cap;
   uint64_t* tile_pos;      // [total tiles] position of each tile's bytes in scratch
   uint32_t* tile_total;    // [total tiles] chunk bytes of each tile
-  uint64_t* tile_prefix;   // [total tiles] chunk bytes before each tile in file order (scan_tiles_kernel)
+  uint64_t* tile_prefix;   // [total tiles] chunk bytes before each tile: in file order over the batch (compress,
+                           // scan_tiles_kernel) or inside its plane (decompress, dec_scan_planes_kernel)
   void* plane_desc;        // [n_frames*3] PlaneDesc (decompress)
   int grid;                // persistent grid size of the codec kernels
   cudaEvent_t k_begin, k_end;  // recorded around the main codec kernel of each launch (myyuvb_last_kernel_ms)
