@@ -279,38 +279,69 @@ def b200_main(args):
     assert payload_bytes > 0 and int(d_off[0].item()) == 0
 
     # ---- end to end through the C ABI with host buffers (pinned), H2D/D2H inside the timed region ----
+    # Two host threads, one context each: while one batch is being compressed (H2D heavy) the previous batch is
+    # being decompressed (D2H heavy), so both PCIe directions are busy -- what a transcoding service would do with
+    # the batch_host calls.  Every frame still makes the full host -> GPU -> host -> GPU -> host round trip.
     e2e = None
     if not args.no_e2e:
+        import queue
+        import threading
+
         Fe = min(F, 32)
         h_in = capi.PinnedBuffer(Fe * frame_bytes)
         h_in.array[:] = d_in[:Fe].reshape(-1).cpu().numpy()
-        h_pay = capi.PinnedBuffer(Fe * 6 * 1024 * 1024)
+        h_pay = [capi.PinnedBuffer(Fe * 6 * 1024 * 1024) for _ in range(2)]
+        offs = [np.zeros(Fe + 1, np.uint64) for _ in range(2)]
         h_back = capi.PinnedBuffer(Fe * frame_bytes)
-        offs = np.zeros(Fe + 1, np.uint64)
-        ectx = pkg.Context(local)
+        cctx, dctx = pkg.Context(local), pkg.Context(local)
 
-        def e2e_step():
-            ectx.compress_batch_host(h_in.array, W, H, q, Fe, h_pay.array, offs)
-            ectx.decompress_batch_host(h_pay.array, offs, W, H, q, Fe, h_back.array)
+        def run_e2e(n_steps):
+            full, free = queue.Queue(), queue.Queue()
+            free.put(0)
+            free.put(1)
+            err = []
 
-        for _ in range(2):
-            e2e_step()
+            def producer():
+                try:
+                    for _ in range(n_steps):
+                        slot = free.get()
+                        cctx.compress_batch_host(h_in.array, W, H, q, Fe, h_pay[slot].array, offs[slot])
+                        full.put(slot)
+                except Exception as e:  # noqa: BLE001
+                    err.append(e)
+                full.put(None)
+
+            t = threading.Thread(target=producer)
+            t.start()
+            while True:
+                slot = full.get()
+                if slot is None:
+                    break
+                dctx.decompress_batch_host(h_pay[slot].array, offs[slot], W, H, q, Fe, h_back.array)
+                free.put(slot)
+            t.join()
+            if err:
+                raise err[0]
+
+        run_e2e(2)
         barrier()
-        n_e2e = max(3, min(args.steps, 5))
+        n_e2e = max(4, min(args.steps, 8))
         te0 = time.perf_counter()
-        for _ in range(n_e2e):
-            e2e_step()
+        run_e2e(n_e2e)
         barrier()
         te = torch.tensor([time.perf_counter() - te0], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        pay = int(offs[Fe])
+        pay = int(offs[0][Fe])
         e2e = {"value": round(world * Fe * W * H * n_e2e / float(te.item()) / 1e6, 1), "unit": UNIT,
                "h2d_bytes_per_step": Fe * frame_bytes + pay, "d2h_bytes_per_step": pay + Fe * frame_bytes,
-               "frames_per_step": Fe, "steps": n_e2e, "api": "myyuvb_dct_compress_batch_host + myyuvb_dct_decompress_batch_host, pinned host buffers"}
+               "frames_per_step": Fe, "steps": n_e2e,
+               "api": "myyuvb_dct_compress_batch_host + myyuvb_dct_decompress_batch_host on pinned host buffers; two host threads "
+                      "(one context each) so batch k+1 is compressed while batch k is decompressed"}
         same = bool((torch.from_numpy(h_back.array.copy()).to(dev) == d_back[:Fe].reshape(-1)).all().item())
         e2e["matches_device_path"] = same
-        ectx.close()
+        cctx.close()
+        dctx.close()
 
     if rank != 0:
         if world > 1:

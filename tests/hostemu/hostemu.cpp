@@ -24,17 +24,15 @@ struct ZArray {
 };
 }  // namespace
 
-extern "C" {
-
-// coef: n x 64 row-major.  stride: element stride of the scratch arrays (1, or e.g. 128 to mimic the
-// shared-memory interleave).  fast_cap16 != 0: try the 15-symbol scratch first like the kernel does.
-int hostemu_encode_blocks(const int16_t* coef, uint32_t n, int stride, int fast_cap16, uint8_t* out, uint8_t* sizes) {
-  using Fast = HuffScratch<15>;
-  using Big = HuffScratch<64>;
-  uint8_t* fb = new uint8_t[(size_t)Fast::kBytes * stride]();
-  int16_t* fh = new int16_t[(size_t)Fast::kSyms * stride]();
-  uint8_t* bb = new uint8_t[(size_t)Big::kBytes * stride]();
-  int16_t* bh = new int16_t[(size_t)Big::kSyms * stride]();
+namespace {
+template <int STRIDE>
+int encode_blocks(const int16_t* coef, uint32_t n, int fast_cap15, uint8_t* out, uint8_t* sizes) {
+  using Fast = HuffScratch<15, STRIDE>;
+  using Big = HuffScratch<64, STRIDE>;
+  uint8_t* fb = new uint8_t[(size_t)Fast::kBytes * STRIDE]();
+  int16_t* fh = new int16_t[(size_t)Fast::kSyms * STRIDE]();
+  uint8_t* bb = new uint8_t[(size_t)Big::kBytes * STRIDE]();
+  int16_t* bh = new int16_t[(size_t)Big::kSyms * STRIDE]();
   int big_used = 0;
   for (uint32_t b = 0; b < n; b++) {
     int16_t z[64];
@@ -42,20 +40,20 @@ int hostemu_encode_blocks(const int16_t* coef, uint32_t n, int stride, int fast_
     int L = 64;
     while (L > 0 && z[L - 1] == 0) L--;
     ZArray za{z};
-    Fast fs{fb, fh, stride};
-    Big bs{bb, bh, stride};
+    Fast fs{fb, fh};
+    Big bs{bb, bh};
     HuffPlan pl;
     pl.n = -1;
-    if (fast_cap16) pl = huff_plan<15>(za, L, fs, NoWarp{});
+    if (fast_cap15) pl = huff_plan(za, L, fs, NoWarp{});
     bool big = false;
     if (pl.n < 0) {
       big = true;
       big_used++;
-      pl = huff_plan<64>(za, L, bs, NoWarp{});
+      pl = huff_plan(za, L, bs, NoWarp{});
     }
     uint8_t tmp[256];
-    if (big) huff_emit<64>(za, pl, bs, tmp, NoWarp{});
-    else huff_emit<15>(za, pl, fs, tmp, NoWarp{});
+    if (big) huff_emit(za, pl, bs, tmp, NoWarp{});
+    else huff_emit(za, pl, fs, tmp, NoWarp{});
     const int sz = pl.size();
     memcpy(out, tmp, (size_t)sz);
     out += sz;
@@ -63,6 +61,15 @@ int hostemu_encode_blocks(const int16_t* coef, uint32_t n, int stride, int fast_
   }
   delete[] fb; delete[] fh; delete[] bb; delete[] bh;
   return big_used;
+}
+}  // namespace
+
+extern "C" {
+
+// coef: n x 64 row-major.  stride: element stride of the scratch arrays (1, or 128 to mimic the shared-memory
+// interleave of the kernel).  fast_cap15 != 0: try the 15-symbol scratch first like the kernel does.
+int hostemu_encode_blocks(const int16_t* coef, uint32_t n, int stride, int fast_cap15, uint8_t* out, uint8_t* sizes) {
+  return stride == 128 ? encode_blocks<128>(coef, n, fast_cap15, out, sizes) : encode_blocks<1>(coef, n, fast_cap15, out, sizes);
 }
 
 int hostemu_decode_blocks(const uint8_t* chunks, const uint8_t* sizes, uint32_t n, int16_t* coef) {

@@ -68,16 +68,15 @@ MYB_HD int ctz64(uint64_t v) {
 
 // ---------------------------------------------------------------------------------------------------
 // Scratch memory of one block's Huffman build.  All arrays are bytes addressed as b[(off + i) * stride]
-// (symbols: 16-bit, h[i * stride]).  On the GPU the fast instance lives in shared memory with
-// stride = threads per CTA, so the lanes of a warp hit consecutive bytes; the fallback instance for
+// (symbols: 16-bit, h[i * stride]; the stride is a template constant so index arithmetic folds into the
+// addressing).  On the GPU the fast instance lives in shared memory with stride = threads per CTA, so the lanes of a warp hit consecutive bytes; the fallback instance for
 // blocks with many distinct symbols lives in per-thread local memory with stride 1.
 // CAP = max distinct symbols (+1 slot for the key 0 that freq[0] may insert, Huffman.cpp:195).
 // ---------------------------------------------------------------------------------------------------
-template <int CAP>
+template <int CAP, int STRIDE>
 struct HuffScratch {
   uint8_t* b;
   int16_t* h;
-  int stride;
   static constexpr int kCap = CAP;
   static constexpr int kCnt = 0;                 // [CAP+1] occurrences of slot s in the message
   static constexpr int kOrd = kCnt + CAP + 1;    // [CAP+1] hash-list order: slot at list position p
@@ -89,8 +88,8 @@ struct HuffScratch {
   static constexpr int kSorted = kCode + CAP;    // [CAP]   slots ordered by (length, symbol value)
   static constexpr int kBytes = kSorted + CAP;   // bytes per block
   static constexpr int kSyms = CAP + 1;          // int16 per block
-  MYB_HD uint8_t& at(int off, int i) const { return b[(off + i) * stride]; }
-  MYB_HD int16_t& sym(int i) const { return h[i * stride]; }
+  MYB_HD uint8_t& at(int off, int i) const { return b[(off + i) * STRIDE]; }
+  MYB_HD int16_t& sym(int i) const { return h[i * STRIDE]; }
 };
 
 struct HuffPlan {
@@ -125,8 +124,8 @@ MYB_HD int hash_bucket(int v, int nb) {
 
 // libstdc++ _M_insert_bucket_begin / _M_rehash_aux: a key whose bucket already holds nodes goes right
 // before the first node of that bucket's run, otherwise to the front of the whole list.
-template <int CAP>
-MYB_HD void list_place(const HuffScratch<CAP>& S, int& ln, int slot, int bucket) {
+template <int CAP, int STRIDE>
+MYB_HD void list_place(const HuffScratch<CAP, STRIDE>& S, int& ln, int slot, int bucket) {
   int p = 0;
   for (int i = 0; i < ln; i++)
     if (S.at(S.kBkt, i) == bucket) { p = i; break; }
@@ -142,8 +141,8 @@ MYB_HD void list_place(const HuffScratch<CAP>& S, int& ln, int slot, int bucket)
 // General case of the map's iteration order (more than 13 keys): 13 -> 29 -> 59 -> 127 buckets, rehash before
 // inserting key number 14, 30, 60 (_Prime_rehash_policy::_M_need_rehash, max_load_factor 1, growth 2).
 // Keys are slots 0..m-1 in first-occurrence order; erase_slot (>= 0) is removed at the end.  Result in kOrd.
-template <int CAP>
-MYB_HD void hash_list_order_general(const HuffScratch<CAP>& S, int m, int erase_slot) {
+template <int CAP, int STRIDE>
+MYB_HD void hash_list_order_general(const HuffScratch<CAP, STRIDE>& S, int m, int erase_slot) {
   int ln = 0, nb = 13;
   for (int s = 0; s < m; s++) {
     if (s == 13 || s == 29 || s == 59) {
@@ -170,8 +169,8 @@ MYB_HD void hash_list_order_general(const HuffScratch<CAP>& S, int m, int erase_
 
 // std::push_heap with Compare(a,b) = a.freq > b.freq (Huffman.hpp:41-45; stl_heap.h __push_heap).
 // heap lives in kBkt (free after the list order is final).
-template <int CAP>
-MYB_HD void heap_sift_up(const HuffScratch<CAP>& S, int hole, int node, int wnode) {
+template <int CAP, int STRIDE>
+MYB_HD void heap_sift_up(const HuffScratch<CAP, STRIDE>& S, int hole, int node, int wnode) {
   while (hole > 0) {
     const int parent = (hole - 1) >> 1;
     const int pn = S.at(S.kBkt, parent);
@@ -183,8 +182,8 @@ MYB_HD void heap_sift_up(const HuffScratch<CAP>& S, int hole, int node, int wnod
 }
 
 // std::pop_heap + pop_back (stl_heap.h __pop_heap / __adjust_heap); returns the removed top node.
-template <int CAP>
-MYB_HD int heap_pop(const HuffScratch<CAP>& S, int& hsize) {
+template <int CAP, int STRIDE>
+MYB_HD int heap_pop(const HuffScratch<CAP, STRIDE>& S, int& hsize) {
   const int top = S.at(S.kBkt, 0);
   const int len = hsize - 1;
   hsize = len;
@@ -220,8 +219,8 @@ MYB_HD int group_table_bytes(int cnt) {  // one code length with cnt symbols, sp
 // void set(int i, int v); on success the first msg_len entries are overwritten with slot numbers
 // (the coefficient of slot s is S.sym(s)).  L = index of the last non-zero zigzag coefficient + 1 (0: all zero).
 // `warp`: cooperation policy; with WarpLockstep all 32 lanes must call this together (idle lanes pass L = 0).
-template <int CAP, class Z, class W>
-MYB_HD HuffPlan huff_plan(Z& z, int L, const HuffScratch<CAP>& S, const W& warp) {
+template <int CAP, int STRIDE, class Z, class W>
+MYB_HD HuffPlan huff_plan(Z& z, int L, const HuffScratch<CAP, STRIDE>& S, const W& warp) {
   HuffPlan pl;
   // ---- histogram in first-occurrence order (Huffman.cpp:176-189, message part only; the trailing zeros
   // only matter through the key 0 they may add to the map, handled below).  Coefficients in [-8, 7] find
@@ -412,8 +411,8 @@ struct BitSink {
 };
 
 // Serialise the chunk planned by huff_plan into dst[0 .. pl.size()).  Lanes without a chunk pass pl.n = 0.
-template <int CAP, class Z, class W>
-MYB_HD void huff_emit(Z& z, const HuffPlan& pl, const HuffScratch<CAP>& S, uint8_t* dst, const W& warp) {
+template <int CAP, int STRIDE, class Z, class W>
+MYB_HD void huff_emit(Z& z, const HuffPlan& pl, const HuffScratch<CAP, STRIDE>& S, uint8_t* dst, const W& warp) {
   const int n = pl.n > 0 ? pl.n : 0;
   if (n > 0) {
     dst[0] = (uint8_t)(pl.bits & 0xff);

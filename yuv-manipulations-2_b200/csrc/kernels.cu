@@ -254,8 +254,8 @@ void launch_xrgb_to_iyuv(const uint8_t* d_bgrx, uint8_t* d_iyuv, uint32_t w, uin
 // ===================================================================================================
 constexpr int kStageBytes = 4 * 1024;                  // shared-memory staging of one tile's chunk bytes
 constexpr int kFastSyms = 15;                          // distinct symbols handled with shared-memory scratch
-using FastScratch = HuffScratch<kFastSyms>;
-using BigScratch = HuffScratch<64>;
+using FastScratch = HuffScratch<kFastSyms, kCtaThreads>;
+using BigScratch = HuffScratch<64, 1>;
 
 struct EncSmem {
   uint16_t zz[64][kTileBlocks];                        // quantised coefficients, zigzag order; later slot ids
@@ -365,8 +365,8 @@ MYB_D int fdct_quant_block(const uint32_t (&raw)[16], const QTables& qt, int pla
 }
 
 // blocks with more than kFastSyms distinct symbols: same code on per-thread local-memory scratch, kept out of line
-__device__ __noinline__ HuffPlan plan_big(ZShared z, int L, BigScratch bs) { return huff_plan<64>(z, L, bs, NoWarp{}); }
-__device__ __noinline__ void emit_big(ZShared z, HuffPlan pl, BigScratch bs, uint8_t* dst) { huff_emit<64>(z, pl, bs, dst, NoWarp{}); }
+__device__ __noinline__ HuffPlan plan_big(ZShared z, int L, BigScratch bs) { return huff_plan(z, L, bs, NoWarp{}); }
+__device__ __noinline__ void emit_big(ZShared z, HuffPlan pl, BigScratch bs, uint8_t* dst) { huff_emit(z, pl, bs, dst, NoWarp{}); }
 
 __global__ void __launch_bounds__(kCtaThreads, 5)
     dct_compress_kernel(const __grid_constant__ EncParams P, const __grid_constant__ QTables qt) {
@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(kCtaThreads, 5)
   EncSmem& sm = *reinterpret_cast<EncSmem*>(smem_raw);
   const int tid = threadIdx.x;
   const FrameGeom& g = P.g;
-  FastScratch fs{&sm.hs_bytes[0][tid], &sm.hs_syms[0][tid], kCtaThreads};
+  FastScratch fs{&sm.hs_bytes[0][tid], &sm.hs_syms[0][tid]};
   ZShared z{&sm.zz[0][tid]};
   uint8_t* const overflow = P.ws.overflow + (uint64_t)blockIdx.x * (kEncTile * 256u);
 
@@ -423,11 +423,11 @@ __global__ void __launch_bounds__(kCtaThreads, 5)
       if (!live) L = 0;
       while (L > 0 && z.get(L - 1) == 0) L--;  // exact message length (Huffman.cpp:184-190); at most 8 steps
       __syncwarp();
-      HuffPlan pl = huff_plan<kFastSyms>(z, L, fs, WarpLockstep{});
+      HuffPlan pl = huff_plan(z, L, fs, WarpLockstep{});
       bool big = false;
       uint8_t lbytes[BigScratch::kBytes];
       int16_t lsyms[BigScratch::kSyms];
-      BigScratch bs{lbytes, lsyms, 1};
+      BigScratch bs{lbytes, lsyms};
       if (live && pl.n < 0) {  // more distinct symbols than the shared-memory scratch holds
         big = true;
         pl = plan_big(z, L, bs);
@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(kCtaThreads, 5)
         if (live && !fits && off <= (uint32_t)kStageBytes) atomicMin(&sm.split, off);
         HuffPlan plf = pl;
         if (!live || big) plf.n = 0;
-        huff_emit<kFastSyms>(z, plf, fs, dst, WarpLockstep{});
+        huff_emit(z, plf, fs, dst, WarpLockstep{});
         if (live && big) emit_big(z, pl, bs, dst);
       }
       carried += pass_total;
