@@ -262,6 +262,11 @@ struct EncSmem {
   uint8_t hs_bytes[FastScratch::kBytes][kCtaThreads];
   int16_t hs_syms[FastScratch::kSyms][kCtaThreads];
   alignas(16) uint8_t stage[kStageBytes + 8];
+  uint32_t hist[68];                                   // counting sort of the tile's blocks by message length
+  uint16_t boff[kTileBlocks];                          // chunk offset of block b inside the tile
+  uint8_t msg_len[kTileBlocks];                        // exact message length of block b
+  uint8_t csize[kTileBlocks];                          // chunk size of block b
+  uint8_t perm[kTileBlocks];                           // perm[t] = block entropy-coded by thread t
   uint32_t warp_sums[4];
   uint32_t tile;
   uint32_t split;
@@ -419,35 +424,68 @@ __global__ void __launch_bounds__(kCtaThreads, 5)
         }
         L = fdct_quant_block(raw, qt, plane, P.one, z.col);
       }
-      // ---- phase B: entropy-code the block (same thread, so no CTA barrier in between); warp lockstep ----
+      // ---- exact message length (Huffman.cpp:184-190; at most 8 steps back from the bound), then a counting sort of
+      //      the tile's blocks by it: thread t entropy-codes the block of rank t, so the lanes of a warp get messages
+      //      of similar length and the lockstep loops (trip count = warp maximum) waste few lanes ----
       if (!live) L = 0;
-      while (L > 0 && z.get(L - 1) == 0) L--;  // exact message length (Huffman.cpp:184-190); at most 8 steps
-      __syncwarp();
-      HuffPlan pl = huff_plan(z, L, fs, WarpLockstep{});
+      while (L > 0 && z.get(L - 1) == 0) L--;
+      const int lane = tid & 31, wid = tid >> 5;
+      sm.msg_len[tid] = (uint8_t)L;
+      if (tid < 68) sm.hist[tid] = 0;
+      __syncthreads();
+      const uint32_t within = atomicAdd(&sm.hist[L], 1u);
+      __syncthreads();
+      if (wid == 0) {  // exclusive prefix of the 65 (padded to 96) bins, three per lane
+        const uint32_t h0 = lane < 22 ? sm.hist[3 * lane] : 0, h1 = lane < 22 ? sm.hist[3 * lane + 1] : 0,
+                       h2 = lane < 22 ? sm.hist[3 * lane + 2] : 0;
+        uint32_t inc = h0 + h1 + h2;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t nn = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += nn;
+        }
+        if (lane < 22) {
+          sm.hist[3 * lane] = inc - h0 - h1 - h2;
+          sm.hist[3 * lane + 1] = inc - h1 - h2;
+          sm.hist[3 * lane + 2] = inc - h2;
+        }
+      }
+      __syncthreads();
+      sm.perm[sm.hist[L] + within] = (uint8_t)tid;
+      __syncthreads();
+      // ---- phase B: entropy-code block `mine` of this pass; warp lockstep ----
+      const uint32_t mine = sm.perm[tid];
+      const bool mlive = pass * kTileBlocks + mine < tc.nblk;
+      ZShared zm{&sm.zz[0][mine]};
+      const int Lm = sm.msg_len[mine];
+      HuffPlan pl = huff_plan(zm, Lm, fs, WarpLockstep{});
       bool big = false;
       uint8_t lbytes[BigScratch::kBytes];
       int16_t lsyms[BigScratch::kSyms];
       BigScratch bs{lbytes, lsyms};
-      if (live && pl.n < 0) {  // more distinct symbols than the shared-memory scratch holds
+      if (mlive && pl.n < 0) {  // more distinct symbols than the shared-memory scratch holds
         big = true;
-        pl = plan_big(z, L, bs);
+        pl = plan_big(zm, Lm, bs);
       }
-      __syncwarp();
-      const uint32_t size = live ? (uint32_t)pl.size() : 0u;
+      sm.csize[mine] = mlive ? (uint8_t)pl.size() : (uint8_t)0;
+      __syncthreads();
       // chunk sizes go to a linear side array; finalize_frames_kernel moves them behind the plane headers,
       // whose position depends on the (data dependent) size of the previous planes
+      const uint32_t size = sm.csize[tid];  // block `tid` again: offsets follow raster order
       if (live) P.ws.chunk_sizes[gblk0 + blk] = (uint8_t)size;
       uint32_t pass_total;
       const uint32_t off = carried + cta_exclusive_scan(size, sm.warp_sums, &pass_total);
+      sm.boff[tid] = (uint16_t)off;
+      // first chunk that does not fit the shared staging buffer (chunks never straddle; offsets only grow)
+      if (live && off + size > (uint32_t)kStageBytes && off <= (uint32_t)kStageBytes) atomicMin(&sm.split, off);
+      __syncthreads();
       {
-        const bool fits = off + size <= (uint32_t)kStageBytes;
-        uint8_t* dst = fits ? &sm.stage[off] : overflow + off;
-        // first chunk that does not fit the shared staging buffer (chunks never straddle; offsets only grow)
-        if (live && !fits && off <= (uint32_t)kStageBytes) atomicMin(&sm.split, off);
+        const uint32_t moff = sm.boff[mine], msize = sm.csize[mine];
+        uint8_t* dst = (moff + msize <= (uint32_t)kStageBytes) ? &sm.stage[moff] : overflow + moff;
         HuffPlan plf = pl;
-        if (!live || big) plf.n = 0;
-        huff_emit(z, plf, fs, dst, WarpLockstep{});
-        if (live && big) emit_big(z, pl, bs, dst);
+        if (!mlive || big) plf.n = 0;
+        huff_emit(zm, plf, fs, dst, WarpLockstep{});
+        if (mlive && big) emit_big(zm, pl, bs, dst);
       }
       carried += pass_total;
     }
@@ -476,8 +514,9 @@ __global__ void __launch_bounds__(kCtaThreads, 5)
   }
 }
 
-// Pass 2: exclusive scan of the tile totals in file order (one CTA; a 4K batch of 64 frames has ~10^5 tiles),
-// plus the number of code bytes before every plane.
+// Pass 2: exclusive scan of the tile totals in file order (one CTA, 8 tiles per thread per round; a 4K batch of
+// 64 frames has ~10^5 tiles), plus the number of code bytes before every plane.
+constexpr int kScanPerThread = 8;
 __global__ void __launch_bounds__(1024) scan_tiles_kernel(const __grid_constant__ EncParams P) {
   __shared__ u64 warp_sums[32];
   __shared__ u64 carry_s;
@@ -485,10 +524,16 @@ __global__ void __launch_bounds__(1024) scan_tiles_kernel(const __grid_constant_
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (threadIdx.x == 0) carry_s = 0;
   __syncthreads();
-  for (uint32_t base = 0; base < P.total_tiles; base += 1024) {
-    const uint32_t t = base + threadIdx.x;
-    const u64 v = t < P.total_tiles ? (u64)P.ws.tile_total[t] : 0;
-    u64 inc = v;
+  for (uint32_t base = 0; base < P.total_tiles; base += 1024 * kScanPerThread) {
+    const uint32_t t0 = base + threadIdx.x * kScanPerThread;
+    uint32_t v[kScanPerThread];
+    u64 mine = 0;
+#pragma unroll
+    for (int j = 0; j < kScanPerThread; j++) {
+      v[j] = t0 + j < P.total_tiles ? P.ws.tile_total[t0 + j] : 0u;
+      mine += v[j];
+    }
+    u64 inc = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const u64 n = __shfl_up_sync(0xffffffffu, inc, o);
@@ -507,15 +552,20 @@ __global__ void __launch_bounds__(1024) scan_tiles_kernel(const __grid_constant_
     }
     __syncthreads();
     const u64 carry = carry_s;
-    const u64 excl = carry + (wid ? warp_sums[wid - 1] : 0) + inc - v;
-    if (t < P.total_tiles) {
-      P.ws.tile_prefix[t] = excl;
-      // first tile of a plane: code bytes before this plane
-      const uint32_t f = t / g.tiles_per_frame, r = t - f * g.tiles_per_frame;
-      if (r == 0) P.ws.plane_start[f * 3] = excl;
-      else if (r == g.tiles[0]) P.ws.plane_start[f * 3 + 1] = excl;
-      else if (r == g.tiles[0] + g.tiles[1]) P.ws.plane_start[f * 3 + 2] = excl;
-      if (t == P.total_tiles - 1) P.ws.plane_start[g.n_frames * 3] = excl + v;
+    u64 excl = carry + (wid ? warp_sums[wid - 1] : 0) + inc - mine;
+#pragma unroll
+    for (int j = 0; j < kScanPerThread; j++) {
+      const uint32_t t = t0 + j;
+      if (t < P.total_tiles) {
+        P.ws.tile_prefix[t] = excl;
+        // first tile of a plane: code bytes before this plane
+        const uint32_t f = t / g.tiles_per_frame, r = t - f * g.tiles_per_frame;
+        if (r == 0) P.ws.plane_start[f * 3] = excl;
+        else if (r == g.tiles[0]) P.ws.plane_start[f * 3 + 1] = excl;
+        else if (r == g.tiles[0] + g.tiles[1]) P.ws.plane_start[f * 3 + 2] = excl;
+        if (t == P.total_tiles - 1) P.ws.plane_start[g.n_frames * 3] = excl + v[j];
+      }
+      excl += v[j];
     }
     __syncthreads();
     if (threadIdx.x == 1023) carry_s = carry + warp_sums[31];
