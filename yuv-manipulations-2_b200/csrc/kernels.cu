@@ -658,6 +658,10 @@ struct DecSmem {
   alignas(16) uint8_t stage[kDecStageBytes];  // the tile's chunk bytes
   uint8_t zigzag[64];
   float q[64];
+  uint32_t hist[64];                  // counting sort of the tile's blocks by chunk size
+  uint16_t boff[kTileBlocks];         // chunk offset of block b inside the tile
+  uint8_t bsize[kTileBlocks];
+  uint8_t perm[kTileBlocks];          // perm[t] = block decoded by thread t
   uint32_t warp_sums[4];
   uint32_t tile;
   u64 base;
@@ -853,25 +857,52 @@ __global__ void __launch_bounds__(kCtaThreads, 5)
     }
 #pragma unroll
     for (int i = 0; i < 64; i++) col[i * kTileBlocks] = 0.0f;
+    // Counting sort of the blocks by chunk size (4-byte bins) while the staging loads are in flight: thread t
+    // decodes the block of rank t, so the lanes of a warp get messages of similar length and the lockstep decode
+    // loop (trip count = warp maximum) wastes few lanes.
+    sm.boff[tid] = (uint16_t)off;
+    sm.bsize[tid] = (uint8_t)size;
+    if (tid < 64) sm.hist[tid] = 0;
+    __syncthreads();
+    const uint32_t key = (size >> 2) < 63u ? (size >> 2) : 63u;
+    const uint32_t within = atomicAdd(&sm.hist[key], 1u);
+    __syncthreads();
+    if (tid < 32) {  // exclusive prefix of the 64 bins, two per lane
+      const int lane = tid;
+      const uint32_t h0 = sm.hist[2 * lane], h1 = sm.hist[2 * lane + 1];
+      uint32_t inc = h0 + h1;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t nn = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += nn;
+      }
+      sm.hist[2 * lane] = inc - h0 - h1;
+      sm.hist[2 * lane + 1] = inc - h1;
+    }
+    __syncthreads();
+    sm.perm[sm.hist[key] + within] = (uint8_t)tid;
     __syncthreads();
 
     // ---- phase 1: canonical Huffman decode + dequantise into the thread's shared-memory column (warp lockstep) ----
+    const uint32_t blk = sm.perm[tid];
+    const bool mine = blk < tc.nblk;
     {
-      const uint8_t* chunk = (off + size <= (uint32_t)kDecStageBytes) ? &sm.stage[off] : content + off;
-      const int err = huff_decode_block(chunk, (int)size, [&](int j, int v) {
+      const uint32_t moff = sm.boff[blk], msize = sm.bsize[blk];
+      const uint8_t* chunk = (moff + msize <= (uint32_t)kDecStageBytes) ? &sm.stage[moff] : content + moff;
+      const int err = huff_decode_block(chunk, (int)msize, [&](int j, int v) {
         const int pos = sm.zigzag[j];
         col[pos * kTileBlocks] = __fmul_rn((float)v, sm.q[pos]);  // DCT.cpp:330-332
       }, WarpLockstep{});
-      if (live && (err || size == 0)) atomicOr(&P.ws.counters[1], kFlagHuffman);  // a chunk is at least 7 bytes
+      if (mine && (err || msize == 0)) atomicOr(&P.ws.counters[1], kFlagHuffman);  // a chunk is at least 7 bytes
     }
     __syncwarp();
     // ---- phase 2: inverse DCT, round, clamp, store ----
     {
       uint32_t outw[16];
       idct_block(col, P.one, outw);
-      if (live) {
+      if (mine) {
         const uint32_t pw = g.pw[plane], bw = g.bw[plane];
-        const uint32_t k = tc.k0 + tid;
+        const uint32_t k = tc.k0 + blk;
         const uint32_t by = k / bw, bx = k - by * bw;
         uint8_t* p = P.dst + (uint64_t)tc.frame * g.frame_bytes + g.plane_off[plane] + (uint64_t)by * 8 * pw + (uint64_t)bx * 8;
 #pragma unroll
