@@ -360,9 +360,15 @@ def b200_main(args):
     dom = "dct_compress_kernel" if c_ms >= d_ms else "dct_decompress_kernel"
     dom_ms = max(c_ms, d_ms)
     achieved = alg_bytes / (dom_ms / 1e3) / 1e9
+    traffic = None
+    try:  # DRAM bytes of the dominant kernel from the committed ncu capture, scaled to this run's frame count
+        tr = json.loads((ROOT / "profiles" / "r01_traffic.json").read_text())
+        traffic = int((tr[dom]["dram_read"] + tr[dom]["dram_write"]) * F / tr["frames"])
+    except Exception:  # noqa: BLE001
+        pass
     roofline = {
         "bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
-        "frac": round(achieved / hbm_peak, 4), "traffic": None, "peak_source": peak_src,
+        "frac": round(achieved / hbm_peak, 4), "traffic": traffic, "peak_source": peak_src,
         "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": round(dom_ms, 4),
         "compress_kernel_ms": round(c_ms, 4), "decompress_kernel_ms": round(d_ms, 4),
         "timed": "CUDA events recorded inside the library on its stream: compress = the 4-kernel sequence code/scan/place/headers "

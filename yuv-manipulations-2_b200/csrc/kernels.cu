@@ -746,6 +746,44 @@ MYB_D void idct_block(const float* col, float onef, uint32_t (&out)[16]) {
   }
 }
 
+// The same transform when every non-zero coefficient of the block lies in the top-left 4x4 corner (true for any
+// message of at most 10 zigzag positions).  Products with a zero coefficient are +-0 and adding +-0 leaves a partial
+// sum unchanged (an all-zero sum can only differ in the sign of zero, which round() discards), so dropping the terms
+// k >= 4 and the columns c >= 4 gives bit-identical pixels with 336 instead of 960 packed instructions.
+MYB_D void idct_block_4x4(const float* col, float onef, uint32_t (&out)[16]) {
+  const f2 ONE = dup(onef);
+  f2 d[16];  // d[a2 * 4 + c] = (D[2 a2][c], D[2 a2 + 1][c]), c < 4
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    float bk[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) bk[k] = col[(k * 8 + c) * kTileBlocks];
+#pragma unroll
+    for (int a2 = 0; a2 < 4; a2++) {
+      f2 acc = mul2(dup(bk[0]), mkp(dct_c(2 * a2), dct_c(2 * a2 + 1)));
+#pragma unroll
+      for (int k = 1; k < 4; k++) acc = sum2(acc, mul2(dup(bk[k]), mkp(dct_c(k * 8 + 2 * a2), dct_c(k * 8 + 2 * a2 + 1))), ONE);
+      d[a2 * 4 + c] = acc;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 16; r++) out[r] = 0;
+#pragma unroll
+  for (int a2 = 0; a2 < 4; a2++) {
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+      f2 acc = mul2(d[a2 * 4], dup(dct_c(b)));
+#pragma unroll
+      for (int k = 1; k < 4; k++) acc = sum2(acc, mul2(d[a2 * 4 + k], dup(dct_c(k * 8 + b))), ONE);
+      const f2 t = add2_rz(acc, half_like(acc));
+      const uint32_t ia = (uint32_t)__viaddmin_s32_relu(__float2int_rz(t.x), 128, 255);
+      const uint32_t ib = (uint32_t)__viaddmin_s32_relu(__float2int_rz(t.y), 128, 255);
+      out[(2 * a2) * 2 + (b >> 2)] |= ia << (8 * (b & 3));
+      out[(2 * a2 + 1) * 2 + (b >> 2)] |= ib << (8 * (b & 3));
+    }
+  }
+}
+
 // Decompress pre-pass 1: chunk bytes of every tile (one warp per tile, 4 size bytes per lane).
 __global__ void __launch_bounds__(256) dec_tile_totals_kernel(const __grid_constant__ DecParams P) {
   const FrameGeom& g = P.g;
@@ -886,12 +924,14 @@ __global__ void __launch_bounds__(kCtaThreads, 5)
     // ---- phase 1: canonical Huffman decode + dequantise into the thread's shared-memory column (warp lockstep) ----
     const uint32_t blk = sm.perm[tid];
     const bool mine = blk < tc.nblk;
+    int nsym = 0;  // decoded zigzag positions: the non-zero coefficients lie in positions [0, nsym)
     {
       const uint32_t moff = sm.boff[blk], msize = sm.bsize[blk];
       const uint8_t* chunk = (moff + msize <= (uint32_t)kDecStageBytes) ? &sm.stage[moff] : content + moff;
       const int err = huff_decode_block(chunk, (int)msize, [&](int j, int v) {
         const int pos = sm.zigzag[j];
         col[pos * kTileBlocks] = __fmul_rn((float)v, sm.q[pos]);  // DCT.cpp:330-332
+        nsym = j + 1;
       }, WarpLockstep{});
       if (mine && (err || msize == 0)) atomicOr(&P.ws.counters[1], kFlagHuffman);  // a chunk is at least 7 bytes
     }
@@ -899,7 +939,20 @@ __global__ void __launch_bounds__(kCtaThreads, 5)
     // ---- phase 2: inverse DCT, round, clamp, store ----
     {
       uint32_t outw[16];
-      idct_block(col, P.one, outw);
+      // zigzag positions 0..9 are the anti-diagonals row + col <= 3, all inside the top-left 4x4 corner
+      if (__all_sync(0xffffffffu, nsym <= 1)) {
+        // DC only: D[a][0] = C[0][a] * B00 and P[a][b] = D[a][0] * C[0][b] with all C[0][.] equal -> a flat block
+        const float c0 = dct_c(0);
+        const float pv = __fmul_rn(__fmul_rn(c0, col[0]), c0);
+        const float t = __fadd_rz(pv, __int_as_float((__float_as_int(pv) & 0x80000000) | 0x3f000000));
+        const uint32_t px = (uint32_t)__viaddmin_s32_relu(__float2int_rz(t), 128, 255) * 0x01010101u;
+#pragma unroll
+        for (int r = 0; r < 16; r++) outw[r] = px;
+      } else if (__all_sync(0xffffffffu, nsym <= 10)) {
+        idct_block_4x4(col, P.one, outw);
+      } else {
+        idct_block(col, P.one, outw);
+      }
       if (mine) {
         const uint32_t pw = g.pw[plane], bw = g.bw[plane];
         const uint32_t k = tc.k0 + blk;
