@@ -134,7 +134,7 @@ int ensure_workspace(myyuvb_ctx* c, const FrameGeom& g, bool encoder, Workspace*
   }
   if (encoder) {
     if ((rc = c->d_sizes.reserve((uint64_t)g.nblk_frame * g.n_frames + 16))) return rc;
-    if ((rc = c->d_overflow.reserve((uint64_t)c->grid * (kCtaThreads / 32) * kEncTile * 256))) return rc;
+    if ((rc = c->d_overflow.reserve((uint64_t)c->grid * kEncTile * 256))) return rc;
     // pass-1 parking area: never more than the payload itself, i.e. never more than the caller's capacity
     const uint64_t worst = (uint64_t)g.nblk_frame * g.n_frames * 255;
     ws->scratch_cap = std::min<uint64_t>(out_capacity, worst);

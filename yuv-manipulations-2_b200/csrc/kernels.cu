@@ -124,70 +124,67 @@ MYB_D TileCoord tile_coord(const FrameGeom& g, uint32_t tile) {
   return t;
 }
 
-// Warp-wide exclusive scan of one value per lane; *total gets the warp sum.
-MYB_D uint32_t warp_exclusive_scan(uint32_t v, int lane, uint32_t* total) {
+// CTA-wide exclusive scan of one value per thread (kCtaThreads = 128 -> 4 warps); returns exclusive
+// prefix, *total gets the CTA sum.  Contains two __syncthreads.
+MYB_D uint32_t cta_exclusive_scan(uint32_t v, uint32_t* warp_sums /* [4] shared */, uint32_t* total) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   uint32_t inc = v;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     const uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
     if (lane >= o) inc += n;
   }
-  *total = __shfl_sync(0xffffffffu, inc, 31);
-  return inc - v;
+  if (lane == 31) warp_sums[wid] = inc;
+  __syncthreads();
+  uint32_t base = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < kCtaThreads / 32; w++) {
+    const uint32_t s = warp_sums[w];
+    if (w < wid) base += s;
+    tot += s;
+  }
+  __syncthreads();
+  *total = tot;
+  return base + inc - v;
 }
 
-// Copy n bytes from shared memory (4-byte aligned base, readable up to n + 4) to global memory at arbitrary
-// alignment with coalesced 32-bit stores; `tid` of `nthreads` cooperating threads (a warp or a CTA).
-MYB_D void copy_smem_to_global(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint32_t n, uint32_t tid, uint32_t nthreads) {
+// Copy n bytes from shared memory (4-byte aligned base) to global memory at arbitrary alignment with
+// coalesced 32-bit stores.
+MYB_D void copy_smem_to_global(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint32_t n) {
   const uint32_t head = min((uint32_t)((4 - ((uintptr_t)dst & 3)) & 3), n);
-  if (tid < head) dst[tid] = src[tid];
+  if (threadIdx.x < head) dst[threadIdx.x] = src[threadIdx.x];
   const uint32_t words = (n - head) >> 2;
   uint32_t* dw = reinterpret_cast<uint32_t*>(dst + head);
   const uint32_t* sw = reinterpret_cast<const uint32_t*>(src);
   const uint32_t sh = head * 8;  // source is `head` bytes off word alignment
-  for (uint32_t w = tid; w < words; w += nthreads) {
+  for (uint32_t w = threadIdx.x; w < words; w += kCtaThreads) {
     const uint32_t lo = sw[w], hi = sw[w + 1];  // sw[w+1] is inside the padded staging buffer
     dw[w] = sh ? __funnelshift_r(lo, hi, sh) : lo;
   }
   const uint32_t done = head + (words << 2);
-  if (tid < n - done) dst[done + tid] = src[done + tid];
+  if (threadIdx.x < n - done) dst[done + threadIdx.x] = src[done + threadIdx.x];
 }
 
-// Copy n bytes global -> global, both at arbitrary alignment: destination-aligned 32-bit stores, source words
-// funnel-shifted.  Never reads a source word that holds no byte of [src, src + n).
-MYB_D void copy_global_to_global(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint32_t n, uint32_t tid, uint32_t nthreads) {
+
+// Copy n bytes global -> global, both at arbitrary alignment, by the whole CTA: destination-aligned 32-bit
+// stores, source words funnel-shifted.  Reads stay inside [src, src + n) rounded out to aligned words that
+// overlap it (never touches a word that holds no source byte).
+MYB_D void copy_global_to_global(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint32_t n, int nthreads) {
   const uint32_t head = min((uint32_t)((4 - ((uintptr_t)dst & 3)) & 3), n);
-  if (tid < head) dst[tid] = src[tid];
+  if (threadIdx.x < head) dst[threadIdx.x] = src[threadIdx.x];
   const uint32_t words = (n - head) >> 2;
   uint32_t* dw = reinterpret_cast<uint32_t*>(dst + head);
   const uint8_t* s0 = src + head;
   const uint32_t mis = (uint32_t)((uintptr_t)s0 & 3);
   const uint32_t* sw = reinterpret_cast<const uint32_t*>(s0 - mis);
-  for (uint32_t w = tid; w < words; w += nthreads) {
+  for (uint32_t w = threadIdx.x; w < words; w += nthreads) {
     const uint32_t lo = sw[w];
     uint32_t v = lo;
     if (mis) v = __funnelshift_r(lo, sw[w + 1], mis * 8);  // sw[w+1] holds source bytes 4w+4-mis.. < n
     dw[w] = v;
   }
   const uint32_t done = head + (words << 2);
-  if (tid < n - done) dst[done + tid] = src[done + tid];
-}
-
-// Copy n bytes global (arbitrary alignment) -> shared memory (4-byte aligned) with aligned 32-bit loads.
-MYB_D void copy_global_to_smem(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint32_t n, uint32_t tid, uint32_t nthreads) {
-  const uint32_t mis = (uint32_t)((uintptr_t)src & 3);
-  const uint32_t* gw = reinterpret_cast<const uint32_t*>(src - mis);
-  uint32_t* dw = reinterpret_cast<uint32_t*>(dst);
-  const uint32_t words = (n + 3) >> 2;
-  for (uint32_t w = tid; w < words; w += nthreads) {
-    const uint32_t lo = __ldg(gw + w);  // holds source byte 4w, which is < n
-    uint32_t v = lo;
-    if (mis) {
-      const uint32_t hi = (4 * (w + 1) < n + mis) ? __ldg(gw + w + 1) : 0u;  // only if it holds a byte of the range
-      v = __funnelshift_r(lo, hi, mis * 8);
-    }
-    dw[w] = v;
-  }
+  if (threadIdx.x < n - done) dst[done + threadIdx.x] = src[done + threadIdx.x];
 }
 
 // ===================================================================================================
@@ -255,22 +252,29 @@ void launch_xrgb_to_iyuv(const uint8_t* d_bgrx, uint8_t* d_iyuv, uint32_t w, uin
 //   stage 2:  (Y[a][b], Y[a+1][b]) = sum_k (T[a][k], T[a+1][k]) * C[b][k]      data pair x broadcast immediate
 // so no transposition or register shuffling is needed between the stages (cuobjdump: 960 FMUL2/FFMA2, 0 MOV).
 // ===================================================================================================
-constexpr int kStageBytes = 1024;                      // per-warp shared-memory staging of one tile's chunk bytes
+constexpr int kStageBytes = 4 * 1024;                  // shared-memory staging of one tile's chunk bytes
 constexpr int kFastSyms = 15;                          // distinct symbols handled with shared-memory scratch
-constexpr int kWarps = kCtaThreads / 32;
-using FastScratch = HuffScratch<kFastSyms, 32>;
+using FastScratch = HuffScratch<kFastSyms, kCtaThreads>;
 using BigScratch = HuffScratch<64, 1>;
 
-// Everything a warp needs for its tile; warps of a CTA share nothing and never meet at a barrier.
-struct EncWarpSmem {
+struct EncSmem {
   uint16_t zz[64][kTileBlocks];                        // quantised coefficients, zigzag order; later slot ids
-  uint8_t hs_bytes[FastScratch::kBytes][32];
-  int16_t hs_syms[FastScratch::kSyms][32];
+  uint8_t hs_bytes[FastScratch::kBytes][kCtaThreads];
+  int16_t hs_syms[FastScratch::kSyms][kCtaThreads];
   alignas(16) uint8_t stage[kStageBytes + 8];
+  uint32_t hist[68];                                   // counting sort of the tile's blocks by message length
+  uint16_t boff[kTileBlocks];                          // chunk offset of block b inside the tile
+  uint8_t msg_len[kTileBlocks];                        // exact message length of block b
+  uint8_t csize[kTileBlocks];                          // chunk size of block b
+  uint8_t perm[kTileBlocks];                           // perm[t] = block entropy-coded by thread t
+  uint32_t warp_sums[4];
+  uint32_t tile;
+  uint32_t split;
+  u64 base;
 };
-static_assert(sizeof(EncWarpSmem) * kWarps <= 44 * 1024 + 256, "encoder shared memory must allow 5 CTAs per SM");
+static_assert(sizeof(EncSmem) <= 44 * 1024 + 256, "EncSmem must allow 5 CTAs per SM");
 
-struct ZShared {  // accessor of one block's column in EncWarpSmem::zz
+struct ZShared {  // accessor of one block's column in EncSmem::zz
   uint16_t* col;
   MYB_D int get(int i) const { return (int)(int16_t)col[i * kTileBlocks]; }
   MYB_D void set(int i, int v) { col[i * kTileBlocks] = (uint16_t)v; }
@@ -372,33 +376,42 @@ __device__ __noinline__ void emit_big(ZShared z, HuffPlan pl, BigScratch bs, uin
 __global__ void __launch_bounds__(kCtaThreads, 5)
     dct_compress_kernel(const __grid_constant__ EncParams P, const __grid_constant__ QTables qt) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  EncWarpSmem& sm = reinterpret_cast<EncWarpSmem*>(smem_raw)[wid];
+  EncSmem& sm = *reinterpret_cast<EncSmem*>(smem_raw);
+  const int tid = threadIdx.x;
   const FrameGeom& g = P.g;
-  FastScratch fs{&sm.hs_bytes[0][lane], &sm.hs_syms[0][lane]};
-  ZShared z{&sm.zz[0][lane]};
-  uint8_t* const overflow = P.ws.overflow + ((uint64_t)blockIdx.x * kWarps + wid) * (kEncTile * 256u);
+  FastScratch fs{&sm.hs_bytes[0][tid], &sm.hs_syms[0][tid]};
+  ZShared z{&sm.zz[0][tid]};
+  uint8_t* const overflow = P.ws.overflow + (uint64_t)blockIdx.x * (kEncTile * 256u);
 
   while (true) {
-    uint32_t t0 = 0;
-    if (lane == 0) t0 = atomicAdd(&P.ws.counters[0], (uint32_t)kTicketBatch);
-    t0 = __shfl_sync(0xffffffffu, t0, 0);
-    if (t0 >= P.total_tiles) break;
-    const uint32_t t1 = t0 + kTicketBatch < P.total_tiles ? t0 + kTicketBatch : P.total_tiles;
+    if (tid == 0) {
+      sm.tile = atomicAdd(&P.ws.counters[0], 1u);
+      sm.split = 0xffffffffu;
+    }
+    __syncthreads();
+    const uint32_t tile = sm.tile;
+    if (tile >= P.total_tiles) break;
+    const TileCoord tc = tile_coord(g, tile);
+    const int plane = (int)tc.plane;
+    const uint32_t pw = g.pw[plane], bw = g.bw[plane];
+    const uint8_t* plane_src = P.src + (uint64_t)tc.frame * g.frame_bytes + g.plane_off[plane];
+    const uint64_t gblk0 = (uint64_t)tc.frame * g.nblk_frame + (plane > 0 ? g.nblk[0] : 0) + (plane > 1 ? g.nblk[1] : 0) + tc.k0;
+    uint32_t carried = 0;  // chunk bytes staged by the earlier passes of this tile
+
+    // A tile is kEncPasses passes of 128 blocks (one per thread) so that the serial look-back chain advances
+    // 512 blocks per hop; each pass runs phase A (DCT) and phase B (entropy coding) and appends to the staging area.
 #pragma unroll 1
-    for (uint32_t tile = t0; tile < t1; tile++) {
-      const TileCoord tc = tile_coord(g, tile);
-      const int plane = (int)tc.plane;
-      const bool live = (uint32_t)lane < tc.nblk;
+    for (uint32_t pass = 0; pass * kTileBlocks < tc.nblk; pass++) {
+      const uint32_t blk = pass * kTileBlocks + tid;
+      const bool live = blk < tc.nblk;
       // ---- phase A: load the block, forward DCT, quantise, coefficients (zigzag order) to shared memory ----
       int L;
       {
         uint32_t raw[16];
         if (live) {
-          const uint32_t pw = g.pw[plane], bw = g.bw[plane];
-          const uint32_t k = tc.k0 + lane;
+          const uint32_t k = tc.k0 + blk;
           const uint32_t by = k / bw, bx = k - by * bw;
-          const uint8_t* p = P.src + (uint64_t)tc.frame * g.frame_bytes + g.plane_off[plane] + (uint64_t)by * 8 * pw + (uint64_t)bx * 8;
+          const uint8_t* p = plane_src + (uint64_t)by * 8 * pw + (uint64_t)bx * 8;
 #pragma unroll
           for (int r = 0; r < 8; r++) {
             const uint2 v = __ldg(reinterpret_cast<const uint2*>(p + (uint64_t)r * pw));
@@ -411,63 +424,99 @@ __global__ void __launch_bounds__(kCtaThreads, 5)
         }
         L = fdct_quant_block(raw, qt, plane, P.one, z.col);
       }
-      // ---- phase B: entropy-code the block (same lane); the 32 lanes run the coder in lockstep ----
+      // ---- exact message length (Huffman.cpp:184-190; at most 8 steps back from the bound), then a counting sort of
+      //      the tile's blocks by it: thread t entropy-codes the block of rank t, so the lanes of a warp get messages
+      //      of similar length and the lockstep loops (trip count = warp maximum) waste few lanes ----
       if (!live) L = 0;
-      while (L > 0 && z.get(L - 1) == 0) L--;  // exact message length (Huffman.cpp:184-190); at most 8 steps
-      __syncwarp();
-      HuffPlan pl = huff_plan(z, L, fs, WarpLockstep{});
+      while (L > 0 && z.get(L - 1) == 0) L--;
+      const int lane = tid & 31, wid = tid >> 5;
+      sm.msg_len[tid] = (uint8_t)L;
+      if (tid < 68) sm.hist[tid] = 0;
+      __syncthreads();
+      const uint32_t within = atomicAdd(&sm.hist[L], 1u);
+      __syncthreads();
+      if (wid == 0) {  // exclusive prefix of the 65 (padded to 96) bins, three per lane
+        const uint32_t h0 = lane < 22 ? sm.hist[3 * lane] : 0, h1 = lane < 22 ? sm.hist[3 * lane + 1] : 0,
+                       h2 = lane < 22 ? sm.hist[3 * lane + 2] : 0;
+        uint32_t inc = h0 + h1 + h2;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t nn = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += nn;
+        }
+        if (lane < 22) {
+          sm.hist[3 * lane] = inc - h0 - h1 - h2;
+          sm.hist[3 * lane + 1] = inc - h1 - h2;
+          sm.hist[3 * lane + 2] = inc - h2;
+        }
+      }
+      __syncthreads();
+      sm.perm[sm.hist[L] + within] = (uint8_t)tid;
+      __syncthreads();
+      // ---- phase B: entropy-code block `mine` of this pass; warp lockstep ----
+      const uint32_t mine = sm.perm[tid];
+      const bool mlive = pass * kTileBlocks + mine < tc.nblk;
+      ZShared zm{&sm.zz[0][mine]};
+      const int Lm = sm.msg_len[mine];
+      HuffPlan pl = huff_plan(zm, Lm, fs, WarpLockstep{});
       bool big = false;
       uint8_t lbytes[BigScratch::kBytes];
       int16_t lsyms[BigScratch::kSyms];
       BigScratch bs{lbytes, lsyms};
-      if (live && pl.n < 0) {  // more distinct symbols than the shared-memory scratch holds
+      if (mlive && pl.n < 0) {  // more distinct symbols than the shared-memory scratch holds
         big = true;
-        pl = plan_big(z, L, bs);
+        pl = plan_big(zm, Lm, bs);
       }
-      __syncwarp();
-      const uint32_t size = live ? (uint32_t)pl.size() : 0u;
+      sm.csize[mine] = mlive ? (uint8_t)pl.size() : (uint8_t)0;
+      __syncthreads();
       // chunk sizes go to a linear side array; finalize_frames_kernel moves them behind the plane headers,
       // whose position depends on the (data dependent) size of the previous planes
-      if (live) {
-        const uint64_t gblk = (uint64_t)tc.frame * g.nblk_frame + (plane > 0 ? g.nblk[0] : 0) + (plane > 1 ? g.nblk[1] : 0) + tc.k0;
-        P.ws.chunk_sizes[gblk + lane] = (uint8_t)size;
-      }
-      uint32_t total;
-      const uint32_t off = warp_exclusive_scan(size, lane, &total);
-      const bool fits = off + size <= (uint32_t)kStageBytes;
+      const uint32_t size = sm.csize[tid];  // block `tid` again: offsets follow raster order
+      if (live) P.ws.chunk_sizes[gblk0 + blk] = (uint8_t)size;
+      uint32_t pass_total;
+      const uint32_t off = carried + cta_exclusive_scan(size, sm.warp_sums, &pass_total);
+      sm.boff[tid] = (uint16_t)off;
+      // first chunk that does not fit the shared staging buffer (chunks never straddle; offsets only grow)
+      if (live && off + size > (uint32_t)kStageBytes && off <= (uint32_t)kStageBytes) atomicMin(&sm.split, off);
+      __syncthreads();
       {
-        uint8_t* dst = fits ? &sm.stage[off] : overflow + off;
+        const uint32_t moff = sm.boff[mine], msize = sm.csize[mine];
+        uint8_t* dst = (moff + msize <= (uint32_t)kStageBytes) ? &sm.stage[moff] : overflow + moff;
         HuffPlan plf = pl;
-        if (!live || big) plf.n = 0;
-        huff_emit(z, plf, fs, dst, WarpLockstep{});
-        if (live && big) emit_big(z, pl, bs, dst);
+        if (!mlive || big) plf.n = 0;
+        huff_emit(zm, plf, fs, dst, WarpLockstep{});
+        if (mlive && big) emit_big(zm, pl, bs, dst);
       }
-      // first chunk that did not fit the shared staging buffer (chunks never straddle; offsets only grow)
-      const uint32_t split = __reduce_min_sync(0xffffffffu, (live && !fits) ? off : total);
-      // ---- park the tile's bytes in the scratch area (bump allocation, completion order); file-order offsets
-      //      are computed afterwards by scan_tiles_kernel, so no warp ever waits for another one ----
-      u64 pos = 0;
-      if (lane == 0) {
-        pos = atomicAdd(reinterpret_cast<u64*>(P.ws.counters + 2), (u64)total);
-        P.ws.tile_pos[tile] = pos;
-        P.ws.tile_total[tile] = total;
-      }
-      pos = __shfl_sync(0xffffffffu, pos, 0);
-      __syncwarp();  // staged bytes of all lanes are visible
-      if (pos + total > P.ws.scratch_cap) {
-        if (lane == 0) atomicOr(&P.ws.counters[1], kFlagCapacity);
-      } else {
-        copy_smem_to_global(P.ws.scratch + pos, sm.stage, split, lane, 32);
-        for (uint32_t i = split + lane; i < total; i += 32) P.ws.scratch[pos + i] = overflow[i];
-      }
-      __syncwarp();  // the staging buffer and the coefficient columns are reused by the next tile
+      carried += pass_total;
     }
+    __syncthreads();
+
+    // ---- park the tile's bytes in the scratch area (bump allocation, completion order); file-order offsets
+    //      are computed afterwards by scan_tiles_kernel, so no CTA ever waits for another one ----
+    if (tid == 0) {
+      const u64 pos = atomicAdd(reinterpret_cast<u64*>(P.ws.counters + 2), (u64)carried);
+      P.ws.tile_pos[tile] = pos;
+      P.ws.tile_total[tile] = carried;
+      sm.base = pos;
+    }
+    __syncthreads();
+    {
+      const u64 pos = sm.base;
+      if (pos + carried > P.ws.scratch_cap) {
+        if (tid == 0) atomicOr(&P.ws.counters[1], kFlagCapacity);
+      } else {
+        const uint32_t split = sm.split < carried ? sm.split : carried;
+        copy_smem_to_global(P.ws.scratch + pos, sm.stage, split);
+        for (uint32_t i = split + tid; i < carried; i += kCtaThreads) P.ws.scratch[pos + i] = overflow[i];
+      }
+    }
+    __syncthreads();  // shared memory is reused by the next tile
   }
 }
 
-// Pass 2: exclusive scan of the tile totals in file order (one CTA, 16 tiles per thread per round; a 4K batch of
-// 64 frames has ~4*10^5 warp tiles), plus the number of code bytes before every plane.
-constexpr int kScanPerThread = 16;
+// Pass 2: exclusive scan of the tile totals in file order (one CTA, 8 tiles per thread per round; a 4K batch of
+// 64 frames has ~10^5 tiles), plus the number of code bytes before every plane.
+constexpr int kScanPerThread = 8;
 __global__ void __launch_bounds__(1024) scan_tiles_kernel(const __grid_constant__ EncParams P) {
   __shared__ u64 warp_sums[32];
   __shared__ u64 carry_s;
@@ -524,13 +573,11 @@ __global__ void __launch_bounds__(1024) scan_tiles_kernel(const __grid_constant_
   }
 }
 
-// Pass 3: move every tile's chunk bytes from the scratch area to their place in the payload (one warp per tile).
+// Pass 3: move every tile's chunk bytes from the scratch area to their place in the payload.
 // Absolute position = fixed part (headers + size arrays up to this plane) + code bytes before the tile.
 __global__ void __launch_bounds__(256) place_tiles_kernel(const __grid_constant__ EncParams P) {
   const FrameGeom& g = P.g;
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t warps = gridDim.x * (blockDim.x >> 5);
-  for (uint32_t tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); tile < P.total_tiles; tile += warps) {
+  for (uint32_t tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
     const TileCoord tc = tile_coord(g, tile);
     const int plane = (int)tc.plane;
     const uint32_t total = P.ws.tile_total[tile];
@@ -538,10 +585,10 @@ __global__ void __launch_bounds__(256) place_tiles_kernel(const __grid_constant_
     const uint32_t fixed = 12 + 8 * (plane + 1) + g.nblk[0] + (plane > 0 ? g.nblk[1] : 0) + (plane > 1 ? g.nblk[2] : 0);
     const u64 pos = (u64)tc.frame * (36 + g.nblk_frame) + fixed + P.ws.tile_prefix[tile];
     if (pos + total > P.out_cap || src + total > P.ws.scratch_cap) {
-      if (lane == 0) atomicOr(&P.ws.counters[1], kFlagCapacity);
+      if (threadIdx.x == 0) atomicOr(&P.ws.counters[1], kFlagCapacity);
       continue;
     }
-    copy_global_to_global(P.out + pos, P.ws.scratch + src, total, lane, 32);
+    copy_global_to_global(P.out + pos, P.ws.scratch + src, total, 256);
   }
 }
 
@@ -592,7 +639,7 @@ __global__ void __launch_bounds__(256) finalize_frames_kernel(const __grid_const
   }
   const uint32_t i0 = slice * kSizeSlice;
   const uint32_t cnt = n - i0 < kSizeSlice ? n - i0 : kSizeSlice;
-  copy_global_to_global(out + ppos + 8 + i0, P.ws.chunk_sizes + sidx + i0, cnt, threadIdx.x, 256);
+  copy_global_to_global(out + ppos + 8 + i0, P.ws.chunk_sizes + sidx + i0, cnt, 256);
 }
 
 int codec_grid_size(int device, bool encoder) {
@@ -605,15 +652,19 @@ int codec_grid_size(int device, bool encoder) {
 // ===================================================================================================
 // Decompression (one thread = one block; tile = 128 blocks; five CTAs per SM)
 // ===================================================================================================
-constexpr int kDecStageBytes = 1024;
-struct DecWarpSmem {
-  float coef[64][kTileBlocks];                  // dequantised coefficients B[k][c] (row-major index), per block column
-  alignas(16) uint8_t stage[kDecStageBytes + 8];  // the tile's chunk bytes
-};
+constexpr int kDecStageBytes = 4 * 1024;
 struct DecSmem {
-  DecWarpSmem w[kWarps];
-  float q[3][64];     // dequantisation factors of the three planes
+  float coef[64][kTileBlocks];        // dequantised coefficients B[k][c] (row-major index), per block column
+  alignas(16) uint8_t stage[kDecStageBytes];  // the tile's chunk bytes
   uint8_t zigzag[64];
+  float q[64];
+  uint32_t hist[64];                  // counting sort of the tile's blocks by chunk size
+  uint16_t boff[kTileBlocks];         // chunk offset of block b inside the tile
+  uint8_t bsize[kTileBlocks];
+  uint8_t perm[kTileBlocks];          // perm[t] = block decoded by thread t
+  uint32_t warp_sums[4];
+  uint32_t tile;
+  u64 base;
 };
 static_assert(sizeof(DecSmem) <= 44 * 1024 + 256, "DecSmem must allow 5 CTAs per SM");
 
@@ -733,31 +784,26 @@ MYB_D void idct_block_4x4(const float* col, float onef, uint32_t (&out)[16]) {
   }
 }
 
-// Decompress pre-pass 1: chunk bytes of every tile.  A warp handles 4 consecutive tiles: 8 lanes per tile, 4 size
-// bytes per lane.
+// Decompress pre-pass 1: chunk bytes of every tile (one warp per tile, 4 size bytes per lane).
 __global__ void __launch_bounds__(256) dec_tile_totals_kernel(const __grid_constant__ DecParams P) {
   const FrameGeom& g = P.g;
   const int lane = threadIdx.x & 31;
   const uint32_t warps = gridDim.x * (blockDim.x >> 5);
-  const uint32_t groups = (P.total_tiles + 3) / 4;
-  for (uint32_t grp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); grp < groups; grp += warps) {
-    const uint32_t tile = grp * 4 + (lane >> 3);
+  for (uint32_t tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); tile < P.total_tiles; tile += warps) {
+    const TileCoord tc = tile_coord(g, tile);
+    const PlaneDesc d = reinterpret_cast<const PlaneDesc*>(P.ws.plane_desc)[(uint64_t)tc.frame * 3 + tc.plane];
     uint32_t sum = 0;
-    if (tile < P.total_tiles) {
-      const TileCoord tc = tile_coord(g, tile);
-      const PlaneDesc d = reinterpret_cast<const PlaneDesc*>(P.ws.plane_desc)[(uint64_t)tc.frame * 3 + tc.plane];
-      if (d.ok) {
-        const uint8_t* sizes = P.payloads + d.sizes_off + tc.k0;
+    if (d.ok) {
+      const uint8_t* sizes = P.payloads + d.sizes_off + tc.k0;
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const uint32_t b = 4 * (lane & 7) + j;
-          if (b < tc.nblk) sum += sizes[b];
-        }
+      for (int j = 0; j < 4; j++) {
+        const uint32_t b = 4 * lane + j;
+        if (b < tc.nblk) sum += sizes[b];
       }
     }
 #pragma unroll
-    for (int o = 4; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    if ((lane & 7) == 0 && tile < P.total_tiles) P.ws.tile_total[tile] = sum;
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) P.ws.tile_total[tile] = sum;
   }
 }
 
@@ -805,62 +851,95 @@ __global__ void __launch_bounds__(1024) dec_scan_planes_kernel(const __grid_cons
 __global__ void __launch_bounds__(kCtaThreads, 5)
     dct_decompress_kernel(const __grid_constant__ DecParams P, const __grid_constant__ QTables qt) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  DecSmem& cta = *reinterpret_cast<DecSmem*>(smem_raw);
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  DecWarpSmem& sm = cta.w[wid];
+  DecSmem& sm = *reinterpret_cast<DecSmem*>(smem_raw);
+  const int tid = threadIdx.x;
   const FrameGeom& g = P.g;
-  if (threadIdx.x < 64) {
+  if (tid < 64) {
     constexpr uint8_t zz[64] = {MYB_ZIGZAG_LIST};
-    cta.zigzag[threadIdx.x] = zz[threadIdx.x];
+    sm.zigzag[tid] = zz[tid];
   }
-  for (int i = threadIdx.x; i < 192; i += kCtaThreads) cta.q[i / 64][i % 64] = qt.q[i / 64][i % 64];
-  __syncthreads();  // the only CTA barrier: from here on the four warps run independently
-  float* const col = &sm.coef[0][lane];
+  int q_plane = -1;
+  float* const col = &sm.coef[0][tid];
 
   while (true) {
-    uint32_t t0 = 0;
-    if (lane == 0) t0 = atomicAdd(&P.ws.counters[0], (uint32_t)kTicketBatch);
-    t0 = __shfl_sync(0xffffffffu, t0, 0);
-    if (t0 >= P.total_tiles) break;
-    const uint32_t t1 = t0 + kTicketBatch < P.total_tiles ? t0 + kTicketBatch : P.total_tiles;
-#pragma unroll 1
-    for (uint32_t tile = t0; tile < t1; tile++) {
-      const TileCoord tc = tile_coord(g, tile);
-      const int plane = (int)tc.plane;
-      const PlaneDesc d = reinterpret_cast<const PlaneDesc*>(P.ws.plane_desc)[(uint64_t)tc.frame * 3 + plane];
-      if (!d.ok) continue;  // header error already flagged by parse_payload_kernel (uniform per warp)
-      const bool live = (uint32_t)lane < tc.nblk;
-      // chunk sizes of the tile -> per-block offsets (warp scan); the tile's offset inside content[] comes from the
-      // pre-passes (dec_tile_totals_kernel, dec_scan_planes_kernel), so no warp waits for another one
-      const uint32_t size = live ? (uint32_t)P.payloads[d.sizes_off + tc.k0 + lane] : 0u;
-      const u64 base = P.ws.tile_prefix[tile];
-      uint32_t total;
-      const uint32_t off = warp_exclusive_scan(size, lane, &total);
-      if (base + total > d.content_size) {  // chunks must lie inside content[] (undefined behaviour in the reference)
-        if (lane == 0) atomicOr(&P.ws.counters[1], kFlagHuffman);
-        continue;
-      }
-      // stage the tile's chunk bytes in shared memory (aligned 32-bit loads) and zero the coefficient column
-      const uint8_t* content = P.payloads + d.content_off + base;
-      copy_global_to_smem(sm.stage, content, total < (uint32_t)kDecStageBytes ? total : (uint32_t)kDecStageBytes, lane, 32);
+    __syncthreads();  // previous tile done with shared memory (and zigzag table visible)
+    if (tid == 0) sm.tile = atomicAdd(&P.ws.counters[0], 1u);
+    __syncthreads();
+    const uint32_t tile = sm.tile;
+    if (tile >= P.total_tiles) break;
+    const TileCoord tc = tile_coord(g, tile);
+    const int plane = (int)tc.plane;
+    const PlaneDesc d = reinterpret_cast<const PlaneDesc*>(P.ws.plane_desc)[(uint64_t)tc.frame * 3 + plane];
+    if (!d.ok) continue;  // header error already flagged by parse_payload_kernel (uniform per CTA)
+    if (q_plane != plane) {
+      if (tid < 64) sm.q[tid] = qt.q[plane][tid];
+      q_plane = plane;
+    }
+    const bool live = (uint32_t)tid < tc.nblk;
+    // chunk sizes of the tile -> per-block offsets (CTA scan); the tile's offset inside content[] was computed by
+    // the pre-passes (dec_tile_totals_kernel, dec_scan_planes_kernel), so no CTA waits for another one
+    const uint32_t size = live ? (uint32_t)P.payloads[d.sizes_off + tc.k0 + tid] : 0u;
+    const u64 base = P.ws.tile_prefix[tile];
+    uint32_t total;
+    const uint32_t off = cta_exclusive_scan(size, sm.warp_sums, &total);
+    if (base + total > d.content_size) {  // chunks must lie inside content[] (undefined behaviour in the reference)
+      if (tid == 0) atomicOr(&P.ws.counters[1], kFlagHuffman);
+      continue;
+    }
+    // stage the tile's chunk bytes in shared memory (coalesced byte loads; the global offset is arbitrary) and
+    // zero this thread's coefficient column while they are in flight
+    const uint8_t* content = P.payloads + d.content_off + base;
+    {
+      const uint32_t n = total < (uint32_t)kDecStageBytes ? total : (uint32_t)kDecStageBytes;
+      for (uint32_t i = tid; i < n; i += kCtaThreads) sm.stage[i] = __ldg(content + i);
+    }
 #pragma unroll
-      for (int i = 0; i < 64; i++) col[i * kTileBlocks] = 0.0f;
-      __syncwarp();
-      // ---- phase 1: canonical Huffman decode + dequantise into the lane's shared-memory column (warp lockstep) ----
-      int nsym = 0;  // decoded zigzag positions: the non-zero coefficients lie in positions [0, nsym)
-      {
-        const uint8_t* chunk = (off + size <= (uint32_t)kDecStageBytes) ? &sm.stage[off] : content + off;
-        const float* qp = cta.q[plane];
-        const int err = huff_decode_block(chunk, (int)size, [&](int j, int v) {
-          const int pos = cta.zigzag[j];
-          col[pos * kTileBlocks] = __fmul_rn((float)v, qp[pos]);  // DCT.cpp:330-332
-          nsym = j + 1;
-        }, WarpLockstep{});
-        if (live && (err || size == 0)) atomicOr(&P.ws.counters[1], kFlagHuffman);  // a chunk is at least 7 bytes
+    for (int i = 0; i < 64; i++) col[i * kTileBlocks] = 0.0f;
+    // Counting sort of the blocks by chunk size (4-byte bins) while the staging loads are in flight: thread t
+    // decodes the block of rank t, so the lanes of a warp get messages of similar length and the lockstep decode
+    // loop (trip count = warp maximum) wastes few lanes.
+    sm.boff[tid] = (uint16_t)off;
+    sm.bsize[tid] = (uint8_t)size;
+    if (tid < 64) sm.hist[tid] = 0;
+    __syncthreads();
+    const uint32_t key = (size >> 2) < 63u ? (size >> 2) : 63u;
+    const uint32_t within = atomicAdd(&sm.hist[key], 1u);
+    __syncthreads();
+    if (tid < 32) {  // exclusive prefix of the 64 bins, two per lane
+      const int lane = tid;
+      const uint32_t h0 = sm.hist[2 * lane], h1 = sm.hist[2 * lane + 1];
+      uint32_t inc = h0 + h1;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t nn = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += nn;
       }
-      __syncwarp();
-      // ---- phase 2: inverse DCT, round, clamp, store ----
+      sm.hist[2 * lane] = inc - h0 - h1;
+      sm.hist[2 * lane + 1] = inc - h1;
+    }
+    __syncthreads();
+    sm.perm[sm.hist[key] + within] = (uint8_t)tid;
+    __syncthreads();
+
+    // ---- phase 1: canonical Huffman decode + dequantise into the thread's shared-memory column (warp lockstep) ----
+    const uint32_t blk = sm.perm[tid];
+    const bool mine = blk < tc.nblk;
+    int nsym = 0;  // decoded zigzag positions: the non-zero coefficients lie in positions [0, nsym)
+    {
+      const uint32_t moff = sm.boff[blk], msize = sm.bsize[blk];
+      const uint8_t* chunk = (moff + msize <= (uint32_t)kDecStageBytes) ? &sm.stage[moff] : content + moff;
+      const int err = huff_decode_block(chunk, (int)msize, [&](int j, int v) {
+        const int pos = sm.zigzag[j];
+        col[pos * kTileBlocks] = __fmul_rn((float)v, sm.q[pos]);  // DCT.cpp:330-332
+        nsym = j + 1;
+      }, WarpLockstep{});
+      if (mine && (err || msize == 0)) atomicOr(&P.ws.counters[1], kFlagHuffman);  // a chunk is at least 7 bytes
+    }
+    __syncwarp();
+    // ---- phase 2: inverse DCT, round, clamp, store ----
+    {
       uint32_t outw[16];
+      // zigzag positions 0..9 are the anti-diagonals row + col <= 3, all inside the top-left 4x4 corner
       if (__all_sync(0xffffffffu, nsym <= 1)) {
         // DC only: D[a][0] = C[0][a] * B00 and P[a][b] = D[a][0] * C[0][b] with all C[0][.] equal -> a flat block
         const float c0 = dct_c(0);
@@ -870,20 +949,18 @@ __global__ void __launch_bounds__(kCtaThreads, 5)
 #pragma unroll
         for (int r = 0; r < 16; r++) outw[r] = px;
       } else if (__all_sync(0xffffffffu, nsym <= 10)) {
-        // zigzag positions 0..9 are the anti-diagonals row + col <= 3, all inside the top-left 4x4 corner
         idct_block_4x4(col, P.one, outw);
       } else {
         idct_block(col, P.one, outw);
       }
-      if (live) {
+      if (mine) {
         const uint32_t pw = g.pw[plane], bw = g.bw[plane];
-        const uint32_t k = tc.k0 + lane;
+        const uint32_t k = tc.k0 + blk;
         const uint32_t by = k / bw, bx = k - by * bw;
         uint8_t* p = P.dst + (uint64_t)tc.frame * g.frame_bytes + g.plane_off[plane] + (uint64_t)by * 8 * pw + (uint64_t)bx * 8;
 #pragma unroll
         for (int r = 0; r < 8; r++) *reinterpret_cast<uint2*>(p + (uint64_t)r * pw) = make_uint2(outw[2 * r], outw[2 * r + 1]);
       }
-      __syncwarp();  // column and staging buffer are reused by the next tile
     }
   }
 }
@@ -899,20 +976,17 @@ void launch_compress(const uint8_t* d_iyuv, const FrameGeom& g, const QTables& q
   P.one = 1.0f;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(dct_compress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(EncWarpSmem) * kWarps));
+    cudaFuncSetAttribute(dct_compress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncSmem));
     attr_set = true;
   }
   cudaMemsetAsync(ws.counters, 0, 4, s);      // ticket only; error flags accumulate until read
   cudaMemsetAsync(ws.counters + 2, 0, 8, s);  // scratch bump allocator
-  const uint32_t cta_items = (P.total_tiles + kWarps * kTicketBatch - 1) / (kWarps * kTicketBatch);
-  const int grid = (int)(cta_items < (uint32_t)ws.grid ? cta_items : (uint32_t)ws.grid);
+  const int grid = (int)(P.total_tiles < (uint32_t)ws.grid ? P.total_tiles : (uint32_t)ws.grid);
   if (ws.k_begin) cudaEventRecord(ws.k_begin, s);
-  dct_compress_kernel<<<grid, kCtaThreads, sizeof(EncWarpSmem) * kWarps, s>>>(P, qt);
+  dct_compress_kernel<<<grid, kCtaThreads, sizeof(EncSmem), s>>>(P, qt);
   scan_tiles_kernel<<<1, 1024, 0, s>>>(P);
-  {
-    const uint32_t want = (P.total_tiles + 7) / 8;
-    place_tiles_kernel<<<want < 148u * 16 ? want : 148u * 16, 256, 0, s>>>(P);
-  }
+  const int pgrid = (int)(P.total_tiles < 148u * 16 ? P.total_tiles : 148u * 16);
+  place_tiles_kernel<<<pgrid, 256, 0, s>>>(P);
   {
     uint32_t slices = 0;
     for (int p = 0; p < 3; p++) slices += (g.nblk[p] + kSizeSlice - 1) / kSizeSlice;
@@ -937,12 +1011,11 @@ void launch_decompress(const uint8_t* d_payloads, const uint64_t* d_offsets, con
   if (ws.k_begin) cudaEventRecord(ws.k_begin, s);
   parse_payload_kernel<<<(g.n_frames + 127) / 128, 128, 0, s>>>(P);
   {
-    const uint32_t want = (P.total_tiles + 31) / 32;
+    const uint32_t want = (P.total_tiles + 7) / 8;
     dec_tile_totals_kernel<<<want < 148u * 8 ? want : 148u * 8, 256, 0, s>>>(P);
   }
   dec_scan_planes_kernel<<<g.n_frames * 3, 1024, 0, s>>>(P);
-  const uint32_t cta_items = (P.total_tiles + kWarps * kTicketBatch - 1) / (kWarps * kTicketBatch);
-  const int grid = (int)(cta_items < (uint32_t)ws.grid ? cta_items : (uint32_t)ws.grid);
+  const int grid = (int)(P.total_tiles < (uint32_t)ws.grid ? P.total_tiles : (uint32_t)ws.grid);
   dct_decompress_kernel<<<grid, kCtaThreads, sizeof(DecSmem), s>>>(P, qt);
   if (ws.k_end) cudaEventRecord(ws.k_end, s);  // the whole decompress sequence (4 kernels) is what gets timed
   g_launches += 4;

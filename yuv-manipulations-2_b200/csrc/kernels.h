@@ -5,11 +5,11 @@
 
 namespace myyuvb {
 
-constexpr int kTileBlocks = 32;    // 8x8 blocks per tile: one warp, one block per lane; warps run independently
-constexpr int kEncTile = kTileBlocks;
+constexpr int kTileBlocks = 128;   // 8x8 blocks per pass of a CTA (one per thread)
+constexpr int kEncPasses = 1;      // compress: passes of 128 blocks per tile
+constexpr int kEncTile = kTileBlocks * kEncPasses;
 constexpr int kDecTile = kTileBlocks;
-constexpr int kCtaThreads = 128;   // threads per CTA of the codec kernels (4 autonomous warps)
-constexpr int kTicketBatch = 4;    // consecutive tiles a warp takes per atomic ticket
+constexpr int kCtaThreads = 128;   // threads per CTA of the codec kernels
 
 // error bits raised by kernels (OR-ed into Workspace::flags)
 enum : uint32_t {
@@ -51,7 +51,7 @@ struct Workspace {
   uint64_t* plane_start;   // [n_frames*3 + 1] code bytes before each plane (compress)
   uint32_t* counters;      // [0] tile ticket, [1] error flags, [2..3] u64 scratch bump allocator
   uint8_t* chunk_sizes;    // [n_frames * nblk_frame] per-block chunk size, linear block order (compress)
-  uint8_t* overflow;       // [grid * 4 warps * kEncTile * 256] staging overflow area (compress; a chunk is at most 255 bytes)
+  uint8_t* overflow;       // [grid * kEncTile * 256] staging overflow area (compress; a chunk is at most 255 bytes)
   uint8_t* scratch;        // [scratch_cap] chunk bytes of all tiles in completion order (compress, pass 1)
   uint64_t scratch_cap;
   uint64_t* tile_pos;      // [total tiles] position of each tile's bytes in scratch
