@@ -20,8 +20,10 @@
 
 #if defined(__CUDACC__)
 #define MYB_HD __host__ __device__ __forceinline__
+#define MYB_NOUNROLL _Pragma("unroll 1")  // keep the (large, divergent) coder loops rolled: code size is I-cache bound
 #else
 #define MYB_HD inline
+#define MYB_NOUNROLL
 #endif
 
 namespace myyuvb {
@@ -127,8 +129,10 @@ MYB_HD int hash_bucket(int v, int nb) {
 template <int CAP, int STRIDE>
 MYB_HD void list_place(const HuffScratch<CAP, STRIDE>& S, int& ln, int slot, int bucket) {
   int p = 0;
+  MYB_NOUNROLL
   for (int i = 0; i < ln; i++)
     if (S.at(S.kBkt, i) == bucket) { p = i; break; }
+  MYB_NOUNROLL
   for (int i = ln; i > p; i--) {
     S.at(S.kOrd, i) = S.at(S.kOrd, i - 1);
     S.at(S.kBkt, i) = S.at(S.kBkt, i - 1);
@@ -144,6 +148,7 @@ MYB_HD void list_place(const HuffScratch<CAP, STRIDE>& S, int& ln, int slot, int
 template <int CAP, int STRIDE>
 MYB_HD void hash_list_order_general(const HuffScratch<CAP, STRIDE>& S, int m, int erase_slot) {
   int ln = 0, nb = 13;
+  MYB_NOUNROLL
   for (int s = 0; s < m; s++) {
     if (s == 13 || s == 29 || s == 59) {
       nb = (s == 13) ? 29 : (s == 29) ? 59 : 127;
@@ -151,6 +156,7 @@ MYB_HD void hash_list_order_general(const HuffScratch<CAP, STRIDE>& S, int m, in
       for (int i = 0; i < ln; i++) S.at(S.kFreq, i) = S.at(S.kOrd, i);
       const int old = ln;
       ln = 0;
+      MYB_NOUNROLL
       for (int i = 0; i < old; i++) {
         const int t = S.at(S.kFreq, i);
         list_place(S, ln, t, hash_bucket(S.sym(t), nb));
@@ -160,6 +166,7 @@ MYB_HD void hash_list_order_general(const HuffScratch<CAP, STRIDE>& S, int m, in
   }
   if (erase_slot >= 0) {
     int w = 0;
+    MYB_NOUNROLL
     for (int i = 0; i < ln; i++) {
       const uint8_t t = S.at(S.kOrd, i);
       if (t != erase_slot) S.at(S.kOrd, w++) = t;
@@ -171,6 +178,7 @@ MYB_HD void hash_list_order_general(const HuffScratch<CAP, STRIDE>& S, int m, in
 // heap lives in kBkt (free after the list order is final).
 template <int CAP, int STRIDE>
 MYB_HD void heap_sift_up(const HuffScratch<CAP, STRIDE>& S, int hole, int node, int wnode) {
+  MYB_NOUNROLL
   while (hole > 0) {
     const int parent = (hole - 1) >> 1;
     const int pn = S.at(S.kBkt, parent);
@@ -190,6 +198,7 @@ MYB_HD int heap_pop(const HuffScratch<CAP, STRIDE>& S, int& hsize) {
   if (len == 0) return top;
   const int value = S.at(S.kBkt, len);
   int hole = 0, child = 0;
+  MYB_NOUNROLL
   while (child < ((len - 1) >> 1)) {
     child = 2 * (child + 1);
     if (S.at(S.kFreq, S.at(S.kBkt, child)) > S.at(S.kFreq, S.at(S.kBkt, child - 1))) child--;
@@ -229,6 +238,7 @@ MYB_HD HuffPlan huff_plan(Z& z, int L, const HuffScratch<CAP, STRIDE>& S, const 
   bool bail = false;
   uint64_t small = ~0ull;  // nibble v+8: slot of value v, 0xF = not seen (or slot >= 15)
   const int Lw = warp.max(L);
+  MYB_NOUNROLL
   for (int i = 0; i < Lw; i++) {
     if (i < L && !bail) {
       const int v = z.get(i);
@@ -297,6 +307,7 @@ MYB_HD HuffPlan huff_plan(Z& z, int L, const HuffScratch<CAP, STRIDE>& S, const 
     const bool fast = m <= 13;
     const int mw = warp.max(fast ? m : 0);
     uint64_t ord = 0, bkt = ~0ull;  // empty fields hold 0xF, which is no bucket
+    MYB_NOUNROLL
     for (int s = 0; s < mw; s++) {
       if (s < m && fast) {
         const uint64_t b = (uint64_t)hash_bucket13(S.sym(s));
@@ -309,6 +320,7 @@ MYB_HD HuffPlan huff_plan(Z& z, int L, const HuffScratch<CAP, STRIDE>& S, const 
       }
     }
     if (fast) {
+      MYB_NOUNROLL
       for (int i = 0; i < mw; i++)
         if (i < m) S.at(S.kOrd, i) = (uint8_t)((ord >> (4 * i)) & 15u);
     } else {
@@ -320,6 +332,7 @@ MYB_HD HuffPlan huff_plan(Z& z, int L, const HuffScratch<CAP, STRIDE>& S, const 
   const int nt = tree ? n : 0;
   const int nw = warp.max(nt);
   int hsize = 0;
+  MYB_NOUNROLL
   for (int j = 0; j < nw; j++) {
     if (j < nt) {
       const int w = S.at(S.kCnt, S.at(S.kOrd, j));
@@ -330,6 +343,7 @@ MYB_HD HuffPlan huff_plan(Z& z, int L, const HuffScratch<CAP, STRIDE>& S, const 
     warp.sync();
   }
   int nnode = nt;
+  MYB_NOUNROLL
   for (int t = 0; t + 1 < nw; t++) {  // Huffman.cpp:210-217: n - 1 merges
     if (t + 1 < nt) {
       const int l = heap_pop(S, hsize);
@@ -346,17 +360,21 @@ MYB_HD HuffPlan huff_plan(Z& z, int L, const HuffScratch<CAP, STRIDE>& S, const 
   }
   // ---- code length = leaf depth (Huffman.cpp:71-83); parents always have larger ids than children
   if (tree) S.at(S.kPar, nnode - 1) = 0;
+  MYB_NOUNROLL
   for (int k = 2; k <= 2 * nw - 1; k++) {
     const int i = nnode - k;
     if (tree && i >= 0) S.at(S.kPar, i) = (uint8_t)(S.at(S.kPar, S.at(S.kPar, i)) + 1);
   }
+  MYB_NOUNROLL
   for (int j = 0; j < nw; j++)
     if (j < nt) S.at(S.kLen, S.at(S.kOrd, j)) = S.at(S.kPar, j);
   // ---- tree_data: lengths ascending, symbols ascending inside a length (Huffman.cpp:76-78): insertion sort
+  MYB_NOUNROLL
   for (int i = 0; i < nw; i++) {
     if (i < nt) {
       const int key = ((int)S.at(S.kLen, i) << 12) + (S.sym(i) + 2048);
       int j = i - 1;
+      MYB_NOUNROLL
       while (j >= 0) {
         const int t = S.at(S.kSorted, j);
         if ((((int)S.at(S.kLen, t) << 12) + (S.sym(t) + 2048)) <= key) break;
@@ -372,6 +390,7 @@ MYB_HD HuffPlan huff_plan(Z& z, int L, const HuffScratch<CAP, STRIDE>& S, const 
   const int ncw = warp.max(nc);
   int code = 0, prev = 0, bits = 0;
   uint64_t per_len = 0;
+  MYB_NOUNROLL
   for (int i = 0; i < ncw; i++) {
     if (i < nc) {
       const int s = S.at(S.kSorted, i);
@@ -424,6 +443,7 @@ MYB_HD void huff_emit(Z& z, const HuffPlan& pl, const HuffScratch<CAP, STRIDE>& 
   // a length and after every 32 symbols of the same length; every group is padded to whole bytes
   const int nw = warp.max(n);
   int run_len = 0, in_run = 0;
+  MYB_NOUNROLL
   for (int i = 0; i < nw; i++) {
     if (i < n) {
       const int s = S.at(S.kSorted, i);
@@ -441,6 +461,7 @@ MYB_HD void huff_emit(Z& z, const HuffPlan& pl, const HuffScratch<CAP, STRIDE>& 
   w.flush();
   const int L = n > 0 ? pl.msg_len : 0;
   const int Lw = warp.max(L);
+  MYB_NOUNROLL
   for (int k = 0; k < Lw; k++) {  // code stream, Huffman.cpp:227-236, :319-325
     if (k < L) {
       const int s = z.get(k);
@@ -459,6 +480,7 @@ MYB_HD void huff_emit(Z& z, const HuffPlan& pl, const HuffScratch<CAP, STRIDE>& 
 // ---------------------------------------------------------------------------------------------------
 MYB_HD int table_symbol(const uint8_t* groups, int table_bytes, int len, int idx, int* out) {
   int i = 0;
+  MYB_NOUNROLL
   while (i < table_bytes) {  // groups of the same length are concatenated in file order (Huffman.cpp:258-266)
     const int info = groups[i];
     const int glen = (info >> 5) + 1, c = (info & 31) + 1;
@@ -499,6 +521,7 @@ MYB_HD int huff_decode_block(const uint8_t* chunk, int size, Emit&& emit, const 
   {
     int i = 0, last_len = 0;
     const int tw = warp.max(table_bytes);
+    MYB_NOUNROLL
     for (int guard = 0; guard < tw; guard++) {  // at most one group per iteration, each group is >= 3 bytes
       if (i < table_bytes && !err) {
         const int info = groups[i];
@@ -520,12 +543,14 @@ MYB_HD int huff_decode_block(const uint8_t* chunk, int size, Emit&& emit, const 
   uint32_t acc = 0;
   int have = 0, nbyte = 0, p = 0, j = 0;
   const int data_bytes = (bits + 7) >> 3;
+  MYB_NOUNROLL
   while (warp.any(p < bits && j < 64)) {
     if (p < bits && j < 64) {
       if (have <= 8 && nbyte < data_bytes) { acc |= (uint32_t)data[nbyte++] << have; have += 8; }
       if (have <= 8 && nbyte < data_bytes) { acc |= (uint32_t)data[nbyte++] << have; have += 8; }
       uint32_t code = 0, first = 0;  // uint8_t in the reference (Huffman.cpp:107-108): keep the 8-bit wrap
       int len = 1, found = 0;
+      MYB_NOUNROLL
       for (; len <= 8; len++) {
         const uint32_t c = (uint32_t)(counts >> (8 * (len - 1))) & 0xff;
         if (p + len - 1 >= bits) break;  // "Huffman bad code" :120-122

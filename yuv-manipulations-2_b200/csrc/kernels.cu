@@ -262,11 +262,6 @@ struct EncSmem {
   uint8_t hs_bytes[FastScratch::kBytes][kCtaThreads];
   int16_t hs_syms[FastScratch::kSyms][kCtaThreads];
   alignas(16) uint8_t stage[kStageBytes + 8];
-  uint32_t hist[68];                                   // counting sort of the tile's blocks by message length
-  uint16_t boff[kTileBlocks];                          // chunk offset of block b inside the tile
-  uint8_t msg_len[kTileBlocks];                        // exact message length of block b
-  uint8_t csize[kTileBlocks];                          // chunk size of block b
-  uint8_t perm[kTileBlocks];                           // perm[t] = block entropy-coded by thread t
   uint32_t warp_sums[4];
   uint32_t tile;
   uint32_t split;
@@ -424,68 +419,37 @@ __global__ void __launch_bounds__(kCtaThreads, 5)
         }
         L = fdct_quant_block(raw, qt, plane, P.one, z.col);
       }
-      // ---- exact message length (Huffman.cpp:184-190; at most 8 steps back from the bound), then a counting sort of
-      //      the tile's blocks by it: thread t entropy-codes the block of rank t, so the lanes of a warp get messages
-      //      of similar length and the lockstep loops (trip count = warp maximum) waste few lanes ----
+      // ---- phase B: entropy-code the block (same thread, so no CTA barrier in between); warp lockstep ----
+      // (Sorting the tile's blocks by message length so that warps get homogeneous work was tried: it cut issued
+      //  instructions by 11% but not the time, because a CTA waits for its slowest warp -- profiles/r01_notes.md.)
       if (!live) L = 0;
-      while (L > 0 && z.get(L - 1) == 0) L--;
-      const int lane = tid & 31, wid = tid >> 5;
-      sm.msg_len[tid] = (uint8_t)L;
-      if (tid < 68) sm.hist[tid] = 0;
-      __syncthreads();
-      const uint32_t within = atomicAdd(&sm.hist[L], 1u);
-      __syncthreads();
-      if (wid == 0) {  // exclusive prefix of the 65 (padded to 96) bins, three per lane
-        const uint32_t h0 = lane < 22 ? sm.hist[3 * lane] : 0, h1 = lane < 22 ? sm.hist[3 * lane + 1] : 0,
-                       h2 = lane < 22 ? sm.hist[3 * lane + 2] : 0;
-        uint32_t inc = h0 + h1 + h2;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const uint32_t nn = __shfl_up_sync(0xffffffffu, inc, o);
-          if (lane >= o) inc += nn;
-        }
-        if (lane < 22) {
-          sm.hist[3 * lane] = inc - h0 - h1 - h2;
-          sm.hist[3 * lane + 1] = inc - h1 - h2;
-          sm.hist[3 * lane + 2] = inc - h2;
-        }
-      }
-      __syncthreads();
-      sm.perm[sm.hist[L] + within] = (uint8_t)tid;
-      __syncthreads();
-      // ---- phase B: entropy-code block `mine` of this pass; warp lockstep ----
-      const uint32_t mine = sm.perm[tid];
-      const bool mlive = pass * kTileBlocks + mine < tc.nblk;
-      ZShared zm{&sm.zz[0][mine]};
-      const int Lm = sm.msg_len[mine];
-      HuffPlan pl = huff_plan(zm, Lm, fs, WarpLockstep{});
+      while (L > 0 && z.get(L - 1) == 0) L--;  // exact message length (Huffman.cpp:184-190); at most 8 steps
+      __syncwarp();
+      HuffPlan pl = huff_plan(z, L, fs, WarpLockstep{});
       bool big = false;
       uint8_t lbytes[BigScratch::kBytes];
       int16_t lsyms[BigScratch::kSyms];
       BigScratch bs{lbytes, lsyms};
-      if (mlive && pl.n < 0) {  // more distinct symbols than the shared-memory scratch holds
+      if (live && pl.n < 0) {  // more distinct symbols than the shared-memory scratch holds
         big = true;
-        pl = plan_big(zm, Lm, bs);
+        pl = plan_big(z, L, bs);
       }
-      sm.csize[mine] = mlive ? (uint8_t)pl.size() : (uint8_t)0;
-      __syncthreads();
+      __syncwarp();
+      const uint32_t size = live ? (uint32_t)pl.size() : 0u;
       // chunk sizes go to a linear side array; finalize_frames_kernel moves them behind the plane headers,
       // whose position depends on the (data dependent) size of the previous planes
-      const uint32_t size = sm.csize[tid];  // block `tid` again: offsets follow raster order
       if (live) P.ws.chunk_sizes[gblk0 + blk] = (uint8_t)size;
       uint32_t pass_total;
       const uint32_t off = carried + cta_exclusive_scan(size, sm.warp_sums, &pass_total);
-      sm.boff[tid] = (uint16_t)off;
-      // first chunk that does not fit the shared staging buffer (chunks never straddle; offsets only grow)
-      if (live && off + size > (uint32_t)kStageBytes && off <= (uint32_t)kStageBytes) atomicMin(&sm.split, off);
-      __syncthreads();
       {
-        const uint32_t moff = sm.boff[mine], msize = sm.csize[mine];
-        uint8_t* dst = (moff + msize <= (uint32_t)kStageBytes) ? &sm.stage[moff] : overflow + moff;
+        const bool fits = off + size <= (uint32_t)kStageBytes;
+        uint8_t* dst = fits ? &sm.stage[off] : overflow + off;
+        // first chunk that does not fit the shared staging buffer (chunks never straddle; offsets only grow)
+        if (live && !fits && off <= (uint32_t)kStageBytes) atomicMin(&sm.split, off);
         HuffPlan plf = pl;
-        if (!mlive || big) plf.n = 0;
-        huff_emit(zm, plf, fs, dst, WarpLockstep{});
-        if (mlive && big) emit_big(zm, pl, bs, dst);
+        if (!live || big) plf.n = 0;
+        huff_emit(z, plf, fs, dst, WarpLockstep{});
+        if (live && big) emit_big(z, pl, bs, dst);
       }
       carried += pass_total;
     }
@@ -658,10 +622,6 @@ struct DecSmem {
   alignas(16) uint8_t stage[kDecStageBytes];  // the tile's chunk bytes
   uint8_t zigzag[64];
   float q[64];
-  uint32_t hist[64];                  // counting sort of the tile's blocks by chunk size
-  uint16_t boff[kTileBlocks];         // chunk offset of block b inside the tile
-  uint8_t bsize[kTileBlocks];
-  uint8_t perm[kTileBlocks];          // perm[t] = block decoded by thread t
   uint32_t warp_sums[4];
   uint32_t tile;
   u64 base;
@@ -895,45 +855,20 @@ __global__ void __launch_bounds__(kCtaThreads, 5)
     }
 #pragma unroll
     for (int i = 0; i < 64; i++) col[i * kTileBlocks] = 0.0f;
-    // Counting sort of the blocks by chunk size (4-byte bins) while the staging loads are in flight: thread t
-    // decodes the block of rank t, so the lanes of a warp get messages of similar length and the lockstep decode
-    // loop (trip count = warp maximum) wastes few lanes.
-    sm.boff[tid] = (uint16_t)off;
-    sm.bsize[tid] = (uint8_t)size;
-    if (tid < 64) sm.hist[tid] = 0;
-    __syncthreads();
-    const uint32_t key = (size >> 2) < 63u ? (size >> 2) : 63u;
-    const uint32_t within = atomicAdd(&sm.hist[key], 1u);
-    __syncthreads();
-    if (tid < 32) {  // exclusive prefix of the 64 bins, two per lane
-      const int lane = tid;
-      const uint32_t h0 = sm.hist[2 * lane], h1 = sm.hist[2 * lane + 1];
-      uint32_t inc = h0 + h1;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t nn = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += nn;
-      }
-      sm.hist[2 * lane] = inc - h0 - h1;
-      sm.hist[2 * lane + 1] = inc - h1;
-    }
-    __syncthreads();
-    sm.perm[sm.hist[key] + within] = (uint8_t)tid;
     __syncthreads();
 
     // ---- phase 1: canonical Huffman decode + dequantise into the thread's shared-memory column (warp lockstep) ----
-    const uint32_t blk = sm.perm[tid];
-    const bool mine = blk < tc.nblk;
+    const uint32_t blk = tid;
+    const bool mine = live;
     int nsym = 0;  // decoded zigzag positions: the non-zero coefficients lie in positions [0, nsym)
     {
-      const uint32_t moff = sm.boff[blk], msize = sm.bsize[blk];
-      const uint8_t* chunk = (moff + msize <= (uint32_t)kDecStageBytes) ? &sm.stage[moff] : content + moff;
-      const int err = huff_decode_block(chunk, (int)msize, [&](int j, int v) {
+      const uint8_t* chunk = (off + size <= (uint32_t)kDecStageBytes) ? &sm.stage[off] : content + off;
+      const int err = huff_decode_block(chunk, (int)size, [&](int j, int v) {
         const int pos = sm.zigzag[j];
         col[pos * kTileBlocks] = __fmul_rn((float)v, sm.q[pos]);  // DCT.cpp:330-332
         nsym = j + 1;
       }, WarpLockstep{});
-      if (mine && (err || msize == 0)) atomicOr(&P.ws.counters[1], kFlagHuffman);  // a chunk is at least 7 bytes
+      if (mine && (err || size == 0)) atomicOr(&P.ws.counters[1], kFlagHuffman);  // a chunk is at least 7 bytes
     }
     __syncwarp();
     // ---- phase 2: inverse DCT, round, clamp, store ----
