@@ -480,7 +480,6 @@ MYB_HD void huff_emit(Z& z, const HuffPlan& pl, const HuffScratch<CAP, STRIDE>& 
 // ---------------------------------------------------------------------------------------------------
 MYB_HD int table_symbol(const uint8_t* groups, int table_bytes, int len, int idx, int* out) {
   int i = 0;
-  MYB_NOUNROLL
   while (i < table_bytes) {  // groups of the same length are concatenated in file order (Huffman.cpp:258-266)
     const int info = groups[i];
     const int glen = (info >> 5) + 1, c = (info & 31) + 1;
@@ -521,7 +520,6 @@ MYB_HD int huff_decode_block(const uint8_t* chunk, int size, Emit&& emit, const 
   {
     int i = 0, last_len = 0;
     const int tw = warp.max(table_bytes);
-    MYB_NOUNROLL
     for (int guard = 0; guard < tw; guard++) {  // at most one group per iteration, each group is >= 3 bytes
       if (i < table_bytes && !err) {
         const int info = groups[i];
@@ -543,15 +541,13 @@ MYB_HD int huff_decode_block(const uint8_t* chunk, int size, Emit&& emit, const 
   uint32_t acc = 0;
   int have = 0, nbyte = 0, p = 0, j = 0;
   const int data_bytes = (bits + 7) >> 3;
-  MYB_NOUNROLL
   while (warp.any(p < bits && j < 64)) {
     if (p < bits && j < 64) {
       if (have <= 8 && nbyte < data_bytes) { acc |= (uint32_t)data[nbyte++] << have; have += 8; }
       if (have <= 8 && nbyte < data_bytes) { acc |= (uint32_t)data[nbyte++] << have; have += 8; }
       uint32_t code = 0, first = 0;  // uint8_t in the reference (Huffman.cpp:107-108): keep the 8-bit wrap
       int len = 1, found = 0;
-      MYB_NOUNROLL
-      for (; len <= 8; len++) {
+        for (; len <= 8; len++) {
         const uint32_t c = (uint32_t)(counts >> (8 * (len - 1))) & 0xff;
         if (p + len - 1 >= bits) break;  // "Huffman bad code" :120-122
         code |= (acc >> (len - 1)) & 1u;
