@@ -163,10 +163,11 @@ int ensure_workspace(myyuvb_ctx* c, const FrameGeom& g, bool encoder, Workspace*
 }
 
 int flags_to_error(uint32_t flags) {
+  // a capacity overflow leaves an incomplete payload behind, which a following decompress then rejects: report the cause
+  if (flags & kFlagCapacity) return fail(MYYUVB_ERR_CAPACITY, "Error. output buffer is too small for the compressed data");
   if (flags & kFlagDctYuvSize) return fail(MYYUVB_ERR_DCTYUV_SIZE, "DCTYUV load bad size");
   if (flags & kFlagPlaneSize) return fail(MYYUVB_ERR_PLANE_SIZE, "DCTYUVPlane load bad size");
   if (flags & kFlagHuffman) return fail(MYYUVB_ERR_HUFFMAN, "Huffman bad code");
-  if (flags & kFlagCapacity) return fail(MYYUVB_ERR_CAPACITY, "Error. output buffer is too small for the compressed data");
   return MYYUVB_OK;
 }
 
