@@ -706,24 +706,26 @@ MYB_D void idct_block(const float* col, float onef, uint32_t (&out)[16]) {
   }
 }
 
-// The same transform when every non-zero coefficient of the block lies in the top-left 4x4 corner (true for any
-// message of at most 10 zigzag positions).  Products with a zero coefficient are +-0 and adding +-0 leaves a partial
-// sum unchanged (an all-zero sum can only differ in the sign of zero, which round() discards), so dropping the terms
-// k >= 4 and the columns c >= 4 gives bit-identical pixels with 336 instead of 960 packed instructions.
-MYB_D void idct_block_4x4(const float* col, float onef, uint32_t (&out)[16]) {
+// The same transform when every non-zero coefficient lies on the anti-diagonals row + col < K, i.e. the message has at
+// most K (K + 1) / 2 zigzag positions.  Products with a zero coefficient are +-0 and adding +-0 leaves a partial sum
+// unchanged (an all-zero sum can only differ in the sign of zero, which round() discards), so dropping the terms
+// k >= K - c of column c in the first product and the terms k >= K of the second gives bit-identical pixels:
+// K = 4 needs 288 packed instructions instead of 960, K = 6 needs 496.
+template <int K>
+MYB_D void idct_block_tri(const float* col, float onef, uint32_t (&out)[16]) {
   const f2 ONE = dup(onef);
-  f2 d[16];  // d[a2 * 4 + c] = (D[2 a2][c], D[2 a2 + 1][c]), c < 4
+  f2 d[4 * K];  // d[a2 * K + c] = (D[2 a2][c], D[2 a2 + 1][c]), c < K
 #pragma unroll
-  for (int c = 0; c < 4; c++) {
-    float bk[4];
+  for (int c = 0; c < K; c++) {
+    float bk[K];
 #pragma unroll
-    for (int k = 0; k < 4; k++) bk[k] = col[(k * 8 + c) * kTileBlocks];
+    for (int k = 0; k < K - c; k++) bk[k] = col[(k * 8 + c) * kTileBlocks];
 #pragma unroll
     for (int a2 = 0; a2 < 4; a2++) {
       f2 acc = mul2(dup(bk[0]), mkp(dct_c(2 * a2), dct_c(2 * a2 + 1)));
 #pragma unroll
-      for (int k = 1; k < 4; k++) acc = sum2(acc, mul2(dup(bk[k]), mkp(dct_c(k * 8 + 2 * a2), dct_c(k * 8 + 2 * a2 + 1))), ONE);
-      d[a2 * 4 + c] = acc;
+      for (int k = 1; k < K - c; k++) acc = sum2(acc, mul2(dup(bk[k]), mkp(dct_c(k * 8 + 2 * a2), dct_c(k * 8 + 2 * a2 + 1))), ONE);
+      d[a2 * K + c] = acc;
     }
   }
 #pragma unroll
@@ -732,9 +734,9 @@ MYB_D void idct_block_4x4(const float* col, float onef, uint32_t (&out)[16]) {
   for (int a2 = 0; a2 < 4; a2++) {
 #pragma unroll
     for (int b = 0; b < 8; b++) {
-      f2 acc = mul2(d[a2 * 4], dup(dct_c(b)));
+      f2 acc = mul2(d[a2 * K], dup(dct_c(b)));
 #pragma unroll
-      for (int k = 1; k < 4; k++) acc = sum2(acc, mul2(d[a2 * 4 + k], dup(dct_c(k * 8 + b))), ONE);
+      for (int k = 1; k < K; k++) acc = sum2(acc, mul2(d[a2 * K + k], dup(dct_c(k * 8 + b))), ONE);
       const f2 t = add2_rz(acc, half_like(acc));
       const uint32_t ia = (uint32_t)__viaddmin_s32_relu(__float2int_rz(t.x), 128, 255);
       const uint32_t ib = (uint32_t)__viaddmin_s32_relu(__float2int_rz(t.y), 128, 255);
@@ -874,8 +876,9 @@ __global__ void __launch_bounds__(kCtaThreads, 5)
     // ---- phase 2: inverse DCT, round, clamp, store ----
     {
       uint32_t outw[16];
-      // zigzag positions 0..9 are the anti-diagonals row + col <= 3, all inside the top-left 4x4 corner
-      if (__all_sync(0xffffffffu, nsym <= 1)) {
+      // zigzag positions 0 .. K (K + 1) / 2 - 1 are the anti-diagonals row + col < K; the variant is chosen per warp
+      const int nmax = __reduce_max_sync(0xffffffffu, nsym);
+      if (nmax <= 1) {
         // DC only: D[a][0] = C[0][a] * B00 and P[a][b] = D[a][0] * C[0][b] with all C[0][.] equal -> a flat block
         const float c0 = dct_c(0);
         const float pv = __fmul_rn(__fmul_rn(c0, col[0]), c0);
@@ -883,8 +886,18 @@ __global__ void __launch_bounds__(kCtaThreads, 5)
         const uint32_t px = (uint32_t)__viaddmin_s32_relu(__float2int_rz(t), 128, 255) * 0x01010101u;
 #pragma unroll
         for (int r = 0; r < 16; r++) outw[r] = px;
-      } else if (__all_sync(0xffffffffu, nsym <= 10)) {
-        idct_block_4x4(col, P.one, outw);
+      } else if (nmax <= 3) {
+        idct_block_tri<2>(col, P.one, outw);
+      } else if (nmax <= 6) {
+        idct_block_tri<3>(col, P.one, outw);
+      } else if (nmax <= 10) {
+        idct_block_tri<4>(col, P.one, outw);
+      } else if (nmax <= 15) {
+        idct_block_tri<5>(col, P.one, outw);
+      } else if (nmax <= 21) {
+        idct_block_tri<6>(col, P.one, outw);
+      } else if (nmax <= 28) {
+        idct_block_tri<7>(col, P.one, outw);
       } else {
         idct_block(col, P.one, outw);
       }
