@@ -25,14 +25,18 @@ struct ZArray {
 }  // namespace
 
 namespace {
+// mode 0: general code on the 64-symbol scratch only; 1: 15-symbol scratch first (the kernel's pre-fast8 flow);
+// 2: the kernel's flow -- hash histogram, then the 8-symbol fast path, the general tail, or the 64-symbol scratch
 template <int STRIDE>
-int encode_blocks(const int16_t* coef, uint32_t n, int fast_cap15, uint8_t* out, uint8_t* sizes) {
+int encode_blocks(const int16_t* coef, uint32_t n, int mode, uint8_t* out, uint8_t* sizes) {
   using Fast = HuffScratch<15, STRIDE>;
   using Big = HuffScratch<64, STRIDE>;
   uint8_t* fb = new uint8_t[(size_t)Fast::kBytes * STRIDE]();
   int16_t* fh = new int16_t[(size_t)Fast::kSyms * STRIDE]();
   uint8_t* bb = new uint8_t[(size_t)Big::kBytes * STRIDE]();
   int16_t* bh = new int16_t[(size_t)Big::kSyms * STRIDE]();
+  uint32_t* f8sc = new uint32_t[(size_t)16 * STRIDE]();
+  uint16_t* f8ht = new uint16_t[(size_t)32 * STRIDE]();
   int big_used = 0;
   for (uint32_t b = 0; b < n; b++) {
     int16_t z[64];
@@ -42,24 +46,45 @@ int encode_blocks(const int16_t* coef, uint32_t n, int fast_cap15, uint8_t* out,
     ZArray za{z};
     Fast fs{fb, fh};
     Big bs{bb, bh};
-    HuffPlan pl;
-    pl.n = -1;
-    if (fast_cap15) pl = huff_plan(za, L, fs, NoWarp{});
-    bool big = false;
-    if (pl.n < 0) {
-      big = true;
-      big_used++;
-      pl = huff_plan(za, L, bs, NoWarp{});
-    }
     uint8_t tmp[256];
-    if (big) huff_emit(za, pl, bs, tmp, NoWarp{});
-    else huff_emit(za, pl, fs, tmp, NoWarp{});
-    const int sz = pl.size();
+    int sz;
+    bool done = false;
+    if (mode == 2) {
+      Fast8Scratch<STRIDE> F{f8sc, f8ht};
+      for (int i = 0; i < 32; i++) F.tab(i) = 0xffff;
+      const int ns = huff_hist(za, L, true, F, NoWarp{});
+      if (ns >= 0 && ns <= 8) {
+        const Fast8Plan pl = huff_fast8_plan(ns, L == 0 ? 1 : L, F, NoWarp{});
+        huff_fast8_emit(za, pl, F, tmp, NoWarp{});
+        sz = pl.size();
+        done = true;
+      } else if (ns >= 0) {
+        const int zero_slot = hist_to_general(ns, F, fs, NoWarp{});
+        const HuffPlan pl = huff_plan_tail(L, ns, zero_slot, false, fs, NoWarp{});
+        huff_emit(za, pl, fs, tmp, NoWarp{});
+        sz = pl.size();
+        done = true;
+      }
+    }
+    if (!done) {
+      HuffPlan pl;
+      pl.n = -1;
+      if (mode == 1) pl = huff_plan(za, L, fs, NoWarp{});
+      bool big = false;
+      if (pl.n < 0) {
+        big = true;
+        big_used++;
+        pl = huff_plan(za, L, bs, NoWarp{});
+      }
+      if (big) huff_emit(za, pl, bs, tmp, NoWarp{});
+      else huff_emit(za, pl, fs, tmp, NoWarp{});
+      sz = pl.size();
+    }
     memcpy(out, tmp, (size_t)sz);
     out += sz;
     sizes[b] = (uint8_t)sz;
   }
-  delete[] fb; delete[] fh; delete[] bb; delete[] bh;
+  delete[] fb; delete[] fh; delete[] bb; delete[] bh; delete[] f8sc; delete[] f8ht;
   return big_used;
 }
 }  // namespace
@@ -67,9 +92,10 @@ int encode_blocks(const int16_t* coef, uint32_t n, int fast_cap15, uint8_t* out,
 extern "C" {
 
 // coef: n x 64 row-major.  stride: element stride of the scratch arrays (1, or 128 to mimic the shared-memory
-// interleave of the kernel).  fast_cap15 != 0: try the 15-symbol scratch first like the kernel does.
-int hostemu_encode_blocks(const int16_t* coef, uint32_t n, int stride, int fast_cap15, uint8_t* out, uint8_t* sizes) {
-  return stride == 128 ? encode_blocks<128>(coef, n, fast_cap15, out, sizes) : encode_blocks<1>(coef, n, fast_cap15, out, sizes);
+// interleave of the kernel).  mode: see encode_blocks.
+int hostemu_encode_blocks(const int16_t* coef, uint32_t n, int stride, int mode, uint8_t* out, uint8_t* sizes) {
+  return stride == 128 ? encode_blocks<128>(coef, n, mode, out, sizes) : stride == 32 ? encode_blocks<32>(coef, n, mode, out, sizes)
+                                                                                  : encode_blocks<1>(coef, n, mode, out, sizes);
 }
 
 int hostemu_decode_blocks(const uint8_t* chunks, const uint8_t* sizes, uint32_t n, int16_t* coef) {

@@ -224,13 +224,15 @@ MYB_HD int group_table_bytes(int cnt) {  // one code length with cnt symbols, sp
   return bytes;
 }
 
+template <int CAP, int STRIDE, class W>
+MYB_HD HuffPlan huff_plan_tail(int L, int n, int zero_slot, bool bail, const HuffScratch<CAP, STRIDE>& S, const W& warp);
+
 // Build the code of one block.  Z: accessor with  int get(int i)  (zigzag coefficient i) and
 // void set(int i, int v); on success the first msg_len entries are overwritten with slot numbers
 // (the coefficient of slot s is S.sym(s)).  L = index of the last non-zero zigzag coefficient + 1 (0: all zero).
 // `warp`: cooperation policy; with WarpLockstep all 32 lanes must call this together (idle lanes pass L = 0).
 template <int CAP, int STRIDE, class Z, class W>
 MYB_HD HuffPlan huff_plan(Z& z, int L, const HuffScratch<CAP, STRIDE>& S, const W& warp) {
-  HuffPlan pl;
   // ---- histogram in first-occurrence order (Huffman.cpp:176-189, message part only; the trailing zeros
   // only matter through the key 0 they may add to the map, handled below).  Coefficients in [-8, 7] find
   // their slot through a 16 x 4-bit table held in a register pair; the rest by a short linear search.
@@ -277,7 +279,16 @@ MYB_HD HuffPlan huff_plan(Z& z, int L, const HuffScratch<CAP, STRIDE>& S, const 
     S.at(S.kCnt, 0) = 1;
     z.set(0, 0);
     n = 1;
+    zero_slot = 0;
   }
+  return huff_plan_tail(L, n, zero_slot, bail, S, warp);
+}
+
+// Everything after the histogram: S.sym(s) / S.at(kCnt, s) hold the n distinct symbols of the message in
+// first-occurrence order and their counts, zero_slot the slot of the value 0 (-1: not in the message).
+template <int CAP, int STRIDE, class W>
+MYB_HD HuffPlan huff_plan_tail(int L, int n, int zero_slot, bool bail, const HuffScratch<CAP, STRIDE>& S, const W& warp) {
+  HuffPlan pl;
   pl.n = bail ? -1 : n;
   pl.msg_len = L == 0 ? 1 : L;
   const bool tree = !bail && n > 2;  // one or two symbols: every code has length 1 (Huffman.cpp:76, :218-221)
@@ -470,6 +481,395 @@ MYB_HD void huff_emit(Z& z, const HuffPlan& pl, const HuffScratch<CAP, STRIDE>& 
   }
   w.flush();
 }
+
+// ---------------------------------------------------------------------------------------------------
+// Fast path: blocks with at most 8 distinct symbols (every block of natural content up to q ~ 75).
+// Same results as huff_plan / huff_emit, organised for few instructions per block:
+//  * histogram through a 32-entry open-addressing table, one 32-bit word per slot (symbol << 16 | count);
+//  * with at most 8 keys the reference's unordered_map never rehashes (13 buckets) and its iteration order,
+//    the heap of the initial leaves, the (length, value) sort and the canonical codes are straight-line code
+//    on registers (nibble-packed lists, an 8-input sorting network);
+//  * heap entries carry weight << 8 | leaf set, so a merge needs no parent links: it adds 1 to the depth
+//    nibble of every leaf below it, and the code-stream size is the sum of the merged weights.
+// ---------------------------------------------------------------------------------------------------
+template <int STRIDE>
+struct Fast8Scratch {
+  uint32_t* sc;    // [16] symbol << 16 | occurrences, slots in first-occurrence order
+  uint16_t* ht;    // [32] (value & 0x7ff) << 4 | slot, 0xffff = empty; must be all empty when huff_hist starts.
+                   //      After the histogram the same memory holds the heap [0..8) and the code table [8..16).
+  MYB_HD uint32_t& slot(int s) const { return sc[s * STRIDE]; }
+  MYB_HD uint16_t& tab(int h) const { return ht[h * STRIDE]; }
+  MYB_HD uint16_t& heap(int i) const { return ht[i * STRIDE]; }
+  MYB_HD uint16_t& code(int s) const { return ht[(8 + s) * STRIDE]; }
+};
+constexpr int kHistCap = 15;  // distinct symbols huff_hist accepts (the capacity of the general shared-memory scratch)
+
+// Histogram of the message z[0 .. L) in first-occurrence order; z[i] is replaced by the slot of its value.
+// Returns the number of distinct symbols, or -1 (z restored) when there are more than kHistCap.
+// Idle lanes pass live = false and get 0.
+template <int STRIDE, class Z, class W>
+MYB_HD int huff_hist(Z& z, int L, bool live, const Fast8Scratch<STRIDE>& F, const W& warp) {
+  int n = 0;
+  bool bail = false;
+  if (!live) L = 0;
+  const int Lw = warp.max(L);
+  MYB_NOUNROLL
+  for (int i = 0; i < Lw; i++) {
+    if (i < L && !bail) {
+      const int v = z.get(i);
+      const uint32_t tag = (uint32_t)v & 0x7ffu;
+      uint32_t h = tag & 31u;
+      uint32_t e = F.tab((int)h);
+      while (e != 0xffffu && (e >> 4) != tag) {  // rare: two values of the block share their low five bits
+        h = (h + 1u) & 31u;
+        e = F.tab((int)h);
+      }
+      if (e == 0xffffu && n == kHistCap) {
+        bail = true;
+        for (int j = 0; j < i; j++) z.set(j, (int)(int16_t)(F.slot(z.get(j)) >> 16));
+      } else {
+        int s;
+        uint32_t word;
+        if (e == 0xffffu) {
+          s = n++;
+          F.tab((int)h) = (uint16_t)((tag << 4) | (uint32_t)s);
+          word = ((uint32_t)v << 16) | 1u;
+        } else {
+          s = (int)(e & 15u);
+          word = F.slot(s) + 1u;
+        }
+        F.slot(s) = word;
+        z.set(i, s);
+      }
+    }
+    warp.sync();
+  }
+  if (live && L == 0) {  // all-zero block: the single symbol 0, one bit (Huffman.cpp:195-199)
+    F.slot(0) = 1u;
+    z.set(0, 0);
+    n = 1;
+  }
+  return bail ? -1 : n;
+}
+
+// Hand the histogram over to the general code (huff_plan_tail) when a warp holds a block with more than 8 symbols.
+template <int STRIDE, int CAP, int GSTRIDE, class W>
+MYB_HD int hist_to_general(int n, const Fast8Scratch<STRIDE>& F, const HuffScratch<CAP, GSTRIDE>& S, const W& warp) {
+  int zero_slot = -1;
+  const int nn = n > 0 ? n : 0;
+  const int nw = warp.max(nn);
+  MYB_NOUNROLL
+  for (int k = 0; k < nw; k++) {
+    if (k < nn) {
+      const uint32_t w = F.slot(k);
+      const int v = (int)(int16_t)(w >> 16);
+      S.sym(k) = (int16_t)v;
+      S.at(S.kCnt, k) = (uint8_t)(w & 0xffu);
+      if (v == 0) zero_slot = k;
+    }
+  }
+  warp.sync();
+  return zero_slot;
+}
+
+struct Fast8Plan {
+  int n;           // distinct symbols, 0 = idle lane
+  int msg_len;     // coded symbols
+  int bits;        // code stream bits
+  int table_bytes; // bytes of the serialised code table
+  uint32_t depth;  // code length of slot s in nibble s
+  MYB_HD int size() const { return n > 0 ? 3 + table_bytes + ((bits + 7) >> 3) : 0; }
+};
+
+MYB_HD uint32_t spread8(uint32_t m) {  // bit k of m -> bit 4k
+  uint32_t x = m;
+  x = (x | (x << 12)) & 0x000f000fu;
+  x = (x | (x << 6)) & 0x03030303u;
+  x = (x | (x << 3)) & 0x11111111u;
+  return x;
+}
+MYB_HD int ctz32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+  return __ffs((int)v) - 1;
+#else
+  return __builtin_ctz(v);
+#endif
+}
+
+// std::push_heap of `ent` as element number J of a heap held in registers (J is a compile-time constant, so the
+// path to the root is fixed and only the stopping point is data dependent).  Entries compare by weight (bits 8..15).
+template <int J>
+MYB_HD void heap_push_static(uint32_t (&H)[8], uint32_t ent) {
+  const uint32_t key = ent | 0xffu;
+  bool go = true;
+  int hole = J;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int lvl = 0; lvl < 3; lvl++) {
+    if (hole > 0) {
+      const int parent = (hole - 1) >> 1;
+      const bool up = go && H[parent] > key;
+      H[hole] = up ? H[parent] : (go ? ent : H[hole]);
+      go = up;
+      hole = parent;
+    }
+  }
+  if (go) H[0] = ent;
+}
+
+template <int STRIDE>
+MYB_HD void heap16_sift_up(const Fast8Scratch<STRIDE>& F, int hole, uint32_t ent) {
+  const uint32_t key = ent | 0xffu;
+  MYB_NOUNROLL
+  while (hole > 0) {
+    const int parent = (hole - 1) >> 1;
+    const uint32_t pe = F.heap(parent);
+    if (!(pe > key)) break;
+    F.heap(hole) = (uint16_t)pe;
+    hole = parent;
+  }
+  F.heap(hole) = (uint16_t)ent;
+}
+
+// std::pop_heap + pop_back (stl_heap.h __adjust_heap, then __push_heap of the former last element)
+template <int STRIDE>
+MYB_HD uint32_t heap16_pop(const Fast8Scratch<STRIDE>& F, int& hsize) {
+  const uint32_t top = F.heap(0);
+  const int len = hsize - 1;
+  hsize = len;
+  if (len == 0) return top;
+  const uint32_t value = F.heap(len);
+  int hole = 0, child = 0;
+  const int half = (len - 1) >> 1;
+  MYB_NOUNROLL
+  while (child < half) {
+    child = 2 * child + 2;
+    uint32_t r = F.heap(child);
+    const uint32_t l = F.heap(child - 1);
+    if (r > (l | 0xffu)) {
+      child--;
+      r = l;
+    }
+    F.heap(hole) = (uint16_t)r;
+    hole = child;
+  }
+  if ((len & 1) == 0 && child == ((len - 2) >> 1)) {
+    child = 2 * child + 2;
+    F.heap(hole) = F.heap(child - 1);
+    hole = child - 1;
+  }
+  heap16_sift_up(F, hole, value);
+  return top;
+}
+
+template <int STRIDE, class W>
+MYB_HD Fast8Plan huff_fast8_plan(int n, int msg_len, const Fast8Scratch<STRIDE>& F, const W& warp) {
+  Fast8Plan pl;
+  pl.n = n;
+  pl.msg_len = msg_len;
+  const int nw = warp.max(n);
+  // ---- iteration order of the reference's map (13 buckets, no rehash): list and buckets as 4-bit fields
+  uint32_t ord = 0, bkt = ~0u;
+  uint32_t cnt0 = 0;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int k = 0; k < 8; k++) {
+    if (k < nw) {
+      if (k < n) {
+        const uint32_t w = F.slot(k);
+        if (k == 0) cnt0 = w & 0xffu;
+        const int v = (int)(int16_t)(w >> 16);
+        // std::hash<short> = the value sign-extended to 64 bits; 2^64 mod 13 = 3
+        const uint32_t x13 = (uint32_t)(v + 1040 + (v < 0 ? 3 : 0));  // >= 0, same residue as the 64-bit hash
+        const uint32_t b = x13 - 13u * ((x13 * 5042u) >> 16);          // x13 % 13 for x13 < 6547
+        const uint32_t x = bkt ^ (b * 0x11111111u);
+        const uint32_t zero_nib = (x - 0x11111111u) & ~x & 0x88888888u;  // lowest hit is exact
+        const int p4 = zero_nib ? (ctz32(zero_nib) & ~3) : 0;
+        const uint32_t low = (1u << p4) - 1u;
+        ord = (ord & low) | ((ord & ~low) << 4) | ((uint32_t)k << p4);
+        bkt = (bkt & low) | ((bkt & ~low) << 4) | (b << p4);
+      }
+    }
+  }
+  // ---- leaves pushed in list order (Huffman.cpp:207-209) into a heap held in registers
+  uint32_t H[8];
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int k = 0; k < 8; k++) H[k] = 0;
+#define MYB_PUSH_LEAF(J)                                                           \
+  if (J < nw) {                                                                    \
+    if (J < n) {                                                                   \
+      const uint32_t sl = (ord >> (4 * J)) & 15u;                                  \
+      heap_push_static<J>(H, ((F.slot((int)sl) & 0xffu) << 8) | (1u << sl));       \
+    }                                                                              \
+  }
+  MYB_PUSH_LEAF(0) MYB_PUSH_LEAF(1) MYB_PUSH_LEAF(2) MYB_PUSH_LEAF(3)
+  MYB_PUSH_LEAF(4) MYB_PUSH_LEAF(5) MYB_PUSH_LEAF(6) MYB_PUSH_LEAF(7)
+#undef MYB_PUSH_LEAF
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int k = 0; k < 8; k++)
+    if (k < nw) F.heap(k) = (uint16_t)H[k];
+  // ---- n - 1 merges (Huffman.cpp:210-217)
+  int hsize = n, bits = 0;
+  uint32_t depth = 0;
+  MYB_NOUNROLL
+  for (int t = 0; t + 1 < nw; t++) {
+    if (t + 1 < n) {
+      const uint32_t a = heap16_pop(F, hsize);
+      const uint32_t b = heap16_pop(F, hsize);
+      const uint32_t w = (a >> 8) + (b >> 8);
+      const uint32_t m = (a | b) & 0xffu;
+      depth += spread8(m);
+      bits += (int)w;
+      hsize++;
+      heap16_sift_up(F, hsize - 1, (w << 8) | m);
+    }
+    warp.sync();
+  }
+  if (n == 1) {  // a single symbol gets a one-bit code (Huffman.cpp:76, :218-221)
+    depth = 1;
+    bits = (int)cnt0;
+  }
+  pl.depth = depth;
+  pl.bits = bits;
+  // ---- size of the code table: one group per used length, 1 + ceil(11 c / 8) bytes for c symbols (Huffman.cpp:284-293)
+  uint32_t per_len = 0;  // symbols per length, 4-bit fields (length 0 = unused slots, ignored)
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int k = 0; k < 8; k++) per_len += 1u << (((depth >> (4 * k)) & 15u) * 4u);
+  uint32_t lo = per_len & 0xfff0u, hi = per_len >> 16;
+  lo = (lo | (lo << 8)) & 0x00ff00ffu;
+  lo = (lo | (lo << 4)) & 0x0f0f0f0fu;
+  hi = (hi | (hi << 8)) & 0x00ff00ffu;
+  hi = (hi | (hi << 4)) & 0x0f0f0f0fu;
+  uint32_t f = 0;
+  {
+    const uint32_t t = ((lo * 3u + 0x07070707u) >> 3) & 0x1f1f1f1fu;
+    const uint32_t nz = ((lo + 0x7f7f7f7fu) >> 7) & 0x01010101u;
+    f += lo + t + nz;
+  }
+  {
+    const uint32_t t = ((hi * 3u + 0x07070707u) >> 3) & 0x1f1f1f1fu;
+    const uint32_t nz = ((hi + 0x7f7f7f7fu) >> 7) & 0x01010101u;
+    f += hi + t + nz;
+  }
+  // unused slots counted under length 0 add 7 >> 3 = 0 to t but their byte was masked out of lo above
+  pl.table_bytes = (int)((f * 0x01010101u) >> 24);
+  return pl;
+}
+
+#define MYB_CSWAP(a, b)                          \
+  {                                              \
+    const uint32_t lo_ = a < b ? a : b;          \
+    b = a < b ? b : a;                           \
+    a = lo_;                                     \
+  }
+
+// Serialise the chunk planned by huff_fast8_plan into dst[0 .. pl.size()): header, code table in (length, value)
+// order with canonical codes assigned on the way (Huffman.cpp:86-103, :300-316), code stream (:227-236, :319-325).
+template <int STRIDE, class Z, class W>
+MYB_HD void huff_fast8_emit(Z& z, const Fast8Plan& pl, const Fast8Scratch<STRIDE>& F, uint8_t* dst, const W& warp) {
+  const int n = pl.n;
+  const int nw = warp.max(n);
+  if (n > 0) {
+    dst[0] = (uint8_t)(pl.bits & 0xff);
+    dst[1] = (uint8_t)(pl.bits >> 8);
+    dst[2] = (uint8_t)pl.table_bytes;
+  }
+  // sort keys: length << 16 | (value + 1024) << 4 | slot; unused slots sort last
+  uint32_t K[8];
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int k = 0; k < 8; k++) {
+    K[k] = 0xffffffffu;
+    if (k < nw) {
+      if (k < n) {
+        const int v = (int)(int16_t)(F.slot(k) >> 16);
+        K[k] = (((pl.depth >> (4 * k)) & 15u) << 16) | ((uint32_t)(v + 1024) << 4) | (uint32_t)k;
+      }
+    }
+  }
+  if (nw > 4) {  // Batcher's odd-even merge sort, 19 compare-exchanges
+    MYB_CSWAP(K[0], K[1]) MYB_CSWAP(K[2], K[3]) MYB_CSWAP(K[4], K[5]) MYB_CSWAP(K[6], K[7])
+    MYB_CSWAP(K[0], K[2]) MYB_CSWAP(K[1], K[3]) MYB_CSWAP(K[4], K[6]) MYB_CSWAP(K[5], K[7])
+    MYB_CSWAP(K[1], K[2]) MYB_CSWAP(K[5], K[6])
+    MYB_CSWAP(K[0], K[4]) MYB_CSWAP(K[1], K[5]) MYB_CSWAP(K[2], K[6]) MYB_CSWAP(K[3], K[7])
+    MYB_CSWAP(K[2], K[4]) MYB_CSWAP(K[3], K[5])
+    MYB_CSWAP(K[1], K[2]) MYB_CSWAP(K[3], K[4]) MYB_CSWAP(K[5], K[6])
+  } else {
+    MYB_CSWAP(K[0], K[1]) MYB_CSWAP(K[2], K[3]) MYB_CSWAP(K[0], K[2]) MYB_CSWAP(K[1], K[3]) MYB_CSWAP(K[1], K[2])
+  }
+  uint8_t* p = dst + 3;
+  uint8_t* hdr = dst;  // header byte of the open group (dst: none yet)
+  uint32_t acc = 0, code = 0;
+  int nb = 0, prev = 0, cnt = 0;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int i = 0; i < 8; i++) {
+    if (i < nw) {
+      if (i < n) {
+        const uint32_t key = K[i];
+        const int len = (int)(key >> 16);
+        code <<= (len - prev);
+        F.code((int)(key & 15u)) = (uint16_t)((bit_reverse32(code) >> (32 - len)) | ((uint32_t)len << 8));
+        code++;
+        if (len != prev) {  // a new group: close the previous one, pad to a whole byte, reserve the header byte
+          if (prev) *hdr = (uint8_t)(((prev - 1) << 5) | (cnt - 1));
+          if (nb > 0) *p++ = (uint8_t)acc;
+          acc = 0;
+          nb = 0;
+          hdr = p++;
+          cnt = 0;
+          prev = len;
+        }
+        // pack11bit (Huffman.cpp:36-52): 11 bits on top of nb < 8 pending ones always complete one byte, sometimes two
+        acc |= (((key >> 4) + 1024u) & 0x7ffu) << nb;
+        nb += 11;
+        *p++ = (uint8_t)acc;
+        acc >>= 8;
+        nb -= 8;
+        if (nb >= 8) {
+          *p++ = (uint8_t)acc;
+          acc >>= 8;
+          nb -= 8;
+        }
+        cnt++;
+      }
+    }
+  }
+  if (n > 0) {
+    *hdr = (uint8_t)(((prev - 1) << 5) | (cnt - 1));
+    if (nb > 0) *p++ = (uint8_t)acc;
+  }
+  acc = 0;
+  nb = 0;
+  warp.sync();
+  const int L = n > 0 ? pl.msg_len : 0;
+  const int Lw = warp.max(L);
+  MYB_NOUNROLL
+  for (int k = 0; k < Lw; k++) {
+    if (k < L) {
+      const uint32_t ce = F.code(z.get(k));
+      acc |= (ce & 0xffu) << nb;
+      nb += (int)(ce >> 8);
+      if (nb >= 8) {
+        *p++ = (uint8_t)acc;
+        acc >>= 8;
+        nb -= 8;
+      }
+    }
+  }
+  if (nb > 0) *p++ = (uint8_t)acc;
+}
+#undef MYB_CSWAP
 
 // ---------------------------------------------------------------------------------------------------
 // Decoder (Huffman.cpp:243-277, :54-69, :106-154).  chunk/size: one block's bytes.  emit(j, v) receives

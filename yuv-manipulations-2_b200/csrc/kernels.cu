@@ -254,13 +254,21 @@ void launch_xrgb_to_iyuv(const uint8_t* d_bgrx, uint8_t* d_iyuv, uint32_t w, uin
 // ===================================================================================================
 constexpr int kStageBytes = 4 * 1024;                  // shared-memory staging of one tile's chunk bytes
 constexpr int kFastSyms = 15;                          // distinct symbols handled with shared-memory scratch
-using FastScratch = HuffScratch<kFastSyms, kCtaThreads>;
+// Entropy-coder scratch is one region per WARP, lanes interleaved (stride 32): the 8-symbol fast path and the general
+// code lay different element widths over the same bytes, which is safe because a warp runs one of them at a time.
+//   [0, 1024)     general: symbols  int16[16][32]
+//   [1024, 5920)  general: byte arrays uint8[153][32]  (first 16 rows = counts)
+//   [1536, 3584)  fast:    slot words uint32[16][32]   (dead before the general code writes its lists)
+//   [3584, 5632)  fast:    hash table uint16[32][32], later heap and code table
+using FastScratch = HuffScratch<kFastSyms, 32>;
 using BigScratch = HuffScratch<64, 1>;
+using F8Scratch = Fast8Scratch<32>;
+constexpr int kWarpScratchBytes = 1024 + FastScratch::kBytes * 32;
+static_assert(kWarpScratchBytes >= 5632 && kWarpScratchBytes % 16 == 0, "fast-path arrays must fit the warp region");
 
 struct EncSmem {
   uint16_t zz[64][kTileBlocks];                        // quantised coefficients, zigzag order; later slot ids
-  uint8_t hs_bytes[FastScratch::kBytes][kCtaThreads];
-  int16_t hs_syms[FastScratch::kSyms][kCtaThreads];
+  alignas(16) uint8_t coder[kCtaThreads / 32][kWarpScratchBytes];
   alignas(16) uint8_t stage[kStageBytes + 8];
   uint32_t warp_sums[4];
   uint32_t tile;
@@ -374,7 +382,10 @@ __global__ void __launch_bounds__(kCtaThreads, 5)
   EncSmem& sm = *reinterpret_cast<EncSmem*>(smem_raw);
   const int tid = threadIdx.x;
   const FrameGeom& g = P.g;
-  FastScratch fs{&sm.hs_bytes[0][tid], &sm.hs_syms[0][tid]};
+  uint8_t* const wbase = sm.coder[tid >> 5];
+  const int lane = tid & 31;
+  FastScratch fs{wbase + 1024 + lane, reinterpret_cast<int16_t*>(wbase) + lane};
+  F8Scratch f8{reinterpret_cast<uint32_t*>(wbase + 1536) + lane, reinterpret_cast<uint16_t*>(wbase + 3584) + lane};
   ZShared z{&sm.zz[0][tid]};
   uint8_t* const overflow = P.ws.overflow + (uint64_t)blockIdx.x * (kEncTile * 256u);
 
@@ -424,18 +435,34 @@ __global__ void __launch_bounds__(kCtaThreads, 5)
       //  instructions by 11% but not the time, because a CTA waits for its slowest warp -- profiles/r01_notes.md.)
       if (!live) L = 0;
       while (L > 0 && z.get(L - 1) == 0) L--;  // exact message length (Huffman.cpp:184-190); at most 8 steps
+      {  // empty the warp's hash table (2 KB, 64 bytes per lane)
+        uint4* q = reinterpret_cast<uint4*>(wbase + 3584);
+#pragma unroll
+        for (int j = 0; j < 4; j++) q[lane + 32 * j] = make_uint4(~0u, ~0u, ~0u, ~0u);
+      }
       __syncwarp();
-      HuffPlan pl = huff_plan(z, L, fs, WarpLockstep{});
+      const int nsym = huff_hist(z, L, live, f8, WarpLockstep{});
+      const bool fast = __all_sync(0xffffffffu, nsym >= 0 && nsym <= 8);  // warp-uniform choice of the code path
+      Fast8Plan pl8{};
+      HuffPlan pl{};
       bool big = false;
       uint8_t lbytes[BigScratch::kBytes];
       int16_t lsyms[BigScratch::kSyms];
       BigScratch bs{lbytes, lsyms};
-      if (live && pl.n < 0) {  // more distinct symbols than the shared-memory scratch holds
-        big = true;
-        pl = plan_big(z, L, bs);
+      uint32_t size;
+      if (fast) {
+        pl8 = huff_fast8_plan(nsym, L == 0 ? 1 : L, f8, WarpLockstep{});
+        size = (uint32_t)pl8.size();
+      } else {
+        const int zero_slot = hist_to_general(nsym, f8, fs, WarpLockstep{});
+        pl = huff_plan_tail(L, nsym > 0 ? nsym : 0, zero_slot, nsym < 0, fs, WarpLockstep{});
+        if (live && pl.n < 0) {  // more distinct symbols than the shared-memory scratch holds
+          big = true;
+          pl = plan_big(z, L, bs);
+        }
+        __syncwarp();
+        size = live ? (uint32_t)pl.size() : 0u;
       }
-      __syncwarp();
-      const uint32_t size = live ? (uint32_t)pl.size() : 0u;
       // chunk sizes go to a linear side array; finalize_frames_kernel moves them behind the plane headers,
       // whose position depends on the (data dependent) size of the previous planes
       if (live) P.ws.chunk_sizes[gblk0 + blk] = (uint8_t)size;
@@ -446,10 +473,14 @@ __global__ void __launch_bounds__(kCtaThreads, 5)
         uint8_t* dst = fits ? &sm.stage[off] : overflow + off;
         // first chunk that does not fit the shared staging buffer (chunks never straddle; offsets only grow)
         if (live && !fits && off <= (uint32_t)kStageBytes) atomicMin(&sm.split, off);
-        HuffPlan plf = pl;
-        if (!live || big) plf.n = 0;
-        huff_emit(z, plf, fs, dst, WarpLockstep{});
-        if (live && big) emit_big(z, pl, bs, dst);
+        if (fast) {
+          huff_fast8_emit(z, pl8, f8, dst, WarpLockstep{});
+        } else {
+          HuffPlan plf = pl;
+          if (!live || big) plf.n = 0;
+          huff_emit(z, plf, fs, dst, WarpLockstep{});
+          if (live && big) emit_big(z, pl, bs, dst);
+        }
       }
       carried += pass_total;
     }
