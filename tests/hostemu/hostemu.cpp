@@ -17,10 +17,17 @@ using namespace myyuvb;
 namespace {
 const uint8_t kZigzag[64] = {MYB_ZIGZAG_LIST};
 
-struct ZArray {
+struct ZArray {  // same views as the kernel's ZShared / ZSlots
   int16_t* z;
-  int get(int i) const { return z[i]; }
+  int get(int i) const { return ((int)((uint32_t)(uint16_t)z[i] << 21)) >> 21; }
   void set(int i, int v) { z[i] = (int16_t)v; }
+  uint32_t raw(int i) const { return (uint16_t)z[i]; }
+  void setraw(int i, uint32_t w) { z[i] = (int16_t)(uint16_t)w; }
+  int slot(int i) const { return ((uint16_t)z[i] >> 11) & 15; }
+};
+struct ZSlots {
+  int16_t* z;
+  int get(int i) const { return ((uint16_t)z[i] >> 11) & 15; }
 };
 }  // namespace
 
@@ -61,7 +68,8 @@ int encode_blocks(const int16_t* coef, uint32_t n, int mode, uint8_t* out, uint8
       } else if (ns >= 0) {
         const int zero_slot = hist_to_general(ns, F, fs, NoWarp{});
         const HuffPlan pl = huff_plan_tail(L, ns, zero_slot, false, fs, NoWarp{});
-        huff_emit(za, pl, fs, tmp, NoWarp{});
+        ZSlots zs{z};
+        huff_emit(zs, pl, fs, tmp, NoWarp{});
         sz = pl.size();
         done = true;
       }

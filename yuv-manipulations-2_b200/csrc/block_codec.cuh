@@ -504,52 +504,47 @@ struct Fast8Scratch {
 };
 constexpr int kHistCap = 15;  // distinct symbols huff_hist accepts (the capacity of the general shared-memory scratch)
 
-// Histogram of the message z[0 .. L) in first-occurrence order; z[i] is replaced by the slot of its value.
-// Returns the number of distinct symbols, or -1 (z restored) when there are more than kHistCap.
-// Idle lanes pass live = false and get 0.
+// Histogram of the message z[0 .. L) in first-occurrence order.  Z here is an accessor of raw 16-bit words:
+// raw(i) / setraw(i, w).  A coefficient needs 11 bits, so the slot of its value is written into bits 11..14 of
+// the same word and the value stays readable (sign-extend the low 11 bits) for the code that takes over when
+// the block has more symbols than this path handles.
+// Returns the number of distinct symbols, or -1 when there are more than kHistCap.  Idle lanes pass live = false
+// and get 0.
 template <int STRIDE, class Z, class W>
 MYB_HD int huff_hist(Z& z, int L, bool live, const Fast8Scratch<STRIDE>& F, const W& warp) {
   int n = 0;
-  bool bail = false;
   if (!live) L = 0;
   const int Lw = warp.max(L);
   MYB_NOUNROLL
   for (int i = 0; i < Lw; i++) {
-    if (i < L && !bail) {
-      const int v = z.get(i);
-      const uint32_t tag = (uint32_t)v & 0x7ffu;
-      uint32_t h = tag & 31u;
+    if (i < L && n <= kHistCap) {
+      const uint32_t raw = z.raw(i);
+      const uint32_t tag = raw & 0x7ffu;
+      uint32_t h = raw & 31u;
       uint32_t e = F.tab((int)h);
-      while (e != 0xffffu && (e >> 4) != tag) {  // rare: two values of the block share their low five bits
-        h = (h + 1u) & 31u;
-        e = F.tab((int)h);
+      if (e != 0xffffu && (e >> 4) != tag) {  // rare: two values of the block share their low five bits
+        do {
+          h = (h + 1u) & 31u;
+          e = F.tab((int)h);
+        } while (e != 0xffffu && (e >> 4) != tag);
       }
-      if (e == 0xffffu && n == kHistCap) {
-        bail = true;
-        for (int j = 0; j < i; j++) z.set(j, (int)(int16_t)(F.slot(z.get(j)) >> 16));
-      } else {
-        int s;
-        uint32_t word;
-        if (e == 0xffffu) {
-          s = n++;
-          F.tab((int)h) = (uint16_t)((tag << 4) | (uint32_t)s);
-          word = ((uint32_t)v << 16) | 1u;
-        } else {
-          s = (int)(e & 15u);
-          word = F.slot(s) + 1u;
-        }
-        F.slot(s) = word;
-        z.set(i, s);
-      }
+      const bool isnew = e == 0xffffu;
+      const uint32_t s = isnew ? (uint32_t)n : (e & 15u);  // n == 16 cannot get here
+      uint32_t word = raw << 16;
+      if (isnew) F.tab((int)h) = (uint16_t)((tag << 4) | s);
+      else word = F.slot((int)s);
+      F.slot((int)s) = word + 1u;
+      n += isnew ? 1 : 0;
+      z.setraw(i, tag | (s << 11));
     }
     warp.sync();
   }
   if (live && L == 0) {  // all-zero block: the single symbol 0, one bit (Huffman.cpp:195-199)
     F.slot(0) = 1u;
-    z.set(0, 0);
+    z.setraw(0, 0u);
     n = 1;
   }
-  return bail ? -1 : n;
+  return n > kHistCap ? -1 : n;
 }
 
 // Hand the histogram over to the general code (huff_plan_tail) when a warp holds a block with more than 8 symbols.
@@ -857,7 +852,7 @@ MYB_HD void huff_fast8_emit(Z& z, const Fast8Plan& pl, const Fast8Scratch<STRIDE
   MYB_NOUNROLL
   for (int k = 0; k < Lw; k++) {
     if (k < L) {
-      const uint32_t ce = F.code(z.get(k));
+      const uint32_t ce = F.code(z.slot(k));
       acc |= (ce & 0xffu) << nb;
       nb += (int)(ce >> 8);
       if (nb >= 8) {

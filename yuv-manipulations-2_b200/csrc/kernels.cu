@@ -279,8 +279,16 @@ static_assert(sizeof(EncSmem) <= 44 * 1024 + 256, "EncSmem must allow 5 CTAs per
 
 struct ZShared {  // accessor of one block's column in EncSmem::zz
   uint16_t* col;
-  MYB_D int get(int i) const { return (int)(int16_t)col[i * kTileBlocks]; }
+  // value view: a coefficient is 11 bits two's complement; bits 11..14 may hold its slot (huff_hist)
+  MYB_D int get(int i) const { return ((int)((uint32_t)col[i * kTileBlocks] << 21)) >> 21; }
   MYB_D void set(int i, int v) { col[i * kTileBlocks] = (uint16_t)v; }
+  MYB_D uint32_t raw(int i) const { return col[i * kTileBlocks]; }
+  MYB_D void setraw(int i, uint32_t w) { col[i * kTileBlocks] = (uint16_t)w; }
+  MYB_D int slot(int i) const { return (col[i * kTileBlocks] >> 11) & 15; }
+};
+struct ZSlots {  // slot view of the same column for the general emit code after huff_hist
+  uint16_t* col;
+  MYB_D int get(int i) const { return (col[i * kTileBlocks] >> 11) & 15; }
 };
 
 struct EncParams {
@@ -478,7 +486,8 @@ __global__ void __launch_bounds__(kCtaThreads, 5)
         } else {
           HuffPlan plf = pl;
           if (!live || big) plf.n = 0;
-          huff_emit(z, plf, fs, dst, WarpLockstep{});
+          ZSlots zs{z.col};
+          huff_emit(zs, plf, fs, dst, WarpLockstep{});
           if (live && big) emit_big(z, pl, bs, dst);
         }
       }
