@@ -97,6 +97,16 @@ MYYUVB_API int myyuvb_dct_compress_batch_dev(myyuvb_ctx* ctx, const uint8_t* d_i
                                              const uint8_t quality[3], uint32_t n_frames, uint8_t* d_out,
                                              uint64_t out_capacity, uint64_t* d_offsets);
 
+/* The whole pipeline of the reference's  YUV(bmp, IYUV).compress(DCT, q)  (myyuv_yuv.cpp:88-128 then DCT.cpp:371-430) for a
+ * batch of XRGB8888 frames, device resident: d_bgrx n_frames * w*h*4 (rows as stored in the BMP), payloads and offsets as
+ * in myyuvb_dct_compress_batch_dev.  Frames are converted and coded in chunks of chunk_frames (0: about 100 MB of IYUV) so
+ * that the intermediate IYUV image is read back from L2, not HBM.  d_iyuv: NULL, or n_frames * w*h*3/2 bytes that receive
+ * the IYUV frames as well (the product of the conversion step alone). */
+MYYUVB_API int myyuvb_xrgb_dct_compress_batch_dev(myyuvb_ctx* ctx, const uint8_t* d_bgrx, uint32_t width, uint32_t height,
+                                                  int bottom_up, const uint8_t quality[3], uint32_t n_frames,
+                                                  uint32_t chunk_frames, uint8_t* d_iyuv, uint8_t* d_out,
+                                                  uint64_t out_capacity, uint64_t* d_offsets);
+
 /* d_payloads + d_offsets as produced above (any packing is fine as long as frame f occupies
  * [d_offsets[f], d_offsets[f+1])).  d_iyuv: n_frames * w*h*3/2. */
 MYYUVB_API int myyuvb_dct_decompress_batch_dev(myyuvb_ctx* ctx, const uint8_t* d_payloads, const uint64_t* d_offsets,

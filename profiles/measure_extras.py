@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Side measurements for profiles/r01_notes.md (run on the GPU box): the colour-conversion kernel against the HBM
 roofline, single-image latency through the host-pointer C ABI (what the class API / CLI path pays), quality sweep."""
-import importlib, json, pathlib, sys, time
+import importlib, json, os, pathlib, sys, time
 ROOT = pathlib.Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 import numpy as np
@@ -36,6 +36,31 @@ byts = F * W * H * 5.5
 peak = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()).get("hbm_gbs", 6650.0) if (ROOT / "MEASURED_PEAKS.json").exists() else 6650.0
 out["xrgb_to_iyuv"] = {"frames": F, "ms": round(ms, 4), "Mpixel_s": round(F * W * H / ms / 1e3, 1), "GBps": round(byts / ms / 1e6, 1),
                        "frac_of_hbm_peak": round(byts / ms / 1e6 / peak, 3), "algorithmic_bytes": int(byts)}
+
+# ---- full pipeline XRGB -> IYUV -> DCT-50 (BASELINE configs[2]), device resident, by chunk size ----
+capp = F * pkg.capi.compress_bound(W, H)
+p_out = torch.empty(capp, dtype=torch.uint8, device=dev)
+p_off = torch.zeros(F + 1, dtype=torch.int64, device=dev)
+for chunk in (1, 2, 3, 4, 8, 16, 32):
+    for _ in range(2):
+        ctx.xrgb_compress_batch_dev(bg, W, H, True, (50, 50, 50), F, p_out, capp, p_off, None, chunk)
+    ctx.batch_status()
+    torch.cuda.synchronize()
+    ev[0].record(stream)
+    for _ in range(5):
+        ctx.xrgb_compress_batch_dev(bg, W, H, True, (50, 50, 50), F, p_out, capp, p_off, None, chunk)
+    ev[1].record(stream)
+    torch.cuda.synchronize()
+    ctx.batch_status()
+    ms = ev[0].elapsed_time(ev[1]) / 5
+    pay = int(p_off[F].item())
+    out[f"pipeline_chunk{chunk}"] = {"ms": round(ms, 3), "Mpixel_s": round(F * W * H / ms / 1e3, 1), "payload_bytes": pay,
+                                    "GBps_fused_bytes": round((F * W * H * 4 + pay) / ms / 1e6, 1)}
+del p_out
+
+if os.environ.get("EXTRAS_ONLY") == "pipeline":
+    print(json.dumps(out, indent=1))
+    sys.exit(0)
 
 # ---- single image latency through the host-pointer C ABI (pageable numpy buffers, like the class API) ----
 hctx = pkg.Context(0)

@@ -23,6 +23,14 @@ def test_colour_conversion_matches_oracle(ctx, ora, synth, w, h):
         assert np.array_equal(got, ora.bgrx_to_iyuv(bgrx, w, h, bottom_up))
 
 
+@pytest.mark.parametrize("w,h", [(2, 2), (12, 10), (20, 6), (36, 4), (1002, 14)])
+def test_colour_conversion_narrow_widths(ctx, ora, synth, w, h):
+    # widths that are not a multiple of 8 take the one-quad-per-thread kernel (the reference only needs even sizes)
+    bgrx = synth.bgrx_frames_numpy(w, h, 1, first=5)[0]
+    for bottom_up in (True, False):
+        assert np.array_equal(ctx.xrgb_to_iyuv(bgrx, w, h, bottom_up), ora.bgrx_to_iyuv(bgrx, w, h, bottom_up))
+
+
 def test_colour_conversion_extremes(ctx, ora):
     # every (B,G,R) on a coarse lattice plus the pure-blue quad whose Cb sum wraps to 0
     vals = np.array([0, 1, 2, 15, 16, 17, 63, 64, 127, 128, 129, 191, 200, 253, 254, 255], np.uint8)
@@ -158,6 +166,38 @@ def test_batch_device_api(ctx, ora, synth, pkg):
     got = d_yuv.cpu().numpy()
     for i in range(3):
         assert np.array_equal(got[i], ora.bgrx_to_iyuv(bg[i], w, h, True))
+
+
+@pytest.mark.parametrize("chunk,keep_iyuv", [(0, False), (1, True), (3, False), (4, True), (7, True)])
+def test_full_pipeline_xrgb_to_payload(ctx, ora, synth, pkg, chunk, keep_iyuv):
+    """BASELINE configs[2]: XRGB -> IYUV -> DCT-50 in one call, chunks chained on the device; every frame's payload and
+    (optionally) IYUV image must equal the oracle's two-step result."""
+    torch = pytest.importorskip("torch")
+    w, h, n, q = 320, 176, 7, (50, 50, 50)
+    bg = synth.bgrx_frames_numpy(w, h, n, first=2)
+    d_bg = torch.from_numpy(bg).cuda()
+    cap = pkg.capi.compress_bound(w, h) * n
+    d_out = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    d_off = torch.full((n + 1,), -1, dtype=torch.int64, device="cuda")
+    d_yuv = torch.zeros((n, w * h * 3 // 2), dtype=torch.uint8, device="cuda") if keep_iyuv else None
+    torch.cuda.synchronize()
+    ctx.xrgb_compress_batch_dev(d_bg, w, h, True, q, n, d_out, cap, d_off, d_yuv, chunk)
+    ctx.batch_status()
+    off, out = d_off.cpu().numpy(), d_out.cpu().numpy()
+    assert off[0] == 0 and np.all(np.diff(off) > 0)
+    for i in range(n):
+        iyuv = ora.bgrx_to_iyuv(bg[i], w, h, True)
+        if keep_iyuv:
+            assert np.array_equal(d_yuv[i].cpu().numpy(), iyuv), f"frame {i} iyuv"
+        assert np.array_equal(out[off[i]: off[i + 1]], ora.compress(iyuv, w, h, q)), f"frame {i}"
+    # a capacity that cuts the batch short is reported, nothing is written past it
+    small = int(off[4]) + 10
+    d_out2 = torch.zeros(cap, dtype=torch.uint8, device="cuda")
+    ctx.xrgb_compress_batch_dev(d_bg, w, h, True, q, n, d_out2, small, d_off, None, chunk)
+    with pytest.raises(pkg.MyyuvError) as e:
+        ctx.batch_status()
+    assert e.value.code == pkg.capi.ERR_CAPACITY
+    assert not d_out2[small:].any()
 
 
 def test_batch_host_api_multi_chunk(ctx, ora, synth, pkg):

@@ -22,6 +22,7 @@ EXPORTS = [
     "myyuvb_ctx_create", "myyuvb_ctx_destroy", "myyuvb_last_error", "myyuvb_sync", "myyuvb_stream",
     "myyuvb_compress_bound", "myyuvb_xrgb_to_iyuv", "myyuvb_dct_compress", "myyuvb_dct_decompress",
     "myyuvb_xrgb_to_iyuv_batch_dev", "myyuvb_dct_compress_batch_dev", "myyuvb_dct_decompress_batch_dev",
+    "myyuvb_xrgb_dct_compress_batch_dev",
     "myyuvb_batch_status", "myyuvb_dct_compress_batch_host", "myyuvb_dct_decompress_batch_host",
     "myyuvb_host_alloc", "myyuvb_host_free", "myyuvb_launch_count", "myyuvb_last_kernel_ms",
 ]
@@ -69,6 +70,8 @@ def lib() -> C.CDLL:
                                                 C.c_uint64, C.c_void_p]
     L.myyuvb_dct_decompress_batch_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, _u8p, C.c_uint32,
                                                   C.c_void_p]
+    L.myyuvb_xrgb_dct_compress_batch_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, _u8p, C.c_uint32,
+                                                      C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
     L.myyuvb_batch_status.argtypes = [C.c_void_p]
     L.myyuvb_dct_compress_batch_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, _u8p, C.c_uint32, C.c_void_p,
                                                  C.c_uint64, C.c_void_p]
@@ -227,6 +230,15 @@ class Context:
         qa = _q(q)
         _check(lib().myyuvb_dct_decompress_batch_dev(self._h, _ptr(d_payloads), _ptr(d_offsets), w, h, qa.ctypes.data_as(_u8p),
                                                      n_frames, _ptr(d_iyuv)))
+
+    def xrgb_compress_batch_dev(self, d_bgrx, w: int, h: int, bottom_up: bool, q, n_frames: int, d_out, out_capacity: int,
+                                d_offsets, d_iyuv=None, chunk_frames: int = 0) -> None:
+        """YUV(bmp, IYUV).compress(DCT, q) for a device-resident batch of XRGB frames (chunked so that the IYUV
+        intermediate is read back from L2); d_iyuv optionally receives the IYUV frames too."""
+        qa = _q(q)
+        _check(lib().myyuvb_xrgb_dct_compress_batch_dev(self._h, _ptr(d_bgrx), w, h, int(bottom_up), qa.ctypes.data_as(_u8p), n_frames,
+                                                        chunk_frames, _ptr(d_iyuv) if d_iyuv is not None else None, _ptr(d_out),
+                                                        out_capacity, _ptr(d_offsets)))
 
     def last_kernel_ms(self) -> float:
         ms = C.c_float(0)

@@ -278,21 +278,19 @@ int myyuvb_xrgb_to_iyuv_batch_dev(myyuvb_ctx* c, const uint8_t* d_bgrx, uint32_t
                                   uint32_t n_frames, uint8_t* d_iyuv) {
   if (!c || !d_bgrx || !d_iyuv) return fail(MYYUVB_ERR_ARG, "null argument");
   if (w == 0 || h == 0 || (w % 2) || (h % 2)) return fail(MYYUVB_ERR_EVEN, "Error. width and height must be even");
-  if (w % 4) return fail(MYYUVB_ERR_EVEN, "Error. width must be a multiple of 4 (BMP rows are not padded, myyuv_bmp.cpp:130)");
   if ((uint64_t)w * h * 4 > 0xffffffffull) return fail(MYYUVB_ERR_TOO_LARGE, "Error. image does not fit the format's uint32 sizes");
-  if (((uintptr_t)d_bgrx & 15) || ((uintptr_t)d_iyuv & 3)) return fail(MYYUVB_ERR_ARG, "device buffers must be 16-byte aligned");
+  if (((uintptr_t)d_bgrx & 15) || ((uintptr_t)d_iyuv & 7)) return fail(MYYUVB_ERR_ARG, "device buffers must be 16-byte (input) / 8-byte (output) aligned");
   CU(cudaSetDevice(c->device));
   launch_xrgb_to_iyuv(d_bgrx, d_iyuv, w, h, bottom_up, n_frames, c->stream);
   CU(cudaGetLastError());
   return MYYUVB_OK;
 }
 
-int myyuvb_dct_compress_batch_dev(myyuvb_ctx* c, const uint8_t* d_iyuv, uint32_t w, uint32_t h, const uint8_t quality[3],
-                                  uint32_t n_frames, uint8_t* d_out, uint64_t out_capacity, uint64_t* d_offsets) {
-  if (!c || !d_iyuv || !quality || !d_out || !d_offsets || n_frames == 0) return fail(MYYUVB_ERR_ARG, "null argument");
+namespace {
+// d_base: nullptr, or a device pointer to the position of the first payload inside d_out (written by an earlier launch)
+int compress_dev_impl(myyuvb_ctx* c, const uint8_t* d_iyuv, uint32_t w, uint32_t h, const uint8_t quality[3], uint32_t n_frames,
+                      uint8_t* d_out, uint64_t out_capacity, uint64_t* d_offsets, const uint64_t* d_base) {
   int rc;
-  if ((rc = check_quality(quality))) return rc;
-  if ((rc = check_dims(w, h))) return rc;
   if ((uintptr_t)d_iyuv & 7) return fail(MYYUVB_ERR_ARG, "device input must be 8-byte aligned");
   CU(cudaSetDevice(c->device));
   const FrameGeom g = make_geom(w, h, n_frames, kEncTile);
@@ -301,8 +299,48 @@ int myyuvb_dct_compress_batch_dev(myyuvb_ctx* c, const uint8_t* d_iyuv, uint32_t
   if ((rc = ensure_workspace(c, g, true, &ws, out_capacity))) return rc;
   QTables qt;
   make_qtables(quality, &qt);
-  launch_compress(d_iyuv, g, qt, d_out, out_capacity, d_offsets, ws, c->stream);
+  launch_compress(d_iyuv, g, qt, d_out, out_capacity, d_offsets, d_base, ws, c->stream);
   CU(cudaGetLastError());
+  return MYYUVB_OK;
+}
+}  // namespace
+
+int myyuvb_dct_compress_batch_dev(myyuvb_ctx* c, const uint8_t* d_iyuv, uint32_t w, uint32_t h, const uint8_t quality[3],
+                                  uint32_t n_frames, uint8_t* d_out, uint64_t out_capacity, uint64_t* d_offsets) {
+  if (!c || !d_iyuv || !quality || !d_out || !d_offsets || n_frames == 0) return fail(MYYUVB_ERR_ARG, "null argument");
+  int rc;
+  if ((rc = check_quality(quality))) return rc;
+  if ((rc = check_dims(w, h))) return rc;
+  return compress_dev_impl(c, d_iyuv, w, h, quality, n_frames, d_out, out_capacity, d_offsets, nullptr);
+}
+
+// XRGB -> IYUV -> DCT payloads.  Frames go through in chunks: a chunk is converted, then coded while its IYUV bytes are
+// still in L2 (126 MB), so the intermediate image of the reference's two-step API (YUV(bmp) then compress) costs no
+// HBM read.  Fusing the conversion into the coding kernel itself was rejected: that kernel is instruction-issue bound
+//  and every pixel would be converted up to three times (once per plane tile that needs it).
+int myyuvb_xrgb_dct_compress_batch_dev(myyuvb_ctx* c, const uint8_t* d_bgrx, uint32_t w, uint32_t h, int bottom_up,
+                                       const uint8_t quality[3], uint32_t n_frames, uint32_t chunk_frames, uint8_t* d_iyuv,
+                                       uint8_t* d_out, uint64_t out_capacity, uint64_t* d_offsets) {
+  if (!c || !d_bgrx || !quality || !d_out || !d_offsets || n_frames == 0) return fail(MYYUVB_ERR_ARG, "null argument");
+  int rc;
+  if ((rc = check_quality(quality))) return rc;
+  if ((rc = check_dims(w, h))) return rc;
+  if ((uint64_t)w * h * 4 > 0xffffffffull) return fail(MYYUVB_ERR_TOO_LARGE, "Error. image does not fit the format's uint32 sizes");
+  CU(cudaSetDevice(c->device));
+  const uint64_t frame_bytes = (uint64_t)w * h * 3 / 2;
+  if (chunk_frames == 0) chunk_frames = (uint32_t)std::max<uint64_t>(1, (100ull << 20) / frame_bytes);  // ~100 MB of IYUV per chunk
+  chunk_frames = std::min(chunk_frames, n_frames);
+  uint8_t* ring = nullptr;
+  if (!d_iyuv) {
+    if ((rc = c->d_in.reserve((uint64_t)chunk_frames * frame_bytes))) return rc;
+    ring = c->d_in.as<uint8_t>();
+  }
+  for (uint32_t f0 = 0; f0 < n_frames; f0 += chunk_frames) {
+    const uint32_t nf = std::min(chunk_frames, n_frames - f0);
+    uint8_t* iy = d_iyuv ? d_iyuv + (uint64_t)f0 * frame_bytes : ring;
+    if ((rc = myyuvb_xrgb_to_iyuv_batch_dev(c, d_bgrx + (uint64_t)f0 * w * h * 4, w, h, bottom_up, nf, iy))) return rc;
+    if ((rc = compress_dev_impl(c, iy, w, h, quality, nf, d_out, out_capacity, d_offsets + f0, f0 ? d_offsets + f0 : nullptr))) return rc;
+  }
   return MYYUVB_OK;
 }
 

@@ -42,6 +42,7 @@ typedef unsigned long long u64;
 #define F2R(v) reinterpret_cast<u64&>(v)
 
 MYB_D f2 dup(float c) { f2 r; r.x = c; r.y = c; return r; }
+MYB_D f2 mkp(float a, float b) { f2 r; r.x = a; r.y = b; return r; }
 MYB_D f2 mul2(f2 a, f2 b) {  // RN(a*b) per lane
   f2 d;
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(F2R(d)) : "l"(F2R(a)), "l"(F2R(b)));
@@ -189,58 +190,151 @@ MYB_D void copy_global_to_global(uint8_t* __restrict__ dst, const uint8_t* __res
 
 // ===================================================================================================
 // Colour conversion  (myyuv_yuv.cpp:34-52, :88-128; row flip of myyuv_bmp.cpp:95-98 folded into addressing)
-// One thread = 4 pixels x 2 rows: two 128-bit loads, two 32-bit Y stores, one 16-bit U and V store.
+// One thread = 8 pixels x 2 rows: four 128-bit loads, two 64-bit Y stores, one 32-bit U and V store.
+// The kernel must stay under the HBM time of 5.5 bytes per pixel, so the per-pixel work avoids the quarter-rate
+// conversion unit where it can: bytes become floats through the 2^23 mantissa trick, (uint8_t)Y (Y >= 0) is a
+// round-toward-zero add of 2^23, and two pixels share every multiply / add as the lanes of an f32x2 instruction.
+// Only the two possibly negative chroma values per pixel go through F2I.  Every product and sum is rounded
+// separately in the reference's order.
 // ===================================================================================================
-MYB_D void pixel_yuv(uint32_t px, uint32_t& y, uint32_t& cb, uint32_t& cr) {
-  const float B = (float)(px & 0xff), G = (float)((px >> 8) & 0xff), R = (float)((px >> 16) & 0xff);
-  const float Y = __fadd_rn(__fadd_rn(__fmul_rn(0.299f, R), __fmul_rn(0.587f, G)), __fmul_rn(0.114f, B));
-  y = (uint32_t)__float2int_rz(Y) & 0xff;
-  // (uint8_t)(float) of a possibly negative value is cvttss2si + low byte on the reference's x86-64 build,
-  // then "+ 128" and the store to uint8_t wrap again (myyuv_yuv.cpp:48-49)
-  cb = (uint32_t)(__float2int_rz(__fmul_rn(__fsub_rn(B, Y), 0.564f)) + 128) & 0xff;
-  cr = (uint32_t)(__float2int_rz(__fmul_rn(__fsub_rn(R, Y), 0.713f)) + 128) & 0xff;
+struct PixelPair {
+  uint32_t ybits0, ybits1;  // 0x4B0000yy
+  int cb0, cb1, cr0, cr1;   // trunc((B - Y) * 0.564), trunc((R - Y) * 0.713)
+};
+
+MYB_D PixelPair pixel_pair_yuv(uint32_t p0, uint32_t p1, f2 ONE) {
+  const f2 bias = dup(-8388608.0f);
+  f2 B, G, R;
+  B.x = __uint_as_float(__byte_perm(p0, 0x4B000000u, 0x7440)); B.y = __uint_as_float(__byte_perm(p1, 0x4B000000u, 0x7440));
+  G.x = __uint_as_float(__byte_perm(p0, 0x4B000000u, 0x7441)); G.y = __uint_as_float(__byte_perm(p1, 0x4B000000u, 0x7441));
+  R.x = __uint_as_float(__byte_perm(p0, 0x4B000000u, 0x7442)); R.y = __uint_as_float(__byte_perm(p1, 0x4B000000u, 0x7442));
+  B = add2(B, bias); G = add2(G, bias); R = add2(R, bias);
+  // Y = ((0.299f * R) + (0.587f * G)) + (0.114f * B)          myyuv_yuv.cpp:44-46
+  const f2 Y = sum2(sum2(mul2(dup(0.299f), R), mul2(dup(0.587f), G), ONE), mul2(dup(0.114f), B), ONE);
+  const f2 yi = add2_rz(Y, dup(8388608.0f));  // low byte = (uint8_t)Y
+  const f2 NEG = mkp(-ONE.x, -ONE.y);
+  // (uint8_t)(float) of a possibly negative value is cvttss2si + low byte on the reference's x86-64 build, then
+  // "+ 128" and the store to uint8_t wrap again (myyuv_yuv.cpp:48-49)
+  const f2 db = mul2(fma2(Y, NEG, B), dup(0.564f));  // RN(B - Y) * 0.564
+  const f2 dr = mul2(fma2(Y, NEG, R), dup(0.713f));
+  PixelPair o;
+  o.ybits0 = __float_as_uint(yi.x); o.ybits1 = __float_as_uint(yi.y);
+  o.cb0 = __float2int_rz(db.x); o.cb1 = __float2int_rz(db.y);
+  o.cr0 = __float2int_rz(dr.x); o.cr1 = __float2int_rz(dr.y);
+  return o;
+}
+
+// four chroma samples (low bytes of a, b, c, d) -> (uint8_t)(sum of divide_roundnearest(sample + 128, 4))  myyuv_yuv.cpp:114-115
+MYB_D uint32_t chroma_quad(int a, int b, int c, int d) {
+  uint32_t v = __byte_perm(__byte_perm((uint32_t)a, (uint32_t)b, 0x0040), __byte_perm((uint32_t)c, (uint32_t)d, 0x0040), 0x5410);
+  v ^= 0x80808080u;                                                   // + 128 modulo 256 on every byte
+  const uint32_t q = ((v >> 2) & 0x3f3f3f3fu) + ((v >> 1) & 0x01010101u);  // (x + 2) / 4 = x / 4 + bit 1 of x
+  return (q * 0x01010101u) >> 24;                                     // byte sum modulo 256 (pure blue wraps to 0)
 }
 
 __global__ void __launch_bounds__(256) xrgb_to_iyuv_kernel(const uint8_t* __restrict__ bgrx, uint8_t* __restrict__ iyuv,
-                                                            uint32_t w, uint32_t h, int bottom_up, uint32_t n_frames) {
-  const uint32_t qw = w >> 2;                       // 4-pixel groups per row
-  const uint64_t per_frame = (uint64_t)qw * (h >> 1);
-  const uint64_t total = per_frame * n_frames;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
-    const uint32_t f = (uint32_t)(i / per_frame);
-    const uint32_t r = (uint32_t)(i - (uint64_t)f * per_frame);
-    const uint32_t row = (r / qw) * 2, col = (r % qw) * 4;
-    const uint8_t* src = bgrx + (uint64_t)f * w * h * 4;
-    uint8_t* dst = iyuv + (uint64_t)f * w * h * 3 / 2;
+                                                            uint32_t w, uint32_t h, int bottom_up, uint32_t n_frames, float onef) {
+  const f2 ONE = dup(onef);
+  const uint32_t ow = w >> 3;                       // 8-pixel groups per row
+  const uint32_t per_frame = ow * (h >> 1);         // < 2^29: w * h * 4 fits 32 bits (checked by the caller)
+  const uint8_t* src = bgrx + (uint64_t)blockIdx.y * w * h * 4;
+  uint8_t* dst = iyuv + (uint64_t)blockIdx.y * w * h * 3 / 2;
+  // software pipeline: the four loads of the next unit are in flight while the current one is converted
+  auto fetch = [&](uint32_t i, uint4& a0, uint4& a1, uint4& b0, uint4& b1) {
+    const uint32_t rp = i / ow;
+    const uint32_t row = rp * 2, col = (i - rp * ow) * 8;
     const uint32_t fr0 = bottom_up ? (h - 1 - row) : row, fr1 = bottom_up ? (h - 2 - row) : row + 1;
-    const uint4 a = __ldg(reinterpret_cast<const uint4*>(src + ((uint64_t)fr0 * w + col) * 4));
-    const uint4 b = __ldg(reinterpret_cast<const uint4*>(src + ((uint64_t)fr1 * w + col) * 4));
-    uint32_t y0[4], y1[4], cb0[4], cb1[4], cr0[4], cr1[4];
-    pixel_yuv(a.x, y0[0], cb0[0], cr0[0]); pixel_yuv(a.y, y0[1], cb0[1], cr0[1]);
-    pixel_yuv(a.z, y0[2], cb0[2], cr0[2]); pixel_yuv(a.w, y0[3], cb0[3], cr0[3]);
-    pixel_yuv(b.x, y1[0], cb1[0], cr1[0]); pixel_yuv(b.y, y1[1], cb1[1], cr1[1]);
-    pixel_yuv(b.z, y1[2], cb1[2], cr1[2]); pixel_yuv(b.w, y1[3], cb1[3], cr1[3]);
-    // divide_roundnearest(v, 4) on each sample, sum of four stored to uint8_t (wraps) -- myyuv_yuv.cpp:114-115
-    const uint32_t u0 = (((cb0[0] + 2) >> 2) + ((cb0[1] + 2) >> 2) + ((cb1[0] + 2) >> 2) + ((cb1[1] + 2) >> 2)) & 0xff;
-    const uint32_t u1 = (((cb0[2] + 2) >> 2) + ((cb0[3] + 2) >> 2) + ((cb1[2] + 2) >> 2) + ((cb1[3] + 2) >> 2)) & 0xff;
-    const uint32_t v0 = (((cr0[0] + 2) >> 2) + ((cr0[1] + 2) >> 2) + ((cr1[0] + 2) >> 2) + ((cr1[1] + 2) >> 2)) & 0xff;
-    const uint32_t v1 = (((cr0[2] + 2) >> 2) + ((cr0[3] + 2) >> 2) + ((cr1[2] + 2) >> 2) + ((cr1[3] + 2) >> 2)) & 0xff;
-    *reinterpret_cast<uint32_t*>(dst + (uint64_t)row * w + col) = y0[0] | (y0[1] << 8) | (y0[2] << 16) | (y0[3] << 24);
-    *reinterpret_cast<uint32_t*>(dst + (uint64_t)(row + 1) * w + col) = y1[0] | (y1[1] << 8) | (y1[2] << 16) | (y1[3] << 24);
+    const uint4* s0 = reinterpret_cast<const uint4*>(src + ((uint64_t)fr0 * w + col) * 4);
+    const uint4* s1 = reinterpret_cast<const uint4*>(src + ((uint64_t)fr1 * w + col) * 4);
+    a0 = __ldcs(s0); a1 = __ldcs(s0 + 1); b0 = __ldcs(s1); b1 = __ldcs(s1 + 1);
+  };
+  const uint32_t step = gridDim.x * blockDim.x;
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  uint4 n0, n1, m0, m1;
+  if (i < per_frame) fetch(i, n0, n1, m0, m1);
+#pragma unroll 1
+  for (; i < per_frame; i += step) {
+    const uint4 a0 = n0, a1 = n1, b0 = m0, b1 = m1;
+    if (i + step < per_frame) fetch(i + step, n0, n1, m0, m1);
+    const uint32_t rp = i / ow;
+    const uint32_t row = rp * 2, col = (i - rp * ow) * 8;
+    const PixelPair t0 = pixel_pair_yuv(a0.x, a0.y, ONE), t1 = pixel_pair_yuv(a0.z, a0.w, ONE);
+    const PixelPair t2 = pixel_pair_yuv(a1.x, a1.y, ONE), t3 = pixel_pair_yuv(a1.z, a1.w, ONE);
+    const PixelPair u0 = pixel_pair_yuv(b0.x, b0.y, ONE), u1 = pixel_pair_yuv(b0.z, b0.w, ONE);
+    const PixelPair u2 = pixel_pair_yuv(b1.x, b1.y, ONE), u3 = pixel_pair_yuv(b1.z, b1.w, ONE);
+    auto pack4 = [](uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+      return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
+    };
+    uint2 y0, y1;
+    y0.x = pack4(t0.ybits0, t0.ybits1, t1.ybits0, t1.ybits1); y0.y = pack4(t2.ybits0, t2.ybits1, t3.ybits0, t3.ybits1);
+    y1.x = pack4(u0.ybits0, u0.ybits1, u1.ybits0, u1.ybits1); y1.y = pack4(u2.ybits0, u2.ybits1, u3.ybits0, u3.ybits1);
+    const uint32_t uu = chroma_quad(t0.cb0, t0.cb1, u0.cb0, u0.cb1) | (chroma_quad(t1.cb0, t1.cb1, u1.cb0, u1.cb1) << 8) |
+                        (chroma_quad(t2.cb0, t2.cb1, u2.cb0, u2.cb1) << 16) | (chroma_quad(t3.cb0, t3.cb1, u3.cb0, u3.cb1) << 24);
+    const uint32_t vv = chroma_quad(t0.cr0, t0.cr1, u0.cr0, u0.cr1) | (chroma_quad(t1.cr0, t1.cr1, u1.cr0, u1.cr1) << 8) |
+                        (chroma_quad(t2.cr0, t2.cr1, u2.cr0, u2.cr1) << 16) | (chroma_quad(t3.cr0, t3.cr1, u3.cr0, u3.cr1) << 24);
+    *reinterpret_cast<uint2*>(dst + (uint64_t)row * w + col) = y0;
+    *reinterpret_cast<uint2*>(dst + (uint64_t)(row + 1) * w + col) = y1;
     const uint64_t k = ((uint64_t)col + (uint64_t)row * w / 2) / 2;  // myyuv_yuv.cpp:120
-    *reinterpret_cast<uint16_t*>(dst + (uint64_t)w * h + k) = (uint16_t)(u0 | (u1 << 8));
-    *reinterpret_cast<uint16_t*>(dst + (uint64_t)w * h * 5 / 4 + k) = (uint16_t)(v0 | (v1 << 8));
+    *reinterpret_cast<uint32_t*>(dst + (uint64_t)w * h + k) = uu;
+    *reinterpret_cast<uint32_t*>(dst + (uint64_t)w * h * 5 / 4 + k) = vv;
+  }
+}
+
+// Narrow images (width not a multiple of 8): one thread = one 2x2 quad, plain scalar code.
+MYB_D void pixel_yuv(uint32_t px, uint32_t& y, int& cb, int& cr) {
+  const float B = (float)(px & 0xff), G = (float)((px >> 8) & 0xff), R = (float)((px >> 16) & 0xff);
+  const float Y = __fadd_rn(__fadd_rn(__fmul_rn(0.299f, R), __fmul_rn(0.587f, G)), __fmul_rn(0.114f, B));
+  y = (uint32_t)__float2int_rz(Y) & 0xff;
+  cb = __float2int_rz(__fmul_rn(__fsub_rn(B, Y), 0.564f));
+  cr = __float2int_rz(__fmul_rn(__fsub_rn(R, Y), 0.713f));
+}
+
+__global__ void __launch_bounds__(256) xrgb_to_iyuv_quad_kernel(const uint8_t* __restrict__ bgrx, uint8_t* __restrict__ iyuv,
+                                                                 uint32_t w, uint32_t h, int bottom_up, uint32_t n_frames) {
+  const uint32_t qw = w >> 1;
+  const uint32_t per_frame = qw * (h >> 1);
+  const uint8_t* src = bgrx + (uint64_t)blockIdx.y * w * h * 4;
+  uint8_t* dst = iyuv + (uint64_t)blockIdx.y * w * h * 3 / 2;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < per_frame; i += gridDim.x * blockDim.x) {
+    const uint32_t rp = i / qw;
+    const uint32_t row = rp * 2, col = (i - rp * qw) * 2;
+    const uint32_t fr0 = bottom_up ? (h - 1 - row) : row, fr1 = bottom_up ? (h - 2 - row) : row + 1;
+    const uint2 a = *reinterpret_cast<const uint2*>(src + ((uint64_t)fr0 * w + col) * 4);
+    const uint2 b = *reinterpret_cast<const uint2*>(src + ((uint64_t)fr1 * w + col) * 4);
+    uint32_t y00, y01, y10, y11;
+    int cb[4], cr[4];
+    pixel_yuv(a.x, y00, cb[0], cr[0]); pixel_yuv(a.y, y01, cb[1], cr[1]);
+    pixel_yuv(b.x, y10, cb[2], cr[2]); pixel_yuv(b.y, y11, cb[3], cr[3]);
+    *reinterpret_cast<uint16_t*>(dst + (uint64_t)row * w + col) = (uint16_t)(y00 | (y01 << 8));
+    *reinterpret_cast<uint16_t*>(dst + (uint64_t)(row + 1) * w + col) = (uint16_t)(y10 | (y11 << 8));
+    const uint64_t k = ((uint64_t)col + (uint64_t)row * w / 2) / 2;
+    dst[(uint64_t)w * h + k] = (uint8_t)chroma_quad(cb[0], cb[1], cb[2], cb[3]);
+    dst[(uint64_t)w * h * 5 / 4 + k] = (uint8_t)chroma_quad(cr[0], cr[1], cr[2], cr[3]);
   }
 }
 
 void launch_xrgb_to_iyuv(const uint8_t* d_bgrx, uint8_t* d_iyuv, uint32_t w, uint32_t h, int bottom_up, uint32_t n_frames,
                          cudaStream_t s) {
-  const uint64_t total = (uint64_t)(w / 4) * (h / 2) * n_frames;
-  if (total == 0) return;
-  const uint64_t want = (total + 255) / 256;
-  const int grid = (int)(want < 148ull * 32 ? want : 148ull * 32);
-  xrgb_to_iyuv_kernel<<<grid, 256, 0, s>>>(d_bgrx, d_iyuv, w, h, bottom_up, n_frames);
-  g_launches++;
+  int sms = 148;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  // frames along grid.y (at most 65535 per launch), a grid-stride loop over the frame along grid.x
+  for (uint32_t f0 = 0; f0 < n_frames; f0 += 65535u) {
+    const uint32_t nf = n_frames - f0 < 65535u ? n_frames - f0 : 65535u;
+    const uint8_t* in = d_bgrx + (uint64_t)f0 * w * h * 4;
+    uint8_t* out = d_iyuv + (uint64_t)f0 * w * h * 3 / 2;
+    const uint32_t units = (w % 8 == 0 ? w / 8 : w / 2) * (h / 2);
+    if (units == 0) return;
+    const uint32_t want = (units + 255) / 256;
+    const uint32_t cap = ((uint32_t)sms * 16 + nf - 1) / nf;  // about 16 CTAs of 256 threads per SM over the whole launch
+    const dim3 grid(want < cap ? want : (cap ? cap : 1), nf);
+    if (w % 8 == 0) xrgb_to_iyuv_kernel<<<grid, 256, 0, s>>>(in, out, w, h, bottom_up, nf, 1.0f);
+    else xrgb_to_iyuv_quad_kernel<<<grid, 256, 0, s>>>(in, out, w, h, bottom_up, nf);
+    g_launches++;
+  }
 }
 
 // ===================================================================================================
@@ -294,6 +388,8 @@ struct ZSlots {  // slot view of the same column for the general emit code after
 struct EncParams {
   const uint8_t* src;
   uint8_t* out;
+  const uint64_t* base;   // device pointer to the byte position of the batch's first payload in out (nullptr: 0);
+                          // lets a pipeline append the payloads of successive chunks without a host round trip
   uint64_t out_cap;
   FrameGeom g;
   Workspace ws;
@@ -309,7 +405,6 @@ MYB_D constexpr int zigzag_of(int i) {
   return t[i];
 }
 
-MYB_D f2 mkp(float a, float b) { f2 r; r.x = a; r.y = b; return r; }
 
 // Forward DCT + quantisation of one block.  raw: 8 rows x 2 words of pixels.  Writes the 64 coefficients in
 // zigzag order to zcol[i * kTileBlocks]; returns an upper bound (multiple of 8) of the message length.
@@ -587,7 +682,7 @@ __global__ void __launch_bounds__(256) place_tiles_kernel(const __grid_constant_
     const uint32_t total = P.ws.tile_total[tile];
     const u64 src = P.ws.tile_pos[tile];
     const uint32_t fixed = 12 + 8 * (plane + 1) + g.nblk[0] + (plane > 0 ? g.nblk[1] : 0) + (plane > 1 ? g.nblk[2] : 0);
-    const u64 pos = (u64)tc.frame * (36 + g.nblk_frame) + fixed + P.ws.tile_prefix[tile];
+    const u64 pos = (P.base ? *P.base : 0) + (u64)tc.frame * (36 + g.nblk_frame) + fixed + P.ws.tile_prefix[tile];
     if (pos + total > P.out_cap || src + total > P.ws.scratch_cap) {
       if (threadIdx.x == 0) atomicOr(&P.ws.counters[1], kFlagCapacity);
       continue;
@@ -603,10 +698,11 @@ __global__ void __launch_bounds__(256) finalize_frames_kernel(const __grid_const
   const FrameGeom& g = P.g;
   const uint32_t f = blockIdx.x;
   const uint64_t* ps = P.ws.plane_start + (uint64_t)f * 3;
-  const u64 frame_pos = (u64)f * (36 + g.nblk_frame) + ps[0];
-  const u64 next_pos = (u64)(f + 1) * (36 + g.nblk_frame) + ps[3];
+  const u64 base = P.base ? *P.base : 0;
+  const u64 frame_pos = base + (u64)f * (36 + g.nblk_frame) + ps[0];
+  const u64 next_pos = base + (u64)(f + 1) * (36 + g.nblk_frame) + ps[3];
   if (blockIdx.y == 0 && threadIdx.x == 0) {
-    offsets[f] = frame_pos;
+    if (!(P.base && f == 0)) offsets[f] = frame_pos;  // a chained launch reads offsets[0] (= *P.base), it does not write it
     if (f == g.n_frames - 1) offsets[f + 1] = next_pos;
   }
   if (next_pos > P.out_cap) {
@@ -957,9 +1053,9 @@ __global__ void __launch_bounds__(kCtaThreads, 5)
 // launchers
 // ===================================================================================================
 void launch_compress(const uint8_t* d_iyuv, const FrameGeom& g, const QTables& qt, uint8_t* d_out, uint64_t out_cap,
-                     uint64_t* d_offsets, const Workspace& ws, cudaStream_t s) {
+                     uint64_t* d_offsets, const uint64_t* d_base, const Workspace& ws, cudaStream_t s) {
   EncParams P;
-  P.src = d_iyuv; P.out = d_out; P.out_cap = out_cap; P.g = g; P.ws = ws;
+  P.src = d_iyuv; P.out = d_out; P.base = d_base; P.out_cap = out_cap; P.g = g; P.ws = ws;
   P.total_tiles = g.tiles_per_frame * g.n_frames;
   P.one = 1.0f;
   static bool attr_set = false;
