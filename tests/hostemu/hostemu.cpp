@@ -106,15 +106,30 @@ int hostemu_encode_blocks(const int16_t* coef, uint32_t n, int stride, int mode,
                                                                                   : encode_blocks<1>(coef, n, mode, out, sizes);
 }
 
-int hostemu_decode_blocks(const uint8_t* chunks, const uint8_t* sizes, uint32_t n, int16_t* coef) {
+// mode 0: the general decoder; mode 1: the kernel's flow (fast decoder, general decoder when it declines).
+// Returns 0, or 1 + index of the first block with an error; *fast_used counts blocks the fast decoder handled.
+int hostemu_decode_blocks2(const uint8_t* chunks, const uint8_t* sizes, uint32_t n, int mode, int16_t* coef, uint32_t* fast_used) {
+  int16_t symtab[16], base[8];
+  DecScratch<1> D{symtab, base};
+  uint32_t used = 0;
   for (uint32_t b = 0; b < n; b++) {
     int16_t* c = coef + 64 * (size_t)b;
     memset(c, 0, 128);
-    const int err = huff_decode_block(chunks, sizes[b], [&](int j, int v) { c[kZigzag[j]] = (int16_t)v; }, NoWarp{});
+    auto emit = [&](int j, int v) { c[kZigzag[j]] = (int16_t)v; };
+    int err = 2;
+    int ne = 0;
+    if (mode == 1) err = huff_decode_fast(chunks, sizes[b], D, emit, &ne, NoWarp{});
+    if (err == 2) err = huff_decode_block(chunks, sizes[b], emit, NoWarp{});
+    else used++;
     if (err) return (int)b + 1;
     chunks += sizes[b];
   }
+  if (fast_used) *fast_used = used;
   return 0;
+}
+
+int hostemu_decode_blocks(const uint8_t* chunks, const uint8_t* sizes, uint32_t n, int16_t* coef) {
+  return hostemu_decode_blocks2(chunks, sizes, n, 0, coef, nullptr);
 }
 
 // kernels.cu fdct_quant_pair: q1 = fma(fma(-q, y*r, y), r, y*r) with r = RN(1/q) must equal RN(y/q)

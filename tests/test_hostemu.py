@@ -18,6 +18,7 @@ def emu():
     L = C.CDLL(str(HERE / "libhostemu.so"))
     L.hostemu_encode_blocks.argtypes = [i16p, C.c_uint32, C.c_int, C.c_int, u8p, u8p]
     L.hostemu_decode_blocks.argtypes = [u8p, u8p, C.c_uint32, i16p]
+    L.hostemu_decode_blocks2.argtypes = [u8p, u8p, C.c_uint32, C.c_int, i16p, C.POINTER(C.c_uint32)]
     L.hostemu_division_check.argtypes = [C.c_uint32, C.c_uint32]
     L.hostemu_division_check.restype = C.c_uint64
     L.hostemu_round_check.argtypes = [C.c_uint32, C.c_uint32]
@@ -80,6 +81,12 @@ def test_block_coder_matches_oracle(emu, ora, kind, n, stride, fast):
     dec = np.empty((n, 64), np.int16)
     rc = emu.hostemu_decode_blocks(want_c.ctypes.data_as(u8p), want_s.ctypes.data_as(u8p), n, dec.ctypes.data_as(i16p))
     assert rc == 0 and np.array_equal(dec, b)
+    dec2 = np.empty((n, 64), np.int16)
+    used = C.c_uint32(0)
+    rc = emu.hostemu_decode_blocks2(want_c.ctypes.data_as(u8p), want_s.ctypes.data_as(u8p), n, 1, dec2.ctypes.data_as(i16p), C.byref(used))
+    assert rc == 0 and np.array_equal(dec2, b)
+    if kind in ("sparse", "small", "few", "zeros"):
+        assert used.value > n // 2  # the fast decoder really ran
 
 
 def test_decoder_rejects_truncated_stream(emu, ora):
@@ -90,6 +97,28 @@ def test_decoder_rejects_truncated_stream(emu, ora):
     bad[1] = 0x01  # 511 code bits in a chunk that holds far fewer
     dec = np.empty((4, 64), np.int16)
     assert emu.hostemu_decode_blocks(bad.ctypes.data_as(u8p), s.ctypes.data_as(u8p), 4, dec.ctypes.data_as(i16p)) == 1
+    assert emu.hostemu_decode_blocks2(bad.ctypes.data_as(u8p), s.ctypes.data_as(u8p), 4, 1, dec.ctypes.data_as(i16p), None) == 1
+
+
+def test_fast_and_general_decoder_agree_on_damaged_chunks(emu, ora):
+    """Flip bytes of valid chunks: both decoders must report an error for the same blocks and produce the same
+    coefficients for the blocks they accept (the fast one declines what it cannot reproduce)."""
+    rng = np.random.default_rng(7)
+    b = make_blocks("few", 3000, rng)
+    c, s = ora.huff_encode_blocks(b)
+    off = np.concatenate([[0], np.cumsum(s, dtype=np.int64)])
+    bad = c.copy()
+    for i in range(len(s)):
+        k = rng.integers(0, s[i])
+        bad[off[i] + k] ^= 1 << rng.integers(0, 8)
+    for i in range(len(s)):
+        one, sz = bad[off[i]: off[i + 1]].copy(), s[i: i + 1].copy()
+        d0, d1 = np.zeros((1, 64), np.int16), np.zeros((1, 64), np.int16)
+        r0 = emu.hostemu_decode_blocks2(one.ctypes.data_as(u8p), sz.ctypes.data_as(u8p), 1, 0, d0.ctypes.data_as(i16p), None)
+        r1 = emu.hostemu_decode_blocks2(one.ctypes.data_as(u8p), sz.ctypes.data_as(u8p), 1, 1, d1.ctypes.data_as(i16p), None)
+        assert r0 == r1, i
+        if r0 == 0:
+            assert np.array_equal(d0, d1), i
 
 
 def test_exact_division_identity(emu):

@@ -980,4 +980,149 @@ MYB_HD int huff_decode_block(const uint8_t* chunk, int size, Emit&& emit, const 
   return err;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Fast decoder for the chunks the reference writes for blocks with at most 15 distinct symbols: one group per code
+// length, lengths strictly increasing, a prefix code that is not over-subscribed.  Anything else (and every
+// malformed table) is handed to huff_decode_block, which follows the reference's decoder step by step.
+//  * the code table is unpacked once into an array of symbols in canonical order;
+//  * a code is decoded without a bit loop: the next 8 stream bits, MSB first, are compared with the left-aligned
+//    end of every length's code range (lim[l] = (first_l + count_l) << (8 - l), non-decreasing in l), the number of
+//    ranges passed is the length, and the symbol index is  code + (symbols before this length - first code);
+//  * the stream is read through a 32-bit window that is reloaded only after 24 consumed bits.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kDecFastSyms = 15;
+template <int STRIDE>
+struct DecScratch {
+  int16_t* symtab;  // [16] symbols in canonical order
+  int16_t* base;    // [8]  index of the first symbol of length l+1 minus its first code
+  MYB_HD int16_t& sym(int k) const { return symtab[k * STRIDE]; }
+  MYB_HD int16_t& bs(int l) const { return base[l * STRIDE]; }
+};
+
+MYB_HD uint32_t load_window(const uint8_t* data, int byte0, int data_bytes) {
+  uint32_t w = 0;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int t = 0; t < 4; t++)
+    if (byte0 + t < data_bytes) w |= (uint32_t)data[byte0 + t] << (8 * t);
+  return w;
+}
+
+// Returns 0 (ok), 1 (error: the conditions huff_decode_block reports) or 2 (not handled here, nothing emitted).
+template <int STRIDE, class Emit, class W>
+MYB_HD int huff_decode_fast(const uint8_t* chunk, int size, const DecScratch<STRIDE>& D, Emit&& emit, int* n_emitted, const W& warp) {
+  int err = 0;
+  int bits = 0, table_bytes = 0;
+  if (size >= 3) {
+    bits = chunk[0] | (chunk[1] << 8);
+    table_bytes = chunk[2];
+    if (bits > 512 || 3 + table_bytes + ((bits + 7) >> 3) > size) err = 1;
+  } else if (size > 0) {
+    err = 1;
+  }
+  if (err || size == 0) { bits = 0; table_bytes = 0; }
+  const uint8_t* groups = chunk + 3;
+  // ---- pass 1: one table symbol per step (Huffman.cpp:258-266, :54-69)
+  bool general = false;
+  uint32_t cnts = 0;  // symbols per length, 4-bit fields
+  int n = 0;
+  {
+    int gi = 0, ci = 0, cnt = 0, glen = 0, symbase = 0;
+    while (warp.any(!err && !general && (ci < cnt || gi < table_bytes))) {
+      if (!err && !general && (ci < cnt || gi < table_bytes)) {
+        if (ci == cnt) {  // next group
+          const int info = groups[gi];
+          const int len = (info >> 5) + 1, c = (info & 31) + 1;
+          if (len <= glen || n + c > kDecFastSyms) {
+            general = true;
+          } else {
+            glen = len;
+            cnt = c;
+            ci = 0;
+            symbase = gi + 1;
+            gi += 1 + ((c * 11 + 7) >> 3);
+            if (gi > table_bytes) err = 1;
+            cnts += (uint32_t)c << (4 * (len - 1));
+          }
+        }
+        if (!err && !general) {
+          const int bit = ci * 11, byte = symbase + (bit >> 3);
+          uint32_t t = groups[byte] | ((uint32_t)groups[byte + 1] << 8);
+          if ((bit & 7) > 5) t |= (uint32_t)groups[byte + 2] << 16;
+          t = (t >> (bit & 7)) & 0x7ffu;
+          D.sym(n) = (int16_t)((t >= 1024u) ? (int)t - 2048 : (int)t);
+          n++;
+          ci++;
+        }
+      }
+    }
+  }
+  // ---- pass 2: code ranges.  k[l] = 256 - lim[l] with lim[l] = (first_l + count_l) << (7 - l) the left-aligned end of the
+  // codes of length l + 1, so that  (r + k[l]) >> 8 == (r >= lim[l])  for an 8-bit r; two lengths share a register.
+  // Lengths past the longest one get k = 0 (never passed), so an unassigned code shows up as length maxlen + 1.
+  uint32_t kk[4] = {0, 0, 0, 0};
+  int maxlen = 0;
+  {
+    uint32_t first = 0, off = 0;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int l = 0; l < 8; l++) {
+      const uint32_t c = (cnts >> (4 * l)) & 15u;
+      D.bs(l) = (int16_t)((int)off - (int)first);
+      const uint32_t end = first + c;
+      if (end > (2u << l)) general = true;  // more codes of this length than exist: let the general decoder reproduce the reference
+      if (c) maxlen = l + 1;
+      first = end << 1;
+      off += c;
+    }
+    first = 0;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int l = 0; l < 8; l++) {
+      const uint32_t c = (cnts >> (4 * l)) & 15u;
+      const uint32_t end = first + c;
+      const uint32_t k = l < maxlen ? 256u - ((end << (7 - l)) & 0x1ffu) : 0u;
+      kk[l >> 1] |= k << (16 * (l & 1));
+      first = end << 1;
+    }
+  }
+  if (err || general) bits = 0;  // such lanes idle through the lockstep loop below (no early return: the warp stays converged)
+  const int maxlw = warp.max(maxlen);
+  const uint8_t* data = groups + table_bytes;
+  const int data_bytes = (bits + 7) >> 3;
+  // ---- code stream (Huffman.cpp:106-154).  rwin: 32 stream bits starting at bit pw, the first one in bit 31.
+  int p = 0, j = 0, pw = 0;
+  uint32_t rwin = bit_reverse32(load_window(data, 0, data_bytes));
+  while (warp.any(p < bits && j < 64)) {
+    if (p < bits && j < 64) {
+      if (p - pw > 24) {
+        pw = p & ~7;
+        rwin = bit_reverse32(load_window(data, pw >> 3, data_bytes));
+      }
+      const uint32_t r = (rwin << (p - pw)) >> 24;  // next 8 bits, first stream bit on top
+      const uint32_t r2 = r * 0x10001u;
+      uint32_t acc = (r2 + kk[0]) & 0x01000100u;
+      if (maxlw > 2) acc += (r2 + kk[1]) & 0x01000100u;
+      if (maxlw > 4) acc += (r2 + kk[2]) & 0x01000100u;
+      if (maxlw > 6) acc += (r2 + kk[3]) & 0x01000100u;
+      const int len = 1 + (int)((acc >> 8) & 7u) + (int)(acc >> 24);
+      if (len > maxlen || p + len > bits) {
+        err = 1;  // "Huffman unknown symbol" :139, or the stream ends inside a code: "Huffman bad code" :120-122
+        bits = 0;
+      } else {
+        const int idx = (int)(r >> (8 - len)) + D.bs(len - 1);
+        emit(j, (int)D.sym(idx));
+        j++;
+        p += len;
+      }
+    }
+    warp.sync();
+  }
+  *n_emitted = j;
+  return err ? 1 : (general ? 2 : 0);
+}
+
 }  // namespace myyuvb

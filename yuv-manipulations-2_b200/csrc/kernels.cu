@@ -756,8 +756,9 @@ constexpr int kDecStageBytes = 4 * 1024;
 struct DecSmem {
   float coef[64][kTileBlocks];        // dequantised coefficients B[k][c] (row-major index), per block column
   alignas(16) uint8_t stage[kDecStageBytes];  // the tile's chunk bytes
-  uint8_t zigzag[64];
-  float q[64];
+  int16_t symtab[16][kTileBlocks];    // fast decoder: the block's symbols in canonical order
+  int16_t lenbase[8][kTileBlocks];    // fast decoder: symbol index offsets per code length
+  uint2 zq[64];                       // per zigzag position: {dequantisation factor (float bits), byte offset in a coef column}
   uint32_t warp_sums[4];
   uint32_t tile;
   u64 base;
@@ -952,10 +953,6 @@ __global__ void __launch_bounds__(kCtaThreads, 5)
   DecSmem& sm = *reinterpret_cast<DecSmem*>(smem_raw);
   const int tid = threadIdx.x;
   const FrameGeom& g = P.g;
-  if (tid < 64) {
-    constexpr uint8_t zz[64] = {MYB_ZIGZAG_LIST};
-    sm.zigzag[tid] = zz[tid];
-  }
   int q_plane = -1;
   float* const col = &sm.coef[0][tid];
 
@@ -969,8 +966,12 @@ __global__ void __launch_bounds__(kCtaThreads, 5)
     const int plane = (int)tc.plane;
     const PlaneDesc d = reinterpret_cast<const PlaneDesc*>(P.ws.plane_desc)[(uint64_t)tc.frame * 3 + plane];
     if (!d.ok) continue;  // header error already flagged by parse_payload_kernel (uniform per CTA)
-    if (q_plane != plane) {
-      if (tid < 64) sm.q[tid] = qt.q[plane][tid];
+    if (q_plane != plane) {  // visible to all threads after the barriers of the size scan below
+      if (tid < 64) {
+        constexpr uint8_t zz[64] = {MYB_ZIGZAG_LIST};
+        const int pos = zz[tid];
+        sm.zq[tid] = make_uint2(__float_as_uint(qt.q[plane][pos]), (uint32_t)pos * kTileBlocks * 4u);
+      }
       q_plane = plane;
     }
     const bool live = (uint32_t)tid < tc.nblk;
@@ -1001,11 +1002,17 @@ __global__ void __launch_bounds__(kCtaThreads, 5)
     int nsym = 0;  // decoded zigzag positions: the non-zero coefficients lie in positions [0, nsym)
     {
       const uint8_t* chunk = (off + size <= (uint32_t)kDecStageBytes) ? &sm.stage[off] : content + off;
-      const int err = huff_decode_block(chunk, (int)size, [&](int j, int v) {
-        const int pos = sm.zigzag[j];
-        col[pos * kTileBlocks] = __fmul_rn((float)v, sm.q[pos]);  // DCT.cpp:330-332
-        nsym = j + 1;
-      }, WarpLockstep{});
+      auto emit = [&](int j, int v) {
+        const uint2 e = sm.zq[j];
+        *reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(col) + e.y) = __fmul_rn((float)v, __uint_as_float(e.x));  // DCT.cpp:330-332
+      };
+      const DecScratch<kTileBlocks> ds{&sm.symtab[0][tid], &sm.lenbase[0][tid]};
+      int err = huff_decode_fast(chunk, (int)size, ds, emit, &nsym, WarpLockstep{});
+      if (__any_sync(0xffffffffu, err == 2)) {  // a table the fast decoder does not take: the step-by-step decoder, for those lanes
+        int cnt = 0;
+        const int e2 = huff_decode_block(chunk, err == 2 ? (int)size : 0, [&](int j, int v) { emit(j, v); cnt = j + 1; }, WarpLockstep{});
+        if (err == 2) { err = e2; nsym = cnt; }
+      }
       if (mine && (err || size == 0)) atomicOr(&P.ws.counters[1], kFlagHuffman);  // a chunk is at least 7 bytes
     }
     __syncwarp();
