@@ -755,7 +755,7 @@ int codec_grid_size(int device, bool encoder) {
 constexpr int kDecStageBytes = 4 * 1024;
 struct DecSmem {
   float coef[64][kTileBlocks];        // dequantised coefficients B[k][c] (row-major index), per block column
-  alignas(16) uint8_t stage[kDecStageBytes];  // the tile's chunk bytes
+  alignas(16) uint8_t stage[kDecStageBytes + 16];  // the tile's chunk bytes, shifted by the source's offset in its 16-byte line
   int16_t symtab[16][kTileBlocks];    // fast decoder: the block's symbols in canonical order
   int16_t lenbase[8][kTileBlocks];    // fast decoder: symbol index offsets per code length
   uint2 zq[64];                       // per zigzag position: {dequantisation factor (float bits), byte offset in a coef column}
@@ -979,19 +979,27 @@ __global__ void __launch_bounds__(kCtaThreads, 5)
     // the pre-passes (dec_tile_totals_kernel, dec_scan_planes_kernel), so no CTA waits for another one
     const uint32_t size = live ? (uint32_t)P.payloads[d.sizes_off + tc.k0 + tid] : 0u;
     const u64 base = P.ws.tile_prefix[tile];
-    uint32_t total;
-    const uint32_t off = cta_exclusive_scan(size, sm.warp_sums, &total);
+    const uint32_t total = P.ws.tile_total[tile];  // = the sum of the sizes above (dec_tile_totals_kernel)
     if (base + total > d.content_size) {  // chunks must lie inside content[] (undefined behaviour in the reference)
       if (tid == 0) atomicOr(&P.ws.counters[1], kFlagHuffman);
       continue;
     }
-    // stage the tile's chunk bytes in shared memory (coalesced byte loads; the global offset is arbitrary) and
-    // zero this thread's coefficient column while they are in flight
+    // stage the tile's chunk bytes in shared memory with 128-bit loads: the copy keeps the source's offset inside its
+    // 16-byte line (the first vector may start in the size array that precedes content[], the ragged end is copied
+    // bytewise so nothing past the tile is read).  The loads are in flight during the size scan and the zero fill.
     const uint8_t* content = P.payloads + d.content_off + base;
+    const uint32_t mis = (uint32_t)((uintptr_t)content & 15u);
     {
       const uint32_t n = total < (uint32_t)kDecStageBytes ? total : (uint32_t)kDecStageBytes;
-      for (uint32_t i = tid; i < n; i += kCtaThreads) sm.stage[i] = __ldg(content + i);
+      const uint32_t full = (mis + n) >> 4;  // whole 16-byte vectors
+      const uint4* src = reinterpret_cast<const uint4*>(content - mis);
+      uint4* dst = reinterpret_cast<uint4*>(sm.stage);
+      for (uint32_t v = tid; v < full; v += kCtaThreads) dst[v] = __ldg(src + v);
+      const uint32_t done = full << 4;  // bytes of stage[] filled so far (counted from the aligned start)
+      if (tid < mis + n - done) sm.stage[done + tid] = __ldg(content - mis + done + tid);
     }
+    uint32_t scanned;
+    const uint32_t off = cta_exclusive_scan(size, sm.warp_sums, &scanned);
 #pragma unroll
     for (int i = 0; i < 64; i++) col[i * kTileBlocks] = 0.0f;
     __syncthreads();
@@ -1001,7 +1009,7 @@ __global__ void __launch_bounds__(kCtaThreads, 5)
     const bool mine = live;
     int nsym = 0;  // decoded zigzag positions: the non-zero coefficients lie in positions [0, nsym)
     {
-      const uint8_t* chunk = (off + size <= (uint32_t)kDecStageBytes) ? &sm.stage[off] : content + off;
+      const uint8_t* chunk = (off + size <= (uint32_t)kDecStageBytes) ? &sm.stage[mis + off] : content + off;
       auto emit = [&](int j, int v) {
         const uint2 e = sm.zq[j];
         *reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(col) + e.y) = __fmul_rn((float)v, __uint_as_float(e.x));  // DCT.cpp:330-332
