@@ -742,28 +742,30 @@ __global__ void __launch_bounds__(256) finalize_frames_kernel(const __grid_const
   copy_global_to_global(out + ppos + 8 + i0, P.ws.chunk_sizes + sidx + i0, cnt, 256);
 }
 
+constexpr int kEncCtasPerSm = 5, kDecCtasPerSm = 6;  // resident CTAs per SM (registers and shared memory sized for it)
 int codec_grid_size(int device, bool encoder) {
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-  (void)encoder;
-  return sms * 5;
+  return sms * (encoder ? kEncCtasPerSm : kDecCtasPerSm);
 }
 
 // ===================================================================================================
-// Decompression (one thread = one block; tile = 128 blocks; five CTAs per SM)
+// Decompression (one thread = one block; tile = 128 blocks; six CTAs per SM: 80 registers, 27 KB shared memory)
 // ===================================================================================================
 constexpr int kDecStageBytes = 4 * 1024;
 struct DecSmem {
-  float coef[64][kTileBlocks];        // dequantised coefficients B[k][c] (row-major index), per block column
+  int16_t coef[64][kTileBlocks];      // quantised coefficients [k][c] (row-major index), per block column; the
+                                      // dequantisation (coef * q, DCT.cpp:330-332) happens when the IDCT loads them
   alignas(16) uint8_t stage[kDecStageBytes + 16];  // the tile's chunk bytes, shifted by the source's offset in its 16-byte line
   int16_t symtab[16][kTileBlocks];    // fast decoder: the block's symbols in canonical order
   int16_t lenbase[8][kTileBlocks];    // fast decoder: symbol index offsets per code length
-  uint2 zq[64];                       // per zigzag position: {dequantisation factor (float bits), byte offset in a coef column}
+  float q[64];                        // dequantisation factors of the current plane, row-major
+  uint16_t zoff[64];                  // per zigzag position: byte offset in a coef column
   uint32_t warp_sums[4];
   uint32_t tile;
   u64 base;
 };
-static_assert(sizeof(DecSmem) <= 44 * 1024 + 256, "DecSmem must allow 5 CTAs per SM");
+static_assert(sizeof(DecSmem) <= 36 * 1024, "DecSmem must allow 6 CTAs per SM");
 
 struct DecParams {
   const uint8_t* payloads;
@@ -808,14 +810,14 @@ __global__ void parse_payload_kernel(const __grid_constant__ DecParams P) {
 //   D = C^T . B :  (D[a][c], D[a+1][c]) = sum_k (C[k][a], C[k][a+1]) * B[k][c]       (DCT.cpp:256-266)
 //   P = D . C   :  (P[a][b], P[a+1][b]) = sum_k (D[a][k], D[a+1][k]) * C[k][b]       (DCT.cpp:232-242)
 // followed by round, +128, clamp (DCT.cpp:360).  out[r] = 8 pixels of row r as two words.
-MYB_D void idct_block(const float* col, float onef, uint32_t (&out)[16]) {
+MYB_D void idct_block(const int16_t* col, const float* q, float onef, uint32_t (&out)[16]) {
   const f2 ONE = dup(onef);
   f2 d[32];  // d[a2 * 8 + c] = (D[2 a2][c], D[2 a2 + 1][c])
 #pragma unroll
   for (int c = 0; c < 8; c++) {
     float bk[8];
 #pragma unroll
-    for (int k = 0; k < 8; k++) bk[k] = col[(k * 8 + c) * kTileBlocks];
+    for (int k = 0; k < 8; k++) bk[k] = __fmul_rn((float)col[(k * 8 + c) * kTileBlocks], q[k * 8 + c]);
 #pragma unroll
     for (int a2 = 0; a2 < 4; a2++) {
       f2 acc = mul2(dup(bk[0]), mkp(dct_c(2 * a2), dct_c(2 * a2 + 1)));
@@ -849,14 +851,14 @@ MYB_D void idct_block(const float* col, float onef, uint32_t (&out)[16]) {
 // k >= K - c of column c in the first product and the terms k >= K of the second gives bit-identical pixels:
 // K = 4 needs 288 packed instructions instead of 960, K = 6 needs 496.
 template <int K>
-MYB_D void idct_block_tri(const float* col, float onef, uint32_t (&out)[16]) {
+MYB_D void idct_block_tri(const int16_t* col, const float* q, float onef, uint32_t (&out)[16]) {
   const f2 ONE = dup(onef);
   f2 d[4 * K];  // d[a2 * K + c] = (D[2 a2][c], D[2 a2 + 1][c]), c < K
 #pragma unroll
   for (int c = 0; c < K; c++) {
     float bk[K];
 #pragma unroll
-    for (int k = 0; k < K - c; k++) bk[k] = col[(k * 8 + c) * kTileBlocks];
+    for (int k = 0; k < K - c; k++) bk[k] = __fmul_rn((float)col[(k * 8 + c) * kTileBlocks], q[k * 8 + c]);
 #pragma unroll
     for (int a2 = 0; a2 < 4; a2++) {
       f2 acc = mul2(dup(bk[0]), mkp(dct_c(2 * a2), dct_c(2 * a2 + 1)));
@@ -947,14 +949,14 @@ __global__ void __launch_bounds__(1024) dec_scan_planes_kernel(const __grid_cons
   }
 }
 
-__global__ void __launch_bounds__(kCtaThreads, 5)
+__global__ void __launch_bounds__(kCtaThreads, 6)
     dct_decompress_kernel(const __grid_constant__ DecParams P, const __grid_constant__ QTables qt) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   DecSmem& sm = *reinterpret_cast<DecSmem*>(smem_raw);
   const int tid = threadIdx.x;
   const FrameGeom& g = P.g;
   int q_plane = -1;
-  float* const col = &sm.coef[0][tid];
+  int16_t* const col = &sm.coef[0][tid];
 
   while (true) {
     __syncthreads();  // previous tile done with shared memory (and zigzag table visible)
@@ -970,7 +972,8 @@ __global__ void __launch_bounds__(kCtaThreads, 5)
       if (tid < 64) {
         constexpr uint8_t zz[64] = {MYB_ZIGZAG_LIST};
         const int pos = zz[tid];
-        sm.zq[tid] = make_uint2(__float_as_uint(qt.q[plane][pos]), (uint32_t)pos * kTileBlocks * 4u);
+        sm.zoff[tid] = (uint16_t)(pos * kTileBlocks * 2);
+        sm.q[tid] = qt.q[plane][tid];
       }
       q_plane = plane;
     }
@@ -1001,7 +1004,7 @@ __global__ void __launch_bounds__(kCtaThreads, 5)
     uint32_t scanned;
     const uint32_t off = cta_exclusive_scan(size, sm.warp_sums, &scanned);
 #pragma unroll
-    for (int i = 0; i < 64; i++) col[i * kTileBlocks] = 0.0f;
+    for (int i = 0; i < 64; i++) col[i * kTileBlocks] = 0;
     __syncthreads();
 
     // ---- phase 1: canonical Huffman decode + dequantise into the thread's shared-memory column (warp lockstep) ----
@@ -1011,8 +1014,7 @@ __global__ void __launch_bounds__(kCtaThreads, 5)
     {
       const uint8_t* chunk = (off + size <= (uint32_t)kDecStageBytes) ? &sm.stage[mis + off] : content + off;
       auto emit = [&](int j, int v) {
-        const uint2 e = sm.zq[j];
-        *reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(col) + e.y) = __fmul_rn((float)v, __uint_as_float(e.x));  // DCT.cpp:330-332
+        *reinterpret_cast<int16_t*>(reinterpret_cast<uint8_t*>(col) + sm.zoff[j]) = (int16_t)v;
       };
       const DecScratch<kTileBlocks> ds{&sm.symtab[0][tid], &sm.lenbase[0][tid]};
       int err = huff_decode_fast(chunk, (int)size, ds, emit, &nsym, WarpLockstep{});
@@ -1032,25 +1034,25 @@ __global__ void __launch_bounds__(kCtaThreads, 5)
       if (nmax <= 1) {
         // DC only: D[a][0] = C[0][a] * B00 and P[a][b] = D[a][0] * C[0][b] with all C[0][.] equal -> a flat block
         const float c0 = dct_c(0);
-        const float pv = __fmul_rn(__fmul_rn(c0, col[0]), c0);
+        const float pv = __fmul_rn(__fmul_rn(c0, __fmul_rn((float)col[0], sm.q[0])), c0);
         const float t = __fadd_rz(pv, __int_as_float((__float_as_int(pv) & 0x80000000) | 0x3f000000));
         const uint32_t px = (uint32_t)__viaddmin_s32_relu(__float2int_rz(t), 128, 255) * 0x01010101u;
 #pragma unroll
         for (int r = 0; r < 16; r++) outw[r] = px;
       } else if (nmax <= 3) {
-        idct_block_tri<2>(col, P.one, outw);
+        idct_block_tri<2>(col, sm.q, P.one, outw);
       } else if (nmax <= 6) {
-        idct_block_tri<3>(col, P.one, outw);
+        idct_block_tri<3>(col, sm.q, P.one, outw);
       } else if (nmax <= 10) {
-        idct_block_tri<4>(col, P.one, outw);
+        idct_block_tri<4>(col, sm.q, P.one, outw);
       } else if (nmax <= 15) {
-        idct_block_tri<5>(col, P.one, outw);
+        idct_block_tri<5>(col, sm.q, P.one, outw);
       } else if (nmax <= 21) {
-        idct_block_tri<6>(col, P.one, outw);
+        idct_block_tri<6>(col, sm.q, P.one, outw);
       } else if (nmax <= 28) {
-        idct_block_tri<7>(col, P.one, outw);
+        idct_block_tri<7>(col, sm.q, P.one, outw);
       } else {
-        idct_block(col, P.one, outw);
+        idct_block(col, sm.q, P.one, outw);
       }
       if (mine) {
         const uint32_t pw = g.pw[plane], bw = g.bw[plane];
