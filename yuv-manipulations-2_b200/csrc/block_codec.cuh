@@ -502,7 +502,7 @@ struct Fast8Scratch {
   MYB_HD uint16_t& heap(int i) const { return ht[i * STRIDE]; }
   MYB_HD uint16_t& code(int s) const { return ht[(8 + s) * STRIDE]; }
 };
-constexpr int kHistCap = 15;  // distinct symbols huff_hist accepts (the capacity of the general shared-memory scratch)
+constexpr int kHistCap = 11;  // distinct symbols huff_hist accepts (the capacity of the general shared-memory scratch)
 
 // Histogram of the message z[0 .. L) in first-occurrence order.  Z here is an accessor of raw 16-bit words:
 // raw(i) / setraw(i, w).  A coefficient needs 11 bits, so the slot of its value is written into bits 11..14 of
@@ -548,18 +548,25 @@ MYB_HD int huff_hist(Z& z, int L, bool live, const Fast8Scratch<STRIDE>& F, cons
 }
 
 // Hand the histogram over to the general code (huff_plan_tail) when a warp holds a block with more than 8 symbols.
+// The two scratch layouts may share memory, so every slot word is read into registers before anything is written.
 template <int STRIDE, int CAP, int GSTRIDE, class W>
 MYB_HD int hist_to_general(int n, const Fast8Scratch<STRIDE>& F, const HuffScratch<CAP, GSTRIDE>& S, const W& warp) {
+  static_assert(CAP >= kHistCap, "the general scratch must hold what the histogram accepts");
+  uint32_t w[kHistCap];
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int k = 0; k < kHistCap; k++) w[k] = k < n ? F.slot(k) : 0u;
+  warp.sync();
   int zero_slot = -1;
-  const int nn = n > 0 ? n : 0;
-  const int nw = warp.max(nn);
-  MYB_NOUNROLL
-  for (int k = 0; k < nw; k++) {
-    if (k < nn) {
-      const uint32_t w = F.slot(k);
-      const int v = (int)(int16_t)(w >> 16);
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int k = 0; k < kHistCap; k++) {
+    if (k < n) {
+      const int v = (int)(int16_t)(w[k] >> 16);
       S.sym(k) = (int16_t)v;
-      S.at(S.kCnt, k) = (uint8_t)(w & 0xffu);
+      S.at(S.kCnt, k) = (uint8_t)(w[k] & 0xffu);
       if (v == 0) zero_slot = k;
     }
   }

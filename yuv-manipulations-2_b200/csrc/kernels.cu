@@ -339,26 +339,26 @@ void launch_xrgb_to_iyuv(const uint8_t* d_bgrx, uint8_t* d_iyuv, uint32_t w, uin
 
 // ===================================================================================================
 // Compression
-// One thread = one 8x8 block for both phases (tile = 128 blocks = 128 threads), sized so that five CTAs
-// (20 warps) fit an SM: <= 102 registers, <= 44 KB shared memory.
+// One thread = one 8x8 block for both phases (tile = 128 blocks = 128 threads), sized so that six CTAs
+// (24 warps) fit an SM: 80 registers (a handful of spills in the DCT), <= 36.5 KB shared memory.
 // The DCT is packed along the ROW-PAIR axis: lane .x = row a, lane .y = row a+1 of the same block.
 //   stage 1:  (T[a][c], T[a+1][c]) = sum_k (C[a][k], C[a+1][k]) * X[k][c]      scalar register broadcast x constant pair
 //   stage 2:  (Y[a][b], Y[a+1][b]) = sum_k (T[a][k], T[a+1][k]) * C[b][k]      data pair x broadcast immediate
 // so no transposition or register shuffling is needed between the stages (cuobjdump: 960 FMUL2/FFMA2, 0 MOV).
 // ===================================================================================================
-constexpr int kStageBytes = 4 * 1024;                  // shared-memory staging of one tile's chunk bytes
-constexpr int kFastSyms = 15;                          // distinct symbols handled with shared-memory scratch
-// Entropy-coder scratch is one region per WARP, lanes interleaved (stride 32): the 8-symbol fast path and the general
-// code lay different element widths over the same bytes, which is safe because a warp runs one of them at a time.
-//   [0, 1024)     general: symbols  int16[16][32]
-//   [1024, 5920)  general: byte arrays uint8[153][32]  (first 16 rows = counts)
-//   [1536, 3584)  fast:    slot words uint32[16][32]   (dead before the general code writes its lists)
-//   [3584, 5632)  fast:    hash table uint16[32][32], later heap and code table
+constexpr int kStageBytes = 3 * 1024;                  // shared-memory staging of one tile's chunk bytes
+constexpr int kFastSyms = kHistCap;                    // distinct symbols handled with shared-memory scratch
+// Entropy-coder scratch is one region per WARP, lanes interleaved (stride 32).  The 8-symbol fast path and the general
+// code lay different element widths over the same bytes, which is safe because a warp runs one of them at a time
+// (hist_to_general reads the fast layout into registers before it writes the general one).
+//   general: symbols int16[12][32] at 0, byte arrays uint8[113][32] at 768
+//   fast:    slot words uint32[16][32] at 0, hash table uint16[32][32] at 2048 (later heap and code table)
 using FastScratch = HuffScratch<kFastSyms, 32>;
 using BigScratch = HuffScratch<64, 1>;
 using F8Scratch = Fast8Scratch<32>;
-constexpr int kWarpScratchBytes = 1024 + FastScratch::kBytes * 32;
-static_assert(kWarpScratchBytes >= 5632 && kWarpScratchBytes % 16 == 0, "fast-path arrays must fit the warp region");
+constexpr int kWarpSymBytes = (kFastSyms + 1) * 2 * 32;
+constexpr int kWarpScratchBytes = ((kWarpSymBytes + FastScratch::kBytes * 32 + 15) / 16) * 16;
+static_assert(kWarpScratchBytes >= 4096, "fast-path arrays must fit the warp region");
 
 struct EncSmem {
   uint16_t zz[64][kTileBlocks];                        // quantised coefficients, zigzag order; later slot ids
@@ -369,7 +369,7 @@ struct EncSmem {
   uint32_t split;
   u64 base;
 };
-static_assert(sizeof(EncSmem) <= 44 * 1024 + 256, "EncSmem must allow 5 CTAs per SM");
+static_assert(sizeof(EncSmem) <= 37 * 1024 - 512, "EncSmem must allow 6 CTAs per SM");
 
 struct ZShared {  // accessor of one block's column in EncSmem::zz
   uint16_t* col;
@@ -479,7 +479,7 @@ MYB_D int fdct_quant_block(const uint32_t (&raw)[16], const QTables& qt, int pla
 __device__ __noinline__ HuffPlan plan_big(ZShared z, int L, BigScratch bs) { return huff_plan(z, L, bs, NoWarp{}); }
 __device__ __noinline__ void emit_big(ZShared z, HuffPlan pl, BigScratch bs, uint8_t* dst) { huff_emit(z, pl, bs, dst, NoWarp{}); }
 
-__global__ void __launch_bounds__(kCtaThreads, 5)
+__global__ void __launch_bounds__(kCtaThreads, 6)
     dct_compress_kernel(const __grid_constant__ EncParams P, const __grid_constant__ QTables qt) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   EncSmem& sm = *reinterpret_cast<EncSmem*>(smem_raw);
@@ -487,8 +487,8 @@ __global__ void __launch_bounds__(kCtaThreads, 5)
   const FrameGeom& g = P.g;
   uint8_t* const wbase = sm.coder[tid >> 5];
   const int lane = tid & 31;
-  FastScratch fs{wbase + 1024 + lane, reinterpret_cast<int16_t*>(wbase) + lane};
-  F8Scratch f8{reinterpret_cast<uint32_t*>(wbase + 1536) + lane, reinterpret_cast<uint16_t*>(wbase + 3584) + lane};
+  FastScratch fs{wbase + kWarpSymBytes + lane, reinterpret_cast<int16_t*>(wbase) + lane};
+  F8Scratch f8{reinterpret_cast<uint32_t*>(wbase) + lane, reinterpret_cast<uint16_t*>(wbase + 2048) + lane};
   ZShared z{&sm.zz[0][tid]};
   uint8_t* const overflow = P.ws.overflow + (uint64_t)blockIdx.x * (kEncTile * 256u);
 
@@ -539,7 +539,7 @@ __global__ void __launch_bounds__(kCtaThreads, 5)
       if (!live) L = 0;
       while (L > 0 && z.get(L - 1) == 0) L--;  // exact message length (Huffman.cpp:184-190); at most 8 steps
       {  // empty the warp's hash table (2 KB, 64 bytes per lane)
-        uint4* q = reinterpret_cast<uint4*>(wbase + 3584);
+        uint4* q = reinterpret_cast<uint4*>(wbase + 2048);
 #pragma unroll
         for (int j = 0; j < 4; j++) q[lane + 32 * j] = make_uint4(~0u, ~0u, ~0u, ~0u);
       }
@@ -742,7 +742,7 @@ __global__ void __launch_bounds__(256) finalize_frames_kernel(const __grid_const
   copy_global_to_global(out + ppos + 8 + i0, P.ws.chunk_sizes + sidx + i0, cnt, 256);
 }
 
-constexpr int kEncCtasPerSm = 5, kDecCtasPerSm = 6;  // resident CTAs per SM (registers and shared memory sized for it)
+constexpr int kEncCtasPerSm = 6, kDecCtasPerSm = 6;  // resident CTAs per SM (registers and shared memory sized for it)
 int codec_grid_size(int device, bool encoder) {
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
