@@ -569,11 +569,43 @@ __global__ void __launch_bounds__(kCtaThreads, 6)
       // chunk sizes go to a linear side array; finalize_frames_kernel moves them behind the plane headers,
       // whose position depends on the (data dependent) size of the previous planes
       if (live) P.ws.chunk_sizes[gblk0 + blk] = (uint8_t)size;
-      uint32_t pass_total;
-      const uint32_t off = carried + cta_exclusive_scan(size, sm.warp_sums, &pass_total);
+      // CTA scan of the chunk sizes.  Between its two barriers thread 0 reserves the tile's place in the scratch area
+      // (bump allocation, completion order; file-order offsets are computed afterwards by scan_tiles_kernel, so no CTA
+      // ever waits for another one): chunks that do not fit the shared staging buffer are then written straight to it.
+      uint32_t pass_total, off;
+      {
+        const int wid = tid >> 5;
+        uint32_t inc = size;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t nb = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += nb;
+        }
+        if (lane == 31) sm.warp_sums[wid] = inc;
+        __syncthreads();
+        uint32_t before = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < kCtaThreads / 32; w++) {
+          const uint32_t v = sm.warp_sums[w];
+          if (w < wid) before += v;
+          tot += v;
+        }
+        if (tid == 0) {
+          const u64 pos = atomicAdd(reinterpret_cast<u64*>(P.ws.counters + 2), (u64)tot);
+          P.ws.tile_pos[tile] = pos;
+          P.ws.tile_total[tile] = tot;
+          sm.base = pos;
+        }
+        __syncthreads();
+        off = carried + before + inc - size;
+        pass_total = tot;
+      }
+      const u64 pos = sm.base;
+      const bool room = pos + pass_total <= P.ws.scratch_cap;  // CTA uniform
       {
         const bool fits = off + size <= (uint32_t)kStageBytes;
-        uint8_t* dst = fits ? &sm.stage[off] : overflow + off;
+        // no room: the capacity flag is raised below and the bytes go to a per-CTA dummy area
+        uint8_t* dst = fits ? &sm.stage[off] : (room ? P.ws.scratch + pos + off : overflow + off);
         // first chunk that does not fit the shared staging buffer (chunks never straddle; offsets only grow)
         if (live && !fits && off <= (uint32_t)kStageBytes) atomicMin(&sm.split, off);
         if (fast) {
@@ -587,26 +619,12 @@ __global__ void __launch_bounds__(kCtaThreads, 6)
         }
       }
       carried += pass_total;
-    }
-    __syncthreads();
-
-    // ---- park the tile's bytes in the scratch area (bump allocation, completion order); file-order offsets
-    //      are computed afterwards by scan_tiles_kernel, so no CTA ever waits for another one ----
-    if (tid == 0) {
-      const u64 pos = atomicAdd(reinterpret_cast<u64*>(P.ws.counters + 2), (u64)carried);
-      P.ws.tile_pos[tile] = pos;
-      P.ws.tile_total[tile] = carried;
-      sm.base = pos;
-    }
-    __syncthreads();
-    {
-      const u64 pos = sm.base;
-      if (pos + carried > P.ws.scratch_cap) {
+      __syncthreads();  // the staged part of the tile is complete
+      if (!room) {
         if (tid == 0) atomicOr(&P.ws.counters[1], kFlagCapacity);
       } else {
-        const uint32_t split = sm.split < carried ? sm.split : carried;
+        const uint32_t split = sm.split < pass_total ? sm.split : pass_total;
         copy_smem_to_global(P.ws.scratch + pos, sm.stage, split);
-        for (uint32_t i = split + tid; i < carried; i += kCtaThreads) P.ws.scratch[pos + i] = overflow[i];
       }
     }
     __syncthreads();  // shared memory is reused by the next tile
