@@ -95,4 +95,28 @@ for q in (10, 50, 90, 100):
     pay = int(d_off[F].item())
     out[f"q{q}"] = {"compress_ms": round(min(cs), 3), "decompress_ms": round(min(ds), 3), "bytes_per_pixel": round(pay / (F * W * H), 4),
                     "compress_Mpixel_s": round(F * W * H / min(cs) / 1e3, 1), "decompress_Mpixel_s": round(F * W * H / min(ds) / 1e3, 1)}
+# ---- natural content (SURVEY 8(d)(i) "tiled-real": the reference's chef-with-trumpet.myyuv tiled to 4K), 16 frames ----
+gold = ROOT / "oracle" / "_ref" / "golden" / "chef-with-trumpet.myyuv"
+if gold.exists():
+    raw = gold.read_bytes()
+    base = np.frombuffer(raw, np.uint8, 992 * 736 * 3 // 2, 64).copy()
+    FR = 16
+    host = synth.tiled_real_iyuv(base, 992, 736, W, H, FR)
+    r_in = torch.from_numpy(host).to(dev)
+    r_out = torch.empty(FR * pkg.capi.compress_bound(W, H), dtype=torch.uint8, device=dev)
+    r_off = torch.zeros(FR + 1, dtype=torch.int64, device=dev)
+    r_back = torch.empty_like(r_in)
+    for q in (50, 90):
+        qq = (q, q, q)
+        cs, ds = [], []
+        for it in range(6):
+            ctx.compress_batch_dev(r_in, W, H, qq, FR, r_out, r_out.numel(), r_off); c_ms = ctx.last_kernel_ms()
+            ctx.decompress_batch_dev(r_out, r_off, W, H, qq, FR, r_back); d_ms = ctx.last_kernel_ms()
+            if it:
+                cs.append(c_ms); ds.append(d_ms)
+        ctx.batch_status()
+        pay = int(r_off[FR].item())
+        out[f"tiled_real_q{q}"] = {"frames": FR, "compress_ms": round(min(cs), 3), "decompress_ms": round(min(ds), 3),
+                                   "bytes_per_pixel": round(pay / (FR * W * H), 4),
+                                   "compress_Mpixel_s": round(FR * W * H / min(cs) / 1e3, 1), "decompress_Mpixel_s": round(FR * W * H / min(ds) / 1e3, 1)}
 print(json.dumps(out, indent=1))

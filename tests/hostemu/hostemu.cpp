@@ -33,7 +33,7 @@ struct ZSlots {
 
 namespace {
 // mode 0: general code on the 64-symbol scratch only; 1: 15-symbol scratch first (the kernel's pre-fast8 flow);
-// 2: the kernel's flow -- hash histogram, then the 8-symbol fast path, the general tail, or the 64-symbol scratch
+// 2: the kernel's flow -- hash histogram, then the 15-symbol fast path or the general code on the 64-symbol scratch
 template <int STRIDE>
 int encode_blocks(const int16_t* coef, uint32_t n, int mode, uint8_t* out, uint8_t* sizes) {
   using Fast = HuffScratch<15, STRIDE>;
@@ -43,7 +43,7 @@ int encode_blocks(const int16_t* coef, uint32_t n, int mode, uint8_t* out, uint8
   uint8_t* bb = new uint8_t[(size_t)Big::kBytes * STRIDE]();
   int16_t* bh = new int16_t[(size_t)Big::kSyms * STRIDE]();
   uint32_t* f8sc = new uint32_t[(size_t)16 * STRIDE]();
-  uint16_t* f8ht = new uint16_t[(size_t)32 * STRIDE]();
+  uint32_t* f8aux = new uint32_t[(size_t)16 * STRIDE]();
   int big_used = 0;
   for (uint32_t b = 0; b < n; b++) {
     int16_t z[64];
@@ -57,19 +57,13 @@ int encode_blocks(const int16_t* coef, uint32_t n, int mode, uint8_t* out, uint8
     int sz;
     bool done = false;
     if (mode == 2) {
-      Fast8Scratch<STRIDE> F{f8sc, f8ht};
+      const int lane = STRIDE > 1 ? (int)(b % STRIDE) : 0;  // exercise the lane interleave
+      FastScratch<STRIDE> F{f8sc + lane, reinterpret_cast<uint8_t*>(f8aux), lane};
       for (int i = 0; i < 32; i++) F.tab(i) = 0xffff;
       const int ns = huff_hist(za, L, true, F, NoWarp{});
-      if (ns >= 0 && ns <= 8) {
-        const Fast8Plan pl = huff_fast8_plan(ns, L == 0 ? 1 : L, F, NoWarp{});
-        huff_fast8_emit(za, pl, F, tmp, NoWarp{});
-        sz = pl.size();
-        done = true;
-      } else if (ns >= 0) {
-        const int zero_slot = hist_to_general(ns, F, fs, NoWarp{});
-        const HuffPlan pl = huff_plan_tail(L, ns, zero_slot, false, fs, NoWarp{});
-        ZSlots zs{z};
-        huff_emit(zs, pl, fs, tmp, NoWarp{});
+      if (ns >= 0) {
+        const FastPlan pl = huff_fast_plan(ns, L == 0 ? 1 : L, F, NoWarp{});
+        huff_fast_emit(za, pl, F, tmp, NoWarp{});
         sz = pl.size();
         done = true;
       }
@@ -92,7 +86,7 @@ int encode_blocks(const int16_t* coef, uint32_t n, int mode, uint8_t* out, uint8
     out += sz;
     sizes[b] = (uint8_t)sz;
   }
-  delete[] fb; delete[] fh; delete[] bb; delete[] bh; delete[] f8sc; delete[] f8ht;
+  delete[] fb; delete[] fh; delete[] bb; delete[] bh; delete[] f8sc; delete[] f8aux;
   return big_used;
 }
 }  // namespace

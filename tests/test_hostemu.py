@@ -53,9 +53,9 @@ def make_blocks(kind, n, rng):
             seq = np.concatenate([vals, vals[rng.integers(0, m, 64 - m)]])
             rng.shuffle(seq)
             b[i] = seq
-    elif kind == "few":  # 1..9 distinct symbols (the fast path and its boundary), with frequency ties and hash collisions
+    elif kind == "few":  # 1..17 distinct symbols (the fast path, its rehash replay and its boundary), with frequency ties and hash collisions
         for i in range(n):
-            m = rng.integers(1, 10)
+            m = rng.integers(1, 18)
             pool = [np.arange(-4, 5), np.arange(-1024, 1024), np.arange(-60, 61), np.arange(-13 * 6, 13 * 6 + 1, 13),
                     np.arange(-32 * 8, 32 * 8 + 1, 32)][i % 5]
             vals = rng.choice(pool, min(m, pool.size), replace=False)
@@ -67,7 +67,7 @@ def make_blocks(kind, n, rng):
 
 
 @pytest.mark.parametrize("kind,n", [("sparse", 6000), ("mid", 6000), ("distinct", 6000), ("full", 1500), ("small", 6000),
-                                    ("nozero", 1800), ("zeros", 64), ("few", 20000)])
+                                    ("nozero", 1800), ("zeros", 64), ("few", 40000)])
 @pytest.mark.parametrize("stride,fast", [(1, 1), (128, 1), (1, 0), (1, 2), (32, 2)])
 def test_block_coder_matches_oracle(emu, ora, kind, n, stride, fast):
     rng = np.random.default_rng(hash(kind) % 1000)

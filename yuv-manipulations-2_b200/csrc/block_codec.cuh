@@ -483,26 +483,35 @@ MYB_HD void huff_emit(Z& z, const HuffPlan& pl, const HuffScratch<CAP, STRIDE>& 
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Fast path: blocks with at most 8 distinct symbols (every block of natural content up to q ~ 75).
-// Same results as huff_plan / huff_emit, organised for few instructions per block:
+// Fast path: blocks with at most 15 distinct symbols (all blocks of typical content up to q ~ 90; natural images at
+// q 50 have 2..8).  Same results as huff_plan / huff_emit, organised for few instructions per block:
 //  * histogram through a 32-entry open-addressing table, one 32-bit word per slot (symbol << 16 | count);
-//  * with at most 8 keys the reference's unordered_map never rehashes (13 buckets) and its iteration order,
-//    the heap of the initial leaves, the (length, value) sort and the canonical codes are straight-line code
-//    on registers (nibble-packed lists, an 8-input sorting network);
-//  * heap entries carry weight << 8 | leaf set, so a merge needs no parent links: it adds 1 to the depth
+//  * up to 13 keys the reference's unordered_map never rehashes (13 buckets) and its iteration order is one SWAR
+//    list insertion per key on 4-bit fields; 14..16 keys (one rehash to 29 buckets) replay the list rules on a small
+//    byte list; the heap of the initial leaves, the (length, value) sort and the canonical codes are straight-line
+//    code on registers (a 15-input sorting network);
+//  * heap entries carry weight << 16 | leaf set, so a merge needs no parent links: it adds 1 to the depth
 //    nibble of every leaf below it, and the code-stream size is the sum of the merged weights.
+// Every loop over slots is unrolled with a warp-uniform guard (k < warp maximum of n), so a warp of 4-symbol blocks
+// does not pay for the capacity.
 // ---------------------------------------------------------------------------------------------------
+constexpr int kFastCap = 15;   // distinct symbols of the fast path = what huff_hist accepts
+constexpr int kHistCap = kFastCap;
 template <int STRIDE>
-struct Fast8Scratch {
-  uint32_t* sc;    // [16] symbol << 16 | occurrences, slots in first-occurrence order
-  uint16_t* ht;    // [32] (value & 0x7ff) << 4 | slot, 0xffff = empty; must be all empty when huff_hist starts.
-                   //      After the histogram the same memory holds the heap [0..8) and the code table [8..16).
+struct FastScratch {
+  uint32_t* sc;    // [16][STRIDE] + lane: symbol << 16 | occurrences, slots in first-occurrence order; after the code
+                   //      assignment the low half holds length << 8 | bit-reversed code instead of the count
+  uint8_t* aux;    // 64 * STRIDE bytes shared by the lanes, viewed as
+                   //   uint16[32][STRIDE]  hash table (value & 0x7ff) << 4 | slot, 0xffff = empty; all empty when huff_hist starts
+                   //   uint8[60][STRIDE]   three byte lists of the rehash replay
+                   //   uint32[16][STRIDE]  the heap
+  int lane;        // this thread's column
   MYB_HD uint32_t& slot(int s) const { return sc[s * STRIDE]; }
-  MYB_HD uint16_t& tab(int h) const { return ht[h * STRIDE]; }
-  MYB_HD uint16_t& heap(int i) const { return ht[i * STRIDE]; }
-  MYB_HD uint16_t& code(int s) const { return ht[(8 + s) * STRIDE]; }
+  MYB_HD uint16_t& codeword(int s) const { return reinterpret_cast<uint16_t*>(sc + s * STRIDE)[0]; }  // low half (little endian)
+  MYB_HD uint16_t& tab(int h) const { return reinterpret_cast<uint16_t*>(aux)[h * STRIDE + lane]; }
+  MYB_HD uint32_t& heap(int i) const { return reinterpret_cast<uint32_t*>(aux)[i * STRIDE + lane]; }
+  MYB_HD uint8_t& lst(int a, int i) const { return aux[(a * 20 + i) * STRIDE + lane]; }
 };
-constexpr int kHistCap = 11;  // distinct symbols huff_hist accepts (the capacity of the general shared-memory scratch)
 
 // Histogram of the message z[0 .. L) in first-occurrence order.  Z here is an accessor of raw 16-bit words:
 // raw(i) / setraw(i, w).  A coefficient needs 11 bits, so the slot of its value is written into bits 11..14 of
@@ -511,7 +520,7 @@ constexpr int kHistCap = 11;  // distinct symbols huff_hist accepts (the capacit
 // Returns the number of distinct symbols, or -1 when there are more than kHistCap.  Idle lanes pass live = false
 // and get 0.
 template <int STRIDE, class Z, class W>
-MYB_HD int huff_hist(Z& z, int L, bool live, const Fast8Scratch<STRIDE>& F, const W& warp) {
+MYB_HD int huff_hist(Z& z, int L, bool live, const FastScratch<STRIDE>& F, const W& warp) {
   int n = 0;
   if (!live) L = 0;
   const int Lw = warp.max(L);
@@ -547,39 +556,12 @@ MYB_HD int huff_hist(Z& z, int L, bool live, const Fast8Scratch<STRIDE>& F, cons
   return n > kHistCap ? -1 : n;
 }
 
-// Hand the histogram over to the general code (huff_plan_tail) when a warp holds a block with more than 8 symbols.
-// The two scratch layouts may share memory, so every slot word is read into registers before anything is written.
-template <int STRIDE, int CAP, int GSTRIDE, class W>
-MYB_HD int hist_to_general(int n, const Fast8Scratch<STRIDE>& F, const HuffScratch<CAP, GSTRIDE>& S, const W& warp) {
-  static_assert(CAP >= kHistCap, "the general scratch must hold what the histogram accepts");
-  uint32_t w[kHistCap];
-#if defined(__CUDACC__)
-#pragma unroll
-#endif
-  for (int k = 0; k < kHistCap; k++) w[k] = k < n ? F.slot(k) : 0u;
-  warp.sync();
-  int zero_slot = -1;
-#if defined(__CUDACC__)
-#pragma unroll
-#endif
-  for (int k = 0; k < kHistCap; k++) {
-    if (k < n) {
-      const int v = (int)(int16_t)(w[k] >> 16);
-      S.sym(k) = (int16_t)v;
-      S.at(S.kCnt, k) = (uint8_t)(w[k] & 0xffu);
-      if (v == 0) zero_slot = k;
-    }
-  }
-  warp.sync();
-  return zero_slot;
-}
-
-struct Fast8Plan {
+struct FastPlan {
   int n;           // distinct symbols, 0 = idle lane
   int msg_len;     // coded symbols
   int bits;        // code stream bits
   int table_bytes; // bytes of the serialised code table
-  uint32_t depth;  // code length of slot s in nibble s
+  uint32_t dlo, dhi;  // code length of slot s in nibble s (slots 0..7, 8..14)
   MYB_HD int size() const { return n > 0 ? 3 + table_bytes + ((bits + 7) >> 3) : 0; }
 };
 
@@ -597,12 +579,33 @@ MYB_HD int ctz32(uint32_t v) {
   return __builtin_ctz(v);
 #endif
 }
+// position (in bits) of the lowest 4-bit field of w that equals b, or -1
+MYB_HD int nib_find(uint32_t w, uint32_t b) {
+  const uint32_t x = w ^ (b * 0x11111111u);
+  const uint32_t z = (x - 0x11111111u) & ~x & 0x88888888u;  // lowest hit is exact
+  return z ? (ctz32(z) & ~3) : -1;
+}
+// insert the 4-bit value v at bit position p4, moving the higher fields up by one (the top field is dropped)
+MYB_HD uint32_t nib_insert(uint32_t w, int p4, uint32_t v) {
+  const uint32_t low = (1u << p4) - 1u;
+  return (w & low) | ((w & ~low) << 4) | (v << p4);
+}
+
+// std::hash<short> = the value sign-extended to 64 bits; 2^64 mod 13 = 3, 2^64 mod 29 = 24
+MYB_HD uint32_t bucket13(int v) {
+  const uint32_t x = (uint32_t)(v + 1040 + (v < 0 ? 3 : 0));  // >= 0, same residue as the 64-bit hash
+  return x - 13u * ((x * 5042u) >> 16);                        // x % 13 for x < 6547
+}
+MYB_HD uint32_t bucket29(int v) {
+  const uint32_t x = (uint32_t)(v + 1044 + (v < 0 ? 24 : 0));  // 1044 = 36 * 29
+  return x - 29u * ((x * 2260u) >> 16);                        // x % 29 for x < 3276... checked in tests
+}
 
 // std::push_heap of `ent` as element number J of a heap held in registers (J is a compile-time constant, so the
-// path to the root is fixed and only the stopping point is data dependent).  Entries compare by weight (bits 8..15).
-template <int J>
-MYB_HD void heap_push_static(uint32_t (&H)[8], uint32_t ent) {
-  const uint32_t key = ent | 0xffu;
+// path to the root is fixed and only the stopping point is data dependent).  Entries compare by weight (bits 16..).
+template <int J, int CAP>
+MYB_HD void heap_push_static(uint32_t (&H)[CAP], uint32_t ent) {
+  const uint32_t key = ent | 0xffffu;
   bool go = true;
   int hole = J;
 #if defined(__CUDACC__)
@@ -621,22 +624,22 @@ MYB_HD void heap_push_static(uint32_t (&H)[8], uint32_t ent) {
 }
 
 template <int STRIDE>
-MYB_HD void heap16_sift_up(const Fast8Scratch<STRIDE>& F, int hole, uint32_t ent) {
-  const uint32_t key = ent | 0xffu;
+MYB_HD void heap32_sift_up(const FastScratch<STRIDE>& F, int hole, uint32_t ent) {
+  const uint32_t key = ent | 0xffffu;
   MYB_NOUNROLL
   while (hole > 0) {
     const int parent = (hole - 1) >> 1;
     const uint32_t pe = F.heap(parent);
     if (!(pe > key)) break;
-    F.heap(hole) = (uint16_t)pe;
+    F.heap(hole) = pe;
     hole = parent;
   }
-  F.heap(hole) = (uint16_t)ent;
+  F.heap(hole) = ent;
 }
 
 // std::pop_heap + pop_back (stl_heap.h __adjust_heap, then __push_heap of the former last element)
 template <int STRIDE>
-MYB_HD uint32_t heap16_pop(const Fast8Scratch<STRIDE>& F, int& hsize) {
+MYB_HD uint32_t heap32_pop(const FastScratch<STRIDE>& F, int& hsize) {
   const uint32_t top = F.heap(0);
   const int len = hsize - 1;
   hsize = len;
@@ -649,11 +652,11 @@ MYB_HD uint32_t heap16_pop(const Fast8Scratch<STRIDE>& F, int& hsize) {
     child = 2 * child + 2;
     uint32_t r = F.heap(child);
     const uint32_t l = F.heap(child - 1);
-    if (r > (l | 0xffu)) {
+    if (r > (l | 0xffffu)) {
       child--;
       r = l;
     }
-    F.heap(hole) = (uint16_t)r;
+    F.heap(hole) = r;
     hole = child;
   }
   if ((len & 1) == 0 && child == ((len - 2) >> 1)) {
@@ -661,90 +664,215 @@ MYB_HD uint32_t heap16_pop(const Fast8Scratch<STRIDE>& F, int& hsize) {
     F.heap(hole) = F.heap(child - 1);
     hole = child - 1;
   }
-  heap16_sift_up(F, hole, value);
+  heap32_sift_up(F, hole, value);
   return top;
 }
 
-template <int STRIDE, class W>
-MYB_HD Fast8Plan huff_fast8_plan(int n, int msg_len, const Fast8Scratch<STRIDE>& F, const W& warp) {
-  Fast8Plan pl;
+// libstdc++ _M_insert_bucket_begin on byte lists (list a = slots, list b = buckets): a key whose bucket already holds
+// nodes goes right before the first node of that bucket's run, otherwise to the front of the whole list.
+template <int STRIDE>
+MYB_HD void lst_place(const FastScratch<STRIDE>& F, int la, int lb, int& ln, int slot, int bucket) {
+  int p = 0;
+  MYB_NOUNROLL
+  for (int i = 0; i < ln; i++)
+    if (F.lst(lb, i) == bucket) { p = i; break; }
+  MYB_NOUNROLL
+  for (int i = ln; i > p; i--) {
+    F.lst(la, i) = F.lst(la, i - 1);
+    F.lst(lb, i) = F.lst(lb, i - 1);
+  }
+  F.lst(la, p) = (uint8_t)slot;
+  F.lst(lb, p) = (uint8_t)bucket;
+  ln++;
+}
+
+// CAP = 8 or 15: capacity of this instantiation; every lane of the warp has n <= CAP (nw = warp maximum of n)
+template <int CAP, int STRIDE, class W>
+MYB_HD FastPlan huff_fast_plan_n(int n, int nw, int msg_len, const FastScratch<STRIDE>& F, const W& warp) {
+  FastPlan pl;
   pl.n = n;
   pl.msg_len = msg_len;
-  const int nw = warp.max(n);
-  // ---- iteration order of the reference's map (13 buckets, no rehash): list and buckets as 4-bit fields
-  uint32_t ord = 0, bkt = ~0u;
-  uint32_t cnt0 = 0;
+  // ---- slot words into registers; is the value 0 part of the message?
+  uint32_t sw[CAP];
+  bool has_zero = false;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int k = 0; k < CAP; k++) sw[k] = 0;
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
   for (int k = 0; k < 8; k++) {
-    if (k < nw) {
-      if (k < n) {
-        const uint32_t w = F.slot(k);
-        if (k == 0) cnt0 = w & 0xffu;
-        const int v = (int)(int16_t)(w >> 16);
-        // std::hash<short> = the value sign-extended to 64 bits; 2^64 mod 13 = 3
-        const uint32_t x13 = (uint32_t)(v + 1040 + (v < 0 ? 3 : 0));  // >= 0, same residue as the 64-bit hash
-        const uint32_t b = x13 - 13u * ((x13 * 5042u) >> 16);          // x13 % 13 for x13 < 6547
-        const uint32_t x = bkt ^ (b * 0x11111111u);
-        const uint32_t zero_nib = (x - 0x11111111u) & ~x & 0x88888888u;  // lowest hit is exact
-        const int p4 = zero_nib ? (ctz32(zero_nib) & ~3) : 0;
-        const uint32_t low = (1u << p4) - 1u;
-        ord = (ord & low) | ((ord & ~low) << 4) | ((uint32_t)k << p4);
-        bkt = (bkt & low) | ((bkt & ~low) << 4) | (b << p4);
-      }
+    if (k < n) {
+      sw[k] = F.slot(k);
+      if ((sw[k] >> 16) == 0) has_zero = true;
     }
   }
-  // ---- leaves pushed in list order (Huffman.cpp:207-209) into a heap held in registers
-  uint32_t H[8];
+  if (CAP > 8) {
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
-  for (int k = 0; k < 8; k++) H[k] = 0;
-#define MYB_PUSH_LEAF(J)                                                           \
-  if (J < nw) {                                                                    \
-    if (J < n) {                                                                   \
-      const uint32_t sl = (ord >> (4 * J)) & 15u;                                  \
-      heap_push_static<J>(H, ((F.slot((int)sl) & 0xffu) << 8) | (1u << sl));       \
-    }                                                                              \
+    for (int k = 8; k < CAP; k++) {
+      if (k < n) {
+        sw[k] = F.slot(k);
+        if ((sw[k] >> 16) == 0) has_zero = true;
+      }
+    }
+  }
+  // The reference's map also holds the key 0 while it is filled (trailing zeros or freq[0], Huffman.cpp:192-195); when
+  // the message has no zero it is inserted last and erased again (:201), which only matters when it is key number 14
+  // and triggers the rehash to 29 buckets.
+  const int keys = n + ((n > 0 && !has_zero) ? 1 : 0);
+  const bool rehash = CAP > 8 && warp.any(keys >= 14);
+  // ---- iteration order of the reference's map as a list of slots, 4 bits each (olo: positions 0..7, ohi: 8..14)
+  uint32_t olo = 0, ohi = 0;
+  if (!rehash) {
+    uint32_t blo = ~0u, bhi = ~0u;  // bucket of each list position; 0xF = empty, which is no bucket
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int k = 0; k < 8; k++) {  // the list still fits the low word
+      if (k < n) {
+        const uint32_t b = bucket13((int)(int16_t)(sw[k] >> 16));
+        const int f = nib_find(blo, b);
+        const int p4 = f < 0 ? 0 : f;
+        olo = nib_insert(olo, p4, (uint32_t)k);
+        blo = nib_insert(blo, p4, b);
+      }
+    }
+    if (CAP > 8) {
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+      for (int k = 8; k < (CAP < 13 ? CAP : 13); k++) {
+        if (k < n) {
+          const uint32_t b = bucket13((int)(int16_t)(sw[k] >> 16));
+          int f = nib_find(blo, b);
+          int p = f >= 0 ? (f >> 2) : -1;
+          if (p < 0) {
+            f = nib_find(bhi, b);
+            p = f >= 0 ? 8 + (f >> 2) : 0;
+          }
+          if (p < 8) {
+            ohi = (ohi << 4) | (olo >> 28);
+            bhi = (bhi << 4) | (blo >> 28);
+            olo = nib_insert(olo, 4 * p, (uint32_t)k);
+            blo = nib_insert(blo, 4 * p, b);
+          } else {
+            ohi = nib_insert(ohi, 4 * (p - 8), (uint32_t)k);
+            bhi = nib_insert(bhi, 4 * (p - 8), b);
+          }
+        }
+      }
+    }
+  } else {
+    // 14..16 keys somewhere in the warp: replay the list rules on byte lists (list 0 = slots, 1 = buckets, 2 = copy)
+    const int m = (n == 13 && !has_zero) ? 14 : n;  // the appended key 0 only matters as key number 14
+    const int mw = warp.max(m);
+    int ln = 0;
+    MYB_NOUNROLL
+    for (int s = 0; s < mw; s++) {
+      if (s < m) {
+        if (s == 13) {  // _M_rehash_aux: walk the old list front to back and re-place every node among 29 buckets
+          for (int i = 0; i < 13; i++) F.lst(2, i) = F.lst(0, i);
+          ln = 0;
+          for (int i = 0; i < 13; i++) {
+            const int t = F.lst(2, i);
+            lst_place(F, 0, 1, ln, t, (int)bucket29((int)(int16_t)(F.slot(t) >> 16)));
+          }
+        }
+        const int v = s < n ? (int)(int16_t)(F.slot(s) >> 16) : 0;
+        lst_place(F, 0, 1, ln, s, (int)(s < 13 ? bucket13(v) : bucket29(v)));
+      }
+      warp.sync();
+    }
+    // to the nibble lists, dropping the appended key (slot number n) again
+    int wpos = 0;
+    MYB_NOUNROLL
+    for (int i = 0; i < mw; i++) {
+      if (i < m) {
+        const uint32_t t = F.lst(0, i);
+        if ((int)t < n) {
+          if (wpos < 8) olo |= t << (4 * wpos);
+          else ohi |= t << (4 * (wpos - 8));
+          wpos++;
+        }
+      }
+    }
+    warp.sync();
+  }
+  // ---- leaves pushed in list order (Huffman.cpp:207-209) into a heap held in registers
+  uint32_t H[CAP];
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int k = 0; k < CAP; k++) H[k] = 0;
+#define MYB_PUSH_LEAF(J)                                                                 \
+  if (J < n) {                                                                           \
+    const uint32_t sl = ((J < 8 ? olo >> (4 * (J & 7)) : ohi >> (4 * (J & 7)))) & 15u;   \
+    heap_push_static<J, CAP>(H, ((F.slot((int)sl) & 0xffu) << 16) | (1u << sl));         \
   }
   MYB_PUSH_LEAF(0) MYB_PUSH_LEAF(1) MYB_PUSH_LEAF(2) MYB_PUSH_LEAF(3)
-  MYB_PUSH_LEAF(4) MYB_PUSH_LEAF(5) MYB_PUSH_LEAF(6) MYB_PUSH_LEAF(7)
+  if (nw > 4) { MYB_PUSH_LEAF(4) MYB_PUSH_LEAF(5) MYB_PUSH_LEAF(6) MYB_PUSH_LEAF(7) }
+  if constexpr (CAP > 8) {
+    MYB_PUSH_LEAF(8) MYB_PUSH_LEAF(9) MYB_PUSH_LEAF(10) MYB_PUSH_LEAF(11)
+    MYB_PUSH_LEAF(12) MYB_PUSH_LEAF(13) MYB_PUSH_LEAF(14)
+  }
 #undef MYB_PUSH_LEAF
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
   for (int k = 0; k < 8; k++)
-    if (k < nw) F.heap(k) = (uint16_t)H[k];
+    if (k < nw) F.heap(k) = H[k];
+  if constexpr (CAP > 8) {
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int k = 8; k < CAP; k++) F.heap(k) = H[k];
+  }
   // ---- n - 1 merges (Huffman.cpp:210-217)
   int hsize = n, bits = 0;
-  uint32_t depth = 0;
+  uint32_t dlo = 0, dhi = 0;
   MYB_NOUNROLL
   for (int t = 0; t + 1 < nw; t++) {
     if (t + 1 < n) {
-      const uint32_t a = heap16_pop(F, hsize);
-      const uint32_t b = heap16_pop(F, hsize);
-      const uint32_t w = (a >> 8) + (b >> 8);
-      const uint32_t m = (a | b) & 0xffu;
-      depth += spread8(m);
+      const uint32_t a = heap32_pop(F, hsize);
+      const uint32_t b = heap32_pop(F, hsize);
+      const uint32_t w = (a >> 16) + (b >> 16);
+      const uint32_t m = (a | b) & 0x7fffu;
+      dlo += spread8(m & 0xffu);
+      if (CAP > 8) dhi += spread8(m >> 8);
       bits += (int)w;
       hsize++;
-      heap16_sift_up(F, hsize - 1, (w << 8) | m);
+      heap32_sift_up(F, hsize - 1, (w << 16) | m);
     }
     warp.sync();
   }
   if (n == 1) {  // a single symbol gets a one-bit code (Huffman.cpp:76, :218-221)
-    depth = 1;
-    bits = (int)cnt0;
+    dlo = 1;
+    bits = (int)(sw[0] & 0xffu);
   }
-  pl.depth = depth;
+  pl.dlo = dlo;
+  pl.dhi = dhi;
   pl.bits = bits;
-  // ---- size of the code table: one group per used length, 1 + ceil(11 c / 8) bytes for c symbols (Huffman.cpp:284-293)
-  uint32_t per_len = 0;  // symbols per length, 4-bit fields (length 0 = unused slots, ignored)
+  // ---- size of the code table: one group per used length, 1 + ceil(11 c / 8) bytes for c symbols (Huffman.cpp:284-293);
+  // lengths are 1..8 (64 coefficients cannot make a deeper tree), at most 15 symbols per length
+  uint32_t per_len = 0, len8 = 0;  // symbols per length 0..7 in 4-bit fields (length 0 = unused slots, ignored); length 8
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
-  for (int k = 0; k < 8; k++) per_len += 1u << (((depth >> (4 * k)) & 15u) * 4u);
+  for (int k = 0; k < 8; k++) per_len += 1u << (((dlo >> (4 * k)) & 15u) * 4u);  // at most 8 symbols: lengths <= 7
+  if constexpr (CAP > 8) {
+    per_len = 0;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int k = 0; k < CAP; k++) {
+      const uint32_t d = ((k < 8 ? dlo >> (4 * (k & 7)) : dhi >> (4 * (k & 7)))) & 15u;
+      per_len += d < 8u ? 1u << (4u * d) : 0u;
+      len8 += d == 8u ? 1u : 0u;
+    }
+  }
   uint32_t lo = per_len & 0xfff0u, hi = per_len >> 16;
   lo = (lo | (lo << 8)) & 0x00ff00ffu;
   lo = (lo | (lo << 4)) & 0x0f0f0f0fu;
@@ -761,9 +889,16 @@ MYB_HD Fast8Plan huff_fast8_plan(int n, int msg_len, const Fast8Scratch<STRIDE>&
     const uint32_t nz = ((hi + 0x7f7f7f7fu) >> 7) & 0x01010101u;
     f += hi + t + nz;
   }
-  // unused slots counted under length 0 add 7 >> 3 = 0 to t but their byte was masked out of lo above
-  pl.table_bytes = (int)((f * 0x01010101u) >> 24);
+  pl.table_bytes = (int)((f * 0x01010101u) >> 24) + (len8 ? (int)(1u + len8 + ((3u * len8 + 7u) >> 3)) : 0);
   return pl;
+}
+
+// Two instantiations, chosen per warp: the compact one when no block of the warp has more than 8 symbols.
+template <int STRIDE, class W>
+MYB_HD FastPlan huff_fast_plan(int n, int msg_len, const FastScratch<STRIDE>& F, const W& warp) {
+  const int nw = warp.max(n);
+  if (nw <= 8) return huff_fast_plan_n<8>(n, nw, msg_len, F, warp);
+  return huff_fast_plan_n<kFastCap>(n, nw, msg_len, F, warp);
 }
 
 #define MYB_CSWAP(a, b)                          \
@@ -773,80 +908,91 @@ MYB_HD Fast8Plan huff_fast8_plan(int n, int msg_len, const Fast8Scratch<STRIDE>&
     a = lo_;                                     \
   }
 
-// Serialise the chunk planned by huff_fast8_plan into dst[0 .. pl.size()): header, code table in (length, value)
+// Serialise the chunk planned by huff_fast_plan into dst[0 .. pl.size()): header, code table in (length, value)
 // order with canonical codes assigned on the way (Huffman.cpp:86-103, :300-316), code stream (:227-236, :319-325).
-template <int STRIDE, class Z, class W>
-MYB_HD void huff_fast8_emit(Z& z, const Fast8Plan& pl, const Fast8Scratch<STRIDE>& F, uint8_t* dst, const W& warp) {
+template <int CAP, int STRIDE, class Z, class W>
+MYB_HD void huff_fast_emit_n(Z& z, const FastPlan& pl, int nw, const FastScratch<STRIDE>& F, uint8_t* dst, const W& warp) {
   const int n = pl.n;
-  const int nw = warp.max(n);
   if (n > 0) {
     dst[0] = (uint8_t)(pl.bits & 0xff);
     dst[1] = (uint8_t)(pl.bits >> 8);
     dst[2] = (uint8_t)pl.table_bytes;
   }
   // sort keys: length << 16 | (value + 1024) << 4 | slot; unused slots sort last
-  uint32_t K[8];
+  uint32_t K[CAP];
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
-  for (int k = 0; k < 8; k++) {
-    K[k] = 0xffffffffu;
-    if (k < nw) {
-      if (k < n) {
-        const int v = (int)(int16_t)(F.slot(k) >> 16);
-        K[k] = (((pl.depth >> (4 * k)) & 15u) << 16) | ((uint32_t)(v + 1024) << 4) | (uint32_t)k;
-      }
-    }
+  for (int k = 0; k < CAP; k++) K[k] = 0xffffffffu;
+#define MYB_KEY(k)                                                                                        \
+  if (k < n) {                                                                                            \
+    const int v = (int)(int16_t)(F.slot(k) >> 16);                                                        \
+    const uint32_t d = ((k < 8 ? pl.dlo >> (4 * (k & 7)) : pl.dhi >> (4 * (k & 7)))) & 15u;               \
+    K[k] = (d << 16) | ((uint32_t)(v + 1024) << 4) | (uint32_t)k;                                         \
   }
-  if (nw > 4) {  // Batcher's odd-even merge sort, 19 compare-exchanges
-    MYB_CSWAP(K[0], K[1]) MYB_CSWAP(K[2], K[3]) MYB_CSWAP(K[4], K[5]) MYB_CSWAP(K[6], K[7])
-    MYB_CSWAP(K[0], K[2]) MYB_CSWAP(K[1], K[3]) MYB_CSWAP(K[4], K[6]) MYB_CSWAP(K[5], K[7])
-    MYB_CSWAP(K[1], K[2]) MYB_CSWAP(K[5], K[6])
-    MYB_CSWAP(K[0], K[4]) MYB_CSWAP(K[1], K[5]) MYB_CSWAP(K[2], K[6]) MYB_CSWAP(K[3], K[7])
-    MYB_CSWAP(K[2], K[4]) MYB_CSWAP(K[3], K[5])
-    MYB_CSWAP(K[1], K[2]) MYB_CSWAP(K[3], K[4]) MYB_CSWAP(K[5], K[6])
-  } else {
-    MYB_CSWAP(K[0], K[1]) MYB_CSWAP(K[2], K[3]) MYB_CSWAP(K[0], K[2]) MYB_CSWAP(K[1], K[3]) MYB_CSWAP(K[1], K[2])
+  MYB_KEY(0) MYB_KEY(1) MYB_KEY(2) MYB_KEY(3)
+  if (nw > 4) { MYB_KEY(4) MYB_KEY(5) MYB_KEY(6) MYB_KEY(7) }
+  if constexpr (CAP > 8) { MYB_KEY(8) MYB_KEY(9) MYB_KEY(10) MYB_KEY(11) MYB_KEY(12) MYB_KEY(13) MYB_KEY(14) }
+#undef MYB_KEY
+  // Batcher's odd-even merge sort for 16 inputs without the exchanges that touch input 15; its first 19 exchanges sort K[0..7]
+  MYB_CSWAP(K[0], K[1]) MYB_CSWAP(K[2], K[3]) MYB_CSWAP(K[0], K[2]) MYB_CSWAP(K[1], K[3]) MYB_CSWAP(K[1], K[2])
+  if (nw > 4) {
+    MYB_CSWAP(K[4], K[5]) MYB_CSWAP(K[6], K[7]) MYB_CSWAP(K[4], K[6]) MYB_CSWAP(K[5], K[7]) MYB_CSWAP(K[5], K[6])
+    MYB_CSWAP(K[0], K[4]) MYB_CSWAP(K[2], K[6]) MYB_CSWAP(K[2], K[4]) MYB_CSWAP(K[1], K[5]) MYB_CSWAP(K[3], K[7])
+    MYB_CSWAP(K[3], K[5]) MYB_CSWAP(K[1], K[2]) MYB_CSWAP(K[3], K[4]) MYB_CSWAP(K[5], K[6])
+  }
+  if constexpr (CAP > 8) {
+    MYB_CSWAP(K[8], K[9]) MYB_CSWAP(K[10], K[11]) MYB_CSWAP(K[8], K[10]) MYB_CSWAP(K[9], K[11]) MYB_CSWAP(K[9], K[10])
+    MYB_CSWAP(K[12], K[13]) MYB_CSWAP(K[12], K[14]) MYB_CSWAP(K[13], K[14]) MYB_CSWAP(K[8], K[12]) MYB_CSWAP(K[10], K[14])
+    MYB_CSWAP(K[10], K[12]) MYB_CSWAP(K[9], K[13]) MYB_CSWAP(K[11], K[13]) MYB_CSWAP(K[9], K[10]) MYB_CSWAP(K[11], K[12])
+    MYB_CSWAP(K[13], K[14]) MYB_CSWAP(K[0], K[8]) MYB_CSWAP(K[4], K[12]) MYB_CSWAP(K[4], K[8]) MYB_CSWAP(K[2], K[10])
+    MYB_CSWAP(K[6], K[14]) MYB_CSWAP(K[6], K[10]) MYB_CSWAP(K[2], K[4]) MYB_CSWAP(K[6], K[8]) MYB_CSWAP(K[10], K[12])
+    MYB_CSWAP(K[1], K[9]) MYB_CSWAP(K[5], K[13]) MYB_CSWAP(K[5], K[9]) MYB_CSWAP(K[3], K[11]) MYB_CSWAP(K[7], K[11])
+    MYB_CSWAP(K[3], K[5]) MYB_CSWAP(K[7], K[9]) MYB_CSWAP(K[11], K[13]) MYB_CSWAP(K[1], K[2]) MYB_CSWAP(K[3], K[4])
+    MYB_CSWAP(K[5], K[6]) MYB_CSWAP(K[7], K[8]) MYB_CSWAP(K[9], K[10]) MYB_CSWAP(K[11], K[12]) MYB_CSWAP(K[13], K[14])
   }
   uint8_t* p = dst + 3;
   uint8_t* hdr = dst;  // header byte of the open group (dst: none yet)
   uint32_t acc = 0, code = 0;
   int nb = 0, prev = 0, cnt = 0;
-#if defined(__CUDACC__)
-#pragma unroll
-#endif
-  for (int i = 0; i < 8; i++) {
-    if (i < nw) {
-      if (i < n) {
-        const uint32_t key = K[i];
-        const int len = (int)(key >> 16);
-        code <<= (len - prev);
-        F.code((int)(key & 15u)) = (uint16_t)((bit_reverse32(code) >> (32 - len)) | ((uint32_t)len << 8));
-        code++;
-        if (len != prev) {  // a new group: close the previous one, pad to a whole byte, reserve the header byte
-          if (prev) *hdr = (uint8_t)(((prev - 1) << 5) | (cnt - 1));
-          if (nb > 0) *p++ = (uint8_t)acc;
-          acc = 0;
-          nb = 0;
-          hdr = p++;
-          cnt = 0;
-          prev = len;
-        }
-        // pack11bit (Huffman.cpp:36-52): 11 bits on top of nb < 8 pending ones always complete one byte, sometimes two
-        acc |= (((key >> 4) + 1024u) & 0x7ffu) << nb;
-        nb += 11;
-        *p++ = (uint8_t)acc;
-        acc >>= 8;
-        nb -= 8;
-        if (nb >= 8) {
-          *p++ = (uint8_t)acc;
-          acc >>= 8;
-          nb -= 8;
-        }
-        cnt++;
-      }
-    }
+#define MYB_TABLE_SYMBOL(i)                                                                                              \
+  if (i < n) {                                                                                                           \
+    const uint32_t key = K[i];                                                                                           \
+    const int len = (int)(key >> 16);                                                                                    \
+    code <<= (len - prev);                                                                                               \
+    /* the slot word keeps its symbol and gets length << 8 | bit-reversed code in place of the count */                 \
+    const int sl = (int)(key & 15u);                                                                                     \
+    F.codeword(sl) = (uint16_t)((bit_reverse32(code) >> (32 - len)) | ((uint32_t)len << 8));                             \
+    code++;                                                                                                              \
+    if (len != prev) { /* a new group: close the previous one, pad to a whole byte, reserve the header byte */          \
+      if (prev) *hdr = (uint8_t)(((prev - 1) << 5) | (cnt - 1));                                                         \
+      if (nb > 0) *p++ = (uint8_t)acc;                                                                                   \
+      acc = 0;                                                                                                           \
+      nb = 0;                                                                                                            \
+      hdr = p++;                                                                                                         \
+      cnt = 0;                                                                                                           \
+      prev = len;                                                                                                        \
+    }                                                                                                                    \
+    /* pack11bit (Huffman.cpp:36-52): 11 bits on top of nb < 8 pending ones always complete one byte, sometimes two */   \
+    acc |= (((key >> 4) + 1024u) & 0x7ffu) << nb;                                                                        \
+    nb += 11;                                                                                                            \
+    *p++ = (uint8_t)acc;                                                                                                 \
+    acc >>= 8;                                                                                                           \
+    nb -= 8;                                                                                                             \
+    if (nb >= 8) {                                                                                                       \
+      *p++ = (uint8_t)acc;                                                                                               \
+      acc >>= 8;                                                                                                         \
+      nb -= 8;                                                                                                           \
+    }                                                                                                                    \
+    cnt++;                                                                                                               \
   }
+  MYB_TABLE_SYMBOL(0) MYB_TABLE_SYMBOL(1) MYB_TABLE_SYMBOL(2) MYB_TABLE_SYMBOL(3)
+  if (nw > 4) { MYB_TABLE_SYMBOL(4) MYB_TABLE_SYMBOL(5) MYB_TABLE_SYMBOL(6) MYB_TABLE_SYMBOL(7) }
+  if constexpr (CAP > 8) {
+    MYB_TABLE_SYMBOL(8) MYB_TABLE_SYMBOL(9) MYB_TABLE_SYMBOL(10) MYB_TABLE_SYMBOL(11)
+    MYB_TABLE_SYMBOL(12) MYB_TABLE_SYMBOL(13) MYB_TABLE_SYMBOL(14)
+  }
+#undef MYB_TABLE_SYMBOL
   if (n > 0) {
     *hdr = (uint8_t)(((prev - 1) << 5) | (cnt - 1));
     if (nb > 0) *p++ = (uint8_t)acc;
@@ -859,7 +1005,7 @@ MYB_HD void huff_fast8_emit(Z& z, const Fast8Plan& pl, const Fast8Scratch<STRIDE
   MYB_NOUNROLL
   for (int k = 0; k < Lw; k++) {
     if (k < L) {
-      const uint32_t ce = F.code(z.slot(k));
+      const uint32_t ce = F.codeword(z.slot(k));
       acc |= (ce & 0xffu) << nb;
       nb += (int)(ce >> 8);
       if (nb >= 8) {
@@ -870,6 +1016,13 @@ MYB_HD void huff_fast8_emit(Z& z, const Fast8Plan& pl, const Fast8Scratch<STRIDE
     }
   }
   if (nb > 0) *p++ = (uint8_t)acc;
+}
+
+template <int STRIDE, class Z, class W>
+MYB_HD void huff_fast_emit(Z& z, const FastPlan& pl, const FastScratch<STRIDE>& F, uint8_t* dst, const W& warp) {
+  const int nw = warp.max(pl.n);
+  if (nw <= 8) huff_fast_emit_n<8>(z, pl, nw, F, dst, warp);
+  else huff_fast_emit_n<kFastCap>(z, pl, nw, F, dst, warp);
 }
 #undef MYB_CSWAP
 

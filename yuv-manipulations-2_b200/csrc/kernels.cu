@@ -347,18 +347,12 @@ void launch_xrgb_to_iyuv(const uint8_t* d_bgrx, uint8_t* d_iyuv, uint32_t w, uin
 // so no transposition or register shuffling is needed between the stages (cuobjdump: 960 FMUL2/FFMA2, 0 MOV).
 // ===================================================================================================
 constexpr int kStageBytes = 3 * 1024;                  // shared-memory staging of one tile's chunk bytes
-constexpr int kFastSyms = kHistCap;                    // distinct symbols handled with shared-memory scratch
-// Entropy-coder scratch is one region per WARP, lanes interleaved (stride 32).  The 8-symbol fast path and the general
-// code lay different element widths over the same bytes, which is safe because a warp runs one of them at a time
-// (hist_to_general reads the fast layout into registers before it writes the general one).
-//   general: symbols int16[12][32] at 0, byte arrays uint8[113][32] at 768
-//   fast:    slot words uint32[16][32] at 0, hash table uint16[32][32] at 2048 (later heap and code table)
-using FastScratch = HuffScratch<kFastSyms, 32>;
+// Entropy-coder scratch of the fast path is one 4 KB region per WARP, lanes interleaved (FastScratch<32>):
+//   slot words uint32[16][32] at 0, then 2 KB that are hash table, byte lists and heap in turn.
+// Blocks with more than 15 distinct symbols send their warp through the general code on per-thread local memory.
 using BigScratch = HuffScratch<64, 1>;
-using F8Scratch = Fast8Scratch<32>;
-constexpr int kWarpSymBytes = (kFastSyms + 1) * 2 * 32;
-constexpr int kWarpScratchBytes = ((kWarpSymBytes + FastScratch::kBytes * 32 + 15) / 16) * 16;
-static_assert(kWarpScratchBytes >= 4096, "fast-path arrays must fit the warp region");
+using F8Scratch = FastScratch<32>;
+constexpr int kWarpScratchBytes = 4096;
 
 struct EncSmem {
   uint16_t zz[64][kTileBlocks];                        // quantised coefficients, zigzag order; later slot ids
@@ -380,11 +374,6 @@ struct ZShared {  // accessor of one block's column in EncSmem::zz
   MYB_D void setraw(int i, uint32_t w) { col[i * kTileBlocks] = (uint16_t)w; }
   MYB_D int slot(int i) const { return (col[i * kTileBlocks] >> 11) & 15; }
 };
-struct ZSlots {  // slot view of the same column for the general emit code after huff_hist
-  uint16_t* col;
-  MYB_D int get(int i) const { return (col[i * kTileBlocks] >> 11) & 15; }
-};
-
 struct EncParams {
   const uint8_t* src;
   uint8_t* out;
@@ -475,9 +464,6 @@ MYB_D int fdct_quant_block(const uint32_t (&raw)[16], const QTables& qt, int pla
   return lb;
 }
 
-// blocks with more than kFastSyms distinct symbols: same code on per-thread local-memory scratch, kept out of line
-__device__ __noinline__ HuffPlan plan_big(ZShared z, int L, BigScratch bs) { return huff_plan(z, L, bs, NoWarp{}); }
-__device__ __noinline__ void emit_big(ZShared z, HuffPlan pl, BigScratch bs, uint8_t* dst) { huff_emit(z, pl, bs, dst, NoWarp{}); }
 
 __global__ void __launch_bounds__(kCtaThreads, 6)
     dct_compress_kernel(const __grid_constant__ EncParams P, const __grid_constant__ QTables qt) {
@@ -487,8 +473,7 @@ __global__ void __launch_bounds__(kCtaThreads, 6)
   const FrameGeom& g = P.g;
   uint8_t* const wbase = sm.coder[tid >> 5];
   const int lane = tid & 31;
-  FastScratch fs{wbase + kWarpSymBytes + lane, reinterpret_cast<int16_t*>(wbase) + lane};
-  F8Scratch f8{reinterpret_cast<uint32_t*>(wbase) + lane, reinterpret_cast<uint16_t*>(wbase + 2048) + lane};
+  F8Scratch f8{reinterpret_cast<uint32_t*>(wbase) + lane, wbase + 2048, lane};
   ZShared z{&sm.zz[0][tid]};
   uint8_t* const overflow = P.ws.overflow + (uint64_t)blockIdx.x * (kEncTile * 256u);
 
@@ -545,24 +530,22 @@ __global__ void __launch_bounds__(kCtaThreads, 6)
       }
       __syncwarp();
       const int nsym = huff_hist(z, L, live, f8, WarpLockstep{});
-      const bool fast = __all_sync(0xffffffffu, nsym >= 0 && nsym <= 8);  // warp-uniform choice of the code path
-      Fast8Plan pl8{};
+      const bool fast = __all_sync(0xffffffffu, nsym >= 0);  // warp-uniform choice of the code path
+      FastPlan pl8{};
       HuffPlan pl{};
-      bool big = false;
       uint8_t lbytes[BigScratch::kBytes];
       int16_t lsyms[BigScratch::kSyms];
       BigScratch bs{lbytes, lsyms};
       uint32_t size;
       if (fast) {
-        pl8 = huff_fast8_plan(nsym, L == 0 ? 1 : L, f8, WarpLockstep{});
+        pl8 = huff_fast_plan(nsym, L == 0 ? 1 : L, f8, WarpLockstep{});
         size = (uint32_t)pl8.size();
       } else {
-        const int zero_slot = hist_to_general(nsym, f8, fs, WarpLockstep{});
-        pl = huff_plan_tail(L, nsym > 0 ? nsym : 0, zero_slot, nsym < 0, fs, WarpLockstep{});
-        if (live && pl.n < 0) {  // more distinct symbols than the shared-memory scratch holds
-          big = true;
-          pl = plan_big(z, L, bs);
-        }
+        // A block with more than 15 distinct symbols (noise, q near 100): the whole warp runs the general code in
+        // lockstep on per-thread local-memory scratch (all lanes touch the same offsets together, so the accesses
+        // coalesce in L1).  It redoes the histogram from the coefficient values, which huff_hist left readable in the
+        // low 11 bits of the coefficient words.
+        pl = huff_plan(z, L, bs, WarpLockstep{});
         __syncwarp();
         size = live ? (uint32_t)pl.size() : 0u;
       }
@@ -609,13 +592,11 @@ __global__ void __launch_bounds__(kCtaThreads, 6)
         // first chunk that does not fit the shared staging buffer (chunks never straddle; offsets only grow)
         if (live && !fits && off <= (uint32_t)kStageBytes) atomicMin(&sm.split, off);
         if (fast) {
-          huff_fast8_emit(z, pl8, f8, dst, WarpLockstep{});
+          huff_fast_emit(z, pl8, f8, dst, WarpLockstep{});
         } else {
           HuffPlan plf = pl;
-          if (!live || big) plf.n = 0;
-          ZSlots zs{z.col};
-          huff_emit(zs, plf, fs, dst, WarpLockstep{});
-          if (live && big) emit_big(z, pl, bs, dst);
+          if (!live) plf.n = 0;
+          huff_emit(z, plf, bs, dst, WarpLockstep{});
         }
       }
       carried += pass_total;

@@ -95,3 +95,23 @@ def edge_case_iyuv(w: int, h: int) -> np.ndarray:
     U = np.tile(np.linspace(0, 255, w // 2).astype(np.uint8), (h // 2, 1))
     V = np.where((np.mgrid[0:h // 2, 0:w // 2][0] // 4) % 2 == 0, 0, 255).astype(np.uint8)
     return np.concatenate([Y.reshape(-1), U.reshape(-1), V.reshape(-1)])
+
+
+def tiled_real_iyuv(base: np.ndarray, bw: int, bh: int, w: int, h: int, n_frames: int, first: int = 0) -> np.ndarray:
+    """SURVEY 8(d)(i) "tiled-real": frame f = a natural IYUV image (bw x bh, e.g. the reference's chef-with-trumpet.myyuv)
+    tiled to w x h with its origin shifted by (16 f mod bw, 16 f mod bh).  [n_frames, w*h*3/2] uint8."""
+    Y = base[: bw * bh].reshape(bh, bw)
+    U = base[bw * bh: bw * bh * 5 // 4].reshape(bh // 2, bw // 2)
+    V = base[bw * bh * 5 // 4:].reshape(bh // 2, bw // 2)
+    out = np.empty((n_frames, w * h * 3 // 2), np.uint8)
+    for i in range(n_frames):
+        f = first + i
+        sx, sy = (16 * f) % bw, (16 * f) % bh
+        yy = (np.arange(h) + sy) % bh
+        xx = (np.arange(w) + sx) % bw
+        out[i, : w * h] = Y[np.ix_(yy, xx)].reshape(-1)
+        yc = (np.arange(h // 2) + sy // 2) % (bh // 2)
+        xc = (np.arange(w // 2) + sx // 2) % (bw // 2)
+        out[i, w * h: w * h * 5 // 4] = U[np.ix_(yc, xc)].reshape(-1)
+        out[i, w * h * 5 // 4:] = V[np.ix_(yc, xc)].reshape(-1)
+    return out
