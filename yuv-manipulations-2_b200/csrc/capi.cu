@@ -127,7 +127,7 @@ namespace {
 int ensure_workspace(myyuvb_ctx* c, const FrameGeom& g, bool encoder, Workspace* ws, uint64_t out_capacity = 0) {
   const uint64_t tiles = (uint64_t)g.tiles_per_frame * g.n_frames;
   int rc;
-  if ((rc = c->d_plane_start.reserve(((uint64_t)g.n_frames * 3 + 1) * 8))) return rc;
+  if ((rc = c->d_plane_start.reserve(((uint64_t)g.n_frames * 4 + 2) * 8))) return rc;  // plane starts, then frame bases
   if (!c->d_counters.p) {
     if ((rc = c->d_counters.reserve(64))) return rc;
     CU(cudaMemsetAsync(c->d_counters.p, 0, 64, c->stream));
@@ -148,6 +148,7 @@ int ensure_workspace(myyuvb_ctx* c, const FrameGeom& g, bool encoder, Workspace*
     if ((rc = c->d_tile_prefix.reserve(tiles * 8))) return rc;
   }
   ws->plane_start = c->d_plane_start.as<uint64_t>();
+  ws->frame_base = c->d_plane_start.as<uint64_t>() + ((uint64_t)g.n_frames * 3 + 1);
   ws->counters = c->d_counters.as<uint32_t>();
   ws->chunk_sizes = c->d_sizes.as<uint8_t>();
   ws->overflow = c->d_overflow.as<uint8_t>();

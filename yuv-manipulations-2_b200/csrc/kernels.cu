@@ -188,6 +188,41 @@ MYB_D void copy_global_to_global(uint8_t* __restrict__ dst, const uint8_t* __res
   if (threadIdx.x < n - done) dst[done + threadIdx.x] = src[done + threadIdx.x];
 }
 
+// The same with 128-bit accesses for the bulk: destination-aligned uint4 stores, each built from two source-aligned uint4
+// loads shifted by the (tile-uniform) byte distance between the two alignments.  Head and tail (< 16 bytes each) go
+// bytewise.  Loads stay inside the aligned 16-byte lines that hold at least one source byte.
+MYB_D void copy_global_to_global_v4(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint32_t n, int nthreads, uint32_t t) {
+  const uint32_t head = min((uint32_t)((16 - ((uintptr_t)dst & 15)) & 15), n);
+  if (t < head) dst[t] = src[t];
+  const uint32_t vecs = (n - head) >> 4;
+  uint4* dv = reinterpret_cast<uint4*>(dst + head);
+  const uint8_t* s0 = src + head;
+  const uint32_t mis = (uint32_t)((uintptr_t)s0 & 15);
+  const uint4* sv = reinterpret_cast<const uint4*>(s0 - mis);
+  const uint32_t ws = mis >> 2, bs = (mis & 3) * 8;  // word and bit part of the shift
+  for (uint32_t i = t; i < vecs; i += nthreads) {
+    const uint4 a = sv[i];
+    uint4 b = a;
+    if (mis) b = sv[i + 1];  // holds source bytes 16 i + 16 - mis .. , the first of which is < n
+    uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t x0, x1, x2, x3, x4;
+    switch (ws) {  // uniform over the copy
+      case 0: x0 = w[0]; x1 = w[1]; x2 = w[2]; x3 = w[3]; x4 = w[4]; break;
+      case 1: x0 = w[1]; x1 = w[2]; x2 = w[3]; x3 = w[4]; x4 = w[5]; break;
+      case 2: x0 = w[2]; x1 = w[3]; x2 = w[4]; x3 = w[5]; x4 = w[6]; break;
+      default: x0 = w[3]; x1 = w[4]; x2 = w[5]; x3 = w[6]; x4 = w[7]; break;
+    }
+    uint4 o;
+    o.x = __funnelshift_r(x0, x1, bs);
+    o.y = __funnelshift_r(x1, x2, bs);
+    o.z = __funnelshift_r(x2, x3, bs);
+    o.w = __funnelshift_r(x3, x4, bs);
+    dv[i] = o;
+  }
+  const uint32_t done = head + (vecs << 4);
+  if (t < n - done) dst[done + t] = src[done + t];
+}
+
 // ===================================================================================================
 // Colour conversion  (myyuv_yuv.cpp:34-52, :88-128; row flip of myyuv_bmp.cpp:95-98 folded into addressing)
 // One thread = 8 pixels x 2 rows: four 128-bit loads, two 64-bit Y stores, one 32-bit U and V store.
@@ -553,7 +588,7 @@ __global__ void __launch_bounds__(kCtaThreads, 6)
       // whose position depends on the (data dependent) size of the previous planes
       if (live) P.ws.chunk_sizes[gblk0 + blk] = (uint8_t)size;
       // CTA scan of the chunk sizes.  Between its two barriers thread 0 reserves the tile's place in the scratch area
-      // (bump allocation, completion order; file-order offsets are computed afterwards by scan_tiles_kernel, so no CTA
+      // (bump allocation, completion order; file-order offsets are computed afterwards by the scan kernels, so no CTA
       // ever waits for another one): chunks that do not fit the shared staging buffer are then written straight to it.
       uint32_t pass_total, off;
       {
@@ -612,23 +647,26 @@ __global__ void __launch_bounds__(kCtaThreads, 6)
   }
 }
 
-// Pass 2: exclusive scan of the tile totals in file order (one CTA, 8 tiles per thread per round; a 4K batch of
-// 64 frames has ~10^5 tiles), plus the number of code bytes before every plane.
-constexpr int kScanPerThread = 8;
-__global__ void __launch_bounds__(1024) scan_tiles_kernel(const __grid_constant__ EncParams P) {
-  __shared__ u64 warp_sums[32];
+// Pass 2: exclusive scan of the tile totals in file order, in two levels so that it is not one CTA's latency chain:
+// (a) one CTA per frame scans the frame's tiles (offsets relative to the frame) and leaves the frame total;
+// (b) one CTA scans the frame totals and turns the per-frame plane starts into batch-wide ones.
+constexpr int kScanPerThread = 4;
+__global__ void __launch_bounds__(512) scan_frame_tiles_kernel(const __grid_constant__ EncParams P) {
+  __shared__ u64 warp_sums[16];
   __shared__ u64 carry_s;
   const FrameGeom& g = P.g;
+  const uint32_t f = blockIdx.x;
+  const uint32_t first = f * g.tiles_per_frame, count = g.tiles_per_frame;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (threadIdx.x == 0) carry_s = 0;
   __syncthreads();
-  for (uint32_t base = 0; base < P.total_tiles; base += 1024 * kScanPerThread) {
-    const uint32_t t0 = base + threadIdx.x * kScanPerThread;
+  for (uint32_t base = 0; base < count; base += 512 * kScanPerThread) {
+    const uint32_t r0 = base + threadIdx.x * kScanPerThread;
     uint32_t v[kScanPerThread];
     u64 mine = 0;
 #pragma unroll
     for (int j = 0; j < kScanPerThread; j++) {
-      v[j] = t0 + j < P.total_tiles ? P.ws.tile_total[t0 + j] : 0u;
+      v[j] = r0 + j < count ? P.ws.tile_total[first + r0 + j] : 0u;
       mine += v[j];
     }
     u64 inc = mine;
@@ -640,30 +678,70 @@ __global__ void __launch_bounds__(1024) scan_tiles_kernel(const __grid_constant_
     if (lane == 31) warp_sums[wid] = inc;
     __syncthreads();
     if (wid == 0) {
-      u64 w = warp_sums[lane];
+      u64 w = lane < 16 ? warp_sums[lane] : 0;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
+      for (int o = 1; o < 16; o <<= 1) {
         const u64 n = __shfl_up_sync(0xffffffffu, w, o);
         if (lane >= o) w += n;
       }
-      warp_sums[lane] = w;  // inclusive over warps
+      if (lane < 16) warp_sums[lane] = w;  // inclusive over warps
     }
     __syncthreads();
     const u64 carry = carry_s;
     u64 excl = carry + (wid ? warp_sums[wid - 1] : 0) + inc - mine;
 #pragma unroll
     for (int j = 0; j < kScanPerThread; j++) {
-      const uint32_t t = t0 + j;
-      if (t < P.total_tiles) {
-        P.ws.tile_prefix[t] = excl;
-        // first tile of a plane: code bytes before this plane
-        const uint32_t f = t / g.tiles_per_frame, r = t - f * g.tiles_per_frame;
+      const uint32_t r = r0 + j;
+      if (r < count) {
+        P.ws.tile_prefix[first + r] = excl;  // code bytes of this frame before the tile
+        // first tile of a plane: code bytes of this frame before the plane (made batch-wide by scan_frames_kernel)
         if (r == 0) P.ws.plane_start[f * 3] = excl;
         else if (r == g.tiles[0]) P.ws.plane_start[f * 3 + 1] = excl;
         else if (r == g.tiles[0] + g.tiles[1]) P.ws.plane_start[f * 3 + 2] = excl;
-        if (t == P.total_tiles - 1) P.ws.plane_start[g.n_frames * 3] = excl + v[j];
+        if (r == count - 1) P.ws.frame_base[f] = excl + v[j];  // frame total for now
       }
       excl += v[j];
+    }
+    __syncthreads();
+    if (threadIdx.x == 511) carry_s = carry + warp_sums[15];
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(1024) scan_frames_kernel(const __grid_constant__ EncParams P) {
+  __shared__ u64 warp_sums[32];
+  __shared__ u64 carry_s;
+  const uint32_t n = P.g.n_frames;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < n; base += 1024) {
+    const uint32_t f = base + threadIdx.x;
+    const u64 v = f < n ? P.ws.frame_base[f] : 0;
+    u64 inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const u64 m = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += m;
+    }
+    if (lane == 31) warp_sums[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+      u64 w = warp_sums[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const u64 m = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += m;
+      }
+      warp_sums[lane] = w;
+    }
+    __syncthreads();
+    const u64 carry = carry_s;
+    const u64 excl = carry + (wid ? warp_sums[wid - 1] : 0) + inc - v;
+    if (f < n) {
+      P.ws.frame_base[f] = excl;  // code bytes of the batch before this frame
+      for (int p = 0; p < 3; p++) P.ws.plane_start[f * 3 + p] += excl;
+      if (f == n - 1) P.ws.plane_start[n * 3] = excl + v;
     }
     __syncthreads();
     if (threadIdx.x == 1023) carry_s = carry + warp_sums[31];
@@ -673,20 +751,23 @@ __global__ void __launch_bounds__(1024) scan_tiles_kernel(const __grid_constant_
 
 // Pass 3: move every tile's chunk bytes from the scratch area to their place in the payload.
 // Absolute position = fixed part (headers + size arrays up to this plane) + code bytes before the tile.
+// One warp per tile: the copy of a tile (about 2 KB) is a chain of dependent loads (tile record, then bytes), so the
+// kernel wants many tiles in flight rather than many threads per tile.
 __global__ void __launch_bounds__(256) place_tiles_kernel(const __grid_constant__ EncParams P) {
   const FrameGeom& g = P.g;
-  for (uint32_t tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+  const uint32_t lane = threadIdx.x & 31, warps = gridDim.x * (blockDim.x >> 5);
+  for (uint32_t tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); tile < P.total_tiles; tile += warps) {
     const TileCoord tc = tile_coord(g, tile);
     const int plane = (int)tc.plane;
     const uint32_t total = P.ws.tile_total[tile];
     const u64 src = P.ws.tile_pos[tile];
     const uint32_t fixed = 12 + 8 * (plane + 1) + g.nblk[0] + (plane > 0 ? g.nblk[1] : 0) + (plane > 1 ? g.nblk[2] : 0);
-    const u64 pos = (P.base ? *P.base : 0) + (u64)tc.frame * (36 + g.nblk_frame) + fixed + P.ws.tile_prefix[tile];
+    const u64 pos = (P.base ? *P.base : 0) + (u64)tc.frame * (36 + g.nblk_frame) + fixed + P.ws.frame_base[tc.frame] + P.ws.tile_prefix[tile];
     if (pos + total > P.out_cap || src + total > P.ws.scratch_cap) {
-      if (threadIdx.x == 0) atomicOr(&P.ws.counters[1], kFlagCapacity);
+      if (lane == 0) atomicOr(&P.ws.counters[1], kFlagCapacity);
       continue;
     }
-    copy_global_to_global(P.out + pos, P.ws.scratch + src, total, 256);
+    copy_global_to_global_v4(P.out + pos, P.ws.scratch + src, total, 32, lane);
   }
 }
 
@@ -1084,16 +1165,17 @@ void launch_compress(const uint8_t* d_iyuv, const FrameGeom& g, const QTables& q
   const int grid = (int)(P.total_tiles < (uint32_t)ws.grid ? P.total_tiles : (uint32_t)ws.grid);
   if (ws.k_begin) cudaEventRecord(ws.k_begin, s);
   dct_compress_kernel<<<grid, kCtaThreads, sizeof(EncSmem), s>>>(P, qt);
-  scan_tiles_kernel<<<1, 1024, 0, s>>>(P);
-  const int pgrid = (int)(P.total_tiles < 148u * 16 ? P.total_tiles : 148u * 16);
-  place_tiles_kernel<<<pgrid, 256, 0, s>>>(P);
+  scan_frame_tiles_kernel<<<g.n_frames, 512, 0, s>>>(P);
+  scan_frames_kernel<<<1, 1024, 0, s>>>(P);
+  const uint32_t pwant = (P.total_tiles + 7) / 8;
+  place_tiles_kernel<<<(int)(pwant < 148u * 8 ? pwant : 148u * 8), 256, 0, s>>>(P);
   {
     uint32_t slices = 0;
     for (int p = 0; p < 3; p++) slices += (g.nblk[p] + kSizeSlice - 1) / kSizeSlice;
     finalize_frames_kernel<<<dim3(g.n_frames, slices), 256, 0, s>>>(P, d_offsets);
   }
-  if (ws.k_end) cudaEventRecord(ws.k_end, s);  // the whole compress sequence (4 kernels) is what gets timed
-  g_launches += 4;
+  if (ws.k_end) cudaEventRecord(ws.k_end, s);  // the whole compress sequence (5 kernels) is what gets timed
+  g_launches += 5;
 }
 
 void launch_decompress(const uint8_t* d_payloads, const uint64_t* d_offsets, const FrameGeom& g, const QTables& qt,

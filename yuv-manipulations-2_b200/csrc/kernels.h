@@ -49,6 +49,7 @@ FrameGeom make_geom(uint32_t width, uint32_t height, uint32_t n_frames, uint32_t
 // Device scratch owned by a context (sized for the current batch by capi.cu).
 struct Workspace {
   uint64_t* plane_start;   // [n_frames*3 + 1] code bytes before each plane (compress)
+  uint64_t* frame_base;    // [n_frames] code bytes of the batch before each frame (compress)
   uint32_t* counters;      // [0] tile ticket, [1] error flags, [2..3] u64 scratch bump allocator
   uint8_t* chunk_sizes;    // [n_frames * nblk_frame] per-block chunk size, linear block order (compress)
   uint8_t* overflow;       // [grid * kEncTile * 256] staging overflow area (compress; a chunk is at most 255 bytes)
@@ -56,8 +57,8 @@ struct Workspace {
   uint64_t scratch_cap;
   uint64_t* tile_pos;      // [total tiles] position of each tile's bytes in scratch
   uint32_t* tile_total;    // [total tiles] chunk bytes of each tile
-  uint64_t* tile_prefix;   // [total tiles] chunk bytes before each tile: in file order over the batch (compress,
-                           // scan_tiles_kernel) or inside its plane (decompress, dec_scan_planes_kernel)
+  uint64_t* tile_prefix;   // [total tiles] chunk bytes before each tile: inside its frame (compress,
+                           // scan_frame_tiles_kernel) or inside its plane (decompress, dec_scan_planes_kernel)
   void* plane_desc;        // [n_frames*3] PlaneDesc (decompress)
   int grid;                // persistent grid size of the codec kernels
   cudaEvent_t k_begin, k_end;  // recorded around the main codec kernel of each launch (myyuvb_last_kernel_ms)
