@@ -6,6 +6,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -116,10 +117,11 @@ struct myyuvb_ctx {
   int grid = 0, grid_dec = 0;
   Buffer d_in, d_out, d_plane_start, d_counters, d_sizes, d_overflow, d_desc, d_offsets;
   Buffer d_scratch, d_tile_pos, d_tile_total, d_tile_prefix;
-  Buffer h_small, h_stage_in, h_stage_out;
+  Buffer h_small, h_stage_in, h_stage_out, h_ring;
+  cudaEvent_t ring_ev[4] = {nullptr, nullptr, nullptr, nullptr};  // one per slot of h_ring (pageable <-> device staging)
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t kev[2] = {nullptr, nullptr};  // timing events around the last main codec kernel
-  myyuvb_ctx() { h_small.pinned = h_stage_in.pinned = h_stage_out.pinned = true; }
+  myyuvb_ctx() { h_small.pinned = h_stage_in.pinned = h_stage_out.pinned = h_ring.pinned = true; }
 };
 
 namespace {
@@ -192,6 +194,51 @@ bool is_pinned_or_device(const void* p) {
   return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
+// Host <-> device copies of PAGEABLE host memory (what the class API hands over: YUV::data is new uint8_t[]).
+// Measured on the same box (profiles/host_staging_ab.py): for uploads the driver's own pageable path beats a hand-made
+// ring of pinned slots (one 4K frame: 2.1 vs 2.3 ms per compress call), so uploads go straight to cudaMemcpyAsync;
+// for downloads of 32 MB and more a ring of four 2 MB pinned slots (DMA of slice k+1 in flight during the CPU copy of
+// slice k) wins (one 8K frame: 10 vs 12 ms per decompress call).  MYYUVB_STAGING=direct switches the ring off.
+constexpr size_t kRingSlot = 2u << 20;
+bool ring_enabled() {
+  static const bool on = [] { const char* e = getenv("MYYUVB_STAGING"); return !(e && strcmp(e, "direct") == 0); }();
+  return on;
+}
+
+int staged_upload(myyuvb_ctx* c, void* d_dst, const void* h_src, size_t bytes, cudaStream_t s) {
+  (void)c;
+  if (bytes == 0) return MYYUVB_OK;
+  CU(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, s));
+  return MYYUVB_OK;
+}
+
+int staged_download(myyuvb_ctx* c, void* h_dst, const void* d_src, size_t bytes, cudaStream_t s) {
+  if (bytes == 0) return MYYUVB_OK;
+  if (!ring_enabled() || is_pinned_or_device(h_dst) || bytes < (32u << 20)) {
+    CU(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, s));
+    return MYYUVB_OK;
+  }
+  int rc;
+  if ((rc = c->h_ring.reserve(4 * kRingSlot))) return rc;
+  for (auto& ev : c->ring_ev) CU(cudaEventSynchronize(ev));  // earlier users of the ring have left it
+  const size_t slices = (bytes + kRingSlot - 1) / kRingSlot;
+  auto issue = [&](size_t k) -> int {
+    const size_t off = k * kRingSlot, n = std::min(kRingSlot, bytes - off);
+    CU(cudaMemcpyAsync(c->h_ring.as<uint8_t>() + (k & 3) * kRingSlot, static_cast<const uint8_t*>(d_src) + off, n, cudaMemcpyDeviceToHost, s));
+    CU(cudaEventRecord(c->ring_ev[k & 3], s));
+    return MYYUVB_OK;
+  };
+  for (size_t k = 0; k < std::min<size_t>(3, slices); k++)
+    if ((rc = issue(k))) return rc;
+  for (size_t k = 0; k < slices; k++) {
+    if (k + 3 < slices && (rc = issue(k + 3))) return rc;  // slot (k+3)&3 was drained by the CPU copy of slice k-1
+    CU(cudaEventSynchronize(c->ring_ev[k & 3]));
+    const size_t off = k * kRingSlot, n = std::min(kRingSlot, bytes - off);
+    memcpy(static_cast<uint8_t*>(h_dst) + off, c->h_ring.as<uint8_t>() + (k & 3) * kRingSlot, n);
+  }
+  return MYYUVB_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -223,6 +270,7 @@ int myyuvb_ctx_create(int device, void* stream, myyuvb_ctx** out) {
   }
   CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   for (auto& ev : c->ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  for (auto& ev : c->ring_ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   for (auto& ev : c->kev) CU(cudaEventCreate(&ev));
   c->grid = codec_grid_size(device, true);
   c->grid_dec = codec_grid_size(device, false);
@@ -236,9 +284,11 @@ void myyuvb_ctx_destroy(myyuvb_ctx* c) {
   cudaStreamSynchronize(c->stream);
   cudaStreamSynchronize(c->copy_stream);
   for (Buffer* b : {&c->d_in, &c->d_out, &c->d_plane_start, &c->d_counters, &c->d_sizes,
-                    &c->d_overflow, &c->d_desc, &c->d_offsets, &c->d_scratch, &c->d_tile_pos, &c->d_tile_total, &c->d_tile_prefix, &c->h_small, &c->h_stage_in, &c->h_stage_out})
+                    &c->d_overflow, &c->d_desc, &c->d_offsets, &c->d_scratch, &c->d_tile_pos, &c->d_tile_total, &c->d_tile_prefix, &c->h_small, &c->h_stage_in, &c->h_stage_out, &c->h_ring})
     b->release();
   for (auto& ev : c->ev)
+    if (ev) cudaEventDestroy(ev);
+  for (auto& ev : c->ring_ev)
     if (ev) cudaEventDestroy(ev);
   for (auto& ev : c->kev)
     if (ev) cudaEventDestroy(ev);
@@ -385,9 +435,9 @@ int myyuvb_xrgb_to_iyuv(myyuvb_ctx* c, const uint8_t* bgrx, uint32_t w, uint32_t
   int rc;
   if ((rc = c->d_in.reserve(in_bytes))) return rc;
   if ((rc = c->d_out.reserve(out_bytes))) return rc;
-  CU(cudaMemcpyAsync(c->d_in.p, bgrx, in_bytes, cudaMemcpyHostToDevice, c->stream));
+  if ((rc = staged_upload(c, c->d_in.p, bgrx, in_bytes, c->stream))) return rc;
   if ((rc = myyuvb_xrgb_to_iyuv_batch_dev(c, c->d_in.as<uint8_t>(), w, h, bottom_up, 1, c->d_out.as<uint8_t>()))) return rc;
-  CU(cudaMemcpyAsync(iyuv_out, c->d_out.p, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+  if ((rc = staged_download(c, iyuv_out, c->d_out.p, out_bytes, c->stream))) return rc;
   CU(cudaStreamSynchronize(c->stream));
   return MYYUVB_OK;
 }
@@ -434,8 +484,6 @@ int myyuvb_dct_compress_batch_host(myyuvb_ctx* c, const uint8_t* iyuv, uint32_t 
   if ((rc = c->d_out.reserve(2 * per * bound))) return rc;
   if ((rc = c->d_offsets.reserve(2 * (per + 1) * 8))) return rc;
   if ((rc = c->h_small.reserve(256 + 2 * (per + 1) * 8))) return rc;
-  const bool in_dma = is_pinned_or_device(iyuv), out_dma = is_pinned_or_device(out);
-  if (!in_dma && (rc = c->h_stage_in.reserve(2 * per * frame_bytes))) return rc;
   uint64_t* h_off = reinterpret_cast<uint64_t*>(c->h_small.as<uint8_t>() + 256);
   uint64_t written = 0;
   offsets[0] = 0;
@@ -445,12 +493,8 @@ int myyuvb_dct_compress_batch_host(myyuvb_ctx* c, const uint8_t* iyuv, uint32_t 
     const uint32_t f0 = k * per, nf = std::min(per, n_frames - f0), slot = k & 1;
     const uint8_t* src = iyuv + (uint64_t)f0 * frame_bytes;
     uint8_t* dst = c->d_in.as<uint8_t>() + (uint64_t)slot * per * frame_bytes;
-    if (!in_dma) {
-      uint8_t* st = c->h_stage_in.as<uint8_t>() + (uint64_t)slot * per * frame_bytes;
-      memcpy(st, src, (size_t)nf * frame_bytes);
-      src = st;
-    }
-    CU(cudaMemcpyAsync(dst, src, (size_t)nf * frame_bytes, cudaMemcpyHostToDevice, c->copy_stream));
+    int urc;
+    if ((urc = staged_upload(c, dst, src, (size_t)nf * frame_bytes, c->copy_stream))) return urc;
     CU(cudaEventRecord(c->ev[slot], c->copy_stream));
     return MYYUVB_OK;
   };
@@ -474,8 +518,7 @@ int myyuvb_dct_compress_batch_host(myyuvb_ctx* c, const uint8_t* iyuv, uint32_t 
     if (written + bytes > out_capacity) return fail(MYYUVB_ERR_CAPACITY, "Error. output buffer is too small for the compressed data");
     for (uint32_t i = 0; i <= nf; i++) offsets[f0 + i] = written + (ho[i] - ho[0]);
     // download on the compute stream: the next chunk's kernels use the other output slot
-    CU(cudaMemcpyAsync(out + written, d_dst + ho[0], (size_t)bytes, cudaMemcpyDeviceToHost, c->stream));
-    (void)out_dma;
+    if ((rc = staged_download(c, out + written, d_dst + ho[0], (size_t)bytes, c->stream))) return rc;
     written += bytes;
   }
   return read_flags(c);
@@ -502,22 +545,16 @@ int myyuvb_dct_decompress_batch_host(myyuvb_ctx* c, const uint8_t* payloads, con
   if ((rc = c->d_out.reserve(2 * per * frame_bytes))) return rc;
   if ((rc = c->d_offsets.reserve(2 * (per + 1) * 8))) return rc;
   if ((rc = c->h_small.reserve(256 + 2 * (per + 1) * 8))) return rc;
-  const bool in_dma = is_pinned_or_device(payloads);
-  if (!in_dma && (rc = c->h_stage_in.reserve(2 * (max_in + 16)))) return rc;
   uint64_t* h_off = reinterpret_cast<uint64_t*>(c->h_small.as<uint8_t>() + 256);
   const uint64_t in_slot = (max_in + 16) & ~15ull;
   auto upload = [&](uint32_t k) -> int {
     const uint32_t f0 = k * per, nf = std::min(per, n_frames - f0), slot = k & 1;
     const uint64_t beg = offsets[f0], bytes = offsets[f0 + nf] - beg;
     const uint8_t* src = payloads + beg;
-    if (!in_dma) {
-      uint8_t* st = c->h_stage_in.as<uint8_t>() + (uint64_t)slot * in_slot;
-      memcpy(st, src, (size_t)bytes);
-      src = st;
-    }
     uint64_t* ho = h_off + (uint64_t)slot * (per + 1);
     for (uint32_t i = 0; i <= nf; i++) ho[i] = offsets[f0 + i] - beg;
-    CU(cudaMemcpyAsync(c->d_in.as<uint8_t>() + (uint64_t)slot * in_slot, src, (size_t)bytes, cudaMemcpyHostToDevice, c->copy_stream));
+    int urc;
+    if ((urc = staged_upload(c, c->d_in.as<uint8_t>() + (uint64_t)slot * in_slot, src, (size_t)bytes, c->copy_stream))) return urc;
     CU(cudaMemcpyAsync(c->d_offsets.as<uint64_t>() + (uint64_t)slot * (per + 1), ho, (size_t)(nf + 1) * 8, cudaMemcpyHostToDevice,
                        c->copy_stream));
     CU(cudaEventRecord(c->ev[slot], c->copy_stream));
@@ -531,7 +568,7 @@ int myyuvb_dct_decompress_batch_host(myyuvb_ctx* c, const uint8_t* payloads, con
     if ((rc = myyuvb_dct_decompress_batch_dev(c, c->d_in.as<uint8_t>() + (uint64_t)slot * in_slot,
                                               c->d_offsets.as<uint64_t>() + (uint64_t)slot * (per + 1), w, h, quality, nf, d_dst)))
       return rc;
-    CU(cudaMemcpyAsync(iyuv_out + (uint64_t)f0 * frame_bytes, d_dst, (size_t)nf * frame_bytes, cudaMemcpyDeviceToHost, c->stream));
+    if ((rc = staged_download(c, iyuv_out + (uint64_t)f0 * frame_bytes, d_dst, (size_t)nf * frame_bytes, c->stream))) return rc;
     CU(cudaEventRecord(c->ev[2 + slot], c->stream));
     if (k + 1 < n_chunks) {
       // slot (k+1)&1 was used by chunk k-1: wait until its kernels and download are done before overwriting
