@@ -145,7 +145,11 @@ def reference_main(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    os.environ.setdefault("OMP_NUM_THREADS", str(os.cpu_count() or 1))
+    # All host cores, nested as "1,<cores>" (outer plane loop serial, inner block-row loop parallel: the faster of the two
+    # settings on every box measured, see cpu_baseline_leg).  torchrun exports OMP_NUM_THREADS=1 to its workers, which
+    # would make this arm single-threaded at N > 1, so the variable is overridden unless MYYUV_REF_OMP pins it.
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    os.environ["OMP_NUM_THREADS"] = os.environ.get("MYYUV_REF_OMP", f"1,{ncpu}")
     synth = importlib.import_module("yuv-manipulations-2_b200.synth")
     q = (args.quality,) * 3
     frames = synth.iyuv_frames_numpy(W, H, args.cpu_frames)
@@ -175,7 +179,7 @@ def cpu_baseline_leg(args):
     best = None
     ncpu = os.cpu_count() or 1
     for omp in (str(ncpu), f"1,{ncpu}"):
-        env = dict(os.environ, OMP_NUM_THREADS=omp)
+        env = dict(os.environ, MYYUV_REF_OMP=omp)
         for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
             env.pop(k, None)
         try:
