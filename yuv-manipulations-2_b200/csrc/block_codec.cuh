@@ -1169,6 +1169,45 @@ MYB_HD uint32_t load_window(const uint8_t* data, int byte0, int data_bytes) {
   return w;
 }
 
+// State of the stream reader: rwin holds 32 stream bits starting at byte byte0 of the stream, the first one in bit 31;
+// sh bits of it are consumed, rem = stream bits from the start of the window to the end of the stream.
+struct DecStream {
+  uint32_t rwin;
+  int sh, rem, j, err, byte0;
+};
+
+// PAIRS = code lengths of the table / 2, rounded up to 1, 2 or 4 (warp uniform): how many of the range compares are needed
+template <int PAIRS, int STRIDE, class Emit, class W>
+MYB_HD void decode_stream(DecStream& st, const uint32_t (&kk)[4], int maxlen, const uint8_t* data, int data_bytes,
+                          const DecScratch<STRIDE>& D, Emit& emit, const W& warp) {
+  while (warp.any(st.sh < st.rem && st.j < 64)) {
+    if (st.sh < st.rem && st.j < 64) {
+      if (st.sh > 24) {  // reload the window at the byte that holds the next bit
+        st.byte0 += st.sh >> 3;
+        st.rem -= st.sh & ~7;
+        st.sh &= 7;
+        st.rwin = bit_reverse32(load_window(data, st.byte0, data_bytes));
+      }
+      const uint32_t r = (st.rwin << st.sh) >> 24;  // next 8 bits, first stream bit on top
+      const uint32_t r2 = r * 0x10001u;
+      uint32_t acc = (r2 + kk[0]) & 0x01000100u;
+      if (PAIRS > 1) acc += (r2 + kk[1]) & 0x01000100u;
+      if (PAIRS > 2) acc += ((r2 + kk[2]) & 0x01000100u) + ((r2 + kk[3]) & 0x01000100u);
+      const int len = 1 + (int)((acc * 0x10001u) >> 24);  // both 16-bit fields summed: ranges passed
+      if (len > maxlen || st.sh + len > st.rem) {
+        st.err = 1;  // "Huffman unknown symbol" :139, or the stream ends inside a code: "Huffman bad code" :120-122
+        st.rem = 0;
+      } else {
+        const int idx = (int)(r >> (8 - len)) + D.bs(len - 1);
+        emit(st.j, (int)D.sym(idx));
+        st.j++;
+        st.sh += len;
+      }
+    }
+    warp.sync();
+  }
+}
+
 // Returns 0 (ok), 1 (error: the conditions huff_decode_block reports) or 2 (not handled here, nothing emitted).
 template <int STRIDE, class Emit, class W>
 MYB_HD int huff_decode_fast(const uint8_t* chunk, int size, const DecScratch<STRIDE>& D, Emit&& emit, int* n_emitted, const W& warp) {
@@ -1253,36 +1292,19 @@ MYB_HD int huff_decode_fast(const uint8_t* chunk, int size, const DecScratch<STR
   const int maxlw = warp.max(maxlen);
   const uint8_t* data = groups + table_bytes;
   const int data_bytes = (bits + 7) >> 3;
-  // ---- code stream (Huffman.cpp:106-154).  rwin: 32 stream bits starting at bit pw, the first one in bit 31.
-  int p = 0, j = 0, pw = 0;
-  uint32_t rwin = bit_reverse32(load_window(data, 0, data_bytes));
-  while (warp.any(p < bits && j < 64)) {
-    if (p < bits && j < 64) {
-      if (p - pw > 24) {
-        pw = p & ~7;
-        rwin = bit_reverse32(load_window(data, pw >> 3, data_bytes));
-      }
-      const uint32_t r = (rwin << (p - pw)) >> 24;  // next 8 bits, first stream bit on top
-      const uint32_t r2 = r * 0x10001u;
-      uint32_t acc = (r2 + kk[0]) & 0x01000100u;
-      if (maxlw > 2) acc += (r2 + kk[1]) & 0x01000100u;
-      if (maxlw > 4) acc += (r2 + kk[2]) & 0x01000100u;
-      if (maxlw > 6) acc += (r2 + kk[3]) & 0x01000100u;
-      const int len = 1 + (int)((acc >> 8) & 7u) + (int)(acc >> 24);
-      if (len > maxlen || p + len > bits) {
-        err = 1;  // "Huffman unknown symbol" :139, or the stream ends inside a code: "Huffman bad code" :120-122
-        bits = 0;
-      } else {
-        const int idx = (int)(r >> (8 - len)) + D.bs(len - 1);
-        emit(j, (int)D.sym(idx));
-        j++;
-        p += len;
-      }
-    }
-    warp.sync();
-  }
-  *n_emitted = j;
-  return err ? 1 : (general ? 2 : 0);
+  // ---- code stream (Huffman.cpp:106-154); the loop exists three times, for code tables of up to 2, 4 and 8 lengths
+  DecStream st;
+  st.sh = 0;
+  st.rem = bits;
+  st.j = 0;
+  st.err = err;
+  st.byte0 = 0;
+  st.rwin = bit_reverse32(load_window(data, 0, data_bytes));
+  if (maxlw <= 2) decode_stream<1>(st, kk, maxlen, data, data_bytes, D, emit, warp);
+  else if (maxlw <= 4) decode_stream<2>(st, kk, maxlen, data, data_bytes, D, emit, warp);
+  else decode_stream<4>(st, kk, maxlen, data, data_bytes, D, emit, warp);
+  *n_emitted = st.j;
+  return st.err ? 1 : (general ? 2 : 0);
 }
 
 }  // namespace myyuvb
