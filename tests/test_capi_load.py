@@ -49,10 +49,10 @@ def test_no_fma_contraction_in_sass(pkg):
 
     enc, dec, col = counts("dct_compress_kernel"), counts("dct_decompress_kernel"), counts("xrgb_to_iyuv_kernel")
     assert enc["FFMA"] == 0 and dec["FFMA"] == 0 and col["FFMA"] == 0
-    # decoder: the full transform plus the triangular variants K = 2..7 (4 * sum_c (K - c - 1) + 32 * (K - 1) sums each)
-    tri = sum(4 * (K * (K - 1) // 2) + 32 * (K - 1) for K in range(2, 8))
+    # decoder: the full transform plus the triangular variants K = 4 and 7 (4 * sum_c (K - c - 1) + 32 * (K - 1) sums each)
+    tri = sum(4 * (K * (K - 1) // 2) + 32 * (K - 1) for K in (4, 7))
     assert enc["FFMA2"] == 448 + 64 and dec["FFMA2"] == 448 + tri
-    assert 500 <= enc["FMUL2"] <= 512 + 32 and 1000 <= dec["FMUL2"] <= 512 + sum(2 * K * (K + 1) + 32 * K for K in range(2, 8))  # identical products may be shared (exact)
+    assert 500 <= enc["FMUL2"] <= 512 + 32 and 700 <= dec["FMUL2"] <= 512 + sum(2 * K * (K + 1) + 32 * K for K in (4, 7))  # identical products may be shared (exact)
 
 
 def test_compress_bound(pkg):

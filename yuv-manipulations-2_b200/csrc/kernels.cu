@@ -1109,7 +1109,9 @@ __global__ void __launch_bounds__(kCtaThreads, 6)
     // ---- phase 2: inverse DCT, round, clamp, store ----
     {
       uint32_t outw[16];
-      // zigzag positions 0 .. K (K + 1) / 2 - 1 are the anti-diagonals row + col < K; the variant is chosen per warp
+      // zigzag positions 0 .. K (K + 1) / 2 - 1 are the anti-diagonals row + col < K; the variant is chosen per warp.
+      // Only K = 4 and 7 are instantiated: with all of K = 2..7 the kernel was 8 % slower (instruction cache misses
+      // cost more than the saved multiplies, profiles/r01_notes.md)
       const int nmax = __reduce_max_sync(0xffffffffu, nsym);
       if (nmax <= 1) {
         // DC only: D[a][0] = C[0][a] * B00 and P[a][b] = D[a][0] * C[0][b] with all C[0][.] equal -> a flat block
@@ -1119,16 +1121,8 @@ __global__ void __launch_bounds__(kCtaThreads, 6)
         const uint32_t px = (uint32_t)__viaddmin_s32_relu(__float2int_rz(t), 128, 255) * 0x01010101u;
 #pragma unroll
         for (int r = 0; r < 16; r++) outw[r] = px;
-      } else if (nmax <= 3) {
-        idct_block_tri<2>(col, sm.q, P.one, outw);
-      } else if (nmax <= 6) {
-        idct_block_tri<3>(col, sm.q, P.one, outw);
       } else if (nmax <= 10) {
         idct_block_tri<4>(col, sm.q, P.one, outw);
-      } else if (nmax <= 15) {
-        idct_block_tri<5>(col, sm.q, P.one, outw);
-      } else if (nmax <= 21) {
-        idct_block_tri<6>(col, sm.q, P.one, outw);
       } else if (nmax <= 28) {
         idct_block_tri<7>(col, sm.q, P.one, outw);
       } else {
