@@ -39,8 +39,8 @@ def test_library_is_sm100a_only(pkg):
 
 def test_no_fma_contraction_in_sass(pkg):
     """Bit-exactness needs every product and sum of the DCT and the colour conversion rounded separately.
-    The packed kernels use FMUL2 for products and FFMA2(p, 1.0, acc) for sums (448 per 8x8 transform), plus the
-    64 + 64 true FMAs of the exact-division step in the encoder; a scalar FFMA anywhere would be a contraction."""
+    The packed kernels use FMUL2 for products and FFMA2(p, 1.0, acc) for sums (448 per 8x8 transform when fully
+    unrolled), plus the true FMAs of the exact-division step in the encoder; a scalar FFMA anywhere would be a contraction."""
     sass = subprocess.run(["cuobjdump", "-sass", str(pkg.library_path())], capture_output=True, text=True).stdout
 
     def counts(kernel):
@@ -51,8 +51,10 @@ def test_no_fma_contraction_in_sass(pkg):
     assert enc["FFMA"] == 0 and dec["FFMA"] == 0 and col["FFMA"] == 0
     # decoder: the full transform plus the triangular variants K = 4 and 7 (4 * sum_c (K - c - 1) + 32 * (K - 1) sums each)
     tri = sum(4 * (K * (K - 1) // 2) + 32 * (K - 1) for K in (4, 7))
-    assert enc["FFMA2"] == 448 + 64 and dec["FFMA2"] == 448 + tri
-    assert 500 <= enc["FMUL2"] <= 512 + 32 and 700 <= dec["FMUL2"] <= 512 + sum(2 * K * (K + 1) + 32 * K for K in (4, 7))  # identical products may be shared (exact)
+    # encoder: 224 sums of the first product (unrolled) + 28 of the second, whose loop over the output column is rolled,
+    # + 8 FMAs of the exact-division step in that loop body
+    assert enc["FFMA2"] == 224 + 28 + 8 and dec["FFMA2"] == 448 + tri
+    assert 256 + 32 <= enc["FMUL2"] <= 256 + 32 + 8 and 700 <= dec["FMUL2"] <= 512 + sum(2 * K * (K + 1) + 32 * K for K in (4, 7))  # identical products may be shared (exact)
 
 
 def test_compress_bound(pkg):

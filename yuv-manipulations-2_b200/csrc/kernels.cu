@@ -81,6 +81,15 @@ MYB_D constexpr float dct_c(int i) {
   return t[i];
 }
 
+// row-major coefficient index -> zigzag scan position, for code whose index is not a compile-time constant
+__constant__ uint8_t kZigzagOf[64] = {0,  1,  5,  6,  14, 15, 27, 28, 2,  4,  7,  13, 16, 26, 29, 42, 3,  8,  12, 17, 25, 30,
+                                      41, 43, 9,  11, 18, 24, 31, 40, 44, 53, 10, 19, 23, 32, 39, 45, 52, 54, 20, 22, 33, 38,
+                                      46, 51, 55, 60, 21, 34, 37, 47, 50, 56, 59, 61, 35, 36, 48, 49, 57, 58, 62, 63};
+// The matrix once more in constant memory, for the rolled second product of the forward transform (same bit patterns)
+__constant__ float kDctC[64] = {
+#include "dct_matrix.inc"
+};
+
 // ---------------------------------------------------------------------------------------------------
 // geometry
 // ---------------------------------------------------------------------------------------------------
@@ -431,7 +440,7 @@ MYB_D constexpr int zigzag_of(int i) {
 
 
 // Forward DCT + quantisation of one block.  raw: 8 rows x 2 words of pixels.  Writes the 64 coefficients in
-// zigzag order to zcol[i * kTileBlocks]; returns an upper bound (multiple of 8) of the message length.
+// zigzag order to zcol[i * kTileBlocks]; returns the message length (Huffman.cpp:184-190: trailing zeros are not coded).
 MYB_D int fdct_quant_block(const uint32_t (&raw)[16], const QTables& qt, int plane, float onef, uint16_t* zcol) {
   const f2 ONE = dup(onef);
   // (float)px - 128 (DCT.cpp:303): 0x4B000000 | px is the float 2^23 + px; subtracting 2^23 + 128 is exact
@@ -468,16 +477,21 @@ MYB_D int fdct_quant_block(const uint32_t (&raw)[16], const QTables& qt, int pla
   // The divisor is an integer 1..255, so one Newton step on q0 = Y * RN(1/q) is the correctly rounded quotient:
   // rem = Y - q*q0 is exact, and Y/q is never closer than ulp/510 to a rounding boundary while the step's error is
   // < 2^-23 ulp (DESIGN.md "Exact division"; checked exhaustively around ties by tests/hostemu).
-  int gor[8];
+  // The loop over the output column b is NOT unrolled: its body (4 row pairs x 8 products, quantiser, stores) is 140
+  // instructions instead of 1100 of straight-line code, which the instruction cache feels (profiles/r01_notes.md).
+  // What depends on b comes from constant memory with a warp-uniform index: the matrix row, the quantiser pairs, the
+  // zigzag positions.  Returns the exact message length (last non-zero zigzag position + 1).
+  int L = 0;
+#pragma unroll 1
+  for (int b = 0; b < 8; b++) {
+    float cb[8];
 #pragma unroll
-  for (int g8 = 0; g8 < 8; g8++) gor[g8] = 0;
+    for (int k = 0; k < 8; k++) cb[k] = kDctC[b * 8 + k];
 #pragma unroll
-  for (int a2 = 0; a2 < 4; a2++) {
+    for (int a2 = 0; a2 < 4; a2++) {
+      f2 acc = mul2(t[a2 * 8], dup(cb[0]));
 #pragma unroll
-    for (int b = 0; b < 8; b++) {
-      f2 acc = mul2(t[a2 * 8], dup(dct_c(b * 8)));
-#pragma unroll
-      for (int k = 1; k < 8; k++) acc = sum2(acc, mul2(t[a2 * 8 + k], dup(dct_c(b * 8 + k))), ONE);
+      for (int k = 1; k < 8; k++) acc = sum2(acc, mul2(t[a2 * 8 + k], dup(cb[k])), ONE);
       const f2 r = mkp(qt.rqp[plane][a2 * 8 + b].x, qt.rqp[plane][a2 * 8 + b].y);
       const f2 nq = mkp(qt.nqp[plane][a2 * 8 + b].x, qt.nqp[plane][a2 * 8 + b].y);
       const f2 q0 = mul2(acc, r);
@@ -485,20 +499,15 @@ MYB_D int fdct_quant_block(const uint32_t (&raw)[16], const QTables& qt, int pla
       const f2 q1 = fma2(rem, r, q0);
       const f2 rr = add2_rz(q1, half_like(q1));
       const int na = __float2int_rz(rr.x), nb = __float2int_rz(rr.y);
-      const int za = zigzag_of((2 * a2) * 8 + b), zb = zigzag_of((2 * a2 + 1) * 8 + b);
+      const int za = kZigzagOf[(2 * a2) * 8 + b], zb = kZigzagOf[(2 * a2 + 1) * 8 + b];
       zcol[za * kTileBlocks] = (uint16_t)na;
       zcol[zb * kTileBlocks] = (uint16_t)nb;
-      gor[za >> 3] |= na;
-      gor[zb >> 3] |= nb;
+      if (na != 0) L = max(L, za + 1);
+      if (nb != 0) L = max(L, zb + 1);
     }
   }
-  int lb = 0;
-#pragma unroll
-  for (int g8 = 0; g8 < 8; g8++)
-    if (gor[g8]) lb = 8 * (g8 + 1);
-  return lb;
+  return L;
 }
-
 
 __global__ void __launch_bounds__(kCtaThreads, 6)
     dct_compress_kernel(const __grid_constant__ EncParams P, const __grid_constant__ QTables qt) {
@@ -557,7 +566,6 @@ __global__ void __launch_bounds__(kCtaThreads, 6)
       // (Sorting the tile's blocks by message length so that warps get homogeneous work was tried: it cut issued
       //  instructions by 11% but not the time, because a CTA waits for its slowest warp -- profiles/r01_notes.md.)
       if (!live) L = 0;
-      while (L > 0 && z.get(L - 1) == 0) L--;  // exact message length (Huffman.cpp:184-190); at most 8 steps
       {  // empty the warp's hash table (2 KB, 64 bytes per lane)
         uint4* q = reinterpret_cast<uint4*>(wbase + 2048);
 #pragma unroll
