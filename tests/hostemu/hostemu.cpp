@@ -17,17 +17,13 @@ using namespace myyuvb;
 namespace {
 const uint8_t kZigzag[64] = {MYB_ZIGZAG_LIST};
 
-struct ZArray {  // same views as the kernel's ZShared / ZSlots
+struct ZArray {  // same views as the kernel's ZShared
   int16_t* z;
   int get(int i) const { return ((int)((uint32_t)(uint16_t)z[i] << 21)) >> 21; }
   void set(int i, int v) { z[i] = (int16_t)v; }
   uint32_t raw(int i) const { return (uint16_t)z[i]; }
   void setraw(int i, uint32_t w) { z[i] = (int16_t)(uint16_t)w; }
   int slot(int i) const { return ((uint16_t)z[i] >> 11) & 15; }
-};
-struct ZSlots {
-  int16_t* z;
-  int get(int i) const { return ((uint16_t)z[i] >> 11) & 15; }
 };
 }  // namespace
 

@@ -135,3 +135,19 @@ def test_qtable_formula(ora):
     q1 = ora.qtable(1, False)
     assert q1.max() == 255 and q1.min() == 255  # 50/1 * 10 = 500 -> clamped
     assert ora.qtable(75, False)[0] == 8
+
+
+def test_tiled_real_generator(synth):
+    """natural frames for the side measurements are a base image tiled with a per-frame shift."""
+    rng = np.random.default_rng(0)
+    bw, bh, w, h = 32, 16, 80, 48
+    base = rng.integers(0, 256, bw * bh * 3 // 2, dtype=np.uint8)
+    fr = synth.tiled_real_iyuv(base, bw, bh, w, h, 3, first=1)
+    assert fr.shape == (3, w * h * 3 // 2)
+    Y = base[: bw * bh].reshape(bh, bw)
+    y1 = fr[0, : w * h].reshape(h, w)
+    assert y1[0, 0] == Y[16 % bh, 16 % bw] and y1[5, 7] == Y[(5 + 16) % bh, (7 + 16) % bw]
+    U = base[bw * bh: bw * bh * 5 // 4].reshape(bh // 2, bw // 2)
+    u1 = fr[0, w * h: w * h * 5 // 4].reshape(h // 2, w // 2)
+    assert u1[3, 2] == U[(3 + 8) % (bh // 2), (2 + 8) % (bw // 2)]
+    assert np.array_equal(fr, synth.tiled_real_iyuv(base, bw, bh, w, h, 3, first=1))
