@@ -840,7 +840,7 @@ int codec_grid_size(int device, bool encoder) {
 // ===================================================================================================
 // Decompression (one thread = one block; tile = 128 blocks; six CTAs per SM: 80 registers, 27 KB shared memory)
 // ===================================================================================================
-constexpr int kDecStageBytes = 4 * 1024;
+constexpr int kDecStageBytes = 8 * 1024;
 struct DecSmem {
   int16_t coef[64][kTileBlocks];      // quantised coefficients [k][c] (row-major index), per block column; the
                                       // dequantisation (coef * q, DCT.cpp:330-332) happens when the IDCT loads them
