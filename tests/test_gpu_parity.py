@@ -79,6 +79,38 @@ def test_random_noise_many_symbols(ctx, ora):
         assert np.array_equal(ctx.decompress(got, w, h, q), ora.decompress(want, w, h, q))
 
 
+@pytest.mark.parametrize("q", [(50, 50, 50), (100, 90, 100)])
+def test_batch_with_deferred_blocks(ctx, ora, synth, pkg, q):
+    """Frames that mix smooth content with noise: the noisy blocks have more symbols than the fast path takes, are queued
+    and coded by heavy_blocks_kernel, and their chunks are woven back into the tiles by place_tiles_kernel."""
+    torch = pytest.importorskip("torch")
+    w, h, n = 512, 256, 3
+    rng = np.random.default_rng(11)
+    host = frames(synth, w, h, n, first=7).copy()
+    for i in range(n):
+        Y = host[i, : w * h].reshape(h, w)
+        Y[:, 64 * i: 64 * i + 96] = rng.integers(0, 256, (h, 96), dtype=np.uint8)    # a noisy column band, moves per frame
+        Y[100:108, :] = rng.integers(0, 256, (8, w), dtype=np.uint8)                 # and one noisy row of blocks
+        U = host[i, w * h: w * h * 5 // 4].reshape(h // 2, w // 2)
+        U[16:40, 8:200] = rng.integers(0, 256, (24, 192), dtype=np.uint8)
+    d_in = torch.from_numpy(host).cuda()
+    cap = pkg.capi.compress_bound(w, h) * n
+    d_out = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    d_off = torch.empty(n + 1, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    for _ in range(2):  # twice: the queue and its counters are reused between launches
+        ctx.compress_batch_dev(d_in, w, h, q, n, d_out, cap, d_off)
+        ctx.batch_status()
+        off, out = d_off.cpu().numpy(), d_out.cpu().numpy()
+        for i in range(n):
+            assert np.array_equal(out[off[i]: off[i + 1]], ora.compress(host[i], w, h, q)), f"frame {i}"
+    d_back = torch.zeros_like(d_in)
+    ctx.decompress_batch_dev(d_out, d_off, w, h, q, n, d_back)
+    ctx.batch_status()
+    for i in range(n):
+        assert np.array_equal(d_back[i].cpu().numpy(), ora.decompress(out[off[i]: off[i + 1]], w, h, q))
+
+
 def test_flat_frames_all_zero_blocks(ctx, ora):
     w, h = 64, 48 * 2  # 6144 px
     for level in (0, 128, 255):

@@ -118,6 +118,7 @@ struct myyuvb_ctx {
   int grid = 0, grid_dec = 0;
   Buffer d_in, d_out, d_plane_start, d_counters, d_sizes, d_overflow, d_desc, d_offsets;
   Buffer d_scratch, d_tile_pos, d_tile_total, d_tile_prefix;
+  Buffer d_heavy_rec, d_heavy_coef, d_heavy_bytes, d_block_slot;
   Buffer h_small, h_stage_in, h_stage_out, h_ring;
   cudaEvent_t ring_ev[4] = {nullptr, nullptr, nullptr, nullptr};  // one per slot of h_ring (pageable <-> device staging)
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -145,6 +146,15 @@ int ensure_workspace(myyuvb_ctx* c, const FrameGeom& g, bool encoder, Workspace*
     if ((rc = c->d_tile_pos.reserve(tiles * 8))) return rc;
     if ((rc = c->d_tile_total.reserve(tiles * 4))) return rc;
     if ((rc = c->d_tile_prefix.reserve(tiles * 8))) return rc;
+    // queue of blocks with more than 15 distinct symbols: room for one block in eight (beyond that they are coded in place)
+    const uint64_t nblk_total = (uint64_t)g.nblk_frame * g.n_frames;
+    ws->heavy_cap = nblk_total < 0xfffffff0ull ? (uint32_t)std::max<uint64_t>(1024, nblk_total / 8) : 0u;
+    if (ws->heavy_cap) {
+      if ((rc = c->d_heavy_rec.reserve((uint64_t)ws->heavy_cap * 16))) return rc;
+      if ((rc = c->d_heavy_coef.reserve((uint64_t)ws->heavy_cap * 128))) return rc;
+      if ((rc = c->d_heavy_bytes.reserve((uint64_t)ws->heavy_cap * 256))) return rc;
+      if ((rc = c->d_block_slot.reserve(nblk_total * 4))) return rc;
+    }
   } else {
     if ((rc = c->d_desc.reserve((uint64_t)g.n_frames * 3 * sizeof(PlaneDesc)))) return rc;
     if ((rc = c->d_tile_total.reserve(tiles * 4))) return rc;
@@ -159,6 +169,11 @@ int ensure_workspace(myyuvb_ctx* c, const FrameGeom& g, bool encoder, Workspace*
   ws->tile_pos = c->d_tile_pos.as<uint64_t>();
   ws->tile_total = c->d_tile_total.as<uint32_t>();
   ws->tile_prefix = c->d_tile_prefix.as<uint64_t>();
+  ws->heavy_rec = c->d_heavy_rec.as<uint4>();
+  ws->heavy_coef = c->d_heavy_coef.as<uint16_t>();
+  ws->heavy_bytes = c->d_heavy_bytes.as<uint8_t>();
+  ws->block_slot = c->d_block_slot.as<uint32_t>();
+  if (!encoder) ws->heavy_cap = 0;
   ws->plane_desc = c->d_desc.p;
   ws->grid = encoder ? c->grid : c->grid_dec;
   ws->k_begin = c->kev[0];
@@ -288,7 +303,7 @@ void myyuvb_ctx_destroy(myyuvb_ctx* c) {
   cudaStreamSynchronize(c->copy_stream);
   cudaStreamSynchronize(c->d2h_stream);
   for (Buffer* b : {&c->d_in, &c->d_out, &c->d_plane_start, &c->d_counters, &c->d_sizes,
-                    &c->d_overflow, &c->d_desc, &c->d_offsets, &c->d_scratch, &c->d_tile_pos, &c->d_tile_total, &c->d_tile_prefix, &c->h_small, &c->h_stage_in, &c->h_stage_out, &c->h_ring})
+                    &c->d_overflow, &c->d_desc, &c->d_offsets, &c->d_scratch, &c->d_tile_pos, &c->d_tile_total, &c->d_tile_prefix, &c->d_heavy_rec, &c->d_heavy_coef, &c->d_heavy_bytes, &c->d_block_slot, &c->h_small, &c->h_stage_in, &c->h_stage_out, &c->h_ring})
     b->release();
   for (auto& ev : c->ev)
     if (ev) cudaEventDestroy(ev);
@@ -353,7 +368,7 @@ int compress_dev_impl(myyuvb_ctx* c, const uint8_t* d_iyuv, uint32_t w, uint32_t
   CU(cudaSetDevice(c->device));
   const FrameGeom g = make_geom(w, h, n_frames, kEncTile);
   if ((uint64_t)g.tiles_per_frame * n_frames > 0x7fffffffull) return fail(MYYUVB_ERR_TOO_LARGE, "batch too large");
-  Workspace ws;
+  Workspace ws{};
   if ((rc = ensure_workspace(c, g, true, &ws, out_capacity))) return rc;
   QTables qt;
   make_qtables(quality, &qt);
@@ -412,7 +427,7 @@ int myyuvb_dct_decompress_batch_dev(myyuvb_ctx* c, const uint8_t* d_payloads, co
   CU(cudaSetDevice(c->device));
   const FrameGeom g = make_geom(w, h, n_frames, kDecTile);
   if ((uint64_t)g.tiles_per_frame * n_frames > 0x7fffffffull) return fail(MYYUVB_ERR_TOO_LARGE, "batch too large");
-  Workspace ws;
+  Workspace ws{};
   if ((rc = ensure_workspace(c, g, false, &ws))) return rc;
   QTables qt;
   make_qtables(quality, &qt);

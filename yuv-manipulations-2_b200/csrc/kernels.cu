@@ -405,6 +405,7 @@ struct EncSmem {
   uint32_t warp_sums[4];
   uint32_t tile;
   uint32_t split;
+  uint32_t heavy;            // the tile holds a block that was queued for heavy_blocks_kernel
   u64 base;
 };
 static_assert(sizeof(EncSmem) <= 37 * 1024 - 512, "EncSmem must allow 6 CTAs per SM");
@@ -525,6 +526,7 @@ __global__ void __launch_bounds__(kCtaThreads, 6)
     if (tid == 0) {
       sm.tile = atomicAdd(&P.ws.counters[0], 1u);
       sm.split = 0xffffffffu;
+      sm.heavy = 0;
     }
     __syncthreads();
     const uint32_t tile = sm.tile;
@@ -572,22 +574,49 @@ __global__ void __launch_bounds__(kCtaThreads, 6)
         for (int j = 0; j < 4; j++) q[lane + 32 * j] = make_uint4(~0u, ~0u, ~0u, ~0u);
       }
       __syncwarp();
-      const int nsym = huff_hist(z, L, live, f8, WarpLockstep{});
-      const bool fast = __all_sync(0xffffffffu, nsym >= 0);  // warp-uniform choice of the code path
+      int nsym = huff_hist(z, L, live, f8, WarpLockstep{});
+      // Blocks with more than 15 distinct symbols (0.5 % of the luma blocks of natural images at q 50, every block of
+      // noise at q 100) do not fit the fast path.  Coding one of them in place would send the whole warp through the
+      // general code for it, so they are queued -- coefficient words, block index, message length -- and coded 32 at a
+      // time by heavy_blocks_kernel; here they count as empty chunks.  When the queue is full the warp falls back to
+      // the general code in place.
+      bool fast = true;
+      uint32_t hslot = 0xffffffffu;
+      const uint32_t hmask = __ballot_sync(0xffffffffu, nsym < 0);
+      if (__builtin_expect(hmask != 0u, 0)) {
+        const uint32_t h = (uint32_t)__popc(hmask);
+        uint32_t qbase = 0;
+        if (lane == 0) qbase = atomicAdd(&P.ws.counters[4], h);
+        qbase = __shfl_sync(0xffffffffu, qbase, 0);
+        if (qbase + h <= P.ws.heavy_cap) {
+          if (nsym < 0) {
+            hslot = qbase + (uint32_t)__popc(hmask & ((1u << lane) - 1u));
+            uint32_t* hc = reinterpret_cast<uint32_t*>(P.ws.heavy_coef + (uint64_t)hslot * 64);
+#pragma unroll 4
+            for (int i = 0; i < 32; i++) hc[i] = z.raw(2 * i) | (z.raw(2 * i + 1) << 16);
+            P.ws.heavy_rec[hslot] = make_uint4((uint32_t)(gblk0 + blk), tile, (uint32_t)L, 0u);
+            sm.heavy = 1u;
+            nsym = 0;  // an idle lane of the fast path, chunk size 0 for now
+          }
+        } else {
+          fast = false;
+          // the part of the reservation that lies inside the queue stays unused: mark it, heavy_blocks_kernel skips it
+          if (qbase + lane < P.ws.heavy_cap && lane < h) P.ws.heavy_rec[qbase + lane] = make_uint4(0xffffffffu, 0u, 0u, 0u);
+        }
+      }
       FastPlan pl8{};
       HuffPlan pl{};
       uint8_t lbytes[BigScratch::kBytes];
       int16_t lsyms[BigScratch::kSyms];
       BigScratch bs{lbytes, lsyms};
       uint32_t size;
-      if (fast) {
+      if (__builtin_expect(fast, 1)) {
         pl8 = huff_fast_plan(nsym, L == 0 ? 1 : L, f8, WarpLockstep{});
         size = (uint32_t)pl8.size();
       } else {
-        // A block with more than 15 distinct symbols (noise, q near 100): the whole warp runs the general code in
-        // lockstep on per-thread local-memory scratch (all lanes touch the same offsets together, so the accesses
-        // coalesce in L1).  It redoes the histogram from the coefficient values, which huff_hist left readable in the
-        // low 11 bits of the coefficient words.
+        // the whole warp runs the general code in lockstep on per-thread local-memory scratch (all lanes touch the same
+        // offsets together, so the accesses coalesce in L1).  It redoes the histogram from the coefficient values, which
+        // huff_hist left readable in the low 11 bits of the coefficient words.
         pl = huff_plan(z, L, bs, WarpLockstep{});
         __syncwarp();
         size = live ? (uint32_t)pl.size() : 0u;
@@ -619,12 +648,14 @@ __global__ void __launch_bounds__(kCtaThreads, 6)
         if (tid == 0) {
           const u64 pos = atomicAdd(reinterpret_cast<u64*>(P.ws.counters + 2), (u64)tot);
           P.ws.tile_pos[tile] = pos;
-          P.ws.tile_total[tile] = tot;
+          P.ws.tile_total[tile] = tot | (sm.heavy ? 0x80000000u : 0u);  // bit 31: chunks of queued blocks are still missing
           sm.base = pos;
         }
         __syncthreads();
         off = carried + before + inc - size;
         pass_total = tot;
+        // only place_tiles_kernel's path for tiles with queued blocks reads the slot array
+        if (sm.heavy && live) P.ws.block_slot[gblk0 + blk] = hslot;
       }
       const u64 pos = sm.base;
       const bool room = pos + pass_total <= P.ws.scratch_cap;  // CTA uniform
@@ -634,7 +665,7 @@ __global__ void __launch_bounds__(kCtaThreads, 6)
         uint8_t* dst = fits ? &sm.stage[off] : (room ? P.ws.scratch + pos + off : overflow + off);
         // first chunk that does not fit the shared staging buffer (chunks never straddle; offsets only grow)
         if (live && !fits && off <= (uint32_t)kStageBytes) atomicMin(&sm.split, off);
-        if (fast) {
+        if (__builtin_expect(fast, 1)) {
           huff_fast_emit(z, pl8, f8, dst, WarpLockstep{});
         } else {
           HuffPlan plf = pl;
@@ -652,6 +683,52 @@ __global__ void __launch_bounds__(kCtaThreads, 6)
       }
     }
     __syncthreads();  // shared memory is reused by the next tile
+  }
+}
+
+// Pass 1b: the queued blocks, 32 per warp, through the general code in lockstep.  Writes each chunk to its 256-byte slot,
+// its size to the chunk size array and adds it to the tile total.
+struct HeavySmem {
+  uint16_t zz[64][kTileBlocks];
+};
+struct ZHeavy {  // a column of HeavySmem::zz, value view (low 11 bits, sign extended)
+  uint16_t* col;
+  MYB_D int get(int i) const { return ((int)((uint32_t)col[i * kTileBlocks] << 21)) >> 21; }
+  MYB_D void set(int i, int v) { col[i * kTileBlocks] = (uint16_t)v; }
+};
+__global__ void __launch_bounds__(kCtaThreads) heavy_blocks_kernel(const __grid_constant__ EncParams P) {
+  __shared__ HeavySmem sm;
+  const uint32_t queued = P.ws.counters[4];
+  const uint32_t count = queued < P.ws.heavy_cap ? queued : P.ws.heavy_cap;  // slots past the capacity were never handed out
+  ZHeavy z{&sm.zz[0][threadIdx.x]};
+  for (uint32_t g0 = blockIdx.x * kCtaThreads; g0 < count; g0 += gridDim.x * kCtaThreads) {
+    const uint32_t idx = g0 + threadIdx.x;
+    uint4 rec = make_uint4(0xffffffffu, 0u, 0u, 0u);
+    if (idx < count) rec = P.ws.heavy_rec[idx];
+    const bool live = rec.x != 0xffffffffu;  // a warp that found the queue full leaves its reservation unused
+    if (live) {
+      const uint32_t* hc = reinterpret_cast<const uint32_t*>(P.ws.heavy_coef + (uint64_t)idx * 64);
+#pragma unroll 4
+      for (int i = 0; i < 32; i++) {
+        const uint32_t w = hc[i];
+        z.col[(2 * i) * kTileBlocks] = (uint16_t)w;
+        z.col[(2 * i + 1) * kTileBlocks] = (uint16_t)(w >> 16);
+      }
+    }
+    __syncwarp();
+    uint8_t lbytes[BigScratch::kBytes];
+    int16_t lsyms[BigScratch::kSyms];
+    BigScratch bs{lbytes, lsyms};
+    HuffPlan pl = huff_plan(z, live ? (int)rec.z : 0, bs, WarpLockstep{});
+    __syncwarp();
+    const uint32_t size = live ? (uint32_t)pl.size() : 0u;
+    if (!live) pl.n = 0;
+    huff_emit(z, pl, bs, P.ws.heavy_bytes + (uint64_t)idx * 256, WarpLockstep{});
+    if (live) {
+      P.ws.chunk_sizes[rec.x] = (uint8_t)size;
+      atomicAdd(&P.ws.tile_total[rec.y], size);
+    }
+    __syncwarp();
   }
 }
 
@@ -674,7 +751,7 @@ __global__ void __launch_bounds__(512) scan_frame_tiles_kernel(const __grid_cons
     u64 mine = 0;
 #pragma unroll
     for (int j = 0; j < kScanPerThread; j++) {
-      v[j] = r0 + j < count ? P.ws.tile_total[first + r0 + j] : 0u;
+      v[j] = r0 + j < count ? (P.ws.tile_total[first + r0 + j] & 0x7fffffffu) : 0u;
       mine += v[j];
     }
     u64 inc = mine;
@@ -767,15 +844,58 @@ __global__ void __launch_bounds__(256) place_tiles_kernel(const __grid_constant_
   for (uint32_t tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); tile < P.total_tiles; tile += warps) {
     const TileCoord tc = tile_coord(g, tile);
     const int plane = (int)tc.plane;
-    const uint32_t total = P.ws.tile_total[tile];
+    const uint32_t total_raw = P.ws.tile_total[tile];
+    const uint32_t total = total_raw & 0x7fffffffu;
     const u64 src = P.ws.tile_pos[tile];
     const uint32_t fixed = 12 + 8 * (plane + 1) + g.nblk[0] + (plane > 0 ? g.nblk[1] : 0) + (plane > 1 ? g.nblk[2] : 0);
     const u64 pos = (P.base ? *P.base : 0) + (u64)tc.frame * (36 + g.nblk_frame) + fixed + P.ws.frame_base[tc.frame] + P.ws.tile_prefix[tile];
-    if (pos + total > P.out_cap || src + total > P.ws.scratch_cap) {
+    if (pos + total > P.out_cap) {
       if (lane == 0) atomicOr(&P.ws.counters[1], kFlagCapacity);
       continue;
     }
-    copy_global_to_global_v4(P.out + pos, P.ws.scratch + src, total, 32, lane);
+    if (!(total_raw >> 31)) {
+      if (src + total > P.ws.scratch_cap) {  // the coding pass found no room for this tile (flag already raised there)
+        if (lane == 0) atomicOr(&P.ws.counters[1], kFlagCapacity);
+        continue;
+      }
+      copy_global_to_global_v4(P.out + pos, P.ws.scratch + src, total, 32, lane);
+      continue;
+    }
+    // A tile with queued blocks: the scratch area holds the chunks of the other blocks back to back, the queued ones sit
+    // in their slots.  Every lane takes four consecutive blocks; two warp scans give each block its place in the
+    // payload and in the scratch stream; the chunks are then copied one by one.
+    const u64 gblk0 = (u64)tc.frame * g.nblk_frame + (plane > 0 ? g.nblk[0] : 0) + (plane > 1 ? g.nblk[1] : 0) + tc.k0;
+    uint32_t sz[4], sl[4], all = 0, light = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const uint32_t b = 4 * lane + j;
+      sz[j] = b < tc.nblk ? P.ws.chunk_sizes[gblk0 + b] : 0u;
+      sl[j] = b < tc.nblk ? P.ws.block_slot[gblk0 + b] : 0xffffffffu;
+      all += sz[j];
+      light += sl[j] == 0xffffffffu ? sz[j] : 0u;
+    }
+    uint32_t dsta = all, srca = light;  // inclusive scans over the lanes
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t a = __shfl_up_sync(0xffffffffu, dsta, o), b2 = __shfl_up_sync(0xffffffffu, srca, o);
+      if (lane >= (uint32_t)o) { dsta += a; srca += b2; }
+    }
+    uint32_t doff = dsta - all, soff = srca - light;
+    if (src + __shfl_sync(0xffffffffu, srca, 31) > P.ws.scratch_cap) {
+      if (lane == 0) atomicOr(&P.ws.counters[1], kFlagCapacity);
+      continue;
+    }
+    for (uint32_t owner = 0; owner < 32; owner++) {
+      uint32_t d = __shfl_sync(0xffffffffu, doff, owner), sc = __shfl_sync(0xffffffffu, soff, owner);
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const uint32_t n = __shfl_sync(0xffffffffu, sz[j], owner), slot = __shfl_sync(0xffffffffu, sl[j], owner);
+        const uint8_t* from = slot == 0xffffffffu ? P.ws.scratch + src + sc : P.ws.heavy_bytes + (u64)slot * 256;
+        for (uint32_t i = lane; i < n; i += 32) P.out[pos + d + i] = from[i];
+        d += n;
+        if (slot == 0xffffffffu) sc += n;
+      }
+    }
   }
 }
 
@@ -1162,11 +1282,15 @@ void launch_compress(const uint8_t* d_iyuv, const FrameGeom& g, const QTables& q
     cudaFuncSetAttribute(dct_compress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncSmem));
     attr_set = true;
   }
-  cudaMemsetAsync(ws.counters, 0, 4, s);      // ticket only; error flags accumulate until read
-  cudaMemsetAsync(ws.counters + 2, 0, 8, s);  // scratch bump allocator
+  cudaMemsetAsync(ws.counters, 0, 4, s);       // ticket only; error flags accumulate until read
+  cudaMemsetAsync(ws.counters + 2, 0, 12, s);  // scratch bump allocator, queue of deferred blocks
   const int grid = (int)(P.total_tiles < (uint32_t)ws.grid ? P.total_tiles : (uint32_t)ws.grid);
   if (ws.k_begin) cudaEventRecord(ws.k_begin, s);
   dct_compress_kernel<<<grid, kCtaThreads, sizeof(EncSmem), s>>>(P, qt);
+  if (ws.heavy_cap) {
+    const uint32_t hwant = (ws.heavy_cap + kCtaThreads - 1) / kCtaThreads;
+    heavy_blocks_kernel<<<(int)(hwant < 148u * 8 ? hwant : 148u * 8), kCtaThreads, 0, s>>>(P);
+  }
   scan_frame_tiles_kernel<<<g.n_frames, 512, 0, s>>>(P);
   scan_frames_kernel<<<1, 1024, 0, s>>>(P);
   const uint32_t pwant = (P.total_tiles + 7) / 8;
@@ -1176,8 +1300,8 @@ void launch_compress(const uint8_t* d_iyuv, const FrameGeom& g, const QTables& q
     for (int p = 0; p < 3; p++) slices += (g.nblk[p] + kSizeSlice - 1) / kSizeSlice;
     finalize_frames_kernel<<<dim3(g.n_frames, slices), 256, 0, s>>>(P, d_offsets);
   }
-  if (ws.k_end) cudaEventRecord(ws.k_end, s);  // the whole compress sequence (5 kernels) is what gets timed
-  g_launches += 5;
+  if (ws.k_end) cudaEventRecord(ws.k_end, s);  // the whole compress sequence (6 kernels) is what gets timed
+  g_launches += ws.heavy_cap ? 6 : 5;
 }
 
 void launch_decompress(const uint8_t* d_payloads, const uint64_t* d_offsets, const FrameGeom& g, const QTables& qt,

@@ -50,7 +50,7 @@ FrameGeom make_geom(uint32_t width, uint32_t height, uint32_t n_frames, uint32_t
 struct Workspace {
   uint64_t* plane_start;   // [n_frames*3 + 1] code bytes before each plane (compress)
   uint64_t* frame_base;    // [n_frames] code bytes of the batch before each frame (compress)
-  uint32_t* counters;      // [0] tile ticket, [1] error flags, [2..3] u64 scratch bump allocator
+  uint32_t* counters;      // [0] tile ticket, [1] error flags, [2..3] u64 scratch bump allocator, [4] deferred blocks
   uint8_t* chunk_sizes;    // [n_frames * nblk_frame] per-block chunk size, linear block order (compress)
   uint8_t* overflow;       // [grid * kEncTile * 256] staging overflow area (compress; a chunk is at most 255 bytes)
   uint8_t* scratch;        // [scratch_cap] chunk bytes of all tiles in completion order (compress, pass 1)
@@ -59,6 +59,12 @@ struct Workspace {
   uint32_t* tile_total;    // [total tiles] chunk bytes of each tile
   uint64_t* tile_prefix;   // [total tiles] chunk bytes before each tile: inside its frame (compress,
                            // scan_frame_tiles_kernel) or inside its plane (decompress, dec_scan_planes_kernel)
+  // compress: blocks with more symbols than the fast path takes are queued and coded 32 at a time by heavy_blocks_kernel
+  uint4* heavy_rec;        // [heavy_cap] {block index in the batch, tile, message length, -}; x = 0xffffffff: slot not used
+  uint16_t* heavy_coef;    // [heavy_cap * 64] the block's coefficient words, zigzag order
+  uint8_t* heavy_bytes;    // [heavy_cap * 256] its chunk
+  uint32_t* block_slot;    // [blocks of the batch] queue slot of a deferred block, 0xffffffff otherwise
+  uint32_t heavy_cap;      // 0: nothing is deferred
   void* plane_desc;        // [n_frames*3] PlaneDesc (decompress)
   int grid;                // persistent grid size of the codec kernels
   cudaEvent_t k_begin, k_end;  // recorded around the main codec kernel of each launch (myyuvb_last_kernel_ms)
