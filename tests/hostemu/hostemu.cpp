@@ -99,7 +99,7 @@ int hostemu_encode_blocks(const int16_t* coef, uint32_t n, int stride, int mode,
 // mode 0: the general decoder; mode 1: the kernel's flow (fast decoder, general decoder when it declines).
 // Returns 0, or 1 + index of the first block with an error; *fast_used counts blocks the fast decoder handled.
 int hostemu_decode_blocks2(const uint8_t* chunks, const uint8_t* sizes, uint32_t n, int mode, int16_t* coef, uint32_t* fast_used) {
-  int16_t symtab[16], base[8];
+  int16_t symtab[32], base[8];
   DecScratch<1> D{symtab, base};
   uint32_t used = 0;
   for (uint32_t b = 0; b < n; b++) {

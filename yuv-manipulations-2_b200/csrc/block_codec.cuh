@@ -1141,7 +1141,7 @@ MYB_HD int huff_decode_block(const uint8_t* chunk, int size, Emit&& emit, const 
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Fast decoder for the chunks the reference writes for blocks with at most 15 distinct symbols: one group per code
+// Fast decoder for the chunks the reference writes for blocks with at most 32 distinct symbols: one group per code
 // length, lengths strictly increasing, a prefix code that is not over-subscribed.  Anything else (and every
 // malformed table) is handed to huff_decode_block, which follows the reference's decoder step by step.
 //  * the code table is unpacked once into an array of symbols in canonical order;
@@ -1150,10 +1150,10 @@ MYB_HD int huff_decode_block(const uint8_t* chunk, int size, Emit&& emit, const 
 //    ranges passed is the length, and the symbol index is  code + (symbols before this length - first code);
 //  * the stream is read through a 32-bit window that is reloaded only after 24 consumed bits.
 // ---------------------------------------------------------------------------------------------------
-constexpr int kDecFastSyms = 15;
+constexpr int kDecFastSyms = 32;
 template <int STRIDE>
 struct DecScratch {
-  int16_t* symtab;  // [16] symbols in canonical order
+  int16_t* symtab;  // [32] symbols in canonical order
   int16_t* base;    // [8]  index of the first symbol of length l+1 minus its first code
   MYB_HD int16_t& sym(int k) const { return symtab[k * STRIDE]; }
   MYB_HD int16_t& bs(int l) const { return base[l * STRIDE]; }
@@ -1224,7 +1224,7 @@ MYB_HD int huff_decode_fast(const uint8_t* chunk, int size, const DecScratch<STR
   const uint8_t* groups = chunk + 3;
   // ---- pass 1: one table symbol per step (Huffman.cpp:258-266, :54-69)
   bool general = false;
-  uint32_t cnts = 0;  // symbols per length, 4-bit fields
+  uint32_t cnt_lo = 0, cnt_hi = 0;  // symbols per length, one byte each (lengths 1..4, 5..8)
   int n = 0;
   {
     int gi = 0, ci = 0, cnt = 0, glen = 0, symbase = 0;
@@ -1242,7 +1242,8 @@ MYB_HD int huff_decode_fast(const uint8_t* chunk, int size, const DecScratch<STR
             symbase = gi + 1;
             gi += 1 + ((c * 11 + 7) >> 3);
             if (gi > table_bytes) err = 1;
-            cnts += (uint32_t)c << (4 * (len - 1));
+            if (len <= 4) cnt_lo += (uint32_t)c << (8 * (len - 1));
+            else cnt_hi += (uint32_t)c << (8 * (len - 5));
           }
         }
         if (!err && !general) {
@@ -1268,7 +1269,7 @@ MYB_HD int huff_decode_fast(const uint8_t* chunk, int size, const DecScratch<STR
 #pragma unroll
 #endif
     for (int l = 0; l < 8; l++) {
-      const uint32_t c = (cnts >> (4 * l)) & 15u;
+      const uint32_t c = ((l < 4 ? cnt_lo >> (8 * l) : cnt_hi >> (8 * (l - 4)))) & 0xffu;
       D.bs(l) = (int16_t)((int)off - (int)first);
       const uint32_t end = first + c;
       if (end > (2u << l)) general = true;  // more codes of this length than exist: let the general decoder reproduce the reference
@@ -1281,7 +1282,7 @@ MYB_HD int huff_decode_fast(const uint8_t* chunk, int size, const DecScratch<STR
 #pragma unroll
 #endif
     for (int l = 0; l < 8; l++) {
-      const uint32_t c = (cnts >> (4 * l)) & 15u;
+      const uint32_t c = ((l < 4 ? cnt_lo >> (8 * l) : cnt_hi >> (8 * (l - 4)))) & 0xffu;
       const uint32_t end = first + c;
       const uint32_t k = l < maxlen ? 256u - ((end << (7 - l)) & 0x1ffu) : 0u;
       kk[l >> 1] |= k << (16 * (l & 1));

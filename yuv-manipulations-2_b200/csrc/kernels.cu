@@ -965,7 +965,7 @@ struct DecSmem {
   int16_t coef[64][kTileBlocks];      // quantised coefficients [k][c] (row-major index), per block column; the
                                       // dequantisation (coef * q, DCT.cpp:330-332) happens when the IDCT loads them
   alignas(16) uint8_t stage[kDecStageBytes + 16];  // the tile's chunk bytes, shifted by the source's offset in its 16-byte line
-  int16_t symtab[16][kTileBlocks];    // fast decoder: the block's symbols in canonical order
+  int16_t symtab[32][kTileBlocks];    // fast decoder: the block's symbols in canonical order
   int16_t lenbase[8][kTileBlocks];    // fast decoder: symbol index offsets per code length
   float q[64];                        // dequantisation factors of the current plane, row-major
   uint16_t zoff[64];                  // per zigzag position: byte offset in a coef column
