@@ -687,21 +687,29 @@ __global__ void __launch_bounds__(kCtaThreads, 6)
 }
 
 // Pass 1b: the queued blocks, 32 per warp, through the general code in lockstep.  Writes each chunk to its 256-byte slot,
-// its size to the chunk size array and adds it to the tile total.
+// its size to the chunk size array and adds it to the tile total.  The coder's scratch (773 bytes per block) lives in
+// shared memory, lanes interleaved: in local memory it overflowed L1 and the kernel sat on the long scoreboard for 75 %
+// of its time.  64 threads per CTA so that three CTAs fit an SM.
+constexpr int kHeavyThreads = 64;
+using HeavyScratch = HuffScratch<64, kHeavyThreads>;
 struct HeavySmem {
-  uint16_t zz[64][kTileBlocks];
+  uint16_t zz[64][kHeavyThreads];
+  int16_t syms[HeavyScratch::kSyms][kHeavyThreads];
+  uint8_t bytes[HeavyScratch::kBytes][kHeavyThreads];
 };
 struct ZHeavy {  // a column of HeavySmem::zz, value view (low 11 bits, sign extended)
   uint16_t* col;
-  MYB_D int get(int i) const { return ((int)((uint32_t)col[i * kTileBlocks] << 21)) >> 21; }
-  MYB_D void set(int i, int v) { col[i * kTileBlocks] = (uint16_t)v; }
+  MYB_D int get(int i) const { return ((int)((uint32_t)col[i * kHeavyThreads] << 21)) >> 21; }
+  MYB_D void set(int i, int v) { col[i * kHeavyThreads] = (uint16_t)v; }
 };
-__global__ void __launch_bounds__(kCtaThreads) heavy_blocks_kernel(const __grid_constant__ EncParams P) {
-  __shared__ HeavySmem sm;
+__global__ void __launch_bounds__(kHeavyThreads) heavy_blocks_kernel(const __grid_constant__ EncParams P) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  HeavySmem& sm = *reinterpret_cast<HeavySmem*>(smem_raw);
   const uint32_t queued = P.ws.counters[4];
   const uint32_t count = queued < P.ws.heavy_cap ? queued : P.ws.heavy_cap;  // slots past the capacity were never handed out
   ZHeavy z{&sm.zz[0][threadIdx.x]};
-  for (uint32_t g0 = blockIdx.x * kCtaThreads; g0 < count; g0 += gridDim.x * kCtaThreads) {
+  HeavyScratch bs{&sm.bytes[0][threadIdx.x], &sm.syms[0][threadIdx.x]};
+  for (uint32_t g0 = blockIdx.x * kHeavyThreads; g0 < count; g0 += gridDim.x * kHeavyThreads) {
     const uint32_t idx = g0 + threadIdx.x;
     uint4 rec = make_uint4(0xffffffffu, 0u, 0u, 0u);
     if (idx < count) rec = P.ws.heavy_rec[idx];
@@ -711,14 +719,11 @@ __global__ void __launch_bounds__(kCtaThreads) heavy_blocks_kernel(const __grid_
 #pragma unroll 4
       for (int i = 0; i < 32; i++) {
         const uint32_t w = hc[i];
-        z.col[(2 * i) * kTileBlocks] = (uint16_t)w;
-        z.col[(2 * i + 1) * kTileBlocks] = (uint16_t)(w >> 16);
+        z.col[(2 * i) * kHeavyThreads] = (uint16_t)w;
+        z.col[(2 * i + 1) * kHeavyThreads] = (uint16_t)(w >> 16);
       }
     }
     __syncwarp();
-    uint8_t lbytes[BigScratch::kBytes];
-    int16_t lsyms[BigScratch::kSyms];
-    BigScratch bs{lbytes, lsyms};
     HuffPlan pl = huff_plan(z, live ? (int)rec.z : 0, bs, WarpLockstep{});
     __syncwarp();
     const uint32_t size = live ? (uint32_t)pl.size() : 0u;
@@ -1288,8 +1293,13 @@ void launch_compress(const uint8_t* d_iyuv, const FrameGeom& g, const QTables& q
   if (ws.k_begin) cudaEventRecord(ws.k_begin, s);
   dct_compress_kernel<<<grid, kCtaThreads, sizeof(EncSmem), s>>>(P, qt);
   if (ws.heavy_cap) {
-    const uint32_t hwant = (ws.heavy_cap + kCtaThreads - 1) / kCtaThreads;
-    heavy_blocks_kernel<<<(int)(hwant < 148u * 8 ? hwant : 148u * 8), kCtaThreads, 0, s>>>(P);
+    static bool heavy_attr = false;
+    if (!heavy_attr) {
+      cudaFuncSetAttribute(heavy_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HeavySmem));
+      heavy_attr = true;
+    }
+    const uint32_t hwant = (ws.heavy_cap + kHeavyThreads - 1) / kHeavyThreads;
+    heavy_blocks_kernel<<<(int)(hwant < 148u * 6 ? hwant : 148u * 6), kHeavyThreads, sizeof(HeavySmem), s>>>(P);
   }
   scan_frame_tiles_kernel<<<g.n_frames, 512, 0, s>>>(P);
   scan_frames_kernel<<<1, 1024, 0, s>>>(P);
