@@ -88,7 +88,8 @@ struct HuffScratch {
   static constexpr int kLen = kPar + 2 * CAP;    // [CAP]   code length of slot s
   static constexpr int kCode = kLen + CAP;       // [CAP]   bit-reversed canonical code of slot s
   static constexpr int kSorted = kCode + CAP;    // [CAP]   slots ordered by (length, symbol value)
-  static constexpr int kBytes = kSorted + CAP;   // bytes per block
+  static constexpr int kLut = kSorted + CAP;     // [128] slot of the value v at index v + 64, 0xff = not seen (histogram only)
+  static constexpr int kBytes = kLut + 128;      // bytes per block
   static constexpr int kSyms = CAP + 1;          // int16 per block
   MYB_HD uint8_t& at(int off, int i) const { return b[(off + i) * STRIDE]; }
   MYB_HD int16_t& sym(int i) const { return h[i * STRIDE]; }
@@ -234,23 +235,24 @@ MYB_HD HuffPlan huff_plan_tail(int L, int n, int zero_slot, bool bail, const Huf
 template <int CAP, int STRIDE, class Z, class W>
 MYB_HD HuffPlan huff_plan(Z& z, int L, const HuffScratch<CAP, STRIDE>& S, const W& warp) {
   // ---- histogram in first-occurrence order (Huffman.cpp:176-189, message part only; the trailing zeros
-  // only matter through the key 0 they may add to the map, handled below).  Coefficients in [-8, 7] find
-  // their slot through a 16 x 4-bit table held in a register pair; the rest by a short linear search.
+  // only matter through the key 0 they may add to the map, handled below).  Coefficients in [-64, 63] find
+  // their slot through a 128-byte table in the scratch; the rest by a linear search.
   int n = 0, zero_slot = -1;
   bool bail = false;
-  uint64_t small = ~0ull;  // nibble v+8: slot of value v, 0xF = not seen (or slot >= 15)
   const int Lw = warp.max(L);
+  if (Lw > 0) {
+    for (int i = 0; i < 128; i++) S.at(S.kLut, i) = 0xff;
+  }
   MYB_NOUNROLL
   for (int i = 0; i < Lw; i++) {
     if (i < L && !bail) {
       const int v = z.get(i);
-      const unsigned vi = (unsigned)(v + 8);
+      const unsigned vi = (unsigned)(v + 64);
       int s = -1;
-      if (vi < 16u) {
-        const int t = (int)((small >> (4 * vi)) & 15u);
-        if (t != 15) s = t;
-      }
-      if (s < 0 && (vi >= 16u || n > 15)) {  // not answered by the table: short linear search
+      if (vi < 128u) {
+        const int t = S.at(S.kLut, (int)vi);
+        if (t != 0xff) s = t;
+      } else {
         int k = 0;
         while (k < n && S.sym(k) != v) k++;
         if (k < n) s = k;
@@ -264,7 +266,7 @@ MYB_HD HuffPlan huff_plan(Z& z, int L, const HuffScratch<CAP, STRIDE>& S, const 
           S.sym(s) = (int16_t)v;
           S.at(S.kCnt, s) = 0;
           if (v == 0) zero_slot = s;
-          if (vi < 16u && s < 15) small = (small & ~(15ull << (4 * vi))) | ((uint64_t)s << (4 * vi));
+          if (vi < 128u) S.at(S.kLut, (int)vi) = (uint8_t)s;
         }
       }
       if (!bail) {
