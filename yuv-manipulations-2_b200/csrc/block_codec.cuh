@@ -80,16 +80,22 @@ struct HuffScratch {
   uint8_t* b;
   int16_t* h;
   static constexpr int kCap = CAP;
+  // Arrays that are never live at the same time share their bytes (the scratch of 64-symbol blocks sits in shared memory
+  // in heavy_blocks_kernel, where every byte per lane costs occupancy):
+  //   list order -> (dead after the code lengths are assigned) -> canonical codes
+  //   bucket list, then heap -> (dead after the merges) -> sorted slots
+  //   node weights -> (dead after the merges) -> code lengths
+  //   value table of the histogram -> (dead after the histogram) -> parent links / depths
   static constexpr int kCnt = 0;                 // [CAP+1] occurrences of slot s in the message
   static constexpr int kOrd = kCnt + CAP + 1;    // [CAP+1] hash-list order: slot at list position p
+  static constexpr int kCode = kOrd;             // [CAP]   bit-reversed canonical code of slot s
   static constexpr int kBkt = kOrd + CAP + 1;    // [CAP+1] bucket of list position p; later: heap
+  static constexpr int kSorted = kBkt;           // [CAP]   slots ordered by (length, symbol value)
   static constexpr int kFreq = kBkt + CAP + 1;   // [2*CAP] node weight
+  static constexpr int kLen = kFreq;             // [CAP]   code length of slot s
   static constexpr int kPar = kFreq + 2 * CAP;   // [2*CAP] parent node, then depth
-  static constexpr int kLen = kPar + 2 * CAP;    // [CAP]   code length of slot s
-  static constexpr int kCode = kLen + CAP;       // [CAP]   bit-reversed canonical code of slot s
-  static constexpr int kSorted = kCode + CAP;    // [CAP]   slots ordered by (length, symbol value)
-  static constexpr int kLut = kSorted + CAP;     // [128] slot of the value v at index v + 64, 0xff = not seen (histogram only)
-  static constexpr int kBytes = kLut + 128;      // bytes per block
+  static constexpr int kLut = 2 * CAP >= 128 ? kPar : kPar + 2 * CAP;  // [128] slot of the value v at index v + 64, 0xff = not seen
+  static constexpr int kBytes = kLut + (2 * CAP >= 128 ? 2 * CAP : 128);  // bytes per block
   static constexpr int kSyms = CAP + 1;          // int16 per block
   MYB_HD uint8_t& at(int off, int i) const { return b[(off + i) * STRIDE]; }
   MYB_HD int16_t& sym(int i) const { return h[i * STRIDE]; }
