@@ -233,7 +233,7 @@ def test_full_pipeline_xrgb_to_payload(ctx, ora, synth, pkg, chunk, keep_iyuv):
 
 
 def test_batch_host_api_multi_chunk(ctx, ora, synth, pkg):
-    # 1920x1088 frames are 3.1 MB: 30 frames span two 64 MB pipeline chunks
+    # 1920x1088 frames are 3.1 MB: 30 frames span three 32 MB pipeline chunks
     w, h, n, q = 1920, 1088, 30, (50, 50, 50)
     host = frames(synth, w, h, n)
     cap = 40 << 20
@@ -246,6 +246,35 @@ def test_batch_host_api_multi_chunk(ctx, ora, synth, pkg):
     ctx.decompress_batch_host(out, off, w, h, q, n, back)
     for i in (0, 19, 20, 21, 29):
         assert np.array_equal(back[i], ora.decompress(out[int(off[i]): int(off[i + 1])], w, h, q))
+
+
+def test_batch_host_api_pinned_buffers(ctx, ora, synth, pkg):
+    """Pinned (mapped) caller buffers take the SM-copy path for payloads and offsets; payloads start at arbitrary byte
+    positions of the caller's buffer, so the copy kernel's unaligned cases are all met.  Same bytes as pageable buffers."""
+    w, h, n, q = 1920, 1088, 24, (50, 50, 50)
+    host = frames(synth, w, h, n)
+    fb = w * h * 3 // 2
+    pin_in, pin_out, pin_back = pkg.capi.PinnedBuffer(n * fb), pkg.capi.PinnedBuffer((30 << 20) + 3), pkg.capi.PinnedBuffer(n * fb)
+    pin_in.array[:] = host.reshape(-1)
+    out_p, off_p = pin_out.array[3:], np.zeros(n + 1, np.uint64)      # odd start address
+    ctx.compress_batch_host(pin_in.array, w, h, q, n, out_p, off_p)
+    out, off = np.empty(30 << 20, np.uint8), np.zeros(n + 1, np.uint64)
+    ctx.compress_batch_host(host, w, h, q, n, out, off)
+    assert np.array_equal(off, off_p)
+    total = int(off[n])
+    assert np.array_equal(out[:total], out_p[:total])
+    for i in (0, 9, 10, 23):
+        assert np.array_equal(out_p[int(off[i]): int(off[i + 1])], ora.compress(host[i], w, h, q)), f"frame {i}"
+    ctx.decompress_batch_host(out_p, off_p, w, h, q, n, pin_back.array)
+    back = np.empty_like(host)
+    ctx.decompress_batch_host(out, off, w, h, q, n, back)
+    assert np.array_equal(back.reshape(-1), pin_back.array)
+    assert np.array_equal(back[11], ora.decompress(out[int(off[11]): int(off[12])], w, h, q))
+    # a payload buffer that is too small is still reported, and the context stays usable
+    with pytest.raises(pkg.MyyuvError):
+        ctx.compress_batch_host(pin_in.array, w, h, q, n, pin_out.array[: total // 2], off_p)
+    ctx.compress_batch_host(pin_in.array, w, h, q, n, out_p, off_p)
+    assert np.array_equal(out[:total], out_p[:total])
 
 
 def test_round_trip_properties_4k(ctx, synth):

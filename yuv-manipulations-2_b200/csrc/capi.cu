@@ -74,7 +74,7 @@ struct Buffer {
     if (bytes <= cap) return MYYUVB_OK;
     release();
     const size_t want = bytes + bytes / 8 + 256;
-    cudaError_t e = pinned ? cudaHostAlloc(&p, want, cudaHostAllocDefault) : cudaMalloc(&p, want);
+    cudaError_t e = pinned ? cudaHostAlloc(&p, want, cudaHostAllocMapped | cudaHostAllocPortable) : cudaMalloc(&p, want);
     if (e != cudaSuccess) {
       p = nullptr;
       return fail(MYYUVB_ERR_CUDA, std::string("CUDA error: ") + cudaGetErrorString(e) + " allocating " + std::to_string(want) + " bytes");
@@ -112,7 +112,7 @@ int check_dims(uint32_t w, uint32_t h) {
 
 struct myyuvb_ctx {
   int device = 0;
-  cudaStream_t stream = nullptr, copy_stream = nullptr, d2h_stream = nullptr;
+  cudaStream_t stream = nullptr, copy_stream = nullptr, d2h_stream = nullptr, hi_stream = nullptr;
   cudaEvent_t d2h_ev[2] = {nullptr, nullptr};  // per output slot: the download of the chunk that last used it
   bool own_stream = false;
   int grid = 0, grid_dec = 0;
@@ -194,8 +194,10 @@ int flags_to_error(uint32_t flags) {
 int read_flags(myyuvb_ctx* c) {
   int rc;
   if ((rc = c->h_small.reserve(256))) return rc;
-  uint32_t* h = c->h_small.as<uint32_t>();
-  CU(cudaMemcpyAsync(h, c->d_counters.as<uint32_t>() + 1, 4, cudaMemcpyDeviceToHost, c->stream));
+  volatile uint32_t* h = c->h_small.as<uint32_t>();
+  uint32_t* h_dev = nullptr;
+  CU(cudaHostGetDevicePointer(reinterpret_cast<void**>(&h_dev), c->h_small.p, 0));
+  launch_publish_words(h_dev, c->d_counters.as<uint32_t>() + 1, 1, c->stream);  // no copy engine: see launch_publish_words
   CU(cudaMemsetAsync(c->d_counters.as<uint32_t>() + 1, 0, 4, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   return flags_to_error(*h);
@@ -216,24 +218,98 @@ bool is_pinned_or_device(const void* p) {
 // for downloads of 32 MB and more a ring of four 2 MB pinned slots (DMA of slice k+1 in flight during the CPU copy of
 // slice k) wins (one 8K frame: 10 vs 12 ms per decompress call).  MYYUVB_STAGING=direct switches the ring off.
 constexpr size_t kRingSlot = 2u << 20;
+constexpr long kDefaultCopyPieceMB = 0;
+constexpr bool kDefaultOwnD2H = true;
+constexpr int kDefaultSmallCopy = 2;
+constexpr long kDefaultChunkMB = 32;
 bool ring_enabled() {
   static const bool on = [] { const char* e = getenv("MYYUVB_STAGING"); return !(e && strcmp(e, "direct") == 0); }();
   return on;
 }
 
+// Large copies are issued in pieces so that another context's small transfer in the same direction (the copy engines
+// serve their queues first come, first served) waits for one piece, not for a whole chunk.  MYYUVB_COPY_PIECE_MB=0: whole.
+size_t copy_piece_bytes() {
+  static const size_t piece = [] {
+    const char* e = getenv("MYYUVB_COPY_PIECE_MB");
+    const long mb = e ? atol(e) : kDefaultCopyPieceMB;
+    return mb > 0 ? (size_t)mb << 20 : ~(size_t)0;
+  }();
+  return piece;
+}
+
+int copy_in_pieces(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, cudaStream_t s) {
+  const size_t piece = copy_piece_bytes();
+  for (size_t off = 0; off < bytes; off += std::min(piece, bytes - off))
+    CU(cudaMemcpyAsync(static_cast<uint8_t*>(dst) + off, static_cast<const uint8_t*>(src) + off, std::min(piece, bytes - off), kind, s));
+  return MYYUVB_OK;
+}
+
+// batch_host calls: bytes of IYUV per pipeline chunk (MYYUVB_CHUNK_MB)
+uint64_t host_chunk_bytes() {
+  static const uint64_t b = [] {
+    const char* e = getenv("MYYUVB_CHUNK_MB");
+    const long mb = e ? atol(e) : kDefaultChunkMB;
+    return (uint64_t)(mb > 0 ? mb : kDefaultChunkMB) << 20;
+  }();
+  return b;
+}
+
+// batch_host calls: downloads on their own stream (MYYUVB_D2H_STREAM=0: on the kernel stream)
+bool own_d2h_stream() {
+  static const bool on = [] { const char* e = getenv("MYYUVB_D2H_STREAM"); return e ? e[0] == '1' : kDefaultOwnD2H; }();
+  return on;
+}
+
+// The small side of a batch_host call (payloads): 0 = copy engine on the usual stream, 1 = copy engine on a high-priority
+// stream, 2 = SM copy kernel when the host buffer is mapped pinned memory (else 0).
+int small_copy_mode() {
+  static const int m = [] { const char* e = getenv("MYYUVB_SMALL_COPY"); return e ? atoi(e) : kDefaultSmallCopy; }();
+  return m;
+}
+
+// device-side address of h if it lies in mapped pinned host memory, else nullptr
+uint8_t* mapped_devptr(const void* h) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, h) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return a.type == cudaMemoryTypeHost ? static_cast<uint8_t*>(a.devicePointer) : nullptr;
+}
+
+int small_upload(myyuvb_ctx* c, void* d_dst, const void* h_src, size_t bytes, cudaStream_t s) {
+  if (small_copy_mode() == 2)
+    if (const uint8_t* dp = mapped_devptr(h_src)) {
+      launch_sm_copy(static_cast<uint8_t*>(d_dst), dp, bytes, s);
+      CU(cudaGetLastError());
+      return MYYUVB_OK;
+    }
+  if (bytes == 0) return MYYUVB_OK;
+  return copy_in_pieces(d_dst, h_src, bytes, cudaMemcpyHostToDevice, s);
+}
+
+int staged_download(myyuvb_ctx* c, void* h_dst, const void* d_src, size_t bytes, cudaStream_t s);
+int small_download(myyuvb_ctx* c, void* h_dst, const void* d_src, size_t bytes, cudaStream_t s) {
+  if (small_copy_mode() == 2)
+    if (uint8_t* dp = mapped_devptr(h_dst)) {
+      launch_sm_copy(dp, static_cast<const uint8_t*>(d_src), bytes, s);
+      CU(cudaGetLastError());
+      return MYYUVB_OK;
+    }
+  return staged_download(c, h_dst, d_src, bytes, s);
+}
+
 int staged_upload(myyuvb_ctx* c, void* d_dst, const void* h_src, size_t bytes, cudaStream_t s) {
   (void)c;
   if (bytes == 0) return MYYUVB_OK;
-  CU(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, s));
-  return MYYUVB_OK;
+  return copy_in_pieces(d_dst, h_src, bytes, cudaMemcpyHostToDevice, s);
 }
 
 int staged_download(myyuvb_ctx* c, void* h_dst, const void* d_src, size_t bytes, cudaStream_t s) {
   if (bytes == 0) return MYYUVB_OK;
-  if (!ring_enabled() || is_pinned_or_device(h_dst) || bytes < (32u << 20)) {
-    CU(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, s));
-    return MYYUVB_OK;
-  }
+  if (!ring_enabled() || is_pinned_or_device(h_dst) || bytes < (32u << 20))
+    return copy_in_pieces(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, s);
   int rc;
   if ((rc = c->h_ring.reserve(4 * kRingSlot))) return rc;
   for (auto& ev : c->ring_ev) CU(cudaEventSynchronize(ev));  // earlier users of the ring have left it
@@ -286,6 +362,11 @@ int myyuvb_ctx_create(int device, void* stream, myyuvb_ctx** out) {
   }
   CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+  {
+    int lo = 0, hi = 0;
+    CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CU(cudaStreamCreateWithPriority(&c->hi_stream, cudaStreamNonBlocking, hi));
+  }
   for (auto& ev : c->d2h_ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   for (auto& ev : c->ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   for (auto& ev : c->ring_ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -302,6 +383,7 @@ void myyuvb_ctx_destroy(myyuvb_ctx* c) {
   cudaStreamSynchronize(c->stream);
   cudaStreamSynchronize(c->copy_stream);
   cudaStreamSynchronize(c->d2h_stream);
+  cudaStreamSynchronize(c->hi_stream);
   for (Buffer* b : {&c->d_in, &c->d_out, &c->d_plane_start, &c->d_counters, &c->d_sizes,
                     &c->d_overflow, &c->d_desc, &c->d_offsets, &c->d_scratch, &c->d_tile_pos, &c->d_tile_total, &c->d_tile_prefix, &c->d_heavy_rec, &c->d_heavy_coef, &c->d_heavy_bytes, &c->d_block_slot, &c->h_small, &c->h_stage_in, &c->h_stage_out, &c->h_ring})
     b->release();
@@ -316,6 +398,7 @@ void myyuvb_ctx_destroy(myyuvb_ctx* c) {
   if (c->own_stream) cudaStreamDestroy(c->stream);
   cudaStreamDestroy(c->copy_stream);
   cudaStreamDestroy(c->d2h_stream);
+  cudaStreamDestroy(c->hi_stream);
   delete c;
 }
 
@@ -500,17 +583,22 @@ int myyuvb_dct_compress_batch_host(myyuvb_ctx* c, const uint8_t* iyuv, uint32_t 
   CU(cudaSetDevice(c->device));
   const uint64_t frame_bytes = (uint64_t)w * h * 3 / 2;
   const uint64_t bound = myyuvb_compress_bound(w, h);
-  // chunk size: ~64 MB of input per chunk, at least one frame
-  const uint32_t per = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(n_frames, (64ull << 20) / frame_bytes));
+  // chunk size: ~32 MB of input per chunk, at least one frame
+  const uint32_t per = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(n_frames, host_chunk_bytes() / frame_bytes));
   if ((rc = c->d_in.reserve(2 * per * frame_bytes))) return rc;
   if ((rc = c->d_out.reserve(2 * per * bound))) return rc;
   if ((rc = c->d_offsets.reserve(2 * (per + 1) * 8))) return rc;
   if ((rc = c->h_small.reserve(256 + 2 * (per + 1) * 8))) return rc;
   uint64_t* h_off = reinterpret_cast<uint64_t*>(c->h_small.as<uint8_t>() + 256);
+  uint64_t* h_off_dev = nullptr;  // the same words as the kernels see them (mapped pinned memory)
+  CU(cudaHostGetDevicePointer(reinterpret_cast<void**>(&h_off_dev), h_off, 0));
   uint64_t written = 0;
   offsets[0] = 0;
   const uint32_t n_chunks = (n_frames + per - 1) / per;
-  // software pipeline over chunks: upload(k+1) overlaps code(k); download(k) is issued once sizes are known
+  // Software pipeline over chunks: upload(k+1) overlaps code(k).  The host needs chunk k's sizes before it can issue the
+  // download; a kernel stores them into mapped host memory, so that wait depends on the kernel stream only, never on a
+  // copy engine that may be busy with another context's downloads (a 64 MB download ahead in the queue used to stall
+  // this loop for a millisecond per chunk when a decompress call ran next to it).
   auto upload = [&](uint32_t k) -> int {
     const uint32_t f0 = k * per, nf = std::min(per, n_frames - f0), slot = k & 1;
     const uint8_t* src = iyuv + (uint64_t)f0 * frame_bytes;
@@ -520,6 +608,7 @@ int myyuvb_dct_compress_batch_host(myyuvb_ctx* c, const uint8_t* iyuv, uint32_t 
     CU(cudaEventRecord(c->ev[slot], c->copy_stream));
     return MYYUVB_OK;
   };
+  cudaStream_t dl = small_copy_mode() == 1 ? c->hi_stream : own_d2h_stream() ? c->d2h_stream : c->stream;
   if ((rc = upload(0))) return rc;
   for (uint32_t k = 0; k < n_chunks; k++) {
     const uint32_t f0 = k * per, nf = std::min(per, n_frames - f0), slot = k & 1;
@@ -527,22 +616,31 @@ int myyuvb_dct_compress_batch_host(myyuvb_ctx* c, const uint8_t* iyuv, uint32_t 
     uint8_t* d_dst = c->d_out.as<uint8_t>() + (uint64_t)slot * per * bound;
     uint64_t* d_off = c->d_offsets.as<uint64_t>() + (uint64_t)slot * (per + 1);
     CU(cudaStreamWaitEvent(c->stream, c->ev[slot], 0));
+    if (k >= 2) CU(cudaStreamWaitEvent(c->stream, c->d2h_ev[slot], 0));  // the payloads of chunk k-2 have left this output slot
     if ((rc = myyuvb_dct_compress_batch_dev(c, d_src, w, h, quality, nf, d_dst, (uint64_t)per * bound, d_off))) return rc;
-    CU(cudaMemcpyAsync(h_off + (uint64_t)slot * (per + 1), d_off, (size_t)(nf + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+    launch_publish_words(reinterpret_cast<uint32_t*>(h_off_dev + (uint64_t)slot * (per + 1)), reinterpret_cast<const uint32_t*>(d_off),
+                         2 * (nf + 1), c->stream);
     CU(cudaEventRecord(c->ev[2 + slot], c->stream));
     if (k + 1 < n_chunks) {
       // the other input slot was last read by chunk k-1, which has been synchronised below
       if ((rc = upload(k + 1))) return rc;
     }
     CU(cudaEventSynchronize(c->ev[2 + slot]));
-    const uint64_t* ho = h_off + (uint64_t)slot * (per + 1);
-    const uint64_t bytes = ho[nf] - ho[0];
-    if (written + bytes > out_capacity) return fail(MYYUVB_ERR_CAPACITY, "Error. output buffer is too small for the compressed data");
-    for (uint32_t i = 0; i <= nf; i++) offsets[f0 + i] = written + (ho[i] - ho[0]);
-    // download on the compute stream: the next chunk's kernels use the other output slot
-    if ((rc = staged_download(c, out + written, d_dst + ho[0], (size_t)bytes, c->stream))) return rc;
+    const volatile uint64_t* ho = h_off + (uint64_t)slot * (per + 1);
+    const uint64_t first = ho[0], bytes = ho[nf] - first;
+    if (written + bytes > out_capacity) {
+      cudaStreamSynchronize(c->copy_stream);
+      cudaStreamSynchronize(dl);
+      read_flags(c);
+      return fail(MYYUVB_ERR_CAPACITY, "Error. output buffer is too small for the compressed data");
+    }
+    for (uint32_t i = 0; i <= nf; i++) offsets[f0 + i] = written + (ho[i] - first);
+    // the next chunk's kernels use the other output slot
+    if ((rc = small_download(c, out + written, d_dst + first, (size_t)bytes, dl))) return rc;
+    CU(cudaEventRecord(c->d2h_ev[slot], dl));
     written += bytes;
   }
+  if (dl != c->stream) CU(cudaStreamSynchronize(dl));
   return read_flags(c);
 }
 
@@ -556,7 +654,7 @@ int myyuvb_dct_decompress_batch_host(myyuvb_ctx* c, const uint8_t* payloads, con
     if (offsets[f + 1] < offsets[f]) return fail(MYYUVB_ERR_ARG, "frame offsets must be non-decreasing");
   CU(cudaSetDevice(c->device));
   const uint64_t frame_bytes = (uint64_t)w * h * 3 / 2;
-  const uint32_t per = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(n_frames, (64ull << 20) / frame_bytes));
+  const uint32_t per = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(n_frames, host_chunk_bytes() / frame_bytes));
   const uint32_t n_chunks = (n_frames + per - 1) / per;
   uint64_t max_in = 0;
   for (uint32_t k = 0; k < n_chunks; k++) {
@@ -569,6 +667,7 @@ int myyuvb_dct_decompress_batch_host(myyuvb_ctx* c, const uint8_t* payloads, con
   if ((rc = c->h_small.reserve(256 + 2 * (per + 1) * 8))) return rc;
   uint64_t* h_off = reinterpret_cast<uint64_t*>(c->h_small.as<uint8_t>() + 256);
   const uint64_t in_slot = (max_in + 16) & ~15ull;
+  cudaStream_t up = small_copy_mode() == 1 ? c->hi_stream : c->copy_stream;
   auto upload = [&](uint32_t k) -> int {
     const uint32_t f0 = k * per, nf = std::min(per, n_frames - f0), slot = k & 1;
     const uint64_t beg = offsets[f0], bytes = offsets[f0 + nf] - beg;
@@ -576,18 +675,17 @@ int myyuvb_dct_decompress_batch_host(myyuvb_ctx* c, const uint8_t* payloads, con
     uint64_t* ho = h_off + (uint64_t)slot * (per + 1);
     for (uint32_t i = 0; i <= nf; i++) ho[i] = offsets[f0 + i] - beg;
     int urc;
-    if ((urc = staged_upload(c, c->d_in.as<uint8_t>() + (uint64_t)slot * in_slot, src, (size_t)bytes, c->copy_stream))) return urc;
-    CU(cudaMemcpyAsync(c->d_offsets.as<uint64_t>() + (uint64_t)slot * (per + 1), ho, (size_t)(nf + 1) * 8, cudaMemcpyHostToDevice,
-                       c->copy_stream));
-    CU(cudaEventRecord(c->ev[slot], c->copy_stream));
+    if ((urc = small_upload(c, c->d_in.as<uint8_t>() + (uint64_t)slot * in_slot, src, (size_t)bytes, up))) return urc;
+    if ((urc = small_upload(c, c->d_offsets.as<uint64_t>() + (uint64_t)slot * (per + 1), ho, (size_t)(nf + 1) * 8, up))) return urc;
+    CU(cudaEventRecord(c->ev[slot], up));
     return MYYUVB_OK;
   };
-  // Uploads run on copy_stream, kernels and downloads on the context stream; events order the reuse of the two input and
-  // two output slots.  Downloads on a third stream (MYYUVB_D2H_STREAM=1) make this call alone 9 % faster (8.9 -> 8.1 ms for
-  // 32 4K frames) but the bench's concurrent compress + decompress pipeline 20 % slower (20.4 -> 16.5 Gpixel/s, A/B on one
-  // box), so it is off by default.
-  static const bool own_d2h = [] { const char* e = getenv("MYYUVB_D2H_STREAM"); return e && e[0] == '1'; }();
-  cudaStream_t dl = own_d2h ? c->d2h_stream : c->stream;
+  // Uploads run on copy_stream, kernels on the context stream, downloads on d2h_stream; events order the reuse of the two
+  // input and two output slots.  Measured with a compress call running next to this one on a second context
+  // (profiles/e2e_ab.py, 32 4K frames per call, ms per compress+decompress pair): everything on the copy engines 15.9;
+  // downloads on their own stream 15.2; payloads and offsets moved by sm_copy_kernel as well 13.1; 32 MB chunks 12.9
+  // (the box's raw two-way copy rate allows 11.5).
+  cudaStream_t dl = own_d2h_stream() ? c->d2h_stream : c->stream;
   if ((rc = upload(0))) return rc;
   for (uint32_t k = 0; k < n_chunks; k++) {
     const uint32_t f0 = k * per, nf = std::min(per, n_frames - f0), slot = k & 1;
@@ -605,7 +703,7 @@ int myyuvb_dct_decompress_batch_host(myyuvb_ctx* c, const uint8_t* payloads, con
       if (k >= 1) {
         // input slot (k+1)&1 was read by the kernels of chunk k-1; its pinned offsets staging was read by that chunk's upload
         CU(cudaEventSynchronize(c->ev[(k + 1) & 1]));
-        CU(cudaStreamWaitEvent(c->copy_stream, c->ev[2 + ((k + 1) & 1)], 0));
+        CU(cudaStreamWaitEvent(up, c->ev[2 + ((k + 1) & 1)], 0));
       }
       if ((rc = upload(k + 1))) return rc;
     }

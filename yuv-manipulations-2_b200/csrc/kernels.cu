@@ -1339,4 +1339,37 @@ void launch_decompress(const uint8_t* d_payloads, const uint64_t* d_offsets, con
   g_launches += 4;
 }
 
+// Byte copy between device memory and mapped pinned host memory done by the SMs (any alignment on both sides).  The copy
+// engines serve one transfer per direction at a time in order of arrival, so a small transfer issued next to another
+// context's large ones waits for everything queued ahead of it; loads and stores issued by a kernel share the link with
+// the engine's traffic instead of queueing behind it.
+constexpr uint32_t kSmCopySegment = 32u << 10;
+__global__ void __launch_bounds__(256) sm_copy_kernel(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint64_t bytes) {
+  const uint64_t nseg = (bytes + kSmCopySegment - 1) / kSmCopySegment;
+  for (uint64_t seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
+    const uint64_t off = seg * kSmCopySegment;
+    const uint32_t n = (uint32_t)(bytes - off < kSmCopySegment ? bytes - off : kSmCopySegment);
+    copy_global_to_global_v4(dst + off, src + off, n, 256, threadIdx.x);
+  }
+}
+
+void launch_sm_copy(uint8_t* dst, const uint8_t* src, uint64_t bytes, cudaStream_t s) {
+  if (bytes == 0) return;
+  const uint64_t nseg = (bytes + kSmCopySegment - 1) / kSmCopySegment;
+  sm_copy_kernel<<<(int)(nseg < 296 ? nseg : 296), 256, 0, s>>>(dst, src, bytes);
+  g_launches++;
+}
+
+// Copies a few 32-bit words (frame offsets, error flags) into mapped pinned host memory with plain stores, so that the host
+// can read them after an event on the kernel stream without a copy-engine transfer queued behind other contexts' downloads.
+__global__ void publish_words_kernel(uint32_t* __restrict__ h_dst, const uint32_t* __restrict__ d_src, uint32_t n) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) h_dst[i] = d_src[i];
+  __threadfence_system();
+}
+
+void launch_publish_words(uint32_t* h_dst_devptr, const uint32_t* d_src, uint32_t n, cudaStream_t s) {
+  publish_words_kernel<<<1, 256, 0, s>>>(h_dst_devptr, d_src, n);
+  g_launches++;
+}
+
 }  // namespace myyuvb

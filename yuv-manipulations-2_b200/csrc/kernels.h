@@ -88,6 +88,11 @@ void launch_compress(const uint8_t* d_iyuv, const FrameGeom& g, const QTables& q
 void launch_decompress(const uint8_t* d_payloads, const uint64_t* d_offsets, const FrameGeom& g, const QTables& qt,
                        uint8_t* d_iyuv, const Workspace& ws, cudaStream_t s);
 
+// dst / src: device memory or the device-side address of mapped pinned host memory
+void launch_sm_copy(uint8_t* dst, const uint8_t* src, uint64_t bytes, cudaStream_t s);
+// h_dst_devptr: device-side address of mapped pinned host memory
+void launch_publish_words(uint32_t* h_dst_devptr, const uint32_t* d_src, uint32_t n, cudaStream_t s);  // n 32-bit words
+
 extern thread_local uint64_t g_launches;
 
 }  // namespace myyuvb
