@@ -73,6 +73,13 @@ MYYUVB_API uint64_t myyuvb_compress_bound(uint32_t width, uint32_t height);
 MYYUVB_API int myyuvb_xrgb_to_iyuv(myyuvb_ctx* ctx, const uint8_t* bgrx, uint32_t width, uint32_t height,
                                    int bottom_up, uint8_t* iyuv_out);
 
+/* The same registry entry for a 24-bit BMP: getYUV444FromRGB2x2 addresses pixel i at byte i * bit_count / 8
+ * (myyuv_yuv.cpp:34-41), and the "bit_count == 32" assert at :92 ("TODO: test 24") is compiled out of the Release build
+ * the reference's README asks for, so B,G,R triplets are what that build converts.  bgr: width*height*3 bytes, rows as
+ * stored in the file (no padding: a valid BMP has width % 4 == 0, myyuv_bmp.cpp:130).  SURVEY 8(f) row 3. */
+MYYUVB_API int myyuvb_bgr24_to_iyuv(myyuvb_ctx* ctx, const uint8_t* bgr, uint32_t width, uint32_t height,
+                                    int bottom_up, uint8_t* iyuv_out);
+
 /* replaces compress_map[DCT][IYUV] -> myyuvDCT::compress_DCT_planar (myyuv_yuv.cpp:130-143, DCT.cpp:371-430).
  * quality[3]: Y,U,V quality 1..100.  out receives the payload (YUV::data of the compressed image). */
 MYYUVB_API int myyuvb_dct_compress(myyuvb_ctx* ctx, const uint8_t* iyuv, uint32_t width, uint32_t height,
@@ -89,6 +96,10 @@ MYYUVB_API int myyuvb_dct_decompress(myyuvb_ctx* ctx, const uint8_t* payload, ui
 /* d_bgrx: n_frames * w*h*4, d_iyuv: n_frames * w*h*3/2. */
 MYYUVB_API int myyuvb_xrgb_to_iyuv_batch_dev(myyuvb_ctx* ctx, const uint8_t* d_bgrx, uint32_t width, uint32_t height,
                                              int bottom_up, uint32_t n_frames, uint8_t* d_iyuv);
+
+/* d_bgr: n_frames * w*h*3 (8-byte aligned, w*h*3 a multiple of 8), d_iyuv: n_frames * w*h*3/2. */
+MYYUVB_API int myyuvb_bgr24_to_iyuv_batch_dev(myyuvb_ctx* ctx, const uint8_t* d_bgr, uint32_t width, uint32_t height,
+                                              int bottom_up, uint32_t n_frames, uint8_t* d_iyuv);
 
 /* Payloads are written back to back into d_out; d_offsets[f] .. d_offsets[f+1] (n_frames+1 entries,
  * device memory) delimit frame f.  Nothing is written past out_capacity: an overflow is reported by

@@ -60,6 +60,8 @@ class Oracle:
         L = self.lib
         L.ora_bgrx_to_iyuv.argtypes = [_u8p, C.c_uint32, C.c_uint32, C.c_int, _u8p]
         L.ora_bgrx_to_iyuv.restype = None
+        L.ora_bgr_to_iyuv_pb.argtypes = [_u8p, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, _u8p]
+        L.ora_bgr_to_iyuv_pb.restype = None
         L.ora_qtable.argtypes = [C.c_uint8, C.c_int, C.POINTER(C.c_float)]
         L.ora_qtable.restype = None
         L.ora_compress_bound.argtypes = [C.c_uint32, C.c_uint32]
@@ -77,6 +79,14 @@ class Oracle:
         assert bgrx.size == w * h * 4
         out = np.empty(w * h * 3 // 2, np.uint8)
         self.lib.ora_bgrx_to_iyuv(_p8(bgrx), w, h, int(bottom_up), _p8(out))
+        return out
+
+    def bgr24_to_iyuv(self, bgr: np.ndarray, w: int, h: int, bottom_up: bool = True) -> np.ndarray:
+        """24-bit BMP pixel rows (B,G,R; width % 4 == 0 so rows carry no padding, myyuv_bmp.cpp:130)."""
+        bgr = np.ascontiguousarray(bgr, dtype=np.uint8).reshape(-1)
+        assert bgr.size == w * h * 3
+        out = np.empty(w * h * 3 // 2, np.uint8)
+        self.lib.ora_bgr_to_iyuv_pb(_p8(bgr), w, h, int(bottom_up), 3, _p8(out))
         return out
 
     def qtable(self, q: int, chroma: bool) -> np.ndarray:
@@ -158,6 +168,7 @@ class Reference:
         L.refshim_threads.restype = C.c_int
         dp = C.POINTER(C.c_double)
         L.refshim_bgrx_to_iyuv.argtypes = [_u8p, C.c_int32, C.c_int32, _u8p, dp]
+        L.refshim_bmp_to_iyuv.argtypes = [_u8p, C.c_int32, C.c_int32, C.c_uint32, _u8p, dp]
         L.refshim_compress.argtypes = [_u8p, C.c_uint32, C.c_uint32, _u8p, C.c_uint32, _u8p, C.c_uint32,
                                        C.POINTER(C.c_uint32), dp]
         L.refshim_decompress.argtypes = [_u8p, C.c_uint32, C.c_uint32, C.c_uint32, _u8p, _u8p, dp]
@@ -178,6 +189,16 @@ class Reference:
         out = np.empty(w * h * 3 // 2, np.uint8)
         sec = C.c_double(0)
         self._check(self.lib.refshim_bgrx_to_iyuv(_p8(bgrx), w, h if bottom_up else -h, _p8(out), C.byref(sec)))
+        self.last_seconds = sec.value
+        return out
+
+    def bgr24_to_iyuv(self, bgr: np.ndarray, w: int, h: int, bottom_up: bool = True) -> np.ndarray:
+        """The reference's converter on a 24-bit BMP (its 32-bit assert is compiled out by -DNDEBUG, oracle/Makefile)."""
+        bgr = np.ascontiguousarray(bgr, dtype=np.uint8).reshape(-1)
+        assert bgr.size == w * h * 3
+        out = np.empty(w * h * 3 // 2, np.uint8)
+        sec = C.c_double(0)
+        self._check(self.lib.refshim_bmp_to_iyuv(_p8(bgr), w, h if bottom_up else -h, 24, _p8(out), C.byref(sec)))
         self.last_seconds = sec.value
         return out
 

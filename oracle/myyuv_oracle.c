@@ -61,9 +61,11 @@ static inline unsigned ora_div4_nearest(uint8_t v) {
   return ((unsigned)v + 2u) / 4u;
 }
 
-/* bgrx: rows as they lie in the BMP file.  bottom_up != 0: file row 0 is the bottom image row
+/* px: rows as they lie in the BMP file, pixel_bytes bytes per pixel (4: B,G,R,X; 3: B,G,R -- getYUV444FromRGB2x2
+ * addresses pixels as index * (bit_count / 8), myyuv_yuv.cpp:34-41; the 32-bit assert at :92 is compiled out of the
+ * Release build the reference's README asks for).  bottom_up != 0: file row 0 is the bottom image row
  * (BMP height > 0, myyuv_bmp.cpp:95-98); bottom_up == 0: rows already top-down (height < 0, :87-88). */
-void ora_bgrx_to_iyuv(const uint8_t* bgrx, uint32_t w, uint32_t h, int bottom_up, uint8_t* out) {
+void ora_bgr_to_iyuv_pb(const uint8_t* bgrx, uint32_t w, uint32_t h, int bottom_up, uint32_t pixel_bytes, uint8_t* out) {
   uint8_t* yp = out;
   uint8_t* up = out + (size_t)w * h;          /* myyuv_yuv.cpp:105-107 */
   uint8_t* vp = out + (size_t)w * h * 5 / 4;
@@ -73,7 +75,7 @@ void ora_bgrx_to_iyuv(const uint8_t* bgrx, uint32_t w, uint32_t h, int bottom_up
       for (int s = 0; s < 4; s++) {
         const uint32_t row = j + (uint32_t)(s >> 1), col = i + (uint32_t)(s & 1);
         const uint32_t frow = bottom_up ? (h - 1 - row) : row;
-        ora_pixel_yuv444(bgrx + ((size_t)frow * w + col) * 4, &y4[s], &cb4[s], &cr4[s]);
+        ora_pixel_yuv444(bgrx + ((size_t)frow * w + col) * pixel_bytes, &y4[s], &cb4[s], &cr4[s]);
       }
       /* :114-115: the four rounded quarters are summed and stored to uint8_t (wraps at 256) */
       const uint8_t Cb = (uint8_t)(ora_div4_nearest(cb4[0]) + ora_div4_nearest(cb4[1]) + ora_div4_nearest(cb4[2]) +
@@ -90,6 +92,10 @@ void ora_bgrx_to_iyuv(const uint8_t* bgrx, uint32_t w, uint32_t h, int bottom_up
       vp[k] = Cr;
     }
   }
+}
+
+void ora_bgrx_to_iyuv(const uint8_t* bgrx, uint32_t w, uint32_t h, int bottom_up, uint8_t* out) {
+  ora_bgr_to_iyuv_pb(bgrx, w, h, bottom_up, 4, out);
 }
 
 /* ------------------------------------------------------------------------------------------------

@@ -50,22 +50,22 @@ int refshim_threads() {
 #endif
 }
 
-// bgrx: pixel rows exactly as stored in a BMP file; height_signed > 0 = bottom-up file.
-int refshim_bgrx_to_iyuv(const uint8_t* bgrx, int32_t width, int32_t height_signed, uint8_t* iyuv_out,
-                         double* seconds) {
+// px: pixel rows exactly as stored in a BMP file of bit_count bits per pixel; height_signed > 0 = bottom-up file.
+int refshim_bmp_to_iyuv(const uint8_t* px, int32_t width, int32_t height_signed, uint32_t bit_count, uint8_t* iyuv_out,
+                        double* seconds) {
   try {
     myyuv::BMP bmp;
     bmp.header.width = width;
     bmp.header.height = height_signed;
-    bmp.header.bit_count = 32;
+    bmp.header.bit_count = static_cast<uint16_t>(bit_count);
     bmp.header.planes = 1;
-    bmp.header.header_size = 124;
-    bmp.header.compression = 3;
-    bmp.header.data_pos = sizeof(myyuv::BMPHeader) + sizeof(myyuv::BMPColorHeader);
+    bmp.header.header_size = bit_count == 32 ? 124 : 40;
+    bmp.header.compression = bit_count == 32 ? 3 : 0;
+    bmp.header.data_pos = sizeof(myyuv::BMPHeader) + (bit_count == 32 ? sizeof(myyuv::BMPColorHeader) : 0);
     const uint32_t sz = bmp.imageSize();
     bmp.header.file_size = bmp.header.data_pos + sz;
     bmp.data = new uint8_t[sz];
-    std::memcpy(bmp.data, bgrx, sz);
+    std::memcpy(bmp.data, px, sz);
     auto t0 = clk::now();
     myyuv::YUV yuv(bmp, myyuv::YUV::FourccFormats::IYUV);
     auto t1 = clk::now();
@@ -73,6 +73,11 @@ int refshim_bgrx_to_iyuv(const uint8_t* bgrx, int32_t width, int32_t height_sign
     std::memcpy(iyuv_out, yuv.data, yuv.header.data_size);
     return 0;
   } catch (const std::exception& e) { return fail(e); }
+}
+
+int refshim_bgrx_to_iyuv(const uint8_t* bgrx, int32_t width, int32_t height_signed, uint8_t* iyuv_out,
+                         double* seconds) {
+  return refshim_bmp_to_iyuv(bgrx, width, height_signed, 32, iyuv_out, seconds);
 }
 
 int refshim_compress(const uint8_t* iyuv, uint32_t w, uint32_t h, const uint8_t* q, uint32_t nq, uint8_t* out,

@@ -37,6 +37,24 @@ peak = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()).get("hbm_gbs", 665
 out["xrgb_to_iyuv"] = {"frames": F, "ms": round(ms, 4), "Mpixel_s": round(F * W * H / ms / 1e3, 1), "GBps": round(byts / ms / 1e6, 1),
                        "frac_of_hbm_peak": round(byts / ms / 1e6 / peak, 3), "algorithmic_bytes": int(byts)}
 
+# ---- the same frames as 24-bit BMP rows (B,G,R triplets): 4.5 bytes per pixel ----
+bg24 = bg[..., :3].contiguous()
+yuv24 = torch.empty_like(yuv)
+for _ in range(3):
+    ctx.bgr24_to_iyuv_batch_dev(bg24, W, H, True, F, yuv24)
+torch.cuda.synchronize()
+ev[0].record(stream)
+for _ in range(10):
+    ctx.bgr24_to_iyuv_batch_dev(bg24, W, H, True, F, yuv24)
+ev[1].record(stream)
+torch.cuda.synchronize()
+ms = ev[0].elapsed_time(ev[1]) / 10
+byts = F * W * H * 4.5
+out["bgr24_to_iyuv"] = {"frames": F, "ms": round(ms, 4), "Mpixel_s": round(F * W * H / ms / 1e3, 1), "GBps": round(byts / ms / 1e6, 1),
+                        "frac_of_hbm_peak": round(byts / ms / 1e6 / peak, 3), "algorithmic_bytes": int(byts),
+                        "same_planes_as_32bit": bool(torch.equal(yuv24, yuv))}
+del bg24, yuv24
+
 # ---- full pipeline XRGB -> IYUV -> DCT-50 (BASELINE configs[2]), device resident, by chunk size ----
 capp = F * pkg.capi.compress_bound(W, H)
 p_out = torch.empty(capp, dtype=torch.uint8, device=dev)

@@ -45,6 +45,13 @@ def main():
         for bottom_up in (True, False):
             y = ref.bgrx_to_iyuv(b, w, h, bottom_up)
             out["colour"].append({"w": w, "h": h, "first": first, "bottom_up": bottom_up, "input_sha256": sha(b), "iyuv_sha256": sha(y)})
+    # 24-bit BMP rows (the reference's Release build converts them as B,G,R triplets): the same frames without the X byte
+    out["colour24"] = []
+    for w, h, first in [(16, 16, 0), (64, 48, 1), (36, 20, 5), (992, 736, 2), (1920, 1080, 3)]:
+        b = np.ascontiguousarray(synth.bgrx_frames_numpy(w, h, 1, first)[0].reshape(-1, 4)[:, :3]).reshape(-1)
+        for bottom_up in (True, False):
+            y = ref.bgr24_to_iyuv(b, w, h, bottom_up)
+            out["colour24"].append({"w": w, "h": h, "first": first, "bottom_up": bottom_up, "input_sha256": sha(b), "iyuv_sha256": sha(y)})
     for q in [(50, 50, 50), (1, 1, 1), (100, 100, 100), (97, 3, 64)]:
         f = synth.edge_case_iyuv(128, 128)
         c = ref.compress(f, 128, 128, q)

@@ -95,3 +95,31 @@ def test_cli_and_reference_cli_agree_on_synthetic(synth, tmp_path):
         subprocess.run([str(ref_cli), str(tmp_path / "ours.myyuv"), "-decompress", "-o", str(d1)], check=True, capture_output=True, timeout=300)
         subprocess.run([str(cli), str(tmp_path / "ref.myyuv"), "-decompress", "-o", str(d2)], check=True, capture_output=True, timeout=300)
         assert d1.read_bytes() == d2.read_bytes()
+
+
+@pytest.mark.gpu
+def test_cli_converts_24bit_bmp_like_the_reference_cli(synth, tmp_path):
+    """A 24-bit BMP through the unmodified CLI linked to the replacement library and through the reference's own CLI
+    (Release build: the 32-bit assert is compiled out): identical .myyuv files."""
+    import struct
+
+    import numpy as np
+
+    ref_cli = ROOT / "oracle" / "_ref" / "serial" / "myyuv_cli"
+    cli = LIB / "myyuv_cli"
+    if not (ref_cli.exists() and cli.exists()):
+        pytest.skip("CLIs not built")
+    for w, h_signed in ((64, 48), (40, -24)):
+        h = abs(h_signed)
+        px = np.ascontiguousarray(synth.bgrx_frames_numpy(w, h, 1, 4)[0].reshape(-1, 4)[:, :3]).tobytes()
+        header = b"BM" + struct.pack("<IHHIIiiHHIIiiII", 54 + len(px), 0, 0, 54, 40, w, h_signed, 1, 24, 0, 0, 2835, 2835, 0, 0)
+        assert len(header) == 54
+        bmp = tmp_path / f"in{w}.bmp"
+        bmp.write_bytes(header + px)
+        outs = []
+        for exe, tag in ((cli, "ours"), (ref_cli, "ref")):
+            o = tmp_path / f"{tag}{w}.myyuv"
+            r = subprocess.run([str(exe), str(bmp), "-to_yuv", "IYUV", "-o", str(o)], capture_output=True, text=True, timeout=300)
+            assert r.returncode == 0 and "Success!" in r.stdout, r.stdout + r.stderr
+            outs.append(o.read_bytes())
+        assert outs[0] == outs[1] and len(outs[0]) == 64 + w * h * 3 // 2

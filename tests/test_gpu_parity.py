@@ -31,6 +31,33 @@ def test_colour_conversion_narrow_widths(ctx, ora, synth, w, h):
         assert np.array_equal(ctx.xrgb_to_iyuv(bgrx, w, h, bottom_up), ora.bgrx_to_iyuv(bgrx, w, h, bottom_up))
 
 
+@pytest.mark.parametrize("w,h", SMALL + [(4, 2), (12, 10), (20, 6), (36, 4), (1004, 14), (3840, 2160)])
+def test_bgr24_conversion_matches_oracle(ctx, ora, synth, w, h):
+    """24-bit BMP rows: 8-pixel kernel for widths that are a multiple of 8, quad kernel otherwise."""
+    bgr = np.ascontiguousarray(synth.bgrx_frames_numpy(w, h, 1, first=7)[0].reshape(-1, 4)[:, :3]).reshape(-1)
+    for bottom_up in (True, False):
+        assert np.array_equal(ctx.bgr24_to_iyuv(bgr, w, h, bottom_up), ora.bgr24_to_iyuv(bgr, w, h, bottom_up))
+
+
+def test_bgr24_random_bytes_and_batch(ctx, ora, ref, pkg):
+    import torch
+
+    rng = np.random.default_rng(2424)
+    w, h, n = 200, 64, 3
+    frames24 = rng.integers(0, 256, (n, w * h * 3), dtype=np.uint8)
+    for f in frames24[:2]:
+        assert np.array_equal(ctx.bgr24_to_iyuv(f, w, h, True), ref.bgr24_to_iyuv(f, w, h, True))
+    d_in = torch.from_numpy(frames24).cuda()
+    d_out = torch.empty(n * w * h * 3 // 2, dtype=torch.uint8, device="cuda")
+    ctx.bgr24_to_iyuv_batch_dev(d_in, w, h, False, n, d_out)
+    ctx.sync()
+    got = d_out.cpu().numpy().reshape(n, -1)
+    for i in range(n):
+        assert np.array_equal(got[i], ora.bgr24_to_iyuv(frames24[i], w, h, False))
+    with pytest.raises(pkg.MyyuvError):
+        ctx.bgr24_to_iyuv(frames24[0][: 3 * 3 * 2], 3, 2)   # odd width
+
+
 def test_colour_conversion_extremes(ctx, ora):
     # every (B,G,R) on a coarse lattice plus the pure-blue quad whose Cb sum wraps to 0 (SURVEY A.1)
     vals = np.array([0, 1, 2, 15, 16, 17, 63, 64, 127, 128, 129, 191, 200, 253, 254, 255], np.uint8)

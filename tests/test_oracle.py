@@ -33,6 +33,30 @@ def test_colour_matches_reference_hashes(ora, synth, case):
     assert sha(ora.bgrx_to_iyuv(b, case["w"], case["h"], case["bottom_up"])) == case["iyuv_sha256"]
 
 
+def bgr24_frame(synth, w, h, first):
+    return np.ascontiguousarray(synth.bgrx_frames_numpy(w, h, 1, first)[0].reshape(-1, 4)[:, :3]).reshape(-1)
+
+
+@pytest.mark.parametrize("case", GOLDEN["colour24"], ids=lambda c: f"{c['w']}x{c['h']}bu{int(c['bottom_up'])}")
+def test_colour24_matches_reference_hashes(ora, synth, case):
+    """24-bit BMP rows: what the reference's Release build (assert compiled out) makes of B,G,R triplets."""
+    b = bgr24_frame(synth, case["w"], case["h"], case["first"])
+    assert sha(b) == case["input_sha256"]
+    got = ora.bgr24_to_iyuv(b, case["w"], case["h"], case["bottom_up"])
+    assert sha(got) == case["iyuv_sha256"]
+    # the X byte never enters the arithmetic: same planes as the 32-bit frame the triplets were cut from
+    full = synth.bgrx_frames_numpy(case["w"], case["h"], 1, case["first"])[0]
+    assert np.array_equal(got, ora.bgrx_to_iyuv(full, case["w"], case["h"], case["bottom_up"]))
+
+
+def test_colour24_oracle_against_reference_itself(ora, ref):
+    rng = np.random.default_rng(24)
+    for w, h in ((4, 2), (12, 6), (40, 18)):
+        b = rng.integers(0, 256, w * h * 3, dtype=np.uint8)
+        for bottom_up in (True, False):
+            assert np.array_equal(ora.bgr24_to_iyuv(b, w, h, bottom_up), ref.bgr24_to_iyuv(b, w, h, bottom_up))
+
+
 @pytest.mark.parametrize("case", GOLDEN["edge"], ids=lambda c: f"q{c['q']}")
 def test_edge_cases_match_reference_hashes(ora, synth, case):
     f = synth.edge_case_iyuv(case["w"], case["h"])

@@ -22,7 +22,7 @@ EXPORTS = [
     "myyuvb_ctx_create", "myyuvb_ctx_destroy", "myyuvb_last_error", "myyuvb_sync", "myyuvb_stream",
     "myyuvb_compress_bound", "myyuvb_xrgb_to_iyuv", "myyuvb_dct_compress", "myyuvb_dct_decompress",
     "myyuvb_xrgb_to_iyuv_batch_dev", "myyuvb_dct_compress_batch_dev", "myyuvb_dct_decompress_batch_dev",
-    "myyuvb_xrgb_dct_compress_batch_dev",
+    "myyuvb_xrgb_dct_compress_batch_dev", "myyuvb_bgr24_to_iyuv", "myyuvb_bgr24_to_iyuv_batch_dev",
     "myyuvb_batch_status", "myyuvb_dct_compress_batch_host", "myyuvb_dct_decompress_batch_host",
     "myyuvb_host_alloc", "myyuvb_host_free", "myyuvb_launch_count", "myyuvb_last_kernel_ms",
 ]
@@ -62,10 +62,12 @@ def lib() -> C.CDLL:
     L.myyuvb_compress_bound.argtypes = [C.c_uint32, C.c_uint32]
     L.myyuvb_compress_bound.restype = C.c_uint64
     L.myyuvb_xrgb_to_iyuv.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p]
+    L.myyuvb_bgr24_to_iyuv.argtypes = L.myyuvb_xrgb_to_iyuv.argtypes
     L.myyuvb_dct_compress.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, _u8p, C.c_void_p, C.c_uint64,
                                       C.POINTER(C.c_uint32)]
     L.myyuvb_dct_decompress.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, _u8p, C.c_void_p]
     L.myyuvb_xrgb_to_iyuv_batch_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_void_p]
+    L.myyuvb_bgr24_to_iyuv_batch_dev.argtypes = L.myyuvb_xrgb_to_iyuv_batch_dev.argtypes
     L.myyuvb_dct_compress_batch_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, _u8p, C.c_uint32, C.c_void_p,
                                                 C.c_uint64, C.c_void_p]
     L.myyuvb_dct_decompress_batch_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, _u8p, C.c_uint32,
@@ -184,6 +186,15 @@ class Context:
         _check(lib().myyuvb_xrgb_to_iyuv(self._h, bgrx.ctypes.data, w, h, int(bottom_up), out.ctypes.data))
         return out
 
+    def bgr24_to_iyuv(self, bgr: np.ndarray, w: int, h: int, bottom_up: bool = True) -> np.ndarray:
+        """24-bit BMP pixel rows (B,G,R triplets, no row padding)."""
+        bgr = np.ascontiguousarray(bgr, dtype=np.uint8).reshape(-1)
+        if bgr.size != w * h * 3:
+            raise ValueError("bgr must hold width*height*3 bytes")
+        out = np.empty(w * h * 3 // 2, np.uint8)
+        _check(lib().myyuvb_bgr24_to_iyuv(self._h, bgr.ctypes.data, w, h, int(bottom_up), out.ctypes.data))
+        return out
+
     def compress(self, iyuv: np.ndarray, w: int, h: int, q, capacity: int | None = None) -> np.ndarray:
         iyuv = np.ascontiguousarray(iyuv, dtype=np.uint8).reshape(-1)
         if iyuv.size != w * h * 3 // 2:
@@ -220,6 +231,9 @@ class Context:
     # ---- device-pointer batch calls (torch CUDA tensors or raw device addresses; asynchronous) ----
     def xrgb_to_iyuv_batch_dev(self, d_bgrx, w: int, h: int, bottom_up: bool, n_frames: int, d_iyuv) -> None:
         _check(lib().myyuvb_xrgb_to_iyuv_batch_dev(self._h, _ptr(d_bgrx), w, h, int(bottom_up), n_frames, _ptr(d_iyuv)))
+
+    def bgr24_to_iyuv_batch_dev(self, d_bgr, w: int, h: int, bottom_up: bool, n_frames: int, d_iyuv) -> None:
+        _check(lib().myyuvb_bgr24_to_iyuv_batch_dev(self._h, _ptr(d_bgr), w, h, int(bottom_up), n_frames, _ptr(d_iyuv)))
 
     def compress_batch_dev(self, d_iyuv, w: int, h: int, q, n_frames: int, d_out, out_capacity: int, d_offsets) -> None:
         qa = _q(q)

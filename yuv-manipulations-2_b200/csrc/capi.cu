@@ -430,16 +430,46 @@ void myyuvb_host_free(void* p) {
 // ------------------------------------------------------------------------------------------------
 // device-pointer batch entry points
 // ------------------------------------------------------------------------------------------------
-int myyuvb_xrgb_to_iyuv_batch_dev(myyuvb_ctx* c, const uint8_t* d_bgrx, uint32_t w, uint32_t h, int bottom_up,
-                                  uint32_t n_frames, uint8_t* d_iyuv) {
-  if (!c || !d_bgrx || !d_iyuv) return fail(MYYUVB_ERR_ARG, "null argument");
+namespace {
+int convert_dev_impl(myyuvb_ctx* c, const uint8_t* d_px, uint32_t pixel_bytes, uint32_t w, uint32_t h, int bottom_up,
+                     uint32_t n_frames, uint8_t* d_iyuv) {
+  if (!c || !d_px || !d_iyuv) return fail(MYYUVB_ERR_ARG, "null argument");
   if (w == 0 || h == 0 || (w % 2) || (h % 2)) return fail(MYYUVB_ERR_EVEN, "Error. width and height must be even");
   if ((uint64_t)w * h * 4 > 0xffffffffull) return fail(MYYUVB_ERR_TOO_LARGE, "Error. image does not fit the format's uint32 sizes");
-  if (((uintptr_t)d_bgrx & 15) || ((uintptr_t)d_iyuv & 7)) return fail(MYYUVB_ERR_ARG, "device buffers must be 16-byte (input) / 8-byte (output) aligned");
+  if (pixel_bytes == 4 ? ((uintptr_t)d_px & 15) != 0 : ((uintptr_t)d_px & 7) != 0 || ((uint64_t)w * h * 3) % 8 != 0)
+    return fail(MYYUVB_ERR_ARG, pixel_bytes == 4 ? "device buffers must be 16-byte (input) / 8-byte (output) aligned"
+                                                 : "24-bit input: device buffer must be 8-byte aligned and a frame a multiple of 8 bytes");
+  if ((uintptr_t)d_iyuv & 7) return fail(MYYUVB_ERR_ARG, "device buffers must be 16-byte (input) / 8-byte (output) aligned");
   CU(cudaSetDevice(c->device));
-  launch_xrgb_to_iyuv(d_bgrx, d_iyuv, w, h, bottom_up, n_frames, c->stream);
+  launch_bgr_to_iyuv(d_px, pixel_bytes, d_iyuv, w, h, bottom_up, n_frames, c->stream);
   CU(cudaGetLastError());
   return MYYUVB_OK;
+}
+
+int convert_host_impl(myyuvb_ctx* c, const uint8_t* px, uint32_t pixel_bytes, uint32_t w, uint32_t h, int bottom_up, uint8_t* iyuv_out) {
+  if (!c || !px || !iyuv_out) return fail(MYYUVB_ERR_ARG, "null argument");
+  if (w == 0 || h == 0 || (w % 2) || (h % 2)) return fail(MYYUVB_ERR_EVEN, "Error. width and height must be even");
+  CU(cudaSetDevice(c->device));
+  const size_t in_bytes = (size_t)w * h * pixel_bytes, out_bytes = (size_t)w * h * 3 / 2;
+  int rc;
+  if ((rc = c->d_in.reserve(in_bytes))) return rc;
+  if ((rc = c->d_out.reserve(out_bytes))) return rc;
+  if ((rc = staged_upload(c, c->d_in.p, px, in_bytes, c->stream))) return rc;
+  if ((rc = convert_dev_impl(c, c->d_in.as<uint8_t>(), pixel_bytes, w, h, bottom_up, 1, c->d_out.as<uint8_t>()))) return rc;
+  if ((rc = staged_download(c, iyuv_out, c->d_out.p, out_bytes, c->stream))) return rc;
+  CU(cudaStreamSynchronize(c->stream));
+  return MYYUVB_OK;
+}
+}  // namespace
+
+int myyuvb_xrgb_to_iyuv_batch_dev(myyuvb_ctx* c, const uint8_t* d_bgrx, uint32_t w, uint32_t h, int bottom_up,
+                                  uint32_t n_frames, uint8_t* d_iyuv) {
+  return convert_dev_impl(c, d_bgrx, 4, w, h, bottom_up, n_frames, d_iyuv);
+}
+
+int myyuvb_bgr24_to_iyuv_batch_dev(myyuvb_ctx* c, const uint8_t* d_bgr, uint32_t w, uint32_t h, int bottom_up,
+                                   uint32_t n_frames, uint8_t* d_iyuv) {
+  return convert_dev_impl(c, d_bgr, 3, w, h, bottom_up, n_frames, d_iyuv);
 }
 
 namespace {
@@ -533,18 +563,11 @@ int myyuvb_batch_status(myyuvb_ctx* c) {
 // host-pointer single image entry points
 // ------------------------------------------------------------------------------------------------
 int myyuvb_xrgb_to_iyuv(myyuvb_ctx* c, const uint8_t* bgrx, uint32_t w, uint32_t h, int bottom_up, uint8_t* iyuv_out) {
-  if (!c || !bgrx || !iyuv_out) return fail(MYYUVB_ERR_ARG, "null argument");
-  if (w == 0 || h == 0 || (w % 2) || (h % 2)) return fail(MYYUVB_ERR_EVEN, "Error. width and height must be even");
-  CU(cudaSetDevice(c->device));
-  const size_t in_bytes = (size_t)w * h * 4, out_bytes = (size_t)w * h * 3 / 2;
-  int rc;
-  if ((rc = c->d_in.reserve(in_bytes))) return rc;
-  if ((rc = c->d_out.reserve(out_bytes))) return rc;
-  if ((rc = staged_upload(c, c->d_in.p, bgrx, in_bytes, c->stream))) return rc;
-  if ((rc = myyuvb_xrgb_to_iyuv_batch_dev(c, c->d_in.as<uint8_t>(), w, h, bottom_up, 1, c->d_out.as<uint8_t>()))) return rc;
-  if ((rc = staged_download(c, iyuv_out, c->d_out.p, out_bytes, c->stream))) return rc;
-  CU(cudaStreamSynchronize(c->stream));
-  return MYYUVB_OK;
+  return convert_host_impl(c, bgrx, 4, w, h, bottom_up, iyuv_out);
+}
+
+int myyuvb_bgr24_to_iyuv(myyuvb_ctx* c, const uint8_t* bgr, uint32_t w, uint32_t h, int bottom_up, uint8_t* iyuv_out) {
+  return convert_host_impl(c, bgr, 3, w, h, bottom_up, iyuv_out);
 }
 
 int myyuvb_dct_compress(myyuvb_ctx* c, const uint8_t* iyuv, uint32_t w, uint32_t h, const uint8_t quality[3], uint8_t* out,

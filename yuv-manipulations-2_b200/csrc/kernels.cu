@@ -324,6 +324,77 @@ __global__ void __launch_bounds__(256) xrgb_to_iyuv_kernel(const uint8_t* __rest
   }
 }
 
+// 24-bit BMP rows (B,G,R triplets; getYUV444FromRGB2x2 addresses pixel i at byte i * bit_count / 8, myyuv_yuv.cpp:34-41;
+// rows carry no padding because a valid BMP has width % 4 == 0, myyuv_bmp.cpp:130).  Same unit of work as the 32-bit
+// kernel -- 8 pixels x 2 rows per thread -- read as three 64-bit loads per row (24 bytes, 8-byte aligned when
+// width % 8 == 0); byte permutes rebuild the B,G,R,* words pixel_pair_yuv takes.  4.5 bytes per pixel of traffic.
+struct Row24 { uint2 a, b, c; };
+
+MYB_D void unpack_row24(const Row24& r, uint32_t p[8]) {
+  p[0] = r.a.x;                                  // bytes 0..2
+  p[1] = __byte_perm(r.a.x, r.a.y, 0x0543);     // 3..5
+  p[2] = __byte_perm(r.a.y, r.b.x, 0x0432);     // 6..8
+  p[3] = r.b.x >> 8;                             // 9..11
+  p[4] = r.b.y;                                  // 12..14
+  p[5] = __byte_perm(r.b.y, r.c.x, 0x0543);     // 15..17
+  p[6] = __byte_perm(r.c.x, r.c.y, 0x0432);     // 18..20
+  p[7] = r.c.y >> 8;                             // 21..23
+}
+
+__global__ void __launch_bounds__(256) bgr24_to_iyuv_kernel(const uint8_t* __restrict__ bgr, uint8_t* __restrict__ iyuv,
+                                                             uint32_t w, uint32_t h, int bottom_up, uint32_t n_frames, float onef) {
+  const f2 ONE = dup(onef);
+  const uint32_t ow = w >> 3;
+  const uint32_t per_frame = ow * (h >> 1);
+  const uint8_t* src = bgr + (uint64_t)blockIdx.y * w * h * 3;
+  uint8_t* dst = iyuv + (uint64_t)blockIdx.y * w * h * 3 / 2;
+  auto fetch = [&](uint32_t i, Row24& t, Row24& u) {
+    const uint32_t rp = i / ow;
+    const uint32_t row = rp * 2, col = (i - rp * ow) * 8;
+    const uint32_t fr0 = bottom_up ? (h - 1 - row) : row, fr1 = bottom_up ? (h - 2 - row) : row + 1;
+    const uint2* s0 = reinterpret_cast<const uint2*>(src + ((uint64_t)fr0 * w + col) * 3);
+    const uint2* s1 = reinterpret_cast<const uint2*>(src + ((uint64_t)fr1 * w + col) * 3);
+    t.a = __ldcs(s0); t.b = __ldcs(s0 + 1); t.c = __ldcs(s0 + 2);
+    u.a = __ldcs(s1); u.b = __ldcs(s1 + 1); u.c = __ldcs(s1 + 2);
+  };
+  const uint32_t step = gridDim.x * blockDim.x;
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  Row24 nt, nu;
+  if (i < per_frame) fetch(i, nt, nu);
+#pragma unroll 1
+  for (; i < per_frame; i += step) {
+    uint32_t pt[8], pu[8];
+    unpack_row24(nt, pt);
+    unpack_row24(nu, pu);
+    if (i + step < per_frame) fetch(i + step, nt, nu);
+    const uint32_t rp = i / ow;
+    const uint32_t row = rp * 2, col = (i - rp * ow) * 8;
+    PixelPair t[4], u[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      t[k] = pixel_pair_yuv(pt[2 * k], pt[2 * k + 1], ONE);
+      u[k] = pixel_pair_yuv(pu[2 * k], pu[2 * k + 1], ONE);
+    }
+    auto pack4 = [](uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+      return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
+    };
+    uint2 y0, y1;
+    y0.x = pack4(t[0].ybits0, t[0].ybits1, t[1].ybits0, t[1].ybits1); y0.y = pack4(t[2].ybits0, t[2].ybits1, t[3].ybits0, t[3].ybits1);
+    y1.x = pack4(u[0].ybits0, u[0].ybits1, u[1].ybits0, u[1].ybits1); y1.y = pack4(u[2].ybits0, u[2].ybits1, u[3].ybits0, u[3].ybits1);
+    uint32_t uu = 0, vv = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      uu |= chroma_quad(t[k].cb0, t[k].cb1, u[k].cb0, u[k].cb1) << (8 * k);
+      vv |= chroma_quad(t[k].cr0, t[k].cr1, u[k].cr0, u[k].cr1) << (8 * k);
+    }
+    *reinterpret_cast<uint2*>(dst + (uint64_t)row * w + col) = y0;
+    *reinterpret_cast<uint2*>(dst + (uint64_t)(row + 1) * w + col) = y1;
+    const uint64_t k = ((uint64_t)col + (uint64_t)row * w / 2) / 2;  // myyuv_yuv.cpp:120
+    *reinterpret_cast<uint32_t*>(dst + (uint64_t)w * h + k) = uu;
+    *reinterpret_cast<uint32_t*>(dst + (uint64_t)w * h * 5 / 4 + k) = vv;
+  }
+}
+
 // Narrow images (width not a multiple of 8): one thread = one 2x2 quad, plain scalar code.
 MYB_D void pixel_yuv(uint32_t px, uint32_t& y, int& cb, int& cr) {
   const float B = (float)(px & 0xff), G = (float)((px >> 8) & 0xff), R = (float)((px >> 16) & 0xff);
@@ -333,18 +404,27 @@ MYB_D void pixel_yuv(uint32_t px, uint32_t& y, int& cb, int& cr) {
   cr = __float2int_rz(__fmul_rn(__fsub_rn(R, Y), 0.713f));
 }
 
+template <int PB>  // bytes per pixel: 4 (B,G,R,X) or 3 (B,G,R)
 __global__ void __launch_bounds__(256) xrgb_to_iyuv_quad_kernel(const uint8_t* __restrict__ bgrx, uint8_t* __restrict__ iyuv,
                                                                  uint32_t w, uint32_t h, int bottom_up, uint32_t n_frames) {
   const uint32_t qw = w >> 1;
   const uint32_t per_frame = qw * (h >> 1);
-  const uint8_t* src = bgrx + (uint64_t)blockIdx.y * w * h * 4;
+  const uint8_t* src = bgrx + (uint64_t)blockIdx.y * w * h * PB;
   uint8_t* dst = iyuv + (uint64_t)blockIdx.y * w * h * 3 / 2;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < per_frame; i += gridDim.x * blockDim.x) {
     const uint32_t rp = i / qw;
     const uint32_t row = rp * 2, col = (i - rp * qw) * 2;
     const uint32_t fr0 = bottom_up ? (h - 1 - row) : row, fr1 = bottom_up ? (h - 2 - row) : row + 1;
-    const uint2 a = *reinterpret_cast<const uint2*>(src + ((uint64_t)fr0 * w + col) * 4);
-    const uint2 b = *reinterpret_cast<const uint2*>(src + ((uint64_t)fr1 * w + col) * 4);
+    uint2 a, b;
+    if (PB == 4) {
+      a = *reinterpret_cast<const uint2*>(src + ((uint64_t)fr0 * w + col) * 4);
+      b = *reinterpret_cast<const uint2*>(src + ((uint64_t)fr1 * w + col) * 4);
+    } else {
+      const uint8_t* s0 = src + ((uint64_t)fr0 * w + col) * 3;
+      const uint8_t* s1 = src + ((uint64_t)fr1 * w + col) * 3;
+      a.x = s0[0] | (s0[1] << 8) | (s0[2] << 16); a.y = s0[3] | (s0[4] << 8) | (s0[5] << 16);
+      b.x = s1[0] | (s1[1] << 8) | (s1[2] << 16); b.y = s1[3] | (s1[4] << 8) | (s1[5] << 16);
+    }
     uint32_t y00, y01, y10, y11;
     int cb[4], cr[4];
     pixel_yuv(a.x, y00, cb[0], cr[0]); pixel_yuv(a.y, y01, cb[1], cr[1]);
@@ -357,8 +437,8 @@ __global__ void __launch_bounds__(256) xrgb_to_iyuv_quad_kernel(const uint8_t* _
   }
 }
 
-void launch_xrgb_to_iyuv(const uint8_t* d_bgrx, uint8_t* d_iyuv, uint32_t w, uint32_t h, int bottom_up, uint32_t n_frames,
-                         cudaStream_t s) {
+void launch_bgr_to_iyuv(const uint8_t* d_px, uint32_t pixel_bytes, uint8_t* d_iyuv, uint32_t w, uint32_t h, int bottom_up,
+                        uint32_t n_frames, cudaStream_t s) {
   int sms = 148;
   {
     int dev = 0;
@@ -368,17 +448,27 @@ void launch_xrgb_to_iyuv(const uint8_t* d_bgrx, uint8_t* d_iyuv, uint32_t w, uin
   // frames along grid.y (at most 65535 per launch), a grid-stride loop over the frame along grid.x
   for (uint32_t f0 = 0; f0 < n_frames; f0 += 65535u) {
     const uint32_t nf = n_frames - f0 < 65535u ? n_frames - f0 : 65535u;
-    const uint8_t* in = d_bgrx + (uint64_t)f0 * w * h * 4;
+    const uint8_t* in = d_px + (uint64_t)f0 * w * h * pixel_bytes;
     uint8_t* out = d_iyuv + (uint64_t)f0 * w * h * 3 / 2;
     const uint32_t units = (w % 8 == 0 ? w / 8 : w / 2) * (h / 2);
     if (units == 0) return;
     const uint32_t want = (units + 255) / 256;
     const uint32_t cap = ((uint32_t)sms * 16 + nf - 1) / nf;  // about 16 CTAs of 256 threads per SM over the whole launch
     const dim3 grid(want < cap ? want : (cap ? cap : 1), nf);
-    if (w % 8 == 0) xrgb_to_iyuv_kernel<<<grid, 256, 0, s>>>(in, out, w, h, bottom_up, nf, 1.0f);
-    else xrgb_to_iyuv_quad_kernel<<<grid, 256, 0, s>>>(in, out, w, h, bottom_up, nf);
+    if (pixel_bytes == 4) {
+      if (w % 8 == 0) xrgb_to_iyuv_kernel<<<grid, 256, 0, s>>>(in, out, w, h, bottom_up, nf, 1.0f);
+      else xrgb_to_iyuv_quad_kernel<4><<<grid, 256, 0, s>>>(in, out, w, h, bottom_up, nf);
+    } else {
+      if (w % 8 == 0) bgr24_to_iyuv_kernel<<<grid, 256, 0, s>>>(in, out, w, h, bottom_up, nf, 1.0f);
+      else xrgb_to_iyuv_quad_kernel<3><<<grid, 256, 0, s>>>(in, out, w, h, bottom_up, nf);
+    }
     g_launches++;
   }
+}
+
+void launch_xrgb_to_iyuv(const uint8_t* d_bgrx, uint8_t* d_iyuv, uint32_t w, uint32_t h, int bottom_up, uint32_t n_frames,
+                         cudaStream_t s) {
+  launch_bgr_to_iyuv(d_bgrx, 4, d_iyuv, w, h, bottom_up, n_frames, s);
 }
 
 // ===================================================================================================

@@ -81,6 +81,9 @@ int codec_grid_size(int device, bool encoder);
 
 void launch_xrgb_to_iyuv(const uint8_t* d_bgrx, uint8_t* d_iyuv, uint32_t w, uint32_t h, int bottom_up, uint32_t n_frames,
                          cudaStream_t s);
+// pixel_bytes: 4 (B,G,R,X) or 3 (B,G,R)
+void launch_bgr_to_iyuv(const uint8_t* d_px, uint32_t pixel_bytes, uint8_t* d_iyuv, uint32_t w, uint32_t h, int bottom_up,
+                        uint32_t n_frames, cudaStream_t s);
 // d_base: device pointer to the position of the first payload inside d_out (nullptr: 0).  finalize writes
 // d_offsets[0 .. n_frames]; a chained launch passes d_base = &offsets[first frame], which the previous chunk wrote.
 void launch_compress(const uint8_t* d_iyuv, const FrameGeom& g, const QTables& qt, uint8_t* d_out, uint64_t out_cap,

@@ -41,7 +41,11 @@ bool has(const Map& m, const Key& k) {
 // ---- registry entry: BMP (XRGB8888) -> IYUV, replaces the lambda at myyuv_yuv.cpp:89-127 ----
 YUV bmp_to_iyuv(const BMP& bmp) {
   if (!bmp.isValid()) throw std::runtime_error("BMP data is invalid");  // what colorData() would throw (:99)
-  if (bmp.header.bit_count != 32) throw std::runtime_error("Error. only 32-bit BMP is supported");  // assert at :92
+  // assert(bit_count == 32) at :92 ("TODO: test 24"); the Release build (NDEBUG) goes on and reads 24-bit files as B,G,R
+  // triplets through the same pixel_bits / 8 addressing (:34-41), which is what the 24-bit entry point does
+  if (bmp.header.bit_count != 32 && bmp.header.bit_count != 24)
+    throw std::runtime_error("Error. only 24-bit and 32-bit BMP are supported");
+  const auto convert = bmp.header.bit_count == 32 ? myyuvb_xrgb_to_iyuv : myyuvb_bgr24_to_iyuv;
   const uint32_t w = bmp.trueWidth(), h = bmp.trueHeight();
   YUV out;
   out.header.fourcc_format = YUV::FourccFormats::IYUV;
@@ -53,10 +57,10 @@ YUV bmp_to_iyuv(const BMP& bmp) {
   CtxLock ctx;
   if (bmp.header.width > 0 && bmp.header.height != 0) {
     // rows stay where they are; the kernel reads them bottom-up when height > 0 (myyuv_bmp.cpp:95-98)
-    check(myyuvb_xrgb_to_iyuv(ctx.get(), bmp.data, w, h, bmp.header.height > 0 ? 1 : 0, out.data));
+    check(convert(ctx.get(), bmp.data, w, h, bmp.header.height > 0 ? 1 : 0, out.data));
   } else if (bmp.header.width < 0 && bmp.header.height > 0) {
     std::unique_ptr<uint8_t[]> px(bmp.colorData());  // reversed pixel order, rare: reorder on the host
-    check(myyuvb_xrgb_to_iyuv(ctx.get(), px.get(), w, h, 0, out.data));
+    check(convert(ctx.get(), px.get(), w, h, 0, out.data));
   } else {
     throw std::runtime_error("Unaccounted width and height sign");
   }

@@ -295,8 +295,9 @@ class YUV:
 
 # ---- registry entries: the three slots the B200 path plugs into ----
 def _bmp_to_iyuv(bmp: BMP) -> YUV:  # replaces myyuv_yuv.cpp:89-127
-    if bmp.header.bit_count != 32:
-        raise RuntimeError("Error. only 32-bit BMP is supported")  # assert in the reference (:92)
+    # the reference asserts 32 bpp (:92, "TODO: test 24"); its Release build (NDEBUG) converts 24-bit files as B,G,R triplets
+    if bmp.header.bit_count not in (24, 32):
+        raise RuntimeError("Error. only 24-bit and 32-bit BMP are supported")
     w, h = bmp.trueWidth(), bmp.trueHeight()
     if bmp.header.width > 0 and bmp.header.height > 0:
         bottom_up = True
@@ -310,7 +311,8 @@ def _bmp_to_iyuv(bmp: BMP) -> YUV:  # replaces myyuv_yuv.cpp:89-127
     res.header.data_size = (w * h * 3 // 2) & 0xFFFFFFFF
     res.header.data_pos = 64
     try:
-        res.data = capi.default_context().xrgb_to_iyuv(bmp.data, w, h, bottom_up)
+        ctx = capi.default_context()
+        res.data = (ctx.xrgb_to_iyuv if bmp.header.bit_count == 32 else ctx.bgr24_to_iyuv)(bmp.data, w, h, bottom_up)
     except capi.MyyuvError as e:
         raise RuntimeError(str(e)) from e
     return res
