@@ -29,7 +29,8 @@ struct ZArray {  // same views as the kernel's ZShared
 
 namespace {
 // mode 0: general code on the 64-symbol scratch only; 1: 15-symbol scratch first (the kernel's pre-fast8 flow);
-// 2: the kernel's flow -- hash histogram, then the 15-symbol fast path or the general code on the 64-symbol scratch
+// 2: the kernel's flow -- hash histogram, then the 15-symbol fast path or the general code on the 64-symbol scratch;
+// 3: as 2, with the general code as heavy_blocks_kernel runs it (split accessors, 32-symbol scratch, then 64)
 template <int STRIDE>
 int encode_blocks(const int16_t* coef, uint32_t n, int mode, uint8_t* out, uint8_t* sizes) {
   using Fast = HuffScratch<15, STRIDE>;
@@ -52,7 +53,7 @@ int encode_blocks(const int16_t* coef, uint32_t n, int mode, uint8_t* out, uint8
     uint8_t tmp[256];
     int sz;
     bool done = false;
-    if (mode == 2) {
+    if (mode == 2 || mode == 3) {
       const int lane = STRIDE > 1 ? (int)(b % STRIDE) : 0;  // exercise the lane interleave
       FastScratch<STRIDE> F{f8sc + lane, reinterpret_cast<uint8_t*>(f8aux), lane};
       for (int i = 0; i < 32; i++) F.tab(i) = 0xffff;
@@ -63,6 +64,30 @@ int encode_blocks(const int16_t* coef, uint32_t n, int mode, uint8_t* out, uint8
         sz = pl.size();
         done = true;
       }
+    }
+    if (!done && mode == 3) {
+      // heavy_blocks_kernel's flow: coefficients read in place, slot numbers in a byte column; 32-symbol scratch, then 64
+      using Mid = HuffScratch<32, STRIDE>;
+      static uint8_t* mb = new uint8_t[(size_t)Mid::kBytes * STRIDE]();
+      static int16_t* mh = new int16_t[(size_t)Mid::kSyms * STRIDE]();
+      static uint8_t* slots = new uint8_t[(size_t)64 * STRIDE]();
+      uint16_t words[64];
+      for (int i = 0; i < 64; i++) words[i] = (uint16_t)za.raw(i);  // may carry huff_hist's slot bits 11..14
+      const int lane = STRIDE > 1 ? (int)(b % STRIDE) : 0;
+      Mid ms{mb + lane, mh + lane};
+      Big bl{bb + lane, bh + lane};
+      ZSplitValues<STRIDE> zv{words, slots + lane};
+      ZSplitSlots<STRIDE> zs{slots + lane};
+      HuffPlan pl = huff_plan(zv, L, ms, NoWarp{});
+      if (pl.n >= 0) {
+        huff_emit(zs, pl, ms, tmp, NoWarp{});
+      } else {
+        big_used++;
+        pl = huff_plan(zv, L, bl, NoWarp{});
+        huff_emit(zs, pl, bl, tmp, NoWarp{});
+      }
+      sz = pl.size();
+      done = true;
     }
     if (!done) {
       HuffPlan pl;
@@ -92,8 +117,8 @@ extern "C" {
 // coef: n x 64 row-major.  stride: element stride of the scratch arrays (1, or 128 to mimic the shared-memory
 // interleave of the kernel).  mode: see encode_blocks.
 int hostemu_encode_blocks(const int16_t* coef, uint32_t n, int stride, int mode, uint8_t* out, uint8_t* sizes) {
-  return stride == 128 ? encode_blocks<128>(coef, n, mode, out, sizes) : stride == 32 ? encode_blocks<32>(coef, n, mode, out, sizes)
-                                                                                  : encode_blocks<1>(coef, n, mode, out, sizes);
+  return stride == 128 ? encode_blocks<128>(coef, n, mode, out, sizes) : stride == 64 ? encode_blocks<64>(coef, n, mode, out, sizes)
+       : stride == 32 ? encode_blocks<32>(coef, n, mode, out, sizes) : encode_blocks<1>(coef, n, mode, out, sizes);
 }
 
 // mode 0: the general decoder; mode 1: the kernel's flow (fast decoder, general decoder when it declines).

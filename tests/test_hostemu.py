@@ -61,14 +61,24 @@ def make_blocks(kind, n, rng):
             vals = rng.choice(pool, min(m, pool.size), replace=False)
             L = rng.integers(1, 65)
             b[i, :L] = vals[rng.integers(0, vals.size, L)]
+    elif kind == "around32":  # the boundary between heavy_blocks_kernel's 32-symbol and 64-symbol scratch
+        for i in range(n):
+            m = 30 + i % 6
+            pool = np.arange(-70, 71) if i % 2 else np.arange(-1024, 1024)
+            vals = rng.choice(pool, m, replace=False)
+            seq = np.concatenate([vals, vals[rng.integers(0, m, 64 - m)]])
+            rng.shuffle(seq)
+            b[i] = seq
+            if i % 3 == 0:
+                b[i, 50 + i % 14:] = 0
     elif kind == "zeros":
         pass
     return b
 
 
 @pytest.mark.parametrize("kind,n", [("sparse", 6000), ("mid", 6000), ("distinct", 6000), ("full", 1500), ("small", 6000),
-                                    ("nozero", 1800), ("zeros", 64), ("few", 40000)])
-@pytest.mark.parametrize("stride,fast", [(1, 1), (128, 1), (1, 0), (1, 2), (32, 2)])
+                                    ("nozero", 1800), ("zeros", 64), ("few", 40000), ("around32", 3000)])
+@pytest.mark.parametrize("stride,fast", [(1, 1), (128, 1), (1, 0), (1, 2), (32, 2), (1, 3), (64, 3)])
 def test_block_coder_matches_oracle(emu, ora, kind, n, stride, fast):
     rng = np.random.default_rng(hash(kind) % 1000)
     b = make_blocks(kind, n, rng)

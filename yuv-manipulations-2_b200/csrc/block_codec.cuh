@@ -94,12 +94,34 @@ struct HuffScratch {
   static constexpr int kFreq = kBkt + CAP + 1;   // [2*CAP] node weight
   static constexpr int kLen = kFreq;             // [CAP]   code length of slot s
   static constexpr int kPar = kFreq + 2 * CAP;   // [2*CAP] parent node, then depth
-  static constexpr int kLut = 2 * CAP >= 128 ? kPar : kPar + 2 * CAP;  // [128] slot of the value v at index v + 64, 0xff = not seen
-  static constexpr int kBytes = kLut + (2 * CAP >= 128 ? 2 * CAP : 128);  // bytes per block
+  // [128] slot of the value v at index v + 64, 0xff = not seen: over the parent links when those are 128 bytes, over
+  // node weights + parent links when the two together are (CAP = 32), else behind them
+  static constexpr int kLut = 2 * CAP >= 128 ? kPar : 4 * CAP >= 128 ? kFreq : kPar + 2 * CAP;
+  static constexpr int kBytes = 4 * CAP >= 128 ? kPar + 2 * CAP : kLut + 128;  // bytes per block
   static constexpr int kSyms = CAP + 1;          // int16 per block
   MYB_HD uint8_t& at(int off, int i) const { return b[(off + i) * STRIDE]; }
   MYB_HD int16_t& sym(int i) const { return h[i * STRIDE]; }
 };
+
+// Accessor pair for coefficients that stay where they are (read only, e.g. the queue of deferred blocks in global
+// memory) while the slot numbers go to a byte column of the scratch: huff_plan takes ZSplitValues, huff_emit ZSplitSlots.
+template <int STRIDE>
+struct ZSplitValues {
+  const uint16_t* v;  // 64 coefficient words, zigzag order (low 11 bits: the value)
+  uint8_t* col;       // slot of message position i at col[i * STRIDE]
+  static constexpr bool kKeepsValues = true;
+  MYB_HD int get(int i) const { return ((int)((uint32_t)v[i] << 21)) >> 21; }
+  MYB_HD void set(int i, int s) { col[i * STRIDE] = (uint8_t)s; }
+};
+template <int STRIDE>
+struct ZSplitSlots {
+  const uint8_t* col;
+  MYB_HD int get(int i) const { return col[i * STRIDE]; }
+};
+template <class Z, class = void>
+struct z_keeps_values { static constexpr bool value = false; };
+template <class Z>
+struct z_keeps_values<Z, decltype((void)Z::kKeepsValues)> { static constexpr bool value = Z::kKeepsValues; };
 
 struct HuffPlan {
   int n;            // distinct symbols (leaves); < 0: scratch capacity exceeded, retry with the large instance
@@ -266,7 +288,8 @@ MYB_HD HuffPlan huff_plan(Z& z, int L, const HuffScratch<CAP, STRIDE>& S, const 
       if (s < 0) {
         if (n == CAP) {
           bail = true;  // does not fit this scratch instance: undo and let the caller retry with the big one
-          for (int j = 0; j < i; j++) z.set(j, S.sym(z.get(j)));
+          if constexpr (!z_keeps_values<Z>::value)
+            for (int j = 0; j < i; j++) z.set(j, S.sym(z.get(j)));
         } else {
           s = n++;
           S.sym(s) = (int16_t)v;

@@ -118,7 +118,7 @@ struct myyuvb_ctx {
   int grid = 0, grid_dec = 0;
   Buffer d_in, d_out, d_plane_start, d_counters, d_sizes, d_overflow, d_desc, d_offsets;
   Buffer d_scratch, d_tile_pos, d_tile_total, d_tile_prefix;
-  Buffer d_heavy_rec, d_heavy_coef, d_heavy_bytes, d_block_slot;
+  Buffer d_heavy_rec, d_heavy_coef, d_heavy_bytes, d_block_slot, d_heavy_list;
   Buffer h_small, h_stage_in, h_stage_out, h_ring;
   cudaEvent_t ring_ev[4] = {nullptr, nullptr, nullptr, nullptr};  // one per slot of h_ring (pageable <-> device staging)
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -154,6 +154,7 @@ int ensure_workspace(myyuvb_ctx* c, const FrameGeom& g, bool encoder, Workspace*
       if ((rc = c->d_heavy_coef.reserve((uint64_t)ws->heavy_cap * 128))) return rc;
       if ((rc = c->d_heavy_bytes.reserve((uint64_t)ws->heavy_cap * 256))) return rc;
       if ((rc = c->d_block_slot.reserve(nblk_total * 4))) return rc;
+      if ((rc = c->d_heavy_list.reserve((uint64_t)ws->heavy_cap * 4))) return rc;
     }
   } else {
     if ((rc = c->d_desc.reserve((uint64_t)g.n_frames * 3 * sizeof(PlaneDesc)))) return rc;
@@ -173,6 +174,7 @@ int ensure_workspace(myyuvb_ctx* c, const FrameGeom& g, bool encoder, Workspace*
   ws->heavy_coef = c->d_heavy_coef.as<uint16_t>();
   ws->heavy_bytes = c->d_heavy_bytes.as<uint8_t>();
   ws->block_slot = c->d_block_slot.as<uint32_t>();
+  ws->heavy_list = c->d_heavy_list.as<uint32_t>();
   if (!encoder) ws->heavy_cap = 0;
   ws->plane_desc = c->d_desc.p;
   ws->grid = encoder ? c->grid : c->grid_dec;
@@ -385,7 +387,7 @@ void myyuvb_ctx_destroy(myyuvb_ctx* c) {
   cudaStreamSynchronize(c->d2h_stream);
   cudaStreamSynchronize(c->hi_stream);
   for (Buffer* b : {&c->d_in, &c->d_out, &c->d_plane_start, &c->d_counters, &c->d_sizes,
-                    &c->d_overflow, &c->d_desc, &c->d_offsets, &c->d_scratch, &c->d_tile_pos, &c->d_tile_total, &c->d_tile_prefix, &c->d_heavy_rec, &c->d_heavy_coef, &c->d_heavy_bytes, &c->d_block_slot, &c->h_small, &c->h_stage_in, &c->h_stage_out, &c->h_ring})
+                    &c->d_overflow, &c->d_desc, &c->d_offsets, &c->d_scratch, &c->d_tile_pos, &c->d_tile_total, &c->d_tile_prefix, &c->d_heavy_rec, &c->d_heavy_coef, &c->d_heavy_bytes, &c->d_block_slot, &c->d_heavy_list, &c->h_small, &c->h_stage_in, &c->h_stage_out, &c->h_ring})
     b->release();
   for (auto& ev : c->ev)
     if (ev) cudaEventDestroy(ev);

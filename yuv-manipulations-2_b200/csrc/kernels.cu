@@ -777,49 +777,49 @@ __global__ void __launch_bounds__(kCtaThreads, 6)
 }
 
 // Pass 1b: the queued blocks, 32 per warp, through the general code in lockstep.  Writes each chunk to its 256-byte slot,
-// its size to the chunk size array and adds it to the tile total.  The coder's scratch (773 bytes per block) lives in
-// shared memory, lanes interleaved: in local memory it overflowed L1 and the kernel sat on the long scoreboard for 75 %
-// of its time.  64 threads per CTA so that three CTAs fit an SM.
+// its size to the chunk size array and adds it to the tile total.  The coder's scratch lives in shared memory, lanes
+// interleaved: in local memory it overflowed L1 and the kernel sat on the long scoreboard for 75 % of its time.
+// The kernel is latency bound (dependent shared-memory accesses; 19 % of the issue slots used at 8 warps per SM), so
+// what counts is warps per SM, i.e. scratch bytes per block.  Two instances: CAP = 32 (357 bytes per block: the
+// coefficients are read from the queue in global memory instead of being staged, slot numbers take a byte each, the
+// value table lies over weights + parent links; 9 CTAs of 64 threads per SM) takes every queued block and passes the
+// few with more than 32 distinct symbols on, through a list, to CAP = 64 (645 bytes per block, 5 CTAs per SM).
 constexpr int kHeavyThreads = 64;
-using HeavyScratch = HuffScratch<64, kHeavyThreads>;
+template <int CAP>
 struct HeavySmem {
-  uint16_t zz[64][kHeavyThreads];
-  int16_t syms[HeavyScratch::kSyms][kHeavyThreads];
-  uint8_t bytes[HeavyScratch::kBytes][kHeavyThreads];
+  using Scratch = HuffScratch<CAP, kHeavyThreads>;
+  uint8_t slot[64][kHeavyThreads];
+  int16_t syms[Scratch::kSyms][kHeavyThreads];
+  uint8_t bytes[Scratch::kBytes][kHeavyThreads];
 };
-struct ZHeavy {  // a column of HeavySmem::zz, value view (low 11 bits, sign extended)
-  uint16_t* col;
-  MYB_D int get(int i) const { return ((int)((uint32_t)col[i * kHeavyThreads] << 21)) >> 21; }
-  MYB_D void set(int i, int v) { col[i * kHeavyThreads] = (uint16_t)v; }
-};
-__global__ void __launch_bounds__(kHeavyThreads) heavy_blocks_kernel(const __grid_constant__ EncParams P) {
+// list == nullptr: the blocks are the queue slots 0 .. counters[4]; else: the queue slots list[0 .. counters[5]).
+// overflow != nullptr: blocks that do not fit CAP symbols are appended to it (count in counters[5]).
+template <int CAP>
+__global__ void __launch_bounds__(kHeavyThreads) heavy_blocks_kernel(const __grid_constant__ EncParams P, const uint32_t* __restrict__ list,
+                                                                     uint32_t* __restrict__ overflow) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  HeavySmem& sm = *reinterpret_cast<HeavySmem*>(smem_raw);
-  const uint32_t queued = P.ws.counters[4];
+  HeavySmem<CAP>& sm = *reinterpret_cast<HeavySmem<CAP>*>(smem_raw);
+  const uint32_t queued = list ? P.ws.counters[5] : P.ws.counters[4];
   const uint32_t count = queued < P.ws.heavy_cap ? queued : P.ws.heavy_cap;  // slots past the capacity were never handed out
-  ZHeavy z{&sm.zz[0][threadIdx.x]};
-  HeavyScratch bs{&sm.bytes[0][threadIdx.x], &sm.syms[0][threadIdx.x]};
+  typename HeavySmem<CAP>::Scratch bs{&sm.bytes[0][threadIdx.x], &sm.syms[0][threadIdx.x]};
   for (uint32_t g0 = blockIdx.x * kHeavyThreads; g0 < count; g0 += gridDim.x * kHeavyThreads) {
-    const uint32_t idx = g0 + threadIdx.x;
+    uint32_t idx = g0 + threadIdx.x;
     uint4 rec = make_uint4(0xffffffffu, 0u, 0u, 0u);
-    if (idx < count) rec = P.ws.heavy_rec[idx];
-    const bool live = rec.x != 0xffffffffu;  // a warp that found the queue full leaves its reservation unused
-    if (live) {
-      const uint32_t* hc = reinterpret_cast<const uint32_t*>(P.ws.heavy_coef + (uint64_t)idx * 64);
-#pragma unroll 4
-      for (int i = 0; i < 32; i++) {
-        const uint32_t w = hc[i];
-        z.col[(2 * i) * kHeavyThreads] = (uint16_t)w;
-        z.col[(2 * i + 1) * kHeavyThreads] = (uint16_t)(w >> 16);
-      }
+    if (idx < count) {
+      if (list) idx = list[idx];
+      rec = P.ws.heavy_rec[idx];
     }
+    const bool live = rec.x != 0xffffffffu;  // a warp that found the queue full leaves its reservation unused
+    ZSplitValues<kHeavyThreads> zv{P.ws.heavy_coef + (uint64_t)(live ? idx : 0u) * 64, &sm.slot[0][threadIdx.x]};
+    HuffPlan pl = huff_plan(zv, live ? (int)rec.z : 0, bs, WarpLockstep{});
     __syncwarp();
-    HuffPlan pl = huff_plan(z, live ? (int)rec.z : 0, bs, WarpLockstep{});
-    __syncwarp();
-    const uint32_t size = live ? (uint32_t)pl.size() : 0u;
-    if (!live) pl.n = 0;
-    huff_emit(z, pl, bs, P.ws.heavy_bytes + (uint64_t)idx * 256, WarpLockstep{});
-    if (live) {
+    const bool fits = pl.n >= 0;
+    if (live && !fits && overflow) overflow[atomicAdd(&P.ws.counters[5], 1u)] = idx;
+    const uint32_t size = live && fits ? (uint32_t)pl.size() : 0u;
+    if (!live || !fits) pl.n = 0;
+    ZSplitSlots<kHeavyThreads> zs{&sm.slot[0][threadIdx.x]};
+    huff_emit(zs, pl, bs, P.ws.heavy_bytes + (uint64_t)idx * 256, WarpLockstep{});
+    if (live && fits) {
       P.ws.chunk_sizes[rec.x] = (uint8_t)size;
       atomicAdd(&P.ws.tile_total[rec.y], size);
     }
@@ -1378,18 +1378,20 @@ void launch_compress(const uint8_t* d_iyuv, const FrameGeom& g, const QTables& q
     attr_set = true;
   }
   cudaMemsetAsync(ws.counters, 0, 4, s);       // ticket only; error flags accumulate until read
-  cudaMemsetAsync(ws.counters + 2, 0, 12, s);  // scratch bump allocator, queue of deferred blocks
+  cudaMemsetAsync(ws.counters + 2, 0, 16, s);  // scratch bump allocator, queue of deferred blocks, list of those with > 32 symbols
   const int grid = (int)(P.total_tiles < (uint32_t)ws.grid ? P.total_tiles : (uint32_t)ws.grid);
   if (ws.k_begin) cudaEventRecord(ws.k_begin, s);
   dct_compress_kernel<<<grid, kCtaThreads, sizeof(EncSmem), s>>>(P, qt);
   if (ws.heavy_cap) {
     static bool heavy_attr = false;
     if (!heavy_attr) {
-      cudaFuncSetAttribute(heavy_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HeavySmem));
+      cudaFuncSetAttribute(heavy_blocks_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HeavySmem<32>));
+      cudaFuncSetAttribute(heavy_blocks_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HeavySmem<64>));
       heavy_attr = true;
     }
     const uint32_t hwant = (ws.heavy_cap + kHeavyThreads - 1) / kHeavyThreads;
-    heavy_blocks_kernel<<<(int)(hwant < 148u * 6 ? hwant : 148u * 6), kHeavyThreads, sizeof(HeavySmem), s>>>(P);
+    heavy_blocks_kernel<32><<<(int)(hwant < 148u * 9 ? hwant : 148u * 9), kHeavyThreads, sizeof(HeavySmem<32>), s>>>(P, nullptr, ws.heavy_list);
+    heavy_blocks_kernel<64><<<(int)(hwant < 148u * 5 ? hwant : 148u * 5), kHeavyThreads, sizeof(HeavySmem<64>), s>>>(P, ws.heavy_list, nullptr);
   }
   scan_frame_tiles_kernel<<<g.n_frames, 512, 0, s>>>(P);
   scan_frames_kernel<<<1, 1024, 0, s>>>(P);
@@ -1401,7 +1403,7 @@ void launch_compress(const uint8_t* d_iyuv, const FrameGeom& g, const QTables& q
     finalize_frames_kernel<<<dim3(g.n_frames, slices), 256, 0, s>>>(P, d_offsets);
   }
   if (ws.k_end) cudaEventRecord(ws.k_end, s);  // the whole compress sequence (6 kernels) is what gets timed
-  g_launches += ws.heavy_cap ? 6 : 5;
+  g_launches += ws.heavy_cap ? 7 : 5;
 }
 
 void launch_decompress(const uint8_t* d_payloads, const uint64_t* d_offsets, const FrameGeom& g, const QTables& qt,

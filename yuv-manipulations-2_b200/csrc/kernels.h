@@ -64,6 +64,7 @@ struct Workspace {
   uint16_t* heavy_coef;    // [heavy_cap * 64] the block's coefficient words, zigzag order
   uint8_t* heavy_bytes;    // [heavy_cap * 256] its chunk
   uint32_t* block_slot;    // [blocks of the batch] queue slot of a deferred block, 0xffffffff otherwise
+  uint32_t* heavy_list;    // [heavy_cap] queue slots of the blocks with more than 32 distinct symbols (second pass)
   uint32_t heavy_cap;      // 0: nothing is deferred
   void* plane_desc;        // [n_frames*3] PlaneDesc (decompress)
   int grid;                // persistent grid size of the codec kernels
