@@ -1,6 +1,7 @@
 """A/B of the host-pointer batch calls under the bench's e2e pattern (one compress thread, one decompress thread, payload
-slots between them).  Run once per setting of MYYUVB_D2H_STREAM / MYYUVB_COPY_PIECE_MB / MYYUVB_SMALL_COPY (read once per process):
-    for d in 0 1; do for p in 0 16; do MYYUVB_D2H_STREAM=$d MYYUVB_COPY_PIECE_MB=$p python profiles/e2e_ab.py; done; done
+slots between them).  Run once per setting of MYYUVB_D2H_STREAM / MYYUVB_SMALL_COPY / MYYUVB_CHUNK_MB (read once per process; the A/B in r01_e2e_ab_*.jsonl also
+had MYYUVB_COPY_PIECE_MB and MYYUVB_SMALL_COPY=1 = high-priority stream, both removed since):
+    for d in 0 1; do for m in 0 2; do MYYUVB_D2H_STREAM=$d MYYUVB_SMALL_COPY=$m python profiles/e2e_ab.py; done; done
 Prints one JSON line."""
 import importlib, json, os, queue, sys, threading, time
 sys.path.insert(0, '.')

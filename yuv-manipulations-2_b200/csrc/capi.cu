@@ -112,7 +112,7 @@ int check_dims(uint32_t w, uint32_t h) {
 
 struct myyuvb_ctx {
   int device = 0;
-  cudaStream_t stream = nullptr, copy_stream = nullptr, d2h_stream = nullptr, hi_stream = nullptr;
+  cudaStream_t stream = nullptr, copy_stream = nullptr, d2h_stream = nullptr;
   cudaEvent_t d2h_ev[2] = {nullptr, nullptr};  // per output slot: the download of the chunk that last used it
   bool own_stream = false;
   int grid = 0, grid_dec = 0;
@@ -220,30 +220,15 @@ bool is_pinned_or_device(const void* p) {
 // for downloads of 32 MB and more a ring of four 2 MB pinned slots (DMA of slice k+1 in flight during the CPU copy of
 // slice k) wins (one 8K frame: 10 vs 12 ms per decompress call).  MYYUVB_STAGING=direct switches the ring off.
 constexpr size_t kRingSlot = 2u << 20;
-constexpr long kDefaultCopyPieceMB = 0;
 constexpr bool kDefaultOwnD2H = true;
-constexpr int kDefaultSmallCopy = 2;
 constexpr long kDefaultChunkMB = 32;
 bool ring_enabled() {
   static const bool on = [] { const char* e = getenv("MYYUVB_STAGING"); return !(e && strcmp(e, "direct") == 0); }();
   return on;
 }
 
-// Large copies are issued in pieces so that another context's small transfer in the same direction (the copy engines
-// serve their queues first come, first served) waits for one piece, not for a whole chunk.  MYYUVB_COPY_PIECE_MB=0: whole.
-size_t copy_piece_bytes() {
-  static const size_t piece = [] {
-    const char* e = getenv("MYYUVB_COPY_PIECE_MB");
-    const long mb = e ? atol(e) : kDefaultCopyPieceMB;
-    return mb > 0 ? (size_t)mb << 20 : ~(size_t)0;
-  }();
-  return piece;
-}
-
-int copy_in_pieces(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, cudaStream_t s) {
-  const size_t piece = copy_piece_bytes();
-  for (size_t off = 0; off < bytes; off += std::min(piece, bytes - off))
-    CU(cudaMemcpyAsync(static_cast<uint8_t*>(dst) + off, static_cast<const uint8_t*>(src) + off, std::min(piece, bytes - off), kind, s));
+int copy_async(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, cudaStream_t s) {
+  CU(cudaMemcpyAsync(dst, src, bytes, kind, s));  // issuing large copies in 4-16 MB pieces was measured: no gain
   return MYYUVB_OK;
 }
 
@@ -263,11 +248,12 @@ bool own_d2h_stream() {
   return on;
 }
 
-// The small side of a batch_host call (payloads): 0 = copy engine on the usual stream, 1 = copy engine on a high-priority
-// stream, 2 = SM copy kernel when the host buffer is mapped pinned memory (else 0).
-int small_copy_mode() {
-  static const int m = [] { const char* e = getenv("MYYUVB_SMALL_COPY"); return e ? atoi(e) : kDefaultSmallCopy; }();
-  return m;
+// The small side of a batch_host call (payloads, offsets): moved by sm_copy_kernel when the caller's buffer is mapped
+// pinned memory, so that it does not queue behind another context's large transfers on the copy engine (a high-priority
+// stream did not help, profiles/r01_notes.md).  MYYUVB_SMALL_COPY=0: always the copy engine.
+bool sm_copy_enabled() {
+  static const bool on = [] { const char* e = getenv("MYYUVB_SMALL_COPY"); return !(e && e[0] == '0'); }();
+  return on;
 }
 
 // device-side address of h if it lies in mapped pinned host memory, else nullptr
@@ -281,19 +267,19 @@ uint8_t* mapped_devptr(const void* h) {
 }
 
 int small_upload(myyuvb_ctx* c, void* d_dst, const void* h_src, size_t bytes, cudaStream_t s) {
-  if (small_copy_mode() == 2)
+  if (sm_copy_enabled())
     if (const uint8_t* dp = mapped_devptr(h_src)) {
       launch_sm_copy(static_cast<uint8_t*>(d_dst), dp, bytes, s);
       CU(cudaGetLastError());
       return MYYUVB_OK;
     }
   if (bytes == 0) return MYYUVB_OK;
-  return copy_in_pieces(d_dst, h_src, bytes, cudaMemcpyHostToDevice, s);
+  return copy_async(d_dst, h_src, bytes, cudaMemcpyHostToDevice, s);
 }
 
 int staged_download(myyuvb_ctx* c, void* h_dst, const void* d_src, size_t bytes, cudaStream_t s);
 int small_download(myyuvb_ctx* c, void* h_dst, const void* d_src, size_t bytes, cudaStream_t s) {
-  if (small_copy_mode() == 2)
+  if (sm_copy_enabled())
     if (uint8_t* dp = mapped_devptr(h_dst)) {
       launch_sm_copy(dp, static_cast<const uint8_t*>(d_src), bytes, s);
       CU(cudaGetLastError());
@@ -305,13 +291,13 @@ int small_download(myyuvb_ctx* c, void* h_dst, const void* d_src, size_t bytes, 
 int staged_upload(myyuvb_ctx* c, void* d_dst, const void* h_src, size_t bytes, cudaStream_t s) {
   (void)c;
   if (bytes == 0) return MYYUVB_OK;
-  return copy_in_pieces(d_dst, h_src, bytes, cudaMemcpyHostToDevice, s);
+  return copy_async(d_dst, h_src, bytes, cudaMemcpyHostToDevice, s);
 }
 
 int staged_download(myyuvb_ctx* c, void* h_dst, const void* d_src, size_t bytes, cudaStream_t s) {
   if (bytes == 0) return MYYUVB_OK;
   if (!ring_enabled() || is_pinned_or_device(h_dst) || bytes < (32u << 20))
-    return copy_in_pieces(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, s);
+    return copy_async(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, s);
   int rc;
   if ((rc = c->h_ring.reserve(4 * kRingSlot))) return rc;
   for (auto& ev : c->ring_ev) CU(cudaEventSynchronize(ev));  // earlier users of the ring have left it
@@ -364,11 +350,6 @@ int myyuvb_ctx_create(int device, void* stream, myyuvb_ctx** out) {
   }
   CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
-  {
-    int lo = 0, hi = 0;
-    CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    CU(cudaStreamCreateWithPriority(&c->hi_stream, cudaStreamNonBlocking, hi));
-  }
   for (auto& ev : c->d2h_ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   for (auto& ev : c->ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   for (auto& ev : c->ring_ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -385,7 +366,6 @@ void myyuvb_ctx_destroy(myyuvb_ctx* c) {
   cudaStreamSynchronize(c->stream);
   cudaStreamSynchronize(c->copy_stream);
   cudaStreamSynchronize(c->d2h_stream);
-  cudaStreamSynchronize(c->hi_stream);
   for (Buffer* b : {&c->d_in, &c->d_out, &c->d_plane_start, &c->d_counters, &c->d_sizes,
                     &c->d_overflow, &c->d_desc, &c->d_offsets, &c->d_scratch, &c->d_tile_pos, &c->d_tile_total, &c->d_tile_prefix, &c->d_heavy_rec, &c->d_heavy_coef, &c->d_heavy_bytes, &c->d_block_slot, &c->d_heavy_list, &c->h_small, &c->h_stage_in, &c->h_stage_out, &c->h_ring})
     b->release();
@@ -400,7 +380,6 @@ void myyuvb_ctx_destroy(myyuvb_ctx* c) {
   if (c->own_stream) cudaStreamDestroy(c->stream);
   cudaStreamDestroy(c->copy_stream);
   cudaStreamDestroy(c->d2h_stream);
-  cudaStreamDestroy(c->hi_stream);
   delete c;
 }
 
@@ -633,7 +612,7 @@ int myyuvb_dct_compress_batch_host(myyuvb_ctx* c, const uint8_t* iyuv, uint32_t 
     CU(cudaEventRecord(c->ev[slot], c->copy_stream));
     return MYYUVB_OK;
   };
-  cudaStream_t dl = small_copy_mode() == 1 ? c->hi_stream : own_d2h_stream() ? c->d2h_stream : c->stream;
+  cudaStream_t dl = own_d2h_stream() ? c->d2h_stream : c->stream;
   if ((rc = upload(0))) return rc;
   for (uint32_t k = 0; k < n_chunks; k++) {
     const uint32_t f0 = k * per, nf = std::min(per, n_frames - f0), slot = k & 1;
@@ -692,7 +671,7 @@ int myyuvb_dct_decompress_batch_host(myyuvb_ctx* c, const uint8_t* payloads, con
   if ((rc = c->h_small.reserve(256 + 2 * (per + 1) * 8))) return rc;
   uint64_t* h_off = reinterpret_cast<uint64_t*>(c->h_small.as<uint8_t>() + 256);
   const uint64_t in_slot = (max_in + 16) & ~15ull;
-  cudaStream_t up = small_copy_mode() == 1 ? c->hi_stream : c->copy_stream;
+  cudaStream_t up = c->copy_stream;
   auto upload = [&](uint32_t k) -> int {
     const uint32_t f0 = k * per, nf = std::min(per, n_frames - f0), slot = k & 1;
     const uint64_t beg = offsets[f0], bytes = offsets[f0 + nf] - beg;
