@@ -21,9 +21,11 @@
 #if defined(__CUDACC__)
 #define MYB_HD __host__ __device__ __forceinline__
 #define MYB_NOUNROLL _Pragma("unroll 1")  // keep the (large, divergent) coder loops rolled: code size is I-cache bound
+#define MYB_UNROLL4 _Pragma("unroll 4")
 #else
 #define MYB_HD inline
 #define MYB_NOUNROLL
+#define MYB_UNROLL4
 #endif
 
 namespace myyuvb {
@@ -153,54 +155,63 @@ MYB_HD int hash_bucket(int v, int nb) {
   return r < 0 ? r + nb : r;
 }
 
-// libstdc++ _M_insert_bucket_begin / _M_rehash_aux: a key whose bucket already holds nodes goes right
-// before the first node of that bucket's run, otherwise to the front of the whole list.
-template <int CAP, int STRIDE>
-MYB_HD void list_place(const HuffScratch<CAP, STRIDE>& S, int& ln, int slot, int bucket) {
-  int p = 0;
-  MYB_NOUNROLL
-  for (int i = 0; i < ln; i++)
-    if (S.at(S.kBkt, i) == bucket) { p = i; break; }
-  MYB_NOUNROLL
-  for (int i = ln; i > p; i--) {
-    S.at(S.kOrd, i) = S.at(S.kOrd, i - 1);
-    S.at(S.kBkt, i) = S.at(S.kBkt, i - 1);
-  }
-  S.at(S.kOrd, p) = (uint8_t)slot;
-  S.at(S.kBkt, p) = (uint8_t)bucket;
-  ln++;
-}
-
 // General case of the map's iteration order (more than 13 keys): 13 -> 29 -> 59 -> 127 buckets, rehash before
 // inserting key number 14, 30, 60 (_Prime_rehash_policy::_M_need_rehash, max_load_factor 1, growth 2).
 // Keys are slots 0..m-1 in first-occurrence order; erase_slot (>= 0) is removed at the end.  Result in kOrd.
+// The container is emulated as it is built (hashtable.h): a singly linked list of nodes and a bucket table whose entry is
+// the node BEFORE the bucket's first node.  _M_insert_bucket_begin: a key whose bucket already holds nodes goes right
+// before the first of them, otherwise to the front of the whole list (and the bucket of the former first node now hangs
+// off the new one).  _M_rehash_aux walks the old list front to back and re-inserts every node the same way.  Every
+// insertion is a handful of accesses, where shifting an array-shaped list cost O(list length).
+// Table and links live in the weight / parent area, which is not in use yet.
 template <int CAP, int STRIDE>
 MYB_HD void hash_list_order_general(const HuffScratch<CAP, STRIDE>& S, int m, int erase_slot) {
-  int ln = 0, nb = 13;
+  using SC = HuffScratch<CAP, STRIDE>;
+  constexpr int kTbl = SC::kFreq;                        // [nb] 0xff: empty bucket, 0xfe: before-begin, else a slot
+  constexpr int kNxt = SC::kFreq + (CAP <= 32 ? 64 : 128);  // [CAP+1] next slot in the list, 0xff: end
+  static_assert(kNxt + CAP + 1 <= SC::kBytes, "table and links must fit the weight / parent area");
+  static_assert(CAP <= 32 ? CAP + 1 <= 59 : true, "a 64-byte table holds at most 59 buckets");
+  int head = 0xff, nb = 13;
+  auto insert = [&](int s) {
+    const int b = hash_bucket(S.sym(s), nb);
+    S.at(SC::kBkt, s) = (uint8_t)b;  // bucket of slot s
+    const int prev = S.at(kTbl, b);
+    if (prev == 0xff) {
+      S.at(kNxt, s) = (uint8_t)head;
+      if (head != 0xff) S.at(kTbl, S.at(SC::kBkt, head)) = (uint8_t)s;
+      head = s;
+      S.at(kTbl, b) = 0xfe;
+    } else if (prev == 0xfe) {
+      S.at(kNxt, s) = (uint8_t)head;
+      head = s;
+    } else {
+      S.at(kNxt, s) = S.at(kNxt, prev);
+      S.at(kNxt, prev) = (uint8_t)s;
+    }
+  };
+  MYB_NOUNROLL
+  for (int i = 0; i < 13; i++) S.at(kTbl, i) = 0xff;
   MYB_NOUNROLL
   for (int s = 0; s < m; s++) {
     if (s == 13 || s == 29 || s == 59) {
       nb = (s == 13) ? 29 : (s == 29) ? 59 : 127;
-      // walk the old list front to back and re-place every node (old order parked in kFreq, unused so far)
-      for (int i = 0; i < ln; i++) S.at(S.kFreq, i) = S.at(S.kOrd, i);
-      const int old = ln;
-      ln = 0;
       MYB_NOUNROLL
-      for (int i = 0; i < old; i++) {
-        const int t = S.at(S.kFreq, i);
-        list_place(S, ln, t, hash_bucket(S.sym(t), nb));
+      for (int i = 0; i < nb; i++) S.at(kTbl, i) = 0xff;
+      int p = head;
+      head = 0xff;
+      MYB_NOUNROLL
+      while (p != 0xff) {
+        const int nx = S.at(kNxt, p);
+        insert(p);
+        p = nx;
       }
     }
-    list_place(S, ln, s, hash_bucket(S.sym(s), nb));
+    insert(s);
   }
-  if (erase_slot >= 0) {
-    int w = 0;
-    MYB_NOUNROLL
-    for (int i = 0; i < ln; i++) {
-      const uint8_t t = S.at(S.kOrd, i);
-      if (t != erase_slot) S.at(S.kOrd, w++) = t;
-    }
-  }
+  int w = 0;
+  MYB_NOUNROLL
+  for (int p = head; p != 0xff; p = S.at(kNxt, p))
+    if (p != erase_slot) S.at(SC::kOrd, w++) = (uint8_t)p;
 }
 
 // std::push_heap with Compare(a,b) = a.freq > b.freq (Huffman.hpp:41-45; stl_heap.h __push_heap).
@@ -410,20 +421,17 @@ MYB_HD HuffPlan huff_plan_tail(int L, int n, int zero_slot, bool bail, const Huf
   MYB_NOUNROLL
   for (int j = 0; j < nw; j++)
     if (j < nt) S.at(S.kLen, S.at(S.kOrd, j)) = S.at(S.kPar, j);
-  // ---- tree_data: lengths ascending, symbols ascending inside a length (Huffman.cpp:76-78): insertion sort
+  // ---- tree_data: lengths ascending, symbols ascending inside a length (Huffman.cpp:76-78).  The keys are distinct, so a
+  // slot's place is the number of smaller keys: n^2 compares whose loads do not depend on one another, where an insertion
+  // sort walks a chain of dependent loads (this code runs with few warps per SM and is bound by exactly that latency).
   MYB_NOUNROLL
   for (int i = 0; i < nw; i++) {
     if (i < nt) {
       const int key = ((int)S.at(S.kLen, i) << 12) + (S.sym(i) + 2048);
-      int j = i - 1;
-      MYB_NOUNROLL
-      while (j >= 0) {
-        const int t = S.at(S.kSorted, j);
-        if ((((int)S.at(S.kLen, t) << 12) + (S.sym(t) + 2048)) <= key) break;
-        S.at(S.kSorted, j + 1) = (uint8_t)t;
-        j--;
-      }
-      S.at(S.kSorted, j + 1) = (uint8_t)i;
+      int rank = 0;
+      MYB_UNROLL4
+      for (int j = 0; j < nt; j++) rank += ((((int)S.at(S.kLen, j) << 12) + (S.sym(j) + 2048)) < key) ? 1 : 0;
+      S.at(S.kSorted, rank) = (uint8_t)i;
     }
     warp.sync();
   }
