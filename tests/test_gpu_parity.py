@@ -304,6 +304,46 @@ def test_batch_host_api_pinned_buffers(ctx, ora, synth, pkg):
     assert np.array_equal(out[:total], out_p[:total])
 
 
+@pytest.mark.parametrize("env", [{"MYYUVB_SMALL_COPY": "0", "MYYUVB_CHUNK_MB": "4"}, {"MYYUVB_D2H_STREAM": "0", "MYYUVB_CHUNK_MB": "4"},
+                                 {"MYYUVB_CHUNK_MB": "4", "MYYUVB_STAGING": "direct"}],
+                         ids=lambda e: ",".join(f"{k}={v}" for k, v in e.items()))
+def test_batch_host_api_env_switches(env, tmp_path):
+    """The switches of INTEGRATION.md select other copy paths of the *_batch_host calls (read once per process, hence a
+    subprocess); every one must give the bytes of the default path, here checked against the oracle."""
+    import os, pathlib, subprocess, sys
+    root = pathlib.Path(__file__).resolve().parent.parent
+    script = tmp_path / "switches.py"
+    script.write_text('''
+import importlib, sys
+import numpy as np
+sys.path.insert(0, sys.argv[1])
+import oracle
+pkg = importlib.import_module("yuv-manipulations-2_b200"); synth = importlib.import_module("yuv-manipulations-2_b200.synth")
+w, h, n, q = 1280, 720 - 720 % 16, 9, (60, 40, 70)
+fb = w * h * 3 // 2
+host = synth.iyuv_frames_numpy(w, h, n, 11)
+ctx = pkg.Context(0)
+ora = oracle.Oracle()
+for pinned in (True, False):
+    if pinned:
+        a, b, c = pkg.capi.PinnedBuffer(n * fb), pkg.capi.PinnedBuffer((8 << 20) + 1), pkg.capi.PinnedBuffer(n * fb)
+        a.array[:] = host.reshape(-1)
+        src, out, back = a.array, b.array[1:], c.array
+    else:
+        src, out, back = host.reshape(-1).copy(), np.empty(8 << 20, np.uint8), np.empty(n * fb, np.uint8)
+    off = np.zeros(n + 1, np.uint64)
+    ctx.compress_batch_host(src, w, h, q, n, out, off)
+    for i in (0, 4, 8):
+        assert np.array_equal(out[int(off[i]): int(off[i + 1])], ora.compress(host[i], w, h, q)), (pinned, i)
+    ctx.decompress_batch_host(out, off, w, h, q, n, back)
+    assert np.array_equal(back[8 * fb:], ora.decompress(out[int(off[8]): int(off[9])], w, h, q)), pinned
+    assert np.array_equal(back[:fb], ora.decompress(out[int(off[0]): int(off[1])], w, h, q)), pinned
+print("switches ok")
+''')
+    r = subprocess.run([sys.executable, str(script), str(root)], env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "switches ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
 def test_round_trip_properties_4k(ctx, synth):
     """Size-independent properties at the benchmark's frame size: decode(encode(x)) is idempotent under a
     second encode/decode cycle's stream sizes, planes stay within the quantisation error, chunk sizes sum up."""
