@@ -128,8 +128,11 @@ MYYUVB_API int myyuvb_dct_decompress_batch_dev(myyuvb_ctx* ctx, const uint8_t* d
  * since the previous status call (capacity overflow, malformed payload), MYYUVB_OK otherwise. */
 MYYUVB_API int myyuvb_batch_status(myyuvb_ctx* ctx);
 
-/* ---- host-pointer batch entry points: pinned staging, H2D / kernels / D2H pipelined over chunks of
- * frames on two streams.  This is the end-to-end path bench.py times ("e2e"). ---- */
+/* ---- host-pointer batch entry points: H2D / kernels / D2H pipelined over chunks of frames on three streams.  This is
+ * the end-to-end path bench.py times ("e2e").  Any host memory is accepted; with page-locked buffers (myyuvb_host_alloc,
+ * cudaHostAlloc, cudaHostRegister) the large transfers run at link speed and the small ones (payloads, offsets) are
+ * moved by a kernel, so that two calls running side by side on two contexts do not wait for each other's copies.
+ * One context serves one host thread at a time. ---- */
 MYYUVB_API int myyuvb_dct_compress_batch_host(myyuvb_ctx* ctx, const uint8_t* iyuv, uint32_t width, uint32_t height,
                                               const uint8_t quality[3], uint32_t n_frames, uint8_t* out,
                                               uint64_t out_capacity, uint64_t* offsets /* n_frames+1 */);

@@ -400,7 +400,8 @@ int myyuvb_last_kernel_ms(myyuvb_ctx* c, float* ms) {
 
 int myyuvb_host_alloc(size_t bytes, void** out) {
   if (!out) return fail(MYYUVB_ERR_ARG, "null output pointer");
-  CU(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+  // mapped and portable (what unified addressing implies anyway): the batch_host calls let kernels read and write it
+  CU(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocMapped | cudaHostAllocPortable));
   return MYYUVB_OK;
 }
 
