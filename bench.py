@@ -72,14 +72,34 @@ def workload_config(args, n_gpus):
 
 
 # ------------------------------------------------------------------------------------------------
-# clocks sampler (nvidia-smi during the timed region)
+# clocks sampler: NVML polled every ~2 ms during the timed region (a 10-step region lasts 40 ms, too short for more than
+# one line of `nvidia-smi -lms 100`), nvidia-smi kept running beside it as the fallback
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, index: int):
-        self.rows, self.proc = [], None
+    def __init__(self, index: int, uuid: str | None = None):
+        self.rows, self.proc, self.samples, self.nvml, self.done, self.mx = [], None, [], None, False, None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            try:
+                h = pynvml.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid) if uuid else None
+            except Exception:
+                h = None
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.nvml = (pynvml, h)
+            self.bits = [pynvml.nvmlClocksEventReasonHwSlowdown, pynvml.nvmlClocksEventReasonHwThermalSlowdown,
+                         pynvml.nvmlClocksEventReasonSwThermalSlowdown, pynvml.nvmlClocksEventReasonSwPowerCap]
+            self.tn = threading.Thread(target=self._poll, daemon=True)
+            self.tn.start()
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
                                           "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -88,17 +108,33 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def _poll(self):
+        nv, h = self.nvml
+        while not self.done:
+            try:
+                self.samples.append((time.perf_counter(), float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)),
+                                     int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))))
+            except Exception:
+                return
+            time.sleep(0.002)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append((time.perf_counter(), line.strip()))
 
     def stop(self, t0, t1):
+        time.sleep(0.15)
+        self.done = True
+        if self.proc:
+            self.proc.terminate()
+        inside = [x for x in self.samples if t0 <= x[0] <= t1]
+        if inside:
+            reasons = {n for _, _, r in inside for n, b in zip(self.NAMES, self.bits) if r & b}
+            return {"sm_mhz": statistics.median(x[1] for x in inside), "sm_max_mhz": self.mx, "reasons": sorted(reasons),
+                    "samples": len(inside), "source": "nvml, polled every ~2 ms inside the timed region"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
         sm, mx, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ts, line in self.rows:
             if ts < t0 or ts > t1 + 0.15:
                 continue
@@ -108,10 +144,11 @@ class ClockSampler:
                 mx = float(p[1])
             except (ValueError, IndexError):
                 continue
-            for n, v in zip(names, p[2:6]):
+            for n, v in zip(self.NAMES, p[2:6]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm),
+                "source": "nvidia-smi -lms 100"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -282,7 +319,13 @@ def b200_main(args):
         dec_ms.append(ctx.last_kernel_ms())
 
     launches0 = capi.launch_count()
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = None
+    if rank == 0:
+        try:
+            gpu_uuid = str(torch.cuda.get_device_properties(local).uuid)
+        except Exception:
+            gpu_uuid = None
+        sampler = ClockSampler(local, gpu_uuid)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     kc, kd = [], []
     barrier()

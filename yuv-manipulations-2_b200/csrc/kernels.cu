@@ -246,12 +246,9 @@ struct PixelPair {
   int cb0, cb1, cr0, cr1;   // trunc((B - Y) * 0.564), trunc((R - Y) * 0.713)
 };
 
-MYB_D PixelPair pixel_pair_yuv(uint32_t p0, uint32_t p1, f2 ONE) {
+// B, G, R: two pixels' channel bytes as the floats 2^23 + byte (bit pattern 0x4B0000xx)
+MYB_D PixelPair pixel_pair_from_biased(f2 B, f2 G, f2 R, f2 ONE) {
   const f2 bias = dup(-8388608.0f);
-  f2 B, G, R;
-  B.x = __uint_as_float(__byte_perm(p0, 0x4B000000u, 0x7440)); B.y = __uint_as_float(__byte_perm(p1, 0x4B000000u, 0x7440));
-  G.x = __uint_as_float(__byte_perm(p0, 0x4B000000u, 0x7441)); G.y = __uint_as_float(__byte_perm(p1, 0x4B000000u, 0x7441));
-  R.x = __uint_as_float(__byte_perm(p0, 0x4B000000u, 0x7442)); R.y = __uint_as_float(__byte_perm(p1, 0x4B000000u, 0x7442));
   B = add2(B, bias); G = add2(G, bias); R = add2(R, bias);
   // Y = ((0.299f * R) + (0.587f * G)) + (0.114f * B)          myyuv_yuv.cpp:44-46
   const f2 Y = sum2(sum2(mul2(dup(0.299f), R), mul2(dup(0.587f), G), ONE), mul2(dup(0.114f), B), ONE);
@@ -266,6 +263,14 @@ MYB_D PixelPair pixel_pair_yuv(uint32_t p0, uint32_t p1, f2 ONE) {
   o.cb0 = __float2int_rz(db.x); o.cb1 = __float2int_rz(db.y);
   o.cr0 = __float2int_rz(dr.x); o.cr1 = __float2int_rz(dr.y);
   return o;
+}
+
+MYB_D PixelPair pixel_pair_yuv(uint32_t p0, uint32_t p1, f2 ONE) {
+  f2 B, G, R;
+  B.x = __uint_as_float(__byte_perm(p0, 0x4B000000u, 0x7440)); B.y = __uint_as_float(__byte_perm(p1, 0x4B000000u, 0x7440));
+  G.x = __uint_as_float(__byte_perm(p0, 0x4B000000u, 0x7441)); G.y = __uint_as_float(__byte_perm(p1, 0x4B000000u, 0x7441));
+  R.x = __uint_as_float(__byte_perm(p0, 0x4B000000u, 0x7442)); R.y = __uint_as_float(__byte_perm(p1, 0x4B000000u, 0x7442));
+  return pixel_pair_from_biased(B, G, R, ONE);
 }
 
 // four chroma samples (low bytes of a, b, c, d) -> (uint8_t)(sum of divide_roundnearest(sample + 128, 4))  myyuv_yuv.cpp:114-115
@@ -327,18 +332,23 @@ __global__ void __launch_bounds__(256) xrgb_to_iyuv_kernel(const uint8_t* __rest
 // 24-bit BMP rows (B,G,R triplets; getYUV444FromRGB2x2 addresses pixel i at byte i * bit_count / 8, myyuv_yuv.cpp:34-41;
 // rows carry no padding because a valid BMP has width % 4 == 0, myyuv_bmp.cpp:130).  Same unit of work as the 32-bit
 // kernel -- 8 pixels x 2 rows per thread -- read as three 64-bit loads per row (24 bytes, 8-byte aligned when
-// width % 8 == 0); byte permutes rebuild the B,G,R,* words pixel_pair_yuv takes.  4.5 bytes per pixel of traffic.
+// width % 8 == 0); one byte permute per channel byte, as in the 32-bit kernel.  4.5 bytes per pixel of traffic.
 struct Row24 { uint2 a, b, c; };
 
-MYB_D void unpack_row24(const Row24& r, uint32_t p[8]) {
-  p[0] = r.a.x;                                  // bytes 0..2
-  p[1] = __byte_perm(r.a.x, r.a.y, 0x0543);     // 3..5
-  p[2] = __byte_perm(r.a.y, r.b.x, 0x0432);     // 6..8
-  p[3] = r.b.x >> 8;                             // 9..11
-  p[4] = r.b.y;                                  // 12..14
-  p[5] = __byte_perm(r.b.y, r.c.x, 0x0543);     // 15..17
-  p[6] = __byte_perm(r.c.x, r.c.y, 0x0432);     // 18..20
-  p[7] = r.c.y >> 8;                             // 21..23
+// pixels 2k and 2k+1 of a 24-byte row: channel byte 3 * pixel + c sits in word (3 * pixel + c) / 4; one permute per
+// channel byte builds the float 2^23 + byte straight from that word
+template <int K>
+MYB_D PixelPair pixel_pair_row24(const Row24& r, f2 ONE) {
+  const uint32_t w[6] = {r.a.x, r.a.y, r.b.x, r.b.y, r.c.x, r.c.y};
+  auto ch = [&](int pixel, int c) {
+    const int k = 3 * pixel + c;
+    return __uint_as_float(__byte_perm(w[k >> 2], 0x4B000000u, 0x7440 + (k & 3)));
+  };
+  f2 B, G, R;
+  B.x = ch(2 * K, 0); B.y = ch(2 * K + 1, 0);
+  G.x = ch(2 * K, 1); G.y = ch(2 * K + 1, 1);
+  R.x = ch(2 * K, 2); R.y = ch(2 * K + 1, 2);
+  return pixel_pair_from_biased(B, G, R, ONE);
 }
 
 __global__ void __launch_bounds__(256) bgr24_to_iyuv_kernel(const uint8_t* __restrict__ bgr, uint8_t* __restrict__ iyuv,
@@ -363,18 +373,12 @@ __global__ void __launch_bounds__(256) bgr24_to_iyuv_kernel(const uint8_t* __res
   if (i < per_frame) fetch(i, nt, nu);
 #pragma unroll 1
   for (; i < per_frame; i += step) {
-    uint32_t pt[8], pu[8];
-    unpack_row24(nt, pt);
-    unpack_row24(nu, pu);
+    const Row24 ct = nt, cu = nu;
     if (i + step < per_frame) fetch(i + step, nt, nu);
     const uint32_t rp = i / ow;
     const uint32_t row = rp * 2, col = (i - rp * ow) * 8;
-    PixelPair t[4], u[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      t[k] = pixel_pair_yuv(pt[2 * k], pt[2 * k + 1], ONE);
-      u[k] = pixel_pair_yuv(pu[2 * k], pu[2 * k + 1], ONE);
-    }
+    const PixelPair t[4] = {pixel_pair_row24<0>(ct, ONE), pixel_pair_row24<1>(ct, ONE), pixel_pair_row24<2>(ct, ONE), pixel_pair_row24<3>(ct, ONE)};
+    const PixelPair u[4] = {pixel_pair_row24<0>(cu, ONE), pixel_pair_row24<1>(cu, ONE), pixel_pair_row24<2>(cu, ONE), pixel_pair_row24<3>(cu, ONE)};
     auto pack4 = [](uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
       return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
     };
