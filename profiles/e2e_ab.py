@@ -7,12 +7,12 @@ import importlib, json, os, queue, sys, threading, time
 sys.path.insert(0, '.')
 import numpy as np
 pkg = importlib.import_module("yuv-manipulations-2_b200"); synth = importlib.import_module("yuv-manipulations-2_b200.synth"); capi = pkg.capi
-W, H, F = 3840, 2160, 32
+W, H, F = 3840, 2160, int(os.environ.get("E2E_AB_FRAMES", "32"))
 fb = W * H * 3 // 2
 q = (50, 50, 50)
 h_in = capi.PinnedBuffer(F * fb); h_in.array[:] = np.tile(synth.iyuv_frames_numpy(W, H, 4).reshape(-1), F // 4)
 out = {"d2h_stream": os.environ.get("MYYUVB_D2H_STREAM", "default"), "piece_mb": os.environ.get("MYYUVB_COPY_PIECE_MB", "default"),
-       "small_copy": os.environ.get("MYYUVB_SMALL_COPY", "default"), "chunk_mb": os.environ.get("MYYUVB_CHUNK_MB", "default")}
+       "small_copy": os.environ.get("MYYUVB_SMALL_COPY", "default"), "chunk_mb": os.environ.get("MYYUVB_CHUNK_MB", "default"), "frames": F}
 ctx = pkg.Context(0)
 h_pay = capi.PinnedBuffer(F * 6 * 1024 * 1024); offs = np.zeros(F + 1, np.uint64); h_back = capi.PinnedBuffer(F * fb)
 for name, fn in (("compress_ms", lambda: ctx.compress_batch_host(h_in.array, W, H, q, F, h_pay.array, offs)),
@@ -25,7 +25,7 @@ for name, fn in (("compress_ms", lambda: ctx.compress_batch_host(h_in.array, W, 
 # correctness: frames 0 and 31 against the single-image device path
 one = ctx.compress(h_in.array[:fb].copy(), W, H, q)
 out["payload_ok"] = bool(np.array_equal(one, h_pay.array[int(offs[0]):int(offs[1])])) and bool(np.array_equal(ctx.decompress(one, W, H, q), h_back.array[:fb]))
-out["last_frame_ok"] = bool(np.array_equal(h_back.array[31 * fb:], h_back.array[3 * fb:4 * fb]))
+out["last_frame_ok"] = bool(np.array_equal(h_back.array[(F - 1) * fb:], h_back.array[3 * fb:4 * fb]))
 import zlib
 out["crc_payload"] = zlib.crc32(h_pay.array[:int(offs[F])].tobytes()); out["crc_back"] = zlib.crc32(h_back.array.tobytes())
 ctx.close()
