@@ -109,16 +109,17 @@ def test_cli_converts_24bit_bmp_like_the_reference_cli(synth, tmp_path):
     cli = LIB / "myyuv_cli"
     if not (ref_cli.exists() and cli.exists()):
         pytest.skip("CLIs not built")
-    for w, h_signed in ((64, 48), (40, -24)):
-        h = abs(h_signed)
+    # bottom-up, top-down, and the reversed pixel order colorData() produces for a negative width (myyuv_bmp.cpp:89-94)
+    for w_signed, h_signed in ((64, 48), (40, -24), (-40, 24)):
+        w, h = abs(w_signed), abs(h_signed)
         px = np.ascontiguousarray(synth.bgrx_frames_numpy(w, h, 1, 4)[0].reshape(-1, 4)[:, :3]).tobytes()
-        header = b"BM" + struct.pack("<IHHIIiiHHIIiiII", 54 + len(px), 0, 0, 54, 40, w, h_signed, 1, 24, 0, 0, 2835, 2835, 0, 0)
+        header = b"BM" + struct.pack("<IHHIIiiHHIIiiII", 54 + len(px), 0, 0, 54, 40, w_signed, h_signed, 1, 24, 0, 0, 2835, 2835, 0, 0)
         assert len(header) == 54
-        bmp = tmp_path / f"in{w}.bmp"
+        bmp = tmp_path / f"in{w_signed}_{h_signed}.bmp"
         bmp.write_bytes(header + px)
         outs = []
         for exe, tag in ((cli, "ours"), (ref_cli, "ref")):
-            o = tmp_path / f"{tag}{w}.myyuv"
+            o = tmp_path / f"{tag}{w_signed}_{h_signed}.myyuv"
             r = subprocess.run([str(exe), str(bmp), "-to_yuv", "IYUV", "-o", str(o)], capture_output=True, text=True, timeout=300)
             assert r.returncode == 0 and "Success!" in r.stdout, r.stdout + r.stderr
             outs.append(o.read_bytes())
