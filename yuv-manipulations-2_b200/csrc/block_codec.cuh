@@ -86,14 +86,14 @@ struct HuffScratch {
   // in heavy_blocks_kernel, where every byte per lane costs occupancy):
   //   list order -> (dead after the code lengths are assigned) -> canonical codes
   //   bucket list, then heap -> (dead after the merges) -> sorted slots
-  //   node weights -> (dead after the merges) -> code lengths
+  //   map emulation's table and links -> heap weights (upper half, dead after the merges); lower half: code lengths
   //   value table of the histogram -> (dead after the histogram) -> parent links / depths
   static constexpr int kCnt = 0;                 // [CAP+1] occurrences of slot s in the message
   static constexpr int kOrd = kCnt + CAP + 1;    // [CAP+1] hash-list order: slot at list position p
   static constexpr int kCode = kOrd;             // [CAP]   bit-reversed canonical code of slot s
   static constexpr int kBkt = kOrd + CAP + 1;    // [CAP+1] bucket of list position p; later: heap
   static constexpr int kSorted = kBkt;           // [CAP]   slots ordered by (length, symbol value)
-  static constexpr int kFreq = kBkt + CAP + 1;   // [2*CAP] node weight
+  static constexpr int kFreq = kBkt + CAP + 1;   // [2*CAP] hash table + links of the map emulation, then upper half: heap weights
   static constexpr int kLen = kFreq;             // [CAP]   code length of slot s
   static constexpr int kPar = kFreq + 2 * CAP;   // [2*CAP] parent node, then depth
   // [128] slot of the value v at index v + 64, 0xff = not seen: over the parent links when those are 128 bytes, over
@@ -215,42 +215,53 @@ MYB_HD void hash_list_order_general(const HuffScratch<CAP, STRIDE>& S, int m, in
 }
 
 // std::push_heap with Compare(a,b) = a.freq > b.freq (Huffman.hpp:41-45; stl_heap.h __push_heap).
-// heap lives in kBkt (free after the list order is final).
+// The heap is two parallel byte arrays: node ids in kBkt (free after the list order is final) and their weights in the
+// upper half of kFreq, so a comparison reads the weight at the heap position itself instead of going through the node id
+// (this code is bound by the latency of such chains).  Weights are at most 64 (a block has 64 coefficients).
 template <int CAP, int STRIDE>
 MYB_HD void heap_sift_up(const HuffScratch<CAP, STRIDE>& S, int hole, int node, int wnode) {
+  constexpr int kHeapW = HuffScratch<CAP, STRIDE>::kFreq + CAP;
   MYB_NOUNROLL
   while (hole > 0) {
     const int parent = (hole - 1) >> 1;
-    const int pn = S.at(S.kBkt, parent);
-    if (!(S.at(S.kFreq, pn) > wnode)) break;
-    S.at(S.kBkt, hole) = (uint8_t)pn;
+    const int pw = S.at(kHeapW, parent);
+    if (!(pw > wnode)) break;
+    S.at(S.kBkt, hole) = S.at(S.kBkt, parent);
+    S.at(kHeapW, hole) = (uint8_t)pw;
     hole = parent;
   }
   S.at(S.kBkt, hole) = (uint8_t)node;
+  S.at(kHeapW, hole) = (uint8_t)wnode;
 }
 
-// std::pop_heap + pop_back (stl_heap.h __pop_heap / __adjust_heap); returns the removed top node.
+// std::pop_heap + pop_back (stl_heap.h __pop_heap / __adjust_heap); returns the removed top node, its weight in wtop.
 template <int CAP, int STRIDE>
-MYB_HD int heap_pop(const HuffScratch<CAP, STRIDE>& S, int& hsize) {
+MYB_HD int heap_pop(const HuffScratch<CAP, STRIDE>& S, int& hsize, int& wtop) {
+  constexpr int kHeapW = HuffScratch<CAP, STRIDE>::kFreq + CAP;
   const int top = S.at(S.kBkt, 0);
+  wtop = S.at(kHeapW, 0);
   const int len = hsize - 1;
   hsize = len;
   if (len == 0) return top;
-  const int value = S.at(S.kBkt, len);
+  const int value = S.at(S.kBkt, len), wvalue = S.at(kHeapW, len);
   int hole = 0, child = 0;
   MYB_NOUNROLL
   while (child < ((len - 1) >> 1)) {
     child = 2 * (child + 1);
-    if (S.at(S.kFreq, S.at(S.kBkt, child)) > S.at(S.kFreq, S.at(S.kBkt, child - 1))) child--;
+    int wc = S.at(kHeapW, child);
+    const int wl = S.at(kHeapW, child - 1);
+    if (wc > wl) { child--; wc = wl; }
     S.at(S.kBkt, hole) = S.at(S.kBkt, child);
+    S.at(kHeapW, hole) = (uint8_t)wc;
     hole = child;
   }
   if ((len & 1) == 0 && child == ((len - 2) >> 1)) {
     child = 2 * (child + 1);
     S.at(S.kBkt, hole) = S.at(S.kBkt, child - 1);
+    S.at(kHeapW, hole) = S.at(kHeapW, child - 1);
     hole = child - 1;
   }
-  heap_sift_up(S, hole, value, S.at(S.kFreq, value));
+  heap_sift_up(S, hole, value, wvalue);
   return top;
 }
 
@@ -381,7 +392,7 @@ MYB_HD HuffPlan huff_plan_tail(int L, int n, int zero_slot, bool bail, const Huf
     }
     warp.sync();
   }
-  // ---- leaves pushed in list order (Huffman.cpp:207-209); node id = list position, weights in kFreq
+  // ---- leaves pushed in list order (Huffman.cpp:207-209); node id = list position, weights travel with the heap entries
   const int nt = tree ? n : 0;
   const int nw = warp.max(nt);
   int hsize = 0;
@@ -389,7 +400,6 @@ MYB_HD HuffPlan huff_plan_tail(int L, int n, int zero_slot, bool bail, const Huf
   for (int j = 0; j < nw; j++) {
     if (j < nt) {
       const int w = S.at(S.kCnt, S.at(S.kOrd, j));
-      S.at(S.kFreq, j) = (uint8_t)w;
       hsize++;
       heap_sift_up(S, hsize - 1, j, w);
     }
@@ -399,10 +409,10 @@ MYB_HD HuffPlan huff_plan_tail(int L, int n, int zero_slot, bool bail, const Huf
   MYB_NOUNROLL
   for (int t = 0; t + 1 < nw; t++) {  // Huffman.cpp:210-217: n - 1 merges
     if (t + 1 < nt) {
-      const int l = heap_pop(S, hsize);
-      const int r = heap_pop(S, hsize);
-      const int w = S.at(S.kFreq, l) + S.at(S.kFreq, r);
-      S.at(S.kFreq, nnode) = (uint8_t)w;
+      int wl, wr;
+      const int l = heap_pop(S, hsize, wl);
+      const int r = heap_pop(S, hsize, wr);
+      const int w = wl + wr;
       S.at(S.kPar, l) = (uint8_t)nnode;
       S.at(S.kPar, r) = (uint8_t)nnode;
       hsize++;
