@@ -57,7 +57,7 @@ MYYUVB_API const char* myyuvb_last_error(void); /* thread-local, valid until the
 MYYUVB_API int myyuvb_sync(myyuvb_ctx* ctx);    /* wait for the context's stream */
 MYYUVB_API void* myyuvb_stream(myyuvb_ctx* ctx);
 /* Device time (CUDA events on the context stream) of the most recent compress launch sequence (code tiles,
- * two scans, place, headers: 5 kernels) or decompress kernel on this context -- the figure bench.py's roofline uses.
+ * deferred blocks, two scans, place, headers: 8 kernels) or decompress kernel on this context -- the figure bench.py's roofline uses.
  * Synchronises. */
 MYYUVB_API int myyuvb_last_kernel_ms(myyuvb_ctx* ctx, float* ms);
 

@@ -952,47 +952,89 @@ __global__ void __launch_bounds__(256) place_tiles_kernel(const __grid_constant_
       if (lane == 0) atomicOr(&P.ws.counters[1], kFlagCapacity);
       continue;
     }
-    if (!(total_raw >> 31)) {
-      if (src + total > P.ws.scratch_cap) {  // the coding pass found no room for this tile (flag already raised there)
-        if (lane == 0) atomicOr(&P.ws.counters[1], kFlagCapacity);
-        continue;
-      }
-      copy_global_to_global_v4(P.out + pos, P.ws.scratch + src, total, 32, lane);
+    if (total_raw >> 31) {  // a tile with queued blocks: listed for place_heavy_tiles_kernel (the list of the heavy kernels is free again)
+      if (lane == 0) P.ws.heavy_list[atomicAdd(&P.ws.counters[6], 1u)] = tile;
       continue;
     }
-    // A tile with queued blocks: the scratch area holds the chunks of the other blocks back to back, the queued ones sit
-    // in their slots.  Every lane takes four consecutive blocks; two warp scans give each block its place in the
-    // payload and in the scratch stream; the chunks are then copied one by one.
-    const u64 gblk0 = (u64)tc.frame * g.nblk_frame + (plane > 0 ? g.nblk[0] : 0) + (plane > 1 ? g.nblk[1] : 0) + tc.k0;
-    uint32_t sz[4], sl[4], all = 0, light = 0;
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const uint32_t b = 4 * lane + j;
-      sz[j] = b < tc.nblk ? P.ws.chunk_sizes[gblk0 + b] : 0u;
-      sl[j] = b < tc.nblk ? P.ws.block_slot[gblk0 + b] : 0xffffffffu;
-      all += sz[j];
-      light += sl[j] == 0xffffffffu ? sz[j] : 0u;
-    }
-    uint32_t dsta = all, srca = light;  // inclusive scans over the lanes
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t a = __shfl_up_sync(0xffffffffu, dsta, o), b2 = __shfl_up_sync(0xffffffffu, srca, o);
-      if (lane >= (uint32_t)o) { dsta += a; srca += b2; }
-    }
-    uint32_t doff = dsta - all, soff = srca - light;
-    if (src + __shfl_sync(0xffffffffu, srca, 31) > P.ws.scratch_cap) {
+    if (src + total > P.ws.scratch_cap) {  // the coding pass found no room for this tile (flag already raised there)
       if (lane == 0) atomicOr(&P.ws.counters[1], kFlagCapacity);
       continue;
     }
-    for (uint32_t owner = 0; owner < 32; owner++) {
-      uint32_t d = __shfl_sync(0xffffffffu, doff, owner), sc = __shfl_sync(0xffffffffu, soff, owner);
+    copy_global_to_global_v4(P.out + pos, P.ws.scratch + src, total, 32, lane);
+  }
+}
+
+// The tiles that hold queued blocks (listed by place_tiles_kernel), a warp per tile; a kernel of its own because the weaving
+// below needs 80 registers and the plain copy above lives on having 64 warps per SM in flight.  A batch without such tiles
+// pays one empty launch.
+__global__ void __launch_bounds__(256) place_heavy_tiles_kernel(const __grid_constant__ EncParams P) {
+  const FrameGeom& g = P.g;
+  const uint32_t lane = threadIdx.x & 31, warps = gridDim.x * (blockDim.x >> 5);
+  const uint32_t count = P.ws.counters[6];
+  {
+    for (uint32_t e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < count; e += warps) {
+      const uint32_t tile = P.ws.heavy_list[e];
+      const TileCoord tc = tile_coord(g, tile);
+      const int plane = (int)tc.plane;
+      const uint32_t total = P.ws.tile_total[tile] & 0x7fffffffu;
+      const u64 src = P.ws.tile_pos[tile];
+      const uint32_t fixed = 12 + 8 * (plane + 1) + g.nblk[0] + (plane > 0 ? g.nblk[1] : 0) + (plane > 1 ? g.nblk[2] : 0);
+      const u64 pos = (P.base ? *P.base : 0) + (u64)tc.frame * (36 + g.nblk_frame) + fixed + P.ws.frame_base[tc.frame] + P.ws.tile_prefix[tile];
+      if (pos + total > P.out_cap) {
+        if (lane == 0) atomicOr(&P.ws.counters[1], kFlagCapacity);
+        continue;
+      }
+      // A tile with queued blocks: the scratch area holds the chunks of the other blocks back to back, the queued ones sit
+      // in their slots.  Every lane takes four consecutive blocks; two warp scans give each block its place in the
+      // payload and in the scratch stream; the chunks are then copied eight at a time.
+      const u64 gblk0 = (u64)tc.frame * g.nblk_frame + (plane > 0 ? g.nblk[0] : 0) + (plane > 1 ? g.nblk[1] : 0) + tc.k0;
+      uint32_t sz[4], sl[4], all = 0, light = 0;
 #pragma unroll
       for (int j = 0; j < 4; j++) {
-        const uint32_t n = __shfl_sync(0xffffffffu, sz[j], owner), slot = __shfl_sync(0xffffffffu, sl[j], owner);
-        const uint8_t* from = slot == 0xffffffffu ? P.ws.scratch + src + sc : P.ws.heavy_bytes + (u64)slot * 256;
-        for (uint32_t i = lane; i < n; i += 32) P.out[pos + d + i] = from[i];
-        d += n;
-        if (slot == 0xffffffffu) sc += n;
+        const uint32_t b = 4 * lane + j;
+        sz[j] = b < tc.nblk ? P.ws.chunk_sizes[gblk0 + b] : 0u;
+        sl[j] = b < tc.nblk ? P.ws.block_slot[gblk0 + b] : 0xffffffffu;
+        all += sz[j];
+        light += sl[j] == 0xffffffffu ? sz[j] : 0u;
+      }
+      uint32_t dsta = all, srca = light;  // inclusive scans over the lanes
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t a = __shfl_up_sync(0xffffffffu, dsta, o), b2 = __shfl_up_sync(0xffffffffu, srca, o);
+        if (lane >= (uint32_t)o) { dsta += a; srca += b2; }
+      }
+      uint32_t doff = dsta - all, soff = srca - light;
+      if (src + __shfl_sync(0xffffffffu, srca, 31) > P.ws.scratch_cap) {
+        if (lane == 0) atomicOr(&P.ws.counters[1], kFlagCapacity);
+        continue;
+      }
+      // Eight chunks (the blocks of two lanes) per step: all their loads are issued before the first store, so a step costs
+      // one memory latency instead of eight (a store waits for its load and holds back everything behind it).
+      for (uint32_t owner = 0; owner < 32; owner += 2) {
+        const uint8_t* from[8];
+        uint32_t to[8], n[8], nmax = 0;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          uint32_t d = __shfl_sync(0xffffffffu, doff, owner + h), sc = __shfl_sync(0xffffffffu, soff, owner + h);
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const uint32_t nn = __shfl_sync(0xffffffffu, sz[j], owner + h), slot = __shfl_sync(0xffffffffu, sl[j], owner + h);
+            from[4 * h + j] = slot == 0xffffffffu ? P.ws.scratch + src + sc : P.ws.heavy_bytes + (u64)slot * 256;
+            to[4 * h + j] = d;
+            n[4 * h + j] = nn;
+            nmax = nn > nmax ? nn : nmax;
+            d += nn;
+            if (slot == 0xffffffffu) sc += nn;
+          }
+        }
+        for (uint32_t i = lane; i < nmax; i += 32) {
+          uint8_t v[8];
+#pragma unroll
+          for (int c = 0; c < 8; c++) v[c] = i < n[c] ? from[c][i] : (uint8_t)0;
+#pragma unroll
+          for (int c = 0; c < 8; c++)
+            if (i < n[c]) P.out[pos + to[c] + i] = v[c];
+        }
       }
     }
   }
@@ -1382,7 +1424,7 @@ void launch_compress(const uint8_t* d_iyuv, const FrameGeom& g, const QTables& q
     attr_set = true;
   }
   cudaMemsetAsync(ws.counters, 0, 4, s);       // ticket only; error flags accumulate until read
-  cudaMemsetAsync(ws.counters + 2, 0, 16, s);  // scratch bump allocator, queue of deferred blocks, list of those with > 32 symbols
+  cudaMemsetAsync(ws.counters + 2, 0, 20, s);  // scratch bump allocator, queue of deferred blocks, list of those with > 32 symbols, list of tiles with queued blocks
   const int grid = (int)(P.total_tiles < (uint32_t)ws.grid ? P.total_tiles : (uint32_t)ws.grid);
   if (ws.k_begin) cudaEventRecord(ws.k_begin, s);
   dct_compress_kernel<<<grid, kCtaThreads, sizeof(EncSmem), s>>>(P, qt);
@@ -1401,13 +1443,14 @@ void launch_compress(const uint8_t* d_iyuv, const FrameGeom& g, const QTables& q
   scan_frames_kernel<<<1, 1024, 0, s>>>(P);
   const uint32_t pwant = (P.total_tiles + 7) / 8;
   place_tiles_kernel<<<(int)(pwant < 148u * 8 ? pwant : 148u * 8), 256, 0, s>>>(P);
+  if (ws.heavy_cap) place_heavy_tiles_kernel<<<(int)(pwant < 148u * 3 ? pwant : 148u * 3), 256, 0, s>>>(P);
   {
     uint32_t slices = 0;
     for (int p = 0; p < 3; p++) slices += (g.nblk[p] + kSizeSlice - 1) / kSizeSlice;
     finalize_frames_kernel<<<dim3(g.n_frames, slices), 256, 0, s>>>(P, d_offsets);
   }
-  if (ws.k_end) cudaEventRecord(ws.k_end, s);  // the whole compress sequence (6 kernels) is what gets timed
-  g_launches += ws.heavy_cap ? 7 : 5;
+  if (ws.k_end) cudaEventRecord(ws.k_end, s);  // the whole compress sequence (8 kernels) is what gets timed
+  g_launches += ws.heavy_cap ? 8 : 5;
 }
 
 void launch_decompress(const uint8_t* d_payloads, const uint64_t* d_offsets, const FrameGeom& g, const QTables& qt,
