@@ -501,8 +501,18 @@ struct EncSmem {
   uint32_t split;
   uint32_t heavy;            // the tile holds a block that was queued for heavy_blocks_kernel
   u64 base;
+  // counting sort of the tile's blocks by message length (kSortBlocks): thread t entropy-codes block perm[t]
+  uint32_t hist[68];
+  uint16_t boff[kTileBlocks];   // chunk offset of block b inside the tile
+  uint8_t msg_len[kTileBlocks];
+  uint8_t csize[kTileBlocks];
+  uint8_t perm[kTileBlocks];
 };
 static_assert(sizeof(EncSmem) <= 37 * 1024 - 512, "EncSmem must allow 6 CTAs per SM");
+// Thread t codes the block of rank t in message-length order, so that the lanes of a warp get messages of similar length
+// and the lockstep loops (trip count = warp maximum) waste few lanes.  Five more CTA barriers per tile.
+constexpr bool kSortBlocks = true;
+static_assert(!kSortBlocks || kEncPasses == 1, "boff holds 16-bit offsets of a one-pass tile");
 
 struct ZShared {  // accessor of one block's column in EncSmem::zz
   uint16_t* col;
@@ -658,17 +668,46 @@ __global__ void __launch_bounds__(kCtaThreads, 6)
         }
         L = fdct_quant_block(raw, qt, plane, P.one, z.col);
       }
-      // ---- phase B: entropy-code the block (same thread, so no CTA barrier in between); warp lockstep ----
-      // (Sorting the tile's blocks by message length so that warps get homogeneous work was tried: it cut issued
-      //  instructions by 11% but not the time, because a CTA waits for its slowest warp -- profiles/r01_notes.md.)
+      // ---- phase B: entropy-code one block; warp lockstep ----
       if (!live) L = 0;
+      uint32_t mine = (uint32_t)tid;  // the block (of this pass) this thread codes
+      if (kSortBlocks) {
+        sm.msg_len[tid] = (uint8_t)L;
+        if (tid < 68) sm.hist[tid] = 0;
+        __syncthreads();
+        const uint32_t within = atomicAdd(&sm.hist[L], 1u);
+        __syncthreads();
+        if (tid < 32) {  // exclusive prefix of the 65 bins (padded to 66), three per lane
+          const uint32_t h0 = lane < 22 ? sm.hist[3 * lane] : 0u, h1 = lane < 22 ? sm.hist[3 * lane + 1] : 0u,
+                         h2 = lane < 22 ? sm.hist[3 * lane + 2] : 0u;
+          uint32_t inc = h0 + h1 + h2;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t nn = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += nn;
+          }
+          if (lane < 22) {
+            sm.hist[3 * lane] = inc - h0 - h1 - h2;
+            sm.hist[3 * lane + 1] = inc - h1 - h2;
+            sm.hist[3 * lane + 2] = inc - h2;
+          }
+        }
+        __syncthreads();
+        sm.perm[sm.hist[L] + within] = (uint8_t)tid;
+        __syncthreads();
+        mine = sm.perm[tid];
+        L = sm.msg_len[mine];
+      }
+      const uint32_t mblk = pass * kTileBlocks + mine;
+      const bool mlive = mblk < tc.nblk;
+      ZShared zm{&sm.zz[0][mine]};
       {  // empty the warp's hash table (2 KB, 64 bytes per lane)
         uint4* q = reinterpret_cast<uint4*>(wbase + 2048);
 #pragma unroll
         for (int j = 0; j < 4; j++) q[lane + 32 * j] = make_uint4(~0u, ~0u, ~0u, ~0u);
       }
       __syncwarp();
-      int nsym = huff_hist(z, L, live, f8, WarpLockstep{});
+      int nsym = huff_hist(zm, L, mlive, f8, WarpLockstep{});
       // Blocks with more than 15 distinct symbols (0.5 % of the luma blocks of natural images at q 50, every block of
       // noise at q 100) do not fit the fast path.  Coding one of them in place would send the whole warp through the
       // general code for it, so they are queued -- coefficient words, block index, message length -- and coded 32 at a
@@ -687,8 +726,8 @@ __global__ void __launch_bounds__(kCtaThreads, 6)
             hslot = qbase + (uint32_t)__popc(hmask & ((1u << lane) - 1u));
             uint32_t* hc = reinterpret_cast<uint32_t*>(P.ws.heavy_coef + (uint64_t)hslot * 64);
 #pragma unroll 4
-            for (int i = 0; i < 32; i++) hc[i] = z.raw(2 * i) | (z.raw(2 * i + 1) << 16);
-            P.ws.heavy_rec[hslot] = make_uint4((uint32_t)(gblk0 + blk), tile, (uint32_t)L, 0u);
+            for (int i = 0; i < 32; i++) hc[i] = zm.raw(2 * i) | (zm.raw(2 * i + 1) << 16);
+            P.ws.heavy_rec[hslot] = make_uint4((uint32_t)(gblk0 + mblk), tile, (uint32_t)L, 0u);
             sm.heavy = 1u;
             nsym = 0;  // an idle lane of the fast path, chunk size 0 for now
           }
@@ -711,20 +750,26 @@ __global__ void __launch_bounds__(kCtaThreads, 6)
         // the whole warp runs the general code in lockstep on per-thread local-memory scratch (all lanes touch the same
         // offsets together, so the accesses coalesce in L1).  It redoes the histogram from the coefficient values, which
         // huff_hist left readable in the low 11 bits of the coefficient words.
-        pl = huff_plan(z, L, bs, WarpLockstep{});
+        pl = huff_plan(zm, L, bs, WarpLockstep{});
         __syncwarp();
-        size = live ? (uint32_t)pl.size() : 0u;
+        size = mlive ? (uint32_t)pl.size() : 0u;
       }
       // chunk sizes go to a linear side array; finalize_frames_kernel moves them behind the plane headers,
       // whose position depends on the (data dependent) size of the previous planes
-      if (live) P.ws.chunk_sizes[gblk0 + blk] = (uint8_t)size;
+      if (mlive) P.ws.chunk_sizes[gblk0 + mblk] = (uint8_t)size;
       // CTA scan of the chunk sizes.  Between its two barriers thread 0 reserves the tile's place in the scratch area
       // (bump allocation, completion order; file-order offsets are computed afterwards by the scan kernels, so no CTA
       // ever waits for another one): chunks that do not fit the shared staging buffer are then written straight to it.
       uint32_t pass_total, off;
       {
         const int wid = tid >> 5;
-        uint32_t inc = size;
+        uint32_t rsize = size;  // the size of block tid: offsets follow raster order
+        if (kSortBlocks) {
+          sm.csize[mine] = (uint8_t)size;
+          __syncthreads();
+          rsize = sm.csize[tid];
+        }
+        uint32_t inc = rsize;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
           const uint32_t nb = __shfl_up_sync(0xffffffffu, inc, o);
@@ -745,11 +790,12 @@ __global__ void __launch_bounds__(kCtaThreads, 6)
           P.ws.tile_total[tile] = tot | (sm.heavy ? 0x80000000u : 0u);  // bit 31: chunks of queued blocks are still missing
           sm.base = pos;
         }
+        if (kSortBlocks) sm.boff[tid] = (uint16_t)(carried + before + inc - rsize);
         __syncthreads();
-        off = carried + before + inc - size;
+        off = kSortBlocks ? (uint32_t)sm.boff[mine] : carried + before + inc - size;
         pass_total = tot;
         // only place_tiles_kernel's path for tiles with queued blocks reads the slot array
-        if (sm.heavy && live) P.ws.block_slot[gblk0 + blk] = hslot;
+        if (sm.heavy && mlive) P.ws.block_slot[gblk0 + mblk] = hslot;
       }
       const u64 pos = sm.base;
       const bool room = pos + pass_total <= P.ws.scratch_cap;  // CTA uniform
@@ -758,13 +804,13 @@ __global__ void __launch_bounds__(kCtaThreads, 6)
         // no room: the capacity flag is raised below and the bytes go to a per-CTA dummy area
         uint8_t* dst = fits ? &sm.stage[off] : (room ? P.ws.scratch + pos + off : overflow + off);
         // first chunk that does not fit the shared staging buffer (chunks never straddle; offsets only grow)
-        if (live && !fits && off <= (uint32_t)kStageBytes) atomicMin(&sm.split, off);
+        if (mlive && !fits && off <= (uint32_t)kStageBytes) atomicMin(&sm.split, off);
         if (__builtin_expect(fast, 1)) {
-          huff_fast_emit(z, pl8, f8, dst, WarpLockstep{});
+          huff_fast_emit(zm, pl8, f8, dst, WarpLockstep{});
         } else {
           HuffPlan plf = pl;
-          if (!live) plf.n = 0;
-          huff_emit(z, plf, bs, dst, WarpLockstep{});
+          if (!mlive) plf.n = 0;
+          huff_emit(zm, plf, bs, dst, WarpLockstep{});
         }
       }
       carried += pass_total;
