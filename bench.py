@@ -81,7 +81,7 @@ class ClockSampler:
     NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index: int, uuid: str | None = None):
-        self.rows, self.proc, self.samples, self.nvml, self.done, self.mx = [], None, [], None, False, None
+        self.rows, self.proc, self.samples, self.nvml, self.done, self.mx, self.err = [], None, [], None, False, None, None
         try:
             import pynvml
 
@@ -108,15 +108,33 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
-    def _poll(self):
+    def _query(self):
         nv, h = self.nvml
+        sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+        try:
+            r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+        except Exception:
+            try:
+                r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+            except Exception:
+                r = 0
+        return (time.perf_counter(), sm, r)
+
+    def _poll(self):
         while not self.done:
             try:
-                self.samples.append((time.perf_counter(), float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)),
-                                     int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))))
-            except Exception:
-                return
+                self.samples.append(self._query())
+            except Exception as e:  # keep polling: one failed reading must not end the sampling
+                self.err = repr(e)
+                time.sleep(0.01)
             time.sleep(0.002)
+
+    def sample_now(self):
+        if self.nvml:
+            try:
+                self.samples.append(self._query())
+            except Exception as e:
+                self.err = repr(e)
 
     def _read(self):
         for line in self.proc.stdout:
@@ -128,15 +146,20 @@ class ClockSampler:
         if self.proc:
             self.proc.terminate()
         inside = [x for x in self.samples if t0 <= x[0] <= t1]
+        source = "nvml, polled every ~2 ms inside the timed region"
+        if not inside:  # the poller was starved: the readings closest to the region (the GPU is under the same load in the warm-up before it)
+            inside = [x for x in self.samples if t0 - 0.25 <= x[0] <= t1 + 0.05]
+            source = "nvml, readings within 250 ms before the timed region (none fell inside)"
         if inside:
             reasons = {n for _, _, r in inside for n, b in zip(self.NAMES, self.bits) if r & b}
             return {"sm_mhz": statistics.median(x[1] for x in inside), "sm_max_mhz": self.mx, "reasons": sorted(reasons),
-                    "samples": len(inside), "source": "nvml, polled every ~2 ms inside the timed region"}
+                    "samples": len(inside), "source": source}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         sm, mx, reasons = [], None, set()
+        lo = t0 if any(t0 <= ts <= t1 + 0.15 for ts, _ in self.rows) else t0 - 0.5  # nothing inside: the lines just before
         for ts, line in self.rows:
-            if ts < t0 or ts > t1 + 0.15:
+            if ts < lo or ts > t1 + 0.15:
                 continue
             p = [x.strip() for x in line.split(",")]
             try:
@@ -147,8 +170,11 @@ class ClockSampler:
             for n, v in zip(self.NAMES, p[2:6]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm),
-                "source": "nvidia-smi -lms 100"}
+        out = {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm),
+               "source": "nvidia-smi -lms 100"}
+        if self.err:
+            out["nvml_error"] = self.err
+        return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -305,6 +331,14 @@ def b200_main(args):
         ctx.compress_batch_dev(d_in, W, H, q, F, d_out, cap, d_off)
         ctx.decompress_batch_dev(d_out, d_off, W, H, q, F, d_back)
 
+    # the clock sampler starts before the warm-up, so that it is up and polling when the timed region begins
+    sampler = None
+    if rank == 0:
+        try:
+            gpu_uuid = str(torch.cuda.get_device_properties(local).uuid)
+        except Exception:
+            gpu_uuid = None
+        sampler = ClockSampler(local, gpu_uuid)
     for _ in range(max(args.warmup, 3)):
         step()
     ctx.batch_status()
@@ -319,13 +353,6 @@ def b200_main(args):
         dec_ms.append(ctx.last_kernel_ms())
 
     launches0 = capi.launch_count()
-    sampler = None
-    if rank == 0:
-        try:
-            gpu_uuid = str(torch.cuda.get_device_properties(local).uuid)
-        except Exception:
-            gpu_uuid = None
-        sampler = ClockSampler(local, gpu_uuid)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     kc, kd = [], []
     barrier()
@@ -334,6 +361,8 @@ def b200_main(args):
     for _ in range(args.steps):
         step()
     ev[1].record(stream)
+    if sampler:
+        sampler.sample_now()  # the steps are queued and running: one reading from this thread as well
     barrier()
     t1 = time.perf_counter()
     dev_ms = ev[0].elapsed_time(ev[1])

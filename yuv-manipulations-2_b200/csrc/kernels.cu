@@ -1159,8 +1159,16 @@ struct DecSmem {
   uint32_t warp_sums[4];
   uint32_t tile;
   u64 base;
+  // counting sort of the tile's blocks by chunk size (kSortDecBlocks): thread t decodes block perm[t]
+  uint32_t hist[64];
+  uint16_t boff[kTileBlocks];
+  uint8_t bsize[kTileBlocks];
+  uint8_t perm[kTileBlocks];
 };
 static_assert(sizeof(DecSmem) <= 36 * 1024, "DecSmem must allow 6 CTAs per SM");
+// Thread t decodes the block of rank t in chunk-size order (4-byte bins): the lanes of a warp get messages of similar
+// length and, more often than not, the same sparse IDCT variant.  Three more CTA barriers per tile.
+constexpr bool kSortDecBlocks = true;
 
 struct DecParams {
   const uint8_t* payloads;
@@ -1400,13 +1408,41 @@ __global__ void __launch_bounds__(kCtaThreads, 6)
     const uint32_t off = cta_exclusive_scan(size, sm.warp_sums, &scanned);
 #pragma unroll
     for (int i = 0; i < 64; i++) col[i * kTileBlocks] = 0;
+    if (kSortDecBlocks) {
+      sm.boff[tid] = (uint16_t)off;
+      sm.bsize[tid] = (uint8_t)size;
+      if (tid < 64) sm.hist[tid] = 0;
+    }
     __syncthreads();
 
     // ---- phase 1: canonical Huffman decode + dequantise into the thread's shared-memory column (warp lockstep) ----
-    const uint32_t blk = tid;
-    const bool mine = live;
+    uint32_t blk = tid, boff = off, bsize = size;  // the block this thread decodes and transforms
+    if (kSortDecBlocks) {
+      const uint32_t key = (size >> 2) < 63u ? (size >> 2) : 63u;
+      const uint32_t within = atomicAdd(&sm.hist[key], 1u);
+      __syncthreads();
+      if (tid < 32) {  // exclusive prefix of the 64 bins, two per lane
+        const uint32_t h0 = sm.hist[2 * tid], h1 = sm.hist[2 * tid + 1];
+        uint32_t inc = h0 + h1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t nn = __shfl_up_sync(0xffffffffu, inc, o);
+          if (tid >= o) inc += nn;
+        }
+        sm.hist[2 * tid] = inc - h0 - h1;
+        sm.hist[2 * tid + 1] = inc - h1;
+      }
+      __syncthreads();
+      sm.perm[sm.hist[key] + within] = (uint8_t)tid;
+      __syncthreads();
+      blk = sm.perm[tid];
+      boff = sm.boff[blk];
+      bsize = sm.bsize[blk];
+    }
+    const bool mine = blk < tc.nblk;
     int nsym = 0;  // decoded zigzag positions: the non-zero coefficients lie in positions [0, nsym)
     {
+      const uint32_t off = boff, size = bsize;  // of block blk from here on
       const uint8_t* chunk = (off + size <= (uint32_t)kDecStageBytes) ? &sm.stage[mis + off] : content + off;
       auto emit = [&](int j, int v) {
         *reinterpret_cast<int16_t*>(reinterpret_cast<uint8_t*>(col) + sm.zoff[j]) = (int16_t)v;
