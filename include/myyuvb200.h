@@ -86,6 +86,13 @@ MYYUVB_API int myyuvb_dct_compress(myyuvb_ctx* ctx, const uint8_t* iyuv, uint32_
                                    const uint8_t quality[3], uint8_t* out, uint64_t out_capacity,
                                    uint32_t* out_size);
 
+/* The same in two steps, for bindings that must return an exact-size allocation (YUV::data is new uint8_t[data_size],
+ * released with delete[] in ~YUV, myyuv_yuv.cpp:243-246; alloc site DCT.cpp:162): _begin uploads and codes the image and
+ * reports the payload size, the payload stays on the device; _fetch copies it into the caller's buffer. */
+MYYUVB_API int myyuvb_dct_compress_begin(myyuvb_ctx* ctx, const uint8_t* iyuv, uint32_t width, uint32_t height,
+                                         const uint8_t quality[3], uint32_t* out_size);
+MYYUVB_API int myyuvb_dct_compress_fetch(myyuvb_ctx* ctx, uint8_t* out, uint64_t out_capacity);
+
 /* replaces decompress_map[DCT][IYUV] -> myyuvDCT::decompress_DCT_planar (myyuv_yuv.cpp:146-159, DCT.cpp:432-488). */
 MYYUVB_API int myyuvb_dct_decompress(myyuvb_ctx* ctx, const uint8_t* payload, uint32_t payload_size, uint32_t width,
                                      uint32_t height, const uint8_t quality[3], uint8_t* iyuv_out);
@@ -146,6 +153,10 @@ MYYUVB_API void myyuvb_host_free(void* p);
 
 /* number of kernels this library has launched on this thread's contexts since process start (bench.py's gpu_launches) */
 MYYUVB_API uint64_t myyuvb_launch_count(void);
+
+/* Profiling aid: clock sums per phase of the two codec kernels, out24 = [2][12] (compress, decompress).  All zero in the
+ * product library; the -DMYYUVB_PHASE_CLOCKS build (lib/libmyyuvb200_clk.so, profiles/phase_clocks.py) fills them. */
+MYYUVB_API void myyuvb_phase_clocks(uint64_t* out24, int reset);
 
 #ifdef __cplusplus
 }

@@ -74,6 +74,16 @@ def main():
             blocks[i, rng.integers(0, 64, 40)] = 0
     chunks, sizes = ref.huff_encode_blocks(blocks)
     out["huffman_blocks"] = {"seed": 20261018, "n": 4096, "sizes_sha256": sha(sizes), "chunks_sha256": sha(chunks)}
+    # natural content at the benchmark's frame size (SURVEY 8(d) config 3(i) "tiled-real"): the reference's sample image
+    # tiled to 3840x2160, origin shifted per frame
+    out["tiled_real"] = []
+    if (O.GOLDEN_DIR / "chef-with-trumpet.myyuv").exists():
+        g = O.read_myyuv(O.GOLDEN_DIR / "chef-with-trumpet.myyuv")
+        for q, first in [((50, 50, 50), 0), ((90, 90, 90), 3), ((10, 10, 10), 5)]:
+            f = synth.tiled_real_iyuv(g["data"], g["w"], g["h"], 3840, 2160, 1, first)[0]
+            c = ref.compress(f, 3840, 2160, q)
+            out["tiled_real"].append({"w": 3840, "h": 2160, "q": list(q), "first": first, "input_sha256": sha(f), "payload_size": int(c.size),
+                                      "payload_sha256": sha(c), "decoded_sha256": sha(ref.decompress(c, 3840, 2160, q))})
     # the reference's sample images
     if (O.GOLDEN_DIR / "chef-with-trumpet.bmp").exists():
         for name in ["chef-with-trumpet.bmp", "chef-with-trumpet.myyuv", "chef-with-trumpet-DCT-50.myyuv", "chef-with-trumpet-DCT-90.myyuv",

@@ -124,3 +124,10 @@ def test_cli_converts_24bit_bmp_like_the_reference_cli(synth, tmp_path):
             assert r.returncode == 0 and "Success!" in r.stdout, r.stdout + r.stderr
             outs.append(o.read_bytes())
         assert outs[0] == outs[1] and len(outs[0]) == 64 + w * h * 3 // 2
+        # the Python mirror of the class API takes the same orientations (it used to refuse width < 0, height > 0)
+        import importlib
+
+        pkg = importlib.import_module("yuv-manipulations-2_b200")
+        py = tmp_path / f"py{w_signed}_{h_signed}.myyuv"
+        pkg.YUV(pkg.BMP(str(bmp)), pkg.YUV.FourccFormats.IYUV).dump(str(py))
+        assert py.read_bytes() == outs[1]

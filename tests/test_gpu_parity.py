@@ -344,6 +344,79 @@ print("switches ok")
     assert r.returncode == 0 and "switches ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
 
+def _golden():
+    import json
+    import pathlib
+
+    return json.loads((pathlib.Path(__file__).resolve().parent / "golden" / "golden.json").read_text())
+
+
+def _sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def test_headline_4k_frame_matches_reference_hashes(ctx, synth):
+    """The benchmark's own frame 0 (3840x2160 noise-grad, q 50): payload and decoded image against the hashes the
+    unmodified reference produced for it (tests/golden/make_golden.py)."""
+    case = next(c for c in _golden()["synthetic"] if c["w"] == 3840)
+    w, h, q = case["w"], case["h"], tuple(case["q"])
+    f = frames(synth, w, h, 1, case["first"])[0]
+    assert _sha(f) == case["input_sha256"], "synthetic generator changed"
+    p = ctx.compress(f, w, h, q)
+    assert p.size == case["payload_size"]
+    assert _sha(p) == case["payload_sha256"]
+    assert _sha(ctx.decompress(p, w, h, q)) == case["decoded_sha256"]
+
+
+def test_headline_4k_batch_of_64_matches_oracle(ctx, ora, synth, pkg):
+    """bench.py's step -- 64 frames of 3840x2160 at q 50 through compress_batch_dev / decompress_batch_dev -- with frames
+    0, 31 and 63 compared byte for byte with the oracle (frame 0 also with the reference's hash)."""
+    torch = pytest.importorskip("torch")
+    w, h, n, q = 3840, 2160, 64, (50, 50, 50)
+    d_in = synth.iyuv_frames_torch(w, h, n, torch.device("cuda", 0))
+    cap = n * 6 * 1024 * 1024
+    d_out = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    d_off = torch.zeros(n + 1, dtype=torch.int64, device="cuda")
+    d_back = torch.empty_like(d_in)
+    torch.cuda.synchronize()
+    ctx.compress_batch_dev(d_in, w, h, q, n, d_out, cap, d_off)
+    ctx.decompress_batch_dev(d_out, d_off, w, h, q, n, d_back)
+    ctx.batch_status()
+    off = d_off.cpu().numpy()
+    assert off[0] == 0 and (np.diff(off) > 0).all()
+    case = next(c for c in _golden()["synthetic"] if c["w"] == 3840)
+    for i in (0, 31, 63):
+        f = d_in[i].cpu().numpy()
+        assert np.array_equal(f, frames(synth, w, h, 1, i)[0]), "torch and numpy generators differ"
+        got = d_out[int(off[i]): int(off[i + 1])].cpu().numpy()
+        want = ora.compress(f, w, h, q)
+        assert got.size == want.size and np.array_equal(got, want), f"payload of frame {i}"
+        assert np.array_equal(d_back[i].cpu().numpy(), ora.decompress(want, w, h, q)), f"decoded frame {i}"
+        if i == 0:
+            assert _sha(got) == case["payload_sha256"] and _sha(d_back[0].cpu().numpy()) == case["decoded_sha256"]
+    del d_in, d_out, d_back
+    torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("idx", [0, 1, 2])
+def test_natural_content_4k_matches_reference_and_oracle(ctx, ora, synth, golden_dir, idx):
+    """Natural content at the benchmark's frame size (the reference's sample image tiled to 4K)
+    at q 50, 90 and 10: against the reference's hashes and, byte for byte, the oracle."""
+    import oracle
+
+    case = _golden()["tiled_real"][idx]
+    g = oracle.read_myyuv(golden_dir / "chef-with-trumpet.myyuv")
+    w, h, q = case["w"], case["h"], tuple(case["q"])
+    f = synth.tiled_real_iyuv(g["data"], g["w"], g["h"], w, h, 1, case["first"])[0]
+    assert _sha(f) == case["input_sha256"]
+    p = ctx.compress(f, w, h, q)
+    assert p.size == case["payload_size"] and _sha(p) == case["payload_sha256"]
+    assert np.array_equal(p, ora.compress(f, w, h, q))
+    d = ctx.decompress(p, w, h, q)
+    assert _sha(d) == case["decoded_sha256"]
+    assert np.array_equal(d, ora.decompress(p, w, h, q))
+
+
 def test_round_trip_properties_4k(ctx, synth):
     """Size-independent properties at the benchmark's frame size: decode(encode(x)) is idempotent under a
     second encode/decode cycle's stream sizes, planes stay within the quantisation error, chunk sizes sum up."""

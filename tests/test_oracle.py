@@ -161,6 +161,21 @@ def test_qtable_formula(ora):
     assert ora.qtable(75, False)[0] == 8
 
 
+@pytest.mark.parametrize("idx", [0, 1, 2])
+def test_natural_content_4k_matches_reference_hashes(ora, synth, golden_dir, idx):
+    """tiled-real 4K frames at q 50 / 90 / 10 against the reference's hashes."""
+    import oracle
+
+    case = GOLDEN["tiled_real"][idx]
+    g = oracle.read_myyuv(golden_dir / "chef-with-trumpet.myyuv")
+    w, h, q = case["w"], case["h"], tuple(case["q"])
+    f = synth.tiled_real_iyuv(g["data"], g["w"], g["h"], w, h, 1, case["first"])[0]
+    assert sha(f) == case["input_sha256"]
+    c = ora.compress(f, w, h, q)
+    assert c.size == case["payload_size"] and sha(c) == case["payload_sha256"]
+    assert sha(ora.decompress(c, w, h, q)) == case["decoded_sha256"]
+
+
 def test_tiled_real_generator(synth):
     """natural frames for the side measurements are a base image tiled with a per-frame shift."""
     rng = np.random.default_rng(0)

@@ -38,13 +38,16 @@ def _run(cmd, verbose):
     subprocess.run([str(c) for c in cmd], check=True)
 
 
-def build_cuda(force: bool = False, verbose: bool = False) -> pathlib.Path:
+def build_cuda(force: bool = False, verbose: bool = False, variant: str = "") -> pathlib.Path:
+    """variant "clk": the same sources with -DMYYUVB_PHASE_CLOCKS (per-phase clock counters in the codec kernels), a
+    profiling build next to the product library, loaded only when MYYUVB_LIB_VARIANT=clk (profiles/phase_clocks.py)."""
     LIB.mkdir(exist_ok=True)
-    out = LIB / "libmyyuvb200.so"
+    out = LIB / ("libmyyuvb200.so" if not variant else f"libmyyuvb200_{variant}.so")
     srcs = [CSRC / "kernels.cu", CSRC / "capi.cu"]
     deps = srcs + [CSRC / "kernels.h", CSRC / "block_codec.cuh", CSRC / "dct_matrix.inc", ROOT / "include/myyuvb200.h"]
     if force or _newer(out, deps):
-        _run([NVCC, *ARCH, "-O3", "-lineinfo", "-std=c++17", "-fmad=false", "-ccbin", CXX,
+        extra = ["-DMYYUVB_PHASE_CLOCKS"] if variant == "clk" else []
+        _run([NVCC, *ARCH, "-O3", "-lineinfo", "-std=c++17", "-fmad=false", *extra, "-ccbin", CXX,
               "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden", "--shared", "-o", out, *srcs], verbose)
     return out
 
@@ -73,4 +76,7 @@ def build(force: bool = False, verbose: bool = False):
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose=True)
+    if "--clk" in sys.argv:
+        build_cuda(force="--force" in sys.argv, verbose=True, variant="clk")
+    else:
+        build(force="--force" in sys.argv, verbose=True)

@@ -25,6 +25,7 @@ EXPORTS = [
     "myyuvb_xrgb_dct_compress_batch_dev", "myyuvb_bgr24_to_iyuv", "myyuvb_bgr24_to_iyuv_batch_dev",
     "myyuvb_batch_status", "myyuvb_dct_compress_batch_host", "myyuvb_dct_decompress_batch_host",
     "myyuvb_host_alloc", "myyuvb_host_free", "myyuvb_launch_count", "myyuvb_last_kernel_ms",
+    "myyuvb_dct_compress_begin", "myyuvb_dct_compress_fetch", "myyuvb_phase_clocks",
 ]
 
 
@@ -37,7 +38,10 @@ class MyyuvError(RuntimeError):
 
 
 def library_path() -> pathlib.Path:
-    return _PKG / "lib" / "libmyyuvb200.so"
+    import os
+
+    variant = os.environ.get("MYYUVB_LIB_VARIANT", "")  # "clk": the profiling build with per-phase clock counters
+    return _PKG / "lib" / ("libmyyuvb200.so" if not variant else f"libmyyuvb200_{variant}.so")
 
 
 _lib = None
@@ -65,6 +69,8 @@ def lib() -> C.CDLL:
     L.myyuvb_bgr24_to_iyuv.argtypes = L.myyuvb_xrgb_to_iyuv.argtypes
     L.myyuvb_dct_compress.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, _u8p, C.c_void_p, C.c_uint64,
                                       C.POINTER(C.c_uint32)]
+    L.myyuvb_dct_compress_begin.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, _u8p, C.POINTER(C.c_uint32)]
+    L.myyuvb_dct_compress_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
     L.myyuvb_dct_decompress.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, _u8p, C.c_void_p]
     L.myyuvb_xrgb_to_iyuv_batch_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_void_p]
     L.myyuvb_bgr24_to_iyuv_batch_dev.argtypes = L.myyuvb_xrgb_to_iyuv_batch_dev.argtypes
@@ -84,6 +90,8 @@ def lib() -> C.CDLL:
     L.myyuvb_host_free.restype = None
     L.myyuvb_launch_count.restype = C.c_uint64
     L.myyuvb_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    L.myyuvb_phase_clocks.argtypes = [C.c_void_p, C.c_int]
+    L.myyuvb_phase_clocks.restype = None
     _lib = L
     return L
 
@@ -94,15 +102,25 @@ def _check(rc: int):
 
 
 def _q(q) -> np.ndarray:
-    qa = np.ascontiguousarray(np.asarray(q).astype(np.uint8))
-    if qa.size != 3:
+    qi = np.asarray(q).astype(np.int64).reshape(-1)
+    if qi.size != 3:
         # compress_map lambda, myyuv_yuv.cpp:134-136
         raise MyyuvError(ERR_ARG, "Error compression: incorrect parameters count. 3 parameters required")
-    return qa
+    if ((qi < 1) | (qi > 100)).any():
+        # checked before the cast to uint8, which would fold e.g. 306 onto 50 (DCT.cpp:378-382 tests the uint8 the caller stored)
+        raise MyyuvError(ERR_QUALITY, "Level of quality must be between 1 and 100")
+    return np.ascontiguousarray(qi.astype(np.uint8))
 
 
 def compress_bound(w: int, h: int) -> int:
     return int(lib().myyuvb_compress_bound(w, h))
+
+
+def phase_clocks(reset: bool = True) -> np.ndarray:
+    """[2][12] clock sums per phase (compress, decompress); zeros unless MYYUVB_LIB_VARIANT=clk."""
+    out = np.zeros(24, np.uint64)
+    lib().myyuvb_phase_clocks(out.ctypes.data, int(reset))
+    return out.reshape(2, 12)
 
 
 def launch_count() -> int:
@@ -200,10 +218,14 @@ class Context:
         if iyuv.size != w * h * 3 // 2:
             raise ValueError("iyuv must hold width*height*3/2 bytes")
         qa = _q(q)
-        cap = compress_bound(w, h) if capacity is None else capacity
-        out = np.empty(max(cap, 1), np.uint8)
         n = C.c_uint32(0)
-        _check(lib().myyuvb_dct_compress(self._h, iyuv.ctypes.data, w, h, qa.ctypes.data_as(_u8p), out.ctypes.data, cap, C.byref(n)))
+        if capacity is None:  # two steps: the size first, then an exact-size buffer (what the class API does)
+            _check(lib().myyuvb_dct_compress_begin(self._h, iyuv.ctypes.data, w, h, qa.ctypes.data_as(_u8p), C.byref(n)))
+            out = np.empty(max(n.value, 1), np.uint8)
+            _check(lib().myyuvb_dct_compress_fetch(self._h, out.ctypes.data, n.value))
+            return out[: n.value]
+        out = np.empty(max(capacity, 1), np.uint8)
+        _check(lib().myyuvb_dct_compress(self._h, iyuv.ctypes.data, w, h, qa.ctypes.data_as(_u8p), out.ctypes.data, capacity, C.byref(n)))
         return out[: n.value].copy()
 
     def decompress(self, payload: np.ndarray, w: int, h: int, q) -> np.ndarray:

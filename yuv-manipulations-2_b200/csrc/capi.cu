@@ -10,6 +10,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <string>
 
 #include "../../include/myyuvb200.h"
@@ -74,7 +75,12 @@ struct Buffer {
     if (bytes <= cap) return MYYUVB_OK;
     release();
     const size_t want = bytes + bytes / 8 + 256;
+    static const bool trace = getenv("MYYUVB_TRACE") != nullptr;  // where a first call spends its time (profiles/first_call.py)
+    const auto t0 = std::chrono::steady_clock::now();
     cudaError_t e = pinned ? cudaHostAlloc(&p, want, cudaHostAllocMapped | cudaHostAllocPortable) : cudaMalloc(&p, want);
+    if (trace)
+      fprintf(stderr, "[myyuvb] %s %zu bytes: %.3f ms\n", pinned ? "cudaHostAlloc" : "cudaMalloc", want,
+              std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
     if (e != cudaSuccess) {
       p = nullptr;
       return fail(MYYUVB_ERR_CUDA, std::string("CUDA error: ") + cudaGetErrorString(e) + " allocating " + std::to_string(want) + " bytes");
@@ -123,6 +129,7 @@ struct myyuvb_ctx {
   cudaEvent_t ring_ev[4] = {nullptr, nullptr, nullptr, nullptr};  // one per slot of h_ring (pageable <-> device staging)
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t kev[2] = {nullptr, nullptr};  // timing events around the last main codec kernel
+  uint64_t pending_payload = 0;             // bytes of the payload myyuvb_dct_compress_begin left in d_out
   myyuvb_ctx() { h_small.pinned = h_stage_in.pinned = h_stage_out.pinned = h_ring.pinned = true; }
 };
 
@@ -228,6 +235,7 @@ bool ring_enabled() {
 }
 
 int copy_async(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, cudaStream_t s) {
+  if (bytes == 0) return MYYUVB_OK;
   CU(cudaMemcpyAsync(dst, src, bytes, kind, s));  // issuing large copies in 4-16 MB pieces was measured: no gain
   return MYYUVB_OK;
 }
@@ -288,12 +296,6 @@ int small_download(myyuvb_ctx* c, void* h_dst, const void* d_src, size_t bytes, 
   return staged_download(c, h_dst, d_src, bytes, s);
 }
 
-int staged_upload(myyuvb_ctx* c, void* d_dst, const void* h_src, size_t bytes, cudaStream_t s) {
-  (void)c;
-  if (bytes == 0) return MYYUVB_OK;
-  return copy_async(d_dst, h_src, bytes, cudaMemcpyHostToDevice, s);
-}
-
 int staged_download(myyuvb_ctx* c, void* h_dst, const void* d_src, size_t bytes, cudaStream_t s) {
   if (bytes == 0) return MYYUVB_OK;
   if (!ring_enabled() || is_pinned_or_device(h_dst) || bytes < (32u << 20))
@@ -327,6 +329,11 @@ const char* myyuvb_last_error(void) { return g_err.c_str(); }
 
 uint64_t myyuvb_launch_count(void) { return g_launches; }
 
+void myyuvb_phase_clocks(uint64_t* out24, int reset) {
+  static_assert(sizeof(uint64_t) == sizeof(unsigned long long), "");
+  if (out24) read_phase_clocks(reinterpret_cast<unsigned long long*>(out24), reset);
+}
+
 uint64_t myyuvb_compress_bound(uint32_t width, uint32_t height) {
   const uint64_t nblk = (uint64_t)(width / 8) * (height / 8) + 2ull * (width / 16) * (height / 16);
   return 12 + 24 + nblk + nblk * 255;
@@ -342,18 +349,26 @@ int myyuvb_ctx_create(int device, void* stream, myyuvb_ctx** out) {
   CU(cudaSetDevice(device));
   myyuvb_ctx* c = new myyuvb_ctx();
   c->device = device;
-  if (stream) {
-    c->stream = reinterpret_cast<cudaStream_t>(stream);
-  } else {
-    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    c->own_stream = true;
+  const int rc = [&]() -> int {
+    if (stream) {
+      c->stream = reinterpret_cast<cudaStream_t>(stream);
+    } else {
+      CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+      c->own_stream = true;
+    }
+    CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+    for (auto& ev : c->d2h_ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    for (auto& ev : c->ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    for (auto& ev : c->ring_ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    for (auto& ev : c->kev) CU(cudaEventCreate(&ev));
+    return MYYUVB_OK;
+  }();
+  if (rc) {  // a half-built context is taken apart again (the message of the failed call survives the clean-up)
+    const std::string msg = g_err;
+    myyuvb_ctx_destroy(c);
+    return fail(rc, msg);
   }
-  CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-  CU(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
-  for (auto& ev : c->d2h_ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-  for (auto& ev : c->ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-  for (auto& ev : c->ring_ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-  for (auto& ev : c->kev) CU(cudaEventCreate(&ev));
   c->grid = codec_grid_size(device, true);
   c->grid_dec = codec_grid_size(device, false);
   *out = c;
@@ -363,9 +378,9 @@ int myyuvb_ctx_create(int device, void* stream, myyuvb_ctx** out) {
 void myyuvb_ctx_destroy(myyuvb_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
-  cudaStreamSynchronize(c->stream);
-  cudaStreamSynchronize(c->copy_stream);
-  cudaStreamSynchronize(c->d2h_stream);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+  if (c->d2h_stream) cudaStreamSynchronize(c->d2h_stream);
   for (Buffer* b : {&c->d_in, &c->d_out, &c->d_plane_start, &c->d_counters, &c->d_sizes,
                     &c->d_overflow, &c->d_desc, &c->d_offsets, &c->d_scratch, &c->d_tile_pos, &c->d_tile_total, &c->d_tile_prefix, &c->d_heavy_rec, &c->d_heavy_coef, &c->d_heavy_bytes, &c->d_block_slot, &c->d_heavy_list, &c->h_small, &c->h_stage_in, &c->h_stage_out, &c->h_ring})
     b->release();
@@ -377,9 +392,9 @@ void myyuvb_ctx_destroy(myyuvb_ctx* c) {
     if (ev) cudaEventDestroy(ev);
   for (auto& ev : c->d2h_ev)
     if (ev) cudaEventDestroy(ev);
-  if (c->own_stream) cudaStreamDestroy(c->stream);
-  cudaStreamDestroy(c->copy_stream);
-  cudaStreamDestroy(c->d2h_stream);
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
   delete c;
 }
 
@@ -418,10 +433,18 @@ int convert_dev_impl(myyuvb_ctx* c, const uint8_t* d_px, uint32_t pixel_bytes, u
   if (!c || !d_px || !d_iyuv) return fail(MYYUVB_ERR_ARG, "null argument");
   if (w == 0 || h == 0 || (w % 2) || (h % 2)) return fail(MYYUVB_ERR_EVEN, "Error. width and height must be even");
   if ((uint64_t)w * h * 4 > 0xffffffffull) return fail(MYYUVB_ERR_TOO_LARGE, "Error. image does not fit the format's uint32 sizes");
-  if (pixel_bytes == 4 ? ((uintptr_t)d_px & 15) != 0 : ((uintptr_t)d_px & 7) != 0 || ((uint64_t)w * h * 3) % 8 != 0)
-    return fail(MYYUVB_ERR_ARG, pixel_bytes == 4 ? "device buffers must be 16-byte (input) / 8-byte (output) aligned"
-                                                 : "24-bit input: device buffer must be 8-byte aligned and a frame a multiple of 8 bytes");
-  if ((uintptr_t)d_iyuv & 7) return fail(MYYUVB_ERR_ARG, "device buffers must be 16-byte (input) / 8-byte (output) aligned");
+  // Alignment is what the kernel that will run needs: the 8-pixel kernels (width % 8 == 0) use 128-bit (32-bit pixels) or
+  // 64-bit (24-bit pixels) loads and 64-bit stores on every frame of the batch; the quad kernel for other widths reads 24-bit
+  // pixels bytewise and 32-bit pixels as 64-bit pairs, and stores 16 bits at a time.
+  if (w % 8 == 0) {
+    if (pixel_bytes == 4 ? ((uintptr_t)d_px & 15) != 0 : (((uintptr_t)d_px & 7) != 0 || (n_frames > 1 && ((uint64_t)w * h * 3) % 8 != 0)))
+      return fail(MYYUVB_ERR_ARG, pixel_bytes == 4 ? "device buffers must be 16-byte (input) / 8-byte (output) aligned"
+                                                   : "24-bit input: device buffer must be 8-byte aligned and, in a batch, a frame a multiple of 8 bytes");
+    if ((uintptr_t)d_iyuv & 7) return fail(MYYUVB_ERR_ARG, "device buffers must be 16-byte (input) / 8-byte (output) aligned");
+  } else {
+    if (pixel_bytes == 4 && ((uintptr_t)d_px & 7)) return fail(MYYUVB_ERR_ARG, "32-bit input: device buffer must be 8-byte aligned");
+    if ((uintptr_t)d_iyuv & 1) return fail(MYYUVB_ERR_ARG, "device output must be 2-byte aligned");
+  }
   CU(cudaSetDevice(c->device));
   launch_bgr_to_iyuv(d_px, pixel_bytes, d_iyuv, w, h, bottom_up, n_frames, c->stream);
   CU(cudaGetLastError());
@@ -436,7 +459,7 @@ int convert_host_impl(myyuvb_ctx* c, const uint8_t* px, uint32_t pixel_bytes, ui
   int rc;
   if ((rc = c->d_in.reserve(in_bytes))) return rc;
   if ((rc = c->d_out.reserve(out_bytes))) return rc;
-  if ((rc = staged_upload(c, c->d_in.p, px, in_bytes, c->stream))) return rc;
+  if ((rc = copy_async(c->d_in.p, px, in_bytes, cudaMemcpyHostToDevice, c->stream))) return rc;
   if ((rc = convert_dev_impl(c, c->d_in.as<uint8_t>(), pixel_bytes, w, h, bottom_up, 1, c->d_out.as<uint8_t>()))) return rc;
   if ((rc = staged_download(c, iyuv_out, c->d_out.p, out_bytes, c->stream))) return rc;
   CU(cudaStreamSynchronize(c->stream));
@@ -552,14 +575,66 @@ int myyuvb_bgr24_to_iyuv(myyuvb_ctx* c, const uint8_t* bgr, uint32_t w, uint32_t
   return convert_host_impl(c, bgr, 3, w, h, bottom_up, iyuv_out);
 }
 
+// One image, two steps: the payload stays in the context's device memory until the caller, who now knows its size, hands
+// over a buffer of exactly that size (YUV::data must be new uint8_t[data_size], myyuv_yuv.cpp:243-246).  The device-side
+// output buffer starts at half the raw image -- several times what natural content needs at any quality below ~95 -- and
+// only a capacity overflow makes the call repeat with the worst-case bound (255 bytes per block), so a first call does
+// not allocate 4x the image size three times over (output slot, parking area, host bound buffer).
+int myyuvb_dct_compress_begin(myyuvb_ctx* c, const uint8_t* iyuv, uint32_t w, uint32_t h, const uint8_t quality[3], uint32_t* out_size) {
+  if (!c || !iyuv || !quality || !out_size) return fail(MYYUVB_ERR_ARG, "null argument");
+  int rc;
+  if ((rc = check_quality(quality))) return rc;
+  if ((rc = check_dims(w, h))) return rc;
+  CU(cudaSetDevice(c->device));
+  c->pending_payload = 0;
+  const uint64_t frame_bytes = (uint64_t)w * h * 3 / 2;
+  const uint64_t bound = myyuvb_compress_bound(w, h);
+  if ((rc = c->d_in.reserve(frame_bytes))) return rc;
+  if ((rc = c->d_offsets.reserve(16))) return rc;
+  if ((rc = c->h_small.reserve(256 + 16))) return rc;
+  volatile uint64_t* h_off = reinterpret_cast<uint64_t*>(c->h_small.as<uint8_t>() + 256);
+  uint64_t* h_off_dev = nullptr;
+  CU(cudaHostGetDevicePointer(reinterpret_cast<void**>(&h_off_dev), const_cast<uint64_t*>(h_off), 0));
+  if ((rc = copy_async(c->d_in.p, iyuv, (size_t)frame_bytes, cudaMemcpyHostToDevice, c->stream))) return rc;
+  uint64_t cap = std::min<uint64_t>(bound, std::max<uint64_t>(c->d_out.cap, frame_bytes / 2 + 4096));
+  for (;;) {
+    if ((rc = c->d_out.reserve(cap))) return rc;
+    if ((rc = compress_dev_impl(c, c->d_in.as<uint8_t>(), w, h, quality, 1, c->d_out.as<uint8_t>(), cap, c->d_offsets.as<uint64_t>(), nullptr)))
+      return rc;
+    launch_publish_words(reinterpret_cast<uint32_t*>(h_off_dev), c->d_offsets.as<uint32_t>(), 4, c->stream);
+    rc = read_flags(c);  // synchronises
+    if (rc == MYYUVB_ERR_CAPACITY && cap < bound) {
+      cap = bound;
+      continue;
+    }
+    if (rc) return rc;
+    break;
+  }
+  const uint64_t size = h_off[1] - h_off[0];
+  if (size > 0xffffffffull) return fail(MYYUVB_ERR_TOO_LARGE, "Error. image does not fit the format's uint32 sizes");
+  c->pending_payload = size;
+  *out_size = (uint32_t)size;
+  return MYYUVB_OK;
+}
+
+int myyuvb_dct_compress_fetch(myyuvb_ctx* c, uint8_t* out, uint64_t out_capacity) {
+  if (!c || !out) return fail(MYYUVB_ERR_ARG, "null argument");
+  if (c->pending_payload == 0) return fail(MYYUVB_ERR_ARG, "myyuvb_dct_compress_fetch: no payload pending (call myyuvb_dct_compress_begin first)");
+  if (out_capacity < c->pending_payload) return fail(MYYUVB_ERR_CAPACITY, "Error. output buffer is too small for the compressed data");
+  CU(cudaSetDevice(c->device));
+  int rc;
+  if ((rc = staged_download(c, out, c->d_out.p, (size_t)c->pending_payload, c->stream))) return rc;
+  CU(cudaStreamSynchronize(c->stream));
+  c->pending_payload = 0;
+  return MYYUVB_OK;
+}
+
 int myyuvb_dct_compress(myyuvb_ctx* c, const uint8_t* iyuv, uint32_t w, uint32_t h, const uint8_t quality[3], uint8_t* out,
                         uint64_t out_capacity, uint32_t* out_size) {
   if (!c || !iyuv || !quality || !out || !out_size) return fail(MYYUVB_ERR_ARG, "null argument");
-  uint64_t offsets[2];
-  const int rc = myyuvb_dct_compress_batch_host(c, iyuv, w, h, quality, 1, out, out_capacity, offsets);
-  if (rc) return rc;
-  *out_size = (uint32_t)(offsets[1] - offsets[0]);
-  return MYYUVB_OK;
+  int rc;
+  if ((rc = myyuvb_dct_compress_begin(c, iyuv, w, h, quality, out_size))) return rc;
+  return myyuvb_dct_compress_fetch(c, out, out_capacity);
 }
 
 int myyuvb_dct_decompress(myyuvb_ctx* c, const uint8_t* payload, uint32_t payload_size, uint32_t w, uint32_t h,
@@ -579,8 +654,8 @@ int myyuvb_dct_decompress(myyuvb_ctx* c, const uint8_t* payload, uint32_t payloa
 // host-pointer batch entry points: frames are processed in chunks; the H2D copy of chunk i+1 and the D2H
 // copy of chunk i-1 run on the copy stream while chunk i is coded on the compute stream.
 // ------------------------------------------------------------------------------------------------
-int myyuvb_dct_compress_batch_host(myyuvb_ctx* c, const uint8_t* iyuv, uint32_t w, uint32_t h, const uint8_t quality[3],
-                                   uint32_t n_frames, uint8_t* out, uint64_t out_capacity, uint64_t* offsets) {
+static int compress_batch_host_impl(myyuvb_ctx* c, const uint8_t* iyuv, uint32_t w, uint32_t h, const uint8_t quality[3],
+                                    uint32_t n_frames, uint8_t* out, uint64_t out_capacity, uint64_t* offsets) {
   if (!c || !iyuv || !quality || !out || !offsets || n_frames == 0) return fail(MYYUVB_ERR_ARG, "null argument");
   int rc;
   if ((rc = check_quality(quality))) return rc;
@@ -609,7 +684,7 @@ int myyuvb_dct_compress_batch_host(myyuvb_ctx* c, const uint8_t* iyuv, uint32_t 
     const uint8_t* src = iyuv + (uint64_t)f0 * frame_bytes;
     uint8_t* dst = c->d_in.as<uint8_t>() + (uint64_t)slot * per * frame_bytes;
     int urc;
-    if ((urc = staged_upload(c, dst, src, (size_t)nf * frame_bytes, c->copy_stream))) return urc;
+    if ((urc = copy_async(dst, src, (size_t)nf * frame_bytes, cudaMemcpyHostToDevice, c->copy_stream))) return urc;
     CU(cudaEventRecord(c->ev[slot], c->copy_stream));
     return MYYUVB_OK;
   };
@@ -633,12 +708,8 @@ int myyuvb_dct_compress_batch_host(myyuvb_ctx* c, const uint8_t* iyuv, uint32_t 
     CU(cudaEventSynchronize(c->ev[2 + slot]));
     const volatile uint64_t* ho = h_off + (uint64_t)slot * (per + 1);
     const uint64_t first = ho[0], bytes = ho[nf] - first;
-    if (written + bytes > out_capacity) {
-      cudaStreamSynchronize(c->copy_stream);
-      cudaStreamSynchronize(dl);
-      read_flags(c);
+    if (written + bytes > out_capacity)
       return fail(MYYUVB_ERR_CAPACITY, "Error. output buffer is too small for the compressed data");
-    }
     for (uint32_t i = 0; i <= nf; i++) offsets[f0 + i] = written + (ho[i] - first);
     // the next chunk's kernels use the other output slot
     if ((rc = small_download(c, out + written, d_dst + first, (size_t)bytes, dl))) return rc;
@@ -649,8 +720,8 @@ int myyuvb_dct_compress_batch_host(myyuvb_ctx* c, const uint8_t* iyuv, uint32_t 
   return read_flags(c);
 }
 
-int myyuvb_dct_decompress_batch_host(myyuvb_ctx* c, const uint8_t* payloads, const uint64_t* offsets, uint32_t w, uint32_t h,
-                                     const uint8_t quality[3], uint32_t n_frames, uint8_t* iyuv_out) {
+static int decompress_batch_host_impl(myyuvb_ctx* c, const uint8_t* payloads, const uint64_t* offsets, uint32_t w, uint32_t h,
+                                      const uint8_t quality[3], uint32_t n_frames, uint8_t* iyuv_out) {
   if (!c || !payloads || !offsets || !quality || !iyuv_out || n_frames == 0) return fail(MYYUVB_ERR_ARG, "null argument");
   int rc;
   if ((rc = check_quality(quality))) return rc;
@@ -715,6 +786,35 @@ int myyuvb_dct_decompress_batch_host(myyuvb_ctx* c, const uint8_t* payloads, con
   }
   CU(cudaStreamSynchronize(c->d2h_stream));
   return read_flags(c);
+}
+
+// Every way out of the pipelined calls that is not success leaves copies in flight on three streams that read or write
+// the caller's buffers, and possibly sticky device error flags: wait for the streams and clear the flags, so that the
+// caller may free its buffers and the next call on the context starts clean.  The first error's code and text are kept.
+static int drain_after_error(myyuvb_ctx* c, int rc) {
+  if (!c || !c->stream) return rc;
+  const std::string msg = g_err;
+  cudaStreamSynchronize(c->copy_stream);
+  cudaStreamSynchronize(c->stream);
+  cudaStreamSynchronize(c->d2h_stream);
+  if (c->d_counters.p) {
+    cudaMemsetAsync(c->d_counters.as<uint32_t>() + 1, 0, 4, c->stream);
+    cudaStreamSynchronize(c->stream);
+  }
+  cudaGetLastError();
+  return fail(rc, msg);
+}
+
+int myyuvb_dct_compress_batch_host(myyuvb_ctx* c, const uint8_t* iyuv, uint32_t w, uint32_t h, const uint8_t quality[3],
+                                   uint32_t n_frames, uint8_t* out, uint64_t out_capacity, uint64_t* offsets) {
+  const int rc = compress_batch_host_impl(c, iyuv, w, h, quality, n_frames, out, out_capacity, offsets);
+  return rc ? drain_after_error(c, rc) : rc;
+}
+
+int myyuvb_dct_decompress_batch_host(myyuvb_ctx* c, const uint8_t* payloads, const uint64_t* offsets, uint32_t w, uint32_t h,
+                                     const uint8_t quality[3], uint32_t n_frames, uint8_t* iyuv_out) {
+  const int rc = decompress_batch_host_impl(c, payloads, offsets, w, h, quality, n_frames, iyuv_out);
+  return rc ? drain_after_error(c, rc) : rc;
 }
 
 }  // extern "C"

@@ -31,6 +31,46 @@ namespace myyuvb {
 
 thread_local uint64_t g_launches = 0;
 
+// Optional per-phase clock counters of the two codec kernels (build.py builds lib/libmyyuvb200_clk.so with
+// -DMYYUVB_PHASE_CLOCKS; profiles/phase_clocks.py reads them).  Lane 0 of every warp adds the clock64() distance between
+// consecutive marks to a shared-memory slot of its warp; the sums go to g_phase_clk when the CTA retires.  The product
+// library is built without it.
+#ifdef MYYUVB_PHASE_CLOCKS
+constexpr int kPhases = 12;
+__device__ unsigned long long g_phase_clk[2][kPhases];
+#define PH_BEGIN() long long ph_t_ = clock64()
+#define PH(k)                                                     \
+  {                                                               \
+    const long long ph_n_ = clock64();                            \
+    if ((threadIdx.x & 31) == 0) sm.clk[threadIdx.x >> 5][k] += (unsigned long long)(ph_n_ - ph_t_); \
+    ph_t_ = ph_n_;                                                \
+  }
+#define PH_INIT()                                                 \
+  if (threadIdx.x < 4 * kPhases) (&sm.clk[0][0])[threadIdx.x] = 0; \
+  __syncthreads()
+#define PH_FLUSH(which)                                           \
+  __syncthreads();                                                \
+  if (threadIdx.x < kPhases) atomicAdd(&g_phase_clk[which][threadIdx.x], sm.clk[0][threadIdx.x] + sm.clk[1][threadIdx.x] + sm.clk[2][threadIdx.x] + sm.clk[3][threadIdx.x])
+#define PH_MEMBER unsigned long long clk[4][kPhases];
+void read_phase_clocks(unsigned long long* out, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, g_phase_clk, sizeof(unsigned long long) * 2 * kPhases);
+  if (reset) {
+    unsigned long long z[2 * kPhases] = {};
+    cudaMemcpyToSymbol(g_phase_clk, z, sizeof(z));
+  }
+}
+#else
+#define PH_BEGIN()
+#define PH(k)
+#define PH_INIT()
+#define PH_FLUSH(which)
+#define PH_MEMBER
+void read_phase_clocks(unsigned long long* out, int) {
+  for (int i = 0; i < 24; i++) out[i] = 0;
+}
+#endif
+
 // ---------------------------------------------------------------------------------------------------
 // packed FP32x2 helpers
 // ---------------------------------------------------------------------------------------------------
@@ -507,6 +547,7 @@ struct EncSmem {
   uint8_t msg_len[kTileBlocks];
   uint8_t csize[kTileBlocks];
   uint8_t perm[kTileBlocks];
+  PH_MEMBER
 };
 static_assert(sizeof(EncSmem) <= 37 * 1024 - 512, "EncSmem must allow 6 CTAs per SM");
 // Thread t codes the block of rank t in message-length order, so that the lanes of a warp get messages of similar length
@@ -625,6 +666,8 @@ __global__ void __launch_bounds__(kCtaThreads, 6)
   F8Scratch f8{reinterpret_cast<uint32_t*>(wbase) + lane, wbase + 2048, lane};
   ZShared z{&sm.zz[0][tid]};
   uint8_t* const overflow = P.ws.overflow + (uint64_t)blockIdx.x * (kEncTile * 256u);
+  PH_INIT();
+  PH_BEGIN();
 
   while (true) {
     if (tid == 0) {
@@ -635,6 +678,7 @@ __global__ void __launch_bounds__(kCtaThreads, 6)
     __syncthreads();
     const uint32_t tile = sm.tile;
     if (tile >= P.total_tiles) break;
+    PH(0);  // ticket
     const TileCoord tc = tile_coord(g, tile);
     const int plane = (int)tc.plane;
     const uint32_t pw = g.pw[plane], bw = g.bw[plane];
@@ -668,6 +712,7 @@ __global__ void __launch_bounds__(kCtaThreads, 6)
         }
         L = fdct_quant_block(raw, qt, plane, P.one, z.col);
       }
+      PH(1);  // load + DCT + quantise
       // ---- phase B: entropy-code one block; warp lockstep ----
       if (!live) L = 0;
       uint32_t mine = (uint32_t)tid;  // the block (of this pass) this thread codes
@@ -698,6 +743,7 @@ __global__ void __launch_bounds__(kCtaThreads, 6)
         mine = sm.perm[tid];
         L = sm.msg_len[mine];
       }
+      PH(2);  // block sort
       const uint32_t mblk = pass * kTileBlocks + mine;
       const bool mlive = mblk < tc.nblk;
       ZShared zm{&sm.zz[0][mine]};
@@ -708,6 +754,7 @@ __global__ void __launch_bounds__(kCtaThreads, 6)
       }
       __syncwarp();
       int nsym = huff_hist(zm, L, mlive, f8, WarpLockstep{});
+      PH(3);  // histogram
       // Blocks with more than 15 distinct symbols (0.5 % of the luma blocks of natural images at q 50, every block of
       // noise at q 100) do not fit the fast path.  Coding one of them in place would send the whole warp through the
       // general code for it, so they are queued -- coefficient words, block index, message length -- and coded 32 at a
@@ -737,6 +784,7 @@ __global__ void __launch_bounds__(kCtaThreads, 6)
           if (qbase + lane < P.ws.heavy_cap && lane < h) P.ws.heavy_rec[qbase + lane] = make_uint4(0xffffffffu, 0u, 0u, 0u);
         }
       }
+      PH(4);  // deferral queue
       FastPlan pl8{};
       HuffPlan pl{};
       uint8_t lbytes[BigScratch::kBytes];
@@ -754,6 +802,7 @@ __global__ void __launch_bounds__(kCtaThreads, 6)
         __syncwarp();
         size = mlive ? (uint32_t)pl.size() : 0u;
       }
+      PH(5);  // plan: map order, heap, merges, table size
       // chunk sizes go to a linear side array; finalize_frames_kernel moves them behind the plane headers,
       // whose position depends on the (data dependent) size of the previous planes
       if (mlive) P.ws.chunk_sizes[gblk0 + mblk] = (uint8_t)size;
@@ -797,6 +846,7 @@ __global__ void __launch_bounds__(kCtaThreads, 6)
         // only place_tiles_kernel's path for tiles with queued blocks reads the slot array
         if (sm.heavy && mlive) P.ws.block_slot[gblk0 + mblk] = hslot;
       }
+      PH(6);  // size scan, reservation
       const u64 pos = sm.base;
       const bool room = pos + pass_total <= P.ws.scratch_cap;  // CTA uniform
       {
@@ -813,8 +863,10 @@ __global__ void __launch_bounds__(kCtaThreads, 6)
           huff_emit(zm, plf, bs, dst, WarpLockstep{});
         }
       }
+      PH(7);  // emit: sort, canonical codes, table, stream
       carried += pass_total;
       __syncthreads();  // the staged part of the tile is complete
+      PH(8);  // barrier behind the emit
       if (!room) {
         if (tid == 0) atomicOr(&P.ws.counters[1], kFlagCapacity);
       } else {
@@ -823,7 +875,9 @@ __global__ void __launch_bounds__(kCtaThreads, 6)
       }
     }
     __syncthreads();  // shared memory is reused by the next tile
+    PH(9);  // copy out + barrier
   }
+  PH_FLUSH(0);
 }
 
 // Pass 1b: the queued blocks, 32 per warp, through the general code in lockstep.  Writes each chunk to its 256-byte slot,
@@ -1164,6 +1218,7 @@ struct DecSmem {
   uint16_t boff[kTileBlocks];
   uint8_t bsize[kTileBlocks];
   uint8_t perm[kTileBlocks];
+  PH_MEMBER
 };
 static_assert(sizeof(DecSmem) <= 36 * 1024, "DecSmem must allow 6 CTAs per SM");
 // Thread t decodes the block of rank t in chunk-size order (4-byte bins): the lanes of a warp get messages of similar
@@ -1360,6 +1415,8 @@ __global__ void __launch_bounds__(kCtaThreads, 6)
   const FrameGeom& g = P.g;
   int q_plane = -1;
   int16_t* const col = &sm.coef[0][tid];
+  PH_INIT();
+  PH_BEGIN();
 
   while (true) {
     __syncthreads();  // previous tile done with shared memory (and zigzag table visible)
@@ -1367,6 +1424,7 @@ __global__ void __launch_bounds__(kCtaThreads, 6)
     __syncthreads();
     const uint32_t tile = sm.tile;
     if (tile >= P.total_tiles) break;
+    PH(0);  // ticket + barrier behind the previous tile's stores
     const TileCoord tc = tile_coord(g, tile);
     const int plane = (int)tc.plane;
     const PlaneDesc d = reinterpret_cast<const PlaneDesc*>(P.ws.plane_desc)[(uint64_t)tc.frame * 3 + plane];
@@ -1414,6 +1472,7 @@ __global__ void __launch_bounds__(kCtaThreads, 6)
       if (tid < 64) sm.hist[tid] = 0;
     }
     __syncthreads();
+    PH(1);  // staging loads, size scan, zero fill
 
     // ---- phase 1: canonical Huffman decode + dequantise into the thread's shared-memory column (warp lockstep) ----
     uint32_t blk = tid, boff = off, bsize = size;  // the block this thread decodes and transforms
@@ -1439,6 +1498,7 @@ __global__ void __launch_bounds__(kCtaThreads, 6)
       boff = sm.boff[blk];
       bsize = sm.bsize[blk];
     }
+    PH(2);  // block sort
     const bool mine = blk < tc.nblk;
     int nsym = 0;  // decoded zigzag positions: the non-zero coefficients lie in positions [0, nsym)
     {
@@ -1457,6 +1517,7 @@ __global__ void __launch_bounds__(kCtaThreads, 6)
       if (mine && (err || size == 0)) atomicOr(&P.ws.counters[1], kFlagHuffman);  // a chunk is at least 7 bytes
     }
     __syncwarp();
+    PH(3);  // entropy decoder
     // ---- phase 2: inverse DCT, round, clamp, store ----
     {
       uint32_t outw[16];
@@ -1488,7 +1549,9 @@ __global__ void __launch_bounds__(kCtaThreads, 6)
         for (int r = 0; r < 8; r++) *reinterpret_cast<uint2*>(p + (uint64_t)r * pw) = make_uint2(outw[2 * r], outw[2 * r + 1]);
       }
     }
+    PH(4);  // IDCT + stores
   }
+  PH_FLUSH(1);
 }
 
 // ===================================================================================================

@@ -99,4 +99,7 @@ void launch_publish_words(uint32_t* h_dst_devptr, const uint32_t* d_src, uint32_
 
 extern thread_local uint64_t g_launches;
 
+// per-phase clock sums of the codec kernels, [2][12] (encoder, decoder); zeros unless built with -DMYYUVB_PHASE_CLOCKS
+void read_phase_clocks(unsigned long long* out, int reset);
+
 }  // namespace myyuvb

@@ -71,13 +71,11 @@ YUV bmp_to_iyuv(const BMP& bmp) {
 YUV compress_dct_iyuv(const YUV& src, const void* params, uint32_t params_size) {
   if (params_size != 3) throw std::runtime_error("Error compression: incorrect parameters count. 3 parameters required");
   const uint8_t* q = static_cast<const uint8_t*>(params);
-  const uint64_t bound = myyuvb_compress_bound(src.header.width, src.header.height);
-  std::unique_ptr<uint8_t[]> buf(new uint8_t[bound]);
+  // two steps, so that YUV::data is allocated once with its final size (the reference's dump(), DCT.cpp:160-173, allocates
+  // totalSize() bytes): the payload waits in device memory while its size comes back
+  CtxLock ctx;
   uint32_t size = 0;
-  {
-    CtxLock ctx;
-    check(myyuvb_dct_compress(ctx.get(), src.data, src.header.width, src.header.height, q, buf.get(), bound, &size));
-  }
+  check(myyuvb_dct_compress_begin(ctx.get(), src.data, src.header.width, src.header.height, q, &size));
   YUV out;
   out.header = src.header;  // DCT.cpp:390-394
   out.header.compression = YUV::Compressions::DCT;
@@ -87,7 +85,7 @@ YUV compress_dct_iyuv(const YUV& src, const void* params, uint32_t params_size) 
   out.header.data_size = size;
   out.compression_params = new uint8_t[3]{q[0], q[1], q[2]};
   out.data = new uint8_t[size];
-  std::memcpy(out.data, buf.get(), size);
+  check(myyuvb_dct_compress_fetch(ctx.get(), out.data, size));
   return out;
 }
 

@@ -299,9 +299,16 @@ def _bmp_to_iyuv(bmp: BMP) -> YUV:  # replaces myyuv_yuv.cpp:89-127
     if bmp.header.bit_count not in (24, 32):
         raise RuntimeError("Error. only 24-bit and 32-bit BMP are supported")
     w, h = bmp.trueWidth(), bmp.trueHeight()
+    pixels = bmp.data
     if bmp.header.width > 0 and bmp.header.height > 0:
         bottom_up = True
     elif bmp.header.width > 0 and bmp.header.height < 0:
+        bottom_up = False
+    elif bmp.header.width < 0 and bmp.header.height > 0:
+        # colorData() reverses the whole pixel sequence for this orientation (myyuv_bmp.cpp:89-94); rare, so the
+        # reordering is done on the host like the C++ drop-in does (yuv_host.cpp) and the rows are then top-down
+        pb = bmp.header.bit_count // 8
+        pixels = np.ascontiguousarray(np.asarray(bmp.data, np.uint8)[: w * h * pb].reshape(-1, pb)[::-1]).reshape(-1)
         bottom_up = False
     else:
         raise RuntimeError("Unaccounted width and height sign")  # myyuv_bmp.cpp:100
@@ -312,7 +319,7 @@ def _bmp_to_iyuv(bmp: BMP) -> YUV:  # replaces myyuv_yuv.cpp:89-127
     res.header.data_pos = 64
     try:
         ctx = capi.default_context()
-        res.data = (ctx.xrgb_to_iyuv if bmp.header.bit_count == 32 else ctx.bgr24_to_iyuv)(bmp.data, w, h, bottom_up)
+        res.data = (ctx.xrgb_to_iyuv if bmp.header.bit_count == 32 else ctx.bgr24_to_iyuv)(pixels, w, h, bottom_up)
     except capi.MyyuvError as e:
         raise RuntimeError(str(e)) from e
     return res
