@@ -48,6 +48,7 @@ def main():
         d_off = torch.zeros(n + 1, dtype=torch.int64, device=dev)
         d_back = torch.empty_like(d_in)
         qq = (q,) * 3
+        torch.cuda.synchronize()  # the tensors above were filled on torch's stream, the library runs on its own
         for _ in range(2):
             ctx.compress_batch_dev(d_in, W, H, qq, n, d_out, cap, d_off)
             ctx.decompress_batch_dev(d_out, d_off, W, H, qq, n, d_back)
