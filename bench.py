@@ -59,6 +59,9 @@ def parse_args():
     ap.add_argument("--no-sweep", action="store_true", help="skip the natural-content and quality-sweep legs")
     ap.add_argument("--sweep-frames", type=int, default=16, help="4K frames per GPU in the natural-content / quality-sweep legs")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--workload", default="batch4k", choices=["batch4k", "shard8k"],
+                    help="batch4k: the headline metric (frames sharded over the GPUs); shard8k: ONE 7680x4320 image, macroblock rows "
+                         "sharded over the GPUs (BASELINE configs[3])")
     return ap.parse_args()
 
 
@@ -671,6 +674,221 @@ def b200_main(args):
     return 0
 
 
+# ------------------------------------------------------------------------------------------------
+# --workload shard8k: one 7680x4320 image, macroblock rows sharded over the GPUs (BASELINE configs[3])
+# ------------------------------------------------------------------------------------------------
+def shard_main(args):
+    """One step = compress ONE 8K frame: every rank codes its band of macroblock rows (device resident) and stores it
+    straight into rank 0's payload buffer over NVLink; rank 0's stream continues when all bands are in.  No host round
+    trip and no NCCL call inside a step: the ranks meet on the device (shard_exchange_kernel / shard_done_kernel)."""
+    import hashlib
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    SW, SH, q = 7680, 4320, (50, 50, 50)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the b200 arm has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    pkg = importlib.import_module("yuv-manipulations-2_b200")
+    synth = importlib.import_module("yuv-manipulations-2_b200.synth")
+    sharding = importlib.import_module("yuv-manipulations-2_b200.sharding")
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    ctx = pkg.Context(local, stream.cuda_stream)
+    base = natural_base()
+    content = "tiled-real" if base is not None else "noise-grad"
+    frame = (synth.tiled_real_iyuv(base[0], base[1], base[2], SW, SH, 1, 0)[0] if base is not None else synth.iyuv_frames_numpy(SW, SH, 1, 1)[0])
+    group = sharding.ShardGroup.distributed(ctx, dist, SW, SH) if world > 1 else sharding.ShardGroup.local([ctx], SW, SH)[0]
+    y0, y1 = group.band
+    h_band = pkg.capi.PinnedBuffer(max((y1 - y0) * SW * 3 // 2, 16))
+    h_band.array[: (y1 - y0) * SW * 3 // 2] = sharding.slice_iyuv(frame, SW, SH, y0, y1)
+    d_band = torch.from_numpy(h_band.array.copy()).to(dev)
+    d_back = torch.empty_like(d_band)
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def finish():
+        return group.result() if rank == group.root else (ctx.batch_status() or 0)
+
+    # warm-up (also sizes every rank's workspace) and the parity gate: rank 0's assembled payload against the reference's hash
+    for _ in range(max(args.warmup, 3)):
+        group.compress(d_band, q)
+    size = finish()
+    barrier()
+    parity_checked, parity_how = False, None
+    if rank == 0:
+        import ctypes
+
+        rt = ctypes.CDLL("libcudart.so.12")
+        rt.cudaMemcpy.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]
+        got = np.empty(size, np.uint8)
+        assert rt.cudaMemcpy(got.ctypes.data, ctypes.c_void_p(group.root_out), size, 2) == 0
+        try:
+            case = next(c for c in json.loads((ROOT / "tests" / "golden" / "golden.json").read_text())["shard8k"] if c["content"] == content)
+            sha = hashlib.sha256(got.tobytes()).hexdigest()
+            if size != case["payload_size"] or sha != case["payload_sha256"]:
+                raise SystemExit(f"bench.py: PARITY FAILURE: sharded payload {size} B sha {sha[:16]}, the reference gives "
+                                 f"{case['payload_size']} B {case['payload_sha256'][:16]}")
+            parity_checked = True
+            parity_how = "sha256 of the payload assembled from all ranks' bands == the unmodified reference's single-image payload (tests/golden/golden.json shard8k)"
+        except (OSError, StopIteration, KeyError) as e:
+            parity_how = f"golden vector unavailable: {e!r}"
+    szt = torch.tensor([size], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.broadcast(szt, 0)
+    size = int(szt.item())
+
+    # ---- timed: K images back to back, CUDA events on every rank's stream, max over ranks ----
+    def timed(fn, steps):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        barrier()
+        ev[0].record(stream)
+        for _ in range(steps):
+            fn()
+        ev[1].record(stream)
+        finish()
+        barrier()
+        t = torch.tensor([ev[0].elapsed_time(ev[1])], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / steps
+
+    sampler = ClockSampler(local, None) if rank == 0 else None
+    launches0 = pkg.capi.launch_count()
+    t0 = time.perf_counter()
+    comp_ms = timed(lambda: group.compress(d_band, q), args.steps)
+    t1 = time.perf_counter()
+    launches = pkg.capi.launch_count() - launches0
+    clocks = sampler.stop(t0, t1) if sampler else None
+    dec_ms = timed(lambda: group.decompress(size, q, d_back), args.steps)
+    # what the band costs without any exchange: the ordinary batch call on the same band, same GPU
+    bh = y1 - y0
+    code_ms = None
+    if bh:
+        cap = pkg.capi.compress_bound(SW, bh)
+        t_out = torch.empty(cap, dtype=torch.uint8, device=dev)
+        t_off = torch.zeros(2, dtype=torch.int64, device=dev)
+        torch.cuda.synchronize()
+        xs = []
+        for it in range(6):
+            ctx.compress_batch_dev(d_band, SW, bh, q, 1, t_out, cap, t_off)
+            if it:
+                xs.append(ctx.last_kernel_ms())
+        ctx.batch_status()
+        code_ms = statistics.median(xs)
+    ct = torch.tensor([code_ms or 0.0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ct, op=dist.ReduceOp.MAX)
+    code_ms = float(ct.item())
+
+    # ---- end to end: every rank's band starts in pinned host memory, the assembled payload ends in rank 0's host memory ----
+    h_out = pkg.capi.PinnedBuffer(size + 16) if rank == 0 else None
+    d_stage = torch.empty_like(d_band)
+    n_e2e = max(args.steps, 8)
+
+    def e2e_step():
+        d_stage.copy_(torch.from_numpy(h_band.array), non_blocking=True)  # H2D of this rank's band, same stream
+        group.compress(d_stage, q)
+        n = finish()
+        if rank == 0:
+            import ctypes
+
+            assert rt.cudaMemcpy(h_out.array.ctypes.data, ctypes.c_void_p(group.root_out), n, 2) == 0
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    te0 = time.perf_counter()
+    for _ in range(n_e2e):
+        e2e_step()
+    barrier()
+    te = torch.tensor([time.perf_counter() - te0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_ms = 1e3 * float(te.item()) / n_e2e
+    if rank == 0 and parity_checked:
+        assert hashlib.sha256(h_out.array[:size].tobytes()).hexdigest() == case["payload_sha256"], "e2e payload differs"
+
+    if rank != 0:
+        group.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:  # noqa: BLE001
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    frame_bytes = SW * SH * 3 // 2
+    alg = frame_bytes + size
+    exch_ms = max(comp_ms - code_ms, 0.0)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            import oracle
+
+            ref = oracle.Reference("omp")
+            ts = []
+            for _ in range(3):
+                tc0 = time.perf_counter()
+                ref.compress(frame, SW, SH, q)
+                ts.append(time.perf_counter() - tc0)
+            cpu = {"value": round(SW * SH / min(ts) / 1e6, 2), "unit": UNIT, "cores": ref.threads, "kind": "reference",
+                   "sample": "YUV::compress of the same 7680x4320 frame, best of 3, OpenMP build, default nesting"}
+        except Exception as e:  # noqa: BLE001
+            log(f"[cpu_baseline] {e!r}")
+    line = {
+        "metric": "8K single-image DCT-50 compress, macroblock rows sharded over the GPUs", "value": round(SW * SH / (comp_ms / 1e3) / 1e6, 1),
+        "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(comp_ms, 4),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32 DCT (unfused, packed f32x2) + u8/int16 entropy coding", "data": "synthetic",
+        "config": {"workload": f"ONE {SW}x{SH} IYUV frame ({content}), DCT quality 50/50/50, {SH // 16} macroblock rows split "
+                               f"{[ (group.rows[i + 1] - group.rows[i]) // 16 for i in range(world)]} over {world} GPU(s); BASELINE configs[3]",
+                   "width": SW, "height": SH, "quality": 50, "frame_content": content,
+                   "parallelism": f"macroblock rows sharded over {world} GPU(s); exchange = 12 bytes per rank pair by peer stores, bands stored "
+                                  "straight into rank 0's buffer over NVLink (no NCCL call in a step)",
+                   "l2_policy": "one 49.8 MB frame per step: fits L2 when it is re-read (the frame is resident, as for the batch metric)"},
+        "clocks": clocks, "gpu_launches": int(launches), "parity_checked": parity_checked, "parity_check": parity_how,
+        "shard": {"compress_us_per_image": round(1e3 * comp_ms, 1), "decompress_us_per_image": round(1e3 * dec_ms, 1),
+                  "code_us_slowest_band_alone": round(1e3 * code_ms, 1), "exchange_plus_assemble_us": round(1e3 * exch_ms, 1),
+                  "exchange_share": round(exch_ms / comp_ms, 3) if comp_ms else None,
+                  "nvlink_bytes_per_image": int(size * (world - 1) / world) if world > 1 else 0,
+                  "payload_bytes": size,
+                  "how": "compress/decompress: K calls back to back on every rank, CUDA events, max over ranks; code: the ordinary batch call "
+                         "on the largest band alone (library events, median of 5); exchange+assemble = the difference"},
+        "roofline": {"bound": "hbm", "kernel": "dct_compress_kernel (band)", "achieved": round(alg / (comp_ms / 1e3) / 1e9, 1),
+                     "peak": hbm_peak * world, "unit": "GB/s", "frac": round(alg / (comp_ms / 1e3) / 1e9 / (hbm_peak * world), 4), "traffic": None,
+                     "algorithmic_bytes_per_launch": alg, "launch_ms": round(comp_ms, 4),
+                     "binding_limit": "latency of one small image per step: kernel launch chain + instruction issue, not HBM"},
+        "cpu_baseline": cpu,
+        "e2e": {"value": round(SW * SH / (e2e_ms / 1e3) / 1e6, 1), "unit": UNIT, "ms_per_image": round(e2e_ms, 3),
+                "h2d_bytes_per_step": frame_bytes, "d2h_bytes_per_step": size,
+                "api": "pinned host band -> H2D -> myyuvb_dct_compress_shard_dev on every rank -> myyuvb_shard_result -> D2H of the assembled payload on rank 0"},
+    }
+    emit(line)
+    group.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 if __name__ == "__main__":
     a = parse_args()
-    sys.exit(reference_main(a) if a.impl == "reference" else b200_main(a))
+    if a.impl == "reference":
+        sys.exit(reference_main(a))
+    sys.exit(shard_main(a) if a.workload == "shard8k" else b200_main(a))

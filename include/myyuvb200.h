@@ -43,7 +43,8 @@ enum {
   MYYUVB_ERR_PLANE_SIZE = 8,    /* "DCTYUVPlane load bad size" (+ chunks_sizes_size / content_size variants) DCT.cpp:41-55 */
   MYYUVB_ERR_HUFFMAN = 9,       /* "Huffman bad code"                                 Huffman.cpp:121,130,139 */
   MYYUVB_ERR_EVEN = 10,         /* colour conversion needs even width and height      myyuv_yuv.cpp:98       */
-  MYYUVB_ERR_TOO_LARGE = 11     /* sizes do not fit the format's uint32 fields        myyuv_yuv.hpp:20-26    */
+  MYYUVB_ERR_TOO_LARGE = 11,    /* sizes do not fit the format's uint32 fields        myyuv_yuv.hpp:20-26    */
+  MYYUVB_ERR_SHARD_TIMEOUT = 12 /* sharded image: a rank of the group never arrived                          */
 };
 
 typedef struct myyuvb_ctx myyuvb_ctx; /* one device, one stream, reusable device/pinned scratch; not thread-safe
@@ -153,6 +154,39 @@ MYYUVB_API void myyuvb_host_free(void* p);
 
 /* number of kernels this library has launched on this thread's contexts since process start (bench.py's gpu_launches) */
 MYYUVB_API uint64_t myyuvb_launch_count(void);
+
+/* ---- one very large image sharded over the GPUs of one box (the reference has no counterpart:
+ * the property that makes it possible is that every 8x8 block is coded on its own and a plane's content is the blocks'
+ * chunks in raster order, DCT.cpp:297-322, layout DCT.cpp:16-33,160-173) ----
+ * One context per GPU, each in its own process or thread.  Rank q codes the luma rows [rows[q], rows[q+1]) (whole
+ * macroblock rows; myyuvb_shard_rows gives the balanced split, 270 rows of 8K over 8 ranks = 34 x 6 + 33 x 2).
+ * ctrl[q] is rank q's control block (myyuvb_shard_ctrl_bytes() of zeroed device memory) as mapped on THIS device;
+ * root_out / root_payload / root_iyuv are the root's buffers as mapped on this device.  Across processes the mappings come
+ * from the IPC helpers below.  All ranks of a group must make the same call with the same, increasing `epoch` (1, 2, ...):
+ * the calls are asynchronous on each context's stream and meet on the device -- content sizes are exchanged by peer
+ * stores, every band is stored straight into the root's buffer, the root's stream continues when all bands are in.
+ * myyuvb_shard_result (root) synchronises and returns the assembled size.  A rank that never arrives makes the others
+ * fail with MYYUVB_ERR_SHARD_TIMEOUT after 2 s instead of hanging. */
+MYYUVB_API uint64_t myyuvb_shard_ctrl_bytes(void);
+MYYUVB_API int myyuvb_shard_rows(uint32_t height, uint32_t world, uint32_t* rows /* [world + 1] */);
+/* d_iyuv: this rank's band as an IYUV image of height rows[rank+1]-rows[rank] (iyuv_is_full_frame == 0), or the whole
+ * width x height frame resident on this GPU, of which only the band's rows are read (!= 0). */
+MYYUVB_API int myyuvb_dct_compress_shard_dev(myyuvb_ctx* ctx, const uint8_t* d_iyuv, int iyuv_is_full_frame, uint32_t width,
+                                             uint32_t height, const uint8_t quality[3], uint32_t rank, uint32_t world,
+                                             uint32_t root, const uint32_t* rows, void* const* ctrl, uint8_t* root_out,
+                                             uint64_t out_capacity, uint32_t epoch);
+/* The band is decoded into d_band_out (an IYUV image of the band's height, local) and, when root_iyuv is not NULL, its
+ * three planes are copied into the root's width x height frame. */
+MYYUVB_API int myyuvb_dct_decompress_shard_dev(myyuvb_ctx* ctx, const uint8_t* root_payload, uint64_t payload_size,
+                                               uint32_t width, uint32_t height, const uint8_t quality[3], uint32_t rank,
+                                               uint32_t world, uint32_t root, const uint32_t* rows, void* const* ctrl,
+                                               uint8_t* d_band_out, uint8_t* root_iyuv, uint32_t epoch);
+MYYUVB_API int myyuvb_shard_result(myyuvb_ctx* ctx, const void* ctrl_local, uint64_t* total_size);
+/* device memory that other processes can map: cudaMalloc (zeroed) + cudaIpcGetMemHandle / cudaIpcOpenMemHandle */
+MYYUVB_API int myyuvb_ipc_alloc(myyuvb_ctx* ctx, uint64_t bytes, void** d_ptr, uint8_t handle_out[64]);
+MYYUVB_API int myyuvb_ipc_open(myyuvb_ctx* ctx, const uint8_t handle[64], void** d_ptr);
+MYYUVB_API int myyuvb_ipc_close(myyuvb_ctx* ctx, void* d_ptr);
+MYYUVB_API int myyuvb_ipc_free(myyuvb_ctx* ctx, void* d_ptr);
 
 /* Profiling aid: clock sums per phase of the two codec kernels, out24 = [2][12] (compress, decompress).  All zero in the
  * product library; the -DMYYUVB_PHASE_CLOCKS build (lib/libmyyuvb200_clk.so, profiles/phase_clocks.py) fills them. */

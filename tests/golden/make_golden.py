@@ -84,6 +84,15 @@ def main():
             c = ref.compress(f, 3840, 2160, q)
             out["tiled_real"].append({"w": 3840, "h": 2160, "q": list(q), "first": first, "input_sha256": sha(f), "payload_size": int(c.size),
                                       "payload_sha256": sha(c), "decoded_sha256": sha(ref.decompress(c, 3840, 2160, q))})
+        # BASELINE configs[3]: one 7680x4320 frame (the image the sharded path codes); also its synthetic twin
+        out["shard8k"] = []
+        for content, first in (("tiled-real", 0), ("noise-grad", 1)):
+            f = (synth.tiled_real_iyuv(g["data"], g["w"], g["h"], 7680, 4320, 1, first)[0] if content == "tiled-real"
+                 else synth.iyuv_frames_numpy(7680, 4320, 1, first)[0])
+            c = ref.compress(f, 7680, 4320, (50, 50, 50))
+            out["shard8k"].append({"w": 7680, "h": 4320, "q": [50, 50, 50], "content": content, "first": first, "input_sha256": sha(f),
+                                   "payload_size": int(c.size), "payload_sha256": sha(c),
+                                   "decoded_sha256": sha(ref.decompress(c, 7680, 4320, (50, 50, 50)))})
     # the reference's sample images
     if (O.GOLDEN_DIR / "chef-with-trumpet.bmp").exists():
         for name in ["chef-with-trumpet.bmp", "chef-with-trumpet.myyuv", "chef-with-trumpet-DCT-50.myyuv", "chef-with-trumpet-DCT-90.myyuv",

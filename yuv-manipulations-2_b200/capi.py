@@ -16,7 +16,7 @@ _u64p = C.POINTER(C.c_uint64)
 
 # error codes of include/myyuvb200.h
 OK, ERR_CUDA, ERR_ARG, ERR_QUALITY, ERR_WIDTH, ERR_HEIGHT, ERR_CAPACITY, ERR_DCTYUV_SIZE, ERR_PLANE_SIZE, ERR_HUFFMAN, \
-    ERR_EVEN, ERR_TOO_LARGE = range(12)
+    ERR_EVEN, ERR_TOO_LARGE, ERR_SHARD_TIMEOUT = range(13)
 
 EXPORTS = [
     "myyuvb_ctx_create", "myyuvb_ctx_destroy", "myyuvb_last_error", "myyuvb_sync", "myyuvb_stream",
@@ -26,6 +26,8 @@ EXPORTS = [
     "myyuvb_batch_status", "myyuvb_dct_compress_batch_host", "myyuvb_dct_decompress_batch_host",
     "myyuvb_host_alloc", "myyuvb_host_free", "myyuvb_launch_count", "myyuvb_last_kernel_ms",
     "myyuvb_dct_compress_begin", "myyuvb_dct_compress_fetch", "myyuvb_phase_clocks",
+    "myyuvb_shard_ctrl_bytes", "myyuvb_shard_rows", "myyuvb_dct_compress_shard_dev", "myyuvb_dct_decompress_shard_dev",
+    "myyuvb_shard_result", "myyuvb_ipc_alloc", "myyuvb_ipc_open", "myyuvb_ipc_close", "myyuvb_ipc_free",
 ]
 
 
@@ -92,6 +94,17 @@ def lib() -> C.CDLL:
     L.myyuvb_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     L.myyuvb_phase_clocks.argtypes = [C.c_void_p, C.c_int]
     L.myyuvb_phase_clocks.restype = None
+    L.myyuvb_shard_ctrl_bytes.restype = C.c_uint64
+    L.myyuvb_shard_rows.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]
+    L.myyuvb_dct_compress_shard_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, _u8p, C.c_uint32, C.c_uint32,
+                                                C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_void_p), C.c_void_p, C.c_uint64, C.c_uint32]
+    L.myyuvb_dct_decompress_shard_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, _u8p, C.c_uint32, C.c_uint32,
+                                                  C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_uint32]
+    L.myyuvb_shard_result.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
+    L.myyuvb_ipc_alloc.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p), C.c_void_p]
+    L.myyuvb_ipc_open.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+    L.myyuvb_ipc_close.argtypes = [C.c_void_p, C.c_void_p]
+    L.myyuvb_ipc_free.argtypes = [C.c_void_p, C.c_void_p]
     _lib = L
     return L
 
@@ -121,6 +134,17 @@ def phase_clocks(reset: bool = True) -> np.ndarray:
     out = np.zeros(24, np.uint64)
     lib().myyuvb_phase_clocks(out.ctypes.data, int(reset))
     return out.reshape(2, 12)
+
+
+def shard_rows(height: int, world: int):
+    """Balanced split of the height/16 macroblock rows over the ranks: luma row boundaries, world + 1 entries."""
+    rows = (C.c_uint32 * (world + 1))()
+    _check(lib().myyuvb_shard_rows(height, world, rows))
+    return list(rows)
+
+
+def shard_ctrl_bytes() -> int:
+    return int(lib().myyuvb_shard_ctrl_bytes())
 
 
 def launch_count() -> int:
@@ -275,6 +299,47 @@ class Context:
         _check(lib().myyuvb_xrgb_dct_compress_batch_dev(self._h, _ptr(d_bgrx), w, h, int(bottom_up), qa.ctypes.data_as(_u8p), n_frames,
                                                         chunk_frames, _ptr(d_iyuv) if d_iyuv is not None else None, _ptr(d_out),
                                                         out_capacity, _ptr(d_offsets)))
+
+    # ---- one image sharded over the GPUs of a box (see sharding.ShardGroup for the set-up) ----
+    def ipc_alloc(self, nbytes: int):
+        """(device address, 64-byte IPC handle) of zeroed device memory other processes can map."""
+        p = C.c_void_p()
+        h = (C.c_uint8 * 64)()
+        _check(lib().myyuvb_ipc_alloc(self._h, nbytes, C.byref(p), h))
+        return int(p.value), bytes(h)
+
+    def ipc_open(self, handle: bytes) -> int:
+        p = C.c_void_p()
+        buf = (C.c_uint8 * 64).from_buffer_copy(handle)
+        _check(lib().myyuvb_ipc_open(self._h, buf, C.byref(p)))
+        return int(p.value)
+
+    def ipc_close(self, ptr: int) -> None:
+        _check(lib().myyuvb_ipc_close(self._h, C.c_void_p(ptr)))
+
+    def ipc_free(self, ptr: int) -> None:
+        _check(lib().myyuvb_ipc_free(self._h, C.c_void_p(ptr)))
+
+    def compress_shard_dev(self, d_iyuv, full_frame: bool, w: int, h: int, q, rank: int, world: int, root: int, rows, ctrl,
+                           root_out: int, out_capacity: int, epoch: int) -> None:
+        qa = _q(q)
+        ra = (C.c_uint32 * (world + 1))(*rows)
+        ca = (C.c_void_p * world)(*ctrl)
+        _check(lib().myyuvb_dct_compress_shard_dev(self._h, _ptr(d_iyuv), int(full_frame), w, h, qa.ctypes.data_as(_u8p), rank, world, root,
+                                                   ra, ca, C.c_void_p(root_out), out_capacity, epoch))
+
+    def decompress_shard_dev(self, root_payload: int, payload_size: int, w: int, h: int, q, rank: int, world: int, root: int, rows, ctrl,
+                             d_band_out, root_iyuv: int | None, epoch: int) -> None:
+        qa = _q(q)
+        ra = (C.c_uint32 * (world + 1))(*rows)
+        ca = (C.c_void_p * world)(*ctrl)
+        _check(lib().myyuvb_dct_decompress_shard_dev(self._h, C.c_void_p(root_payload), payload_size, w, h, qa.ctypes.data_as(_u8p), rank,
+                                                     world, root, ra, ca, _ptr(d_band_out), C.c_void_p(root_iyuv) if root_iyuv else None, epoch))
+
+    def shard_result(self, ctrl_local: int) -> int:
+        n = C.c_uint64(0)
+        _check(lib().myyuvb_shard_result(self._h, C.c_void_p(ctrl_local), C.byref(n)))
+        return int(n.value)
 
     def last_kernel_ms(self) -> float:
         ms = C.c_float(0)

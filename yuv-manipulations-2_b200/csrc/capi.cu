@@ -190,12 +190,19 @@ int ensure_workspace(myyuvb_ctx* c, const FrameGeom& g, bool encoder, Workspace*
   return MYYUVB_OK;
 }
 
+int ensure_copy_streams(myyuvb_ctx* c) {
+  if (!c->copy_stream) CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  if (!c->d2h_stream) CU(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+  return MYYUVB_OK;
+}
+
 int flags_to_error(uint32_t flags) {
   // a capacity overflow leaves an incomplete payload behind, which a following decompress then rejects: report the cause
   if (flags & kFlagCapacity) return fail(MYYUVB_ERR_CAPACITY, "Error. output buffer is too small for the compressed data");
   if (flags & kFlagDctYuvSize) return fail(MYYUVB_ERR_DCTYUV_SIZE, "DCTYUV load bad size");
   if (flags & kFlagPlaneSize) return fail(MYYUVB_ERR_PLANE_SIZE, "DCTYUVPlane load bad size");
   if (flags & kFlagHuffman) return fail(MYYUVB_ERR_HUFFMAN, "Huffman bad code");
+  if (flags & kFlagShardTimeout) return fail(MYYUVB_ERR_SHARD_TIMEOUT, "shard: a rank of the group did not arrive within 2 s");
   return MYYUVB_OK;
 }
 
@@ -356,8 +363,8 @@ int myyuvb_ctx_create(int device, void* stream, myyuvb_ctx** out) {
       CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
       c->own_stream = true;
     }
-    CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+    // copy_stream and d2h_stream are created by the first pipelined host-pointer call (ensure_copy_streams): contexts that
+    // only serve device-pointer calls stay at one stream each
     for (auto& ev : c->d2h_ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     for (auto& ev : c->ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     for (auto& ev : c->ring_ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -661,6 +668,7 @@ static int compress_batch_host_impl(myyuvb_ctx* c, const uint8_t* iyuv, uint32_t
   if ((rc = check_quality(quality))) return rc;
   if ((rc = check_dims(w, h))) return rc;
   CU(cudaSetDevice(c->device));
+  if ((rc = ensure_copy_streams(c))) return rc;
   const uint64_t frame_bytes = (uint64_t)w * h * 3 / 2;
   const uint64_t bound = myyuvb_compress_bound(w, h);
   // chunk size: ~32 MB of input per chunk, at least one frame
@@ -729,6 +737,7 @@ static int decompress_batch_host_impl(myyuvb_ctx* c, const uint8_t* payloads, co
   for (uint32_t f = 0; f < n_frames; f++)
     if (offsets[f + 1] < offsets[f]) return fail(MYYUVB_ERR_ARG, "frame offsets must be non-decreasing");
   CU(cudaSetDevice(c->device));
+  if ((rc = ensure_copy_streams(c))) return rc;
   const uint64_t frame_bytes = (uint64_t)w * h * 3 / 2;
   const uint32_t per = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(n_frames, host_chunk_bytes() / frame_bytes));
   const uint32_t n_chunks = (n_frames + per - 1) / per;
@@ -794,9 +803,9 @@ static int decompress_batch_host_impl(myyuvb_ctx* c, const uint8_t* payloads, co
 static int drain_after_error(myyuvb_ctx* c, int rc) {
   if (!c || !c->stream) return rc;
   const std::string msg = g_err;
-  cudaStreamSynchronize(c->copy_stream);
+  if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
   cudaStreamSynchronize(c->stream);
-  cudaStreamSynchronize(c->d2h_stream);
+  if (c->d2h_stream) cudaStreamSynchronize(c->d2h_stream);
   if (c->d_counters.p) {
     cudaMemsetAsync(c->d_counters.as<uint32_t>() + 1, 0, 4, c->stream);
     cudaStreamSynchronize(c->stream);
@@ -815,6 +824,162 @@ int myyuvb_dct_decompress_batch_host(myyuvb_ctx* c, const uint8_t* payloads, con
                                      const uint8_t quality[3], uint32_t n_frames, uint8_t* iyuv_out) {
   const int rc = decompress_batch_host_impl(c, payloads, offsets, w, h, quality, n_frames, iyuv_out);
   return rc ? drain_after_error(c, rc) : rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// One image sharded over the GPUs of a box (BASELINE configs[3]): one process (or context) per GPU codes
+// a band of macroblock rows and stores it straight into the root's payload buffer over NVLink (kernels.cu, "the exchange
+// step").  Buffers that several ranks touch -- every rank's control block, the root's payload / image buffers -- are plain
+// device allocations shared through CUDA IPC handles; how the 64-byte handles travel between the processes is the
+// caller's business (sharding.py uses torch.distributed's object collectives once, at set-up).
+// ------------------------------------------------------------------------------------------------
+uint64_t myyuvb_shard_ctrl_bytes(void) { return sizeof(ShardCtrl); }
+
+int myyuvb_shard_rows(uint32_t height, uint32_t world, uint32_t* rows) {
+  if (!rows || world == 0 || world > (uint32_t)kShardMaxWorld) return fail(MYYUVB_ERR_ARG, "shard: world must be 1..16");
+  if (height % 16) return fail(MYYUVB_ERR_HEIGHT, "Error. height % 8 must be 0");
+  const uint32_t mb = height / 16, base = mb / world, extra = mb % world;  // e.g. 270 rows over 8 ranks: 34 x 6 + 33 x 2
+  uint32_t r = 0;
+  for (uint32_t q = 0; q <= world; q++) {
+    rows[q] = r * 16;
+    r += base + (q < extra ? 1 : 0);
+  }
+  return MYYUVB_OK;
+}
+
+int myyuvb_ipc_alloc(myyuvb_ctx* c, uint64_t bytes, void** d_ptr, uint8_t handle_out[64]) {
+  if (!c || !d_ptr || bytes == 0) return fail(MYYUVB_ERR_ARG, "null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the ABI carries IPC handles as 64 bytes");
+  CU(cudaSetDevice(c->device));
+  CU(cudaMalloc(d_ptr, bytes));
+  CU(cudaMemset(*d_ptr, 0, bytes));
+  if (handle_out) {
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, *d_ptr));
+    memcpy(handle_out, &h, 64);
+  }
+  return MYYUVB_OK;
+}
+
+int myyuvb_ipc_open(myyuvb_ctx* c, const uint8_t handle[64], void** d_ptr) {
+  if (!c || !handle || !d_ptr) return fail(MYYUVB_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  CU(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return MYYUVB_OK;
+}
+
+int myyuvb_ipc_close(myyuvb_ctx* c, void* d_ptr) {
+  if (!c || !d_ptr) return fail(MYYUVB_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->device));
+  CU(cudaIpcCloseMemHandle(d_ptr));
+  return MYYUVB_OK;
+}
+
+int myyuvb_ipc_free(myyuvb_ctx* c, void* d_ptr) {
+  if (!c || !d_ptr) return fail(MYYUVB_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->device));
+  CU(cudaFree(d_ptr));
+  return MYYUVB_OK;
+}
+
+static int shard_peers(uint32_t height, uint32_t rank, uint32_t world, uint32_t root, const uint32_t* rows, void* const* ctrl, uint32_t epoch,
+                       ShardPeers* S) {
+  if (!rows || !ctrl || world == 0 || world > (uint32_t)kShardMaxWorld || rank >= world || root >= world)
+    return fail(MYYUVB_ERR_ARG, "shard: bad rank / world / root");
+  if (rows[0] != 0 || rows[world] != height) return fail(MYYUVB_ERR_ARG, "shard: the bands must cover the image");
+  memset(S, 0, sizeof(*S));
+  for (uint32_t q = 0; q < world; q++) {
+    if (!ctrl[q]) return fail(MYYUVB_ERR_ARG, "shard: null control block");
+    if (rows[q + 1] < rows[q] || rows[q] % 16 || rows[q + 1] % 16) return fail(MYYUVB_ERR_ARG, "shard: bands must be whole macroblock rows");
+    S->ctrl[q] = static_cast<ShardCtrl*>(ctrl[q]);
+  }
+  for (uint32_t q = 0; q <= world; q++) S->row[q] = rows[q];
+  S->rank = rank; S->world = world; S->root = root; S->epoch = epoch;
+  return MYYUVB_OK;
+}
+
+// geometry of the band [y0, y1): an image of its own, or rows of a full frame that lies in device memory
+static FrameGeom band_geom(uint32_t w, uint32_t h, uint32_t y0, uint32_t y1, bool in_full_frame, uint32_t tile_blocks) {
+  FrameGeom g = make_geom(w, y1 - y0, 1, tile_blocks);
+  if (in_full_frame) {
+    g.plane_off[0] = (uint64_t)y0 * w;
+    g.plane_off[1] = (uint64_t)w * h + (uint64_t)(y0 / 2) * (w / 2);
+    g.plane_off[2] = (uint64_t)w * h * 5 / 4 + (uint64_t)(y0 / 2) * (w / 2);
+  }
+  return g;
+}
+
+int myyuvb_dct_compress_shard_dev(myyuvb_ctx* c, const uint8_t* d_iyuv, int iyuv_is_full_frame, uint32_t w, uint32_t h,
+                                  const uint8_t quality[3], uint32_t rank, uint32_t world, uint32_t root, const uint32_t* rows,
+                                  void* const* ctrl, uint8_t* root_out, uint64_t out_capacity, uint32_t epoch) {
+  if (!c || !d_iyuv || !quality || !root_out) return fail(MYYUVB_ERR_ARG, "null argument");
+  int rc;
+  if ((rc = check_quality(quality))) return rc;
+  if ((rc = check_dims(w, h))) return rc;
+  if (h % 16) return fail(MYYUVB_ERR_HEIGHT, "Error. height % 8 must be 0");
+  ShardPeers S;
+  if ((rc = shard_peers(h, rank, world, root, rows, ctrl, epoch, &S))) return rc;
+  if ((uintptr_t)d_iyuv & 7) return fail(MYYUVB_ERR_ARG, "device input must be 8-byte aligned");
+  CU(cudaSetDevice(c->device));
+  const FrameGeom g = band_geom(w, h, rows[rank], rows[rank + 1], iyuv_is_full_frame != 0, kEncTile);
+  const FrameGeom full = make_geom(w, h, 1, kEncTile);
+  Workspace ws{};
+  if ((rc = ensure_workspace(c, g, true, &ws, (uint64_t)g.nblk_frame * 255))) return rc;  // parking area: the band's worst case
+  QTables qt;
+  make_qtables(quality, &qt);
+  if (rank == root) launch_shard_go(S, c->stream);
+  launch_compress_shard(d_iyuv, g, full.nblk, qt, root_out, out_capacity, S, ws, c->stream);
+  launch_shard_done(S, ws, 0, c->stream);
+  CU(cudaGetLastError());
+  return MYYUVB_OK;
+}
+
+int myyuvb_dct_decompress_shard_dev(myyuvb_ctx* c, const uint8_t* root_payload, uint64_t payload_size, uint32_t w, uint32_t h,
+                                    const uint8_t quality[3], uint32_t rank, uint32_t world, uint32_t root, const uint32_t* rows,
+                                    void* const* ctrl, uint8_t* d_band_out, uint8_t* root_iyuv, uint32_t epoch) {
+  if (!c || !root_payload || !quality || !d_band_out) return fail(MYYUVB_ERR_ARG, "null argument");
+  int rc;
+  if ((rc = check_quality(quality))) return rc;
+  if ((rc = check_dims(w, h))) return rc;
+  if (h % 16) return fail(MYYUVB_ERR_HEIGHT, "Error. height % 8 must be 0");
+  ShardPeers S;
+  if ((rc = shard_peers(h, rank, world, root, rows, ctrl, epoch, &S))) return rc;
+  if ((uintptr_t)d_band_out & 7) return fail(MYYUVB_ERR_ARG, "device output must be 8-byte aligned");
+  CU(cudaSetDevice(c->device));
+  const uint32_t y0 = rows[rank], y1 = rows[rank + 1];
+  const FrameGeom g = band_geom(w, h, y0, y1, false, kDecTile);
+  const FrameGeom full = make_geom(w, h, 1, kDecTile);
+  Workspace ws{};
+  if ((rc = ensure_workspace(c, g, false, &ws))) return rc;
+  QTables qt;
+  make_qtables(quality, &qt);
+  const uint32_t k_lo[3] = {(y0 / 8) * (w / 8), (y0 / 16) * (w / 16), (y0 / 16) * (w / 16)};
+  if (rank == root) launch_shard_go(S, c->stream);
+  launch_decompress_shard(root_payload, payload_size, g, full.nblk, k_lo, qt, d_band_out, S, ws, c->stream);
+  if (root_iyuv && y1 > y0) {  // the band's three planes into the root's full frame (copy engines over NVLink)
+    const uint64_t bh = y1 - y0;
+    CU(cudaMemcpyAsync(root_iyuv + (uint64_t)y0 * w, d_band_out, bh * w, cudaMemcpyDefault, c->stream));
+    CU(cudaMemcpyAsync(root_iyuv + (uint64_t)w * h + (uint64_t)(y0 / 2) * (w / 2), d_band_out + bh * w, bh * w / 4, cudaMemcpyDefault, c->stream));
+    CU(cudaMemcpyAsync(root_iyuv + (uint64_t)w * h * 5 / 4 + (uint64_t)(y0 / 2) * (w / 2), d_band_out + bh * w * 5 / 4, bh * w / 4,
+                       cudaMemcpyDefault, c->stream));
+  }
+  launch_shard_done(S, ws, (uint64_t)w * h * 3 / 2, c->stream);
+  CU(cudaGetLastError());
+  return MYYUVB_OK;
+}
+
+int myyuvb_shard_result(myyuvb_ctx* c, const void* ctrl_local, uint64_t* total_size) {
+  if (!c || !ctrl_local) return fail(MYYUVB_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->device));
+  const int rc = myyuvb_batch_status(c);  // synchronises; data-dependent errors of this rank's part
+  if (rc) return rc;
+  ShardCtrl h;
+  CU(cudaMemcpy(&h, ctrl_local, sizeof(h), cudaMemcpyDeviceToHost));
+  if (h.status & kFlagShardTimeout) return fail(MYYUVB_ERR_SHARD_TIMEOUT, "shard: a rank of the group did not arrive within 2 s");
+  if (total_size) *total_size = h.total;
+  return MYYUVB_OK;
 }
 
 }  // extern "C"

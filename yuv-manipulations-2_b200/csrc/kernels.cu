@@ -567,6 +567,7 @@ struct ZShared {  // accessor of one block's column in EncSmem::zz
 struct EncParams {
   const uint8_t* src;
   uint8_t* out;
+  const ShardPlace* shard;  // nullptr, or where this rank's band of a sharded image goes in the root's payload buffer (out)
   const uint64_t* base;   // device pointer to the byte position of the batch's first payload in out (nullptr: 0);
                           // lets a pipeline append the payloads of successive chunks without a host round trip
   uint64_t out_cap;
@@ -1033,6 +1034,17 @@ __global__ void __launch_bounds__(1024) scan_frames_kernel(const __grid_constant
   }
 }
 
+// Byte position of a tile's chunks in the output buffer: fixed part (headers + size arrays up to this plane) + code bytes
+// before the tile.  For the band of a sharded image (one frame) the plane's content starts where shard_exchange_kernel
+// computed it from all ranks' content sizes, and the tile prefix counts from the start of the band's plane.
+MYB_D u64 tile_out_pos(const EncParams& P, const TileCoord& tc, uint32_t tile) {
+  const FrameGeom& g = P.g;
+  const int plane = (int)tc.plane;
+  if (P.shard) return P.shard->content_dst[plane] + (P.ws.tile_prefix[tile] - P.ws.plane_start[plane]);
+  const uint32_t fixed = 12 + 8 * (plane + 1) + g.nblk[0] + (plane > 0 ? g.nblk[1] : 0) + (plane > 1 ? g.nblk[2] : 0);
+  return (P.base ? *P.base : 0) + (u64)tc.frame * (36 + g.nblk_frame) + fixed + P.ws.frame_base[tc.frame] + P.ws.tile_prefix[tile];
+}
+
 // Pass 3: move every tile's chunk bytes from the scratch area to their place in the payload.
 // Absolute position = fixed part (headers + size arrays up to this plane) + code bytes before the tile.
 // One warp per tile: the copy of a tile (about 2 KB) is a chain of dependent loads (tile record, then bytes), so the
@@ -1042,12 +1054,11 @@ __global__ void __launch_bounds__(256) place_tiles_kernel(const __grid_constant_
   const uint32_t lane = threadIdx.x & 31, warps = gridDim.x * (blockDim.x >> 5);
   for (uint32_t tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); tile < P.total_tiles; tile += warps) {
     const TileCoord tc = tile_coord(g, tile);
-    const int plane = (int)tc.plane;
     const uint32_t total_raw = P.ws.tile_total[tile];
     const uint32_t total = total_raw & 0x7fffffffu;
     const u64 src = P.ws.tile_pos[tile];
-    const uint32_t fixed = 12 + 8 * (plane + 1) + g.nblk[0] + (plane > 0 ? g.nblk[1] : 0) + (plane > 1 ? g.nblk[2] : 0);
-    const u64 pos = (P.base ? *P.base : 0) + (u64)tc.frame * (36 + g.nblk_frame) + fixed + P.ws.frame_base[tc.frame] + P.ws.tile_prefix[tile];
+    if (P.shard && !P.shard->ok) continue;  // the exchange failed (flag raised there)
+    const u64 pos = tile_out_pos(P, tc, tile);
     if (pos + total > P.out_cap) {
       if (lane == 0) atomicOr(&P.ws.counters[1], kFlagCapacity);
       continue;
@@ -1078,8 +1089,7 @@ __global__ void __launch_bounds__(256) place_heavy_tiles_kernel(const __grid_con
       const int plane = (int)tc.plane;
       const uint32_t total = P.ws.tile_total[tile] & 0x7fffffffu;
       const u64 src = P.ws.tile_pos[tile];
-      const uint32_t fixed = 12 + 8 * (plane + 1) + g.nblk[0] + (plane > 0 ? g.nblk[1] : 0) + (plane > 1 ? g.nblk[2] : 0);
-      const u64 pos = (P.base ? *P.base : 0) + (u64)tc.frame * (36 + g.nblk_frame) + fixed + P.ws.frame_base[tc.frame] + P.ws.tile_prefix[tile];
+      const u64 pos = tile_out_pos(P, tc, tile);
       if (pos + total > P.out_cap) {
         if (lane == 0) atomicOr(&P.ws.counters[1], kFlagCapacity);
         continue;
@@ -1146,6 +1156,22 @@ constexpr uint32_t kSizeSlice = 8192;
 __global__ void __launch_bounds__(256) finalize_frames_kernel(const __grid_constant__ EncParams P, uint64_t* __restrict__ offsets) {
   const FrameGeom& g = P.g;
   const uint32_t f = blockIdx.x;
+  if (P.shard) {  // band of a sharded image: only the chunk-size segments, to where the exchange put them (headers: the root's exchange kernel)
+    if (!P.shard->ok) return;
+    uint32_t slice = blockIdx.y, plane = 0;
+    u64 sidx = 0;
+    for (; plane < 3; plane++) {
+      const uint32_t nsl = (g.nblk[plane] + kSizeSlice - 1) / kSizeSlice;
+      if (slice < nsl) break;
+      slice -= nsl;
+      sidx += g.nblk[plane];
+    }
+    if (plane == 3) return;
+    const uint32_t i0 = slice * kSizeSlice;
+    const uint32_t cnt = g.nblk[plane] - i0 < kSizeSlice ? g.nblk[plane] - i0 : kSizeSlice;
+    copy_global_to_global(P.out + P.shard->sizes_dst[plane] + i0, P.ws.chunk_sizes + sidx + i0, cnt, 256);
+    return;
+  }
   const uint64_t* ps = P.ws.plane_start + (uint64_t)f * 3;
   const u64 base = P.base ? *P.base : 0;
   const u64 frame_pos = base + (u64)f * (36 + g.nblk_frame) + ps[0];
@@ -1189,6 +1215,151 @@ __global__ void __launch_bounds__(256) finalize_frames_kernel(const __grid_const
   const uint32_t i0 = slice * kSizeSlice;
   const uint32_t cnt = n - i0 < kSizeSlice ? n - i0 : kSizeSlice;
   copy_global_to_global(out + ppos + 8 + i0, P.ws.chunk_sizes + sidx + i0, cnt, 256);
+}
+
+// ===================================================================================================
+// One image sharded over the GPUs of a box: the exchange step.
+// Every 8x8 block is coded on its own and a plane's content is the blocks' chunks in raster order (DCT.cpp:297-322), so a
+// band of macroblock rows yields, per plane, one run of chunk sizes (length known up front) and one run of content bytes
+// (length data dependent).  The only thing ranks must tell each other is those three content lengths: 12 bytes per rank,
+// stored by every rank into every peer's control block over NVLink, followed by an epoch flag.  Each rank then knows all
+// destinations (payload layout DCT.cpp:16-33,160-173) and its place kernels store the band straight into the root's buffer.
+// ===================================================================================================
+constexpr unsigned long long kShardTimeoutNs = 2000000000ull;  // a peer that never shows up must not hang the GPU
+
+MYB_D unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+MYB_D bool wait_epoch(const uint32_t* word, uint32_t epoch) {
+  const volatile uint32_t* p = word;
+  const unsigned long long t0 = global_ns();
+  while ((int32_t)(*p - epoch) < 0) {
+    if (global_ns() - t0 > kShardTimeoutNs) return false;
+    __nanosleep(40);
+  }
+  return true;
+}
+MYB_D void store_sys(uint32_t* p, uint32_t v) { *reinterpret_cast<volatile uint32_t*>(p) = v; }
+
+// root, first kernel of its call: its output buffer (and, decoding, its payload) is ready for `epoch`
+__global__ void shard_go_kernel(const __grid_constant__ ShardPeers S) {
+  const uint32_t q = threadIdx.x;
+  __threadfence_system();
+  if (q < S.world) store_sys(&S.ctrl[q]->go, S.epoch);
+}
+
+// One warp.  plane_start: the three content lengths of this rank's band are plane_start[p+1] - plane_start[p]
+// (nullptr: an empty band).  nblk_full: blocks per plane of the whole image.
+__global__ void __launch_bounds__(32) shard_exchange_kernel(const uint64_t* __restrict__ plane_start, uint32_t* __restrict__ flags,
+                                                            uint8_t* __restrict__ out, uint64_t out_cap, uint32_t width,
+                                                            uint32_t nbf0, uint32_t nbf1, uint32_t nbf2, const __grid_constant__ ShardPeers S) {
+  const uint32_t lane = threadIdx.x;
+  ShardCtrl* const mine = S.ctrl[S.rank];
+  bool ok = true;
+  if (lane == 0) ok = wait_epoch(&mine->go, S.epoch);  // the root has consumed the previous image
+  ok = __all_sync(0xffffffffu, ok);
+  uint32_t c[3] = {0, 0, 0};
+  if (plane_start)
+    for (int p = 0; p < 3; p++) c[p] = (uint32_t)(plane_start[p + 1] - plane_start[p]);
+  if (lane < S.world) {  // 12 bytes + flag into every rank's block (my own included)
+    ShardCtrl* peer = S.ctrl[lane];
+    for (int p = 0; p < 3; p++) store_sys(&peer->sizes[S.rank][p], c[p]);
+    __threadfence_system();
+    store_sys(&peer->sizes[S.rank][3], S.epoch);
+  }
+  uint32_t cq[3] = {0, 0, 0};
+  if (lane < S.world) {
+    ok = wait_epoch(&mine->sizes[lane][3], S.epoch) && ok;
+    for (int p = 0; p < 3; p++) cq[p] = *reinterpret_cast<volatile uint32_t*>(&mine->sizes[lane][p]);
+  }
+  ok = __all_sync(0xffffffffu, ok);
+  // blocks of band q per plane: rows [row[q], row[q+1]) of the luma plane
+  uint32_t nb[3] = {0, 0, 0};
+  if (lane < S.world) {
+    const uint32_t rows = S.row[lane + 1] - S.row[lane];
+    nb[0] = (rows / 8) * (width / 8);
+    nb[1] = nb[2] = (rows / 16) * (width / 16);
+  }
+  const uint32_t nbf[3] = {nbf0, nbf1, nbf2};
+  u64 ppos = 12, total = 12;
+  ShardPlace pl;
+  uint32_t csum[3];
+  for (int p = 0; p < 3; p++) {
+    uint32_t call = cq[p], cbefore = lane < S.rank ? cq[p] : 0u, nbefore = lane < S.rank ? nb[p] : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      call += __shfl_xor_sync(0xffffffffu, call, o);
+      cbefore += __shfl_xor_sync(0xffffffffu, cbefore, o);
+      nbefore += __shfl_xor_sync(0xffffffffu, nbefore, o);
+    }
+    csum[p] = call;
+    pl.sizes_dst[p] = ppos + 8 + nbefore;
+    pl.content_dst[p] = ppos + 8 + nbf[p] + cbefore;
+    ppos += 8 + (u64)nbf[p] + call;
+  }
+  total = ppos;
+  pl.total = total;
+  if (total > out_cap || total > 0xffffffffull) {
+    ok = false;
+    if (lane == 0) atomicOr(flags, kFlagCapacity);
+  } else if (!ok && lane == 0) {
+    atomicOr(flags, kFlagShardTimeout);
+  }
+  pl.ok = ok ? 1u : 0u;
+  pl.pad = 0;
+  if (lane == 0) mine->place = pl;
+  if (S.rank == S.root && ok) {  // planes_sizes[3], then {n_chunks, content_size} in front of every plane (DCT.cpp:160-173, :64-73)
+    for (uint32_t t = lane; t < 36; t += 32) {  // 36 header bytes, one per step and lane
+      u64 pp = 12, where = 0;
+      uint32_t val = 0;
+      const uint32_t field = t >> 2;
+      for (int p = 0; p < 3; p++) {
+        if (field == (uint32_t)p) { val = 8 + nbf[p] + csum[p]; where = 4 * p; }
+        if (field == 3u + 2 * p) { val = nbf[p]; where = pp; }
+        if (field == 4u + 2 * p) { val = csum[p]; where = pp + 4; }
+        pp += 8 + (u64)nbf[p] + csum[p];
+      }
+      out[where + (t & 3)] = (uint8_t)(val >> (8 * (t & 3)));
+    }
+  }
+}
+
+// Last kernel of a rank's sharded call: everything this rank stored into the root's buffers is ordered before the flag.
+// On the root: waits for every rank, then publishes total size and status in its own block.
+__global__ void __launch_bounds__(32) shard_done_kernel(uint32_t* __restrict__ flags, uint64_t total_if_known, const __grid_constant__ ShardPeers S) {
+  const uint32_t lane = threadIdx.x;
+  __threadfence_system();
+  if (lane == 0) store_sys(&S.ctrl[S.root]->done[S.rank], S.epoch);
+  if (S.rank != S.root) return;
+  ShardCtrl* const mine = S.ctrl[S.rank];
+  bool ok = true;
+  if (lane < S.world) ok = wait_epoch(&mine->done[lane], S.epoch);
+  ok = __all_sync(0xffffffffu, ok);
+  if (lane == 0) {
+    if (!ok) atomicOr(flags, kFlagShardTimeout);
+    mine->total = total_if_known ? total_if_known : mine->place.total;
+    mine->status = ok ? 0u : kFlagShardTimeout;
+  }
+}
+
+// Kernels of this module are loaded lazily at their first launch, and loading may wait for the device to drain.  A sharded
+// call leaves a kernel spinning on its peers, so everything it launches afterwards must already be loaded: with several
+// ranks in one process (virtual ranks on one device) the host would otherwise block inside a launch while the peers it has
+// not issued yet are what the spinning kernel waits for.
+void shard_preload();
+__global__ void publish_words_kernel(uint32_t* __restrict__ h_dst, const uint32_t* __restrict__ d_src, uint32_t n);
+
+void launch_shard_go(const ShardPeers& peers, cudaStream_t s) {
+  shard_preload();
+  shard_go_kernel<<<1, 32, 0, s>>>(peers);
+  g_launches++;
+}
+
+void launch_shard_done(const ShardPeers& peers, const Workspace& ws, uint64_t total_if_known, cudaStream_t s) {
+  shard_done_kernel<<<1, 32, 0, s>>>(ws.counters + 1, total_if_known, peers);
+  g_launches++;
 }
 
 constexpr int kEncCtasPerSm = 6, kDecCtasPerSm = 6;  // resident CTAs per SM (registers and shared memory sized for it)
@@ -1557,12 +1728,11 @@ __global__ void __launch_bounds__(kCtaThreads, 6)
 // ===================================================================================================
 // launchers
 // ===================================================================================================
-void launch_compress(const uint8_t* d_iyuv, const FrameGeom& g, const QTables& qt, uint8_t* d_out, uint64_t out_cap,
-                     uint64_t* d_offsets, const uint64_t* d_base, const Workspace& ws, cudaStream_t s) {
-  EncParams P;
-  P.src = d_iyuv; P.out = d_out; P.base = d_base; P.out_cap = out_cap; P.g = g; P.ws = ws;
-  P.total_tiles = g.tiles_per_frame * g.n_frames;
-  P.one = 1.0f;
+namespace {
+// code tiles, deferred blocks, the two scans: everything that needs no knowledge of where the payload goes
+void compress_code_and_scan(const EncParams& P, const QTables& qt, cudaStream_t s) {
+  const Workspace& ws = P.ws;
+  const FrameGeom& g = P.g;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(dct_compress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncSmem));
@@ -1586,6 +1756,13 @@ void launch_compress(const uint8_t* d_iyuv, const FrameGeom& g, const QTables& q
   }
   scan_frame_tiles_kernel<<<g.n_frames, 512, 0, s>>>(P);
   scan_frames_kernel<<<1, 1024, 0, s>>>(P);
+  g_launches += ws.heavy_cap ? 5 : 3;
+}
+
+// tiles to their final place, headers and chunk-size arrays
+void compress_place_and_finalize(const EncParams& P, uint64_t* d_offsets, cudaStream_t s) {
+  const Workspace& ws = P.ws;
+  const FrameGeom& g = P.g;
   const uint32_t pwant = (P.total_tiles + 7) / 8;
   place_tiles_kernel<<<(int)(pwant < 148u * 8 ? pwant : 148u * 8), 256, 0, s>>>(P);
   if (ws.heavy_cap) place_heavy_tiles_kernel<<<(int)(pwant < 148u * 3 ? pwant : 148u * 3), 256, 0, s>>>(P);
@@ -1595,7 +1772,147 @@ void launch_compress(const uint8_t* d_iyuv, const FrameGeom& g, const QTables& q
     finalize_frames_kernel<<<dim3(g.n_frames, slices), 256, 0, s>>>(P, d_offsets);
   }
   if (ws.k_end) cudaEventRecord(ws.k_end, s);  // the whole compress sequence (8 kernels) is what gets timed
-  g_launches += ws.heavy_cap ? 8 : 5;
+  g_launches += ws.heavy_cap ? 3 : 2;
+}
+}  // namespace
+
+void launch_compress(const uint8_t* d_iyuv, const FrameGeom& g, const QTables& qt, uint8_t* d_out, uint64_t out_cap,
+                     uint64_t* d_offsets, const uint64_t* d_base, const Workspace& ws, cudaStream_t s) {
+  EncParams P;
+  P.src = d_iyuv; P.out = d_out; P.shard = nullptr; P.base = d_base; P.out_cap = out_cap; P.g = g; P.ws = ws;
+  P.total_tiles = g.tiles_per_frame * g.n_frames;
+  P.one = 1.0f;
+  compress_code_and_scan(P, qt, s);
+  compress_place_and_finalize(P, d_offsets, s);
+}
+
+void launch_compress_shard(const uint8_t* d_iyuv, const FrameGeom& g, const uint32_t nblk_full[3], const QTables& qt, uint8_t* out,
+                           uint64_t out_cap, const ShardPeers& peers, const Workspace& ws, cudaStream_t s) {
+  shard_preload();
+  EncParams P;
+  P.src = d_iyuv; P.out = out; P.shard = &peers.ctrl[peers.rank]->place; P.base = nullptr; P.out_cap = out_cap; P.g = g; P.ws = ws;
+  P.total_tiles = g.tiles_per_frame * g.n_frames;
+  P.one = 1.0f;
+  const bool empty = P.total_tiles == 0;  // more ranks than macroblock rows: this rank only takes part in the exchange
+  if (!empty) compress_code_and_scan(P, qt, s);
+  shard_exchange_kernel<<<1, 32, 0, s>>>(empty ? nullptr : ws.plane_start, ws.counters + 1, out, out_cap, g.width, nblk_full[0], nblk_full[1],
+                                         nblk_full[2], peers);
+  g_launches++;
+  if (!empty) compress_place_and_finalize(P, nullptr, s);
+}
+
+// Decoding a band of a sharded image: the payload lives in the root's memory (read over NVLink).  One CTA per plane checks the
+// headers like parse_payload_kernel does (DCT.cpp:130-159, :39-62, against the FULL image's block counts) and sums the
+// chunk sizes of the blocks above the band, which is where the band's content starts (the reference's getContentPos,
+// DCT.cpp:21-33, restricted to one position).  The plane descriptors then describe the band as if it were an image.
+struct ShardBand {
+  uint32_t nblk_full[3];  // blocks per plane of the whole image
+  uint32_t k_lo[3];       // first block of the band in each plane
+};
+__global__ void __launch_bounds__(1024) shard_dec_prepare_kernel(const __grid_constant__ DecParams P, uint64_t payload_size,
+                                                                 const __grid_constant__ ShardBand B, const __grid_constant__ ShardPeers S) {
+  __shared__ uint32_t warp_sums[32];
+  __shared__ int go_ok;
+  const uint32_t plane = blockIdx.x;
+  if (threadIdx.x == 0) go_ok = wait_epoch(&S.ctrl[S.rank]->go, S.epoch) ? 1 : 0;  // the root's payload is in place
+  __syncthreads();
+  PlaneDesc* desc = reinterpret_cast<PlaneDesc*>(P.ws.plane_desc) + plane;
+  if (!go_ok) {
+    if (threadIdx.x == 0) { desc->ok = 0; atomicOr(&P.ws.counters[1], kFlagShardTimeout); }
+    return;
+  }
+  const uint8_t* pl = P.payloads;
+  auto rd32 = [&](u64 o) { return (uint32_t)pl[o] | ((uint32_t)pl[o + 1] << 8) | ((uint32_t)pl[o + 2] << 16) | ((uint32_t)pl[o + 3] << 24); };
+  uint32_t flag = 0;
+  u64 ppos = 12;
+  uint32_t n = 0, content = 0;
+  if (payload_size <= 12) {
+    flag = kFlagDctYuvSize;
+  } else {
+    u64 psz[3], tot = 12;
+    for (int p = 0; p < 3; p++) { psz[p] = rd32(4 * p); tot += psz[p]; }
+    if (payload_size < tot) flag = kFlagDctYuvSize;
+    for (uint32_t p = 0; p <= plane && !flag; p++) {
+      if (psz[p] <= 8) { flag = kFlagPlaneSize; break; }
+      n = rd32(ppos);
+      content = rd32(ppos + 4);
+      if (n == 0 || content == 0 || psz[p] < 8ull + n + content || n < B.nblk_full[p]) { flag = kFlagPlaneSize; break; }
+      if (p < plane) ppos += psz[p];
+    }
+  }
+  if (flag) {  // uniform over the CTA
+    if (threadIdx.x == 0) { desc->ok = 0; atomicOr(&P.ws.counters[1], flag); }
+    return;
+  }
+  const uint8_t* sizes = pl + ppos + 8;
+  const uint32_t k_lo = B.k_lo[plane];
+  u64 sum = 0;
+  for (uint32_t i = threadIdx.x; i < k_lo; i += blockDim.x) sum += sizes[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = (uint32_t)sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    u64 prefix = 0;
+    for (int w = 0; w < 32; w++) prefix += warp_sums[w];
+    desc->sizes_off = ppos + 8 + k_lo;
+    desc->content_off = ppos + 8 + n + prefix;
+    desc->content_size = prefix <= content ? (uint32_t)(content - prefix) : 0u;
+    desc->ok = 1;
+  }
+}
+
+void launch_decompress_shard(const uint8_t* payload, uint64_t payload_size, const FrameGeom& g, const uint32_t nblk_full[3],
+                             const uint32_t k_lo[3], const QTables& qt, uint8_t* d_band, const ShardPeers& peers, const Workspace& ws,
+                             cudaStream_t s) {
+  shard_preload();
+  DecParams P;
+  P.payloads = payload; P.offsets = nullptr; P.dst = d_band; P.g = g; P.ws = ws;
+  P.total_tiles = g.tiles_per_frame * g.n_frames;
+  P.one = 1.0f;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(dct_decompress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecSmem));
+    attr_set = true;
+  }
+  ShardBand B;
+  for (int p = 0; p < 3; p++) { B.nblk_full[p] = nblk_full[p]; B.k_lo[p] = k_lo[p]; }
+  cudaMemsetAsync(ws.counters, 0, 4, s);
+  if (ws.k_begin) cudaEventRecord(ws.k_begin, s);
+  shard_dec_prepare_kernel<<<3, 1024, 0, s>>>(P, payload_size, B, peers);
+  g_launches++;
+  if (P.total_tiles) {
+    const uint32_t want = (P.total_tiles + 7) / 8;
+    dec_tile_totals_kernel<<<want < 148u * 8 ? want : 148u * 8, 256, 0, s>>>(P);
+    dec_scan_planes_kernel<<<3, 1024, 0, s>>>(P);
+    const int grid = (int)(P.total_tiles < (uint32_t)ws.grid ? P.total_tiles : (uint32_t)ws.grid);
+    dct_decompress_kernel<<<grid, kCtaThreads, sizeof(DecSmem), s>>>(P, qt);
+    g_launches += 3;
+  }
+  if (ws.k_end) cudaEventRecord(ws.k_end, s);
+}
+
+void shard_preload() {
+  static bool done = false;
+  if (done) return;
+  done = true;
+  cudaFuncAttributes a;
+  cudaFuncGetAttributes(&a, shard_go_kernel);
+  cudaFuncGetAttributes(&a, shard_exchange_kernel);
+  cudaFuncGetAttributes(&a, shard_done_kernel);
+  cudaFuncGetAttributes(&a, shard_dec_prepare_kernel);
+  cudaFuncGetAttributes(&a, dct_compress_kernel);
+  cudaFuncGetAttributes(&a, heavy_blocks_kernel<32>);
+  cudaFuncGetAttributes(&a, heavy_blocks_kernel<64>);
+  cudaFuncGetAttributes(&a, scan_frame_tiles_kernel);
+  cudaFuncGetAttributes(&a, scan_frames_kernel);
+  cudaFuncGetAttributes(&a, place_tiles_kernel);
+  cudaFuncGetAttributes(&a, place_heavy_tiles_kernel);
+  cudaFuncGetAttributes(&a, finalize_frames_kernel);
+  cudaFuncGetAttributes(&a, dec_tile_totals_kernel);
+  cudaFuncGetAttributes(&a, dec_scan_planes_kernel);
+  cudaFuncGetAttributes(&a, dct_decompress_kernel);
+  cudaFuncGetAttributes(&a, publish_words_kernel);
 }
 
 void launch_decompress(const uint8_t* d_payloads, const uint64_t* d_offsets, const FrameGeom& g, const QTables& qt,

@@ -78,7 +78,50 @@ struct PlaneDesc {
   uint32_t ok;
 };
 
+// ---- one image sharded over the GPUs of a box ----
+constexpr int kShardMaxWorld = 16;
+constexpr uint32_t kFlagShardTimeout = 1u << 4;
+
+// Where this rank's band goes in the root's payload buffer; written by shard_exchange_kernel, read by the place / finalize kernels
+struct ShardPlace {
+  uint64_t content_dst[3];  // byte position of the band's content of plane p
+  uint64_t sizes_dst[3];    // byte position of the band's chunk-size segment of plane p
+  uint64_t total;           // payload bytes of the whole image
+  uint32_t ok, pad;
+};
+
+// One control block per rank, in device memory that every rank of the group has mapped (CUDA IPC across processes).
+// Peers store into it over NVLink; the owner polls it with volatile loads.  Epochs count calls on the group.
+struct ShardCtrl {
+  uint32_t sizes[kShardMaxWorld][4];  // [q] = content bytes of band q's Y, U, V planes, then the epoch they belong to (stored last)
+  uint32_t done[kShardMaxWorld];      // (root's block) epoch whose band q has arrived in the root's buffer
+  uint32_t go;                        // the root is ready to receive this epoch (its buffer is free again)
+  uint32_t status;                    // (root's block) error bits of the last assembled image
+  uint64_t total;                     // (root's block) payload bytes of the last assembled image
+  ShardPlace place;                   // this rank's destinations for the current epoch
+};
+
+struct ShardPeers {
+  ShardCtrl* ctrl[kShardMaxWorld];    // every rank's control block as mapped on this device; ctrl[rank] is local
+  uint32_t row[kShardMaxWorld + 1];   // luma pixel rows [row[q], row[q+1]) = band of rank q (multiples of 16)
+  uint32_t rank, world, root, epoch;
+};
+
 int codec_grid_size(int device, bool encoder);
+
+// Band of a sharded image (n_frames == 1 in g, plane_off may point into a full frame).  out: the root's payload buffer as mapped
+// here.  Coding and the two scans run locally; shard_exchange_kernel trades the three content sizes with every peer over
+// NVLink and derives the band's destinations; the place / finalize kernels then store the band straight into the root's
+// buffer; shard_done_kernel reports to the root, which waits for all bands.  Everything is stream ordered: no host round trip.
+void launch_compress_shard(const uint8_t* d_iyuv, const FrameGeom& g, const uint32_t nblk_full[3], const QTables& qt, uint8_t* out,
+                           uint64_t out_cap, const ShardPeers& peers, const Workspace& ws, cudaStream_t s);
+// Decoding side: payload = the root's payload buffer as mapped here; the band is decoded into d_band (band geometry g).
+void launch_decompress_shard(const uint8_t* payload, uint64_t payload_size, const FrameGeom& g, const uint32_t nblk_full[3],
+                             const uint32_t k_lo[3], const QTables& qt, uint8_t* d_band, const ShardPeers& peers, const Workspace& ws,
+                             cudaStream_t s);
+// last kernel of a sharded call: tells the root that this rank's part of `epoch` is in place; on the root, waits for all ranks
+void launch_shard_done(const ShardPeers& peers, const Workspace& ws, uint64_t total_if_known, cudaStream_t s);
+void launch_shard_go(const ShardPeers& peers, cudaStream_t s);  // root only, first kernel of its call
 
 void launch_xrgb_to_iyuv(const uint8_t* d_bgrx, uint8_t* d_iyuv, uint32_t w, uint32_t h, int bottom_up, uint32_t n_frames,
                          cudaStream_t s);

@@ -195,3 +195,96 @@ def decompress_image_sharded(payload, w: int, h: int, q, decompress_fn: Callable
     if bands is None:
         return None
     return unslice_iyuv(bands, w, h, ranges)
+
+
+# ------------------------------------------------------------------------------------------------
+# device path: every band goes straight from the coding GPU into the root's buffer over NVLink
+# ------------------------------------------------------------------------------------------------
+class ShardGroup:
+    """One rank's handle on a group of GPUs that code ONE image together (C ABI: myyuvb_dct_{compress,decompress}_shard_dev).
+
+    Set-up (once): every rank allocates a 400-byte control block, the root allocates the payload buffer and a frame
+    buffer; all of them are shared through CUDA IPC handles (``distributed``) or, for virtual ranks that live in one
+    process on one device, by plain pointers (``local``).  After that a call exchanges nothing through the host: the
+    ranks' streams meet on the device (kernels.cu, shard_exchange_kernel / shard_done_kernel).
+
+    ``compress(d_iyuv)`` / ``decompress(payload_size)`` are asynchronous on the context's stream and must be issued by
+    every rank of the group; ``result()`` (root) synchronises and returns the assembled size."""
+
+    def __init__(self, ctx, rank: int, world: int, root: int, w: int, h: int, ctrl, root_out: int, out_capacity: int, root_iyuv: int,
+                 owned=(), opened=()):
+        from . import capi
+
+        self.ctx, self.rank, self.world, self.root, self.w, self.h = ctx, rank, world, root, w, h
+        self.ctrl, self.root_out, self.out_capacity, self.root_iyuv = list(ctrl), root_out, out_capacity, root_iyuv
+        self.rows = capi.shard_rows(h, world)
+        self.epoch = 0
+        self._owned, self._opened = list(owned), list(opened)
+
+    @property
+    def band(self) -> Tuple[int, int]:
+        return self.rows[self.rank], self.rows[self.rank + 1]
+
+    @classmethod
+    def local(cls, ctxs, w: int, h: int, root: int = 0) -> "List[ShardGroup]":
+        """Virtual ranks: several contexts (streams) of one process on one device; used by the single-GPU tests."""
+        from . import capi
+
+        world = len(ctxs)
+        ctrl = [c.ipc_alloc(capi.shard_ctrl_bytes())[0] for c in ctxs]
+        cap = capi.compress_bound(w, h)
+        out = ctxs[root].ipc_alloc(cap)[0]
+        frame = ctxs[root].ipc_alloc(w * h * 3 // 2)[0]
+        return [cls(c, r, world, root, w, h, ctrl, out, cap, frame, owned=([ctrl[r]] + ([out, frame] if r == root else [])))
+                for r, c in enumerate(ctxs)]
+
+    @classmethod
+    def distributed(cls, ctx, dist, w: int, h: int, root: int = 0, out_capacity: int | None = None) -> "ShardGroup":
+        """One process per GPU (torch.distributed initialised): IPC handles travel once through all_gather_object."""
+        from . import capi
+
+        rank, world = dist.get_rank(), dist.get_world_size()
+        my_ctrl, my_handle = ctx.ipc_alloc(capi.shard_ctrl_bytes())
+        mine = {"ctrl": my_handle}
+        owned = [my_ctrl]
+        cap = out_capacity or capi.compress_bound(w, h)
+        if rank == root:
+            out, mine["out"] = ctx.ipc_alloc(cap)
+            frame, mine["frame"] = ctx.ipc_alloc(w * h * 3 // 2)
+            owned += [out, frame]
+        everyone = [None] * world
+        dist.all_gather_object(everyone, mine)
+        ctrl, opened = [], []
+        for q, rec in enumerate(everyone):
+            if q == rank:
+                ctrl.append(my_ctrl)
+            else:
+                ctrl.append(ctx.ipc_open(rec["ctrl"]))
+                opened.append(ctrl[-1])
+        if rank != root:
+            out, frame = ctx.ipc_open(everyone[root]["out"]), ctx.ipc_open(everyone[root]["frame"])
+            opened += [out, frame]
+        return cls(ctx, rank, world, root, w, h, ctrl, out, cap, frame, owned=owned, opened=opened)
+
+    def compress(self, d_iyuv, q, full_frame: bool = False) -> None:
+        """d_iyuv: this rank's band as an IYUV image of its own (or the whole frame when full_frame)."""
+        self.epoch += 1
+        self.ctx.compress_shard_dev(d_iyuv, full_frame, self.w, self.h, q, self.rank, self.world, self.root, self.rows, self.ctrl,
+                                    self.root_out, self.out_capacity, self.epoch)
+
+    def decompress(self, payload_size: int, q, d_band_out, to_root: bool = True) -> None:
+        """Decodes this rank's band of the payload in the root's buffer into d_band_out and, if to_root, into the root's frame."""
+        self.epoch += 1
+        self.ctx.decompress_shard_dev(self.root_out, payload_size, self.w, self.h, q, self.rank, self.world, self.root, self.rows, self.ctrl,
+                                      d_band_out, self.root_iyuv if to_root else None, self.epoch)
+
+    def result(self) -> int:
+        return self.ctx.shard_result(self.ctrl[self.rank])
+
+    def close(self) -> None:
+        self.ctx.sync()
+        for p in self._opened:
+            self.ctx.ipc_close(p)
+        for p in self._owned:
+            self.ctx.ipc_free(p)
+        self._opened, self._owned = [], []
