@@ -53,6 +53,8 @@ def test_virtual_ranks_match_oracle(pkg, ora, synth, w, h, world, q, full_frame)
                 g.ctx.compress_batch_dev(b, w, bh, q, 1, t_out, cap, t_off)
                 g.ctx.decompress_batch_dev(t_out, t_off, w, bh, q, 1, t_back)
                 g.ctx.batch_status()
+                # ... and the context's input buffer, where the decoding side keeps its copy of the band's payload (256 bytes per block)
+                g.ctx.xrgb_to_iyuv(np.zeros(w * 2 * bh * 4, np.uint8), w, 2 * bh)
         torch.cuda.synchronize()
         for rep in range(3):  # epochs 1..3 on the same buffers
             for g, b in zip(groups, bands):

@@ -957,14 +957,9 @@ int myyuvb_dct_decompress_shard_dev(myyuvb_ctx* c, const uint8_t* root_payload, 
   make_qtables(quality, &qt);
   const uint32_t k_lo[3] = {(y0 / 8) * (w / 8), (y0 / 16) * (w / 16), (y0 / 16) * (w / 16)};
   if (rank == root) launch_shard_go(S, c->stream);
-  launch_decompress_shard(root_payload, payload_size, g, full.nblk, k_lo, qt, d_band_out, S, ws, c->stream);
-  if (root_iyuv && y1 > y0) {  // the band's three planes into the root's full frame (copy engines over NVLink)
-    const uint64_t bh = y1 - y0;
-    CU(cudaMemcpyAsync(root_iyuv + (uint64_t)y0 * w, d_band_out, bh * w, cudaMemcpyDefault, c->stream));
-    CU(cudaMemcpyAsync(root_iyuv + (uint64_t)w * h + (uint64_t)(y0 / 2) * (w / 2), d_band_out + bh * w, bh * w / 4, cudaMemcpyDefault, c->stream));
-    CU(cudaMemcpyAsync(root_iyuv + (uint64_t)w * h * 5 / 4 + (uint64_t)(y0 / 2) * (w / 2), d_band_out + bh * w * 5 / 4, bh * w / 4,
-                       cudaMemcpyDefault, c->stream));
-  }
+  if ((rc = c->d_in.reserve((uint64_t)g.nblk_frame * 256 + 64))) return rc;  // the band's part of the payload, pulled from the root
+  launch_decompress_shard(root_payload, payload_size, g, full.nblk, k_lo, qt, d_band_out, c->d_in.as<uint8_t>(), S, ws, c->stream);
+  if (root_iyuv && y1 > y0) launch_shard_push(d_band_out, root_iyuv, w, h, y0, y1, c->stream);  // the band into the root's frame
   launch_shard_done(S, ws, (uint64_t)w * h * 3 / 2, c->stream);
   CU(cudaGetLastError());
   return MYYUVB_OK;

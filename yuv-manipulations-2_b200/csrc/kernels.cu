@@ -174,6 +174,8 @@ MYB_D TileCoord tile_coord(const FrameGeom& g, uint32_t tile) {
   return t;
 }
 
+constexpr uint32_t kSmCopySegment = 32u << 10;  // bytes one CTA copies per step in the SM copy kernels
+
 // CTA-wide exclusive scan of one value per thread (kCtaThreads = 128 -> 4 warps); returns exclusive
 // prefix, *total gets the CTA sum.  Contains two __syncthreads.
 MYB_D uint32_t cta_exclusive_scan(uint32_t v, uint32_t* warp_sums /* [4] shared */, uint32_t* total) {
@@ -1801,27 +1803,65 @@ void launch_compress_shard(const uint8_t* d_iyuv, const FrameGeom& g, const uint
   if (!empty) compress_place_and_finalize(P, nullptr, s);
 }
 
-// Decoding a band of a sharded image: the payload lives in the root's memory (read over NVLink).  One CTA per plane checks the
-// headers like parse_payload_kernel does (DCT.cpp:130-159, :39-62, against the FULL image's block counts) and sums the
-// chunk sizes of the blocks above the band, which is where the band's content starts (the reference's getContentPos,
-// DCT.cpp:21-33, restricted to one position).  The plane descriptors then describe the band as if it were an image.
+// Decoding a band of a sharded image.  The payload lives in the root's memory; a rank first finds its part of it and
+// PULLS that part into local memory with wide loads over NVLink (remote loads are latency bound: decoding straight from the
+// peer mapping made two GPUs slower than one), then decodes locally.
+// shard_dec_prepare_kernel, one CTA per plane: checks the headers like parse_payload_kernel does (DCT.cpp:130-159, :39-62,
+// against the FULL image's block counts), sums the chunk sizes of the blocks above the band -- where the band's content
+// starts, the reference's getContentPos (DCT.cpp:21-33) for one position -- and of the band itself, and describes the
+// band's local copy as if it were an image: [sizes Y | sizes U | sizes V | content Y | content U | content V], the
+// content regions spaced for the worst case so that their positions do not depend on the data.
 struct ShardBand {
   uint32_t nblk_full[3];  // blocks per plane of the whole image
   uint32_t k_lo[3];       // first block of the band in each plane
+  uint32_t nb[3];         // blocks of the band in each plane
 };
+struct ShardPull {        // written by the prepare kernel, read by the pull kernel
+  uint64_t src_sizes, src_content, dst_sizes, dst_content;
+  uint32_t n_sizes, n_content;
+};
+MYB_D uint64_t sum_bytes(const uint8_t* __restrict__ p, uint32_t n, uint32_t t, uint32_t nthreads) {
+  // bytes p[0 .. n) summed by nthreads threads: 128-bit loads for the aligned middle, byte loads for the ragged ends
+  uint64_t sum = 0;
+  const uint32_t head = min((uint32_t)((16 - ((uintptr_t)p & 15)) & 15), n);
+  if (t < head) sum += p[t];
+  const uint32_t vecs = (n - head) >> 4;
+  const uint4* v = reinterpret_cast<const uint4*>(p + head);
+  uint32_t i = t;
+  for (; i + 3 * nthreads < vecs; i += 4 * nthreads) {  // four independent loads in flight: these may cross NVLink
+    const uint4 x0 = v[i], x1 = v[i + nthreads], x2 = v[i + 2 * nthreads], x3 = v[i + 3 * nthreads];
+    const uint32_t w[16] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w, x2.x, x2.y, x2.z, x2.w, x3.x, x3.y, x3.z, x3.w};
+#pragma unroll
+    for (int j = 0; j < 16; j++) sum += __dp4a(w[j], 0x01010101u, 0u);
+  }
+  for (; i < vecs; i += nthreads) {
+    const uint4 x = v[i];
+    const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+    for (int j = 0; j < 4; j++) sum += __dp4a(w[j], 0x01010101u, 0u);
+  }
+  const uint32_t done = head + (vecs << 4);
+  if (t < n - done) sum += p[done + t];
+  return sum;
+}
 __global__ void __launch_bounds__(1024) shard_dec_prepare_kernel(const __grid_constant__ DecParams P, uint64_t payload_size,
-                                                                 const __grid_constant__ ShardBand B, const __grid_constant__ ShardPeers S) {
-  __shared__ uint32_t warp_sums[32];
+                                                                 const __grid_constant__ ShardBand B, ShardPull* __restrict__ pull,
+                                                                 const __grid_constant__ ShardPeers S) {
+  __shared__ unsigned long long sums[2];
   __shared__ int go_ok;
   const uint32_t plane = blockIdx.x;
-  if (threadIdx.x == 0) go_ok = wait_epoch(&S.ctrl[S.rank]->go, S.epoch) ? 1 : 0;  // the root's payload is in place
+  if (threadIdx.x == 0) {
+    go_ok = wait_epoch(&S.ctrl[S.rank]->go, S.epoch) ? 1 : 0;  // the root's payload is in place
+    sums[0] = sums[1] = 0;
+  }
   __syncthreads();
   PlaneDesc* desc = reinterpret_cast<PlaneDesc*>(P.ws.plane_desc) + plane;
+  if (threadIdx.x == 0) pull[plane].n_sizes = pull[plane].n_content = 0;
   if (!go_ok) {
     if (threadIdx.x == 0) { desc->ok = 0; atomicOr(&P.ws.counters[1], kFlagShardTimeout); }
     return;
   }
-  const uint8_t* pl = P.payloads;
+  const uint8_t* pl = P.payloads;  // the root's payload (peer mapping)
   auto rd32 = [&](u64 o) { return (uint32_t)pl[o] | ((uint32_t)pl[o + 1] << 8) | ((uint32_t)pl[o + 2] << 16) | ((uint32_t)pl[o + 3] << 24); };
   uint32_t flag = 0;
   u64 ppos = 12;
@@ -1845,26 +1885,87 @@ __global__ void __launch_bounds__(1024) shard_dec_prepare_kernel(const __grid_co
     return;
   }
   const uint8_t* sizes = pl + ppos + 8;
-  const uint32_t k_lo = B.k_lo[plane];
-  u64 sum = 0;
-  for (uint32_t i = threadIdx.x; i < k_lo; i += blockDim.x) sum += sizes[i];
+  const uint32_t k_lo = B.k_lo[plane], nb = B.nb[plane];
+  u64 above = sum_bytes(sizes, k_lo, threadIdx.x, blockDim.x), inside = sum_bytes(sizes + k_lo, nb, threadIdx.x, blockDim.x);
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = (uint32_t)sum;
+  for (int o = 16; o > 0; o >>= 1) {
+    above += __shfl_xor_sync(0xffffffffu, above, o);
+    inside += __shfl_xor_sync(0xffffffffu, inside, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&sums[0], (unsigned long long)above);
+    atomicAdd(&sums[1], (unsigned long long)inside);
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
-    u64 prefix = 0;
-    for (int w = 0; w < 32; w++) prefix += warp_sums[w];
-    desc->sizes_off = ppos + 8 + k_lo;
-    desc->content_off = ppos + 8 + n + prefix;
-    desc->content_size = prefix <= content ? (uint32_t)(content - prefix) : 0u;
+    const u64 prefix = sums[0], mine = sums[1];
+    const u64 nb_all = (u64)B.nb[0] + B.nb[1] + B.nb[2];
+    const u64 dst_sizes = (plane > 0 ? B.nb[0] : 0) + (plane > 1 ? B.nb[1] : 0);
+    const u64 dst_content = nb_all + 255ull * ((plane > 0 ? B.nb[0] : 0) + (plane > 1 ? B.nb[1] : 0));
+    if (prefix + mine > content) {  // the chunks of the band must lie inside content[]
+      desc->ok = 0;
+      atomicOr(&P.ws.counters[1], kFlagHuffman);
+      return;
+    }
+    pull[plane].src_sizes = ppos + 8 + k_lo;
+    pull[plane].src_content = ppos + 8 + n + prefix;
+    pull[plane].dst_sizes = dst_sizes;
+    pull[plane].dst_content = dst_content;
+    pull[plane].n_sizes = nb;
+    pull[plane].n_content = (uint32_t)mine;
+    desc->sizes_off = dst_sizes;
+    desc->content_off = dst_content;
+    desc->content_size = (uint32_t)mine;
     desc->ok = 1;
   }
 }
 
+// six segments (three runs of chunk sizes, three runs of content) from the root's payload into the local copy, 32 KB per CTA step
+__global__ void __launch_bounds__(256) shard_pull_kernel(const uint8_t* __restrict__ payload, uint8_t* __restrict__ local,
+                                                         const ShardPull* __restrict__ pull) {
+  for (int seg = 0; seg < 6; seg++) {
+    const ShardPull& q = pull[seg >> 1];
+    const uint32_t n = (seg & 1) ? q.n_content : q.n_sizes;
+    const uint8_t* src = payload + ((seg & 1) ? q.src_content : q.src_sizes);
+    uint8_t* dst = local + ((seg & 1) ? q.dst_content : q.dst_sizes);
+    const uint32_t slices = (n + kSmCopySegment - 1) / kSmCopySegment;
+    for (uint32_t sl = blockIdx.x; sl < slices; sl += gridDim.x) {
+      const uint32_t off = sl * kSmCopySegment;
+      const uint32_t cnt = n - off < kSmCopySegment ? n - off : kSmCopySegment;
+      copy_global_to_global_v4(dst + off, src + off, cnt, 256, threadIdx.x);
+    }
+  }
+}
+
+// the decoded band's three planes into the root's frame: 128-bit stores over NVLink by the SMs (one launch, where three
+// peer copies through the copy engines cost three host-side submissions per image)
+struct ShardPush {
+  uint64_t src[3], dst[3], n[3];
+};
+__global__ void __launch_bounds__(256) shard_push_kernel(const uint8_t* __restrict__ band, uint8_t* __restrict__ frame, const __grid_constant__ ShardPush Q) {
+  for (int p = 0; p < 3; p++) {
+    const uint64_t slices = (Q.n[p] + kSmCopySegment - 1) / kSmCopySegment;
+    for (uint64_t sl = blockIdx.x; sl < slices; sl += gridDim.x) {
+      const uint64_t off = sl * kSmCopySegment;
+      const uint32_t cnt = (uint32_t)(Q.n[p] - off < kSmCopySegment ? Q.n[p] - off : kSmCopySegment);
+      copy_global_to_global_v4(frame + Q.dst[p] + off, band + Q.src[p] + off, cnt, 256, threadIdx.x);
+    }
+  }
+}
+void launch_shard_push(const uint8_t* d_band, uint8_t* root_frame, uint32_t w, uint32_t h, uint32_t y0, uint32_t y1, cudaStream_t s) {
+  shard_preload();
+  const uint64_t bh = y1 - y0;
+  ShardPush Q;
+  Q.src[0] = 0; Q.src[1] = bh * w; Q.src[2] = bh * w * 5 / 4;
+  Q.dst[0] = (uint64_t)y0 * w; Q.dst[1] = (uint64_t)w * h + (uint64_t)(y0 / 2) * (w / 2); Q.dst[2] = (uint64_t)w * h * 5 / 4 + (uint64_t)(y0 / 2) * (w / 2);
+  Q.n[0] = bh * w; Q.n[1] = Q.n[2] = bh * w / 4;
+  shard_push_kernel<<<148 * 4, 256, 0, s>>>(d_band, root_frame, Q);
+  g_launches++;
+}
+
 void launch_decompress_shard(const uint8_t* payload, uint64_t payload_size, const FrameGeom& g, const uint32_t nblk_full[3],
-                             const uint32_t k_lo[3], const QTables& qt, uint8_t* d_band, const ShardPeers& peers, const Workspace& ws,
-                             cudaStream_t s) {
+                             const uint32_t k_lo[3], const QTables& qt, uint8_t* d_band, uint8_t* d_local, const ShardPeers& peers,
+                             const Workspace& ws, cudaStream_t s) {
   shard_preload();
   DecParams P;
   P.payloads = payload; P.offsets = nullptr; P.dst = d_band; P.g = g; P.ws = ws;
@@ -1876,18 +1977,22 @@ void launch_decompress_shard(const uint8_t* payload, uint64_t payload_size, cons
     attr_set = true;
   }
   ShardBand B;
-  for (int p = 0; p < 3; p++) { B.nblk_full[p] = nblk_full[p]; B.k_lo[p] = k_lo[p]; }
+  for (int p = 0; p < 3; p++) { B.nblk_full[p] = nblk_full[p]; B.k_lo[p] = k_lo[p]; B.nb[p] = g.nblk[p]; }
+  ShardPull* pull = reinterpret_cast<ShardPull*>(ws.plane_start);  // 3 records in the encoder's plane-start array (always allocated, unused when decoding)
+  static_assert(3 * sizeof(ShardPull) <= 256, "fits the slack every workspace buffer is allocated with");
   cudaMemsetAsync(ws.counters, 0, 4, s);
   if (ws.k_begin) cudaEventRecord(ws.k_begin, s);
-  shard_dec_prepare_kernel<<<3, 1024, 0, s>>>(P, payload_size, B, peers);
+  shard_dec_prepare_kernel<<<3, 1024, 0, s>>>(P, payload_size, B, pull, peers);
   g_launches++;
   if (P.total_tiles) {
+    shard_pull_kernel<<<148 * 8, 256, 0, s>>>(payload, d_local, pull);
+    P.payloads = d_local;  // the descriptors refer to the local copy
     const uint32_t want = (P.total_tiles + 7) / 8;
     dec_tile_totals_kernel<<<want < 148u * 8 ? want : 148u * 8, 256, 0, s>>>(P);
     dec_scan_planes_kernel<<<3, 1024, 0, s>>>(P);
     const int grid = (int)(P.total_tiles < (uint32_t)ws.grid ? P.total_tiles : (uint32_t)ws.grid);
     dct_decompress_kernel<<<grid, kCtaThreads, sizeof(DecSmem), s>>>(P, qt);
-    g_launches += 3;
+    g_launches += 4;
   }
   if (ws.k_end) cudaEventRecord(ws.k_end, s);
 }
@@ -1901,6 +2006,8 @@ void shard_preload() {
   cudaFuncGetAttributes(&a, shard_exchange_kernel);
   cudaFuncGetAttributes(&a, shard_done_kernel);
   cudaFuncGetAttributes(&a, shard_dec_prepare_kernel);
+  cudaFuncGetAttributes(&a, shard_pull_kernel);
+  cudaFuncGetAttributes(&a, shard_push_kernel);
   cudaFuncGetAttributes(&a, dct_compress_kernel);
   cudaFuncGetAttributes(&a, heavy_blocks_kernel<32>);
   cudaFuncGetAttributes(&a, heavy_blocks_kernel<64>);
@@ -1944,7 +2051,6 @@ void launch_decompress(const uint8_t* d_payloads, const uint64_t* d_offsets, con
 // engines serve one transfer per direction at a time in order of arrival, so a small transfer issued next to another
 // context's large ones waits for everything queued ahead of it; loads and stores issued by a kernel share the link with
 // the engine's traffic instead of queueing behind it.
-constexpr uint32_t kSmCopySegment = 32u << 10;
 __global__ void __launch_bounds__(256) sm_copy_kernel(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint64_t bytes) {
   const uint64_t nseg = (bytes + kSmCopySegment - 1) / kSmCopySegment;
   for (uint64_t seg = blockIdx.x; seg < nseg; seg += gridDim.x) {

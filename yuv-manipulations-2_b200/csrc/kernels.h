@@ -115,10 +115,13 @@ int codec_grid_size(int device, bool encoder);
 // buffer; shard_done_kernel reports to the root, which waits for all bands.  Everything is stream ordered: no host round trip.
 void launch_compress_shard(const uint8_t* d_iyuv, const FrameGeom& g, const uint32_t nblk_full[3], const QTables& qt, uint8_t* out,
                            uint64_t out_cap, const ShardPeers& peers, const Workspace& ws, cudaStream_t s);
-// Decoding side: payload = the root's payload buffer as mapped here; the band is decoded into d_band (band geometry g).
+// Decoding side: payload = the root's payload buffer as mapped here; the band's part of it is pulled into d_local
+// (256 bytes per block of the band) and decoded into d_band (band geometry g).
 void launch_decompress_shard(const uint8_t* payload, uint64_t payload_size, const FrameGeom& g, const uint32_t nblk_full[3],
-                             const uint32_t k_lo[3], const QTables& qt, uint8_t* d_band, const ShardPeers& peers, const Workspace& ws,
-                             cudaStream_t s);
+                             const uint32_t k_lo[3], const QTables& qt, uint8_t* d_band, uint8_t* d_local, const ShardPeers& peers,
+                             const Workspace& ws, cudaStream_t s);
+// the decoded band (an image of its own) into rows [y0, y1) of the root's w x h frame
+void launch_shard_push(const uint8_t* d_band, uint8_t* root_frame, uint32_t w, uint32_t h, uint32_t y0, uint32_t y1, cudaStream_t s);
 // last kernel of a sharded call: tells the root that this rank's part of `epoch` is in place; on the root, waits for all ranks
 void launch_shard_done(const ShardPeers& peers, const Workspace& ws, uint64_t total_if_known, cudaStream_t s);
 void launch_shard_go(const ShardPeers& peers, cudaStream_t s);  // root only, first kernel of its call
