@@ -62,6 +62,11 @@ MYYUVB_API void* myyuvb_stream(myyuvb_ctx* ctx);
  * Synchronises. */
 MYYUVB_API int myyuvb_last_kernel_ms(myyuvb_ctx* ctx, float* ms);
 
+/* Which build of the coding kernel compress launches use on this context: 0 (default) chooses from the share of detailed
+ * blocks in the previous launch, 1 always queues blocks with more than 8 distinct symbols for the heavy-block kernels,
+ * 2 codes up to 15 symbols in place.  A performance knob only: the bytes produced are identical in every mode. */
+MYYUVB_API int myyuvb_set_encoder_mode(myyuvb_ctx* ctx, int mode);
+
 /* Upper bound of a compressed payload for one w x h IYUV frame (a chunk is at most 255 bytes because
  * its size is stored in a uint8, DCT.cpp:19,310). */
 MYYUVB_API uint64_t myyuvb_compress_bound(uint32_t width, uint32_t height);

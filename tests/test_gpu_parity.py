@@ -138,6 +138,51 @@ def test_batch_with_deferred_blocks(ctx, ora, synth, pkg, q):
         assert np.array_equal(d_back[i].cpu().numpy(), ora.decompress(out[off[i]: off[i + 1]], w, h, q))
 
 
+def test_encoder_builds_produce_the_same_bytes(pkg, ora, synth):
+    """The coding kernel exists in two builds (queue blocks above 8 symbols / code up to 15 in place, kernels.cu); which one a
+    launch uses is a performance choice made from the previous launch's statistics and must never show in the bytes.  Mixed
+    content (smooth frames with noisy stripes: blocks of 1..64 symbols) under both forced modes and under the automatic
+    mode while it switches (three launches of detailed content, then three of smooth content)."""
+    torch = pytest.importorskip("torch")
+    w, h, n, q = 512, 256, 3, (75, 75, 75)
+    rng = np.random.default_rng(12)
+    mixed = frames(synth, w, h, n, first=2).copy()
+    for i in range(n):
+        Y = mixed[i, : w * h].reshape(h, w)
+        Y[:, 32 * i: 32 * i + 200] = rng.integers(0, 256, (h, 200), dtype=np.uint8)
+        Y[64:128, :] = (Y[64:128, :].astype(np.int32) + rng.integers(-20, 21, (64, w))).clip(0, 255).astype(np.uint8)
+    smooth = synth.iyuv_frames_numpy(w, h, n, first=9, noise=False)
+    cap = pkg.capi.compress_bound(w, h) * n
+    c = pkg.Context(0)
+    try:
+        d_out = torch.empty(cap, dtype=torch.uint8, device="cuda")
+        d_off = torch.empty(n + 1, dtype=torch.int64, device="cuda")
+
+        def run(host):
+            d_in = torch.from_numpy(host).cuda()
+            torch.cuda.synchronize()
+            c.compress_batch_dev(d_in, w, h, q, n, d_out, cap, d_off)
+            c.batch_status()
+            off = d_off.cpu().numpy()
+            out = d_out.cpu().numpy()
+            return [out[off[i]: off[i + 1]].copy() for i in range(n)]
+
+        want_mixed = [ora.compress(mixed[i], w, h, q) for i in range(n)]
+        want_smooth = [ora.compress(smooth[i], w, h, q) for i in range(n)]
+        for mode in (1, 2):
+            c.set_encoder_mode(mode)
+            for got, want in zip(run(mixed), want_mixed):
+                assert np.array_equal(got, want), f"mode {mode}"
+            for got, want in zip(run(smooth), want_smooth):
+                assert np.array_equal(got, want), f"mode {mode}"
+        c.set_encoder_mode(0)
+        for host, want in [(mixed, want_mixed)] * 3 + [(smooth, want_smooth)] * 3 + [(mixed, want_mixed)]:
+            for got, wnt in zip(run(host), want):
+                assert np.array_equal(got, wnt)
+    finally:
+        c.close()
+
+
 def test_flat_frames_all_zero_blocks(ctx, ora):
     w, h = 64, 48 * 2  # 6144 px
     for level in (0, 128, 255):

@@ -27,7 +27,7 @@ EXPORTS = [
     "myyuvb_host_alloc", "myyuvb_host_free", "myyuvb_launch_count", "myyuvb_last_kernel_ms",
     "myyuvb_dct_compress_begin", "myyuvb_dct_compress_fetch", "myyuvb_phase_clocks",
     "myyuvb_shard_ctrl_bytes", "myyuvb_shard_rows", "myyuvb_dct_compress_shard_dev", "myyuvb_dct_decompress_shard_dev",
-    "myyuvb_shard_result", "myyuvb_ipc_alloc", "myyuvb_ipc_open", "myyuvb_ipc_close", "myyuvb_ipc_free",
+    "myyuvb_set_encoder_mode", "myyuvb_shard_result", "myyuvb_ipc_alloc", "myyuvb_ipc_open", "myyuvb_ipc_close", "myyuvb_ipc_free",
 ]
 
 
@@ -94,6 +94,7 @@ def lib() -> C.CDLL:
     L.myyuvb_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     L.myyuvb_phase_clocks.argtypes = [C.c_void_p, C.c_int]
     L.myyuvb_phase_clocks.restype = None
+    L.myyuvb_set_encoder_mode.argtypes = [C.c_void_p, C.c_int]
     L.myyuvb_shard_ctrl_bytes.restype = C.c_uint64
     L.myyuvb_shard_rows.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]
     L.myyuvb_dct_compress_shard_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, _u8p, C.c_uint32, C.c_uint32,
@@ -214,6 +215,10 @@ class Context:
 
     def sync(self):
         _check(lib().myyuvb_sync(self._h))
+
+    def set_encoder_mode(self, mode: int) -> None:
+        """0: automatic, 1: queue blocks with more than 8 symbols, 2: code up to 15 symbols in place (same bytes either way)."""
+        _check(lib().myyuvb_set_encoder_mode(self._h, mode))
 
     @property
     def stream(self) -> int:

@@ -544,8 +544,7 @@ MYB_HD void huff_emit(Z& z, const HuffPlan& pl, const HuffScratch<CAP, STRIDE>& 
 // Every loop over slots is unrolled with a warp-uniform guard (k < warp maximum of n), so a warp of 4-symbol blocks
 // does not pay for the capacity.
 // ---------------------------------------------------------------------------------------------------
-constexpr int kFastCap = 15;   // distinct symbols of the fast path = what huff_hist accepts
-constexpr int kHistCap = kFastCap;
+constexpr int kFastCap = 15;   // distinct symbols of the fast path = the most huff_hist counts
 template <int STRIDE>
 struct FastScratch {
   uint32_t* sc;    // [16][STRIDE] + lane: symbol << 16 | occurrences, slots in first-occurrence order; after the code
@@ -566,16 +565,26 @@ struct FastScratch {
 // raw(i) / setraw(i, w).  A coefficient needs 11 bits, so the slot of its value is written into bits 11..14 of
 // the same word and the value stays readable (sign-extend the low 11 bits) for the code that takes over when
 // the block has more symbols than this path handles.
-// Returns the number of distinct symbols, or -1 when there are more than kHistCap.  Idle lanes pass live = false
-// and get 0.
-template <int STRIDE, class Z, class W>
-MYB_HD int huff_hist(Z& z, int L, bool live, const FastScratch<STRIDE>& F, const W& warp) {
-  int n = 0;
+// Returns the number of distinct symbols, or -1 when there are more than CAP (<= kFastCap; a lane stops counting at
+// symbol number CAP + 1, and the loop ends once every lane of the warp has either finished or stopped).  Idle lanes pass
+// live = false and get 0.
+// st: where the count stands.  A lane that stopped at CAP + 1 symbols can be taken up again with a larger CAP (the tile
+// pass counts to 8 first and goes on to 15 only in tiles that code their detailed blocks in place).
+struct HistState {
+  int n = 0;     // distinct symbols so far
+  int next = 0;  // first message position not counted yet
+};
+template <int CAP, int STRIDE, class Z, class W>
+MYB_HD int huff_hist(Z& z, int L, bool live, const FastScratch<STRIDE>& F, const W& warp, HistState& st) {
+  static_assert(CAP <= kFastCap, "slot numbers are 4 bits");
+  int n = st.n, next = st.next;
   if (!live) L = 0;
   const int Lw = warp.max(L);
+  const int first = -warp.max(-(next < L ? next : Lw));  // the earliest position any lane still has to count
   MYB_NOUNROLL
-  for (int i = 0; i < Lw; i++) {
-    if (i < L && n <= kHistCap) {
+  for (int i = first; i < Lw; i++) {
+    if (((i - first) & 3) == 3 && !warp.any(i < L && n <= CAP)) break;
+    if (i >= next && i < L && n <= CAP) {
       const uint32_t raw = z.raw(i);
       const uint32_t tag = raw & 0x7ffu;
       uint32_t h = raw & 31u;
@@ -594,6 +603,7 @@ MYB_HD int huff_hist(Z& z, int L, bool live, const FastScratch<STRIDE>& F, const
       F.slot((int)s) = word + 1u;
       n += isnew ? 1 : 0;
       z.setraw(i, tag | (s << 11));
+      next = i + 1;
     }
     warp.sync();
   }
@@ -602,7 +612,14 @@ MYB_HD int huff_hist(Z& z, int L, bool live, const FastScratch<STRIDE>& F, const
     z.setraw(0, 0u);
     n = 1;
   }
-  return n > kHistCap ? -1 : n;
+  st.n = n;
+  st.next = next;
+  return n > CAP ? -1 : n;
+}
+template <int CAP, int STRIDE, class Z, class W>
+MYB_HD int huff_hist(Z& z, int L, bool live, const FastScratch<STRIDE>& F, const W& warp) {
+  HistState st;
+  return huff_hist<CAP>(z, L, live, F, warp, st);
 }
 
 struct FastPlan {

@@ -124,12 +124,14 @@ struct myyuvb_ctx {
   int grid = 0, grid_dec = 0;
   Buffer d_in, d_out, d_plane_start, d_counters, d_sizes, d_overflow, d_desc, d_offsets;
   Buffer d_scratch, d_tile_pos, d_tile_total, d_tile_prefix;
-  Buffer d_heavy_rec, d_heavy_coef, d_heavy_bytes, d_block_slot, d_heavy_list;
+  Buffer d_heavy_rec, d_heavy_coef, d_heavy_bytes, d_block_slot, d_heavy_list, d_heavy_list2;
   Buffer h_small, h_stage_in, h_stage_out, h_ring;
   cudaEvent_t ring_ev[4] = {nullptr, nullptr, nullptr, nullptr};  // one per slot of h_ring (pageable <-> device staging)
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t kev[2] = {nullptr, nullptr};  // timing events around the last main codec kernel
   uint64_t pending_payload = 0;             // bytes of the payload myyuvb_dct_compress_begin left in d_out
+  int enc_mode = 0;                         // 0: choose the coding kernel's build from the last launch's queue share, 1: queue, 2: in place
+  int enc_in_place = 0;                     // the current choice in mode 0
   myyuvb_ctx() { h_small.pinned = h_stage_in.pinned = h_stage_out.pinned = h_ring.pinned = true; }
 };
 
@@ -153,15 +155,17 @@ int ensure_workspace(myyuvb_ctx* c, const FrameGeom& g, bool encoder, Workspace*
     if ((rc = c->d_tile_pos.reserve(tiles * 8))) return rc;
     if ((rc = c->d_tile_total.reserve(tiles * 4))) return rc;
     if ((rc = c->d_tile_prefix.reserve(tiles * 8))) return rc;
-    // queue of blocks with more than 15 distinct symbols: room for one block in eight (beyond that they are coded in place)
+    // queue of blocks with more than 8 distinct symbols: room for every second block (beyond that they are coded in place);
+    // natural content queues 10 % of its blocks at q 50 and 29 % at q 90, 404 bytes of device memory per slot
     const uint64_t nblk_total = (uint64_t)g.nblk_frame * g.n_frames;
-    ws->heavy_cap = nblk_total < 0xfffffff0ull ? (uint32_t)std::max<uint64_t>(1024, nblk_total / 8) : 0u;
+    ws->heavy_cap = nblk_total < 0xfffffff0ull ? (uint32_t)std::max<uint64_t>(1024, nblk_total / 2) : 0u;
     if (ws->heavy_cap) {
       if ((rc = c->d_heavy_rec.reserve((uint64_t)ws->heavy_cap * 16))) return rc;
       if ((rc = c->d_heavy_coef.reserve((uint64_t)ws->heavy_cap * 128))) return rc;
       if ((rc = c->d_heavy_bytes.reserve((uint64_t)ws->heavy_cap * 256))) return rc;
       if ((rc = c->d_block_slot.reserve(nblk_total * 4))) return rc;
       if ((rc = c->d_heavy_list.reserve((uint64_t)ws->heavy_cap * 4))) return rc;
+      if ((rc = c->d_heavy_list2.reserve((uint64_t)ws->heavy_cap * 4))) return rc;
     }
   } else {
     if ((rc = c->d_desc.reserve((uint64_t)g.n_frames * 3 * sizeof(PlaneDesc)))) return rc;
@@ -182,8 +186,32 @@ int ensure_workspace(myyuvb_ctx* c, const FrameGeom& g, bool encoder, Workspace*
   ws->heavy_bytes = c->d_heavy_bytes.as<uint8_t>();
   ws->block_slot = c->d_block_slot.as<uint32_t>();
   ws->heavy_list = c->d_heavy_list.as<uint32_t>();
+  ws->heavy_list2 = c->d_heavy_list2.as<uint32_t>();
   if (!encoder) ws->heavy_cap = 0;
   ws->plane_desc = c->d_desc.p;
+  ws->code_in_place = 0;
+  ws->queue_stats = nullptr;
+  if (encoder) {
+    // Which build of the coding kernel: blocks with more than 8 symbols are queued unless more than 30 % of the blocks of the
+    // previous launch on this context were of that kind (content that is detailed throughout: queueing would only add
+    // traffic); below 20 % it goes back.  Every launch reports its count into mapped host memory, read here without any
+    // wait -- a stale value only delays the switch by a launch, and the bytes produced are the same either way.
+    if ((rc = c->h_small.reserve(256 + 64))) return rc;
+    volatile uint32_t* st = c->h_small.as<uint32_t>() + 32;  // bytes 128..135 of the small pinned block
+    if (c->enc_mode == 0) {
+      const uint32_t queued = st[0], blocks = st[1];  // blocks with more than 8 symbols, all blocks
+      if (blocks) {
+        if ((uint64_t)queued * 10 > (uint64_t)blocks * 3) c->enc_in_place = 1;
+        else if ((uint64_t)queued * 10 < (uint64_t)blocks * 2) c->enc_in_place = 0;
+      }
+    } else {
+      c->enc_in_place = c->enc_mode == 2;
+    }
+    ws->code_in_place = c->enc_in_place;
+    uint32_t* st_dev = nullptr;
+    CU(cudaHostGetDevicePointer(reinterpret_cast<void**>(&st_dev), c->h_small.as<uint32_t>() + 32, 0));
+    ws->queue_stats = st_dev;
+  }
   ws->grid = encoder ? c->grid : c->grid_dec;
   ws->k_begin = c->kev[0];
   ws->k_end = c->kev[1];
@@ -389,7 +417,7 @@ void myyuvb_ctx_destroy(myyuvb_ctx* c) {
   if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
   if (c->d2h_stream) cudaStreamSynchronize(c->d2h_stream);
   for (Buffer* b : {&c->d_in, &c->d_out, &c->d_plane_start, &c->d_counters, &c->d_sizes,
-                    &c->d_overflow, &c->d_desc, &c->d_offsets, &c->d_scratch, &c->d_tile_pos, &c->d_tile_total, &c->d_tile_prefix, &c->d_heavy_rec, &c->d_heavy_coef, &c->d_heavy_bytes, &c->d_block_slot, &c->d_heavy_list, &c->h_small, &c->h_stage_in, &c->h_stage_out, &c->h_ring})
+                    &c->d_overflow, &c->d_desc, &c->d_offsets, &c->d_scratch, &c->d_tile_pos, &c->d_tile_total, &c->d_tile_prefix, &c->d_heavy_rec, &c->d_heavy_coef, &c->d_heavy_bytes, &c->d_block_slot, &c->d_heavy_list, &c->d_heavy_list2, &c->h_small, &c->h_stage_in, &c->h_stage_out, &c->h_ring})
     b->release();
   for (auto& ev : c->ev)
     if (ev) cudaEventDestroy(ev);
@@ -412,6 +440,13 @@ int myyuvb_sync(myyuvb_ctx* c) {
 }
 
 void* myyuvb_stream(myyuvb_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+int myyuvb_set_encoder_mode(myyuvb_ctx* c, int mode) {
+  if (!c || mode < 0 || mode > 2) return fail(MYYUVB_ERR_ARG, "myyuvb_set_encoder_mode: mode must be 0, 1 or 2");
+  c->enc_mode = mode;
+  if (mode) c->enc_in_place = mode == 2;
+  return MYYUVB_OK;
+}
 
 int myyuvb_last_kernel_ms(myyuvb_ctx* c, float* ms) {
   if (!c || !ms) return fail(MYYUVB_ERR_ARG, "null argument");

@@ -24,6 +24,7 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "block_codec.cuh"
 
@@ -532,6 +533,7 @@ constexpr int kStageBytes = 3 * 1024;                  // shared-memory staging 
 // Blocks with more than 15 distinct symbols send their warp through the general code on per-thread local memory.
 using BigScratch = HuffScratch<64, 1>;
 using F8Scratch = FastScratch<32>;
+constexpr int kTileCap = 8;    // distinct symbols per block the compact fast-path instantiation takes
 constexpr int kWarpScratchBytes = 4096;
 
 struct EncSmem {
@@ -658,6 +660,19 @@ MYB_D int fdct_quant_block(const uint32_t (&raw)[16], const QTables& qt, int pla
   return L;
 }
 
+// Two builds of the kernel, chosen per launch (EncParams has no say in it: the choice only moves work, never bytes):
+//   kInPlace = false  the tile pass codes blocks of up to 8 distinct symbols and QUEUES the rest.  The lanes of a warp run
+//                     in lockstep and the warps of a CTA meet at barriers, so a tile takes as long as its most expensive
+//                     block: with the few detailed blocks of a natural image coded in place, three of the four warps of
+//                     a tile sat at the barrier for a third of the kernel's time (profiles/r02_notes.md).  Queued blocks
+//                     -- coefficient words, block index, message length -- are coded by kernels whose warps are all of
+//                     the expensive kind (heavy15_kernel: the 15-symbol fast path; heavy_blocks_kernel: the general
+//                     code); here they count as empty chunks.  Only the compact fast-path instantiation is compiled in.
+//   kInPlace = true   for content whose blocks are all detailed (synthetic frames at q 90, noise): tiles are homogeneous,
+//                     queueing half of all blocks only costs traffic.  Up to 15 symbols are coded in place by the
+//                     fast-path instantiation that fits the warp, blocks with more are queued.
+// capi.cu picks the build from the share of blocks the previous launch on the context queued.
+template <bool kInPlace>
 __global__ void __launch_bounds__(kCtaThreads, 6)
     dct_compress_kernel(const __grid_constant__ EncParams P, const __grid_constant__ QTables qt) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -756,13 +771,12 @@ __global__ void __launch_bounds__(kCtaThreads, 6)
         for (int j = 0; j < 4; j++) q[lane + 32 * j] = make_uint4(~0u, ~0u, ~0u, ~0u);
       }
       __syncwarp();
-      int nsym = huff_hist(zm, L, mlive, f8, WarpLockstep{});
+      int nsym = huff_hist<kInPlace ? kFastCap : kTileCap>(zm, L, mlive, f8, WarpLockstep{});
+      {  // statistics for the choice of build: blocks with more than kTileCap symbols
+        const uint32_t dm = __ballot_sync(0xffffffffu, nsym < 0 || nsym > kTileCap);
+        if (dm != 0u && lane == 0) atomicAdd(&P.ws.counters[8], (uint32_t)__popc(dm));
+      }
       PH(3);  // histogram
-      // Blocks with more than 15 distinct symbols (0.5 % of the luma blocks of natural images at q 50, every block of
-      // noise at q 100) do not fit the fast path.  Coding one of them in place would send the whole warp through the
-      // general code for it, so they are queued -- coefficient words, block index, message length -- and coded 32 at a
-      // time by heavy_blocks_kernel; here they count as empty chunks.  When the queue is full the warp falls back to
-      // the general code in place.
       bool fast = true;
       uint32_t hslot = 0xffffffffu;
       const uint32_t hmask = __ballot_sync(0xffffffffu, nsym < 0);
@@ -794,8 +808,10 @@ __global__ void __launch_bounds__(kCtaThreads, 6)
       int16_t lsyms[BigScratch::kSyms];
       BigScratch bs{lbytes, lsyms};
       uint32_t size;
+      const int nw = __reduce_max_sync(0xffffffffu, nsym);
       if (__builtin_expect(fast, 1)) {
-        pl8 = huff_fast_plan(nsym, L == 0 ? 1 : L, f8, WarpLockstep{});
+        if (kInPlace) pl8 = huff_fast_plan(nsym, L == 0 ? 1 : L, f8, WarpLockstep{});
+        else pl8 = huff_fast_plan_n<kTileCap>(nsym, nw, L == 0 ? 1 : L, f8, WarpLockstep{});
         size = (uint32_t)pl8.size();
       } else {
         // the whole warp runs the general code in lockstep on per-thread local-memory scratch (all lanes touch the same
@@ -859,7 +875,8 @@ __global__ void __launch_bounds__(kCtaThreads, 6)
         // first chunk that does not fit the shared staging buffer (chunks never straddle; offsets only grow)
         if (mlive && !fits && off <= (uint32_t)kStageBytes) atomicMin(&sm.split, off);
         if (__builtin_expect(fast, 1)) {
-          huff_fast_emit(zm, pl8, f8, dst, WarpLockstep{});
+          if (kInPlace) huff_fast_emit(zm, pl8, f8, dst, WarpLockstep{});
+          else huff_fast_emit_n<kTileCap>(zm, pl8, nw, f8, dst, WarpLockstep{});
         } else {
           HuffPlan plf = pl;
           if (!mlive) plf.n = 0;
@@ -891,6 +908,65 @@ __global__ void __launch_bounds__(kCtaThreads, 6)
 // coefficients are read from the queue in global memory instead of being staged, slot numbers take a byte each, the
 // value table lies over weights + parent links; 9 CTAs of 64 threads per SM) takes every queued block and passes the
 // few with more than 32 distinct symbols on, through a list, to CAP = 64 (645 bytes per block, 5 CTAs per SM).
+// Pass 1a: the queued blocks through the 15-symbol fast path (everything up to 15 distinct symbols: all queued blocks of
+// natural content at q 50 but 0.4 %).  One thread per queued block, 32 per warp, no CTA barrier: every warp of this kernel is
+// busy with blocks of the expensive kind, which is the point of queueing them.  Coefficient words come from the queue
+// (they may carry slot bits of the tile pass's attempt: masked off), the chunk goes to the block's 256-byte slot.  Blocks
+// with more than 15 symbols are listed for heavy_blocks_kernel.
+struct Heavy15Smem {
+  uint16_t zz[64][kCtaThreads];
+  alignas(16) uint8_t coder[kCtaThreads / 32][kWarpScratchBytes];
+};
+__global__ void __launch_bounds__(kCtaThreads, 7) heavy15_kernel(const __grid_constant__ EncParams P, uint32_t* __restrict__ overflow) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  Heavy15Smem& sm = *reinterpret_cast<Heavy15Smem*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31;
+  uint8_t* const wbase = sm.coder[tid >> 5];
+  F8Scratch f8{reinterpret_cast<uint32_t*>(wbase) + lane, wbase + 2048, lane};
+  ZShared z{&sm.zz[0][tid]};
+  const uint32_t queued = P.ws.counters[4];
+  const uint32_t count = queued < P.ws.heavy_cap ? queued : P.ws.heavy_cap;
+  for (uint32_t g0 = blockIdx.x * kCtaThreads; g0 < count; g0 += gridDim.x * kCtaThreads) {
+    const uint32_t idx = g0 + tid;
+    uint4 rec = make_uint4(0xffffffffu, 0u, 0u, 0u);
+    if (idx < count) rec = P.ws.heavy_rec[idx];
+    const bool live = rec.x != 0xffffffffu;  // a warp that found the queue full leaves its reservation unused
+    {
+      const uint4* src = reinterpret_cast<const uint4*>(P.ws.heavy_coef + (uint64_t)(live ? idx : 0u) * 64);
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const uint4 v = live ? __ldcs(src + j) : make_uint4(0u, 0u, 0u, 0u);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          // back to the 16-bit two's complement words the histogram starts from (the value is the low 11 bits, sign extended)
+          z.setraw(8 * j + 2 * k, (uint32_t)(((int32_t)(w[k] << 21)) >> 21));
+          z.setraw(8 * j + 2 * k + 1, (uint32_t)(((int32_t)(w[k] << 5)) >> 21));
+        }
+      }
+      uint4* q = reinterpret_cast<uint4*>(wbase + 2048);  // empty the warp's hash table
+#pragma unroll
+      for (int j = 0; j < 4; j++) q[lane + 32 * j] = make_uint4(~0u, ~0u, ~0u, ~0u);
+    }
+    __syncwarp();
+    const int L = live ? (int)rec.z : 0;
+    int nsym = huff_hist<kFastCap>(z, L, live, f8, WarpLockstep{});
+    const bool over = nsym < 0;
+    if (over) {
+      overflow[atomicAdd(&P.ws.counters[5], 1u)] = idx;
+      nsym = 0;
+    }
+    const FastPlan pl = huff_fast_plan(nsym, L == 0 ? 1 : L, f8, WarpLockstep{});
+    huff_fast_emit(z, pl, f8, P.ws.heavy_bytes + (uint64_t)idx * 256, WarpLockstep{});
+    if (live && !over) {
+      const uint32_t size = (uint32_t)pl.size();
+      P.ws.chunk_sizes[rec.x] = (uint8_t)size;
+      atomicAdd(&P.ws.tile_total[rec.y], size);
+    }
+    __syncwarp();
+  }
+}
+
 constexpr int kHeavyThreads = 64;
 template <int CAP>
 struct HeavySmem {
@@ -899,21 +975,21 @@ struct HeavySmem {
   int16_t syms[Scratch::kSyms][kHeavyThreads];
   uint8_t bytes[Scratch::kBytes][kHeavyThreads];
 };
-// list == nullptr: the blocks are the queue slots 0 .. counters[4]; else: the queue slots list[0 .. counters[5]).
-// overflow != nullptr: blocks that do not fit CAP symbols are appended to it (count in counters[5]).
+// The blocks are the queue slots list[0 .. counters[list_counter]).  overflow != nullptr: blocks that do not fit CAP symbols
+// are appended to it (count in counters[7]).
 template <int CAP>
 __global__ void __launch_bounds__(kHeavyThreads) heavy_blocks_kernel(const __grid_constant__ EncParams P, const uint32_t* __restrict__ list,
-                                                                     uint32_t* __restrict__ overflow) {
+                                                                     int list_counter, uint32_t* __restrict__ overflow) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   HeavySmem<CAP>& sm = *reinterpret_cast<HeavySmem<CAP>*>(smem_raw);
-  const uint32_t queued = list ? P.ws.counters[5] : P.ws.counters[4];
+  const uint32_t queued = P.ws.counters[list_counter];
   const uint32_t count = queued < P.ws.heavy_cap ? queued : P.ws.heavy_cap;  // slots past the capacity were never handed out
   typename HeavySmem<CAP>::Scratch bs{&sm.bytes[0][threadIdx.x], &sm.syms[0][threadIdx.x]};
   for (uint32_t g0 = blockIdx.x * kHeavyThreads; g0 < count; g0 += gridDim.x * kHeavyThreads) {
     uint32_t idx = g0 + threadIdx.x;
     uint4 rec = make_uint4(0xffffffffu, 0u, 0u, 0u);
     if (idx < count) {
-      if (list) idx = list[idx];
+      idx = list[idx];
       rec = P.ws.heavy_rec[idx];
     }
     const bool live = rec.x != 0xffffffffu;  // a warp that found the queue full leaves its reservation unused
@@ -921,7 +997,7 @@ __global__ void __launch_bounds__(kHeavyThreads) heavy_blocks_kernel(const __gri
     HuffPlan pl = huff_plan(zv, live ? (int)rec.z : 0, bs, WarpLockstep{});
     __syncwarp();
     const bool fits = pl.n >= 0;
-    if (live && !fits && overflow) overflow[atomicAdd(&P.ws.counters[5], 1u)] = idx;
+    if (live && !fits && overflow) overflow[atomicAdd(&P.ws.counters[7], 1u)] = idx;
     const uint32_t size = live && fits ? (uint32_t)pl.size() : 0u;
     if (!live || !fits) pl.n = 0;
     ZSplitSlots<kHeavyThreads> zs{&sm.slot[0][threadIdx.x]};
@@ -1351,6 +1427,7 @@ __global__ void __launch_bounds__(32) shard_done_kernel(uint32_t* __restrict__ f
 // ranks in one process (virtual ranks on one device) the host would otherwise block inside a launch while the peers it has
 // not issued yet are what the spinning kernel waits for.
 void shard_preload();
+__global__ void publish_queue_stats_kernel(uint32_t* __restrict__ h_dst, const uint32_t* __restrict__ queued, uint32_t blocks);
 __global__ void publish_words_kernel(uint32_t* __restrict__ h_dst, const uint32_t* __restrict__ d_src, uint32_t n);
 
 void launch_shard_go(const ShardPeers& peers, cudaStream_t s) {
@@ -1730,6 +1807,14 @@ __global__ void __launch_bounds__(kCtaThreads, 6)
 // ===================================================================================================
 // launchers
 // ===================================================================================================
+__global__ void publish_queue_stats_kernel(uint32_t* __restrict__ h_dst, const uint32_t* __restrict__ queued, uint32_t blocks) {
+  if (threadIdx.x == 0) {
+    h_dst[0] = *queued;
+    h_dst[1] = blocks;
+    __threadfence_system();
+  }
+}
+
 namespace {
 // code tiles, deferred blocks, the two scans: everything that needs no knowledge of where the payload goes
 void compress_code_and_scan(const EncParams& P, const QTables& qt, cudaStream_t s) {
@@ -1737,28 +1822,38 @@ void compress_code_and_scan(const EncParams& P, const QTables& qt, cudaStream_t 
   const FrameGeom& g = P.g;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(dct_compress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncSmem));
+    cudaFuncSetAttribute(dct_compress_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncSmem));
+    cudaFuncSetAttribute(dct_compress_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncSmem));
     attr_set = true;
   }
   cudaMemsetAsync(ws.counters, 0, 4, s);       // ticket only; error flags accumulate until read
-  cudaMemsetAsync(ws.counters + 2, 0, 20, s);  // scratch bump allocator, queue of deferred blocks, list of those with > 32 symbols, list of tiles with queued blocks
+  cudaMemsetAsync(ws.counters + 2, 0, 28, s);  // scratch bump allocator, queue of deferred blocks, lists of those with > 15 and > 32 symbols, list of tiles with queued blocks
   const int grid = (int)(P.total_tiles < (uint32_t)ws.grid ? P.total_tiles : (uint32_t)ws.grid);
   if (ws.k_begin) cudaEventRecord(ws.k_begin, s);
-  dct_compress_kernel<<<grid, kCtaThreads, sizeof(EncSmem), s>>>(P, qt);
+  if (ws.code_in_place) dct_compress_kernel<true><<<grid, kCtaThreads, sizeof(EncSmem), s>>>(P, qt);
+  else dct_compress_kernel<false><<<grid, kCtaThreads, sizeof(EncSmem), s>>>(P, qt);
   if (ws.heavy_cap) {
     static bool heavy_attr = false;
     if (!heavy_attr) {
+      cudaFuncSetAttribute(heavy15_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Heavy15Smem));
       cudaFuncSetAttribute(heavy_blocks_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HeavySmem<32>));
       cudaFuncSetAttribute(heavy_blocks_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HeavySmem<64>));
       heavy_attr = true;
     }
+    // queue -> heavy15_kernel (fast path, <= 15 symbols) -> list A -> heavy_blocks_kernel<32> -> list B -> <64>
+    const uint32_t fwant = (ws.heavy_cap + kCtaThreads - 1) / kCtaThreads;
+    heavy15_kernel<<<(int)(fwant < 148u * 7 ? fwant : 148u * 7), kCtaThreads, sizeof(Heavy15Smem), s>>>(P, ws.heavy_list);
     const uint32_t hwant = (ws.heavy_cap + kHeavyThreads - 1) / kHeavyThreads;
-    heavy_blocks_kernel<32><<<(int)(hwant < 148u * 9 ? hwant : 148u * 9), kHeavyThreads, sizeof(HeavySmem<32>), s>>>(P, nullptr, ws.heavy_list);
-    heavy_blocks_kernel<64><<<(int)(hwant < 148u * 5 ? hwant : 148u * 5), kHeavyThreads, sizeof(HeavySmem<64>), s>>>(P, ws.heavy_list, nullptr);
+    heavy_blocks_kernel<32><<<(int)(hwant < 148u * 9 ? hwant : 148u * 9), kHeavyThreads, sizeof(HeavySmem<32>), s>>>(P, ws.heavy_list, 5, ws.heavy_list2);
+    heavy_blocks_kernel<64><<<(int)(hwant < 148u * 5 ? hwant : 148u * 5), kHeavyThreads, sizeof(HeavySmem<64>), s>>>(P, ws.heavy_list2, 7, nullptr);
   }
   scan_frame_tiles_kernel<<<g.n_frames, 512, 0, s>>>(P);
   scan_frames_kernel<<<1, 1024, 0, s>>>(P);
-  g_launches += ws.heavy_cap ? 5 : 3;
+  g_launches += ws.heavy_cap ? 6 : 3;
+  if (ws.queue_stats) {  // how many blocks this launch queued, for the next launch's choice of build (mapped host memory, read without a sync)
+    publish_queue_stats_kernel<<<1, 32, 0, s>>>(ws.queue_stats, ws.counters + 8, g.nblk_frame * g.n_frames);
+    g_launches++;
+  }
 }
 
 // tiles to their final place, headers and chunk-size arrays
@@ -2008,7 +2103,10 @@ void shard_preload() {
   cudaFuncGetAttributes(&a, shard_dec_prepare_kernel);
   cudaFuncGetAttributes(&a, shard_pull_kernel);
   cudaFuncGetAttributes(&a, shard_push_kernel);
-  cudaFuncGetAttributes(&a, dct_compress_kernel);
+  cudaFuncGetAttributes(&a, dct_compress_kernel<false>);
+  cudaFuncGetAttributes(&a, dct_compress_kernel<true>);
+  cudaFuncGetAttributes(&a, publish_queue_stats_kernel);
+  cudaFuncGetAttributes(&a, heavy15_kernel);
   cudaFuncGetAttributes(&a, heavy_blocks_kernel<32>);
   cudaFuncGetAttributes(&a, heavy_blocks_kernel<64>);
   cudaFuncGetAttributes(&a, scan_frame_tiles_kernel);

@@ -50,7 +50,8 @@ FrameGeom make_geom(uint32_t width, uint32_t height, uint32_t n_frames, uint32_t
 struct Workspace {
   uint64_t* plane_start;   // [n_frames*3 + 1] code bytes before each plane (compress)
   uint64_t* frame_base;    // [n_frames] code bytes of the batch before each frame (compress)
-  uint32_t* counters;      // [0] tile ticket, [1] error flags, [2..3] u64 scratch bump allocator, [4] deferred blocks
+  uint32_t* counters;      // [0] tile ticket, [1] error flags, [2..3] u64 scratch bump allocator, [4] deferred blocks, [5] of those: more
+                           // than 15 symbols, [6] tiles with deferred blocks, [7] blocks with more than 32 symbols, [8] blocks with more than 8 symbols
   uint8_t* chunk_sizes;    // [n_frames * nblk_frame] per-block chunk size, linear block order (compress)
   uint8_t* overflow;       // [grid * kEncTile * 256] staging overflow area (compress; a chunk is at most 255 bytes)
   uint8_t* scratch;        // [scratch_cap] chunk bytes of all tiles in completion order (compress, pass 1)
@@ -64,9 +65,13 @@ struct Workspace {
   uint16_t* heavy_coef;    // [heavy_cap * 64] the block's coefficient words, zigzag order
   uint8_t* heavy_bytes;    // [heavy_cap * 256] its chunk
   uint32_t* block_slot;    // [blocks of the batch] queue slot of a deferred block, 0xffffffff otherwise
-  uint32_t* heavy_list;    // [heavy_cap] queue slots of the blocks with more than 32 distinct symbols (second pass)
+  uint32_t* heavy_list;    // [heavy_cap] queue slots of the blocks with more than 15 distinct symbols (heavy15_kernel's overflow); later
+                           //             the tiles with queued blocks (place_tiles_kernel)
+  uint32_t* heavy_list2;   // [heavy_cap] queue slots of the blocks with more than 32 distinct symbols
   uint32_t heavy_cap;      // 0: nothing is deferred
   void* plane_desc;        // [n_frames*3] PlaneDesc (decompress)
+  int code_in_place;       // compress: launch the build of dct_compress_kernel that codes up to 15 symbols in place (see kernels.cu)
+  uint32_t* queue_stats;   // compress: device-side address of two mapped host words {blocks queued, blocks} the launch reports, or nullptr
   int grid;                // persistent grid size of the codec kernels
   cudaEvent_t k_begin, k_end;  // recorded around the main codec kernel of each launch (myyuvb_last_kernel_ms)
 };
