@@ -1,0 +1,41 @@
+#!/usr/bin/env python3
+"""Same-box A/B of two builds of the CUDA library (MYYUVB_LIB_VARIANT): compress / decompress launch-sequence times of
+the workloads below, variants alternated, median of 5 per round, 3 rounds.  usage: ab.py variantA variantB   ("" = the product build)"""
+import json, os, subprocess, sys
+CHILD = r'''
+import importlib, json, os, pathlib, struct, sys, statistics
+ROOT = pathlib.Path(sys.argv[1]); sys.path.insert(0, str(ROOT))
+import numpy as np, torch
+pkg = importlib.import_module("yuv-manipulations-2_b200"); synth = importlib.import_module("yuv-manipulations-2_b200.synth")
+W, H = 3840, 2160
+def natural(n):
+    blob = (ROOT / "oracle/_ref/golden/chef-with-trumpet.myyuv").read_bytes()
+    _, _, _, _, _, _, w, h, pos = struct.unpack_from("<2sIIHIIIII", blob, 0)
+    return synth.tiled_real_iyuv(np.frombuffer(blob, np.uint8)[pos: pos + w * h * 3 // 2].copy(), w, h, W, H, n, 0)
+dev = torch.device("cuda", 0); ctx = pkg.Context(0); out = {}
+for name, n in (("ng:50", 64), ("nat:50", 16), ("nat:90", 16), ("ng:90", 16)):
+    content, q = name.split(":"); qq = (int(q),) * 3
+    d_in = synth.iyuv_frames_torch(W, H, n, dev) if content == "ng" else torch.from_numpy(natural(n)).to(dev)
+    cap = n * 20 * 1024 * 1024
+    d_out = torch.empty(cap, dtype=torch.uint8, device=dev); d_off = torch.zeros(n + 1, dtype=torch.int64, device=dev); d_back = torch.empty_like(d_in)
+    torch.cuda.synchronize()
+    c, d = [], []
+    for it in range(7):
+        ctx.compress_batch_dev(d_in, W, H, qq, n, d_out, cap, d_off); c1 = ctx.last_kernel_ms()
+        ctx.decompress_batch_dev(d_out, d_off, W, H, qq, n, d_back); d1 = ctx.last_kernel_ms()
+        if it >= 2: c.append(c1); d.append(d1)
+    ctx.batch_status()
+    out[name] = [round(statistics.median(c), 4), round(statistics.median(d), 4)]
+    del d_in, d_out, d_back
+print(json.dumps(out))
+'''
+root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+res = {v: [] for v in sys.argv[1:3]}
+for rnd in range(3):
+    for v in sys.argv[1:3]:
+        r = subprocess.run([sys.executable, "-c", CHILD, root], env=dict(os.environ, MYYUVB_LIB_VARIANT=v), capture_output=True, text=True)
+        res[v].append(json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0 else {"error": r.stderr[-500:]})
+for v, runs in res.items():
+    print(repr(v))
+    for r in runs:
+        print("   ", r)

@@ -1,6 +1,7 @@
 """The drop-in boundary: the reference's UNMODIFIED myyuv_cli (object compiled from /root/reference/myyuv_cli/main.cpp
 against the reference's own headers, oracle/_ref/myyuv_cli_main.o) linked with this repo's libmyyuv_lib.so."""
 import hashlib
+import os
 import pathlib
 import re
 import subprocess
@@ -131,3 +132,36 @@ def test_cli_converts_24bit_bmp_like_the_reference_cli(synth, tmp_path):
         py = tmp_path / f"py{w_signed}_{h_signed}.myyuv"
         pkg.YUV(pkg.BMP(str(bmp)), pkg.YUV.FourccFormats.IYUV).dump(str(py))
         assert py.read_bytes() == outs[1]
+
+
+@pytest.mark.gpu
+def test_registry_plugin_over_the_unmodified_reference_library(tmp_path):
+    """INTEGRATION.md form B: the reference's own CLI and library, with the three hot-path registry slots overridden by the
+    LD_PRELOADed plugin (csrc/registry_plugin.cpp).  Same process image, slots switched by MYYUVB_PLUGIN: the outputs of
+    the CPU reference and of the sm_100a kernels must be the same files, and both equal the shipped golden files."""
+    ref_cli = ROOT / "oracle" / "_ref" / "serial" / "myyuv_cli"
+    plugin = ROOT / "oracle" / "_ref" / "plugin" / "libmyyuvb200_plugin.so"
+    golden = ROOT / "oracle" / "_ref" / "golden"
+    if not (ref_cli.exists() and plugin.exists() and (golden / "chef-with-trumpet.bmp").exists()):
+        pytest.skip("reference CLI / plugin / golden images not built (make -C oracle ref plugin)")
+
+    def run(tag, on, *args):
+        env = dict(os.environ, LD_PRELOAD=str(plugin), MYYUVB_PLUGIN="1" if on else "0", MYYUVB_PLUGIN_VERBOSE="1")
+        r = subprocess.run([str(ref_cli), *[str(a) for a in args]], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0 and "Success!" in r.stdout, r.stdout + r.stderr
+        assert ("registry slots IYUV / DCT overridden" in r.stderr) == on
+        return r
+
+    outs = {}
+    for on in (False, True):
+        t = "gpu" if on else "cpu"
+        a, b, c, d = (tmp_path / f"{t}_{n}.myyuv" for n in "abcd")
+        run(t, on, golden / "chef-with-trumpet.bmp", "-to_yuv", "IYUV", "-o", a)
+        run(t, on, a, "-compress", "DCT", "50", "-o", b)
+        run(t, on, a, "-compress", "DCT", "90", "20", "75", "-o", c)
+        run(t, on, golden / "chef-with-trumpet-big-DCT-50.myyuv", "-decompress", "-o", d)
+        outs[on] = [p.read_bytes() for p in (a, b, c, d)]
+    assert outs[True] == outs[False]
+    assert outs[True][0] == (golden / "chef-with-trumpet.myyuv").read_bytes()
+    assert outs[True][1] == (golden / "chef-with-trumpet-DCT-50.myyuv").read_bytes()
+    assert hashlib.sha256(outs[True][3]).hexdigest().startswith("5e77691911882")
