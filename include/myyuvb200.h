@@ -44,7 +44,8 @@ enum {
   MYYUVB_ERR_HUFFMAN = 9,       /* "Huffman bad code"                                 Huffman.cpp:121,130,139 */
   MYYUVB_ERR_EVEN = 10,         /* colour conversion needs even width and height      myyuv_yuv.cpp:98       */
   MYYUVB_ERR_TOO_LARGE = 11,    /* sizes do not fit the format's uint32 fields        myyuv_yuv.hpp:20-26    */
-  MYYUVB_ERR_SHARD_TIMEOUT = 12 /* sharded image: a rank of the group never arrived                          */
+  MYYUVB_ERR_SHARD_TIMEOUT = 12,/* sharded image: a rank of the group never arrived                          */
+  MYYUVB_ERR_BOUNDS = 13        /* "Image coordinates are out of bounds"              myyuv_yuv.cpp:171-173  */
 };
 
 typedef struct myyuvb_ctx myyuvb_ctx; /* one device, one stream, reusable device/pinned scratch; not thread-safe
@@ -159,6 +160,29 @@ MYYUVB_API void myyuvb_host_free(void* p);
 
 /* number of kernels this library has launched on this thread's contexts since process start (bench.py's gpu_launches) */
 MYYUVB_API uint64_t myyuvb_launch_count(void);
+
+/* ---- consumers of decoded frames that stay on the device: what the reference's viewers do with
+ * a decoded YUV on the host -- YUV::getYUVPlanes / getWidthHeightChannel (myyuv_yuv.cpp:383-427), YUV::getPixel
+ * (yuv_get_pixel_map[IYUV], :162-180) and the fragment shader's YUV -> RGB (myyuv_opengl/viewer/frag_yuv.glsl:18-26) -- on
+ * device pointers, so that a viewer can hand GPU-decoded frames to the display without a host round trip (register the
+ * plane pointers or the RGBA buffer with cudaGraphicsGLRegisterImage / a pixel-unpack buffer). ---- */
+/* plane pointers and sizes of an IYUV frame at `iyuv` (host or device address; pure arithmetic) */
+MYYUVB_API int myyuvb_iyuv_planes(const uint8_t* iyuv, uint32_t width, uint32_t height, const uint8_t* planes[3],
+                                  uint32_t widths[3], uint32_t heights[3]);
+/* getPixel for n coordinate pairs d_xy = {x0, y0, x1, y1, ...}: d_yuv_out[3 i ..] = {Y, U, V}, with the reference's chroma
+ * index x / 2 + y * width / 4.  Out-of-range coordinates are reported by myyuvb_batch_status as MYYUVB_ERR_BOUNDS. */
+MYYUVB_API int myyuvb_get_pixels_dev(myyuvb_ctx* ctx, const uint8_t* d_iyuv, uint32_t width, uint32_t height, uint32_t n,
+                                     const uint32_t* d_xy, uint8_t* d_yuv_out);
+/* IYUV -> RGBA8 (R, G, B, 255) with the viewer shader's arithmetic, chroma sampled bilinearly at the luma pixel centres;
+ * +-1 LSB of the formula in double precision.  flip_rows != 0: rows bottom-up (GL).  d_rgba: n_frames * w*h*4, 16-byte aligned. */
+MYYUVB_API int myyuvb_iyuv_to_rgba_batch_dev(myyuvb_ctx* ctx, const uint8_t* d_iyuv, uint32_t width, uint32_t height,
+                                             uint32_t n_frames, int flip_rows, uint8_t* d_rgba);
+/* decompress + the conversion above, chunk_frames at a time (0: about 48 MB of IYUV) so that the decoded frames are
+ * converted out of L2; d_iyuv: NULL, or n_frames * w*h*3/2 bytes that receive the decoded frames too. */
+MYYUVB_API int myyuvb_dct_decompress_to_rgba_batch_dev(myyuvb_ctx* ctx, const uint8_t* d_payloads, const uint64_t* d_offsets,
+                                                       uint32_t width, uint32_t height, const uint8_t quality[3],
+                                                       uint32_t n_frames, uint32_t chunk_frames, int flip_rows,
+                                                       uint8_t* d_iyuv, uint8_t* d_rgba);
 
 /* ---- one very large image sharded over the GPUs of one box (the reference has no counterpart:
  * the property that makes it possible is that every 8x8 block is coded on its own and a plane's content is the blocks'

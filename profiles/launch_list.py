@@ -28,12 +28,12 @@ seq = [launches[i] for i in sorted(launches)]
 # ones with the longest coding kernel (the e2e leg runs the same kernels on 2-frame chunks); take the last of those
 steps = []
 for i, k in enumerate(seq):
-    if k["kernel"] != "dct_compress_kernel":
+    if not k["kernel"].startswith("dct_compress_kernel"):
         continue
     j = i + 1
-    while j < len(seq) and seq[j]["kernel"] not in ("dct_compress_kernel", "dct_decompress_kernel"):
+    while j < len(seq) and not seq[j]["kernel"].startswith(("dct_compress_kernel", "dct_decompress_kernel")):
         j += 1
-    if j < len(seq) and seq[j]["kernel"] == "dct_decompress_kernel":
+    if j < len(seq) and seq[j]["kernel"].startswith("dct_decompress_kernel"):
         steps.append((i, j))
 longest = max(seq[i].get("duration_us", 0) for i, _ in steps)
 start, end = [st for st in steps if seq[st[0]].get("duration_us", 0) > 0.9 * longest][-1]
@@ -48,6 +48,19 @@ for k in step:
     print(f'{k["kernel"]:28s} {k.get("duration_us", 0):9.1f} us {100 * k.get("duration_us", 0) / tot:5.1f} %  read {k.get("dram_read_bytes", 0):>12d}  write {k.get("dram_write_bytes", 0):>12d}')
 if len(sys.argv) > 3:
     t = {k["kernel"]: {"dram_read": k.get("dram_read_bytes", 0), "dram_write": k.get("dram_write_bytes", 0), "us": round(k.get("duration_us", 0), 1)}
-         for k in step if k["kernel"] in ("dct_compress_kernel", "dct_decompress_kernel")}
+         for k in step if k["kernel"] in ("dct_compress_kernel", "dct_decompress_kernel")}  # (template arguments are stripped from the names)
     src = "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none, one step of bench.py (" + sys.argv[2] + ")"
-    json.dump({"frames": 64, "source": src, **t}, open(sys.argv[3], "w"), indent=1)
+    # the hash of the kernel sources the capture was taken from: bench.py reports the traffic only for the same sources
+    import hashlib, pathlib
+    h = hashlib.sha256()
+    csrc = pathlib.Path(__file__).resolve().parent.parent / "yuv-manipulations-2_b200" / "csrc"
+    for name in ("kernels.cu", "block_codec.cuh", "kernels.h", "dct_matrix.inc"):
+        h.update((csrc / name).read_bytes())
+    ncu = None
+    if len(sys.argv) > 4:  # summarize_ncu.py output of an `ncu --set full` capture of the two codec kernels
+        full = json.load(open(sys.argv[4]))
+        ncu = {k["kernel"].replace("void ", "").split("<")[0]: {f: k.get(f) for f in ("duration_us", "warp_instructions", "threads_per_instruction",
+               "issue_active_pct", "pipe_alu_pct", "pipe_fma_pct", "pipe_lsu_pct", "warps_active_pct", "icache_hit_pct", "dram_throughput_pct",
+               "stall_samples_pct")} for k in full}
+        ncu["workload"] = sys.argv[5] if len(sys.argv) > 5 else "8 frames"
+    json.dump({"frames": 64, "source": src, "sources_sha256": h.hexdigest(), "ncu": ncu, **t}, open(sys.argv[3], "w"), indent=1)

@@ -40,13 +40,15 @@ def _run(cmd, verbose):
 
 def build_cuda(force: bool = False, verbose: bool = False, variant: str = "") -> pathlib.Path:
     """variant "clk": the same sources with -DMYYUVB_PHASE_CLOCKS (per-phase clock counters in the codec kernels), a
-    profiling build next to the product library, loaded only when MYYUVB_LIB_VARIANT=clk (profiles/phase_clocks.py)."""
+    profiling build next to the product library, loaded only when MYYUVB_LIB_VARIANT=clk (profiles/phase_clocks.py).
+    variant "notma": -DMYYUVB_NO_TMA_STAGE, the decoder's chunk staging as a loop of 128-bit loads instead of the 1-D bulk
+    copy (the A/B in profiles/r02_notes.md)."""
     LIB.mkdir(exist_ok=True)
     out = LIB / ("libmyyuvb200.so" if not variant else f"libmyyuvb200_{variant}.so")
     srcs = [CSRC / "kernels.cu", CSRC / "capi.cu"]
     deps = srcs + [CSRC / "kernels.h", CSRC / "block_codec.cuh", CSRC / "dct_matrix.inc", ROOT / "include/myyuvb200.h"]
     if force or _newer(out, deps):
-        extra = ["-DMYYUVB_PHASE_CLOCKS"] if variant == "clk" else []
+        extra = {"clk": ["-DMYYUVB_PHASE_CLOCKS"], "notma": ["-DMYYUVB_NO_TMA_STAGE"]}.get(variant, [])
         _run([NVCC, *ARCH, "-O3", "-lineinfo", "-std=c++17", "-fmad=false", *extra, "-ccbin", CXX,
               "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden", "--shared", "-o", out, *srcs], verbose)
     return out
@@ -76,7 +78,7 @@ def build(force: bool = False, verbose: bool = False):
 
 
 if __name__ == "__main__":
-    if "--clk" in sys.argv:
-        build_cuda(force="--force" in sys.argv, verbose=True, variant="clk")
+    if "--clk" in sys.argv or "--notma" in sys.argv:
+        build_cuda(force="--force" in sys.argv, verbose=True, variant="clk" if "--clk" in sys.argv else "notma")
     else:
         build(force="--force" in sys.argv, verbose=True)

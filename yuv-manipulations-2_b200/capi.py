@@ -16,7 +16,7 @@ _u64p = C.POINTER(C.c_uint64)
 
 # error codes of include/myyuvb200.h
 OK, ERR_CUDA, ERR_ARG, ERR_QUALITY, ERR_WIDTH, ERR_HEIGHT, ERR_CAPACITY, ERR_DCTYUV_SIZE, ERR_PLANE_SIZE, ERR_HUFFMAN, \
-    ERR_EVEN, ERR_TOO_LARGE, ERR_SHARD_TIMEOUT = range(13)
+    ERR_EVEN, ERR_TOO_LARGE, ERR_SHARD_TIMEOUT, ERR_BOUNDS = range(14)
 
 EXPORTS = [
     "myyuvb_ctx_create", "myyuvb_ctx_destroy", "myyuvb_last_error", "myyuvb_sync", "myyuvb_stream",
@@ -27,7 +27,8 @@ EXPORTS = [
     "myyuvb_host_alloc", "myyuvb_host_free", "myyuvb_launch_count", "myyuvb_last_kernel_ms",
     "myyuvb_dct_compress_begin", "myyuvb_dct_compress_fetch", "myyuvb_phase_clocks",
     "myyuvb_shard_ctrl_bytes", "myyuvb_shard_rows", "myyuvb_dct_compress_shard_dev", "myyuvb_dct_decompress_shard_dev",
-    "myyuvb_set_encoder_mode", "myyuvb_shard_result", "myyuvb_ipc_alloc", "myyuvb_ipc_open", "myyuvb_ipc_close", "myyuvb_ipc_free",
+    "myyuvb_set_encoder_mode", "myyuvb_shard_result", "myyuvb_ipc_alloc",
+    "myyuvb_iyuv_planes", "myyuvb_get_pixels_dev", "myyuvb_iyuv_to_rgba_batch_dev", "myyuvb_dct_decompress_to_rgba_batch_dev", "myyuvb_ipc_open", "myyuvb_ipc_close", "myyuvb_ipc_free",
 ]
 
 
@@ -95,6 +96,11 @@ def lib() -> C.CDLL:
     L.myyuvb_phase_clocks.argtypes = [C.c_void_p, C.c_int]
     L.myyuvb_phase_clocks.restype = None
     L.myyuvb_set_encoder_mode.argtypes = [C.c_void_p, C.c_int]
+    L.myyuvb_iyuv_planes.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    L.myyuvb_get_pixels_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+    L.myyuvb_iyuv_to_rgba_batch_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p]
+    L.myyuvb_dct_decompress_to_rgba_batch_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, _u8p, C.c_uint32,
+                                                          C.c_uint32, C.c_int, C.c_void_p, C.c_void_p]
     L.myyuvb_shard_ctrl_bytes.restype = C.c_uint64
     L.myyuvb_shard_rows.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]
     L.myyuvb_dct_compress_shard_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, _u8p, C.c_uint32, C.c_uint32,
@@ -135,6 +141,14 @@ def phase_clocks(reset: bool = True) -> np.ndarray:
     out = np.zeros(24, np.uint64)
     lib().myyuvb_phase_clocks(out.ctypes.data, int(reset))
     return out.reshape(2, 12)
+
+
+def iyuv_planes(addr: int, w: int, h: int):
+    """[(address, width, height)] of the Y, U, V planes of an IYUV frame at `addr` (host or device)."""
+    pl = (C.c_void_p * 3)()
+    ws, hs = (C.c_uint32 * 3)(), (C.c_uint32 * 3)()
+    _check(lib().myyuvb_iyuv_planes(C.c_void_p(addr), w, h, pl, ws, hs))
+    return [(int(pl[i]), int(ws[i]), int(hs[i])) for i in range(3)]
 
 
 def shard_rows(height: int, world: int):
@@ -304,6 +318,20 @@ class Context:
         _check(lib().myyuvb_xrgb_dct_compress_batch_dev(self._h, _ptr(d_bgrx), w, h, int(bottom_up), qa.ctypes.data_as(_u8p), n_frames,
                                                         chunk_frames, _ptr(d_iyuv) if d_iyuv is not None else None, _ptr(d_out),
                                                         out_capacity, _ptr(d_offsets)))
+
+    # ---- consumers of decoded frames on the device: getPixel, display RGB ----
+    def get_pixels_dev(self, d_iyuv, w: int, h: int, n: int, d_xy, d_out) -> None:
+        _check(lib().myyuvb_get_pixels_dev(self._h, _ptr(d_iyuv), w, h, n, _ptr(d_xy), _ptr(d_out)))
+
+    def iyuv_to_rgba_batch_dev(self, d_iyuv, w: int, h: int, n_frames: int, d_rgba, flip_rows: bool = False) -> None:
+        _check(lib().myyuvb_iyuv_to_rgba_batch_dev(self._h, _ptr(d_iyuv), w, h, n_frames, int(flip_rows), _ptr(d_rgba)))
+
+    def decompress_to_rgba_batch_dev(self, d_payloads, d_offsets, w: int, h: int, q, n_frames: int, d_rgba, d_iyuv=None,
+                                     chunk_frames: int = 0, flip_rows: bool = False) -> None:
+        qa = _q(q)
+        _check(lib().myyuvb_dct_decompress_to_rgba_batch_dev(self._h, _ptr(d_payloads), _ptr(d_offsets), w, h, qa.ctypes.data_as(_u8p), n_frames,
+                                                             chunk_frames, int(flip_rows), _ptr(d_iyuv) if d_iyuv is not None else None,
+                                                             _ptr(d_rgba)))
 
     # ---- one image sharded over the GPUs of a box (see sharding.ShardGroup for the set-up) ----
     def ipc_alloc(self, nbytes: int):

@@ -22,6 +22,20 @@ namespace {
 
 thread_local std::string g_err;
 
+// MYYUVB_TRACE=1: where a call spends its host time (profiles/first_call.py, profiles/cli_timing.py)
+struct TraceScope {
+  const char* what;
+  std::chrono::steady_clock::time_point t0;
+  bool on;
+  explicit TraceScope(const char* w) : what(w), t0(std::chrono::steady_clock::now()) {
+    static const bool trace = getenv("MYYUVB_TRACE") != nullptr;
+    on = trace;
+  }
+  ~TraceScope() {
+    if (on) fprintf(stderr, "[myyuvb] %s: %.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+  }
+};
+
 int fail(int code, const std::string& msg) {
   g_err = msg;
   return code;
@@ -231,6 +245,7 @@ int flags_to_error(uint32_t flags) {
   if (flags & kFlagPlaneSize) return fail(MYYUVB_ERR_PLANE_SIZE, "DCTYUVPlane load bad size");
   if (flags & kFlagHuffman) return fail(MYYUVB_ERR_HUFFMAN, "Huffman bad code");
   if (flags & kFlagShardTimeout) return fail(MYYUVB_ERR_SHARD_TIMEOUT, "shard: a rank of the group did not arrive within 2 s");
+  if (flags & kFlagBounds) return fail(MYYUVB_ERR_BOUNDS, "Image coordinates are out of bounds");
   return MYYUVB_OK;
 }
 
@@ -333,6 +348,7 @@ int small_download(myyuvb_ctx* c, void* h_dst, const void* d_src, size_t bytes, 
 
 int staged_download(myyuvb_ctx* c, void* h_dst, const void* d_src, size_t bytes, cudaStream_t s) {
   if (bytes == 0) return MYYUVB_OK;
+  TraceScope ts("staged_download (issue; ring: whole copy)");
   if (!ring_enabled() || is_pinned_or_device(h_dst) || bytes < (32u << 20))
     return copy_async(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, s);
   int rc;
@@ -381,6 +397,7 @@ int myyuvb_ctx_create(int device, void* stream, myyuvb_ctx** out) {
   if (e != cudaSuccess || count == 0)
     return fail(MYYUVB_ERR_CUDA, std::string("CUDA error: no usable CUDA device (") + cudaGetErrorString(e) + "); this library has no CPU path");
   if (device < 0 || device >= count) return fail(MYYUVB_ERR_ARG, "myyuvb_ctx_create: bad device ordinal");
+  TraceScope ts("ctx_create (CUDA context, streams, events)");
   CU(cudaSetDevice(device));
   myyuvb_ctx* c = new myyuvb_ctx();
   c->device = device;
@@ -628,6 +645,7 @@ int myyuvb_dct_compress_begin(myyuvb_ctx* c, const uint8_t* iyuv, uint32_t w, ui
   if ((rc = check_quality(quality))) return rc;
   if ((rc = check_dims(w, h))) return rc;
   CU(cudaSetDevice(c->device));
+  TraceScope ts("dct_compress_begin");
   c->pending_payload = 0;
   const uint64_t frame_bytes = (uint64_t)w * h * 3 / 2;
   const uint64_t bound = myyuvb_compress_bound(w, h);
@@ -772,6 +790,7 @@ static int decompress_batch_host_impl(myyuvb_ctx* c, const uint8_t* payloads, co
   for (uint32_t f = 0; f < n_frames; f++)
     if (offsets[f + 1] < offsets[f]) return fail(MYYUVB_ERR_ARG, "frame offsets must be non-decreasing");
   CU(cudaSetDevice(c->device));
+  TraceScope ts("decompress_batch_host");
   if ((rc = ensure_copy_streams(c))) return rc;
   const uint64_t frame_bytes = (uint64_t)w * h * 3 / 2;
   const uint32_t per = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(n_frames, host_chunk_bytes() / frame_bytes));
@@ -1009,6 +1028,72 @@ int myyuvb_shard_result(myyuvb_ctx* c, const void* ctrl_local, uint64_t* total_s
   CU(cudaMemcpy(&h, ctrl_local, sizeof(h), cudaMemcpyDeviceToHost));
   if (h.status & kFlagShardTimeout) return fail(MYYUVB_ERR_SHARD_TIMEOUT, "shard: a rank of the group did not arrive within 2 s");
   if (total_size) *total_size = h.total;
+  return MYYUVB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Consumers of decoded frames that stay on the device: plane accessors, getPixel, display RGB
+// ------------------------------------------------------------------------------------------------
+int myyuvb_iyuv_planes(const uint8_t* iyuv, uint32_t w, uint32_t h, const uint8_t* planes[3], uint32_t widths[3], uint32_t heights[3]) {
+  if (!iyuv || !planes) return fail(MYYUVB_ERR_ARG, "null argument");
+  // YUV::getYUVPlanes for IYUV (order Y, U, V; 8 + 2 + 2 bits per pixel, myyuv_yuv.cpp:383-421) and getWidthHeightChannel
+  planes[0] = iyuv;
+  planes[1] = iyuv + (uint64_t)w * h;
+  planes[2] = iyuv + (uint64_t)w * h * 5 / 4;
+  if (widths) { widths[0] = w; widths[1] = widths[2] = w / 2; }
+  if (heights) { heights[0] = h; heights[1] = heights[2] = h / 2; }
+  return MYYUVB_OK;
+}
+
+int myyuvb_get_pixels_dev(myyuvb_ctx* c, const uint8_t* d_iyuv, uint32_t w, uint32_t h, uint32_t n, const uint32_t* d_xy, uint8_t* d_yuv_out) {
+  if (!c || !d_iyuv || (n && (!d_xy || !d_yuv_out))) return fail(MYYUVB_ERR_ARG, "null argument");
+  if (w == 0 || h == 0 || (w % 2) || (h % 2)) return fail(MYYUVB_ERR_EVEN, "Error. width and height must be even");
+  if ((uint64_t)w * h * 3 / 2 > 0xffffffffull) return fail(MYYUVB_ERR_TOO_LARGE, "Error. image does not fit the format's uint32 sizes");
+  CU(cudaSetDevice(c->device));
+  if (!c->d_counters.p) {
+    int rc;
+    if ((rc = c->d_counters.reserve(64))) return rc;
+    CU(cudaMemsetAsync(c->d_counters.p, 0, 64, c->stream));
+  }
+  launch_get_pixels(d_iyuv, w, h, n, d_xy, d_yuv_out, c->d_counters.as<uint32_t>() + 1, c->stream);
+  CU(cudaGetLastError());
+  return MYYUVB_OK;
+}
+
+int myyuvb_iyuv_to_rgba_batch_dev(myyuvb_ctx* c, const uint8_t* d_iyuv, uint32_t w, uint32_t h, uint32_t n_frames, int flip_rows, uint8_t* d_rgba) {
+  if (!c || !d_iyuv || !d_rgba || n_frames == 0) return fail(MYYUVB_ERR_ARG, "null argument");
+  if (w == 0 || h == 0 || (w % 4) || (h % 2)) return fail(MYYUVB_ERR_WIDTH, "Error. width % 4 and height % 2 must be 0");
+  if (((uintptr_t)d_iyuv & 3) || ((uintptr_t)d_rgba & 15)) return fail(MYYUVB_ERR_ARG, "device buffers must be 4-byte (input) / 16-byte (output) aligned");
+  CU(cudaSetDevice(c->device));
+  launch_iyuv_to_rgba(d_iyuv, d_rgba, w, h, n_frames, flip_rows, c->stream);
+  CU(cudaGetLastError());
+  return MYYUVB_OK;
+}
+
+// decompress + display conversion, chunked like the XRGB -> payload pipeline so that the IYUV frames are converted while
+// they are still in L2 (d_iyuv: NULL, or n_frames * w*h*3/2 bytes that receive the decoded frames as well)
+int myyuvb_dct_decompress_to_rgba_batch_dev(myyuvb_ctx* c, const uint8_t* d_payloads, const uint64_t* d_offsets, uint32_t w, uint32_t h,
+                                            const uint8_t quality[3], uint32_t n_frames, uint32_t chunk_frames, int flip_rows,
+                                            uint8_t* d_iyuv, uint8_t* d_rgba) {
+  if (!c || !d_payloads || !d_offsets || !quality || !d_rgba || n_frames == 0) return fail(MYYUVB_ERR_ARG, "null argument");
+  int rc;
+  if ((rc = check_quality(quality))) return rc;
+  if ((rc = check_dims(w, h))) return rc;
+  CU(cudaSetDevice(c->device));
+  const uint64_t frame_bytes = (uint64_t)w * h * 3 / 2;
+  if (chunk_frames == 0) chunk_frames = (uint32_t)std::max<uint64_t>(1, (48ull << 20) / frame_bytes);  // IYUV + RGBA of a chunk fit L2
+  chunk_frames = std::min(chunk_frames, n_frames);
+  uint8_t* ring = nullptr;
+  if (!d_iyuv) {
+    if ((rc = c->d_in.reserve((uint64_t)chunk_frames * frame_bytes))) return rc;
+    ring = c->d_in.as<uint8_t>();
+  }
+  for (uint32_t f0 = 0; f0 < n_frames; f0 += chunk_frames) {
+    const uint32_t nf = std::min(chunk_frames, n_frames - f0);
+    uint8_t* iy = d_iyuv ? d_iyuv + (uint64_t)f0 * frame_bytes : ring;
+    if ((rc = myyuvb_dct_decompress_batch_dev(c, d_payloads, d_offsets + f0, w, h, quality, nf, iy))) return rc;
+    if ((rc = myyuvb_iyuv_to_rgba_batch_dev(c, iy, w, h, nf, flip_rows, d_rgba + (uint64_t)f0 * w * h * 4))) return rc;
+  }
   return MYYUVB_OK;
 }
 

@@ -519,6 +519,101 @@ void launch_xrgb_to_iyuv(const uint8_t* d_bgrx, uint8_t* d_iyuv, uint32_t w, uin
 }
 
 // ===================================================================================================
+// Consumers of decoded frames that stay on the device
+// ===================================================================================================
+// YUV::getPixel for a list of coordinates (the IYUV entry of yuv_get_pixel_map, myyuv_yuv.cpp:162-180), including its
+// chroma index  x / 2 + y * width / 4  in 32-bit arithmetic -- for odd y that is NOT row y / 2 of the half-width plane but
+// half a chroma row further; a viewer built on the reference sees exactly these bytes, so they are reproduced, not fixed
+// (except where the formula leaves the image altogether, see below).
+__global__ void get_pixels_kernel(const uint8_t* __restrict__ iyuv, uint32_t w, uint32_t h, uint32_t n, const uint32_t* __restrict__ xy,
+                                  uint8_t* __restrict__ out, uint32_t* __restrict__ flags) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t x = xy[2 * i], y = xy[2 * i + 1];
+    if (x >= w || y >= h) {  // "Image coordinates are out of bounds" (:171-173)
+      atomicOr(flags, kFlagBounds);
+      out[3 * i] = out[3 * i + 1] = out[3 * i + 2] = 0;
+      continue;
+    }
+    const uint32_t uv_index = x / 2 + y * w / 4;
+    const uint64_t frame = (uint64_t)w * h * 3 / 2, vi = (uint64_t)w * h * 5 / 4 + uv_index;
+    out[3 * i] = iyuv[x + y * w];
+    out[3 * i + 1] = iyuv[(uint64_t)w * h + uv_index];
+    // on the last (odd) row the formula runs past the V plane for x >= width / 2: the reference reads whatever follows its
+    // buffer there (undefined behaviour); here that sample is 0
+    out[3 * i + 2] = vi < frame ? iyuv[vi] : (uint8_t)0;
+  }
+}
+
+void launch_get_pixels(const uint8_t* d_iyuv, uint32_t w, uint32_t h, uint32_t n, const uint32_t* d_xy, uint8_t* d_out, uint32_t* flags,
+                       cudaStream_t s) {
+  if (n == 0) return;
+  const uint32_t want = (n + 255) / 256;
+  get_pixels_kernel<<<want < 148u * 8 ? want : 148u * 8, 256, 0, s>>>(d_iyuv, w, h, n, d_xy, d_out, flags);
+  g_launches++;
+}
+
+// IYUV -> RGBA8 as the reference's viewer shows a frame (myyuv_opengl/viewer/frag_yuv.glsl:18-26 with the plane textures of
+// myyuv_opengl_shared.cpp:109-121: GL_LINEAR, clamp to edge), for a 1:1 display: Y at its texel, the half-resolution chroma
+// planes sampled at the luma pixel's centre, i.e. bilinearly between the four nearest chroma texels with weights 3/4 and
+// 1/4 per axis, clamped at the borders.  y = Y/255, u = U/255 - 0.5, v = V/255 - 0.5,
+//   r = y + 1.403 v,  g = y - 0.714 v - 0.344 u,  b = y + 1.773 u,   stored as round(clamp(c, 0, 1) * 255), alpha 255.
+// There is no CPU code in the reference to be bit-identical to (a GPU's texture filter has its own fixed-point weights):
+// the tests hold this kernel to +-1 LSB of the formula evaluated in double precision.
+// One thread = 4 pixels of one row; flip != 0 writes the rows bottom-up (what a GL pixel-unpack buffer wants).
+__global__ void __launch_bounds__(256) iyuv_to_rgba_kernel(const uint8_t* __restrict__ iyuv, uint8_t* __restrict__ rgba, uint32_t w, uint32_t h,
+                                                           int flip) {
+  const uint8_t* src = iyuv + (uint64_t)blockIdx.y * w * h * 3 / 2;
+  uint8_t* dst = rgba + (uint64_t)blockIdx.y * w * h * 4;
+  const uint32_t qw = w / 4, cw = w / 2, ch = h / 2;
+  const uint8_t* U = src + (uint64_t)w * h;
+  const uint8_t* V = U + (uint64_t)cw * ch;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < qw * h; i += gridDim.x * blockDim.x) {
+    const uint32_t y = i / qw, x0 = (i - y * qw) * 4;
+    const uint32_t y4 = *reinterpret_cast<const uint32_t*>(src + (uint64_t)y * w + x0);
+    // chroma rows: centre of luma row y lies at chroma coordinate y / 2 - 1/4 (y even) or y / 2 + 1/4 (y odd)
+    const int cy = (int)(y >> 1);
+    const int ra = (y & 1) ? cy : max(cy - 1, 0), rb = (y & 1) ? min(cy + 1, (int)ch - 1) : cy;
+    const float wa = (y & 1) ? 0.75f : 0.25f, wb = 1.0f - wa;
+    // chroma columns x0/2 - 1 .. x0/2 + 2 (clamped) serve the four pixels
+    const int c0 = (int)(x0 >> 1);
+    float cu[4], cv[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int c = min(max(c0 - 1 + k, 0), (int)cw - 1);
+      cu[k] = wa * (float)__ldg(U + (uint64_t)ra * cw + c) + wb * (float)__ldg(U + (uint64_t)rb * cw + c);
+      cv[k] = wa * (float)__ldg(V + (uint64_t)ra * cw + c) + wb * (float)__ldg(V + (uint64_t)rb * cw + c);
+    }
+    uint32_t px[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      // pixel x0 + k: even -> between columns c-1 (1/4) and c (3/4); odd -> between c (3/4) and c+1 (1/4), c = (x0 + k) / 2
+      const int j = (k >> 1);  // index of column c - 1 in cu[] for this pixel is j, c is j + 1, c + 1 is j + 2
+      const float u8 = (k & 1) ? 0.75f * cu[j + 1] + 0.25f * cu[j + 2] : 0.25f * cu[j] + 0.75f * cu[j + 1];
+      const float v8 = (k & 1) ? 0.75f * cv[j + 1] + 0.25f * cv[j + 2] : 0.25f * cv[j] + 0.75f * cv[j + 1];
+      const float yy = (float)((y4 >> (8 * k)) & 0xffu) * (1.0f / 255.0f);
+      const float u = u8 * (1.0f / 255.0f) - 0.5f, v = v8 * (1.0f / 255.0f) - 0.5f;
+      const float r = yy + 1.403f * v, g = yy - 0.714f * v - 0.344f * u, b = yy + 1.773f * u;
+      const uint32_t R = (uint32_t)__float2int_rn(__saturatef(r) * 255.0f), G = (uint32_t)__float2int_rn(__saturatef(g) * 255.0f),
+                     B = (uint32_t)__float2int_rn(__saturatef(b) * 255.0f);
+      px[k] = R | (G << 8) | (B << 16) | 0xff000000u;
+    }
+    const uint32_t yo = flip ? h - 1 - y : y;
+    *reinterpret_cast<uint4*>(dst + ((uint64_t)yo * w + x0) * 4) = make_uint4(px[0], px[1], px[2], px[3]);
+  }
+}
+
+void launch_iyuv_to_rgba(const uint8_t* d_iyuv, uint8_t* d_rgba, uint32_t w, uint32_t h, uint32_t n_frames, int flip, cudaStream_t s) {
+  for (uint32_t f0 = 0; f0 < n_frames; f0 += 65535u) {
+    const uint32_t nf = n_frames - f0 < 65535u ? n_frames - f0 : 65535u;
+    const uint32_t units = (w / 4) * h;
+    const uint32_t want = (units + 255) / 256;
+    const uint32_t cap = (148u * 16 + nf - 1) / nf;
+    iyuv_to_rgba_kernel<<<dim3(want < cap ? want : cap, nf), 256, 0, s>>>(d_iyuv + (uint64_t)f0 * w * h * 3 / 2, d_rgba + (uint64_t)f0 * w * h * 4, w, h, flip);
+    g_launches++;
+  }
+}
+
+// ===================================================================================================
 // Compression
 // One thread = one 8x8 block for both phases (tile = 128 blocks = 128 threads), sized so that six CTAs
 // (24 warps) fit an SM: 80 registers (a handful of spills in the DCT), <= 36.5 KB shared memory.
@@ -1448,6 +1543,9 @@ int codec_grid_size(int device, bool encoder) {
   return sms * (encoder ? kEncCtasPerSm : kDecCtasPerSm);
 }
 
+#ifndef MYYUVB_NO_TMA_STAGE
+#define MYYUVB_TMA_STAGE 1
+#endif
 // ===================================================================================================
 // Decompression (one thread = one block; tile = 128 blocks; six CTAs per SM: 80 registers, 27 KB shared memory)
 // ===================================================================================================
@@ -1463,6 +1561,9 @@ struct DecSmem {
   uint32_t warp_sums[4];
   uint32_t tile;
   u64 base;
+#ifdef MYYUVB_TMA_STAGE
+  alignas(8) unsigned long long stage_bar;  // mbarrier of the bulk copy into stage[]
+#endif
   // counting sort of the tile's blocks by chunk size (kSortDecBlocks): thread t decodes block perm[t]
   uint32_t hist[64];
   uint16_t boff[kTileBlocks];
@@ -1665,6 +1766,15 @@ __global__ void __launch_bounds__(kCtaThreads, 6)
   const FrameGeom& g = P.g;
   int q_plane = -1;
   int16_t* const col = &sm.coef[0][tid];
+#ifdef MYYUVB_TMA_STAGE
+  uint32_t stage_phase = 0;
+  bool stage_pending = false;
+  if (tid == 0) {
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&sm.stage_bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+#endif
   PH_INIT();
   PH_BEGIN();
 
@@ -1707,8 +1817,26 @@ __global__ void __launch_bounds__(kCtaThreads, 6)
       const uint32_t n = total < (uint32_t)kDecStageBytes ? total : (uint32_t)kDecStageBytes;
       const uint32_t full = (mis + n) >> 4;  // whole 16-byte vectors
       const uint4* src = reinterpret_cast<const uint4*>(content - mis);
+#ifdef MYYUVB_TMA_STAGE
+      // The aligned body of the tile's chunk bytes as ONE 1-D bulk copy (TMA: cp.async.bulk global -> shared, completion on
+      // an mbarrier; SASS UBLKCP) issued by thread 0, instead of one 128-bit load per thread and step: decompress -1.7 % on
+      // the synthetic frames, -0.7 % on natural content in a same-box A/B (profiles/r02_notes.md, "TMA staging").
+      // -DMYYUVB_NO_TMA_STAGE builds the load loop instead (lib/libmyyuvb200_notma.so).
+      if (full) {
+        if (tid == 0) {
+          const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&sm.stage_bar);
+          const uint32_t dsts = (uint32_t)__cvta_generic_to_shared(sm.stage);
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(full << 4) : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dsts), "l"(src),
+                       "r"(full << 4), "r"(bar)
+                       : "memory");
+        }
+        stage_pending = true;
+      }
+#else
       uint4* dst = reinterpret_cast<uint4*>(sm.stage);
       for (uint32_t v = tid; v < full; v += kCtaThreads) dst[v] = __ldg(src + v);
+#endif
       const uint32_t done = full << 4;  // bytes of stage[] filled so far (counted from the aligned start)
       if (tid < mis + n - done) sm.stage[done + tid] = __ldg(content - mis + done + tid);
     }
@@ -1749,6 +1877,16 @@ __global__ void __launch_bounds__(kCtaThreads, 6)
       bsize = sm.bsize[blk];
     }
     PH(2);  // block sort
+#ifdef MYYUVB_TMA_STAGE
+    if (stage_pending) {  // CTA uniform: every thread waits for the bulk copy's bytes, then the barrier's phase flips
+      const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&sm.stage_bar);
+      uint32_t ok = 0;
+      while (!ok)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(bar), "r"(stage_phase) : "memory");
+      stage_phase ^= 1u;
+      stage_pending = false;
+    }
+#endif
     const bool mine = blk < tc.nblk;
     int nsym = 0;  // decoded zigzag positions: the non-zero coefficients lie in positions [0, nsym)
     {

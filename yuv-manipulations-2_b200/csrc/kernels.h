@@ -86,6 +86,7 @@ struct PlaneDesc {
 // ---- one image sharded over the GPUs of a box ----
 constexpr int kShardMaxWorld = 16;
 constexpr uint32_t kFlagShardTimeout = 1u << 4;
+constexpr uint32_t kFlagBounds = 1u << 5;
 
 // Where this rank's band goes in the root's payload buffer; written by shard_exchange_kernel, read by the place / finalize kernels
 struct ShardPlace {
@@ -142,6 +143,12 @@ void launch_compress(const uint8_t* d_iyuv, const FrameGeom& g, const QTables& q
                      uint64_t* d_offsets, const uint64_t* d_base, const Workspace& ws, cudaStream_t s);
 void launch_decompress(const uint8_t* d_payloads, const uint64_t* d_offsets, const FrameGeom& g, const QTables& qt,
                        uint8_t* d_iyuv, const Workspace& ws, cudaStream_t s);
+
+// YUV::getPixel for n coordinate pairs (x, y): out[3 i ..] = {Y, U, V}; out-of-range coordinates raise kFlagBounds in *flags
+void launch_get_pixels(const uint8_t* d_iyuv, uint32_t w, uint32_t h, uint32_t n, const uint32_t* d_xy, uint8_t* d_out, uint32_t* flags,
+                       cudaStream_t s);
+// IYUV -> RGBA8 with the viewer's fragment-shader arithmetic (see kernels.cu); flip: rows bottom-up
+void launch_iyuv_to_rgba(const uint8_t* d_iyuv, uint8_t* d_rgba, uint32_t w, uint32_t h, uint32_t n_frames, int flip, cudaStream_t s);
 
 // dst / src: device memory or the device-side address of mapped pinned host memory
 void launch_sm_copy(uint8_t* dst, const uint8_t* src, uint64_t bytes, cudaStream_t s);
