@@ -59,12 +59,8 @@ int encode_blocks(const int16_t* coef, uint32_t n, int mode, uint8_t* out, uint8
       for (int i = 0; i < 32; i++) F.tab(i) = 0xffff;
       // the tile pass counts up to 8 symbols; blocks with more go to heavy15_kernel, which starts over on the coefficient
       // words (they may carry the first attempt's slot bits) with a histogram of up to 15
-      HistState hs;
-      int ns = huff_hist<8>(za, L, true, F, NoWarp{}, hs);
-      if (ns < 0 && (b & 1)) {
-        // a tile that codes its detailed blocks in place: the count goes on where it stopped, up to 15 symbols
-        ns = huff_hist<kFastCap>(za, L, true, F, NoWarp{}, hs);
-      } else if (ns < 0) {
+      int ns = huff_hist<8>(za, L, true, F, NoWarp{});
+      if (ns < 0) {
         for (int i = 0; i < 64; i++) za.setraw(i, (uint32_t)(((int32_t)(za.raw(i) << 21)) >> 21));  // 11-bit value, sign extended
         for (int i = 0; i < 32; i++) F.tab(i) = 0xffff;
         ns = huff_hist<kFastCap>(za, L, true, F, NoWarp{});

@@ -568,23 +568,16 @@ struct FastScratch {
 // Returns the number of distinct symbols, or -1 when there are more than CAP (<= kFastCap; a lane stops counting at
 // symbol number CAP + 1, and the loop ends once every lane of the warp has either finished or stopped).  Idle lanes pass
 // live = false and get 0.
-// st: where the count stands.  A lane that stopped at CAP + 1 symbols can be taken up again with a larger CAP (the tile
-// pass counts to 8 first and goes on to 15 only in tiles that code their detailed blocks in place).
-struct HistState {
-  int n = 0;     // distinct symbols so far
-  int next = 0;  // first message position not counted yet
-};
 template <int CAP, int STRIDE, class Z, class W>
-MYB_HD int huff_hist(Z& z, int L, bool live, const FastScratch<STRIDE>& F, const W& warp, HistState& st) {
+MYB_HD int huff_hist(Z& z, int L, bool live, const FastScratch<STRIDE>& F, const W& warp) {
   static_assert(CAP <= kFastCap, "slot numbers are 4 bits");
-  int n = st.n, next = st.next;
+  int n = 0;
   if (!live) L = 0;
   const int Lw = warp.max(L);
-  const int first = -warp.max(-(next < L ? next : Lw));  // the earliest position any lane still has to count
   MYB_NOUNROLL
-  for (int i = first; i < Lw; i++) {
-    if (((i - first) & 3) == 3 && !warp.any(i < L && n <= CAP)) break;
-    if (i >= next && i < L && n <= CAP) {
+  for (int i = 0; i < Lw; i++) {
+    if ((i & 3) == 3 && !warp.any(i < L && n <= CAP)) break;
+    if (i < L && n <= CAP) {
       const uint32_t raw = z.raw(i);
       const uint32_t tag = raw & 0x7ffu;
       uint32_t h = raw & 31u;
@@ -603,7 +596,6 @@ MYB_HD int huff_hist(Z& z, int L, bool live, const FastScratch<STRIDE>& F, const
       F.slot((int)s) = word + 1u;
       n += isnew ? 1 : 0;
       z.setraw(i, tag | (s << 11));
-      next = i + 1;
     }
     warp.sync();
   }
@@ -612,14 +604,7 @@ MYB_HD int huff_hist(Z& z, int L, bool live, const FastScratch<STRIDE>& F, const
     z.setraw(0, 0u);
     n = 1;
   }
-  st.n = n;
-  st.next = next;
   return n > CAP ? -1 : n;
-}
-template <int CAP, int STRIDE, class Z, class W>
-MYB_HD int huff_hist(Z& z, int L, bool live, const FastScratch<STRIDE>& F, const W& warp) {
-  HistState st;
-  return huff_hist<CAP>(z, L, live, F, warp, st);
 }
 
 struct FastPlan {

@@ -32,6 +32,20 @@ namespace myyuvb {
 
 thread_local uint64_t g_launches = 0;
 
+// Function attributes (dynamic shared memory above 48 KB) and lazily loaded kernels are per DEVICE: a process that drives
+// several GPUs (one context per device) needs them set / loaded on each one.  True the first time `site` is reached on the
+// current device.
+static bool first_use_on_device(int site) {
+  static unsigned long long seen[8] = {};  // bit d of seen[site]: done on device d (devices beyond 63 redo the calls, harmlessly)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev > 63) return true;
+  const unsigned long long bit = 1ull << dev;
+  if (seen[site] & bit) return false;
+  seen[site] |= bit;
+  return true;
+}
+
 // Optional per-phase clock counters of the two codec kernels (build.py builds lib/libmyyuvb200_clk.so with
 // -DMYYUVB_PHASE_CLOCKS; profiles/phase_clocks.py reads them).  Lane 0 of every warp adds the clock64() distance between
 // consecutive marks to a shared-memory slot of its warp; the sums go to g_phase_clk when the CTA retires.  The product
@@ -1958,11 +1972,9 @@ namespace {
 void compress_code_and_scan(const EncParams& P, const QTables& qt, cudaStream_t s) {
   const Workspace& ws = P.ws;
   const FrameGeom& g = P.g;
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (first_use_on_device(0)) {
     cudaFuncSetAttribute(dct_compress_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncSmem));
     cudaFuncSetAttribute(dct_compress_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncSmem));
-    attr_set = true;
   }
   cudaMemsetAsync(ws.counters, 0, 4, s);       // ticket only; error flags accumulate until read
   cudaMemsetAsync(ws.counters + 2, 0, 28, s);  // scratch bump allocator, queue of deferred blocks, lists of those with > 15 and > 32 symbols, list of tiles with queued blocks
@@ -1971,12 +1983,10 @@ void compress_code_and_scan(const EncParams& P, const QTables& qt, cudaStream_t 
   if (ws.code_in_place) dct_compress_kernel<true><<<grid, kCtaThreads, sizeof(EncSmem), s>>>(P, qt);
   else dct_compress_kernel<false><<<grid, kCtaThreads, sizeof(EncSmem), s>>>(P, qt);
   if (ws.heavy_cap) {
-    static bool heavy_attr = false;
-    if (!heavy_attr) {
+    if (first_use_on_device(1)) {
       cudaFuncSetAttribute(heavy15_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Heavy15Smem));
       cudaFuncSetAttribute(heavy_blocks_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HeavySmem<32>));
       cudaFuncSetAttribute(heavy_blocks_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HeavySmem<64>));
-      heavy_attr = true;
     }
     // queue -> heavy15_kernel (fast path, <= 15 symbols) -> list A -> heavy_blocks_kernel<32> -> list B -> <64>
     const uint32_t fwant = (ws.heavy_cap + kCtaThreads - 1) / kCtaThreads;
@@ -2204,11 +2214,7 @@ void launch_decompress_shard(const uint8_t* payload, uint64_t payload_size, cons
   P.payloads = payload; P.offsets = nullptr; P.dst = d_band; P.g = g; P.ws = ws;
   P.total_tiles = g.tiles_per_frame * g.n_frames;
   P.one = 1.0f;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(dct_decompress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecSmem));
-    attr_set = true;
-  }
+  if (first_use_on_device(2)) cudaFuncSetAttribute(dct_decompress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecSmem));
   ShardBand B;
   for (int p = 0; p < 3; p++) { B.nblk_full[p] = nblk_full[p]; B.k_lo[p] = k_lo[p]; B.nb[p] = g.nblk[p]; }
   ShardPull* pull = reinterpret_cast<ShardPull*>(ws.plane_start);  // 3 records in the encoder's plane-start array (always allocated, unused when decoding)
@@ -2231,9 +2237,7 @@ void launch_decompress_shard(const uint8_t* payload, uint64_t payload_size, cons
 }
 
 void shard_preload() {
-  static bool done = false;
-  if (done) return;
-  done = true;
+  if (!first_use_on_device(3)) return;
   cudaFuncAttributes a;
   cudaFuncGetAttributes(&a, shard_go_kernel);
   cudaFuncGetAttributes(&a, shard_exchange_kernel);
@@ -2264,11 +2268,7 @@ void launch_decompress(const uint8_t* d_payloads, const uint64_t* d_offsets, con
   P.payloads = d_payloads; P.offsets = d_offsets; P.dst = d_iyuv; P.g = g; P.ws = ws;
   P.total_tiles = g.tiles_per_frame * g.n_frames;
   P.one = 1.0f;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(dct_decompress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecSmem));
-    attr_set = true;
-  }
+  if (first_use_on_device(2)) cudaFuncSetAttribute(dct_decompress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecSmem));
   cudaMemsetAsync(ws.counters, 0, 4, s);
   if (ws.k_begin) cudaEventRecord(ws.k_begin, s);
   parse_payload_kernel<<<(g.n_frames + 127) / 128, 128, 0, s>>>(P);
