@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Same-box A/B of two builds of the CUDA library (MYYUVB_LIB_VARIANT): compress / decompress launch-sequence times of
-the workloads below, variants alternated, median of 5 per round, 3 rounds.  usage: ab.py variantA variantB   ("" = the product build)"""
+the workloads below, variants alternated, median of 5 per round, 3 rounds.  usage: ab.py variantA variantB [...]   ("" = the product build)"""
 import json, os, subprocess, sys
 CHILD = r'''
 import importlib, json, os, pathlib, struct, sys, statistics
@@ -30,9 +30,10 @@ for name, n in (("ng:50", 64), ("nat:50", 16), ("nat:90", 16), ("ng:90", 16)):
 print(json.dumps(out))
 '''
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-res = {v: [] for v in sys.argv[1:3]}
+variants = sys.argv[1:]
+res = {v: [] for v in variants}
 for rnd in range(3):
-    for v in sys.argv[1:3]:
+    for v in variants:
         r = subprocess.run([sys.executable, "-c", CHILD, root], env=dict(os.environ, MYYUVB_LIB_VARIANT=v), capture_output=True, text=True)
         res[v].append(json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0 else {"error": r.stderr[-500:]})
 for v, runs in res.items():
