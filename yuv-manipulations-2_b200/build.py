@@ -49,6 +49,7 @@ def build_cuda(force: bool = False, verbose: bool = False, variant: str = "") ->
     deps = srcs + [CSRC / "kernels.h", CSRC / "block_codec.cuh", CSRC / "dct_matrix.inc", ROOT / "include/myyuvb200.h"]
     if force or _newer(out, deps):
         extra = {"clk": ["-DMYYUVB_PHASE_CLOCKS"], "notma": ["-DMYYUVB_NO_TMA_STAGE"]}.get(variant, [])
+        extra += os.environ.get("MYYUVB_VARIANT_FLAGS", "").split() if variant else []  # experiments: profiles/ab.py
         _run([NVCC, *ARCH, "-O3", "-lineinfo", "-std=c++17", "-fmad=false", *extra, "-ccbin", CXX,
               "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden", "--shared", "-o", out, *srcs], verbose)
     return out
@@ -78,7 +79,9 @@ def build(force: bool = False, verbose: bool = False):
 
 
 if __name__ == "__main__":
-    if "--clk" in sys.argv or "--notma" in sys.argv:
+    if "--variant" in sys.argv:  # build.py --variant NAME  with MYYUVB_VARIANT_FLAGS="-D..." in the environment
+        build_cuda(force=True, verbose=True, variant=sys.argv[sys.argv.index("--variant") + 1])
+    elif "--clk" in sys.argv or "--notma" in sys.argv:
         build_cuda(force="--force" in sys.argv, verbose=True, variant="clk" if "--clk" in sys.argv else "notma")
     else:
         build(force="--force" in sys.argv, verbose=True)

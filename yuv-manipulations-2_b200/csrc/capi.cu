@@ -71,12 +71,12 @@ void make_qtables(const uint8_t quality[3], QTables* qt) {
       v = v < 1.0f ? 1.0f : (v > 255.0f ? 255.0f : v);
       qt->q[p][i] = v;
     }
-    for (int a2 = 0; a2 < 4; a2++)
-      for (int b = 0; b < 8; b++) {
-        const float q0 = qt->q[p][(2 * a2) * 8 + b], q1 = qt->q[p][(2 * a2 + 1) * 8 + b];
+    for (int bp = 0; bp < 4; bp++)
+      for (int a = 0; a < 8; a++) {
+        const float q0 = qt->q[p][a * 8 + 2 * bp], q1 = qt->q[p][a * 8 + 2 * bp + 1];
         // correctly rounded reciprocals, used by the exact-division step in the kernel
-        qt->rqp[p][a2 * 8 + b] = {1.0f / q0, 1.0f / q1};
-        qt->nqp[p][a2 * 8 + b] = {-q0, -q1};
+        qt->rqp[p][bp * 8 + a] = {1.0f / q0, 1.0f / q1};
+        qt->nqp[p][bp * 8 + a] = {-q0, -q1};
       }
   }
 }

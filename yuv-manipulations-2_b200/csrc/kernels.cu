@@ -145,6 +145,24 @@ __constant__ float kDctC[64] = {
 #include "dct_matrix.inc"
 };
 
+// and as the row pairs (C[2 bp][k], C[2 bp + 1][k]) the second product multiplies by: one 64-bit uniform load per pair
+struct DctRowPairs {
+  float2 p[32];  // [bp * 8 + k]
+};
+constexpr DctRowPairs make_dct_row_pairs() {
+  constexpr float c[64] = {
+#include "dct_matrix.inc"
+  };
+  DctRowPairs r{};
+  for (int bp = 0; bp < 4; bp++)
+    for (int k = 0; k < 8; k++) {
+      r.p[bp * 8 + k].x = c[(2 * bp) * 8 + k];
+      r.p[bp * 8 + k].y = c[(2 * bp + 1) * 8 + k];
+    }
+  return r;
+}
+__constant__ DctRowPairs kDctRowPairs = make_dct_row_pairs();
+
 // ---------------------------------------------------------------------------------------------------
 // geometry
 // ---------------------------------------------------------------------------------------------------
@@ -193,6 +211,7 @@ constexpr uint32_t kSmCopySegment = 32u << 10;  // bytes one CTA copies per step
 
 // CTA-wide exclusive scan of one value per thread (kCtaThreads = 128 -> 4 warps); returns exclusive
 // prefix, *total gets the CTA sum.  Contains two __syncthreads.
+template <int NT>
 MYB_D uint32_t cta_exclusive_scan(uint32_t v, uint32_t* warp_sums /* [4] shared */, uint32_t* total) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   uint32_t inc = v;
@@ -205,7 +224,7 @@ MYB_D uint32_t cta_exclusive_scan(uint32_t v, uint32_t* warp_sums /* [4] shared 
   __syncthreads();
   uint32_t base = 0, tot = 0;
 #pragma unroll
-  for (int w = 0; w < kCtaThreads / 32; w++) {
+  for (int w = 0; w < NT / 32; w++) {
     const uint32_t s = warp_sums[w];
     if (w < wid) base += s;
     tot += s;
@@ -217,6 +236,7 @@ MYB_D uint32_t cta_exclusive_scan(uint32_t v, uint32_t* warp_sums /* [4] shared 
 
 // Copy n bytes from shared memory (4-byte aligned base) to global memory at arbitrary alignment with
 // coalesced 32-bit stores.
+template <int NT>
 MYB_D void copy_smem_to_global(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint32_t n) {
   const uint32_t head = min((uint32_t)((4 - ((uintptr_t)dst & 3)) & 3), n);
   if (threadIdx.x < head) dst[threadIdx.x] = src[threadIdx.x];
@@ -224,7 +244,7 @@ MYB_D void copy_smem_to_global(uint8_t* __restrict__ dst, const uint8_t* __restr
   uint32_t* dw = reinterpret_cast<uint32_t*>(dst + head);
   const uint32_t* sw = reinterpret_cast<const uint32_t*>(src);
   const uint32_t sh = head * 8;  // source is `head` bytes off word alignment
-  for (uint32_t w = threadIdx.x; w < words; w += kCtaThreads) {
+  for (uint32_t w = threadIdx.x; w < words; w += NT) {
     const uint32_t lo = sw[w], hi = sw[w + 1];  // sw[w+1] is inside the padded staging buffer
     dw[w] = sh ? __funnelshift_r(lo, hi, sh) : lo;
   }
@@ -636,7 +656,9 @@ void launch_iyuv_to_rgba(const uint8_t* d_iyuv, uint8_t* d_rgba, uint32_t w, uin
 //   stage 2:  (Y[a][b], Y[a+1][b]) = sum_k (T[a][k], T[a+1][k]) * C[b][k]      data pair x broadcast immediate
 // so no transposition or register shuffling is needed between the stages (cuobjdump: 960 FMUL2/FFMA2, 0 MOV).
 // ===================================================================================================
-constexpr int kStageBytes = 3 * 1024;                  // shared-memory staging of one tile's chunk bytes
+#ifndef MYB_ENC_OCC7
+#define MYB_ENC_OCC7 0
+#endif
 // Entropy-coder scratch of the fast path is one 4 KB region per WARP, lanes interleaved (FastScratch<32>):
 //   slot words uint32[16][32] at 0, then 2 KB that are hash table, byte lists and heap in turn.
 // Blocks with more than 15 distinct symbols send their warp through the general code on per-thread local memory.
@@ -644,39 +666,55 @@ using BigScratch = HuffScratch<64, 1>;
 using F8Scratch = FastScratch<32>;
 constexpr int kTileCap = 8;    // distinct symbols per block the compact fast-path instantiation takes
 constexpr int kWarpScratchBytes = 4096;
+// Per build of the coding kernel: the queueing build only ever fills slots 0..kTileCap, so its warps need 9 rows of slot words
+// instead of 16; with 2 KB of staging that is 31 KB per CTA and a seventh CTA fits the SM (MYB_ENC_OCC7).
+template <bool kInPlace>
+struct EncCfg {
+  static constexpr bool kCompact = MYB_ENC_OCC7 && !kInPlace && kEncThreads > 32;
+  static constexpr int kSlotRows = kCompact ? kTileCap + 1 : 16;
+  static constexpr int kWarpBytes = kSlotRows * 128 + 2048;
+  static constexpr int kStage = (kCompact ? 1536 : 3 * 1024) * kEncTile / 128;  // shared-memory staging of one tile's chunk bytes
+  static constexpr int kCtasPerSm = kEncThreads > 32 ? (kCompact ? 7 : 6) : 22;  // resident CTAs per SM (registers and shared memory sized for it)
+};
 
-struct EncSmem {
-  uint16_t zz[64][kTileBlocks];                        // quantised coefficients, zigzag order; later slot ids
-  alignas(16) uint8_t coder[kCtaThreads / 32][kWarpScratchBytes];
-  alignas(16) uint8_t stage[kStageBytes + 8];
+template <bool kInPlace>
+struct EncSmemT {
+  using Cfg = EncCfg<kInPlace>;
+  uint16_t zz[64][kEncTile];                        // quantised coefficients, zigzag order; later slot ids
+  alignas(16) uint8_t coder[kEncThreads / 32][Cfg::kWarpBytes];
+  alignas(16) uint8_t stage[Cfg::kStage + 8];
   uint32_t warp_sums[4];
   uint32_t tile;
   uint32_t split;
   uint32_t heavy;            // the tile holds a block that was queued for heavy_blocks_kernel
   u64 base;
   // counting sort of the tile's blocks by message length (kSortBlocks): thread t entropy-codes block perm[t]
-  uint32_t hist[68];
-  uint16_t boff[kTileBlocks];   // chunk offset of block b inside the tile
-  uint8_t msg_len[kTileBlocks];
-  uint8_t csize[kTileBlocks];
-  uint8_t perm[kTileBlocks];
+  uint32_t hist[kEncThreads > 32 ? 68 : 1];
+  uint16_t boff[kEncThreads > 32 ? kEncTile : 1];   // chunk offset of block b inside the tile
+  uint8_t msg_len[kEncThreads > 32 ? kEncTile : 1];
+  uint8_t csize[kEncThreads > 32 ? kEncTile : 1];
+  uint8_t perm[kEncThreads > 32 ? kEncTile : 1];
   PH_MEMBER
 };
-static_assert(sizeof(EncSmem) <= 37 * 1024 - 512, "EncSmem must allow 6 CTAs per SM");
+constexpr int kEncCtasPerSm = EncCfg<false>::kCtasPerSm;  // the persistent grid is sized for the denser build
+static_assert((sizeof(EncSmemT<false>) + 1024) * EncCfg<false>::kCtasPerSm <= 228 * 1024, "EncSmem must allow kCtasPerSm CTAs per SM");
+static_assert((sizeof(EncSmemT<true>) + 1024) * EncCfg<true>::kCtasPerSm <= 228 * 1024, "EncSmem must allow kCtasPerSm CTAs per SM");
 // Thread t codes the block of rank t in message-length order, so that the lanes of a warp get messages of similar length
 // and the lockstep loops (trip count = warp maximum) waste few lanes.  Five more CTA barriers per tile.
-constexpr bool kSortBlocks = true;
+constexpr bool kSortBlocks = kEncThreads > 32;
 static_assert(!kSortBlocks || kEncPasses == 1, "boff holds 16-bit offsets of a one-pass tile");
 
-struct ZShared {  // accessor of one block's column in EncSmem::zz
+template <int S>
+struct ZSharedT {  // accessor of one block's column in EncSmem::zz (S columns)
   uint16_t* col;
   // value view: a coefficient is 11 bits two's complement; bits 11..14 may hold its slot (huff_hist)
-  MYB_D int get(int i) const { return ((int)((uint32_t)col[i * kTileBlocks] << 21)) >> 21; }
-  MYB_D void set(int i, int v) { col[i * kTileBlocks] = (uint16_t)v; }
-  MYB_D uint32_t raw(int i) const { return col[i * kTileBlocks]; }
-  MYB_D void setraw(int i, uint32_t w) { col[i * kTileBlocks] = (uint16_t)w; }
-  MYB_D int slot(int i) const { return (col[i * kTileBlocks] >> 11) & 15; }
+  MYB_D int get(int i) const { return ((int)((uint32_t)col[i * S] << 21)) >> 21; }
+  MYB_D void set(int i, int v) { col[i * S] = (uint16_t)v; }
+  MYB_D uint32_t raw(int i) const { return col[i * S]; }
+  MYB_D void setraw(int i, uint32_t w) { col[i * S] = (uint16_t)w; }
+  MYB_D int slot(int i) const { return (col[i * S] >> 11) & 15; }
 };
+using ZShared = ZSharedT<kEncTile>;
 struct EncParams {
   const uint8_t* src;
   uint8_t* out;
@@ -700,11 +738,20 @@ MYB_D constexpr int zigzag_of(int i) {
 
 
 // Forward DCT + quantisation of one block.  raw: 8 rows x 2 words of pixels.  Writes the 64 coefficients in
-// zigzag order to zcol[i * kTileBlocks]; returns the message length (Huffman.cpp:184-190: trailing zeros are not coded).
+// zigzag order to zcol[i * kEncTile]; returns the message length (Huffman.cpp:184-190: trailing zeros are not coded).
+// Lanes of the packed instructions = two ADJACENT COLUMNS (2cp, 2cp+1) of the same block:
+//   stage 1:  (T[a][2cp], T[a][2cp+1]) = sum_k C[a][k] * (X[k][2cp], X[k][2cp+1])       data pair x scalar constant
+//   stage 2:  (Y[a][2bp], Y[a][2bp+1]) = sum_k T[a][k] * (C[2bp][k], C[2bp+1][k])       scalar data x constant pair
+// In stage 1 every constant is a 32-bit immediate of the instruction (FMUL2 takes a scalar immediate that it broadcasts to
+// both lanes), so the unrolled code is the 480 packed operations and nothing else.  With the constants as PAIRS (the
+// row-pair layout this replaces) ptxas had to build each pair in a 64-bit register or uniform register first: 215 IMAD.MOV,
+// 53 MOV, 38 FADD and 118 UMOV next to the 480 packed operations (cuobjdump, profiles/r02_notes.md).  Stage 2 is a rolled loop,
+// its constant pairs come from constant memory into uniform register pairs (LDCU.64), its data scalars are the halves of the
+// stage-1 registers.  Each output is still the k-ascending sum of separately rounded products (DCT.cpp:232-254).
 MYB_D int fdct_quant_block(const uint32_t (&raw)[16], const QTables& qt, int plane, float onef, uint16_t* zcol) {
   const f2 ONE = dup(onef);
   // (float)px - 128 (DCT.cpp:303): 0x4B000000 | px is the float 2^23 + px; subtracting 2^23 + 128 is exact
-  float x[64];
+  f2 x[32];  // x[k * 4 + cp] = (X[k][2 cp], X[k][2 cp + 1])
   {
     const f2 bias = dup(-8388736.0f);
 #pragma unroll
@@ -714,54 +761,51 @@ MYB_D int fdct_quant_block(const uint32_t (&raw)[16], const QTables& qt, int pla
         f2 v;
         v.x = __uint_as_float(__byte_perm(raw[wd], 0x4B000000u, 0x7440 + bt));
         v.y = __uint_as_float(__byte_perm(raw[wd], 0x4B000000u, 0x7441 + bt));
-        v = add2(v, bias);
-        x[wd * 4 + bt] = v.x;
-        x[wd * 4 + bt + 1] = v.y;
+        x[wd * 2 + (bt >> 1)] = add2(v, bias);
       }
     }
   }
   // T = C . X  (DCT.cpp:232-242), k ascending, every product and sum rounded separately
-  f2 t[32];  // t[a2 * 8 + c] = (T[2 a2][c], T[2 a2 + 1][c])
+  f2 t[32];  // t[a * 4 + cp] = (T[a][2 cp], T[a][2 cp + 1])
 #pragma unroll
-  for (int c = 0; c < 8; c++) {
+  for (int cp = 0; cp < 4; cp++) {
 #pragma unroll
-    for (int a2 = 0; a2 < 4; a2++) {
-      f2 acc = mul2(dup(x[c]), mkp(dct_c(a2 * 16), dct_c(a2 * 16 + 8)));
+    for (int a = 0; a < 8; a++) {
+      f2 acc = mul2(x[cp], dup(dct_c(a * 8)));
 #pragma unroll
-      for (int k = 1; k < 8; k++)
-        acc = sum2(acc, mul2(dup(x[k * 8 + c]), mkp(dct_c(a2 * 16 + k), dct_c(a2 * 16 + 8 + k))), ONE);
-      t[a2 * 8 + c] = acc;
+      for (int k = 1; k < 8; k++) acc = sum2(acc, mul2(x[k * 4 + cp], dup(dct_c(a * 8 + k))), ONE);
+      t[a * 4 + cp] = acc;
     }
   }
   // Y = T . C^T (DCT.cpp:244-254): Y[a][b] = sum_k T[a][k] * C[b][k]; then coef = (int16) round(Y / q) (DCT.cpp:274).
   // The divisor is an integer 1..255, so one Newton step on q0 = Y * RN(1/q) is the correctly rounded quotient:
   // rem = Y - q*q0 is exact, and Y/q is never closer than ulp/510 to a rounding boundary while the step's error is
   // < 2^-23 ulp (DESIGN.md "Exact division"; checked exhaustively around ties by tests/hostemu).
-  // The loop over the output column b is NOT unrolled: its body (4 row pairs x 8 products, quantiser, stores) is 140
+  // The loop over the output column pair bp is NOT unrolled: its body (8 rows x 8 products, quantiser, stores) is 260
   // instructions instead of 1100 of straight-line code, which the instruction cache feels (profiles/r01_notes.md).
-  // What depends on b comes from constant memory with a warp-uniform index: the matrix row, the quantiser pairs, the
+  // What depends on bp comes from constant memory with a warp-uniform index: the matrix row pair, the quantiser pairs, the
   // zigzag positions.  Returns the exact message length (last non-zero zigzag position + 1).
   int L = 0;
 #pragma unroll 1
-  for (int b = 0; b < 8; b++) {
-    float cb[8];
+  for (int bp = 0; bp < 4; bp++) {
+    f2 cb[8];
 #pragma unroll
-    for (int k = 0; k < 8; k++) cb[k] = kDctC[b * 8 + k];
+    for (int k = 0; k < 8; k++) cb[k] = mkp(kDctRowPairs.p[bp * 8 + k].x, kDctRowPairs.p[bp * 8 + k].y);
 #pragma unroll
-    for (int a2 = 0; a2 < 4; a2++) {
-      f2 acc = mul2(t[a2 * 8], dup(cb[0]));
+    for (int a = 0; a < 8; a++) {
+      f2 acc = mul2(dup(t[a * 4].x), cb[0]);
 #pragma unroll
-      for (int k = 1; k < 8; k++) acc = sum2(acc, mul2(t[a2 * 8 + k], dup(cb[k])), ONE);
-      const f2 r = mkp(qt.rqp[plane][a2 * 8 + b].x, qt.rqp[plane][a2 * 8 + b].y);
-      const f2 nq = mkp(qt.nqp[plane][a2 * 8 + b].x, qt.nqp[plane][a2 * 8 + b].y);
+      for (int k = 1; k < 8; k++) acc = sum2(acc, mul2(dup((k & 1) ? t[a * 4 + (k >> 1)].y : t[a * 4 + (k >> 1)].x), cb[k]), ONE);
+      const f2 r = mkp(qt.rqp[plane][bp * 8 + a].x, qt.rqp[plane][bp * 8 + a].y);
+      const f2 nq = mkp(qt.nqp[plane][bp * 8 + a].x, qt.nqp[plane][bp * 8 + a].y);
       const f2 q0 = mul2(acc, r);
       const f2 rem = fma2(nq, q0, acc);
       const f2 q1 = fma2(rem, r, q0);
       const f2 rr = add2_rz(q1, half_like(q1));
       const int na = __float2int_rz(rr.x), nb = __float2int_rz(rr.y);
-      const int za = kZigzagOf[(2 * a2) * 8 + b], zb = kZigzagOf[(2 * a2 + 1) * 8 + b];
-      zcol[za * kTileBlocks] = (uint16_t)na;
-      zcol[zb * kTileBlocks] = (uint16_t)nb;
+      const int za = kZigzagOf[a * 8 + 2 * bp], zb = kZigzagOf[a * 8 + 2 * bp + 1];
+      zcol[za * kEncTile] = (uint16_t)na;
+      zcol[zb * kEncTile] = (uint16_t)nb;
       if (na != 0) L = max(L, za + 1);
       if (nb != 0) L = max(L, zb + 1);
     }
@@ -782,15 +826,17 @@ MYB_D int fdct_quant_block(const uint32_t (&raw)[16], const QTables& qt, int pla
 //                     fast-path instantiation that fits the warp, blocks with more are queued.
 // capi.cu picks the build from the share of blocks the previous launch on the context queued.
 template <bool kInPlace>
-__global__ void __launch_bounds__(kCtaThreads, 6)
+__global__ void __launch_bounds__(kEncThreads, EncCfg<kInPlace>::kCtasPerSm)
     dct_compress_kernel(const __grid_constant__ EncParams P, const __grid_constant__ QTables qt) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  EncSmem& sm = *reinterpret_cast<EncSmem*>(smem_raw);
+  using Cfg = EncCfg<kInPlace>;
+  constexpr int kStageBytes = Cfg::kStage;
+  EncSmemT<kInPlace>& sm = *reinterpret_cast<EncSmemT<kInPlace>*>(smem_raw);
   const int tid = threadIdx.x;
   const FrameGeom& g = P.g;
   uint8_t* const wbase = sm.coder[tid >> 5];
   const int lane = tid & 31;
-  F8Scratch f8{reinterpret_cast<uint32_t*>(wbase) + lane, wbase + 2048, lane};
+  F8Scratch f8{reinterpret_cast<uint32_t*>(wbase) + lane, wbase + Cfg::kSlotRows * 128, lane};
   ZShared z{&sm.zz[0][tid]};
   uint8_t* const overflow = P.ws.overflow + (uint64_t)blockIdx.x * (kEncTile * 256u);
   PH_INIT();
@@ -816,8 +862,8 @@ __global__ void __launch_bounds__(kCtaThreads, 6)
     // A tile is kEncPasses passes of 128 blocks (one per thread) so that the serial look-back chain advances
     // 512 blocks per hop; each pass runs phase A (DCT) and phase B (entropy coding) and appends to the staging area.
 #pragma unroll 1
-    for (uint32_t pass = 0; pass * kTileBlocks < tc.nblk; pass++) {
-      const uint32_t blk = pass * kTileBlocks + tid;
+    for (uint32_t pass = 0; pass * kEncTile < tc.nblk; pass++) {
+      const uint32_t blk = pass * kEncTile + tid;
       const bool live = blk < tc.nblk;
       // ---- phase A: load the block, forward DCT, quantise, coefficients (zigzag order) to shared memory ----
       int L;
@@ -845,7 +891,7 @@ __global__ void __launch_bounds__(kCtaThreads, 6)
       uint32_t mine = (uint32_t)tid;  // the block (of this pass) this thread codes
       if (kSortBlocks) {
         sm.msg_len[tid] = (uint8_t)L;
-        if (tid < 68) sm.hist[tid] = 0;
+        if (kSortBlocks && tid < 68) sm.hist[tid] = 0;
         __syncthreads();
         const uint32_t within = atomicAdd(&sm.hist[L], 1u);
         __syncthreads();
@@ -871,11 +917,11 @@ __global__ void __launch_bounds__(kCtaThreads, 6)
         L = sm.msg_len[mine];
       }
       PH(2);  // block sort
-      const uint32_t mblk = pass * kTileBlocks + mine;
+      const uint32_t mblk = pass * kEncTile + mine;
       const bool mlive = mblk < tc.nblk;
       ZShared zm{&sm.zz[0][mine]};
       {  // empty the warp's hash table (2 KB, 64 bytes per lane)
-        uint4* q = reinterpret_cast<uint4*>(wbase + 2048);
+        uint4* q = reinterpret_cast<uint4*>(wbase + Cfg::kSlotRows * 128);
 #pragma unroll
         for (int j = 0; j < 4; j++) q[lane + 32 * j] = make_uint4(~0u, ~0u, ~0u, ~0u);
       }
@@ -956,7 +1002,7 @@ __global__ void __launch_bounds__(kCtaThreads, 6)
         __syncthreads();
         uint32_t before = 0, tot = 0;
 #pragma unroll
-        for (int w = 0; w < kCtaThreads / 32; w++) {
+        for (int w = 0; w < kEncThreads / 32; w++) {
           const uint32_t v = sm.warp_sums[w];
           if (w < wid) before += v;
           tot += v;
@@ -1000,7 +1046,7 @@ __global__ void __launch_bounds__(kCtaThreads, 6)
         if (tid == 0) atomicOr(&P.ws.counters[1], kFlagCapacity);
       } else {
         const uint32_t split = sm.split < pass_total ? sm.split : pass_total;
-        copy_smem_to_global(P.ws.scratch + pos, sm.stage, split);
+        copy_smem_to_global<kEncThreads>(P.ws.scratch + pos, sm.stage, split);
       }
     }
     __syncthreads();  // shared memory is reused by the next tile
@@ -1032,7 +1078,7 @@ __global__ void __launch_bounds__(kCtaThreads, 7) heavy15_kernel(const __grid_co
   const int tid = threadIdx.x, lane = tid & 31;
   uint8_t* const wbase = sm.coder[tid >> 5];
   F8Scratch f8{reinterpret_cast<uint32_t*>(wbase) + lane, wbase + 2048, lane};
-  ZShared z{&sm.zz[0][tid]};
+  ZSharedT<kCtaThreads> z{&sm.zz[0][tid]};
   const uint32_t queued = P.ws.counters[4];
   const uint32_t count = queued < P.ws.heavy_cap ? queued : P.ws.heavy_cap;
   for (uint32_t g0 = blockIdx.x * kCtaThreads; g0 < count; g0 += gridDim.x * kCtaThreads) {
@@ -1550,12 +1596,6 @@ void launch_shard_done(const ShardPeers& peers, const Workspace& ws, uint64_t to
   g_launches++;
 }
 
-constexpr int kEncCtasPerSm = 6, kDecCtasPerSm = 6;  // resident CTAs per SM (registers and shared memory sized for it)
-int codec_grid_size(int device, bool encoder) {
-  int sms = 148;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-  return sms * (encoder ? kEncCtasPerSm : kDecCtasPerSm);
-}
 
 #ifndef MYYUVB_NO_TMA_STAGE
 #define MYYUVB_TMA_STAGE 1
@@ -1563,13 +1603,13 @@ int codec_grid_size(int device, bool encoder) {
 // ===================================================================================================
 // Decompression (one thread = one block; tile = 128 blocks; six CTAs per SM: 80 registers, 27 KB shared memory)
 // ===================================================================================================
-constexpr int kDecStageBytes = 8 * 1024;
+constexpr int kDecStageBytes = 8 * 1024 * kDecTile / 128;
 struct DecSmem {
-  int16_t coef[64][kTileBlocks];      // quantised coefficients [k][c] (row-major index), per block column; the
+  int16_t coef[64][kDecTile];      // quantised coefficients [k][c] (row-major index), per block column; the
                                       // dequantisation (coef * q, DCT.cpp:330-332) happens when the IDCT loads them
   alignas(16) uint8_t stage[kDecStageBytes + 16];  // the tile's chunk bytes, shifted by the source's offset in its 16-byte line
-  int16_t symtab[32][kTileBlocks];    // fast decoder: the block's symbols in canonical order
-  int16_t lenbase[8][kTileBlocks];    // fast decoder: symbol index offsets per code length
+  int16_t symtab[32][kDecTile];    // fast decoder: the block's symbols in canonical order
+  int16_t lenbase[8][kDecTile];    // fast decoder: symbol index offsets per code length
   float q[64];                        // dequantisation factors of the current plane, row-major
   uint16_t zoff[64];                  // per zigzag position: byte offset in a coef column
   uint32_t warp_sums[4];
@@ -1579,16 +1619,23 @@ struct DecSmem {
   alignas(8) unsigned long long stage_bar;  // mbarrier of the bulk copy into stage[]
 #endif
   // counting sort of the tile's blocks by chunk size (kSortDecBlocks): thread t decodes block perm[t]
-  uint32_t hist[64];
-  uint16_t boff[kTileBlocks];
-  uint8_t bsize[kTileBlocks];
-  uint8_t perm[kTileBlocks];
+  uint32_t hist[kDecThreads > 32 ? 64 : 1];
+  uint16_t boff[kDecThreads > 32 ? kDecTile : 1];
+  uint8_t bsize[kDecThreads > 32 ? kDecTile : 1];
+  uint8_t perm[kDecThreads > 32 ? kDecTile : 1];
   PH_MEMBER
 };
-static_assert(sizeof(DecSmem) <= 36 * 1024, "DecSmem must allow 6 CTAs per SM");
+constexpr int kDecCtasPerSm = kDecThreads > 32 ? 6 : 22;
+static_assert((sizeof(DecSmem) + 1024) * kDecCtasPerSm <= 228 * 1024, "DecSmem must allow kDecCtasPerSm CTAs per SM");
 // Thread t decodes the block of rank t in chunk-size order (4-byte bins): the lanes of a warp get messages of similar
 // length and, more often than not, the same sparse IDCT variant.  Three more CTA barriers per tile.
-constexpr bool kSortDecBlocks = true;
+constexpr bool kSortDecBlocks = kDecThreads > 32;
+
+int codec_grid_size(int device, bool encoder) {
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  return sms * (encoder ? kEncCtasPerSm : kDecCtasPerSm);
+}
 
 struct DecParams {
   const uint8_t* payloads;
@@ -1640,7 +1687,7 @@ MYB_D void idct_block(const int16_t* col, const float* q, float onef, uint32_t (
   for (int c = 0; c < 8; c++) {
     float bk[8];
 #pragma unroll
-    for (int k = 0; k < 8; k++) bk[k] = __fmul_rn((float)col[(k * 8 + c) * kTileBlocks], q[k * 8 + c]);
+    for (int k = 0; k < 8; k++) bk[k] = __fmul_rn((float)col[(k * 8 + c) * kDecTile], q[k * 8 + c]);
 #pragma unroll
     for (int a2 = 0; a2 < 4; a2++) {
       f2 acc = mul2(dup(bk[0]), mkp(dct_c(2 * a2), dct_c(2 * a2 + 1)));
@@ -1681,7 +1728,7 @@ MYB_D void idct_block_tri(const int16_t* col, const float* q, float onef, uint32
   for (int c = 0; c < K; c++) {
     float bk[K];
 #pragma unroll
-    for (int k = 0; k < K - c; k++) bk[k] = __fmul_rn((float)col[(k * 8 + c) * kTileBlocks], q[k * 8 + c]);
+    for (int k = 0; k < K - c; k++) bk[k] = __fmul_rn((float)col[(k * 8 + c) * kDecTile], q[k * 8 + c]);
 #pragma unroll
     for (int a2 = 0; a2 < 4; a2++) {
       f2 acc = mul2(dup(bk[0]), mkp(dct_c(2 * a2), dct_c(2 * a2 + 1)));
@@ -1772,7 +1819,7 @@ __global__ void __launch_bounds__(1024) dec_scan_planes_kernel(const __grid_cons
   }
 }
 
-__global__ void __launch_bounds__(kCtaThreads, 6)
+__global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm)
     dct_decompress_kernel(const __grid_constant__ DecParams P, const __grid_constant__ QTables qt) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   DecSmem& sm = *reinterpret_cast<DecSmem*>(smem_raw);
@@ -1804,11 +1851,10 @@ __global__ void __launch_bounds__(kCtaThreads, 6)
     const PlaneDesc d = reinterpret_cast<const PlaneDesc*>(P.ws.plane_desc)[(uint64_t)tc.frame * 3 + plane];
     if (!d.ok) continue;  // header error already flagged by parse_payload_kernel (uniform per CTA)
     if (q_plane != plane) {  // visible to all threads after the barriers of the size scan below
-      if (tid < 64) {
-        constexpr uint8_t zz[64] = {MYB_ZIGZAG_LIST};
-        const int pos = zz[tid];
-        sm.zoff[tid] = (uint16_t)(pos * kTileBlocks * 2);
-        sm.q[tid] = qt.q[plane][tid];
+      constexpr uint8_t zz[64] = {MYB_ZIGZAG_LIST};
+      for (int i = tid; i < 64; i += kDecThreads) {
+        sm.zoff[i] = (uint16_t)(zz[i] * kDecTile * 2);
+        sm.q[i] = qt.q[plane][i];
       }
       q_plane = plane;
     }
@@ -1849,15 +1895,18 @@ __global__ void __launch_bounds__(kCtaThreads, 6)
       }
 #else
       uint4* dst = reinterpret_cast<uint4*>(sm.stage);
-      for (uint32_t v = tid; v < full; v += kCtaThreads) dst[v] = __ldg(src + v);
+      for (uint32_t v = tid; v < full; v += kDecThreads) dst[v] = __ldg(src + v);
 #endif
       const uint32_t done = full << 4;  // bytes of stage[] filled so far (counted from the aligned start)
       if (tid < mis + n - done) sm.stage[done + tid] = __ldg(content - mis + done + tid);
     }
     uint32_t scanned;
-    const uint32_t off = cta_exclusive_scan(size, sm.warp_sums, &scanned);
+    const uint32_t off = cta_exclusive_scan<kDecThreads>(size, sm.warp_sums, &scanned);
+    {  // the whole coefficient array, 128 bits per store (the columns are only written between the next barrier and the IDCT)
+      uint4* z4 = reinterpret_cast<uint4*>(&sm.coef[0][0]);
 #pragma unroll
-    for (int i = 0; i < 64; i++) col[i * kTileBlocks] = 0;
+      for (int j = 0; j < (int)(sizeof(sm.coef) / 16 / kDecThreads); j++) z4[tid + j * kDecThreads] = make_uint4(0u, 0u, 0u, 0u);
+    }
     if (kSortDecBlocks) {
       sm.boff[tid] = (uint16_t)off;
       sm.bsize[tid] = (uint8_t)size;
@@ -1909,7 +1958,7 @@ __global__ void __launch_bounds__(kCtaThreads, 6)
       auto emit = [&](int j, int v) {
         *reinterpret_cast<int16_t*>(reinterpret_cast<uint8_t*>(col) + sm.zoff[j]) = (int16_t)v;
       };
-      const DecScratch<kTileBlocks> ds{&sm.symtab[0][tid], &sm.lenbase[0][tid]};
+      const DecScratch<kDecTile> ds{&sm.symtab[0][tid], &sm.lenbase[0][tid]};
       int err = huff_decode_fast(chunk, (int)size, ds, emit, &nsym, WarpLockstep{});
       if (__any_sync(0xffffffffu, err == 2)) {  // a table the fast decoder does not take: the step-by-step decoder, for those lanes
         int cnt = 0;
@@ -1973,15 +2022,15 @@ void compress_code_and_scan(const EncParams& P, const QTables& qt, cudaStream_t 
   const Workspace& ws = P.ws;
   const FrameGeom& g = P.g;
   if (first_use_on_device(0)) {
-    cudaFuncSetAttribute(dct_compress_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncSmem));
-    cudaFuncSetAttribute(dct_compress_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncSmem));
+    cudaFuncSetAttribute(dct_compress_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncSmemT<false>));
+    cudaFuncSetAttribute(dct_compress_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncSmemT<true>));
   }
   cudaMemsetAsync(ws.counters, 0, 4, s);       // ticket only; error flags accumulate until read
   cudaMemsetAsync(ws.counters + 2, 0, 28, s);  // scratch bump allocator, queue of deferred blocks, lists of those with > 15 and > 32 symbols, list of tiles with queued blocks
   const int grid = (int)(P.total_tiles < (uint32_t)ws.grid ? P.total_tiles : (uint32_t)ws.grid);
   if (ws.k_begin) cudaEventRecord(ws.k_begin, s);
-  if (ws.code_in_place) dct_compress_kernel<true><<<grid, kCtaThreads, sizeof(EncSmem), s>>>(P, qt);
-  else dct_compress_kernel<false><<<grid, kCtaThreads, sizeof(EncSmem), s>>>(P, qt);
+  if (ws.code_in_place) dct_compress_kernel<true><<<grid, kEncThreads, sizeof(EncSmemT<true>), s>>>(P, qt);
+  else dct_compress_kernel<false><<<grid, kEncThreads, sizeof(EncSmemT<false>), s>>>(P, qt);
   if (ws.heavy_cap) {
     if (first_use_on_device(1)) {
       cudaFuncSetAttribute(heavy15_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Heavy15Smem));
@@ -2230,7 +2279,7 @@ void launch_decompress_shard(const uint8_t* payload, uint64_t payload_size, cons
     dec_tile_totals_kernel<<<want < 148u * 8 ? want : 148u * 8, 256, 0, s>>>(P);
     dec_scan_planes_kernel<<<3, 1024, 0, s>>>(P);
     const int grid = (int)(P.total_tiles < (uint32_t)ws.grid ? P.total_tiles : (uint32_t)ws.grid);
-    dct_decompress_kernel<<<grid, kCtaThreads, sizeof(DecSmem), s>>>(P, qt);
+    dct_decompress_kernel<<<grid, kDecThreads, sizeof(DecSmem), s>>>(P, qt);
     g_launches += 4;
   }
   if (ws.k_end) cudaEventRecord(ws.k_end, s);
@@ -2278,7 +2327,7 @@ void launch_decompress(const uint8_t* d_payloads, const uint64_t* d_offsets, con
   }
   dec_scan_planes_kernel<<<g.n_frames * 3, 1024, 0, s>>>(P);
   const int grid = (int)(P.total_tiles < (uint32_t)ws.grid ? P.total_tiles : (uint32_t)ws.grid);
-  dct_decompress_kernel<<<grid, kCtaThreads, sizeof(DecSmem), s>>>(P, qt);
+  dct_decompress_kernel<<<grid, kDecThreads, sizeof(DecSmem), s>>>(P, qt);
   if (ws.k_end) cudaEventRecord(ws.k_end, s);  // the whole decompress sequence (4 kernels) is what gets timed
   g_launches += 4;
 }

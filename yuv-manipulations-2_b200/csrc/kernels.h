@@ -5,11 +5,21 @@
 
 namespace myyuvb {
 
-constexpr int kTileBlocks = 128;   // 8x8 blocks per pass of a CTA (one per thread)
-constexpr int kEncPasses = 1;      // compress: passes of 128 blocks per tile
-constexpr int kEncTile = kTileBlocks * kEncPasses;
-constexpr int kDecTile = kTileBlocks;
-constexpr int kCtaThreads = 128;   // threads per CTA of the codec kernels
+// A tile = the blocks one CTA of a codec kernel takes per ticket, one per thread.  Two shapes per kernel, chosen at build time:
+// 128 blocks per 4-warp CTA (blocks sorted across the tile, CTA barriers between the phases) or 32 blocks per 1-warp CTA
+// (-DMYB_ENC_WARP_TILES=1 / -DMYB_DEC_WARP_TILES=1: no warp ever waits for another one).
+#ifndef MYB_ENC_WARP_TILES
+#define MYB_ENC_WARP_TILES 0
+#endif
+#ifndef MYB_DEC_WARP_TILES
+#define MYB_DEC_WARP_TILES 0
+#endif
+constexpr int kEncThreads = MYB_ENC_WARP_TILES ? 32 : 128;  // threads per CTA of dct_compress_kernel
+constexpr int kDecThreads = MYB_DEC_WARP_TILES ? 32 : 128;  // threads per CTA of dct_decompress_kernel
+constexpr int kEncPasses = 1;      // compress: passes per tile
+constexpr int kEncTile = kEncThreads * kEncPasses;
+constexpr int kDecTile = kDecThreads;
+constexpr int kCtaThreads = 128;   // threads per CTA of heavy15_kernel
 
 // error bits raised by kernels (OR-ed into Workspace::flags)
 enum : uint32_t {
@@ -26,8 +36,8 @@ struct QPair {
 };
 struct QTables {
   float q[3][64];        // row-major, decoder side (coef * q)
-  QPair rqp[3][32];      // [a/2 * 8 + b] = (1/q[a][b], 1/q[a+1][b]) for even a: the encoder's row-pair lanes
-  QPair nqp[3][32];      // [a/2 * 8 + b] = (-q[a][b], -q[a+1][b])
+  QPair rqp[3][32];      // [b/2 * 8 + a] = (1/q[a][b], 1/q[a][b+1]) for even b: the encoder's column-pair lanes
+  QPair nqp[3][32];      // [b/2 * 8 + a] = (-q[a][b], -q[a][b+1])
 };
 
 // Geometry shared by all frames of a batch.
