@@ -5,7 +5,8 @@
 import csv, importlib, pathlib, struct, sys
 ROOT = pathlib.Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
-W, H, N = 3840, 2160, 8
+import os
+W, H, N = 3840, 2160, int(os.environ.get("ONE_PASS_FRAMES", "8"))
 if sys.argv[1] == "--parse":
     rows = list(csv.reader(open(sys.argv[2])))
     hi = next(i for i, r in enumerate(rows) if "Kernel Name" in r)

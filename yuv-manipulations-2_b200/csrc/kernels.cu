@@ -1071,6 +1071,10 @@ __global__ void __launch_bounds__(kEncThreads, EncCfg<kInPlace>::kCtasPerSm)
 struct Heavy15Smem {
   uint16_t zz[64][kCtaThreads];
   alignas(16) uint8_t coder[kCtaThreads / 32][kWarpScratchBytes];
+  // the CTA's blocks change hands after the histogram, ordered by their number of distinct symbols
+  uint32_t recx[kCtaThreads], recy[kCtaThreads];
+  uint32_t bins[16];
+  uint8_t key[kCtaThreads], len[kCtaThreads], perm[kCtaThreads];
 };
 __global__ void __launch_bounds__(kCtaThreads, 7) heavy15_kernel(const __grid_constant__ EncParams P, uint32_t* __restrict__ overflow) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -1111,9 +1115,66 @@ __global__ void __launch_bounds__(kCtaThreads, 7) heavy15_kernel(const __grid_co
       overflow[atomicAdd(&P.ws.counters[5], 1u)] = idx;
       nsym = 0;
     }
-    const FastPlan pl = huff_fast_plan(nsym, L == 0 ? 1 : L, f8, WarpLockstep{});
-    huff_fast_emit(z, pl, f8, P.ws.heavy_bytes + (uint64_t)idx * 256, WarpLockstep{});
-    if (live && !over) {
+#ifndef MYB_H15_NOSORT
+    // The blocks of the CTA change hands, ordered by their number of distinct symbols: what the rest costs depends on it (the
+    // replay of the reference's rehash runs for a whole warp as soon as one lane has 14 keys, the merge loop runs n - 1 times),
+    // and the queue holds the blocks in tile order.  Thread t takes over the block of rank t: its coefficient words and slot
+    // words move into t's own columns (160 shared-memory accesses against the ~14 000 instructions a block costs here).
+    int Lm = L;
+    uint32_t idxm = idx;
+    {
+      sm.key[tid] = (uint8_t)nsym;
+      sm.len[tid] = (uint8_t)L;
+      sm.recx[tid] = (live && !over) ? rec.x : 0xffffffffu;
+      sm.recy[tid] = rec.y;
+      if (tid < 16) sm.bins[tid] = 0;
+      __syncthreads();
+      const uint32_t within = atomicAdd(&sm.bins[nsym], 1u);
+      __syncthreads();
+      if (tid < 32) {
+        const uint32_t v = lane < 16 ? sm.bins[lane] : 0u;
+        uint32_t inc = v;
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) {
+          const uint32_t nn = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += nn;
+        }
+        if (lane < 16) sm.bins[lane] = inc - v;
+      }
+      __syncthreads();
+      sm.perm[sm.bins[nsym] + within] = (uint8_t)tid;
+      __syncthreads();
+      const int sb = sm.perm[tid];
+      nsym = sm.key[sb];
+      Lm = sm.len[sb];
+      idxm = g0 + (uint32_t)sb;
+      rec.x = sm.recx[sb];
+      rec.y = sm.recy[sb];
+      uint32_t cw[32];
+#pragma unroll
+      for (int i = 0; i < 32; i++) cw[i] = (uint32_t)sm.zz[2 * i][sb] | ((uint32_t)sm.zz[2 * i + 1][sb] << 16);
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < 32; i++) {
+        sm.zz[2 * i][tid] = (uint16_t)cw[i];
+        sm.zz[2 * i + 1][tid] = (uint16_t)(cw[i] >> 16);
+      }
+      const uint32_t* from = reinterpret_cast<const uint32_t*>(sm.coder[sb >> 5]) + (sb & 31);
+#pragma unroll
+      for (int i = 0; i < 16; i++) cw[i] = from[i * 32];
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < 16; i++) f8.slot(i) = cw[i];
+    }
+    const bool mlive = rec.x != 0xffffffffu;
+#else
+    const int Lm = L;
+    const uint32_t idxm = idx;
+    const bool mlive = live && !over;
+#endif
+    const FastPlan pl = huff_fast_plan(nsym, Lm == 0 ? 1 : Lm, f8, WarpLockstep{});
+    huff_fast_emit(z, pl, f8, P.ws.heavy_bytes + (uint64_t)idxm * 256, WarpLockstep{});
+    if (mlive) {
       const uint32_t size = (uint32_t)pl.size();
       P.ws.chunk_sizes[rec.x] = (uint8_t)size;
       atomicAdd(&P.ws.tile_total[rec.y], size);
@@ -1140,8 +1201,13 @@ __global__ void __launch_bounds__(kHeavyThreads) heavy_blocks_kernel(const __gri
   const uint32_t queued = P.ws.counters[list_counter];
   const uint32_t count = queued < P.ws.heavy_cap ? queued : P.ws.heavy_cap;  // slots past the capacity were never handed out
   typename HeavySmem<CAP>::Scratch bs{&sm.bytes[0][threadIdx.x], &sm.syms[0][threadIdx.x]};
-  for (uint32_t g0 = blockIdx.x * kHeavyThreads; g0 < count; g0 += gridDim.x * kHeavyThreads) {
-    uint32_t idx = g0 + threadIdx.x;
+  // A warp's pass through the general code takes as long as its slowest lane (tens of microseconds), so a list that does not
+  // fill the grid is spread thin: `per` blocks per warp instead of 32 (natural content at q 50 lists 0.4 % of its blocks).
+  const uint32_t lane = threadIdx.x & 31u, warps = gridDim.x * (kHeavyThreads / 32);
+  uint32_t per = (count + warps - 1) / warps;
+  per = per < 1u ? 1u : (per > 32u ? 32u : per);
+  for (uint32_t g0 = (blockIdx.x * (kHeavyThreads / 32) + (threadIdx.x >> 5)) * per; g0 < count; g0 += warps * per) {
+    uint32_t idx = lane < per ? g0 + lane : 0xffffffffu;
     uint4 rec = make_uint4(0xffffffffu, 0u, 0u, 0u);
     if (idx < count) {
       idx = list[idx];
@@ -1156,7 +1222,7 @@ __global__ void __launch_bounds__(kHeavyThreads) heavy_blocks_kernel(const __gri
     const uint32_t size = live && fits ? (uint32_t)pl.size() : 0u;
     if (!live || !fits) pl.n = 0;
     ZSplitSlots<kHeavyThreads> zs{&sm.slot[0][threadIdx.x]};
-    huff_emit(zs, pl, bs, P.ws.heavy_bytes + (uint64_t)idx * 256, WarpLockstep{});
+    huff_emit(zs, pl, bs, P.ws.heavy_bytes + (uint64_t)(live ? idx : 0u) * 256, WarpLockstep{});
     if (live && fits) {
       P.ws.chunk_sizes[rec.x] = (uint8_t)size;
       atomicAdd(&P.ws.tile_total[rec.y], size);
@@ -1308,78 +1374,103 @@ __global__ void __launch_bounds__(256) place_tiles_kernel(const __grid_constant_
   }
 }
 
-// The tiles that hold queued blocks (listed by place_tiles_kernel), a warp per tile; a kernel of its own because the weaving
-// below needs 80 registers and the plain copy above lives on having 64 warps per SM in flight.  A batch without such tiles
-// pays one empty launch.
-__global__ void __launch_bounds__(256) place_heavy_tiles_kernel(const __grid_constant__ EncParams P) {
+// The tiles that hold queued blocks (listed by place_tiles_kernel), a warp per tile; a kernel of its own because the plain copy
+// above lives on having 64 warps per SM in flight.  A batch without such tiles pays one empty launch.
+// The scratch area holds the chunks of the tile's other blocks back to back, the queued ones sit in their 256-byte slots.
+// The payload bytes of the tile are therefore a sequence of SEGMENTS that are contiguous at both ends: a queued block's chunk,
+// or the run of chunks between two queued blocks (natural content at q 50: 13 queued blocks per tile, so 27 segments instead
+// of 128 chunks).  Every lane looks at four consecutive blocks, two warp scans give each block its place in the payload and
+// in the scratch stream, the segment starts go to a per-warp list in shared memory, and the segments are copied eight per
+// step: all loads of a step are issued before its first store, so a step costs one memory latency.
+constexpr int kPlaceWarps = 8;
+__global__ void __launch_bounds__(kPlaceWarps * 32, 4) place_heavy_tiles_kernel(const __grid_constant__ EncParams P) {
+  __shared__ uint32_t seg_dst[kPlaceWarps][kEncTile + 4];        // payload offset (inside the tile) where segment i starts; [S] = tile bytes
+  __shared__ const uint8_t* seg_src[kPlaceWarps][kEncTile + 4];  // its first source byte
   const FrameGeom& g = P.g;
-  const uint32_t lane = threadIdx.x & 31, warps = gridDim.x * (blockDim.x >> 5);
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5, warps = gridDim.x * (blockDim.x >> 5);
   const uint32_t count = P.ws.counters[6];
-  {
-    for (uint32_t e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < count; e += warps) {
-      const uint32_t tile = P.ws.heavy_list[e];
-      const TileCoord tc = tile_coord(g, tile);
-      const int plane = (int)tc.plane;
-      const uint32_t total = P.ws.tile_total[tile] & 0x7fffffffu;
-      const u64 src = P.ws.tile_pos[tile];
-      const u64 pos = tile_out_pos(P, tc, tile);
-      if (pos + total > P.out_cap) {
-        if (lane == 0) atomicOr(&P.ws.counters[1], kFlagCapacity);
-        continue;
-      }
-      // A tile with queued blocks: the scratch area holds the chunks of the other blocks back to back, the queued ones sit
-      // in their slots.  Every lane takes four consecutive blocks; two warp scans give each block its place in the
-      // payload and in the scratch stream; the chunks are then copied eight at a time.
-      const u64 gblk0 = (u64)tc.frame * g.nblk_frame + (plane > 0 ? g.nblk[0] : 0) + (plane > 1 ? g.nblk[1] : 0) + tc.k0;
-      uint32_t sz[4], sl[4], all = 0, light = 0;
+  constexpr int kPer = (kEncTile + 31) / 32;  // blocks per lane
+  for (uint32_t e = blockIdx.x * (blockDim.x >> 5) + wid; e < count; e += warps) {
+    const uint32_t tile = P.ws.heavy_list[e];
+    const TileCoord tc = tile_coord(g, tile);
+    const int plane = (int)tc.plane;
+    const uint32_t total = P.ws.tile_total[tile] & 0x7fffffffu;
+    const u64 src = P.ws.tile_pos[tile];
+    const u64 pos = tile_out_pos(P, tc, tile);
+    if (pos + total > P.out_cap) {
+      if (lane == 0) atomicOr(&P.ws.counters[1], kFlagCapacity);
+      continue;
+    }
+    const u64 gblk0 = (u64)tc.frame * g.nblk_frame + (plane > 0 ? g.nblk[0] : 0) + (plane > 1 ? g.nblk[1] : 0) + tc.k0;
+    uint32_t sz[kPer], sl[kPer], all = 0, light = 0;
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const uint32_t b = 4 * lane + j;
-        sz[j] = b < tc.nblk ? P.ws.chunk_sizes[gblk0 + b] : 0u;
-        sl[j] = b < tc.nblk ? P.ws.block_slot[gblk0 + b] : 0xffffffffu;
-        all += sz[j];
-        light += sl[j] == 0xffffffffu ? sz[j] : 0u;
-      }
-      uint32_t dsta = all, srca = light;  // inclusive scans over the lanes
+    for (int j = 0; j < kPer; j++) {
+      const uint32_t b = kPer * lane + j;
+      sz[j] = b < tc.nblk ? P.ws.chunk_sizes[gblk0 + b] : 0u;
+      sl[j] = b < tc.nblk ? P.ws.block_slot[gblk0 + b] : 0xffffffffu;
+      all += sz[j];
+      light += sl[j] == 0xffffffffu ? sz[j] : 0u;
+    }
+    // segment starts among this lane's blocks: every queued block, and every block that follows a queued one (or opens the tile)
+    const uint32_t last_heavy = sl[kPer - 1] != 0xffffffffu ? 1u : 0u;
+    uint32_t prev_heavy = __shfl_up_sync(0xffffffffu, last_heavy, 1);
+    if (lane == 0) prev_heavy = 1u;
+    uint32_t starts = 0, nstart = 0;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t a = __shfl_up_sync(0xffffffffu, dsta, o), b2 = __shfl_up_sync(0xffffffffu, srca, o);
-        if (lane >= (uint32_t)o) { dsta += a; srca += b2; }
-      }
-      uint32_t doff = dsta - all, soff = srca - light;
-      if (src + __shfl_sync(0xffffffffu, srca, 31) > P.ws.scratch_cap) {
-        if (lane == 0) atomicOr(&P.ws.counters[1], kFlagCapacity);
-        continue;
-      }
-      // Eight chunks (the blocks of two lanes) per step: all their loads are issued before the first store, so a step costs
-      // one memory latency instead of eight (a store waits for its load and holds back everything behind it).
-      for (uint32_t owner = 0; owner < 32; owner += 2) {
-        const uint8_t* from[8];
-        uint32_t to[8], n[8], nmax = 0;
+    for (int j = 0; j < kPer; j++) {
+      const uint32_t heavy = sl[j] != 0xffffffffu ? 1u : 0u;
+      if (heavy | prev_heavy) { starts |= 1u << j; nstart++; }
+      prev_heavy = heavy;
+    }
+    uint32_t dsta = all, srca = light, sega = nstart;  // inclusive scans over the lanes
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
-          uint32_t d = __shfl_sync(0xffffffffu, doff, owner + h), sc = __shfl_sync(0xffffffffu, soff, owner + h);
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t a = __shfl_up_sync(0xffffffffu, dsta, o), b2 = __shfl_up_sync(0xffffffffu, srca, o), c2 = __shfl_up_sync(0xffffffffu, sega, o);
+      if (lane >= (uint32_t)o) { dsta += a; srca += b2; sega += c2; }
+    }
+    const uint32_t nseg = __shfl_sync(0xffffffffu, sega, 31);
+    if (src + __shfl_sync(0xffffffffu, srca, 31) > P.ws.scratch_cap) {
+      if (lane == 0) atomicOr(&P.ws.counters[1], kFlagCapacity);
+      continue;
+    }
+    {
+      uint32_t d = dsta - all, sc = srca - light, si = sega - nstart;
 #pragma unroll
-          for (int j = 0; j < 4; j++) {
-            const uint32_t nn = __shfl_sync(0xffffffffu, sz[j], owner + h), slot = __shfl_sync(0xffffffffu, sl[j], owner + h);
-            from[4 * h + j] = slot == 0xffffffffu ? P.ws.scratch + src + sc : P.ws.heavy_bytes + (u64)slot * 256;
-            to[4 * h + j] = d;
-            n[4 * h + j] = nn;
-            nmax = nn > nmax ? nn : nmax;
-            d += nn;
-            if (slot == 0xffffffffu) sc += nn;
-          }
+      for (int j = 0; j < kPer; j++) {
+        const bool heavy = sl[j] != 0xffffffffu;
+        if (starts & (1u << j)) {
+          seg_dst[wid][si] = d;
+          seg_src[wid][si] = heavy ? P.ws.heavy_bytes + (u64)sl[j] * 256 : P.ws.scratch + src + sc;
+          si++;
         }
-        for (uint32_t i = lane; i < nmax; i += 32) {
-          uint8_t v[8];
+        d += sz[j];
+        if (!heavy) sc += sz[j];
+      }
+      if (lane == 31) seg_dst[wid][nseg] = dsta;  // = the tile's bytes
+    }
+    __syncwarp();
+    uint8_t* const out = P.out + pos;
+    for (uint32_t s0 = 0; s0 < nseg; s0 += 8) {
+      const uint8_t* from[8];
+      uint32_t to[8], n[8], nmax = 0;
 #pragma unroll
-          for (int c = 0; c < 8; c++) v[c] = i < n[c] ? from[c][i] : (uint8_t)0;
+      for (int c = 0; c < 8; c++) {
+        const uint32_t i = s0 + c < nseg ? s0 + c : nseg;  // past the end: an empty segment
+        to[c] = seg_dst[wid][i];
+        n[c] = (i < nseg ? seg_dst[wid][i + 1] : to[c]) - to[c];
+        from[c] = seg_src[wid][i < nseg ? i : 0];
+        nmax = n[c] > nmax ? n[c] : nmax;
+      }
+      for (uint32_t i = lane; i < nmax; i += 32) {
+        uint8_t v[8];
 #pragma unroll
-          for (int c = 0; c < 8; c++)
-            if (i < n[c]) P.out[pos + to[c] + i] = v[c];
-        }
+        for (int c = 0; c < 8; c++) v[c] = i < n[c] ? from[c][i] : (uint8_t)0;
+#pragma unroll
+        for (int c = 0; c < 8; c++)
+          if (i < n[c]) out[to[c] + i] = v[c];
       }
     }
+    __syncwarp();  // the list is reused by the warp's next tile
   }
 }
 
@@ -2059,7 +2150,7 @@ void compress_place_and_finalize(const EncParams& P, uint64_t* d_offsets, cudaSt
   const FrameGeom& g = P.g;
   const uint32_t pwant = (P.total_tiles + 7) / 8;
   place_tiles_kernel<<<(int)(pwant < 148u * 8 ? pwant : 148u * 8), 256, 0, s>>>(P);
-  if (ws.heavy_cap) place_heavy_tiles_kernel<<<(int)(pwant < 148u * 3 ? pwant : 148u * 3), 256, 0, s>>>(P);
+  if (ws.heavy_cap) place_heavy_tiles_kernel<<<(int)(pwant < 148u * 4 ? pwant : 148u * 4), kPlaceWarps * 32, 0, s>>>(P);
   {
     uint32_t slices = 0;
     for (int p = 0; p < 3; p++) slices += (g.nblk[p] + kSizeSlice - 1) / kSizeSlice;
