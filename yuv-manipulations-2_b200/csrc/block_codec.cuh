@@ -575,21 +575,10 @@ MYB_HD int huff_hist(Z& z, int L, bool live, const FastScratch<STRIDE>& F, const
   int n = 0;
   if (!live) L = 0;
   const int Lw = warp.max(L);
-#ifdef MYB_SWPIPE
-  uint32_t raw_next = z.raw(0);
-#endif
   MYB_NOUNROLL
   for (int i = 0; i < Lw; i++) {
-#ifdef MYB_SWPIPE
-    const uint32_t raw_now = raw_next;
-    raw_next = z.raw(i < 63 ? i + 1 : 63);
-#endif
     if (i < L && n <= CAP) {
-#ifdef MYB_SWPIPE
-      const uint32_t raw = raw_now;
-#else
       const uint32_t raw = z.raw(i);
-#endif
       const uint32_t tag = raw & 0x7ffu;
       uint32_t h = raw & 31u;
       uint32_t e = F.tab((int)h);
@@ -608,9 +597,7 @@ MYB_HD int huff_hist(Z& z, int L, bool live, const FastScratch<STRIDE>& F, const
       n += isnew ? 1 : 0;
       z.setraw(i, tag | (s << 11));
     }
-#ifndef MYB_SWPIPE
     warp.sync();
-#endif
   }
   if (live && L == 0) {  // all-zero block: the single symbol 0, one bit (Huffman.cpp:195-199)
     F.slot(0) = 1u;
@@ -1066,21 +1053,10 @@ MYB_HD void huff_fast_emit_n(Z& z, const FastPlan& pl, int nw, const FastScratch
   warp.sync();
   const int L = n > 0 ? pl.msg_len : 0;
   const int Lw = warp.max(L);
-#ifdef MYB_SWPIPE
-  uint32_t ce_next = F.codeword(z.slot(0));
-#endif
   MYB_NOUNROLL
   for (int k = 0; k < Lw; k++) {
-#ifdef MYB_SWPIPE
-    const uint32_t ce_now = ce_next;
-    ce_next = F.codeword(z.slot(k < 63 ? k + 1 : 63));
-#endif
     if (k < L) {
-#ifdef MYB_SWPIPE
-      const uint32_t ce = ce_now;
-#else
       const uint32_t ce = F.codeword(z.slot(k));
-#endif
       acc |= (ce & 0xffu) << nb;
       nb += (int)(ce >> 8);
       if (nb >= 8) {

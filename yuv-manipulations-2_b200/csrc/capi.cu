@@ -75,8 +75,7 @@ void make_qtables(const uint8_t quality[3], QTables* qt) {
       for (int a = 0; a < 8; a++) {
         const float q0 = qt->q[p][a * 8 + 2 * bp], q1 = qt->q[p][a * 8 + 2 * bp + 1];
         // correctly rounded reciprocals, used by the exact-division step in the kernel
-        qt->rqp[p][bp * 8 + a] = {1.0f / q0, 1.0f / q1};
-        qt->nqp[p][bp * 8 + a] = {-q0, -q1};
+        qt->rq[p][bp * 8 + a] = {1.0f / q0, 1.0f / q1, -q0, -q1};
       }
   }
 }

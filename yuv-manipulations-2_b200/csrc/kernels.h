@@ -31,13 +31,13 @@ enum : uint32_t {
 
 // Quantisation tables of the three planes, computed on the host with the reference's float expression
 // (DCT.cpp:286-290).  q = divisor / dequantisation factor, rq = correctly rounded 1/q.
-struct QPair {
-  float x, y;
+struct alignas(16) QQuad {
+  float rx, ry, nqx, nqy;
 };
-struct QTables {
+struct alignas(16) QTables {
   float q[3][64];        // row-major, decoder side (coef * q)
-  QPair rqp[3][32];      // [b/2 * 8 + a] = (1/q[a][b], 1/q[a][b+1]) for even b: the encoder's column-pair lanes
-  QPair nqp[3][32];      // [b/2 * 8 + a] = (-q[a][b], -q[a][b+1])
+  QQuad rq[3][32];       // [b/2 * 8 + a] = (1/q[a][b], 1/q[a][b+1], -q[a][b], -q[a][b+1]) for even b: the encoder's column-pair
+                         // lanes, one 128-bit uniform load per pair of coefficients
 };
 
 // Geometry shared by all frames of a batch.
@@ -45,6 +45,7 @@ struct FrameGeom {
   uint32_t width, height, n_frames;
   uint32_t pw[3], ph[3];          // plane width / height in pixels
   uint32_t bw[3];                 // plane width in 8x8 blocks
+  uint32_t bw_magic[3];           // floor(2^32 / bw): block index -> block row without a division (block_row_col)
   uint32_t nblk[3];               // blocks per plane
   uint32_t tile_blocks;           // blocks per tile (kEncTile or kDecTile)
   uint32_t tiles[3];              // tiles per plane
