@@ -51,10 +51,10 @@ def test_no_fma_contraction_in_sass(pkg):
     assert enc["FFMA"] == 0 and dec["FFMA"] == 0 and col["FFMA"] == 0
     # decoder: the full transform plus the triangular variants K = 4 and 7 (4 * sum_c (K - c - 1) + 32 * (K - 1) sums each)
     tri = sum(4 * (K * (K - 1) // 2) + 32 * (K - 1) for K in (4, 7))
-    # encoder: 224 sums of the first product (unrolled) + 28 of the second, whose loop over the output column is rolled,
-    # + 8 FMAs of the exact-division step in that loop body
-    assert enc["FFMA2"] == 224 + 28 + 8 and dec["FFMA2"] == 448 + tri
-    assert 256 + 32 <= enc["FMUL2"] <= 256 + 32 + 8 and 700 <= dec["FMUL2"] <= 512 + sum(2 * K * (K + 1) + 32 * K for K in (4, 7))  # identical products may be shared (exact)
+    # encoder: 224 sums of the first product (unrolled) + 56 of the second, whose loop over the output column PAIR is rolled
+    # (8 rows x 7 sums per iteration), + 16 FMAs of the exact-division step in that loop body (two per coefficient pair)
+    assert enc["FFMA2"] == 224 + 56 + 16 and dec["FFMA2"] == 448 + tri
+    assert 248 + 64 + 8 <= enc["FMUL2"] <= 256 + 64 + 8 and 700 <= dec["FMUL2"] <= 512 + sum(2 * K * (K + 1) + 32 * K for K in (4, 7))  # identical products may be shared (exact)
 
 
 def test_compress_bound(pkg):

@@ -677,7 +677,7 @@ void launch_iyuv_to_rgba(const uint8_t* d_iyuv, uint8_t* d_rgba, uint32_t w, uin
 // so no transposition or register shuffling is needed between the stages (cuobjdump: 960 FMUL2/FFMA2, 0 MOV).
 // ===================================================================================================
 #ifndef MYB_ENC_OCC7
-#define MYB_ENC_OCC7 0
+#define MYB_ENC_OCC7 1  // seven CTAs per SM for the queueing build (72 registers, 31 KB): compress -0.9 % synthetic, -1.8 % natural q50
 #endif
 // Entropy-coder scratch of the fast path is one 4 KB region per WARP, lanes interleaved (FastScratch<32>):
 //   slot words uint32[16][32] at 0, then 2 KB that are hash table, byte lists and heap in turn.
@@ -694,7 +694,11 @@ struct EncCfg {
   static constexpr int kSlotRows = kCompact ? kTileCap + 1 : 16;
   static constexpr int kWarpBytes = kSlotRows * 128 + 2048;
   static constexpr int kStage = (kCompact ? 1536 : 3 * 1024) * kEncTile / 128;  // shared-memory staging of one tile's chunk bytes
+#ifdef MYB_ENC_CTAS
+  static constexpr int kCtasPerSm = MYB_ENC_CTAS;  // experiment: fewer CTAs, more registers each
+#else
   static constexpr int kCtasPerSm = kEncThreads > 32 ? (kCompact ? 7 : 6) : 22;  // resident CTAs per SM (registers and shared memory sized for it)
+#endif
 };
 
 template <bool kInPlace>
