@@ -697,7 +697,8 @@ struct EncCfg {
 #ifdef MYB_ENC_CTAS
   static constexpr int kCtasPerSm = MYB_ENC_CTAS;  // experiment: fewer CTAs, more registers each
 #else
-  static constexpr int kCtasPerSm = kEncThreads > 32 ? (kCompact ? 7 : 6) : 22;  // resident CTAs per SM (registers and shared memory sized for it)
+  // resident CTAs per SM (registers and shared memory sized for it)
+  static constexpr int kCtasPerSm = kEncThreads == 256 ? 3 : kEncThreads == 64 ? 13 : kEncThreads == 32 ? 22 : (kCompact ? 7 : 6);
 #endif
 };
 
@@ -707,7 +708,7 @@ struct EncSmemT {
   uint16_t zz[64][kEncTile];                        // quantised coefficients, zigzag order; later slot ids
   alignas(16) uint8_t coder[kEncThreads / 32][Cfg::kWarpBytes];
   alignas(16) uint8_t stage[Cfg::kStage + 8];
-  uint32_t warp_sums[4];
+  uint32_t warp_sums[kEncThreads / 32 < 4 ? 4 : kEncThreads / 32];
   uint32_t tile;
   uint32_t split;
   uint32_t heavy;            // the tile holds a block that was queued for heavy_blocks_kernel
@@ -917,7 +918,9 @@ __global__ void __launch_bounds__(kEncThreads, EncCfg<kInPlace>::kCtasPerSm)
       uint32_t mine = (uint32_t)tid;  // the block (of this pass) this thread codes
       if (kSortBlocks) {
         sm.msg_len[tid] = (uint8_t)L;
-        if (kSortBlocks && tid < 68) sm.hist[tid] = 0;
+        if (kSortBlocks) {
+          for (int i = tid; i < 68; i += kEncThreads) sm.hist[i] = 0;
+        }
         __syncthreads();
         const uint32_t within = atomicAdd(&sm.hist[L], 1u);
         __syncthreads();
@@ -1718,7 +1721,7 @@ void launch_shard_done(const ShardPeers& peers, const Workspace& ws, uint64_t to
 #define MYYUVB_TMA_STAGE 1
 #endif
 // ===================================================================================================
-// Decompression (one thread = one block; tile = 128 blocks; six CTAs per SM: 80 registers, 27 KB shared memory)
+// Decompression (one thread = one block; tile = 256 blocks; three CTAs of eight warps per SM: 80 registers, 54 KB shared memory)
 // ===================================================================================================
 constexpr int kDecStageBytes = 8 * 1024 * kDecTile / 128;
 struct DecSmem {
@@ -1729,7 +1732,7 @@ struct DecSmem {
   int16_t lenbase[8][kDecTile];    // fast decoder: symbol index offsets per code length
   float q[64];                        // dequantisation factors of the current plane, row-major
   uint16_t zoff[64];                  // per zigzag position: byte offset in a coef column
-  uint32_t warp_sums[4];
+  uint32_t warp_sums[kDecThreads / 32 < 4 ? 4 : kDecThreads / 32];
   uint32_t tile;
   TileCoord tc;
   u64 base;
@@ -1743,7 +1746,7 @@ struct DecSmem {
   uint8_t perm[kDecThreads > 32 ? kDecTile : 1];
   PH_MEMBER
 };
-constexpr int kDecCtasPerSm = kDecThreads > 32 ? 6 : 22;
+constexpr int kDecCtasPerSm = kDecThreads == 256 ? 3 : kDecThreads == 128 ? 6 : kDecThreads == 64 ? 11 : 22;
 static_assert((sizeof(DecSmem) + 1024) * kDecCtasPerSm <= 228 * 1024, "DecSmem must allow kDecCtasPerSm CTAs per SM");
 // Thread t decodes the block of rank t in chunk-size order (4-byte bins): the lanes of a warp get messages of similar
 // length and, more often than not, the same sparse IDCT variant.  Three more CTA barriers per tile.
@@ -1885,8 +1888,8 @@ __global__ void __launch_bounds__(256) dec_tile_totals_kernel(const __grid_const
     if (d.ok) {
       const uint8_t* sizes = P.payloads + d.sizes_off + tc.k0;
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const uint32_t b = 4 * lane + j;
+      for (int j = 0; j < kDecTile / 32; j++) {
+        const uint32_t b = (kDecTile / 32) * lane + j;
         if (b < tc.nblk) sum += sizes[b];
       }
     }
