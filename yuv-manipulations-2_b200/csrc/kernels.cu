@@ -739,6 +739,86 @@ struct ZSharedT {  // accessor of one block's column in EncSmem::zz (S columns)
   MYB_D void setraw(int i, uint32_t w) { col[i * S] = (uint16_t)w; }
   MYB_D int slot(int i) const { return (col[i * S] >> 11) & 15; }
 };
+// huff_hist (block_codec.cuh) for the layout the kernels use -- coefficient words in a shared-memory column with a stride of
+// ZSTRIDE bytes, FastScratch<32> -- written out in PTX.  Same steps, same results; what it removes is what ptxas made of the
+// C++ loop: 45 instructions per coefficient (the table's address from the thread index again in every iteration, the slot's
+// address twice, three instructions for "n += isnew", two BSSY/BSYNC pairs around a body that every lane of the warp runs
+// anyway).  Here an iteration is 29 instructions, stores predicated, one branch for the rare collision.  An idle lane may
+// read slot row CAP + 1 (the first row of the hash table): a valid address, and it stores nothing.
+#ifndef MYB_NO_PTX_HIST
+template <int CAP, int ZSTRIDE>
+MYB_D int huff_hist_smem(uint16_t* zcol, int L, bool live, const F8Scratch& F) {
+  static_assert(CAP <= kFastCap, "slot numbers are 4 bits");
+  if (!live) L = 0;
+  const int Lw = __reduce_max_sync(0xffffffffu, L);
+  int n = 0;
+  if (Lw > 0) {
+    const uint32_t zp = (uint32_t)__cvta_generic_to_shared(zcol);
+    const uint32_t tb = (uint32_t)__cvta_generic_to_shared(F.aux) + 2u * (uint32_t)F.lane;
+    const uint32_t sb = (uint32_t)__cvta_generic_to_shared(F.sc);
+    asm volatile(
+        "{\n\t"
+        ".reg .pred act, isnew, pn, pc, pl;\n\t"
+        ".reg .u32 i, zp, raw, tag, ha, ta, e, es, s, sa, word, t;\n\t"
+        "mov.u32 i, 0;\n\t"
+        "mov.u32 zp, %1;\n"
+        "HLOOP:\n\t"
+        "setp.lt.s32 act, i, %4;\n\t"
+        "setp.le.and.s32 act, %0, %6, act;\n\t"
+        "ld.shared.u16 raw, [zp];\n\t"
+        "and.b32 tag, raw, 0x7ff;\n\t"
+        "shl.b32 ha, raw, 6;\n\t"
+        "and.b32 ha, ha, 0x7c0;\n\t"
+        "add.u32 ta, %2, ha;\n\t"
+        "ld.shared.u16 e, [ta];\n\t"
+        "shr.u32 es, e, 4;\n\t"
+        "setp.ne.u32 pc, es, tag;\n\t"
+        "setp.ne.and.u32 pc, e, 0xffff, pc;\n\t"
+        "and.pred pc, pc, act;\n\t"
+        "@!pc bra HFOUND;\n"
+        "HPROBE:\n\t"  // rare: two values of the block share their low five bits
+        "add.u32 ha, ha, 64;\n\t"
+        "and.b32 ha, ha, 0x7c0;\n\t"
+        "add.u32 ta, %2, ha;\n\t"
+        "ld.shared.u16 e, [ta];\n\t"
+        "shr.u32 es, e, 4;\n\t"
+        "setp.ne.u32 pc, es, tag;\n\t"
+        "setp.ne.and.u32 pc, e, 0xffff, pc;\n\t"
+        "@pc bra HPROBE;\n"
+        "HFOUND:\n\t"
+        "setp.eq.u32 isnew, e, 0xffff;\n\t"
+        "and.b32 s, e, 15;\n\t"
+        "selp.u32 s, %0, s, isnew;\n\t"
+        "mad.lo.u32 sa, s, 128, %3;\n\t"
+        "shl.b32 word, raw, 16;\n\t"
+        "@!isnew ld.shared.u32 word, [sa];\n\t"
+        "add.u32 word, word, 1;\n\t"
+        "and.pred pn, act, isnew;\n\t"
+        "@act st.shared.u32 [sa], word;\n\t"
+        "mad.lo.u32 t, s, 2048, tag;\n\t"
+        "@act st.shared.u16 [zp], t;\n\t"
+        "shl.b32 t, tag, 4;\n\t"
+        "or.b32 t, t, s;\n\t"
+        "@pn st.shared.u16 [ta], t;\n\t"
+        "@pn add.s32 %0, %0, 1;\n\t"
+        "add.u32 zp, zp, %7;\n\t"
+        "add.u32 i, i, 1;\n\t"
+        "setp.lt.s32 pl, i, %5;\n\t"
+        "@pl bra HLOOP;\n\t"
+        "}"
+        : "+r"(n)
+        : "r"(zp), "r"(tb), "r"(sb), "r"(L), "r"(Lw), "n"(CAP), "n"(ZSTRIDE)
+        : "memory");
+  }
+  if (live && L == 0) {  // all-zero block: the single symbol 0, one bit (Huffman.cpp:195-199)
+    F.slot(0) = 1u;
+    zcol[0] = 0;
+    n = 1;
+  }
+  return n > CAP ? -1 : n;
+}
+#endif
+
 using ZShared = ZSharedT<kEncTile>;
 struct EncParams {
   const uint8_t* src;
@@ -955,7 +1035,11 @@ __global__ void __launch_bounds__(kEncThreads, EncCfg<kInPlace>::kCtasPerSm)
         for (int j = 0; j < 4; j++) q[lane + 32 * j] = make_uint4(~0u, ~0u, ~0u, ~0u);
       }
       __syncwarp();
+#ifndef MYB_NO_PTX_HIST
+      int nsym = huff_hist_smem<kInPlace ? kFastCap : kTileCap, kEncTile * 2>(zm.col, L, mlive, f8);
+#else
       int nsym = huff_hist<kInPlace ? kFastCap : kTileCap>(zm, L, mlive, f8, WarpLockstep{});
+#endif
       {  // statistics for the choice of build: blocks with more than kTileCap symbols
         const uint32_t dm = __ballot_sync(0xffffffffu, nsym < 0 || nsym > kTileCap);
         if (dm != 0u && lane == 0) atomicAdd(&P.ws.counters[8], (uint32_t)__popc(dm));
@@ -1138,7 +1222,11 @@ __global__ void __launch_bounds__(kCtaThreads, 7) heavy15_kernel(const __grid_co
     }
     __syncwarp();
     const int L = live ? (int)rec.z : 0;
+#ifndef MYB_NO_PTX_HIST
+    int nsym = huff_hist_smem<kFastCap, kCtaThreads * 2>(z.col, L, live, f8);
+#else
     int nsym = huff_hist<kFastCap>(z, L, live, f8, WarpLockstep{});
+#endif
     const bool over = nsym < 0;
     if (over) {
       overflow[atomicAdd(&P.ws.counters[5], 1u)] = idx;
