@@ -39,12 +39,20 @@ namespace myyuvb {
 // ---- warp cooperation policies -------------------------------------------------------------------
 struct NoWarp {  // host emulation and the out-of-line fallback path: every "lane" runs alone
   MYB_HD int max(int v) const { return v; }
+  MYB_HD int umax(int v) const { return v; }
   MYB_HD bool any(bool p) const { return p; }
   MYB_HD void sync() const {}
 };
 #if defined(__CUDACC__)
+struct WarpFree {  // every lane runs its own trip counts; the hardware reconverges the warp behind each loop
+  __device__ __forceinline__ int max(int v) const { return v; }
+  __device__ __forceinline__ int umax(int v) const { return __reduce_max_sync(0xffffffffu, v); }  // for choices the whole warp makes together
+  __device__ __forceinline__ bool any(bool p) const { return p; }
+  __device__ __forceinline__ void sync() const {}
+};
 struct WarpLockstep {  // all 32 lanes of the warp call the codec functions together
   __device__ __forceinline__ int max(int v) const { return __reduce_max_sync(0xffffffffu, v); }
+  __device__ __forceinline__ int umax(int v) const { return __reduce_max_sync(0xffffffffu, v); }
   __device__ __forceinline__ bool any(bool p) const { return __any_sync(0xffffffffu, p) != 0; }
   __device__ __forceinline__ void sync() const { __syncwarp(); }
 };
@@ -947,7 +955,7 @@ MYB_HD FastPlan huff_fast_plan_n(int n, int nw, int msg_len, const FastScratch<S
 // Two instantiations, chosen per warp: the compact one when no block of the warp has more than 8 symbols.
 template <int STRIDE, class W>
 MYB_HD FastPlan huff_fast_plan(int n, int msg_len, const FastScratch<STRIDE>& F, const W& warp) {
-  const int nw = warp.max(n);
+  const int nw = warp.umax(n);
   if (nw <= 8) return huff_fast_plan_n<8>(n, nw, msg_len, F, warp);
   return huff_fast_plan_n<kFastCap>(n, nw, msg_len, F, warp);
 }
@@ -1071,7 +1079,7 @@ MYB_HD void huff_fast_emit_n(Z& z, const FastPlan& pl, int nw, const FastScratch
 
 template <int STRIDE, class Z, class W>
 MYB_HD void huff_fast_emit(Z& z, const FastPlan& pl, const FastScratch<STRIDE>& F, uint8_t* dst, const W& warp) {
-  const int nw = warp.max(pl.n);
+  const int nw = warp.umax(pl.n);
   if (nw <= 8) huff_fast_emit_n<8>(z, pl, nw, F, dst, warp);
   else huff_fast_emit_n<kFastCap>(z, pl, nw, F, dst, warp);
 }
@@ -1231,8 +1239,10 @@ struct DecStream {
 template <int PAIRS, int STRIDE, class Emit, class W>
 MYB_HD void decode_stream(DecStream& st, const uint32_t (&kk)[4], int maxlen, const uint8_t* data, int data_bytes,
                           const DecScratch<STRIDE>& D, Emit& emit, const W& warp) {
-  while (warp.any(st.sh < st.rem && st.j < 64)) {
-    if (st.sh < st.rem && st.j < 64) {
+  // A plain per-lane loop: lanes that run out of symbols wait where the hardware reconverges the warp, behind the loop.
+  // Holding the lanes in step by hand (a vote per symbol, an inner test, a warp barrier) cost 4-5 % of the decoder's time.
+  while (st.sh < st.rem && st.j < 64) {
+    {
       if (st.sh > 24) {  // reload the window at the byte that holds the next bit
         st.byte0 += st.sh >> 3;
         st.rem -= st.sh & ~7;
@@ -1255,8 +1265,8 @@ MYB_HD void decode_stream(DecStream& st, const uint32_t (&kk)[4], int maxlen, co
         st.sh += len;
       }
     }
-    warp.sync();
   }
+  warp.sync();
 }
 
 // Returns 0 (ok), 1 (error: the conditions huff_decode_block reports) or 2 (not handled here, nothing emitted).
@@ -1279,8 +1289,8 @@ MYB_HD int huff_decode_fast(const uint8_t* chunk, int size, const DecScratch<STR
   int n = 0;
   {
     int gi = 0, ci = 0, cnt = 0, glen = 0, symbase = 0;
-    while (warp.any(!err && !general && (ci < cnt || gi < table_bytes))) {
-      if (!err && !general && (ci < cnt || gi < table_bytes)) {
+    while (!err && !general && (ci < cnt || gi < table_bytes)) {
+      {
         if (ci == cnt) {  // next group
           const int info = groups[gi];
           const int len = (info >> 5) + 1, c = (info & 31) + 1;

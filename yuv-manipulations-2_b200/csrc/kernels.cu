@@ -750,7 +750,11 @@ template <int CAP, int ZSTRIDE>
 MYB_D int huff_hist_smem(uint16_t* zcol, int L, bool live, const F8Scratch& F) {
   static_assert(CAP <= kFastCap, "slot numbers are 4 bits");
   if (!live) L = 0;
+#ifdef MYB_FREE_HIST
+  const int Lw = L;
+#else
   const int Lw = __reduce_max_sync(0xffffffffu, L);
+#endif
   int n = 0;
   if (Lw > 0) {
     const uint32_t zp = (uint32_t)__cvta_generic_to_shared(zcol);
@@ -820,6 +824,16 @@ MYB_D int huff_hist_smem(uint16_t* zcol, int L, bool live, const F8Scratch& F) {
 #endif
 
 using ZShared = ZSharedT<kEncTile>;
+#ifdef MYB_FREE_FAST
+using FastPol = WarpFree;
+#else
+using FastPol = WarpLockstep;
+#endif
+#ifdef MYB_FREE_GENERAL
+using GenPol = WarpFree;
+#else
+using GenPol = WarpLockstep;
+#endif
 struct EncParams {
   const uint8_t* src;
   uint8_t* out;
@@ -1078,14 +1092,14 @@ __global__ void __launch_bounds__(kEncThreads, EncCfg<kInPlace>::kCtasPerSm)
       uint32_t size;
       const int nw = __reduce_max_sync(0xffffffffu, nsym);
       if (__builtin_expect(fast, 1)) {
-        if (kInPlace) pl8 = huff_fast_plan(nsym, L == 0 ? 1 : L, f8, WarpLockstep{});
-        else pl8 = huff_fast_plan_n<kTileCap>(nsym, nw, L == 0 ? 1 : L, f8, WarpLockstep{});
+        if (kInPlace) pl8 = huff_fast_plan(nsym, L == 0 ? 1 : L, f8, FastPol{});
+        else pl8 = huff_fast_plan_n<kTileCap>(nsym, nw, L == 0 ? 1 : L, f8, FastPol{});
         size = (uint32_t)pl8.size();
       } else {
         // the whole warp runs the general code in lockstep on per-thread local-memory scratch (all lanes touch the same
         // offsets together, so the accesses coalesce in L1).  It redoes the histogram from the coefficient values, which
         // huff_hist left readable in the low 11 bits of the coefficient words.
-        pl = huff_plan(zm, L, bs, WarpLockstep{});
+        pl = huff_plan(zm, L, bs, GenPol{});
         __syncwarp();
         size = mlive ? (uint32_t)pl.size() : 0u;
       }
@@ -1143,12 +1157,12 @@ __global__ void __launch_bounds__(kEncThreads, EncCfg<kInPlace>::kCtasPerSm)
         // first chunk that does not fit the shared staging buffer (chunks never straddle; offsets only grow)
         if (mlive && !fits && off <= (uint32_t)kStageBytes) atomicMin(&sm.split, off);
         if (__builtin_expect(fast, 1)) {
-          if (kInPlace) huff_fast_emit(zm, pl8, f8, dst, WarpLockstep{});
-          else huff_fast_emit_n<kTileCap>(zm, pl8, nw, f8, dst, WarpLockstep{});
+          if (kInPlace) huff_fast_emit(zm, pl8, f8, dst, FastPol{});
+          else huff_fast_emit_n<kTileCap>(zm, pl8, nw, f8, dst, FastPol{});
         } else {
           HuffPlan plf = pl;
           if (!mlive) plf.n = 0;
-          huff_emit(zm, plf, bs, dst, WarpLockstep{});
+          huff_emit(zm, plf, bs, dst, GenPol{});
         }
       }
       PH(7);  // emit: sort, canonical codes, table, stream
@@ -1289,8 +1303,8 @@ __global__ void __launch_bounds__(kCtaThreads, 7) heavy15_kernel(const __grid_co
     const uint32_t idxm = idx;
     const bool mlive = live && !over;
 #endif
-    const FastPlan pl = huff_fast_plan(nsym, Lm == 0 ? 1 : Lm, f8, WarpLockstep{});
-    huff_fast_emit(z, pl, f8, P.ws.heavy_bytes + (uint64_t)idxm * 256, WarpLockstep{});
+    const FastPlan pl = huff_fast_plan(nsym, Lm == 0 ? 1 : Lm, f8, FastPol{});
+    huff_fast_emit(z, pl, f8, P.ws.heavy_bytes + (uint64_t)idxm * 256, FastPol{});
     if (mlive) {
       const uint32_t size = (uint32_t)pl.size();
       P.ws.chunk_sizes[rec.x] = (uint8_t)size;
@@ -1332,14 +1346,14 @@ __global__ void __launch_bounds__(kHeavyThreads) heavy_blocks_kernel(const __gri
     }
     const bool live = rec.x != 0xffffffffu;  // a warp that found the queue full leaves its reservation unused
     ZSplitValues<kHeavyThreads> zv{P.ws.heavy_coef + (uint64_t)(live ? idx : 0u) * 64, &sm.slot[0][threadIdx.x]};
-    HuffPlan pl = huff_plan(zv, live ? (int)rec.z : 0, bs, WarpLockstep{});
+    HuffPlan pl = huff_plan(zv, live ? (int)rec.z : 0, bs, GenPol{});
     __syncwarp();
     const bool fits = pl.n >= 0;
     if (live && !fits && overflow) overflow[atomicAdd(&P.ws.counters[7], 1u)] = idx;
     const uint32_t size = live && fits ? (uint32_t)pl.size() : 0u;
     if (!live || !fits) pl.n = 0;
     ZSplitSlots<kHeavyThreads> zs{&sm.slot[0][threadIdx.x]};
-    huff_emit(zs, pl, bs, P.ws.heavy_bytes + (uint64_t)(live ? idx : 0u) * 256, WarpLockstep{});
+    huff_emit(zs, pl, bs, P.ws.heavy_bytes + (uint64_t)(live ? idx : 0u) * 256, GenPol{});
     if (live && fits) {
       P.ws.chunk_sizes[rec.x] = (uint8_t)size;
       atomicAdd(&P.ws.tile_total[rec.y], size);
