@@ -272,6 +272,57 @@ def test_batch_device_api(ctx, ora, synth, pkg):
         assert np.array_equal(got[i], ora.bgrx_to_iyuv(bg[i], w, h, True))
 
 
+@pytest.mark.parametrize("content", ["gradient", "noise"])
+@pytest.mark.parametrize("w,h,n,q", [(48, 80, 3, (50, 50, 50)), (1296, 720, 2, (90, 90, 90)), (256, 128, 4, (100, 100, 100))])
+def test_no_write_outside_the_callers_buffers(ctx, ora, synth, pkg, content, w, h, n, q):
+    """compute-sanitizer is not available on the pool, so the bounds of the tile / scan / place / finalize kernels and of the
+    decoder's stores are checked with guard bands: every device buffer the call writes sits between two 4 KB bands of a known
+    byte, the payload buffer is exactly as large as the payload, and the bands must come back untouched."""
+    torch = pytest.importorskip("torch")
+    G, fill = 4096, 0xA5
+    rng = np.random.default_rng(w * h + n)
+    host = frames(synth, w, h, n) if content == "gradient" else rng.integers(0, 256, (n, w * h * 3 // 2), dtype=np.uint8)
+    want = [ora.compress(host[i], w, h, q) for i in range(n)]
+    total = sum(len(x) for x in want)
+
+    def banded(nbytes, dtype=torch.uint8):
+        raw = torch.full((G + nbytes + G,), fill, dtype=torch.uint8, device="cuda")
+        return raw, raw[G: G + nbytes].view(dtype)
+
+    def bands_intact(raw, nbytes):
+        r = raw.cpu().numpy()
+        return bool((r[:G] == fill).all() and (r[G + nbytes:] == fill).all())
+
+    d_in = torch.from_numpy(host).cuda()
+    raw_out, d_out = banded(total)
+    raw_off, d_off = banded(8 * (n + 1), torch.int64)
+    torch.cuda.synchronize()
+    for mode in (1, 2):  # both builds of the coding kernel
+        ctx.set_encoder_mode(mode)
+        ctx.compress_batch_dev(d_in, w, h, q, n, d_out, total, d_off)
+        ctx.batch_status()
+        assert bands_intact(raw_out, total) and bands_intact(raw_off, 8 * (n + 1)), f"encoder mode {mode}"
+        off = d_off.cpu().numpy()
+        assert off[n] == total
+        out = d_out.cpu().numpy()
+        for i in range(n):
+            assert np.array_equal(out[off[i]: off[i + 1]], want[i])
+    ctx.set_encoder_mode(0)
+    raw_back, d_back = banded(host.size)
+    ctx.decompress_batch_dev(d_out, d_off, w, h, q, n, d_back.view(n, -1))
+    ctx.batch_status()
+    assert bands_intact(raw_back, host.size)
+    back = d_back.cpu().numpy().reshape(n, -1)
+    for i in range(n):
+        assert np.array_equal(back[i], ora.decompress(want[i], w, h, q))
+    # one byte short: the call must report it and still leave the bands alone
+    raw_short, d_short = banded(total - 1)
+    ctx.compress_batch_dev(d_in, w, h, q, n, d_short, total - 1, d_off)
+    with pytest.raises(pkg.MyyuvError):
+        ctx.batch_status()
+    assert bands_intact(raw_short, total - 1)
+
+
 @pytest.mark.parametrize("chunk,keep_iyuv", [(0, False), (1, True), (3, False), (4, True), (7, True)])
 def test_full_pipeline_xrgb_to_payload(ctx, ora, synth, pkg, chunk, keep_iyuv):
     """BASELINE configs[2]: XRGB -> IYUV -> DCT-50 in one call, chunks chained on the device; every frame's payload and

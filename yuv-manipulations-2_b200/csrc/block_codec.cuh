@@ -1269,9 +1269,20 @@ MYB_HD void decode_stream(DecStream& st, const uint32_t (&kk)[4], int maxlen, co
   warp.sync();
 }
 
+// The code-stream loop as a replaceable part of huff_decode_fast: kernels.cu passes one that is written for the kernels'
+// shared-memory layout, everything else (the host emulation included) runs decode_stream above.
+struct GenericStream {
+  template <int PAIRS, int STRIDE, class Emit, class W>
+  MYB_HD void run(DecStream& st, const uint32_t (&kk)[4], int maxlen, const uint8_t* data, int data_bytes, const DecScratch<STRIDE>& D,
+                  Emit& emit, const W& warp) const {
+    decode_stream<PAIRS>(st, kk, maxlen, data, data_bytes, D, emit, warp);
+  }
+};
+
 // Returns 0 (ok), 1 (error: the conditions huff_decode_block reports) or 2 (not handled here, nothing emitted).
-template <int STRIDE, class Emit, class W>
-MYB_HD int huff_decode_fast(const uint8_t* chunk, int size, const DecScratch<STRIDE>& D, Emit&& emit, int* n_emitted, const W& warp) {
+template <int STRIDE, class Emit, class W, class S = GenericStream>
+MYB_HD int huff_decode_fast(const uint8_t* chunk, int size, const DecScratch<STRIDE>& D, Emit&& emit, int* n_emitted, const W& warp,
+                            const S& stream = S{}) {
   int err = 0;
   int bits = 0, table_bytes = 0;
   if (size >= 3) {
@@ -1351,7 +1362,7 @@ MYB_HD int huff_decode_fast(const uint8_t* chunk, int size, const DecScratch<STR
     }
   }
   if (err || general) bits = 0;  // such lanes idle through the lockstep loop below (no early return: the warp stays converged)
-  const int maxlw = warp.max(maxlen);
+  const int maxlw = warp.umax(maxlen);  // the whole warp runs one instantiation of the stream loop
   const uint8_t* data = groups + table_bytes;
   const int data_bytes = (bits + 7) >> 3;
   // ---- code stream (Huffman.cpp:106-154); the loop exists three times, for code tables of up to 2, 4 and 8 lengths
@@ -1362,9 +1373,9 @@ MYB_HD int huff_decode_fast(const uint8_t* chunk, int size, const DecScratch<STR
   st.err = err;
   st.byte0 = 0;
   st.rwin = bit_reverse32(load_window(data, 0, data_bytes));
-  if (maxlw <= 2) decode_stream<1>(st, kk, maxlen, data, data_bytes, D, emit, warp);
-  else if (maxlw <= 4) decode_stream<2>(st, kk, maxlen, data, data_bytes, D, emit, warp);
-  else decode_stream<4>(st, kk, maxlen, data, data_bytes, D, emit, warp);
+  if (maxlw <= 2) stream.template run<1>(st, kk, maxlen, data, data_bytes, D, emit, warp);
+  else if (maxlw <= 4) stream.template run<2>(st, kk, maxlen, data, data_bytes, D, emit, warp);
+  else stream.template run<4>(st, kk, maxlen, data, data_bytes, D, emit, warp);
   *n_emitted = st.j;
   return st.err ? 1 : (general ? 2 : 0);
 }

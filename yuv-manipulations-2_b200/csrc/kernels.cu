@@ -750,10 +750,10 @@ template <int CAP, int ZSTRIDE>
 MYB_D int huff_hist_smem(uint16_t* zcol, int L, bool live, const F8Scratch& F) {
   static_assert(CAP <= kFastCap, "slot numbers are 4 bits");
   if (!live) L = 0;
-#ifdef MYB_FREE_HIST
-  const int Lw = L;
-#else
+#ifdef MYB_LOCKSTEP
   const int Lw = __reduce_max_sync(0xffffffffu, L);
+#else
+  const int Lw = L;  // per-lane trip count, see FastPol
 #endif
   int n = 0;
   if (Lw > 0) {
@@ -824,15 +824,17 @@ MYB_D int huff_hist_smem(uint16_t* zcol, int L, bool live, const F8Scratch& F) {
 #endif
 
 using ZShared = ZSharedT<kEncTile>;
-#ifdef MYB_FREE_FAST
-using FastPol = WarpFree;
-#else
+// How the lanes of a warp go through the coder's data dependent loops.  Round 1 held them in step by hand (every loop ran
+// to the warp's maximum trip count with a predicated body and a warp barrier per iteration), after a first version whose lanes
+// drifted apart.  With today's structure -- one call per phase, warp collectives between the phases -- plain per-lane loops
+// stay converged by themselves (the hardware reconverges the warp behind each loop) and the bookkeeping only costs:
+// compress -1.8 % synthetic, -1.6 % natural q50, -2.4 % synthetic q90 in a same-box A/B.  -DMYB_LOCKSTEP builds the old way.
+#ifdef MYB_LOCKSTEP
 using FastPol = WarpLockstep;
-#endif
-#ifdef MYB_FREE_GENERAL
-using GenPol = WarpFree;
-#else
 using GenPol = WarpLockstep;
+#else
+using FastPol = WarpFree;
+using GenPol = WarpFree;
 #endif
 struct EncParams {
   const uint8_t* src;
@@ -1978,6 +1980,90 @@ MYB_D void idct_block_tri(const int16_t* col, const float* q, float onef, uint32
   }
 }
 
+// decode_stream (block_codec.cuh) for the decoder kernel's layout, its per-symbol part in PTX: symbol table, length bases,
+// zigzag offsets and the coefficient column are shared-memory addresses, so a symbol is 27 (tables of up to two code lengths)
+// to 33 instructions instead of the 41+ ptxas made of the C++ loop (which rebuilt the shared window's base from SR_CgaCtaId for
+// the zigzag table inside the loop and carried five register moves per symbol).  Refilling the 32-bit stream window stays C++.
+#ifndef MYB_NO_PTX_STREAM
+#define MYB_DS_PAIR(K)                    \
+  "add.u32 a, r2, " K ";\n\t"             \
+  "and.b32 a, a, 0x01000100;\n\t"         \
+  "add.u32 acc, acc, a;\n\t"
+#define MYB_DS_HEAD                                   \
+  "{\n\t"                                             \
+  ".reg .pred pe, pl;\n\t"                            \
+  ".reg .u32 r, r2, a, acc, len0, len, nsh, t, bsv, idx, sv, zo;\n" \
+  "DSLOOP:\n\t"                                       \
+  "shl.b32 r, %4, %0;\n\t"                            \
+  "shr.u32 r, r, 24;\n\t"                             \
+  "mul.lo.u32 r2, r, 0x10001;\n\t"                    \
+  "add.u32 acc, r2, %5;\n\t"                          \
+  "and.b32 acc, acc, 0x01000100;\n\t"
+#define MYB_DS_TAIL                                   \
+  "mul.lo.u32 a, acc, 0x10001;\n\t"                   \
+  "shr.u32 len0, a, 24;\n\t"                          \
+  "add.u32 len, len0, 1;\n\t"                         \
+  "add.u32 nsh, %0, len;\n\t"                         \
+  "setp.gt.s32 pe, len, %9;\n\t"                      \
+  "setp.gt.or.s32 pe, nsh, %1, pe;\n\t"               \
+  "@pe bra DSERR;\n\t"                                \
+  "mad.lo.u32 a, len0, %14, %10;\n\t"                 \
+  "ld.shared.s16 bsv, [a];\n\t"                       \
+  "sub.u32 t, 7, len0;\n\t"                           \
+  "shr.u32 t, r, t;\n\t"                              \
+  "add.u32 idx, t, bsv;\n\t"                          \
+  "mad.lo.u32 a, idx, %14, %11;\n\t"                  \
+  "ld.shared.u16 sv, [a];\n\t"                        \
+  "mad.lo.u32 a, %2, 2, %12;\n\t"                     \
+  "ld.shared.u16 zo, [a];\n\t"                        \
+  "add.u32 a, %13, zo;\n\t"                           \
+  "st.shared.u16 [a], sv;\n\t"                        \
+  "add.u32 %2, %2, 1;\n\t"                            \
+  "mov.u32 %0, nsh;\n\t"                              \
+  "setp.le.s32 pl, %0, 24;\n\t"                       \
+  "setp.lt.and.s32 pl, %0, %1, pl;\n\t"               \
+  "setp.lt.and.s32 pl, %2, 64, pl;\n\t"               \
+  "@pl bra DSLOOP;\n\t"                               \
+  "bra DSEND;\n"                                      \
+  "DSERR:\n\t"                                        \
+  "mov.u32 %3, 1;\n\t"                                \
+  "mov.u32 %1, 0;\n"                                  \
+  "DSEND:\n\t"                                        \
+  "}"
+struct SmemStream {
+  uint32_t col;   // shared-memory address of this thread's coefficient column
+  uint32_t zoff;  // shared-memory address of the zigzag offset table (uint16[64])
+  template <int PAIRS, int STRIDE, class Emit, class W>
+  MYB_D void run(DecStream& st, const uint32_t (&kk)[4], int maxlen, const uint8_t* data, int data_bytes, const DecScratch<STRIDE>& D,
+                 Emit&, const W& warp) const {
+    const uint32_t lb = (uint32_t)__cvta_generic_to_shared(D.base), sb = (uint32_t)__cvta_generic_to_shared(D.symtab);
+    int sh = st.sh, rem = st.rem, j = st.j, err = st.err, byte0 = st.byte0;
+    uint32_t rwin = st.rwin;
+    while (sh < rem && j < 64) {
+      if (sh > 24) {  // reload the window at the byte that holds the next bit
+        byte0 += sh >> 3;
+        rem -= sh & ~7;
+        sh &= 7;
+        rwin = bit_reverse32(load_window(data, byte0, data_bytes));
+      }
+#define MYB_DS_OPERANDS                                                                                                        \
+  : "+r"(sh), "+r"(rem), "+r"(j), "+r"(err)                                                                                   \
+  : "r"(rwin), "r"(kk[0]), "r"(kk[1]), "r"(kk[2]), "r"(kk[3]), "r"(maxlen), "r"(lb), "r"(sb), "r"(zoff), "r"(col), "n"(STRIDE * 2) \
+  : "memory"
+      if (PAIRS == 1) asm volatile(MYB_DS_HEAD MYB_DS_TAIL MYB_DS_OPERANDS);
+      else if (PAIRS == 2) asm volatile(MYB_DS_HEAD MYB_DS_PAIR("%6") MYB_DS_TAIL MYB_DS_OPERANDS);
+      else asm volatile(MYB_DS_HEAD MYB_DS_PAIR("%6") MYB_DS_PAIR("%7") MYB_DS_PAIR("%8") MYB_DS_TAIL MYB_DS_OPERANDS);
+#undef MYB_DS_OPERANDS
+    }
+    st.sh = sh; st.rem = rem; st.j = j; st.err = err; st.byte0 = byte0; st.rwin = rwin;
+    warp.sync();
+  }
+};
+#undef MYB_DS_PAIR
+#undef MYB_DS_HEAD
+#undef MYB_DS_TAIL
+#endif
+
 // Decompress pre-pass 1: chunk bytes of every tile (one warp per tile, 4 size bytes per lane).
 __global__ void __launch_bounds__(256) dec_tile_totals_kernel(const __grid_constant__ DecParams P) {
   const FrameGeom& g = P.g;
@@ -2186,10 +2272,15 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm)
         *reinterpret_cast<int16_t*>(reinterpret_cast<uint8_t*>(col) + sm.zoff[j]) = (int16_t)v;
       };
       const DecScratch<kDecTile> ds{&sm.symtab[0][tid], &sm.lenbase[0][tid]};
-      int err = huff_decode_fast(chunk, (int)size, ds, emit, &nsym, WarpLockstep{});
+#ifndef MYB_NO_PTX_STREAM
+      const SmemStream stream{(uint32_t)__cvta_generic_to_shared(col), (uint32_t)__cvta_generic_to_shared(sm.zoff)};
+      int err = huff_decode_fast(chunk, (int)size, ds, emit, &nsym, FastPol{}, stream);
+#else
+      int err = huff_decode_fast(chunk, (int)size, ds, emit, &nsym, FastPol{});
+#endif
       if (__any_sync(0xffffffffu, err == 2)) {  // a table the fast decoder does not take: the step-by-step decoder, for those lanes
         int cnt = 0;
-        const int e2 = huff_decode_block(chunk, err == 2 ? (int)size : 0, [&](int j, int v) { emit(j, v); cnt = j + 1; }, WarpLockstep{});
+        const int e2 = huff_decode_block(chunk, err == 2 ? (int)size : 0, [&](int j, int v) { emit(j, v); cnt = j + 1; }, GenPol{});
         if (err == 2) { err = e2; nsym = cnt; }
       }
       if (mine && (err || size == 0)) atomicOr(&P.ws.counters[1], kFlagHuffman);  // a chunk is at least 7 bytes
