@@ -1218,7 +1218,8 @@ struct DecScratch {
   MYB_HD int16_t& bs(int l) const { return base[l * STRIDE]; }
 };
 
-MYB_HD uint32_t load_window(const uint8_t* data, int byte0, int data_bytes) {
+template <class BP>
+MYB_HD uint32_t load_window(BP data, int byte0, int data_bytes) {
   uint32_t w = 0;
 #if defined(__CUDACC__)
 #pragma unroll
@@ -1236,8 +1237,8 @@ struct DecStream {
 };
 
 // PAIRS = code lengths of the table / 2, rounded up to 1, 2 or 4 (warp uniform): how many of the range compares are needed
-template <int PAIRS, int STRIDE, class Emit, class W>
-MYB_HD void decode_stream(DecStream& st, const uint32_t (&kk)[4], int maxlen, const uint8_t* data, int data_bytes,
+template <int PAIRS, int STRIDE, class BP, class Emit, class W>
+MYB_HD void decode_stream(DecStream& st, const uint32_t (&kk)[4], int maxlen, BP data, int data_bytes,
                           const DecScratch<STRIDE>& D, Emit& emit, const W& warp) {
   // A plain per-lane loop: lanes that run out of symbols wait where the hardware reconverges the warp, behind the loop.
   // Holding the lanes in step by hand (a vote per symbol, an inner test, a warp barrier) cost 4-5 % of the decoder's time.
@@ -1272,16 +1273,18 @@ MYB_HD void decode_stream(DecStream& st, const uint32_t (&kk)[4], int maxlen, co
 // The code-stream loop as a replaceable part of huff_decode_fast: kernels.cu passes one that is written for the kernels'
 // shared-memory layout, everything else (the host emulation included) runs decode_stream above.
 struct GenericStream {
-  template <int PAIRS, int STRIDE, class Emit, class W>
-  MYB_HD void run(DecStream& st, const uint32_t (&kk)[4], int maxlen, const uint8_t* data, int data_bytes, const DecScratch<STRIDE>& D,
+  template <int PAIRS, int STRIDE, class BP, class Emit, class W>
+  MYB_HD void run(DecStream& st, const uint32_t (&kk)[4], int maxlen, BP data, int data_bytes, const DecScratch<STRIDE>& D,
                   Emit& emit, const W& warp) const {
     decode_stream<PAIRS>(st, kk, maxlen, data, data_bytes, D, emit, warp);
   }
 };
 
 // Returns 0 (ok), 1 (error: the conditions huff_decode_block reports) or 2 (not handled here, nothing emitted).
-template <int STRIDE, class Emit, class W, class S = GenericStream>
-MYB_HD int huff_decode_fast(const uint8_t* chunk, int size, const DecScratch<STRIDE>& D, Emit&& emit, int* n_emitted, const W& warp,
+// BP: where the chunk's bytes come from -- a plain pointer, or anything with operator[] and operator+ (the decoder kernel
+// reads chunks that lie in its shared-memory staging area through 32-bit shared addresses).
+template <int STRIDE, class BP, class Emit, class W, class S = GenericStream>
+MYB_HD int huff_decode_fast(BP chunk, int size, const DecScratch<STRIDE>& D, Emit&& emit, int* n_emitted, const W& warp,
                             const S& stream = S{}) {
   int err = 0;
   int bits = 0, table_bytes = 0;
@@ -1293,7 +1296,7 @@ MYB_HD int huff_decode_fast(const uint8_t* chunk, int size, const DecScratch<STR
     err = 1;
   }
   if (err || size == 0) { bits = 0; table_bytes = 0; }
-  const uint8_t* groups = chunk + 3;
+  const BP groups = chunk + 3;
   // ---- pass 1: one table symbol per step (Huffman.cpp:258-266, :54-69)
   bool general = false;
   uint32_t cnt_lo = 0, cnt_hi = 0;  // symbols per length, one byte each (lengths 1..4, 5..8)
@@ -1363,7 +1366,7 @@ MYB_HD int huff_decode_fast(const uint8_t* chunk, int size, const DecScratch<STR
   }
   if (err || general) bits = 0;  // such lanes idle through the lockstep loop below (no early return: the warp stays converged)
   const int maxlw = warp.umax(maxlen);  // the whole warp runs one instantiation of the stream loop
-  const uint8_t* data = groups + table_bytes;
+  const BP data = groups + table_bytes;
   const int data_bytes = (bits + 7) >> 3;
   // ---- code stream (Huffman.cpp:106-154); the loop exists three times, for code tables of up to 2, 4 and 8 lengths
   DecStream st;

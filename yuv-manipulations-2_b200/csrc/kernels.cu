@@ -1831,7 +1831,8 @@ constexpr int kDecStageBytes = 8 * 1024 * kDecTile / 128;
 struct DecSmem {
   int16_t coef[64][kDecTile];      // quantised coefficients [k][c] (row-major index), per block column; the
                                       // dequantisation (coef * q, DCT.cpp:330-332) happens when the IDCT loads them
-  alignas(16) uint8_t stage[kDecStageBytes + 16];  // the tile's chunk bytes, shifted by the source's offset in its 16-byte line
+  alignas(16) uint8_t stage[kDecStageBytes + 32];  // the tile's chunk bytes, shifted by the source's offset in its 16-byte line
+                                                   // (+16), and room for the aligned word behind a chunk's last byte (load_window)
   int16_t symtab[32][kDecTile];    // fast decoder: the block's symbols in canonical order
   int16_t lenbase[8][kDecTile];    // fast decoder: symbol index offsets per code length
   float q[64];                        // dequantisation factors of the current plane, row-major
@@ -2030,11 +2031,34 @@ MYB_D void idct_block_tri(const int16_t* col, const float* q, float onef, uint32
   "mov.u32 %1, 0;\n"                                  \
   "DSEND:\n\t"                                        \
   "}"
+// A chunk inside the kernel's shared-memory staging area, read through 32-bit shared addresses: a byte is one LDS, where the
+// generic pointer it replaces cost 64-bit address arithmetic per access.
+struct SmemBytes {
+  uint32_t a;
+  MYB_D uint32_t operator[](int i) const {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a + (uint32_t)i));
+    return v;
+  }
+  MYB_D SmemBytes operator+(int k) const { return SmemBytes{a + (uint32_t)k}; }
+};
+// the 32-bit stream window from two aligned words (the staging area is padded, so the second one is always there)
+MYB_D uint32_t load_window(SmemBytes data, int byte0, int data_bytes) {
+  const uint32_t a = data.a + (uint32_t)byte0, al = a & ~3u;
+  uint32_t lo, hi;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(lo) : "r"(al));
+  asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(hi) : "r"(al));
+  uint32_t w = __funnelshift_r(lo, hi, (a & 3u) * 8u);
+  const int left = data_bytes - byte0;  // bytes of the stream from here on; what lies behind them must read as zero
+  if (left < 4) w = left > 0 ? w & ((1u << (8 * left)) - 1u) : 0u;
+  return w;
+}
+
 struct SmemStream {
   uint32_t col;   // shared-memory address of this thread's coefficient column
   uint32_t zoff;  // shared-memory address of the zigzag offset table (uint16[64])
-  template <int PAIRS, int STRIDE, class Emit, class W>
-  MYB_D void run(DecStream& st, const uint32_t (&kk)[4], int maxlen, const uint8_t* data, int data_bytes, const DecScratch<STRIDE>& D,
+  template <int PAIRS, int STRIDE, class BP, class Emit, class W>
+  MYB_D void run(DecStream& st, const uint32_t (&kk)[4], int maxlen, BP data, int data_bytes, const DecScratch<STRIDE>& D,
                  Emit&, const W& warp) const {
     const uint32_t lb = (uint32_t)__cvta_generic_to_shared(D.base), sb = (uint32_t)__cvta_generic_to_shared(D.symtab);
     int sh = st.sh, rem = st.rem, j = st.j, err = st.err, byte0 = st.byte0;
@@ -2274,7 +2298,14 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm)
       const DecScratch<kDecTile> ds{&sm.symtab[0][tid], &sm.lenbase[0][tid]};
 #ifndef MYB_NO_PTX_STREAM
       const SmemStream stream{(uint32_t)__cvta_generic_to_shared(col), (uint32_t)__cvta_generic_to_shared(sm.zoff)};
-      int err = huff_decode_fast(chunk, (int)size, ds, emit, &nsym, FastPol{}, stream);
+      int err;
+#ifndef MYB_NO_SMEM_BYTES
+      // every chunk of the warp lies in the staging area (all but tiles of more than 16 KB): read it through shared addresses
+      if (__all_sync(0xffffffffu, off + size <= (uint32_t)kDecStageBytes))
+        err = huff_decode_fast(SmemBytes{(uint32_t)__cvta_generic_to_shared(&sm.stage[mis + off])}, (int)size, ds, emit, &nsym, FastPol{}, stream);
+      else
+#endif
+        err = huff_decode_fast(chunk, (int)size, ds, emit, &nsym, FastPol{}, stream);
 #else
       int err = huff_decode_fast(chunk, (int)size, ds, emit, &nsym, FastPol{});
 #endif
