@@ -1273,6 +1273,9 @@ MYB_HD void decode_stream(DecStream& st, const uint32_t (&kk)[4], int maxlen, BP
 // The code-stream loop as a replaceable part of huff_decode_fast: kernels.cu passes one that is written for the kernels'
 // shared-memory layout, everything else (the host emulation included) runs decode_stream above.
 struct GenericStream {
+  // pass 1 of huff_decode_fast, if this policy has a version of its own for the byte source BP (false: it has not)
+  template <int STRIDE, class BP>
+  MYB_HD bool parse_table(BP, int, const DecScratch<STRIDE>&, int&, bool&, int&, uint32_t&, uint32_t&) const { return false; }
   template <int PAIRS, int STRIDE, class BP, class Emit, class W>
   MYB_HD void run(DecStream& st, const uint32_t (&kk)[4], int maxlen, BP data, int data_bytes, const DecScratch<STRIDE>& D,
                   Emit& emit, const W& warp) const {
@@ -1301,7 +1304,7 @@ MYB_HD int huff_decode_fast(BP chunk, int size, const DecScratch<STRIDE>& D, Emi
   bool general = false;
   uint32_t cnt_lo = 0, cnt_hi = 0;  // symbols per length, one byte each (lengths 1..4, 5..8)
   int n = 0;
-  {
+  if (!stream.parse_table(groups, table_bytes, D, err, general, n, cnt_lo, cnt_hi)) {
     int gi = 0, ci = 0, cnt = 0, glen = 0, symbase = 0;
     while (!err && !general && (ci < cnt || gi < table_bytes)) {
       {

@@ -2057,6 +2057,96 @@ MYB_D uint32_t load_window(SmemBytes data, int byte0, int data_bytes) {
 struct SmemStream {
   uint32_t col;   // shared-memory address of this thread's coefficient column
   uint32_t zoff;  // shared-memory address of the zigzag offset table (uint16[64])
+  // Pass 1 of huff_decode_fast (group headers, 11-bit symbols -> symbol table, symbols per code length) for a chunk in shared
+  // memory, in PTX: 22 instructions per table symbol where ptxas made 40 of the C++ loop (predicate logic, BSSY.RELIABLE /
+  // BREAK scopes).  Same checks, same results; a third table byte is always read (shared memory: harmless) and masked off.
+  template <int STRIDE, class BP>
+  MYB_D bool parse_table(BP, int, const DecScratch<STRIDE>&, int&, bool&, int&, uint32_t&, uint32_t&) const { return false; }
+  template <int STRIDE>
+  MYB_D bool parse_table(SmemBytes groups, int table_bytes, const DecScratch<STRIDE>& D, int& err, bool& general, int& n, uint32_t& cnt_lo,
+                         uint32_t& cnt_hi) const {
+#ifdef MYB_NO_PTX_TABLE
+    return false;
+#else
+    const uint32_t sb = (uint32_t)__cvta_generic_to_shared(D.symtab);
+    int gen = 0;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        ".reg .u32 gi, ci, cnt, glen, symbase, info, len0, len, c, t, a, bit, sh, b0, b1, b2;\n\t"
+        "mov.u32 gi, 0;\n\t"
+        "mov.u32 ci, 0;\n\t"
+        "mov.u32 cnt, 0;\n\t"
+        "mov.u32 glen, 0;\n\t"
+        "mov.u32 symbase, 0;\n\t"
+        "setp.ne.s32 p, %0, 0;\n\t"
+        "@p bra PT_END;\n"
+        "PT_LOOP:\n\t"
+        "setp.lt.s32 p, ci, cnt;\n\t"
+        "@p bra PT_SYM;\n\t"
+        "setp.ge.s32 p, gi, %6;\n\t"
+        "@p bra PT_END;\n\t"
+        // next group
+        "add.u32 a, %5, gi;\n\t"
+        "ld.shared.u8 info, [a];\n\t"
+        "shr.u32 len0, info, 5;\n\t"
+        "add.u32 len, len0, 1;\n\t"
+        "and.b32 c, info, 31;\n\t"
+        "add.u32 c, c, 1;\n\t"
+        "add.u32 t, %2, c;\n\t"
+        "setp.le.s32 p, len, glen;\n\t"
+        "setp.gt.or.s32 p, t, 32, p;\n\t"
+        "@p bra PT_GENERAL;\n\t"
+        "mov.u32 glen, len;\n\t"
+        "mov.u32 cnt, c;\n\t"
+        "mov.u32 ci, 0;\n\t"
+        "add.u32 symbase, gi, 1;\n\t"
+        "mad.lo.u32 t, c, 11, 7;\n\t"
+        "shr.u32 t, t, 3;\n\t"
+        "add.u32 gi, symbase, t;\n\t"
+        "shl.b32 sh, len0, 3;\n\t"
+        "and.b32 sh, sh, 31;\n\t"
+        "shl.b32 t, c, sh;\n\t"
+        "setp.lt.u32 q, len0, 4;\n\t"
+        "@q add.u32 %3, %3, t;\n\t"
+        "@!q add.u32 %4, %4, t;\n\t"
+        "setp.gt.s32 p, gi, %6;\n\t"
+        "@p bra PT_ERR;\n"
+        "PT_SYM:\n\t"
+        "mul.lo.u32 bit, ci, 11;\n\t"
+        "shr.u32 a, bit, 3;\n\t"
+        "add.u32 a, a, symbase;\n\t"
+        "add.u32 a, a, %5;\n\t"
+        "and.b32 sh, bit, 7;\n\t"
+        "ld.shared.u8 b0, [a];\n\t"
+        "ld.shared.u8 b1, [a+1];\n\t"
+        "ld.shared.u8 b2, [a+2];\n\t"
+        "shl.b32 b1, b1, 8;\n\t"
+        "shl.b32 b2, b2, 16;\n\t"
+        "or.b32 t, b0, b1;\n\t"
+        "or.b32 t, t, b2;\n\t"
+        "shr.u32 t, t, sh;\n\t"
+        "shl.b32 t, t, 21;\n\t"
+        "shr.s32 t, t, 21;\n\t"  // 11 bits, sign extended (Huffman.cpp:54-69)
+        "mad.lo.u32 a, %2, %8, %7;\n\t"
+        "st.shared.u16 [a], t;\n\t"
+        "add.u32 %2, %2, 1;\n\t"
+        "add.u32 ci, ci, 1;\n\t"
+        "bra PT_LOOP;\n"
+        "PT_GENERAL:\n\t"
+        "mov.u32 %1, 1;\n\t"
+        "bra PT_END;\n"
+        "PT_ERR:\n\t"
+        "mov.u32 %0, 1;\n"
+        "PT_END:\n\t"
+        "}"
+        : "+r"(err), "+r"(gen), "+r"(n), "+r"(cnt_lo), "+r"(cnt_hi)
+        : "r"(groups.a), "r"(table_bytes), "r"(sb), "n"(STRIDE * 2)
+        : "memory");
+    general = gen != 0;
+    return true;
+#endif
+  }
   template <int PAIRS, int STRIDE, class BP, class Emit, class W>
   MYB_D void run(DecStream& st, const uint32_t (&kk)[4], int maxlen, BP data, int data_bytes, const DecScratch<STRIDE>& D,
                  Emit&, const W& warp) const {
