@@ -1343,28 +1343,32 @@ MYB_HD int huff_decode_fast(BP chunk, int size, const DecScratch<STRIDE>& D, Emi
   int maxlen = 0;
   {
     uint32_t first = 0, off = 0;
-#if defined(__CUDACC__)
-#pragma unroll
-#endif
-    for (int l = 0; l < 8; l++) {
-      const uint32_t c = ((l < 4 ? cnt_lo >> (8 * l) : cnt_hi >> (8 * (l - 4)))) & 0xffu;
+    auto length_step = [&](int l, uint32_t c) {
       D.bs(l) = (int16_t)((int)off - (int)first);
       const uint32_t end = first + c;
       if (end > (2u << l)) general = true;  // more codes of this length than exist: let the general decoder reproduce the reference
       if (c) maxlen = l + 1;
+      kk[l >> 1] |= (256u - ((end << (7 - l)) & 0x1ffu)) << (16 * (l & 1));
       first = end << 1;
       off += c;
-    }
-    first = 0;
+    };
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
-    for (int l = 0; l < 8; l++) {
-      const uint32_t c = ((l < 4 ? cnt_lo >> (8 * l) : cnt_hi >> (8 * (l - 4)))) & 0xffu;
-      const uint32_t end = first + c;
-      const uint32_t k = l < maxlen ? 256u - ((end << (7 - l)) & 0x1ffu) : 0u;
-      kk[l >> 1] |= k << (16 * (l & 1));
-      first = end << 1;
+    for (int l = 0; l < 4; l++) length_step(l, (cnt_lo >> (8 * l)) & 0xffu);
+    if (warp.umax(cnt_hi != 0u ? 1 : 0)) {  // codes of five and more bits somewhere in the warp (rare at q 50)
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+      for (int l = 4; l < 8; l++) length_step(l, (cnt_hi >> (8 * (l - 4))) & 0xffu);
+    }
+    // lengths past the longest one: k = 0
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int w = 0; w < 4; w++) {
+      const int keep = maxlen - 2 * w;
+      kk[w] = keep >= 2 ? kk[w] : (keep == 1 ? kk[w] & 0xffffu : 0u);
     }
   }
   if (err || general) bits = 0;  // such lanes idle through the lockstep loop below (no early return: the warp stays converged)
