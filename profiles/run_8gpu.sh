@@ -11,6 +11,7 @@ for n in 2 4 8; do
   [ $n -le $N ] || continue
   timeout 300 $TR --nproc-per-node $n --master-port $((29600+n)) bench.py --workload shard8k --gpus $n --steps 20 > $O/r02_shard8k_${n}gpu.json 2> $O/shard$n.err; echo "shard N=$n rc=$?"
 done
+if [ 2 -le $N ]; then timeout 600 $TR --nproc-per-node 2 --master-port 29555 bench.py --gpus 2 > $O/r02_bench_2gpu.json 2> $O/bench2gpu.err; echo "bench N=2 rc=$?"; fi
 : > $O/r02_pcie_ceiling.jsonl
 timeout 120 python profiles/pcie_ceiling.py >> $O/r02_pcie_ceiling.jsonl 2>$O/pcie.err
 for n in 2 4 8; do

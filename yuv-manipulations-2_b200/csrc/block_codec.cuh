@@ -1014,6 +1014,46 @@ MYB_HD void huff_fast_emit_n(Z& z, const FastPlan& pl, int nw, const FastScratch
   uint8_t* hdr = dst;  // header byte of the open group (dst: none yet)
   uint32_t acc = 0, code = 0;
   int nb = 0, prev = 0, cnt = 0;
+#ifndef MYB_TABLE_UNROLLED
+  // The sorted keys go through the (now free) heap words so that the table can be written by a ROLLED loop of n steps: the
+  // unrolled version ran 4 or 8 predicated copies of this body whatever n was, and was 360 instructions of code.
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int k = 0; k < CAP; k++)
+    if (k < nw) F.heap(k) = K[k];
+  MYB_NOUNROLL
+  for (int i = 0; i < n; i++) {
+    const uint32_t key = F.heap(i);
+    const int len = (int)(key >> 16);
+    code <<= (len - prev);
+    /* the slot word keeps its symbol and gets length << 8 | bit-reversed code in place of the count */
+    const int sl = (int)(key & 15u);
+    F.codeword(sl) = (uint16_t)((bit_reverse32(code) >> (32 - len)) | ((uint32_t)len << 8));
+    code++;
+    if (len != prev) { /* a new group: close the previous one, pad to a whole byte, reserve the header byte */
+      if (prev) *hdr = (uint8_t)(((prev - 1) << 5) | (cnt - 1));
+      if (nb > 0) *p++ = (uint8_t)acc;
+      acc = 0;
+      nb = 0;
+      hdr = p++;
+      cnt = 0;
+      prev = len;
+    }
+    /* pack11bit (Huffman.cpp:36-52): 11 bits on top of nb < 8 pending ones always complete one byte, sometimes two */
+    acc |= (((key >> 4) + 1024u) & 0x7ffu) << nb;
+    nb += 11;
+    *p++ = (uint8_t)acc;
+    acc >>= 8;
+    nb -= 8;
+    if (nb >= 8) {
+      *p++ = (uint8_t)acc;
+      acc >>= 8;
+      nb -= 8;
+    }
+    cnt++;
+  }
+#else
 #define MYB_TABLE_SYMBOL(i)                                                                                              \
   if (i < n) {                                                                                                           \
     const uint32_t key = K[i];                                                                                           \
@@ -1052,6 +1092,7 @@ MYB_HD void huff_fast_emit_n(Z& z, const FastPlan& pl, int nw, const FastScratch
     MYB_TABLE_SYMBOL(12) MYB_TABLE_SYMBOL(13) MYB_TABLE_SYMBOL(14)
   }
 #undef MYB_TABLE_SYMBOL
+#endif
   if (n > 0) {
     *hdr = (uint8_t)(((prev - 1) << 5) | (cnt - 1));
     if (nb > 0) *p++ = (uint8_t)acc;
