@@ -751,6 +751,32 @@ MYB_HD FastPlan huff_fast_plan_n(int n, int nw, int msg_len, const FastScratch<S
   FastPlan pl;
   pl.n = n;
   pl.msg_len = msg_len;
+#ifndef MYB_PLAN_UNROLLED
+  constexpr bool kRolled = CAP <= 8;
+#else
+  constexpr bool kRolled = false;
+#endif
+  uint32_t count0 = 0;  // occurrences of slot 0 (the whole message when n == 1)
+  if constexpr (kRolled) {
+    // Up to 8 symbols: 13 buckets, never a rehash, the list fits one word.  Two rolled loops of n steps each -- the list
+    // insertions, then the leaves pushed in list order straight into the shared-memory heap -- where the unrolled version ran
+    // 4 or 8 predicated copies of each body whatever n was, built the heap in registers and copied it out.
+    uint32_t olo = 0, blo = ~0u;  // bucket of each list position; 0xF = empty, which is no bucket
+    MYB_NOUNROLL
+    for (int k = 0; k < n; k++) {
+      const uint32_t b = bucket13((int)(int16_t)(F.slot(k) >> 16));
+      const int f = nib_find(blo, b);
+      const int p4 = f < 0 ? 0 : f;
+      olo = nib_insert(olo, p4, (uint32_t)k);
+      blo = nib_insert(blo, p4, b);
+    }
+    MYB_NOUNROLL
+    for (int j = 0; j < n; j++) {  // Huffman.cpp:207-209
+      const uint32_t sl = (olo >> (4 * j)) & 15u;
+      heap32_sift_up(F, j, ((F.slot((int)sl) & 0xffu) << 16) | (1u << sl));
+    }
+    if (n > 0) count0 = F.slot(0) & 0xffu;
+  } else {
   // ---- slot words into registers; is the value 0 part of the message?
   uint32_t sw[CAP];
   bool has_zero = false;
@@ -889,6 +915,8 @@ MYB_HD FastPlan huff_fast_plan_n(int n, int nw, int msg_len, const FastScratch<S
 #endif
     for (int k = 8; k < CAP; k++) F.heap(k) = H[k];
   }
+    count0 = sw[0] & 0xffu;
+  }
   // ---- n - 1 merges (Huffman.cpp:210-217)
   int hsize = n, bits = 0;
   uint32_t dlo = 0, dhi = 0;
@@ -909,7 +937,7 @@ MYB_HD FastPlan huff_fast_plan_n(int n, int nw, int msg_len, const FastScratch<S
   }
   if (n == 1) {  // a single symbol gets a one-bit code (Huffman.cpp:76, :218-221)
     dlo = 1;
-    bits = (int)(sw[0] & 0xffu);
+    bits = (int)count0;
   }
   pl.dlo = dlo;
   pl.dhi = dhi;
