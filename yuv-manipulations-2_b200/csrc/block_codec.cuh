@@ -746,7 +746,9 @@ MYB_HD void lst_place(const FastScratch<STRIDE>& F, int la, int lb, int& ln, int
 }
 
 // CAP = 8 or 15: capacity of this instantiation; every lane of the warp has n <= CAP (nw = warp maximum of n)
-template <int CAP, int STRIDE, class W>
+// ROLL15: the 15-symbol instantiation with rolled loops as well.  Pays where the symbol counts of a warp are mixed (the in-place
+// build of the coding kernel: synthetic q90 -2.7 %), costs where every block has 9..15 (heavy15_kernel: natural q90 +0.9 %).
+template <int CAP, int STRIDE, class W, bool ROLL15 = true>
 MYB_HD FastPlan huff_fast_plan_n(int n, int nw, int msg_len, const FastScratch<STRIDE>& F, const W& warp) {
   FastPlan pl;
   pl.n = n;
@@ -776,6 +778,84 @@ MYB_HD FastPlan huff_fast_plan_n(int n, int nw, int msg_len, const FastScratch<S
       heap32_sift_up(F, j, ((F.slot((int)sl) & 0xffu) << 16) | (1u << sl));
     }
     if (n > 0) count0 = F.slot(0) & 0xffu;
+#ifndef MYB_PLAN_UNROLLED
+  } else if constexpr (CAP > 8 && ROLL15) {
+    // Up to 15 symbols, the same with rolled loops: the list is two words of 4-bit fields, 14 keys and more replay the
+    // reference's rehash on byte lists as before.
+    bool has_zero = false;
+    MYB_NOUNROLL
+    for (int k = 0; k < n; k++)
+      if ((F.slot(k) >> 16) == 0) has_zero = true;
+    // The reference's map also holds the key 0 while it is filled (trailing zeros or freq[0], Huffman.cpp:192-195); when
+    // the message has no zero it is inserted last and erased again (:201), which only matters when it is key number 14
+    // and triggers the rehash to 29 buckets.
+    const int keys = n + ((n > 0 && !has_zero) ? 1 : 0);
+    const bool rehash = warp.any(keys >= 14);
+    uint32_t olo = 0, ohi = 0;
+    if (!rehash) {
+      uint32_t blo = ~0u, bhi = ~0u;  // bucket of each list position; 0xF = empty, which is no bucket
+      MYB_NOUNROLL
+      for (int k = 0; k < n; k++) {
+        const uint32_t b = bucket13((int)(int16_t)(F.slot(k) >> 16));
+        int f = nib_find(blo, b);
+        int p = f >= 0 ? (f >> 2) : -1;
+        if (p < 0) {
+          f = nib_find(bhi, b);
+          p = f >= 0 ? 8 + (f >> 2) : 0;
+        }
+        if (p < 8) {
+          ohi = (ohi << 4) | (olo >> 28);
+          bhi = (bhi << 4) | (blo >> 28);
+          olo = nib_insert(olo, 4 * p, (uint32_t)k);
+          blo = nib_insert(blo, 4 * p, b);
+        } else {
+          ohi = nib_insert(ohi, 4 * (p - 8), (uint32_t)k);
+          bhi = nib_insert(bhi, 4 * (p - 8), b);
+        }
+      }
+    } else {
+      // 14..16 keys: replay the list rules on byte lists (list 0 = slots, 1 = buckets, 2 = copy)
+      const int m = (n == 13 && !has_zero) ? 14 : n;  // the appended key 0 only matters as key number 14
+      const int mw = warp.max(m);
+      int ln = 0;
+      MYB_NOUNROLL
+      for (int s = 0; s < mw; s++) {
+        if (s < m) {
+          if (s == 13) {  // _M_rehash_aux: walk the old list front to back and re-place every node among 29 buckets
+            for (int i = 0; i < 13; i++) F.lst(2, i) = F.lst(0, i);
+            ln = 0;
+            for (int i = 0; i < 13; i++) {
+              const int t = F.lst(2, i);
+              lst_place(F, 0, 1, ln, t, (int)bucket29((int)(int16_t)(F.slot(t) >> 16)));
+            }
+          }
+          const int v = s < n ? (int)(int16_t)(F.slot(s) >> 16) : 0;
+          lst_place(F, 0, 1, ln, s, (int)(s < 13 ? bucket13(v) : bucket29(v)));
+        }
+        warp.sync();
+      }
+      // to the nibble lists, dropping the appended key (slot number n) again
+      int wpos = 0;
+      MYB_NOUNROLL
+      for (int i = 0; i < mw; i++) {
+        if (i < m) {
+          const uint32_t t = F.lst(0, i);
+          if ((int)t < n) {
+            if (wpos < 8) olo |= t << (4 * wpos);
+            else ohi |= t << (4 * (wpos - 8));
+            wpos++;
+          }
+        }
+      }
+      warp.sync();
+    }
+    MYB_NOUNROLL
+    for (int j = 0; j < n; j++) {  // Huffman.cpp:207-209
+      const uint32_t sl = ((j < 8 ? olo >> (4 * (j & 7)) : ohi >> (4 * (j & 7)))) & 15u;
+      heap32_sift_up(F, j, ((F.slot((int)sl) & 0xffu) << 16) | (1u << sl));
+    }
+    if (n > 0) count0 = F.slot(0) & 0xffu;
+#endif
   } else {
   // ---- slot words into registers; is the value 0 part of the message?
   uint32_t sw[CAP];
@@ -981,11 +1061,11 @@ MYB_HD FastPlan huff_fast_plan_n(int n, int nw, int msg_len, const FastScratch<S
 }
 
 // Two instantiations, chosen per warp: the compact one when no block of the warp has more than 8 symbols.
-template <int STRIDE, class W>
+template <bool ROLL15 = true, int STRIDE, class W>
 MYB_HD FastPlan huff_fast_plan(int n, int msg_len, const FastScratch<STRIDE>& F, const W& warp) {
   const int nw = warp.umax(n);
   if (nw <= 8) return huff_fast_plan_n<8>(n, nw, msg_len, F, warp);
-  return huff_fast_plan_n<kFastCap>(n, nw, msg_len, F, warp);
+  return huff_fast_plan_n<kFastCap, STRIDE, W, ROLL15>(n, nw, msg_len, F, warp);
 }
 
 #define MYB_CSWAP(a, b)                          \

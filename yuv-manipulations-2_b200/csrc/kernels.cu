@@ -1305,7 +1305,7 @@ __global__ void __launch_bounds__(kCtaThreads, 7) heavy15_kernel(const __grid_co
     const uint32_t idxm = idx;
     const bool mlive = live && !over;
 #endif
-    const FastPlan pl = huff_fast_plan(nsym, Lm == 0 ? 1 : Lm, f8, FastPol{});
+    const FastPlan pl = huff_fast_plan<false>(nsym, Lm == 0 ? 1 : Lm, f8, FastPol{});  // every block here has 9..15 symbols: unrolled
     huff_fast_emit(z, pl, f8, P.ws.heavy_bytes + (uint64_t)idxm * 256, FastPol{});
     if (mlive) {
       const uint32_t size = (uint32_t)pl.size();
