@@ -20,3 +20,4 @@ ONE_PASS_FRAMES=16 python profiles/one_pass.py --parse $O/raw_nat16.csv nat:50 n
 timeout 900 python bench.py > $O/r02_bench_final.json 2> $O/r02_bench_final.err; echo "bench rc=$?"; tail -c 600 $O/r02_bench_final.json
 timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > $O/r02_bench_reference_arm.json 2> $O/r02_bench_reference_arm.err; echo "reference rc=$?"; cat $O/r02_bench_reference_arm.json | cut -c1-400
 timeout 300 python bench.py --workload shard8k --steps 20 > $O/r02_shard8k_1gpu.json 2> $O/shard1.err; echo "shard rc=$?"
+timeout 400 python profiles/phase_clocks.py > $O/r02_phase_clocks_final.json 2> $O/phase.err; echo "phase clocks rc=$?"

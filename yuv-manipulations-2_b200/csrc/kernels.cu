@@ -60,13 +60,18 @@ __device__ unsigned long long g_phase_clk[2][kPhases];
     if ((threadIdx.x & 31) == 0) sm.clk[threadIdx.x >> 5][k] += (unsigned long long)(ph_n_ - ph_t_); \
     ph_t_ = ph_n_;                                                \
   }
+#define PH_WARPS() ((int)(sizeof(sm.clk) / sizeof(sm.clk[0])))
 #define PH_INIT()                                                 \
-  if (threadIdx.x < 4 * kPhases) (&sm.clk[0][0])[threadIdx.x] = 0; \
+  for (int ph_i_ = threadIdx.x; ph_i_ < PH_WARPS() * kPhases; ph_i_ += blockDim.x) (&sm.clk[0][0])[ph_i_] = 0; \
   __syncthreads()
 #define PH_FLUSH(which)                                           \
   __syncthreads();                                                \
-  if (threadIdx.x < kPhases) atomicAdd(&g_phase_clk[which][threadIdx.x], sm.clk[0][threadIdx.x] + sm.clk[1][threadIdx.x] + sm.clk[2][threadIdx.x] + sm.clk[3][threadIdx.x])
-#define PH_MEMBER unsigned long long clk[4][kPhases];
+  if (threadIdx.x < kPhases) {                                    \
+    unsigned long long ph_s_ = 0;                                 \
+    for (int ph_w_ = 0; ph_w_ < PH_WARPS(); ph_w_++) ph_s_ += sm.clk[ph_w_][threadIdx.x]; \
+    atomicAdd(&g_phase_clk[which][threadIdx.x], ph_s_);           \
+  }
+#define PH_MEMBER(W) unsigned long long clk[W][kPhases];
 void read_phase_clocks(unsigned long long* out, int reset) {
   cudaDeviceSynchronize();
   cudaMemcpyFromSymbol(out, g_phase_clk, sizeof(unsigned long long) * 2 * kPhases);
@@ -80,7 +85,7 @@ void read_phase_clocks(unsigned long long* out, int reset) {
 #define PH(k)
 #define PH_INIT()
 #define PH_FLUSH(which)
-#define PH_MEMBER
+#define PH_MEMBER(W)
 void read_phase_clocks(unsigned long long* out, int) {
   for (int i = 0; i < 24; i++) out[i] = 0;
 }
@@ -719,7 +724,7 @@ struct EncSmemT {
   uint8_t msg_len[kEncThreads > 32 ? kEncTile : 1];
   uint8_t csize[kEncThreads > 32 ? kEncTile : 1];
   uint8_t perm[kEncThreads > 32 ? kEncTile : 1];
-  PH_MEMBER
+  PH_MEMBER(kEncThreads / 32)
 };
 constexpr int kEncCtasPerSm = EncCfg<false>::kCtasPerSm;  // the persistent grid is sized for the denser build
 static_assert((sizeof(EncSmemT<false>) + 1024) * EncCfg<false>::kCtasPerSm <= 228 * 1024, "EncSmem must allow kCtasPerSm CTAs per SM");
@@ -1849,7 +1854,7 @@ struct DecSmem {
   uint16_t boff[kDecThreads > 32 ? kDecTile : 1];
   uint8_t bsize[kDecThreads > 32 ? kDecTile : 1];
   uint8_t perm[kDecThreads > 32 ? kDecTile : 1];
-  PH_MEMBER
+  PH_MEMBER(kDecThreads / 32)
 };
 constexpr int kDecCtasPerSm = kDecThreads == 256 ? 3 : kDecThreads == 128 ? 6 : kDecThreads == 64 ? 11 : 22;
 static_assert((sizeof(DecSmem) + 1024) * kDecCtasPerSm <= 228 * 1024, "DecSmem must allow kDecCtasPerSm CTAs per SM");
