@@ -703,7 +703,7 @@ struct EncCfg {
   static constexpr int kCtasPerSm = MYB_ENC_CTAS;  // experiment: fewer CTAs, more registers each
 #else
   // resident CTAs per SM (registers and shared memory sized for it)
-  static constexpr int kCtasPerSm = kEncThreads == 256 ? 3 : kEncThreads == 64 ? 13 : kEncThreads == 32 ? 22 : (kCompact ? 7 : 6);
+  static constexpr int kCtasPerSm = kEncThreads == 256 ? 3 : kEncThreads == 64 ? (kCompact ? 13 : 11) : kEncThreads == 32 ? 22 : (kCompact ? 7 : 6);
 #endif
 };
 
@@ -1469,6 +1469,12 @@ __global__ void __launch_bounds__(1024) scan_frames_kernel(const __grid_constant
     if (threadIdx.x == 1023) carry_s = carry + warp_sums[31];
     __syncthreads();
   }
+  // how many blocks this launch queued, for the next launch's choice of build (mapped host memory, read without a sync)
+  if (threadIdx.x == 0 && P.ws.queue_stats) {
+    P.ws.queue_stats[0] = P.ws.counters[8];
+    P.ws.queue_stats[1] = P.g.nblk_frame * P.g.n_frames;
+    __threadfence_system();
+  }
 }
 
 // Byte position of a tile's chunks in the output buffer: fixed part (headers + size arrays up to this plane) + code bytes
@@ -1811,7 +1817,6 @@ __global__ void __launch_bounds__(32) shard_done_kernel(uint32_t* __restrict__ f
 // ranks in one process (virtual ranks on one device) the host would otherwise block inside a launch while the peers it has
 // not issued yet are what the spinning kernel waits for.
 void shard_preload();
-__global__ void publish_queue_stats_kernel(uint32_t* __restrict__ h_dst, const uint32_t* __restrict__ queued, uint32_t blocks);
 __global__ void publish_words_kernel(uint32_t* __restrict__ h_dst, const uint32_t* __restrict__ d_src, uint32_t n);
 
 void launch_shard_go(const ShardPeers& peers, cudaStream_t s) {
@@ -2453,14 +2458,6 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm)
 // ===================================================================================================
 // launchers
 // ===================================================================================================
-__global__ void publish_queue_stats_kernel(uint32_t* __restrict__ h_dst, const uint32_t* __restrict__ queued, uint32_t blocks) {
-  if (threadIdx.x == 0) {
-    h_dst[0] = *queued;
-    h_dst[1] = blocks;
-    __threadfence_system();
-  }
-}
-
 namespace {
 // code tiles, deferred blocks, the two scans: everything that needs no knowledge of where the payload goes
 void compress_code_and_scan(const EncParams& P, const QTables& qt, cudaStream_t s) {
@@ -2492,10 +2489,6 @@ void compress_code_and_scan(const EncParams& P, const QTables& qt, cudaStream_t 
   scan_frame_tiles_kernel<<<g.n_frames, 512, 0, s>>>(P);
   scan_frames_kernel<<<1, 1024, 0, s>>>(P);
   g_launches += ws.heavy_cap ? 6 : 3;
-  if (ws.queue_stats) {  // how many blocks this launch queued, for the next launch's choice of build (mapped host memory, read without a sync)
-    publish_queue_stats_kernel<<<1, 32, 0, s>>>(ws.queue_stats, ws.counters + 8, g.nblk_frame * g.n_frames);
-    g_launches++;
-  }
 }
 
 // tiles to their final place, headers and chunk-size arrays
@@ -2741,7 +2734,6 @@ void shard_preload() {
   cudaFuncGetAttributes(&a, shard_push_kernel);
   cudaFuncGetAttributes(&a, dct_compress_kernel<false>);
   cudaFuncGetAttributes(&a, dct_compress_kernel<true>);
-  cudaFuncGetAttributes(&a, publish_queue_stats_kernel);
   cudaFuncGetAttributes(&a, heavy15_kernel);
   cudaFuncGetAttributes(&a, heavy_blocks_kernel<32>);
   cudaFuncGetAttributes(&a, heavy_blocks_kernel<64>);
