@@ -576,6 +576,60 @@ def test_corrupt_code_stream_is_reported(ctx, ora, synth):
         ora.decompress(bad, w, h, q)
 
 
+def test_damaged_chunks_gpu_decoder_agrees_with_its_host_build(ctx, ora, synth, pkg):
+    """The decoder kernel's table parser and stream loop are written in PTX for the kernel's shared-memory layout; the same
+    decoder (block_codec.cuh) compiled for the host is what tests/test_hostemu.py checks against the oracle.  Random byte flips
+    in the chunks of the luma plane: the kernel must flag an error exactly when the host build does, and where both accept the
+    chunks, the pixels must be those of the coefficients the host build decoded (re-encoded cleanly and decoded by the oracle)."""
+    import ctypes as C
+    import pathlib
+    import subprocess
+
+    here = pathlib.Path(__file__).parent / "hostemu"
+    subprocess.run(["make", "-s", "-C", str(here)], check=True)
+    emu = C.CDLL(str(here / "libhostemu.so"))
+    u8p, i16p = C.POINTER(C.c_uint8), C.POINTER(C.c_int16)
+    emu.hostemu_decode_blocks2.argtypes = [u8p, u8p, C.c_uint32, C.c_int, i16p, C.POINTER(C.c_uint32)]
+    w, h, q = 64, 64, (90, 90, 90)
+    rng = np.random.default_rng(20261019)
+    f = rng.integers(0, 256, w * h * 3 // 2, dtype=np.uint8)  # noise: tables of every kind, long streams
+    f[: w * h // 2] = frames(synth, w, h)[0][: w * h // 2]     # and smooth content in the upper half
+    good = np.asarray(ora.compress(f, w, h, q), np.uint8)
+    psz = good[:12].view(np.uint32)
+    n = int(good[12:16].view(np.uint32)[0])
+    content_size = int(good[16:20].view(np.uint32)[0])
+    sizes_at, content_at = 20, 20 + n
+    assert n == (w // 8) * (h // 8) and psz[0] == 8 + n + content_size
+    sizes = np.ascontiguousarray(good[sizes_at: sizes_at + n])
+    rest = good[12 + int(psz[0]):]  # the two chroma planes, untouched
+    errors = accepted = 0
+    for trial in range(120):
+        bad = good.copy()
+        for _ in range(int(rng.integers(1, 4))):
+            at = content_at + int(rng.integers(0, content_size))
+            bad[at] ^= np.uint8(rng.integers(1, 256))
+        chunks = np.ascontiguousarray(bad[content_at: content_at + content_size])
+        coefs = np.zeros(n * 64, np.int16)
+        err = emu.hostemu_decode_blocks2(chunks.ctypes.data_as(u8p), sizes.ctypes.data_as(u8p), n, 1, coefs.ctypes.data_as(i16p), None)
+        try:
+            got = ctx.decompress(bad, w, h, q)
+            gpu_err = False
+        except pkg.MyyuvError:
+            gpu_err = True
+        assert gpu_err == (err != 0), f"trial {trial}: host build says {err}, kernel says {gpu_err}"
+        if err:
+            errors += 1
+            continue
+        accepted += 1
+        ch, sz = ora.huff_encode_blocks(coefs.reshape(n, 64))
+        ch, sz = np.asarray(ch, np.uint8).reshape(-1), np.asarray(sz, np.uint8).reshape(-1)
+        head = np.array([8 + n + ch.size, psz[1], psz[2]], np.uint32).view(np.uint8)
+        plane = np.concatenate([np.array([n, ch.size], np.uint32).view(np.uint8), sz, ch])
+        clean = np.concatenate([head, plane, rest])
+        assert np.array_equal(got, ora.decompress(clean, w, h, q)), f"trial {trial}"
+    assert errors >= 10 and accepted >= 10, (errors, accepted)
+
+
 def test_class_api_round_trip(pkg, ora, synth, tmp_path):
     """The reference-style class API (YUV(bmp, IYUV) -> compress -> dump -> load -> decompress)."""
     YUV, BMP = pkg.YUV, pkg.BMP
