@@ -606,16 +606,20 @@ def b200_main(args):
     dom = "dct_compress_kernel" if c_ms >= d_ms else "dct_decompress_kernel"
     dom_ms = max(c_ms, d_ms)
     achieved = alg_bytes / (dom_ms / 1e3) / 1e9
-    # DRAM bytes of the dominant kernel from the committed ncu capture (profiles/traffic.py writes it together with a hash of
-    # the kernel sources it was taken from); a capture of other sources is not reported
+    # DRAM bytes of the dominant kernel from the committed ncu capture (profiles/launch_list.py writes it together with the hashes
+    # of the library's SASS and of the kernel sources it was taken from); a capture of other code is not reported
     traffic, traffic_note, ncu_view = None, None, None
     try:
         tr = json.loads((ROOT / "profiles" / "r02_traffic.json").read_text())
-        if tr.get("sources_sha256") == kernel_sources_sha256():
+        # the capture counts for the machine code it was taken from: the SASS of the loaded library must hash the same
+        # (build.device_code_sha256); without cuobjdump, the kernel sources must
+        code = importlib.import_module("yuv-manipulations-2_b200.build").device_code_sha256()
+        same = (code == tr.get("device_code_sha256")) if code and tr.get("device_code_sha256") else (tr.get("sources_sha256") == kernel_sources_sha256())
+        if same:
             traffic = int((tr[dom]["dram_read"] + tr[dom]["dram_write"]) * F / tr["frames"])
             ncu_view = tr.get("ncu")
         else:
-            traffic_note = "profiles/r02_traffic.json was captured from other kernel sources than the ones running: not reported"
+            traffic_note = "profiles/r02_traffic.json was captured from other kernel code than the library that is running: not reported"
     except Exception as e:  # noqa: BLE001
         traffic_note = f"no ncu capture for these sources: {e!r}"
     nblocks = F * (W * H // 64 * 3 // 2)

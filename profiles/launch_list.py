@@ -63,4 +63,7 @@ if len(sys.argv) > 3:
                "issue_active_pct", "pipe_alu_pct", "pipe_fma_pct", "pipe_lsu_pct", "warps_active_pct", "icache_hit_pct", "dram_throughput_pct",
                "stall_samples_pct")} for k in full}
         ncu["workload"] = sys.argv[5] if len(sys.argv) > 5 else "8 frames"
-    json.dump({"frames": 64, "source": src, "sources_sha256": h.hexdigest(), "ncu": ncu, **t}, open(sys.argv[3], "w"), indent=1)
+    import importlib
+    sys.path.insert(0, str(csrc.parent.parent))
+    code = importlib.import_module("yuv-manipulations-2_b200.build").device_code_sha256()  # the SASS of the library that ran
+    json.dump({"frames": 64, "source": src, "sources_sha256": h.hexdigest(), "device_code_sha256": code, "ncu": ncu, **t}, open(sys.argv[3], "w"), indent=1)

@@ -57,6 +57,19 @@ def test_no_fma_contraction_in_sass(pkg):
     assert 248 + 64 + 8 <= enc["FMUL2"] <= 256 + 64 + 8 and 700 <= dec["FMUL2"] <= 512 + sum(2 * K * (K + 1) + 32 * K for K in (4, 7))  # identical products may be shared (exact)
 
 
+def test_device_code_identity(pkg):
+    """bench.py reports the DRAM traffic of a committed ncu capture only for the machine code the capture was taken from:
+    the identity is a hash of the library's SASS, which a comment edit keeps and a changed instruction does not."""
+    import importlib, json
+
+    build = importlib.import_module("yuv-manipulations-2_b200.build")
+    a, b = build.device_code_sha256(), build.device_code_sha256(pkg.library_path())
+    assert a is not None and re.fullmatch(r"[0-9a-f]{64}", a) and a == b
+    assert build.device_code_sha256(pathlib.Path(__file__)) is None  # not a CUDA binary: no identity, bench falls back to the source hash
+    tr = json.loads((pathlib.Path(__file__).resolve().parent.parent / "profiles" / "r02_traffic.json").read_text())
+    assert re.fullmatch(r"[0-9a-f]{64}", tr["device_code_sha256"]) and re.fullmatch(r"[0-9a-f]{64}", tr["sources_sha256"])
+
+
 def test_compress_bound(pkg):
     nblk = (3840 // 8) * (2160 // 8) * 3 // 2
     assert pkg.capi.compress_bound(3840, 2160) == 36 + nblk * 256

@@ -55,6 +55,29 @@ def build_cuda(force: bool = False, verbose: bool = False, variant: str = "") ->
     return out
 
 
+def device_code_sha256(lib: pathlib.Path | None = None) -> str | None:
+    """sha256 of the library's SASS (cuobjdump -sass, comment and blank lines dropped): the identity of the machine code the
+    GPU runs.  profiles/launch_list.py records it with an ncu capture and bench.py reports the capture's DRAM traffic only when
+    the library it has loaded hashes the same -- an edit of a comment keeps a capture valid, another compiler flag does not.
+    None when cuobjdump is not available."""
+    import hashlib
+
+    lib = lib or (LIB / "libmyyuvb200.so")
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    try:
+        r = subprocess.run([tool, "-sass", str(lib)], capture_output=True, text=True, timeout=120)
+    except (OSError, subprocess.SubprocessError):
+        return None
+    if r.returncode != 0 or "Function :" not in r.stdout:
+        return None
+    h = hashlib.sha256()
+    for line in r.stdout.splitlines():
+        t = line.strip()
+        if t and not t.startswith("//"):
+            h.update(t.encode() + b"\n")
+    return h.hexdigest()
+
+
 def build_cxx(force: bool = False, verbose: bool = False):
     """The drop-in class library and (if the reference CLI object is available) the unmodified CLI on top of it."""
     LIB.mkdir(exist_ok=True)

@@ -1,9 +1,12 @@
 // block_codec.cuh -- per-8x8-block entropy coding of the reference's DCT payload, written for one GPU
-// thread per block with the 32 lanes of a warp running in LOCKSTEP: every loop has a warp-uniform trip
-// count (the warp maximum) and a predicated body, so lanes with short messages idle in step instead of
-// drifting apart (the first, free-running version averaged 2.6 active lanes per instruction, see
-// profiles/r01_notes.md).  Everything here is integer/byte work, so it is plain __host__ __device__ code:
-// the kernels in kernels.cu call it with the WarpLockstep policy, and tests/hostemu/hostemu.cpp compiles
+// thread per block.  How the 32 lanes of a warp go through the data dependent loops is a POLICY argument of every function:
+//   WarpFree      (the kernels' choice) each lane runs its own trip counts and the hardware reconverges the warp behind the
+//                 loop; only choices the whole warp makes together use a warp reduction (umax);
+//   WarpLockstep  (round 1; -DMYB_LOCKSTEP) every loop runs to the warp maximum with a predicated body and a warp barrier per
+//                 iteration -- written after a first version whose lanes had drifted apart (2.6 active lanes per instruction,
+//                 profiles/r01_notes.md); with one call per phase and sorted blocks it only costs instructions;
+//   NoWarp        every "lane" runs alone: the host build.
+// Everything here is integer/byte work, so it is plain __host__ __device__ code: tests/hostemu/hostemu.cpp compiles
 // the same header with g++ (policy NoWarp) so the logic can be checked against the oracle without a GPU
 // (test infrastructure only -- the product never runs it on the CPU).
 //

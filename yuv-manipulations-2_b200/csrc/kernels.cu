@@ -4,19 +4,25 @@
 //  * The reference's DCT is a plain float C.X.C^T with sequential, UNFUSED multiply/add in a fixed order
 //    (DCT.cpp:232-277) and its results are pinned by golden files, so every product and every sum below
 //    is an individually rounded IEEE binary32 operation: no FMA contraction of mul+add, no tensor cores,
-//    no fast factorisation.  The issue-slot cost is halved with Blackwell's packed FP32x2 instructions:
-//    one thread transforms TWO 8x8 blocks at once, lane .x = block A, lane .y = block B
-//    (mul.rn.f32x2 / fma.rn.f32x2 -> SASS FMUL2 / FFMA2), the 64 DCT constants are immediates.
+//    no fast factorisation.  The issue-slot cost is halved with Blackwell's packed FP32x2 instructions
+//    (mul.rn.f32x2 / fma.rn.f32x2 -> SASS FMUL2 / FFMA2): one thread transforms one 8x8 block, the two lanes of
+//    an instruction are two adjacent columns (forward transform: stage-1 constants are scalar immediates) or two
+//    rows (inverse transform) of that block -- see fdct_quant_block / idct_block.
 //  * ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under -fmad=false (checked with cuobjdump),
 //    which would change results.  The accumulation  acc + p  is therefore issued as fma(p, ONE, acc) with
 //    ONE = 1.0f passed at run time: bit-identical to an add, and not contractible with the producing mul.
-//  * Entropy coding is one thread per block (block_codec.cuh) on coefficients staged in shared memory, the
-//    lanes of a warp in lockstep.  Chunk bytes are laid out per tile in shared memory.
+//  * Entropy coding is one thread per block (block_codec.cuh) on coefficients staged in shared memory.  The
+//    blocks of a tile are sorted by message length (chunk size in the decoder) so that the lanes of a warp get
+//    similar work; the data dependent loops run per lane and the hardware reconverges the warp behind each
+//    (WarpFree policy; holding the lanes in step by hand, round 1's WarpLockstep, only cost instructions).
+//    Chunk bytes are laid out per tile in shared memory.
 //  * Compress needs the byte offset of every chunk in file order.  A single-pass decoupled look-back made
 //    every tile wait for all earlier tiles still being coded (17% of issued instructions were the spin,
-//    18% of stalls the barrier behind it: profiles/r01_notes.md), so compress is three launches with no
-//    inter-CTA waiting: (1) code tiles, park each tile's bytes in a bump-allocated scratch area;
-//    (2) scan the tile totals; (3) move every tile to its final place and write headers and size arrays.
+//    18% of stalls the barrier behind it: profiles/r01_notes.md), so compress is a sequence of launches with no
+//    inter-CTA waiting: (1) code tiles, park each tile's bytes in a bump-allocated scratch area, queue the
+//    blocks with more distinct symbols than the tile pass codes; (1a/1b) code the queue (heavy15_kernel,
+//    heavy_blocks_kernel); (2) scan the tile totals; (3) move every tile to its final place and write headers
+//    and size arrays.
 //    Decompress knows all chunk sizes up front: two tiny pre-passes (tile totals, per-plane scan) give every
 //    tile its offset, so it has no look-back either.
 //  * Persistent CTAs take tiles from an atomic ticket (load balance).
@@ -730,7 +736,8 @@ constexpr int kEncCtasPerSm = EncCfg<false>::kCtasPerSm;  // the persistent grid
 static_assert((sizeof(EncSmemT<false>) + 1024) * EncCfg<false>::kCtasPerSm <= 228 * 1024, "EncSmem must allow kCtasPerSm CTAs per SM");
 static_assert((sizeof(EncSmemT<true>) + 1024) * EncCfg<true>::kCtasPerSm <= 228 * 1024, "EncSmem must allow kCtasPerSm CTAs per SM");
 // Thread t codes the block of rank t in message-length order, so that the lanes of a warp get messages of similar length
-// and the lockstep loops (trip count = warp maximum) waste few lanes.  Five more CTA barriers per tile.
+// and the warp, which reconverges behind each of the coder's per-lane loops, waits little for its longest lane.  Five more
+// CTA barriers per tile.
 constexpr bool kSortBlocks = kEncThreads > 32;
 static_assert(!kSortBlocks || kEncPasses == 1, "boff holds 16-bit offsets of a one-pass tile");
 
@@ -1014,7 +1021,7 @@ __global__ void __launch_bounds__(kEncThreads, EncCfg<kInPlace>::kCtasPerSm)
         L = fdct_quant_block(raw, qt, plane, P.one, z.col);
       }
       PH(1);  // load + DCT + quantise
-      // ---- phase B: entropy-code one block; warp lockstep ----
+      // ---- phase B: entropy-code one block (per-lane loops, warp collectives between the phases) ----
       if (!live) L = 0;
       uint32_t mine = (uint32_t)tid;  // the block (of this pass) this thread codes
       if (kSortBlocks) {
@@ -2352,7 +2359,7 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm)
     __syncthreads();
     PH(1);  // staging loads, size scan, zero fill
 
-    // ---- phase 1: canonical Huffman decode + dequantise into the thread's shared-memory column (warp lockstep) ----
+    // ---- phase 1: canonical Huffman decode + dequantise into the thread's shared-memory column (per-lane loops) ----
     uint32_t blk = tid, boff = off, bsize = size;  // the block this thread decodes and transforms
     if (kSortDecBlocks) {
       const uint32_t key = (size >> 2) < 63u ? (size >> 2) : 63u;
