@@ -2346,6 +2346,12 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm)
     }
     uint32_t scanned;
     const uint32_t off = cta_exclusive_scan<kDecThreads>(size, sm.warp_sums, &scanned);
+#ifdef MYB_DEC_SORT_BITS
+    // The chunk's first two bytes are the length of its code stream in bits (Huffman.cpp:279-283).  They are the sort key
+    // below; the loads are in flight during the zero fill.
+    uint32_t hdr_bits = 0;
+    if (size >= 2u) hdr_bits = (uint32_t)__ldg(content + off) | ((uint32_t)__ldg(content + off + 1) << 8);
+#endif
     {  // the whole coefficient array, 128 bits per store (the columns are only written between the next barrier and the IDCT)
       uint4* z4 = reinterpret_cast<uint4*>(&sm.coef[0][0]);
 #pragma unroll
@@ -2362,7 +2368,11 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm)
     // ---- phase 1: canonical Huffman decode + dequantise into the thread's shared-memory column (per-lane loops) ----
     uint32_t blk = tid, boff = off, bsize = size;  // the block this thread decodes and transforms
     if (kSortDecBlocks) {
+#ifdef MYB_DEC_SORT_BITS
+      const uint32_t key = (hdr_bits >> 1) < 63u ? (hdr_bits >> 1) : 63u;
+#else
       const uint32_t key = (size >> 2) < 63u ? (size >> 2) : 63u;
+#endif
       const uint32_t within = atomicAdd(&sm.hist[key], 1u);
       __syncthreads();
       if (tid < 32) {  // exclusive prefix of the 64 bins, two per lane
