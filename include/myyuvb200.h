@@ -111,7 +111,9 @@ MYYUVB_API int myyuvb_dct_decompress(myyuvb_ctx* ctx, const uint8_t* payload, ui
 MYYUVB_API int myyuvb_xrgb_to_iyuv_batch_dev(myyuvb_ctx* ctx, const uint8_t* d_bgrx, uint32_t width, uint32_t height,
                                              int bottom_up, uint32_t n_frames, uint8_t* d_iyuv);
 
-/* d_bgr: n_frames * w*h*3 (8-byte aligned, w*h*3 a multiple of 8), d_iyuv: n_frames * w*h*3/2. */
+/* d_bgr: n_frames * w*h*3, d_iyuv: n_frames * w*h*3/2.  Alignment follows the kernel that runs: for width % 8 == 0 (64-bit
+ * loads) d_bgr must be 8-byte aligned and, in a batch of more than one frame, w*h*3 a multiple of 8, d_iyuv 8-byte aligned;
+ * other widths are read bytewise and need no input alignment (d_iyuv 2-byte aligned). */
 MYYUVB_API int myyuvb_bgr24_to_iyuv_batch_dev(myyuvb_ctx* ctx, const uint8_t* d_bgr, uint32_t width, uint32_t height,
                                               int bottom_up, uint32_t n_frames, uint8_t* d_iyuv);
 
