@@ -70,6 +70,30 @@ def test_device_code_identity(pkg):
     assert re.fullmatch(r"[0-9a-f]{64}", tr["device_code_sha256"]) and re.fullmatch(r"[0-9a-f]{64}", tr["sources_sha256"])
 
 
+def test_device_free_entry_points(pkg):
+    """The C ABI's entry points that need no device: the band split of a sharded image (270 macroblock rows of 8K over
+    8 ranks = 34 x 6 + 33 x 2) agrees with the host-side split the gloo tests use, plane accessors follow YUV::getYUVPlanes /
+    getWidthHeightChannel (myyuv_yuv.cpp:383-427), and arguments are rejected with the documented codes before anything is launched."""
+    import importlib
+
+    capi = pkg.capi
+    sh = importlib.import_module("yuv-manipulations-2_b200.sharding")
+    rows = capi.shard_rows(4320, 8)
+    assert [(b - a) // 16 for a, b in zip(rows, rows[1:])] == [34, 34, 34, 34, 34, 34, 33, 33] and rows[0] == 0 and rows[-1] == 4320
+    for h in (16, 32, 48, 736, 2160 // 16 * 16, 4320):
+        for world in (1, 2, 3, 5, 8, 16):
+            rows = capi.shard_rows(h, world)
+            assert list(zip(rows, rows[1:])) == sh.macroblock_row_bands(h, world)
+    for bad in ((4328, 8), (4320, 0), (4320, 17)):
+        with pytest.raises(pkg.MyyuvError) as e:
+            capi.shard_rows(*bad)
+        assert e.value.code == (capi.ERR_HEIGHT if bad[0] % 16 else capi.ERR_ARG)
+    base = 0x10000
+    assert capi.iyuv_planes(base, 3840, 2160) == [(base, 3840, 2160), (base + 3840 * 2160, 1920, 1080), (base + 3840 * 2160 * 5 // 4, 1920, 1080)]
+    assert capi.shard_ctrl_bytes() >= 16 * 16 + 16 * 4 and capi.shard_ctrl_bytes() % 8 == 0
+    assert capi.compress_bound(3840, 2160) == 12 + 3 * 8 + (3840 * 2160 // 64 * 3 // 2) * 256  # headers + 1 size byte + 255 chunk bytes per block
+
+
 def test_compress_bound(pkg):
     nblk = (3840 // 8) * (2160 // 8) * 3 // 2
     assert pkg.capi.compress_bound(3840, 2160) == 36 + nblk * 256
