@@ -30,7 +30,9 @@ struct ZArray {  // same views as the kernel's ZShared
 namespace {
 // mode 0: general code on the 64-symbol scratch only; 1: 15-symbol scratch first (the kernel's pre-fast8 flow);
 // 2: the kernel's flow -- hash histogram, then the 15-symbol fast path or the general code on the 64-symbol scratch;
-// 3: as 2, with the general code as heavy_blocks_kernel runs it (split accessors, 32-symbol scratch, then 64)
+// 3: as 2, with the general code as heavy_blocks_kernel runs it (split accessors, 32-symbol scratch, then 64);
+// 4, 5: the fast-path instantiations as the two builds of the coding kernel and heavy15_kernel call them, with a warp maximum
+//       above the lane's own symbol count (see below)
 template <int STRIDE>
 int encode_blocks(const int16_t* coef, uint32_t n, int mode, uint8_t* out, uint8_t* sizes) {
   using Fast = HuffScratch<15, STRIDE>;
@@ -71,6 +73,43 @@ int encode_blocks(const int16_t* coef, uint32_t n, int mode, uint8_t* out, uint8
         sz = pl.size();
         done = true;
       }
+    }
+    if (mode == 4 || mode == 5) {
+      // The instantiations exactly as the kernels call them, for a lane whose warp holds blocks with MORE symbols than its own
+      // (nw = the warp's maximum > n: the loops then run to nw with this lane's part predicated):
+      //   mode 4  dct_compress_kernel<queue>: histogram to 8, huff_fast_plan_n<8> / huff_fast_emit_n<8> with nw in n..8; blocks
+      //           with more go the way of heavy15_kernel: histogram to 15, the UNROLLED 15-symbol plan, nw in n..15
+      //   mode 5  dct_compress_kernel<in place>: histogram to 15, the rolled 15-symbol plan with nw in max(n, 9)..15 also for
+      //           lanes with 8 symbols and fewer
+      const int lane = STRIDE > 1 ? (int)(b % STRIDE) : 0;
+      FastScratch<STRIDE> F{f8sc + lane, reinterpret_cast<uint8_t*>(f8aux), lane};
+      for (int i = 0; i < 32; i++) F.tab(i) = 0xffff;
+      int ns = mode == 4 ? huff_hist<8>(za, L, true, F, NoWarp{}) : huff_hist<kFastCap>(za, L, true, F, NoWarp{});
+      const int ml = L == 0 ? 1 : L;
+      if (mode == 4 && ns >= 0) {
+        const int nw = ns + (int)((b * 5u) % (uint32_t)(9 - ns));  // n..8
+        const FastPlan pl = huff_fast_plan_n<8>(ns, nw, ml, F, NoWarp{});
+        huff_fast_emit_n<8>(za, pl, nw, F, tmp, NoWarp{});
+        sz = pl.size();
+        done = true;
+      } else {
+        if (mode == 4) {
+          for (int i = 0; i < 64; i++) za.setraw(i, (uint32_t)(((int32_t)(za.raw(i) << 21)) >> 21));
+          for (int i = 0; i < 32; i++) F.tab(i) = 0xffff;
+          ns = huff_hist<kFastCap>(za, L, true, F, NoWarp{});
+        }
+        if (ns >= 0) {
+          const int lo = ns < 9 ? 9 : ns;
+          const int nw = lo + (int)((b * 3u) % (uint32_t)(kFastCap + 1 - lo));  // max(n, 9)..15
+          const FastPlan pl = mode == 4 ? huff_fast_plan_n<kFastCap, STRIDE, NoWarp, false>(ns, nw, ml, F, NoWarp{})
+                                        : huff_fast_plan_n<kFastCap, STRIDE, NoWarp, true>(ns, nw, ml, F, NoWarp{});
+          huff_fast_emit_n<kFastCap>(za, pl, nw, F, tmp, NoWarp{});
+          sz = pl.size();
+          done = true;
+        }
+      }
+      if (!done)  // more than 15 symbols: the general code starts over from the coefficient values
+        for (int i = 0; i < 64; i++) za.setraw(i, (uint32_t)(((int32_t)(za.raw(i) << 21)) >> 21));
     }
     if (!done && mode == 3) {
       // heavy_blocks_kernel's flow: coefficients read in place, slot numbers in a byte column; 32-symbol scratch, then 64

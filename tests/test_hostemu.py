@@ -78,7 +78,7 @@ def make_blocks(kind, n, rng):
 
 @pytest.mark.parametrize("kind,n", [("sparse", 6000), ("mid", 6000), ("distinct", 6000), ("full", 1500), ("small", 6000),
                                     ("nozero", 1800), ("zeros", 64), ("few", 40000), ("around32", 3000)])
-@pytest.mark.parametrize("stride,fast", [(1, 1), (128, 1), (1, 0), (1, 2), (32, 2), (1, 3), (64, 3)])
+@pytest.mark.parametrize("stride,fast", [(1, 1), (128, 1), (1, 0), (1, 2), (32, 2), (1, 3), (64, 3), (32, 4), (1, 4), (32, 5)])
 def test_block_coder_matches_oracle(emu, ora, kind, n, stride, fast):
     rng = np.random.default_rng(hash(kind) % 1000)
     b = make_blocks(kind, n, rng)
