@@ -137,3 +137,22 @@ def test_exact_division_identity(emu):
 
 def test_round_half_away_identity(emu):
     assert emu.hostemu_round_check(400000, 2) == 0
+
+
+def test_block_row_col_identity():
+    """kernels.cu block_row_col: block index -> (block row, block column) without a division.  With magic = floor(2^32 / bw),
+    floor(k * magic / 2^32) is the row or one less for every k < 2^32 (the error of the product is below k / 2^32 < 1), and one
+    conditional step repairs it; bw = 1 uses magic = 2^32 - 1.  Checked on every plane width of the tested image sizes, on
+    awkward widths, at the row boundaries and at the top of the 32-bit range."""
+    rng = np.random.default_rng(5)
+    for bw in (1, 2, 3, 5, 7, 62, 124, 240, 252, 480, 504, 960, 1023, 8191, 65535):
+        magic = (1 << 32) // bw if bw > 1 else 0xFFFFFFFF
+        q = rng.integers(0, (1 << 32) // bw, 20000, dtype=np.uint64)
+        k = np.concatenate([q * bw, q * bw + (bw - 1), np.minimum(q * bw + rng.integers(0, bw, q.size, dtype=np.uint64), (1 << 32) - 1),
+                            np.array([0, 1, bw - 1, bw, (1 << 32) - 1, (1 << 32) - bw], np.uint64)])
+        k = k[k < (1 << 32)]
+        by = (k * np.uint64(magic)) >> np.uint64(32)
+        bx = k - by * np.uint64(bw)
+        fix = bx >= bw
+        by, bx = by + fix, bx - fix * np.uint64(bw)
+        assert np.array_equal(by, k // np.uint64(bw)) and np.array_equal(bx, k % np.uint64(bw))
