@@ -47,3 +47,12 @@ def test_reference_arm_under_torchrun_runs_on_rank_0_only():
                         "--cpu-frames", "1"], capture_output=True, text=True, timeout=580, cwd=ROOT, env=env)
     assert r.returncode == 0, r.stderr[-2000:]
     check_line(r.stdout, 2)  # one line for the whole job: the other rank printed nothing
+
+
+def test_product_arm_has_no_cpu_path():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert r.returncode != 0 and "no CUDA device" in r.stderr and not [l for l in r.stdout.splitlines() if l.startswith("{")]
