@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <functional>
@@ -130,9 +131,12 @@ static void yuv_case(const std::string& path, const std::string& tmp) {
         printf("\n");
       });
       const uint32_t w = y.getWidth(), h = y.getHeight();
-      const uint32_t xs[] = {0, 1, w / 2, w - 1, w, 5}, ys[] = {0, 1, h / 2, h - 1, 3, h};
-      for (int i = 0; i < 6; i++)
+      // (the reference's chroma index runs past its buffer on the last row for x >= w / 2: undefined there, not asked for here)
+      const uint32_t xs[] = {0, 1, w / 2, w - 1, w / 2 - 1, w, 5}, ys[] = {0, 1, h / 2, h - 2, h - 1, 3, h};
+      for (int i = 0; i < 7; i++)
         guarded("getPixel", [&] { arr("pixel", y.getPixel(xs[i], ys[i])); });
+      if (getenv("CLASS_DIFF_EXTRA"))  // the drop-in library alone (sanitizer run): where the reference's index leaves its buffer, the sample is 0
+        guarded("getPixel", [&] { arr("pixel (last row, right half)", y.getPixel(w - 1, h - 1)); });
       guarded("decompress (not compressed)", [&] {
         YUV d = y.decompress();
         show(d, "decompress copy");

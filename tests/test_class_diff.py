@@ -50,7 +50,7 @@ def binaries():
     return HERE / "class_diff_ours", HERE / "class_diff_ref"
 
 
-def test_class_api_host_behaviour_equals_the_reference(binaries, tmp_path):
+def write_cases(tmp_path):
     files = {
         "a_32_bottom_up.bmp": bmp_file(8, 6, seed=1),
         "b_32_top_down.bmp": bmp_file(8, -6, seed=2),
@@ -88,6 +88,11 @@ def test_class_api_host_behaviour_equals_the_reference(binaries, tmp_path):
     for g in ("chef-with-trumpet.bmp", "chef-with-trumpet.myyuv", "chef-with-trumpet-DCT-50.myyuv"):
         if (GOLD / g).exists():
             paths.append(str(GOLD / g))
+    return paths
+
+
+def test_class_api_host_behaviour_equals_the_reference(binaries, tmp_path):
+    paths = write_cases(tmp_path)
     outs = []
     for i, exe in enumerate(binaries):
         scratch = tmp_path / f"scratch{i}"
@@ -99,3 +104,19 @@ def test_class_api_host_behaviour_equals_the_reference(binaries, tmp_path):
     assert len(ref) > 150  # the transcript is not trivially empty
     diff = [(a, b) for a, b in zip(ours, ref) if a != b]
     assert len(ours) == len(ref) and not diff, "first differences (ours, reference):\n" + "\n".join(f"{a}\n{b}" for a, b in diff[:8])
+
+
+def test_class_api_host_side_under_sanitizers(tmp_path):
+    """The same transcript with the drop-in library's host classes compiled under AddressSanitizer + UBSan, plus the one query the
+    differential run leaves out because the reference reads past its buffer there (getPixel on the last row, right half)."""
+    r = subprocess.run(["make", "-s", "-C", str(HERE), str(HERE / "class_diff_asan")], capture_output=True, text=True)
+    if r.returncode != 0 and "sanitize" in r.stderr:
+        pytest.skip("no sanitizer runtime for /usr/bin/g++")
+    assert r.returncode == 0, r.stderr[-2000:]
+    paths = write_cases(tmp_path)
+    scratch = tmp_path / "scratch"
+    scratch.mkdir()
+    env = dict(__import__("os").environ, CLASS_DIFF_EXTRA="1", ASAN_OPTIONS="detect_leaks=1:protect_shadow_gap=0", UBSAN_OPTIONS="print_stacktrace=1")
+    r = subprocess.run([str(HERE / "class_diff_asan"), str(scratch)] + paths, capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0 and "Sanitizer" not in r.stderr and "runtime error" not in r.stderr, r.stderr[-3000:]
+    assert "pixel (last row, right half)" in r.stdout and len(r.stdout.splitlines()) > 150

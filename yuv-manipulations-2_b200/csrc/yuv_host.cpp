@@ -110,11 +110,16 @@ std::array<uint8_t, YUV::max_planes> iyuv_pixel(const YUV& img, uint32_t x, uint
   const uint32_t w = img.getWidth(), h = img.getHeight();
   if (img.isCompressed()) throw std::runtime_error("Cannot get pixel from compressed image. Decompress first.");
   if (x >= w || y >= h) throw std::runtime_error("Image coordinates are out of bounds");
-  const uint32_t c = x / 2 + y * w / 4;
+  // The reference's chroma index (x / 2 + y * width / 4, myyuv_yuv.cpp:175) equals (y / 2) * (width / 2) + x / 2 on even rows only; on
+  // odd rows it lies width / 4 further on, and on the LAST row it runs past the V plane for x >= width / 2, where the reference
+  // reads whatever follows its buffer.  Here, as in get_pixels_kernel, that sample is 0.
+  const uint64_t frame = (uint64_t)w * h * 3 / 2;
+  const uint64_t c = x / 2 + (uint64_t)(y * w / 4);
+  const uint64_t vi = (uint64_t)w * h * 5 / 4 + c;
   std::array<uint8_t, YUV::max_planes> px{0};
-  px[0] = img.data[x + y * w];
-  px[1] = img.data[w * h + c];
-  px[2] = img.data[w * h * 5 / 4 + c];
+  px[0] = img.data[x + (uint64_t)y * w];
+  px[1] = img.data[(uint64_t)w * h + c];
+  px[2] = vi < frame ? img.data[vi] : (uint8_t)0;
   return px;
 }
 
