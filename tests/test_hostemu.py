@@ -134,6 +134,50 @@ def test_fast_and_general_decoder_agree_on_damaged_chunks(emu, ora):
             assert np.array_equal(d0, d1), i
 
 
+def test_decoders_agree_on_arbitrary_bytes(emu, ora):
+    """Chunks that no encoder wrote: random bytes of every size from 0 to 255, random bytes behind a plausible header, and valid
+    chunks cut short.  The step-by-step decoder (Huffman.cpp:106-154, :243-277) and the kernels' fast decoder must give the same
+    verdict and, where they accept, the same coefficients; the oracle's decoder must agree with both (it is the reference's
+    behaviour restated).  Each chunk sits in a buffer of exactly its size, so the sanitizer run sees any read past it."""
+    rng = np.random.default_rng(11)
+    valid_c, valid_s = ora.huff_encode_blocks(make_blocks("few", 600, rng))
+    voff = np.concatenate([[0], np.cumsum(valid_s, dtype=np.int64)])
+    cases = []
+    for size in range(0, 256):
+        for _ in range(8):
+            cases.append(rng.integers(0, 256, size, dtype=np.uint8))
+    for _ in range(4000):  # header says: few bits, small table -- the rest is noise
+        size = int(rng.integers(3, 80))
+        c = rng.integers(0, 256, size, dtype=np.uint8)
+        c[0], c[1], c[2] = rng.integers(0, 256), rng.integers(0, 2), rng.integers(0, size)
+        cases.append(c)
+    for i in range(600):  # truncated valid chunks
+        full = valid_c[voff[i]: voff[i + 1]]
+        cases.append(full[: int(rng.integers(0, full.size))].copy())
+    accepted = 0
+    for i, c in enumerate(cases):
+        one = np.ascontiguousarray(c)
+        if one.size == 0:
+            one = np.zeros(1, np.uint8)[:0].copy()
+        sz = np.array([c.size], np.uint8)
+        d0, d1 = np.zeros((1, 64), np.int16), np.zeros((1, 64), np.int16)
+        buf = one if one.size else np.zeros(1, np.uint8)  # a pointer is needed even for an empty chunk
+        r0 = emu.hostemu_decode_blocks2(buf.ctypes.data_as(u8p), sz.ctypes.data_as(u8p), 1, 0, d0.ctypes.data_as(i16p), None)
+        r1 = emu.hostemu_decode_blocks2(buf.ctypes.data_as(u8p), sz.ctypes.data_as(u8p), 1, 1, d1.ctypes.data_as(i16p), None)
+        assert r0 == r1, (i, c.size)
+        try:
+            want = ora.huff_decode_blocks(buf[: c.size], sz) if c.size else None
+        except Exception:  # noqa: BLE001 -- the oracle raises where the reference throws
+            want = None
+        assert (want is not None) == (r0 == 0) or c.size == 0, (i, c.size)
+        if r0 == 0:
+            accepted += 1
+            assert np.array_equal(d0, d1), i
+            if want is not None:
+                assert np.array_equal(want.reshape(1, 64), d0), i
+    assert 0 < accepted < len(cases)  # the family contains both kinds
+
+
 def test_exact_division_identity(emu):
     assert emu.hostemu_division_check(40000, 1) == 0
 
