@@ -3,6 +3,7 @@
 files -- header normalisation on load (myyuv_bmp.cpp:141-166, myyuv_yuv.cpp:485-510), validity rules (:127-139, :248-262),
 orientation handling of colorData() (:80-103), accessors, getPixel (myyuv_yuv.cpp:162-180), copies / moves, dump, exception texts --
 and the two transcripts must be identical.  What reaches the codec is covered by the GPU tests (tests/test_dropin_cli.py)."""
+import os
 import pathlib
 import struct
 import subprocess
@@ -32,7 +33,7 @@ def bmp_file(w, h, bits=32, gap=0, typ=b"BM", compression=None, used=0, importan
     return hdr + col + bytes(range(gap)) + pix
 
 
-def yuv_file(w, h, gap=0, typ=b"YU", fourcc=0x56555949, compression=0, params=b"", params_first=True, data=None, seed=0):
+def yuv_file(w, h, gap=0, typ=b"YU", fourcc=0x56555949, compression=0, params=b"", data=None, seed=0):
     rng = np.random.default_rng(seed)
     if data is None:
         data = rng.integers(0, 256, w * h * 3 // 2, dtype=np.uint8).tobytes()
@@ -116,7 +117,7 @@ def test_class_api_host_side_under_sanitizers(tmp_path):
     paths = write_cases(tmp_path)
     scratch = tmp_path / "scratch"
     scratch.mkdir()
-    env = dict(__import__("os").environ, CLASS_DIFF_EXTRA="1", ASAN_OPTIONS="detect_leaks=1:protect_shadow_gap=0", UBSAN_OPTIONS="print_stacktrace=1")
+    env = dict(os.environ, CLASS_DIFF_EXTRA="1", ASAN_OPTIONS="detect_leaks=1:protect_shadow_gap=0", UBSAN_OPTIONS="print_stacktrace=1")
     r = subprocess.run([str(HERE / "class_diff_asan"), str(scratch)] + paths, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0 and "Sanitizer" not in r.stderr and "runtime error" not in r.stderr, r.stderr[-3000:]
     assert "pixel (last row, right half)" in r.stdout and len(r.stdout.splitlines()) > 150
